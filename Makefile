@@ -1,0 +1,23 @@
+# Builds the in-tree C-ABI library (sm_100a only) and the C oracle helpers.
+NVCC ?= /usr/local/cuda/bin/nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3,-ffp-contract=off -Xptxas -v --fmad=false
+SRC_CU := $(wildcard larvio_b200/csrc/*.cu)
+SRC_CPP := $(wildcard larvio_b200/csrc/*.cpp)
+OBJ := $(SRC_CU:.cu=.o) $(SRC_CPP:.cpp=.o)
+LIB := larvio_b200/lib/liblarvio_b200.so
+
+all: $(LIB)
+
+larvio_b200/csrc/%.o: larvio_b200/csrc/%.cu larvio_b200/csrc/*.h include/larvio_b200.h
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $@.log || (cat $@.log; false)
+
+larvio_b200/csrc/%.o: larvio_b200/csrc/%.cpp include/larvio_b200.h
+	g++ -O2 -std=c++17 -fPIC -ffp-contract=off -c $< -o $@
+
+$(LIB): $(OBJ)
+	mkdir -p larvio_b200/lib
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart
+
+clean:
+	rm -f larvio_b200/csrc/*.o larvio_b200/csrc/*.o.log $(LIB)

@@ -1,0 +1,231 @@
+// Pyramidal iterative Lucas-Kanade with initial flow, one warp per point, all levels in one launch.
+// Replaces the six cv::calcOpticalFlowPyrLK call sites of image_processor.cpp (:368-377, :405-414,
+// :558-567, :618-627, :830-839, :870-879; win 21x21, 3 levels, <=30 iterations, eps 0.01,
+// minEigThreshold 1e-4, OPTFLOW_USE_INITIAL_FLOW) together with the gates that follow each call:
+// predictFeatureTracking (:266-293) as prologue, the in-image test (:571-578) and the
+// forward/backward consistency test (:630-642) as epilogue.  Arithmetic follows SURVEY.md App. A.5:
+// Q14 bilinear weights, int16 patches with 5 fractional bits, float32 normal equations.
+// Scharr derivatives are computed on the fly from the padded level image (zero outside the image,
+// REFLECT_101 at its edge == the pad content), so no derivative pyramid exists in HBM.
+#include "lvb_internal.h"
+
+namespace {
+
+constexpr int WIN = 21;
+constexpr int NPIX = WIN * WIN;            // 441
+constexpr int TILE = WIN + 3;              // 24: window + bilinear +1 + Scharr apron 1 on both sides
+constexpr int DT = WIN + 1;                // 22: derivative grid
+constexpr int WARPS = 4;
+constexpr int W_BITS = 14;
+
+struct WarpSmem {
+  uint8_t tile[TILE * TILE];               // 576
+  short2 dtile[DT * DT];                   // 1936
+  short Iw[NPIX + 7];                      // 896
+  short2 dIw[NPIX];                        // 1764
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+struct LkArgs {
+  const uint8_t* pyrA; const uint8_t* pyrB;
+  LvbPyramidLayout L;
+  int stride;                 // per-sequence stride of point arrays
+  const float2* ptsA;         // [S][stride] source points (indexed through perm if given)
+  const int* perm;            // [S][stride] or null
+  const int* n_pts;           // [S]
+  const float2* init;         // [S][stride] initial flow (ignored when Hmat != null)
+  const float* Hmat;          // [S][9] or null: initial flow = K R K^-1 * ptA
+  float2* out;                // [S][stride] tracked positions (indexed by i, not by perm)
+  uint8_t* status;            // [S][stride]
+  int gate_mode;              // 0 none, 1 in-image, 2 in-image + |out - ref| <= 1
+  const float2* ref;          // [S][stride] reference for gate 2 (indexed by perm like ptsA)
+  int max_iter; double eps2; double min_eig;
+  int max_level;
+};
+
+__global__ void __launch_bounds__(WARPS * 32) lk_kernel(LkArgs a) {
+  __shared__ WarpSmem sm[WARPS];
+  const int s = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * WARPS + warp;
+  if (i >= a.n_pts[s]) return;
+  WarpSmem& w = sm[warp];
+  const int slot = a.perm ? a.perm[(size_t)s * a.stride + i] : i;
+  const float2 pA = a.ptsA[(size_t)s * a.stride + slot];
+  float2 nxt;
+  if (a.Hmat) {
+    const float* H = a.Hmat + (size_t)s * 9;
+    // cv::Matx33f * Vec3f : s = 0; s += H(r,k)*v(k)   (image_processor.cpp:285-290)
+    float q[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      float acc = __fmul_rn(H[r * 3 + 0], pA.x);
+      acc = __fadd_rn(acc, __fmul_rn(H[r * 3 + 1], pA.y));
+      acc = __fadd_rn(acc, H[r * 3 + 2]);
+      q[r] = acc;
+    }
+    nxt.x = __fdiv_rn(q[0], q[2]);
+    nxt.y = __fdiv_rn(q[1], q[2]);
+  } else {
+    nxt = a.init[(size_t)s * a.stride + i];
+  }
+  bool status = true;
+  const float halfWin = (WIN - 1) * 0.5f;
+
+  for (int level = a.max_level; level >= 0; --level) {
+    const LvbLevel lv = a.L.lv[level];
+    const float scale = 1.0f / (float)(1 << level);
+    float2 prevPt = make_float2(__fmul_rn(pA.x, scale), __fmul_rn(pA.y, scale));
+    if (level == a.max_level) nxt = make_float2(__fmul_rn(nxt.x, scale), __fmul_rn(nxt.y, scale));
+    else nxt = make_float2(__fmul_rn(nxt.x, 2.f), __fmul_rn(nxt.y, 2.f));
+    prevPt.x = __fsub_rn(prevPt.x, halfWin);
+    prevPt.y = __fsub_rn(prevPt.y, halfWin);
+    const int ipx = (int)floorf(prevPt.x), ipy = (int)floorf(prevPt.y);
+    if (ipx < -WIN || ipx >= lv.w || ipy < -WIN || ipy >= lv.h) {
+      if (level == 0) status = false;
+      continue;
+    }
+    const uint8_t* orgA = lvb_level_origin(a.pyrA, a.L, s, level);
+    const uint8_t* orgB = lvb_level_origin(a.pyrB, a.L, s, level);
+    __syncwarp();
+    // ---- stage the 24x24 source tile (origin ipx-1, ipy-1)
+    for (int t = lane; t < TILE * TILE; t += 32) {
+      const int ty = t / TILE, tx = t - ty * TILE;
+      w.tile[t] = __ldg(orgA + (ptrdiff_t)(ipy - 1 + ty) * lv.pitch + (ipx - 1 + tx));
+    }
+    __syncwarp();
+    // ---- Scharr derivatives on the 22x22 grid (zero outside the image)
+    for (int t = lane; t < DT * DT; t += 32) {
+      const int dy = t / DT, dx = t - dy * DT;
+      const int gx = ipx + dx, gy = ipy + dy;
+      short2 d = make_short2(0, 0);
+      if (gx >= 0 && gx < lv.w && gy >= 0 && gy < lv.h) {
+        const uint8_t* c = &w.tile[(dy + 1) * TILE + (dx + 1)];
+        const int tl = c[-TILE - 1], tc = c[-TILE], tr = c[-TILE + 1];
+        const int ml = c[-1], mr = c[1];
+        const int bl = c[TILE - 1], bc = c[TILE], br = c[TILE + 1];
+        d.x = (short)(3 * (tr + br - tl - bl) + 10 * (mr - ml));
+        d.y = (short)(3 * (bl + br - tl - tr) + 10 * (bc - tc));
+      }
+      w.dtile[t] = d;
+    }
+    __syncwarp();
+    // ---- window of the previous image
+    float fa = __fsub_rn(prevPt.x, (float)ipx), fb = __fsub_rn(prevPt.y, (float)ipy);
+    int iw00 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, fa), __fsub_rn(1.f, fb)), (float)(1 << W_BITS)));
+    int iw01 = __float2int_rn(__fmul_rn(__fmul_rn(fa, __fsub_rn(1.f, fb)), (float)(1 << W_BITS)));
+    int iw10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, fa), fb), (float)(1 << W_BITS)));
+    int iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+    float A11 = 0.f, A12 = 0.f, A22 = 0.f;
+    for (int p = lane; p < NPIX; p += 32) {
+      const int y = p / WIN, x = p - y * WIN;
+      const uint8_t* c = &w.tile[(y + 1) * TILE + (x + 1)];
+      const int ival = (c[0] * iw00 + c[1] * iw01 + c[TILE] * iw10 + c[TILE + 1] * iw11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+      const short2 d00 = w.dtile[y * DT + x], d01 = w.dtile[y * DT + x + 1];
+      const short2 d10 = w.dtile[(y + 1) * DT + x], d11 = w.dtile[(y + 1) * DT + x + 1];
+      const int ix = (d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
+      const int iy = (d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
+      w.Iw[p] = (short)ival;
+      w.dIw[p] = make_short2((short)ix, (short)iy);
+      A11 = __fadd_rn(A11, (float)(ix * ix));
+      A12 = __fadd_rn(A12, (float)(ix * iy));
+      A22 = __fadd_rn(A22, (float)(iy * iy));
+    }
+    const float FLT_SCALE = 1.f / (float)(1 << 20);
+    A11 = __fmul_rn(warp_sum(A11), FLT_SCALE);
+    A12 = __fmul_rn(warp_sum(A12), FLT_SCALE);
+    A22 = __fmul_rn(warp_sum(A22), FLT_SCALE);
+    float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+    const float dif = __fsub_rn(A11, A22);
+    const float rad = __fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.f, A12), A12));
+    const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(rad)), (float)(2 * WIN * WIN));
+    if ((double)minEig < a.min_eig || D < 1.1920929e-07f) {
+      if (level == 0) status = false;
+      continue;
+    }
+    D = __fdiv_rn(1.f, D);
+    float2 np = make_float2(__fsub_rn(nxt.x, halfWin), __fsub_rn(nxt.y, halfWin));
+    float2 prevDelta = make_float2(0.f, 0.f);
+    __syncwarp();
+    for (int j = 0; j < a.max_iter; ++j) {
+      const int inx = (int)floorf(np.x), iny = (int)floorf(np.y);
+      if (inx < -WIN || inx >= lv.w || iny < -WIN || iny >= lv.h) {
+        if (level == 0) status = false;
+        break;
+      }
+      fa = __fsub_rn(np.x, (float)inx);
+      fb = __fsub_rn(np.y, (float)iny);
+      iw00 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, fa), __fsub_rn(1.f, fb)), (float)(1 << W_BITS)));
+      iw01 = __float2int_rn(__fmul_rn(__fmul_rn(fa, __fsub_rn(1.f, fb)), (float)(1 << W_BITS)));
+      iw10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, fa), fb), (float)(1 << W_BITS)));
+      iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+      float b1 = 0.f, b2 = 0.f;
+      const uint8_t* jbase = orgB + (ptrdiff_t)iny * lv.pitch + inx;
+      for (int p = lane; p < NPIX; p += 32) {
+        const int y = p / WIN, x = p - y * WIN;
+        const uint8_t* c = jbase + (ptrdiff_t)y * lv.pitch + x;
+        const int j00 = __ldg(c), j01 = __ldg(c + 1), j10 = __ldg(c + lv.pitch), j11 = __ldg(c + lv.pitch + 1);
+        const int diff = ((j00 * iw00 + j01 * iw01 + j10 * iw10 + j11 * iw11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5)) - (int)w.Iw[p];
+        const short2 d = w.dIw[p];
+        b1 = __fadd_rn(b1, (float)(diff * d.x));
+        b2 = __fadd_rn(b2, (float)(diff * d.y));
+      }
+      b1 = __fmul_rn(warp_sum(b1), FLT_SCALE);
+      b2 = __fmul_rn(warp_sum(b2), FLT_SCALE);
+      float2 delta;
+      delta.x = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+      delta.y = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+      np.x = __fadd_rn(np.x, delta.x);
+      np.y = __fadd_rn(np.y, delta.y);
+      nxt = make_float2(__fadd_rn(np.x, halfWin), __fadd_rn(np.y, halfWin));
+      const double dd = (double)delta.x * (double)delta.x + (double)delta.y * (double)delta.y;
+      if (dd <= a.eps2) break;
+      if (j > 0 && (double)fabsf(__fadd_rn(delta.x, prevDelta.x)) < 0.01 && (double)fabsf(__fadd_rn(delta.y, prevDelta.y)) < 0.01) {
+        nxt.x = __fsub_rn(nxt.x, __fmul_rn(delta.x, 0.5f));
+        nxt.y = __fsub_rn(nxt.y, __fmul_rn(delta.y, 0.5f));
+        break;
+      }
+      prevDelta = delta;
+    }
+  }
+
+  if (lane == 0) {
+    const LvbLevel l0 = a.L.lv[0];
+    if (status && a.gate_mode >= 1) {
+      if (nxt.y < 0.f || nxt.y > (float)(l0.h - 1) || nxt.x < 0.f || nxt.x > (float)(l0.w - 1)) status = false;
+    }
+    if (status && a.gate_mode == 2) {
+      const float2 r = a.ref[(size_t)s * a.stride + slot];
+      const float dx = __fsub_rn(nxt.x, r.x), dy = __fsub_rn(nxt.y, r.y);
+      const float dis = (float)sqrt((double)dx * (double)dx + (double)dy * (double)dy);
+      if (dis > 1.f) status = false;
+    }
+    a.out[(size_t)s * a.stride + i] = nxt;
+    a.status[(size_t)s * a.stride + i] = status ? 1 : 0;
+  }
+}
+
+}  // namespace
+
+int fe_lk_launch(LvbHandle* h, const uint8_t* pyrA, const uint8_t* pyrB, int n_seq, int stride,
+                 const float2* ptsA, const int* perm, const int* n_pts, const float2* init,
+                 const float* Hmat, float2* out, uint8_t* status, int gate_mode, const float2* ref) {
+  if (h->cfg.patch_size != WIN) return lvb_set_err(LVB_E_UNSUPPORTED, "patch_size %d (kernel is built for 21)", h->cfg.patch_size);
+  LkArgs a;
+  a.pyrA = pyrA; a.pyrB = pyrB; a.L = h->fe.L; a.stride = stride; a.ptsA = ptsA; a.perm = perm;
+  a.n_pts = n_pts; a.init = init; a.Hmat = Hmat; a.out = out; a.status = status;
+  a.gate_mode = gate_mode; a.ref = ref;
+  int mi = h->cfg.max_iteration; if (mi < 0) mi = 0; if (mi > 100) mi = 100;      // cv clamps maxCount to [0,100]
+  double eps = h->cfg.track_precision; if (eps < 0) eps = 0; if (eps > 10) eps = 10;
+  a.max_iter = mi; a.eps2 = eps * eps; a.min_eig = 1e-4;
+  a.max_level = h->cfg.pyramid_levels;
+  dim3 grd((stride + WARPS - 1) / WARPS, n_seq);
+  lk_kernel<<<grd, WARPS * 32, 0, h->stream>>>(a);
+  LVB_LAUNCH_CHECK(h);
+  return LVB_OK;
+}
