@@ -39,6 +39,7 @@ struct LkArgs {
   const int* perm;            // [S][stride] or null
   const int* n_pts;           // [S]
   const float2* init;         // [S][stride] initial flow (ignored when Hmat != null)
+  int init_by_slot;
   const float* Hmat;          // [S][9] or null: initial flow = K R K^-1 * ptA
   float2* out;                // [S][stride] tracked positions (indexed by i, not by perm)
   uint8_t* status;            // [S][stride]
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(WARPS * 32) lk_kernel(LkArgs a) {
     nxt.x = __fdiv_rn(q[0], q[2]);
     nxt.y = __fdiv_rn(q[1], q[2]);
   } else {
-    nxt = a.init[(size_t)s * a.stride + i];
+    nxt = a.init[(size_t)s * a.stride + (a.init_by_slot ? slot : i)];
   }
   bool status = true;
   const float halfWin = (WIN - 1) * 0.5f;
@@ -213,12 +214,12 @@ __global__ void __launch_bounds__(WARPS * 32) lk_kernel(LkArgs a) {
 }  // namespace
 
 int fe_lk_launch(LvbHandle* h, const uint8_t* pyrA, const uint8_t* pyrB, int n_seq, int stride,
-                 const float2* ptsA, const int* perm, const int* n_pts, const float2* init,
+                 const float2* ptsA, const int* perm, const int* n_pts, const float2* init, int init_by_slot,
                  const float* Hmat, float2* out, uint8_t* status, int gate_mode, const float2* ref) {
   if (h->cfg.patch_size != WIN) return lvb_set_err(LVB_E_UNSUPPORTED, "patch_size %d (kernel is built for 21)", h->cfg.patch_size);
   LkArgs a;
   a.pyrA = pyrA; a.pyrB = pyrB; a.L = h->fe.L; a.stride = stride; a.ptsA = ptsA; a.perm = perm;
-  a.n_pts = n_pts; a.init = init; a.Hmat = Hmat; a.out = out; a.status = status;
+  a.n_pts = n_pts; a.init = init; a.init_by_slot = init_by_slot; a.Hmat = Hmat; a.out = out; a.status = status;
   a.gate_mode = gate_mode; a.ref = ref;
   int mi = h->cfg.max_iteration; if (mi < 0) mi = 0; if (mi > 100) mi = 100;      // cv clamps maxCount to [0,100]
   double eps = h->cfg.track_precision; if (eps < 0) eps = 0; if (eps > 10) eps = 10;

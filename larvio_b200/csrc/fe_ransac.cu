@@ -1,0 +1,333 @@
+// Fundamental-matrix RANSAC inlier masks == cv::findFundamentalMat(p1, p2, FM_RANSAC, 1.0, 0.99, mask)
+// at image_processor.cpp:498-500, 755-757, 968-970 (only the mask is consumed there).
+// OpenCV (un-vendored third-party) algorithm restated in oracle/ransac.py and pinned against cv2:
+//   n < 7            -> no mask (the reference then keeps every element, image_processor.h:219-223)
+//   n == 7           -> all ones
+//   8 <= n < 15      -> LMedS registrator (fundam.cpp switches below 15 points): 300 hypotheses,
+//                       least median, sigma-scaled threshold
+//   n >= 15          -> RANSAC: cv::RNG(-1) MWC subsets of 7 (duplicates redrawn, last-point
+//                       collinearity test), 7-point cubic, goodCount > max(best, 6) update rule with
+//                       adaptive iteration count, Sampson-style max line distance^2 <= 1 as float.
+// One CTA per point set.  Thread 0 replays the RNG stream (it does not depend on model quality), the
+// 32 lanes of warp 0 solve 32 minimal problems at once in FP64, all warps score models, thread 0
+// replays the sequential acceptance rule.  The 2-D null space comes from Gauss-Jordan with full
+// pivoting instead of an SVD: the pencil of F matrices and therefore every candidate model is the same.
+#include <float.h>
+#include "lvb_internal.h"
+
+namespace {
+
+constexpr int BATCH = 32;      // hypotheses per round
+constexpr int MAXPTS = 512;
+
+struct RansacArgs {
+  const float2* p1; const float2* p2; const int* n; int stride;
+  uint8_t* mask; const int* enable; int* fail;   // fail[s]=1 -> chain already aborted, skip
+  double threshold, confidence; int max_iters;
+};
+
+struct Rng {
+  unsigned long long state;
+  __device__ unsigned next() {
+    state = (unsigned long long)(unsigned)state * 4164903690ull + (unsigned)(state >> 32);
+    return (unsigned)state;
+  }
+  __device__ int uniform(int a, int b) { return a == b ? a : (int)(next() % (unsigned)(b - a) + a); }
+};
+
+__device__ bool collinear_last(const float2* p, const int* idx, int count) {
+  const int i = count - 1;
+  const float2 pi = p[idx[i]];
+  for (int j = 0; j < i; ++j) {
+    const double dx1 = (double)p[idx[j]].x - (double)pi.x, dy1 = (double)p[idx[j]].y - (double)pi.y;
+    for (int k = 0; k < j; ++k) {
+      const double dx2 = (double)p[idx[k]].x - (double)pi.x, dy2 = (double)p[idx[k]].y - (double)pi.y;
+      if (fabs(dx2 * dy1 - dy2 * dx1) <= (double)FLT_EPSILON * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2))) return true;
+    }
+  }
+  return false;
+}
+
+__device__ int solve_cubic(const double* c, double* x) {
+  double a0 = c[0], a1 = c[1], a2 = c[2], a3 = c[3];
+  if (a0 == 0) {
+    if (a1 == 0) {
+      if (a2 == 0) return 0;
+      x[0] = -a3 / a2; return 1;
+    }
+    double d = a2 * a2 - 4 * a1 * a3;
+    if (d >= 0) {
+      d = sqrt(d);
+      const double q1 = (-a2 + d) * 0.5, q2 = (a2 + d) * -0.5;
+      if (fabs(q1) > fabs(q2)) { x[0] = q1 / a1; x[1] = a3 / q1; }
+      else { x[0] = q2 / a1; x[1] = a3 / q2; }
+      return d > 0 ? 2 : 1;
+    }
+    return 0;
+  }
+  a0 = 1. / a0; a1 *= a0; a2 *= a0; a3 *= a0;
+  const double Q = (a1 * a1 - 3 * a2) * (1. / 9);
+  const double R = (2 * a1 * a1 * a1 - 9 * a1 * a2 + 27 * a3) * (1. / 54);
+  const double Qc = Q * Q * Q;
+  double d = Qc - R * R;
+  if (d > 0) {
+    const double theta = acos(R / sqrt(Qc)), sq = sqrt(Q);
+    const double t0 = -2 * sq, t1 = theta * (1. / 3), t2 = a1 * (1. / 3);
+    x[0] = t0 * cos(t1) - t2;
+    x[1] = t0 * cos(t1 + (2. * 3.14159265358979323846 / 3)) - t2;
+    x[2] = t0 * cos(t1 + (4. * 3.14159265358979323846 / 3)) - t2;
+    return 3;
+  }
+  if (d == 0) {
+    if (R >= 0) { x[0] = -2 * pow(R, 1. / 3) - a1 / 3; x[1] = pow(R, 1. / 3) - a1 / 3; }
+    else { x[0] = 2 * pow(-R, 1. / 3) - a1 / 3; x[1] = -pow(-R, 1. / 3) - a1 / 3; }
+    return x[0] == x[1] ? 1 : 2;
+  }
+  d = sqrt(-d);
+  double e = pow(d + fabs(R), 1. / 3);
+  if (R > 0) e = -e;
+  x[0] = (e + Q / e) - a1 * (1. / 3);
+  return 1;
+}
+
+// 7-point solver of one lane. A lives in shared memory, element-major: A[e*32 + lane].
+__device__ int seven_point(double* A, const float2* p1, const float2* p2, const int* idx, double* F /*[3][9]*/) {
+#define AA(r, c) A[((r) * 9 + (c)) * 32]
+  for (int i = 0; i < 7; ++i) {
+    const double x0 = p1[idx[i]].x, y0 = p1[idx[i]].y, x1 = p2[idx[i]].x, y1 = p2[idx[i]].y;
+    AA(i, 0) = x1 * x0; AA(i, 1) = x1 * y0; AA(i, 2) = x1;
+    AA(i, 3) = y1 * x0; AA(i, 4) = y1 * y0; AA(i, 5) = y1;
+    AA(i, 6) = x0; AA(i, 7) = y0; AA(i, 8) = 1.0;
+  }
+  int perm[9];
+  for (int c = 0; c < 9; ++c) perm[c] = c;
+  for (int k = 0; k < 7; ++k) {
+    // full pivot search in rows k.., columns k..
+    int pr = k, pc = k; double best = -1;
+    for (int r = k; r < 7; ++r)
+      for (int c = k; c < 9; ++c) { const double v = fabs(AA(r, perm[c])); if (v > best) { best = v; pr = r; pc = c; } }
+    if (pr != k) for (int c = 0; c < 9; ++c) { const double t = AA(k, c); AA(k, c) = AA(pr, c); AA(pr, c) = t; }
+    { const int t = perm[k]; perm[k] = perm[pc]; perm[pc] = t; }
+    const double piv = AA(k, perm[k]);
+    const double ip = 1.0 / piv;
+    for (int c = 0; c < 9; ++c) AA(k, c) *= ip;
+    for (int r = 0; r < 7; ++r) {
+      if (r == k) continue;
+      const double f = AA(r, perm[k]);
+      if (f != 0) for (int c = 0; c < 9; ++c) AA(r, c) -= f * AA(k, c);
+    }
+  }
+  double n1[9], n2[9];
+  for (int c = 0; c < 9; ++c) { n1[c] = 0; n2[c] = 0; }
+  n1[perm[7]] = 1.0; n2[perm[8]] = 1.0;
+  for (int k = 0; k < 7; ++k) { n1[perm[k]] = -AA(k, perm[7]); n2[perm[k]] = -AA(k, perm[8]); }
+#undef AA
+  // normalise like singular vectors (unit length) for conditioning of the cubic
+  double s1 = 0, s2 = 0;
+  for (int c = 0; c < 9; ++c) { s1 += n1[c] * n1[c]; s2 += n2[c] * n2[c]; }
+  s1 = 1.0 / sqrt(s1); s2 = 1.0 / sqrt(s2);
+  double f1[9], f2[9];
+  for (int c = 0; c < 9; ++c) { f2[c] = n2[c] * s2; f1[c] = n1[c] * s1 - f2[c]; }
+  double c4[4], r[3] = {0, 0, 0};
+  double t0 = f2[4] * f2[8] - f2[5] * f2[7], t1 = f2[3] * f2[8] - f2[5] * f2[6], t2 = f2[3] * f2[7] - f2[4] * f2[6];
+  c4[3] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2;
+  c4[2] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2 - f1[3] * (f2[1] * f2[8] - f2[2] * f2[7]) +
+          f1[4] * (f2[0] * f2[8] - f2[2] * f2[6]) - f1[5] * (f2[0] * f2[7] - f2[1] * f2[6]) +
+          f1[6] * (f2[1] * f2[5] - f2[2] * f2[4]) - f1[7] * (f2[0] * f2[5] - f2[2] * f2[3]) +
+          f1[8] * (f2[0] * f2[4] - f2[1] * f2[3]);
+  t0 = f1[4] * f1[8] - f1[5] * f1[7]; t1 = f1[3] * f1[8] - f1[5] * f1[6]; t2 = f1[3] * f1[7] - f1[4] * f1[6];
+  c4[0] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2;
+  c4[1] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2 - f2[3] * (f1[1] * f1[8] - f1[2] * f1[7]) +
+          f2[4] * (f1[0] * f1[8] - f1[2] * f1[6]) - f2[5] * (f1[0] * f1[7] - f1[1] * f1[6]) +
+          f2[6] * (f1[1] * f1[5] - f1[2] * f1[4]) - f2[7] * (f1[0] * f1[5] - f1[2] * f1[3]) +
+          f2[8] * (f1[0] * f1[4] - f1[1] * f1[3]);
+  const int n = solve_cubic(c4, r);
+  if (n < 1 || n > 3) return 0;
+  for (int k = 0; k < n; ++k) {
+    double lambda = r[k], mu = 1.;
+    const double s = f1[8] * r[k] + f2[8];
+    double* Fk = F + k * 9;
+    if (fabs(s) > DBL_EPSILON) { mu = 1. / s; lambda *= mu; Fk[8] = 1.; }
+    else Fk[8] = 0.;
+    for (int i = 0; i < 8; ++i) Fk[i] = f1[i] * lambda + f2[i] * mu;
+  }
+  return n;
+}
+
+__device__ __forceinline__ float sampson_err(const double* F, float2 a, float2 b) {
+  const double x1 = a.x, y1 = a.y, x2 = b.x, y2 = b.y;
+  double A = F[0] * x1 + F[1] * y1 + F[2], B = F[3] * x1 + F[4] * y1 + F[5], C = F[6] * x1 + F[7] * y1 + F[8];
+  const double s2 = 1. / (A * A + B * B), d2 = x2 * A + y2 * B + C;
+  A = F[0] * x2 + F[3] * y2 + F[6]; B = F[1] * x2 + F[4] * y2 + F[7]; C = F[2] * x2 + F[5] * y2 + F[8];
+  const double s1 = 1. / (A * A + B * B), d1 = x1 * A + y1 * B + C;
+  return (float)fmax(d1 * d1 * s1, d2 * d2 * s2);
+}
+
+__device__ int update_num_iters(double p, double ep, int model_points, int max_iters) {
+  p = fmin(fmax(p, 0.), 1.); ep = fmin(fmax(ep, 0.), 1.);
+  double num = fmax(1. - p, DBL_MIN);
+  double denom = 1. - pow(1. - ep, (double)model_points);
+  if (denom < DBL_MIN) return 0;
+  num = log(num); denom = log(denom);
+  return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : (int)rint(num / denom);
+}
+
+__global__ void __launch_bounds__(256) ransac_kernel(RansacArgs a) {
+  __shared__ float2 sp1[MAXPTS], sp2[MAXPTS];
+  __shared__ double sA[63 * 32];
+  __shared__ double sF[BATCH][3][9];
+  __shared__ int s_nmodels[BATCH];
+  __shared__ int s_idx[BATCH][7];
+  __shared__ int s_valid[BATCH];       // subset found
+  __shared__ int s_good[BATCH][3];
+  __shared__ float s_med[BATCH][3];
+  __shared__ float s_err[8][16];       // LMedS scratch (n < 15), one row per warp
+  __shared__ int s_ctl[8];             // 0 done, 1 iter, 2 niters, 3 max_good, 4 best hyp, 5 best model, 6 have_best, 7 abort
+  __shared__ double s_minmed;
+  __shared__ unsigned long long s_rng;
+  const int s = blockIdx.x;
+  if (a.enable && !a.enable[s]) return;
+  if (a.fail && a.fail[s]) return;
+  const int n = min(a.n[s], MAXPTS);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* mask = a.mask + (size_t)s * a.stride;
+  if (n < 7) { for (int i = tid; i < n; i += 256) mask[i] = 1; return; }   // "no mask" => keep all
+  for (int i = tid; i < n; i += 256) { sp1[i] = a.p1[(size_t)s * a.stride + i]; sp2[i] = a.p2[(size_t)s * a.stride + i]; }
+  __syncthreads();
+  if (n == 7) { for (int i = tid; i < n; i += 256) mask[i] = 1; return; }
+  const bool lmeds = n < 15;
+  if (tid == 0) {
+    s_ctl[0] = 0; s_ctl[1] = 0; s_ctl[3] = 0; s_ctl[6] = 0; s_ctl[7] = 0;
+    int niters = max(a.max_iters, 1);
+    if (lmeds) { niters = update_num_iters(a.confidence, 0.45, 7, a.max_iters); niters = max(niters, 3); }
+    s_ctl[2] = niters;
+    s_minmed = DBL_MAX;
+    s_rng = 0xffffffffffffffffull;
+  }
+  __syncthreads();
+  const float thr2 = (float)(a.threshold * a.threshold);
+  double bestF[9];
+  for (int q = 0; q < 9; ++q) bestF[q] = 0;
+
+  while (true) {
+    // ---- thread 0: next BATCH subsets from the RNG stream
+    if (tid == 0) {
+      Rng rng; rng.state = s_rng;
+      const int max_attempts = lmeds ? 1000 : 10000;
+      for (int hb = 0; hb < BATCH; ++hb) {
+        bool found = false;
+        int idx[7];
+        for (int at = 0; at < max_attempts && !found; ++at) {
+          for (int i = 0; i < 7; ++i) {
+            int v;
+            bool dup;
+            do {
+              v = rng.uniform(0, n);
+              dup = false;
+              for (int j = 0; j < i; ++j) dup |= (idx[j] == v);
+            } while (dup);
+            idx[i] = v;
+          }
+          found = !collinear_last(sp1, idx, 7) && !collinear_last(sp2, idx, 7);
+        }
+        s_valid[hb] = found;
+        for (int i = 0; i < 7; ++i) s_idx[hb][i] = idx[i];
+        if (!found) { for (int h2 = hb + 1; h2 < BATCH; ++h2) s_valid[h2] = 0; break; }
+      }
+      s_rng = rng.state;
+    }
+    __syncthreads();
+    // ---- warp 0: solve the 32 minimal problems
+    if (warp == 0) {
+      int nm = 0;
+      if (s_valid[lane]) nm = seven_point(&sA[lane], sp1, sp2, s_idx[lane], &sF[lane][0][0]);
+      s_nmodels[lane] = nm;
+    }
+    __syncthreads();
+    // ---- all warps: score every (hypothesis, model)
+    for (int hm = warp; hm < BATCH * 3; hm += 8) {
+      const int hb = hm / 3, m = hm - hb * 3;
+      if (m >= s_nmodels[hb]) { if (lane == 0) { s_good[hb][m] = -1; s_med[hb][m] = 0.f; } continue; }
+      const double* F = &sF[hb][m][0];
+      if (!lmeds) {
+        int good = 0;
+        for (int i = lane; i < n; i += 32) good += (sampson_err(F, sp1[i], sp2[i]) <= thr2);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) good += __shfl_xor_sync(0xffffffffu, good, o);
+        if (lane == 0) s_good[hb][m] = good;
+      } else {
+        if (lane < n) s_err[warp][lane] = sampson_err(F, sp1[lane], sp2[lane]);
+        __syncwarp();
+        if (lane == 0) {
+          // element of rank n/2 (std::nth_element on the raw bits; errors are >= 0)
+          float e[16];
+          for (int i = 0; i < n; ++i) e[i] = s_err[warp][i];
+          for (int i = 1; i < n; ++i) { float v = e[i]; int j = i - 1; while (j >= 0 && e[j] > v) { e[j + 1] = e[j]; --j; } e[j + 1] = v; }
+          s_med[hb][m] = e[n / 2];
+          s_good[hb][m] = 0;
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // ---- thread 0: replay the sequential acceptance rule
+    if (tid == 0) {
+      int iter = s_ctl[1], niters = s_ctl[2], max_good = s_ctl[3];
+      int hb = 0;
+      for (; hb < BATCH && iter < niters; ++hb) {
+        if (!s_valid[hb]) { if (iter == 0) s_ctl[7] = 1; s_ctl[0] = 1; break; }
+        for (int m = 0; m < s_nmodels[hb]; ++m) {
+          if (!lmeds) {
+            const int good = s_good[hb][m];
+            if (good > max(max_good, 6)) {
+              max_good = good; s_ctl[4] = hb; s_ctl[5] = m; s_ctl[6] = 1;
+              niters = update_num_iters(a.confidence, (double)(n - good) / n, 7, niters);
+            }
+          } else {
+            const double med = (double)s_med[hb][m];
+            if (med < s_minmed) { s_minmed = med; s_ctl[4] = hb; s_ctl[5] = m; s_ctl[6] = 1; }
+          }
+        }
+        ++iter;
+      }
+      s_ctl[1] = iter; s_ctl[2] = niters; s_ctl[3] = max_good;
+      if (iter >= niters) s_ctl[0] = 1;
+      // remember whether the best model lives in THIS batch
+    }
+    __syncthreads();
+    // every thread keeps a private copy of the best model when it was (re)assigned in this batch
+    if (s_ctl[6] == 1) {
+      const double* F = &sF[s_ctl[4]][s_ctl[5]][0];
+      for (int q = 0; q < 9; ++q) bestF[q] = F[q];
+    }
+    __syncthreads();
+    if (tid == 0 && s_ctl[6] == 1) s_ctl[6] = 2;   // 2 = have a best model from an earlier batch
+    __syncthreads();
+    if (s_ctl[0]) break;
+  }
+  // ---- final mask
+  if (s_ctl[6] == 0) {
+    // no model at all: cv leaves the mask unspecified; we report all-zero
+    for (int i = tid; i < n; i += 256) mask[i] = 0;
+    return;
+  }
+  float t = thr2;
+  if (lmeds) {
+    double sigma = 2.5 * 1.4826 * (1 + 5. / (n - 7)) * sqrt(s_minmed);
+    sigma = fmax(sigma, 0.001);
+    t = (float)(sigma * sigma);
+  }
+  for (int i = tid; i < n; i += 256) mask[i] = sampson_err(bestF, sp1[i], sp2[i]) <= t ? 1 : 0;
+}
+
+}  // namespace
+
+int fe_ransac_launch(LvbHandle* h, int n_seq, int stride, const float2* p1, const float2* p2, const int* n,
+                     uint8_t* mask, const int* enable, int* fail) {
+  RansacArgs a;
+  a.p1 = p1; a.p2 = p2; a.n = n; a.stride = stride; a.mask = mask; a.enable = enable; a.fail = fail;
+  a.threshold = 1.0; a.confidence = 0.99; a.max_iters = 1000;
+  ransac_kernel<<<n_seq, 256, 0, h->stream>>>(a);
+  LVB_LAUNCH_CHECK(h);
+  return LVB_OK;
+}

@@ -203,10 +203,114 @@ extern "C" int lvbk_lk(LvbHandle* h, const uint8_t* prev, const uint8_t* next, i
   if (rc != LVB_OK) return rc;
   LVB_CUDA(cudaMemcpyAsync(d_p, prev_pts, (size_t)n * m * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
   LVB_CUDA(cudaMemcpyAsync(d_q, next_pts, (size_t)n * m * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
-  rc = fe_lk_launch(h, d_pa, d_pb, n, m, d_p, nullptr, d_n, d_q, nullptr, d_o, d_st, 0, nullptr);
+  rc = fe_lk_launch(h, d_pa, d_pb, n, m, d_p, nullptr, d_n, d_q, 0, nullptr, d_o, d_st, 0, nullptr);
   if (rc != LVB_OK) return rc;
   LVB_CUDA(cudaMemcpyAsync(next_pts, d_o, (size_t)n * m * sizeof(float2), cudaMemcpyDeviceToHost, h->stream));
   LVB_CUDA(cudaMemcpyAsync(status, d_st, (size_t)n * m, cudaMemcpyDeviceToHost, h->stream));
+  LVB_CUDA(cudaStreamSynchronize(h->stream));
+  return LVB_OK;
+}
+
+extern "C" int lvbk_orb(LvbHandle* h, const uint8_t* images, int n, int m, const float* pts, float* angles,
+                        uint8_t* desc) {
+  if (!h || !images || !pts || n <= 0 || m <= 0) return lvb_set_err(LVB_E_ARG, "lvbk_orb: bad argument");
+  LVB_CUDA(cudaSetDevice(h->device));
+  LvbFrontEnd& fe = h->fe;
+  TmpBuf tb;
+  const size_t npx = (size_t)fe.W * fe.H;
+  uint8_t* d_img = tb.get<uint8_t>(npx * n);
+  uint8_t* d_pyr = tb.get<uint8_t>(fe.L.bytes_per_seq * n);
+  uint8_t* d_blur = tb.get<uint8_t>(npx * n);
+  uint8_t* d_lut = tb.get<uint8_t>((size_t)n * 64 * 256);
+  float2* d_p = tb.get<float2>((size_t)n * m);
+  float* d_a = tb.get<float>((size_t)n * m);
+  uint8_t* d_d = tb.get<uint8_t>((size_t)n * m * 32);
+  int* d_n = tb.get<int>(n);
+  if (!d_img || !d_pyr || !d_blur || !d_lut || !d_p || !d_a || !d_d || !d_n) return lvb_set_err(LVB_E_CUDA, "lvbk_orb: cudaMalloc failed");
+  std::vector<int> cnt(n, m);
+  LVB_CUDA(cudaMemcpyAsync(d_n, cnt.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  LVB_CUDA(cudaMemcpyAsync(d_img, images, npx * n, cudaMemcpyHostToDevice, h->stream));
+  LVB_CUDA(cudaMemcpyAsync(d_p, pts, (size_t)n * m * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  uint8_t* saved = fe.lut; fe.lut = d_lut;
+  const int eq = h->cfg.flag_equalize; h->cfg.flag_equalize = 0;
+  int rc = fe_build_pyramid(h, d_img, n, d_pyr, d_blur);
+  h->cfg.flag_equalize = eq; fe.lut = saved;
+  if (rc != LVB_OK) return rc;
+  rc = fe_orb_launch(h, d_pyr, d_blur, n, m, d_p, nullptr, d_n, d_a, d_d, 0, nullptr, nullptr, nullptr);
+  if (rc != LVB_OK) return rc;
+  if (angles) LVB_CUDA(cudaMemcpyAsync(angles, d_a, (size_t)n * m * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (desc) LVB_CUDA(cudaMemcpyAsync(desc, d_d, (size_t)n * m * 32, cudaMemcpyDeviceToHost, h->stream));
+  LVB_CUDA(cudaStreamSynchronize(h->stream));
+  return LVB_OK;
+}
+
+extern "C" int lvbk_detect(LvbHandle* h, const uint8_t* images, const uint8_t* masks, int n, const int* want,
+                           float* out_pts, int* out_n, float* eig_map) {
+  if (!h || !images || !want || !out_pts || !out_n || n <= 0) return lvb_set_err(LVB_E_ARG, "lvbk_detect: bad argument");
+  if (n > h->S) return lvb_set_err(LVB_E_ARG, "lvbk_detect: n (%d) exceeds the handle's sequence count (%d)", n, h->S);
+  LVB_CUDA(cudaSetDevice(h->device));
+  LvbFrontEnd& fe = h->fe;
+  TmpBuf tb;
+  const size_t npx = (size_t)fe.W * fe.H;
+  uint8_t* d_img = tb.get<uint8_t>(npx * n);
+  uint8_t* d_pyr = tb.get<uint8_t>(fe.L.bytes_per_seq * n);
+  uint8_t* d_lut = tb.get<uint8_t>((size_t)n * 64 * 256);
+  uint8_t* d_mask = masks ? tb.get<uint8_t>(npx * n) : nullptr;
+  int* d_want = tb.get<int>(n);
+  float2* d_out = tb.get<float2>((size_t)n * fe.N);
+  int* d_cnt = tb.get<int>(n);
+  if (!d_img || !d_pyr || !d_lut || !d_want || !d_out || !d_cnt || (masks && !d_mask)) return lvb_set_err(LVB_E_CUDA, "lvbk_detect: cudaMalloc failed");
+  LVB_CUDA(cudaMemcpyAsync(d_img, images, npx * n, cudaMemcpyHostToDevice, h->stream));
+  if (masks) LVB_CUDA(cudaMemcpyAsync(d_mask, masks, npx * n, cudaMemcpyHostToDevice, h->stream));
+  LVB_CUDA(cudaMemcpyAsync(d_want, want, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  uint8_t* saved = fe.lut; fe.lut = d_lut;
+  const int eq = h->cfg.flag_equalize; h->cfg.flag_equalize = 0;
+  int rc = fe_build_pyramid(h, d_img, n, d_pyr, nullptr);
+  h->cfg.flag_equalize = eq; fe.lut = saved;
+  if (rc != LVB_OK) return rc;
+  rc = fe_detect_launch(h, d_pyr, n, nullptr, 0, d_mask, nullptr, nullptr, d_want, d_out, d_cnt);
+  if (rc != LVB_OK) return rc;
+  LVB_CUDA(cudaMemcpyAsync(out_pts, d_out, (size_t)n * fe.N * sizeof(float2), cudaMemcpyDeviceToHost, h->stream));
+  LVB_CUDA(cudaMemcpyAsync(out_n, d_cnt, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (eig_map) LVB_CUDA(cudaMemcpyAsync(eig_map, fe.eig, npx * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  int ovf = 0;
+  LVB_CUDA(cudaMemcpyAsync(&ovf, fe.overflow, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  LVB_CUDA(cudaStreamSynchronize(h->stream));
+  if (ovf) return lvb_set_err(LVB_E_CAPACITY, "corner candidate buffer overflow");
+  return LVB_OK;
+}
+
+extern "C" int lvbk_undistort(LvbHandle* h, const float* pts, int m, int to_pixels, float* out) {
+  if (!h || !pts || !out || m <= 0) return lvb_set_err(LVB_E_ARG, "lvbk_undistort: bad argument");
+  LVB_CUDA(cudaSetDevice(h->device));
+  TmpBuf tb;
+  float2* d_p = tb.get<float2>(m); float2* d_o = tb.get<float2>(m); int* d_n = tb.get<int>(1);
+  if (!d_p || !d_o || !d_n) return lvb_set_err(LVB_E_CUDA, "lvbk_undistort: cudaMalloc failed");
+  LVB_CUDA(cudaMemcpyAsync(d_p, pts, sizeof(float2) * m, cudaMemcpyHostToDevice, h->stream));
+  LVB_CUDA(cudaMemcpyAsync(d_n, &m, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  int rc = fe_undistort_launch(h, 1, m, d_p, nullptr, d_n, d_o, to_pixels);
+  if (rc != LVB_OK) return rc;
+  LVB_CUDA(cudaMemcpyAsync(out, d_o, sizeof(float2) * m, cudaMemcpyDeviceToHost, h->stream));
+  LVB_CUDA(cudaStreamSynchronize(h->stream));
+  return LVB_OK;
+}
+
+extern "C" int lvbk_ransac(LvbHandle* h, const float* p1, const float* p2, int n, const int* m, int stride,
+                           uint8_t* mask) {
+  if (!h || !p1 || !p2 || !m || !mask || n <= 0 || stride <= 0) return lvb_set_err(LVB_E_ARG, "lvbk_ransac: bad argument");
+  LVB_CUDA(cudaSetDevice(h->device));
+  TmpBuf tb;
+  const size_t tot = (size_t)n * stride;
+  float2* d1 = tb.get<float2>(tot); float2* d2 = tb.get<float2>(tot); int* dn = tb.get<int>(n);
+  uint8_t* dm = tb.get<uint8_t>(tot);
+  if (!d1 || !d2 || !dn || !dm) return lvb_set_err(LVB_E_CUDA, "lvbk_ransac: cudaMalloc failed");
+  LVB_CUDA(cudaMemcpyAsync(d1, p1, tot * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  LVB_CUDA(cudaMemcpyAsync(d2, p2, tot * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  LVB_CUDA(cudaMemcpyAsync(dn, m, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  LVB_CUDA(cudaMemsetAsync(dm, 0, tot, h->stream));
+  int rc = fe_ransac_launch(h, n, stride, d1, d2, dn, dm, nullptr, nullptr);
+  if (rc != LVB_OK) return rc;
+  LVB_CUDA(cudaMemcpyAsync(mask, dm, tot, cudaMemcpyDeviceToHost, h->stream));
   LVB_CUDA(cudaStreamSynchronize(h->stream));
   return LVB_OK;
 }

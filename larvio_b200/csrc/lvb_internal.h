@@ -41,6 +41,24 @@ struct LvbCamera {
 };
 
 // ---- front-end state (image_processor.h:260-325), one slot set per sequence ----
+struct LvbTracks {                 // prev_pts_, curr_pts_, pts_ids_, pts_lifetime_, init_pts_, vOrbDescriptors
+  float2* prev; float2* curr; float2* init;   // [S][N]
+  unsigned long long* ids; int* lifetime;     // [S][N]
+  uint8_t* desc;                               // [S][N][32]
+  int* n;                                      // [S]
+};
+
+struct LvbChain {                  // scratch of one LK<->LK<->ORB<->RANSAC chain (0 tracked, 1 new)
+  int* perm;        // [S][N] alive slot indices, order preserving
+  int* n;           // [S] alive count
+  int* fail;        // [S] chain aborted / not started
+  float2* out;      // [S][N] per-stage LK output, indexed by rank i
+  uint8_t* status;  // [S][N] per-stage marker, indexed by rank i
+  float2* slot_curr;  // [S][N] tracked position in the current image, indexed by slot
+  float2* uprev; float2* ucurr;   // [S][N] undistorted (pixel) coordinates, indexed by rank i
+  uint8_t* desc;    // [S][N][32] descriptors computed in the previous image (chain 1), by slot
+};
+
 struct LvbFrontEnd {
   int S, W, H, N;                 // sequences, image size, per-sequence track capacity
   LvbPyramidLayout L;
@@ -48,12 +66,10 @@ struct LvbFrontEnd {
   uint8_t* lut;                   // [S][64][256] CLAHE LUTs
   uint8_t* pyr[2];                // ping-pong padded pyramids (prev/curr)
   uint8_t* blur[2];               // ping-pong 7x7-blurred L0 planes [S][H][W]
-  int cur;                        // index of the CURRENT pyramid (host-side toggle)
-  // persistent tracks
-  float2* prev_pts; float2* curr_pts; float2* init_pts;       // [S][N]
-  unsigned long long* ids; int* lifetime; uint8_t* desc;      // [S][N], [S][N], [S][N][32]
-  int* n_tracks;                                              // [S]
-  float2* new_pts; int* n_new;                                // [S][N], [S]
+  int cur;                        // index of the CURRENT pyramid / track set (host-side toggle)
+  LvbTracks trk[2];
+  float2* new_pts; int* n_new;    // [S][N], [S]
+  LvbChain ch[2];
   // per-sequence scalars (device)
   int* image_state;               // 1 FIRST, 2 SECOND, 3 OTHER
   unsigned long long* next_id;
@@ -62,23 +78,17 @@ struct LvbFrontEnd {
   float* Hmat;                    // [S][9] K R K^-1 (float, row-major)
   int* active;                    // [S] bFirstImg gate result for this frame
   double* t_img;                  // [S]
-  // per-frame control flags produced by fe_frame_begin
-  int* do_first; int* do_second; int* do_other; int* do_publish;
-  // chain scratch (two chains: 0 = tracked, 1 = new)
-  float2* ch_prev[2]; float2* ch_curr[2]; float2* ch_back[2];  // [S][N]
-  float2* ch_uprev[2]; float2* ch_ucurr[2];
-  uint8_t* ch_status[2];          // [S][N]
-  int* ch_perm[2];                // [S][N] alive slot indices (order preserving)
-  int* ch_n[2];                   // [S] alive count
-  int* ch_fail[2];                // [S] chain aborted flag
-  uint8_t* ch_desc[2];            // [S][N][32] descriptors computed this frame (prev for new chain)
+  // per-frame control flags
+  int* do_first; int* do_second; int* do_other; int* do_publish; int* do_detect;
+  int* want; int* mask_n;
   // detector scratch
   float* eig;                     // [S][H][W]
   uint8_t* mask;                  // [S][H][W]
-  float* eig_max;                 // [S]
-  unsigned long long* cand;       // [S][cand_cap] packed (value bits<<32 | ~index)
+  int* eig_max;                   // [S] ordered-int key of the masked max
+  unsigned long long* cand;       // [S][cand_cap] packed (value bits<<32 | pixel index)
   int* n_cand; int cand_cap;
-  int* want;                      // [S]
+  int* overflow;                  // [1] sticky capacity-overflow flag
+  float2* det_pts; int* det_n;    // [S][N], [S]
   // outputs
   LvbFeature* msg;                // [S][N]
   int* msg_n;                     // [S]
@@ -126,7 +136,21 @@ int lvb_set_err(int code, const char* fmt, ...);
   } while (0)
 
 // ---- stage launchers (each file owns its kernels) ----
+LvbCamera lvb_camera(const LvbConfig& c);
 int fe_build_pyramid(LvbHandle* h, const uint8_t* d_images /*[n][H][W]*/, int n, uint8_t* pyr, uint8_t* blur);
 int fe_lk_launch(LvbHandle* h, const uint8_t* pyrA, const uint8_t* pyrB, int n_seq, int stride,
-                 const float2* ptsA, const int* perm, const int* n_pts, const float2* init,
+                 const float2* ptsA, const int* perm, const int* n_pts, const float2* init, int init_by_slot,
                  const float* Hmat, float2* out, uint8_t* status, int gate_mode, const float2* ref);
+int fe_orb_launch(LvbHandle* h, const uint8_t* pyr, const uint8_t* blur, int n_seq, int stride,
+                  const float2* pts, const int* perm, const int* n_pts, float* angles, uint8_t* desc_out,
+                  int out_by_slot, const uint8_t* desc_ref, uint8_t* status, int* dist_out);
+int fe_undistort_launch(LvbHandle* h, int n_seq, int stride, const float2* pts, const int* perm,
+                        const int* n_pts, float2* out, int to_pixels);
+int fe_detect_launch(LvbHandle* h, const uint8_t* pyr, int n_seq, const int* enable, int use_mask,
+                     const uint8_t* ext_mask, const float2* mask_pts, const int* mask_n, const int* want,
+                     float2* out, int* out_n);
+int fe_ransac_launch(LvbHandle* h, int n_seq, int stride, const float2* p1, const float2* p2, const int* n,
+                     uint8_t* mask, const int* enable, int* fail);
+int fe_process(LvbHandle* h, const uint8_t* images, int on_device, const double* t_img, const LvbImu* imu,
+               const int* n_imu, int imu_stride);
+int fe_fetch_messages(LvbHandle* h, LvbFeature* out_feat, int* out_n, uint8_t* has_features);

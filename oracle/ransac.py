@@ -1,0 +1,177 @@
+"""Restatement of cv::findFundamentalMat(FM_RANSAC, 1.0, 0.99) (OpenCV 4.x calib3d:
+ptsetreg.cpp RANSACPointSetRegistrator::run/getSubset, fundam.cpp FMEstimatorCallback) —
+TEST INFRASTRUCTURE.  OpenCV is not vendored under /root/reference; this file
+restates its published algorithm and is pinned against cv2 4.13 by tests/test_oracle_ransac.py
+(inlier masks identical on randomized inputs).  The CUDA kernel follows this restatement.
+Call sites in the reference: image_processor.cpp:498-500, 755-757, 968-970.
+"""
+import numpy as np
+
+RNG_COEFF = 4164903690
+
+
+class CvRNG:
+    def __init__(self, state=0xFFFFFFFFFFFFFFFF):
+        self.state = state & 0xFFFFFFFFFFFFFFFF
+
+    def next(self):
+        self.state = ((self.state & 0xFFFFFFFF) * RNG_COEFF + (self.state >> 32)) & 0xFFFFFFFFFFFFFFFF
+        return self.state & 0xFFFFFFFF
+
+    def uniform(self, a, b):
+        return a if a == b else int(self.next() % (b - a) + a)
+
+
+def _collinear(pts, count):
+    """haveCollinearPoints(): only the last point is tested against all earlier pairs."""
+    i = count - 1
+    for j in range(i):
+        dx1 = float(pts[j][0]) - float(pts[i][0]); dy1 = float(pts[j][1]) - float(pts[i][1])
+        for k in range(j):
+            dx2 = float(pts[k][0]) - float(pts[i][0]); dy2 = float(pts[k][1]) - float(pts[i][1])
+            if abs(dx2 * dy1 - dy2 * dx1) <= 1.1920929e-07 * (abs(dx1) + abs(dy1) + abs(dx2) + abs(dy2)):
+                return True
+    return False
+
+
+def get_subset(m1, m2, rng, max_attempts=10000, model_points=7):
+    count = len(m1)
+    for _ in range(max_attempts):
+        idx = []
+        for i in range(model_points):
+            v = rng.uniform(0, count)
+            while v in idx:
+                v = rng.uniform(0, count)
+            idx.append(v)
+        if not _collinear(m1[idx], model_points) and not _collinear(m2[idx], model_points):
+            return idx
+    return None
+
+
+def solve_cubic(c):
+    a0, a1, a2, a3 = (float(x) for x in c)
+    if a0 == 0:
+        if a1 == 0:
+            if a2 == 0:
+                return []
+            return [-a3 / a2]
+        d = a2 * a2 - 4 * a1 * a3
+        if d >= 0:
+            d = np.sqrt(d)
+            q1 = (-a2 + d) * 0.5; q2 = (a2 + d) * -0.5
+            if abs(q1) > abs(q2):
+                x0 = q1 / a1; x1 = a3 / q1
+            else:
+                x0 = q2 / a1; x1 = a3 / q2
+            return [x0, x1] if d > 0 else [x0]
+        return []
+    a0 = 1. / a0; a1 *= a0; a2 *= a0; a3 *= a0
+    Q = (a1 * a1 - 3 * a2) * (1. / 9)
+    R = (2 * a1 * a1 * a1 - 9 * a1 * a2 + 27 * a3) * (1. / 54)
+    Qc = Q * Q * Q
+    d = Qc - R * R
+    if d > 0:
+        theta = np.arccos(R / np.sqrt(Qc)); sq = np.sqrt(Q)
+        t0 = -2 * sq; t1 = theta * (1. / 3); t2 = a1 * (1. / 3)
+        return [t0 * np.cos(t1) - t2, t0 * np.cos(t1 + 2. * np.pi / 3) - t2, t0 * np.cos(t1 + 4. * np.pi / 3) - t2]
+    if d == 0:
+        if R >= 0:
+            x0 = -2 * R ** (1. / 3) - a1 / 3; x1 = R ** (1. / 3) - a1 / 3
+        else:
+            x0 = 2 * (-R) ** (1. / 3) - a1 / 3; x1 = -(-R) ** (1. / 3) - a1 / 3
+        return [x0] if x0 == x1 else [x0, x1]
+    d = np.sqrt(-d)
+    e = (d + abs(R)) ** (1. / 3)
+    if R > 0:
+        e = -e
+    return [(e + Q / e) - a1 * (1. / 3)]
+
+
+def run_7point(m1, m2):
+    A = np.zeros((7, 9))
+    for i in range(7):
+        x0, y0 = float(m1[i][0]), float(m1[i][1]); x1, y1 = float(m2[i][0]), float(m2[i][1])
+        A[i] = [x1 * x0, x1 * y0, x1, y1 * x0, y1 * y0, y1, x0, y0, 1]
+    _, _, Vt = np.linalg.svd(A, full_matrices=True)
+    f1 = Vt[7].copy(); f2 = Vt[8].copy()
+    f1 -= f2
+    t0 = f2[4] * f2[8] - f2[5] * f2[7]; t1 = f2[3] * f2[8] - f2[5] * f2[6]; t2 = f2[3] * f2[7] - f2[4] * f2[6]
+    c = np.zeros(4)
+    c[3] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2
+    c[2] = (f1[0] * t0 - f1[1] * t1 + f1[2] * t2 - f1[3] * (f2[1] * f2[8] - f2[2] * f2[7]) +
+            f1[4] * (f2[0] * f2[8] - f2[2] * f2[6]) - f1[5] * (f2[0] * f2[7] - f2[1] * f2[6]) +
+            f1[6] * (f2[1] * f2[5] - f2[2] * f2[4]) - f1[7] * (f2[0] * f2[5] - f2[2] * f2[3]) +
+            f1[8] * (f2[0] * f2[4] - f2[1] * f2[3]))
+    t0 = f1[4] * f1[8] - f1[5] * f1[7]; t1 = f1[3] * f1[8] - f1[5] * f1[6]; t2 = f1[3] * f1[7] - f1[4] * f1[6]
+    c[0] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2
+    c[1] = (f2[0] * t0 - f2[1] * t1 + f2[2] * t2 - f2[3] * (f1[1] * f1[8] - f1[2] * f1[7]) +
+            f2[4] * (f1[0] * f1[8] - f1[2] * f1[6]) - f2[5] * (f1[0] * f1[7] - f1[1] * f1[6]) +
+            f2[6] * (f1[1] * f1[5] - f1[2] * f1[4]) - f2[7] * (f1[0] * f1[5] - f1[2] * f1[3]) +
+            f2[8] * (f1[0] * f1[4] - f1[1] * f1[3]))
+    roots = solve_cubic(c)
+    Fs = []
+    for r in roots:
+        lam, mu = r, 1.0
+        s = f1[8] * r + f2[8]
+        F = np.zeros(9)
+        if abs(s) > 2.220446049250313e-16:
+            mu = 1. / s; lam *= mu; F[8] = 1.0
+        else:
+            F[8] = 0.0
+        F[:8] = f1[:8] * lam + f2[:8] * mu
+        Fs.append(F)
+    return Fs
+
+
+def compute_error(m1, m2, F):
+    x1 = m1[:, 0].astype(np.float64); y1 = m1[:, 1].astype(np.float64)
+    x2 = m2[:, 0].astype(np.float64); y2 = m2[:, 1].astype(np.float64)
+    a = F[0] * x1 + F[1] * y1 + F[2]; b = F[3] * x1 + F[4] * y1 + F[5]; c = F[6] * x1 + F[7] * y1 + F[8]
+    s2 = 1. / (a * a + b * b); d2 = x2 * a + y2 * b + c
+    a = F[0] * x2 + F[3] * y2 + F[6]; b = F[1] * x2 + F[4] * y2 + F[7]; c = F[2] * x2 + F[5] * y2 + F[8]
+    s1 = 1. / (a * a + b * b); d1 = x1 * a + y1 * b + c
+    return np.maximum(d1 * d1 * s1, d2 * d2 * s2).astype(np.float32)
+
+
+def update_num_iters(p, ep, model_points, max_iters):
+    p = min(max(p, 0.), 1.); ep = min(max(ep, 0.), 1.)
+    num = max(1. - p, 2.2250738585072014e-308)
+    denom = 1. - (1. - ep) ** model_points
+    if denom < 2.2250738585072014e-308:
+        return 0
+    num = np.log(num); denom = np.log(denom)
+    if denom >= 0 or -num >= max_iters * (-denom):
+        return max_iters
+    return int(np.rint(num / denom))
+
+
+def find_fundamental_ransac_mask(p1, p2, threshold=1.0, confidence=0.99, max_iters=1000):
+    """Returns the inlier mask (uint8) or None exactly where cv2 returns mask None."""
+    m1 = np.asarray(p1, np.float32).reshape(-1, 2); m2 = np.asarray(p2, np.float32).reshape(-1, 2)
+    count = len(m1)
+    if count < 7:
+        return None
+    if count == 7:
+        return np.ones(7, np.uint8) if len(run_7point(m1, m2)) > 0 else None
+    if count < 15:
+        raise NotImplementedError("cv2 switches to LMedS below 15 points")
+    rng = CvRNG()
+    niters = max(max_iters, 1)
+    best_mask = None; max_good = 0
+    thr2 = np.float32(threshold * threshold)
+    it = 0
+    while it < niters:
+        idx = get_subset(m1, m2, rng)
+        if idx is None:
+            if it == 0:
+                return None
+            break
+        for F in run_7point(m1[idx], m2[idx]):
+            err = compute_error(m1, m2, F)
+            mask = (err <= thr2).astype(np.uint8)
+            good = int(mask.sum())
+            if good > max(max_good, 6):
+                best_mask = mask; max_good = good
+                niters = update_num_iters(confidence, (count - good) / count, 7, niters)
+        it += 1
+    return best_mask
