@@ -4,7 +4,9 @@
 //   n < 7            -> no mask (the reference then keeps every element, image_processor.h:219-223)
 //   n == 7           -> all ones
 //   8 <= n < 15      -> LMedS registrator (fundam.cpp switches below 15 points): 300 hypotheses,
-//                       least median, sigma-scaled threshold
+//                       least median, sigma-scaled threshold.  For n <= 13 the median index n/2 falls
+//                       inside the 7 exactly-fitted sample points, so OpenCV's winner is decided by
+//                       rounding noise and cannot be reproduced (known non-parity edge)
 //   n >= 15          -> RANSAC: cv::RNG(-1) MWC subsets of 7 (duplicates redrawn, last-point
 //                       collinearity test), 7-point cubic, goodCount > max(best, 6) update rule with
 //                       adaptive iteration count, Sampson-style max line distance^2 <= 1 as float.
@@ -122,12 +124,34 @@ __device__ int seven_point(double* A, const float2* p1, const float2* p2, const 
   n1[perm[7]] = 1.0; n2[perm[8]] = 1.0;
   for (int k = 0; k < 7; ++k) { n1[perm[k]] = -AA(k, perm[7]); n2[perm[k]] = -AA(k, perm[8]); }
 #undef AA
-  // normalise like singular vectors (unit length) for conditioning of the cubic
-  double s1 = 0, s2 = 0;
-  for (int c = 0; c < 9; ++c) { s1 += n1[c] * n1[c]; s2 += n2[c] * n2[c]; }
-  s1 = 1.0 / sqrt(s1); s2 = 1.0 / sqrt(s2);
+  // Re-express the null space in the basis cv::SVDecomp(FULL_UV) returns (oracle/ransac.py
+  // opencv_null_basis): Vt[7] = unit projection of R1 onto null(A), Vt[8] = unit projection of R2
+  // made orthogonal to Vt[7], with R1/R2 the +-1/9 sign vectors OpenCV draws from RNG(0x12345678).
+  // The basis fixes the ORDER of the candidate F matrices, which decides ties between equally good
+  // models of one sample.
+  const double R1[9] = {-1, -1, 1, -1, -1, -1, -1, 1, 1}, R2[9] = {1, -1, 1, 1, 1, 1, 1, -1, 1};
+  double e1[9], e2[9];
+  {
+    double s1 = 0, dot = 0, s2 = 0;
+    for (int c = 0; c < 9; ++c) s1 += n1[c] * n1[c];
+    s1 = 1.0 / sqrt(s1);
+    for (int c = 0; c < 9; ++c) { e1[c] = n1[c] * s1; dot += e1[c] * n2[c]; }
+    for (int c = 0; c < 9; ++c) { e2[c] = n2[c] - dot * e1[c]; s2 += e2[c] * e2[c]; }
+    s2 = 1.0 / sqrt(s2);
+    for (int c = 0; c < 9; ++c) e2[c] *= s2;
+  }
   double f1[9], f2[9];
-  for (int c = 0; c < 9; ++c) { f2[c] = n2[c] * s2; f1[c] = n1[c] * s1 - f2[c]; }
+  {
+    double a1 = 0, b1 = 0, a2 = 0, b2 = 0;
+    for (int c = 0; c < 9; ++c) { a1 += e1[c] * R1[c]; b1 += e2[c] * R1[c]; a2 += e1[c] * R2[c]; b2 += e2[c] * R2[c]; }
+    double nn = 0, dot = 0, n2n = 0;
+    for (int c = 0; c < 9; ++c) { f1[c] = a1 * e1[c] + b1 * e2[c]; nn += f1[c] * f1[c]; }
+    nn = 1.0 / sqrt(nn);
+    for (int c = 0; c < 9; ++c) { f1[c] *= nn; f2[c] = a2 * e1[c] + b2 * e2[c]; dot += f1[c] * f2[c]; }
+    for (int c = 0; c < 9; ++c) { f2[c] -= dot * f1[c]; n2n += f2[c] * f2[c]; }
+    n2n = 1.0 / sqrt(n2n);
+    for (int c = 0; c < 9; ++c) { f2[c] *= n2n; f1[c] -= f2[c]; }
+  }
   double c4[4], r[3] = {0, 0, 0};
   double t0 = f2[4] * f2[8] - f2[5] * f2[7], t1 = f2[3] * f2[8] - f2[5] * f2[6], t2 = f2[3] * f2[7] - f2[4] * f2[6];
   c4[3] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2;

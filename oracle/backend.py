@@ -1,0 +1,740 @@
+"""CPU oracle of ``LarVio`` (TEST INFRASTRUCTURE — see oracle/__init__.py).
+
+numpy float64 restatement of /root/reference/src/larvio.cpp for the pure-MSCKF configuration
+(``max_features_in_one_grid: 0``) with FEJ, online extrinsics and td:
+processFeatures :363-461, batchImuProcessing :464-517, processModel :520-578, predictNewState
+:581-649, calPhi :3475-3530, stateAugmentation :720-801, addFeatureObservations :804-856,
+measurementJacobian_msckf :859-921, featureJacobian_msckf :924-981, measurementUpdate_msckf
+:1420-1602, measurementUpdate_hybrid :1605-1862 (empty SLAM blocks), gatingTest :1865-1880,
+removeLostFeatures :1883-2256, findRedundantImuStates :2259-2307, pruneImuStateBuffer :2310-2641,
+checkZUPT :2751-2788 (detection only); Feature::{cost,jacobian,generateInitialGuess,checkMotion,
+initializePosition,initializePosition_AssignAnchor} include/larvio/feature.hpp:252-721;
+quaternion helpers include/larvio/math_utils.hpp:26-231.
+Third-party pieces are replaced per SURVEY.md §8c: SPQR thin QR -> numpy.linalg.qr, JacobiSVD
+left null space -> numpy.linalg.svd, LDLT solves -> numpy.linalg.solve, boost chi^2 quantile ->
+scipy.stats.chi2.ppf(0.05, k).  The update is invariant to these basis choices up to rounding.
+The initialisers (larvio.cpp:375-391) are out of scope: ``set_initial_state`` injects what they
+would leave behind.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.stats import chi2
+
+GRAVITY = np.array([0.0, 0.0, -9.81])
+
+
+def skew(w):
+    return np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0.0]])
+
+
+def quat_to_rot(q):
+    """Eigen Quaterniond(w,x,y,z).toRotationMatrix() for q = [x y z w]."""
+    x, y, z, w = q
+    return np.array([
+        [1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+        [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+        [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def rot_to_quat(R):
+    """Eigen Quaterniond(Matrix3d).coeffs() -> [x y z w]."""
+    t = R[0, 0] + R[1, 1] + R[2, 2]
+    q = np.zeros(4)
+    if t > 0:
+        t = np.sqrt(t + 1.0)
+        q[3] = 0.5 * t
+        t = 0.5 / t
+        q[0] = (R[2, 1] - R[1, 2]) * t; q[1] = (R[0, 2] - R[2, 0]) * t; q[2] = (R[1, 0] - R[0, 1]) * t
+    else:
+        i = 0
+        if R[1, 1] > R[0, 0]:
+            i = 1
+        if R[2, 2] > R[i, i]:
+            i = 2
+        j = (i + 1) % 3; k = (j + 1) % 3
+        t = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0)
+        q[i] = 0.5 * t
+        t = 0.5 / t
+        q[3] = (R[k, j] - R[j, k]) * t
+        q[j] = (R[j, i] + R[i, j]) * t
+        q[k] = (R[k, i] + R[i, k]) * t
+    return q
+
+
+def quat_mul(a, b):
+    """Hamilton product of Eigen quaternions given as [x y z w]."""
+    ax, ay, az, aw = a; bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by,
+                     aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw,
+                     aw * bw - ax * bx - ay * by - az * bz])
+
+
+def small_angle_quat(dtheta):
+    dq = dtheta / 2.0
+    n2 = float(dq @ dq)
+    q = np.zeros(4)
+    if n2 <= 1:
+        q[:3] = dq; q[3] = np.sqrt(1 - n2)
+    else:
+        q[:3] = dq; q[3] = 1
+        q = q / np.sqrt(1 + n2)
+    return q
+
+
+class ImuState:
+    def __init__(self):
+        self.id = 0; self.time = 0.0; self.dt = 0.0
+        self.q = np.array([0, 0, 0, 1.0]); self.p = np.zeros(3); self.v = np.zeros(3)
+        self.bg = np.zeros(3); self.ba = np.zeros(3)
+        self.R_imu_cam0 = np.eye(3); self.t_cam0_imu = np.zeros(3)
+
+    def copy(self):
+        o = ImuState()
+        o.__dict__.update({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in self.__dict__.items()})
+        return o
+
+
+class AugState:
+    def __init__(self, sid):
+        self.id = sid; self.time = 0.0; self.dt = 0.0
+        self.q = np.array([0, 0, 0, 1.0]); self.p = np.zeros(3); self.p_FEJ = np.zeros(3)
+        self.R_imu_cam0 = np.eye(3); self.t_cam0_imu = np.zeros(3)
+        self.q_cam = np.array([0, 0, 0, 1.0]); self.p_cam = np.zeros(3)
+
+
+class Feature:
+    huber_epsilon = 0.01; estimation_precision = 5e-7; initial_damping = 1e-3
+    outer_max = 10; inner_max = 10
+
+    def __init__(self, fid, translation_threshold):
+        self.id = fid
+        self.obs = {}        # state_id -> (2,)
+        self.obs_vel = {}
+        self.position = np.zeros(3)
+        self.is_initialized = False
+        self.id_anchor = -1
+        self.invDepth = 0.0
+        self.obs_anchor = np.zeros(3)
+        self.in_state = False
+        self.ekf_feature = False
+        self.totalObsNum = 0
+        self.translation_threshold = translation_threshold
+
+    @staticmethod
+    def _cost(R, t, x, z):
+        h = R @ np.array([x[0], x[1], 1.0]) + x[2] * t
+        zh = np.array([h[0] / h[2], h[1] / h[2]])
+        d = zh - z
+        return float(d @ d)
+
+    def _jacobian(self, R, t, x, z):
+        h = R @ np.array([x[0], x[1], 1.0]) + x[2] * t
+        W = np.zeros((3, 3)); W[:, :2] = R[:, :2]; W[:, 2] = t
+        J = np.zeros((2, 3))
+        J[0] = 1 / h[2] * W[0] - h[0] / (h[2] * h[2]) * W[2]
+        J[1] = 1 / h[2] * W[1] - h[1] / (h[2] * h[2]) * W[2]
+        r = np.array([h[0] / h[2], h[1] / h[2]]) - z
+        e = np.linalg.norm(r)
+        w = 1.0 if e <= self.huber_epsilon else np.sqrt(2.0 * self.huber_epsilon / e)
+        return J, r, w
+
+    @staticmethod
+    def _initial_guess(R, t, z1, z2):
+        m = R @ np.array([z1[0], z1[1], 1.0])
+        A = np.array([m[0] - z2[0] * m[2], m[1] - z2[1] * m[2]])
+        b = np.array([z2[0] * t[2] - t[0], z2[1] * t[2] - t[1]])
+        depth = (A @ b) / (A @ A)
+        return np.array([z1[0] * depth, z1[1] * depth, depth])
+
+    def check_motion(self, aug, if_tracked):
+        ids = sorted(self.obs.keys())
+        first = ids[0]
+        last = ids[-2] if if_tracked else ids[-1]
+        Rf = quat_to_rot(aug[first].q_cam); tf = aug[first].p_cam
+        tl = aug[last].p_cam
+        d = np.array([self.obs[first][0], self.obs[first][1], 1.0])
+        d = d / np.linalg.norm(d)
+        d = Rf @ d
+        tr = tl - tf
+        par = float(tr @ d)
+        orth = tr - par * d
+        return np.linalg.norm(orth) > self.translation_threshold
+
+    def initialize_position(self, aug, curr_id=None):
+        """initializePosition (curr_id given: skip the current camera) / _AssignAnchor (curr_id None)."""
+        poses = []; meas = []; cam_ids = []
+        for sid in sorted(self.obs.keys()):
+            if sid not in aug:
+                continue
+            if curr_id is not None and sid == curr_id:
+                continue
+            meas.append(self.obs[sid].copy())
+            poses.append((quat_to_rot(aug[sid].q_cam), aug[sid].p_cam.copy()))
+            cam_ids.append(sid)
+        Rl, tl = poses[-1]
+        rel = []
+        for (R, t) in poses:
+            # pose.inverse() * T_c_w_last
+            Ri = R.T
+            rel.append((Ri @ Rl, Ri @ (tl - t)))
+        if not self.is_initialized:
+            init = self._initial_guess(rel[0][0], rel[0][1], meas[-1], meas[0])
+        else:
+            init = Rl.T @ (self.position - tl)
+        sol = np.array([init[0] / init[2], init[1] / init[2], 1.0 / init[2]])
+        lam = self.initial_damping
+        inner = 0; outer = 0
+        reduced = False
+        delta_norm = 0.0
+        total = sum(self._cost(R, t, sol, z) for (R, t), z in zip(rel, meas))
+        while True:
+            A = np.zeros((3, 3)); b = np.zeros(3)
+            for (R, t), z in zip(rel, meas):
+                J, r, w = self._jacobian(R, t, sol, z)
+                if w == 1:
+                    A += J.T @ J; b += J.T @ r
+                else:
+                    A += w * w * (J.T @ J); b += w * w * (J.T @ r)
+            while True:
+                delta = np.linalg.solve(A + lam * np.eye(3), b)
+                new_sol = sol - delta
+                delta_norm = np.linalg.norm(delta)
+                new_cost = sum(self._cost(R, t, new_sol, z) for (R, t), z in zip(rel, meas))
+                if new_cost < total:
+                    reduced = True; sol = new_sol; total = new_cost
+                    lam = lam / 10 if lam / 10 > 1e-10 else 1e-10
+                else:
+                    reduced = False
+                    lam = lam * 10 if lam * 10 < 1e12 else 1e12
+                cont = (inner < self.inner_max) and (not reduced)
+                inner += 1
+                if not cont:
+                    break
+            inner = 0
+            cont = (outer < self.outer_max) and (delta_norm > self.estimation_precision)
+            outer += 1
+            if not cont:
+                break
+        final = np.array([sol[0] / sol[2], sol[1] / sol[2], 1.0 / sol[2]])
+        valid = True
+        for (R, t) in rel:
+            pos = R @ final + t
+            if pos[2] <= 0:
+                valid = False
+                break
+        n = len(rel)
+        if total / (2 * n * n) > 4.7673e-04:
+            valid = False
+        if valid:
+            self.is_initialized = True
+            self.position = Rl @ final + tl
+            self.id_anchor = cam_ids[-1]
+            self.invDepth = 1 / final[2]
+            self.obs_anchor = np.array([final[0] * self.invDepth, final[1] * self.invDepth, 1.0])
+        return valid
+
+
+class LarVioOracle:
+    def __init__(self, cfg_raw: dict):
+        r = cfg_raw
+        self.features_rate = float(r["pub_frequency"]); self.imu_rate = float(r["imu_rate"])
+        self.imu_img_timeTh = 1 / (2 * self.imu_rate)
+        self.rotation_threshold = float(r["rotation_threshold"])
+        self.translation_threshold = float(r["translation_threshold"])
+        self.tracking_rate_threshold = float(r["tracking_rate_threshold"])
+        self.max_track_len = int(r["max_track_len"])
+        self.feature_translation_threshold = float(r["feature_translation_threshold"])
+        self.td = float(r["td"])
+        self.estimate_td = bool(int(r["estimate_td"])); self.estimate_extrin = bool(int(r["estimate_extrin"]))
+        self.gyro_noise = float(r["noise_gyro"]) ** 2; self.acc_noise = float(r["noise_acc"]) ** 2
+        self.gyro_bias_noise = float(r["noise_gyro_bias"]) ** 2; self.acc_bias_noise = float(r["noise_acc_bias"]) ** 2
+        self.feature_noise = float(r["noise_feature"]) ** 2
+        self.calib_imu = bool(int(r["calib_imu_instrinsic"]))
+        if self.calib_imu:
+            raise NotImplementedError("calib_imu_instrinsic")
+        self.LEG = 22
+        self.Ma = np.eye(3); self.Tg = np.eye(3); self.As = np.zeros((3, 3))
+        P = np.zeros((self.LEG, self.LEG))
+        P[0:3, 0:3] = np.eye(3) * float(r["initial_covariance_orientation"])
+        P[3:6, 3:6] = np.eye(3) * float(r["initial_covariance_velocity"])
+        P[6:9, 6:9] = np.eye(3) * float(r["initial_covariance_position"])
+        P[9:12, 9:12] = np.eye(3) * float(r["initial_covariance_gyro_bias"])
+        P[12:15, 12:15] = np.eye(3) * float(r["initial_covariance_acc_bias"])
+        if self.estimate_extrin:
+            P[15:18, 15:18] = np.eye(3) * float(r["initial_covariance_extrin_rot"])
+            P[18:21, 18:21] = np.eye(3) * float(r["initial_covariance_extrin_trans"])
+        if self.estimate_td:
+            P[21, 21] = 4e-6
+        self.P = P
+        T = np.array(r["T_cam_imu"]["data"], np.float64).reshape(4, 4)
+        self.imu_state = ImuState()
+        self.imu_state.R_imu_cam0 = T[:3, :3].copy()              # larvio.cpp:189-202
+        self.imu_state.t_cam0_imu = -T[:3, :3].T @ T[:3, 3]
+        self.sw_size = int(r["sw_size"]); self.if_FEJ_config = bool(int(r["if_FEJ"]))
+        self.least_obs = int(r["least_observation_number"])
+        self.if_ZUPT_valid = bool(int(r["if_ZUPT_valid"])); self.zupt_max_feature_dis = float(r["zupt_max_feature_dis"])
+        self.max_features = max(int(r["max_features_in_one_grid"]), 0)
+        self.grid_rows = int(r["aug_grid_rows"]); self.grid_cols = int(r["aug_grid_cols"])
+        if self.max_features * self.grid_rows * self.grid_cols != 0:
+            raise NotImplementedError("hybrid EKF-SLAM features (max_features_in_one_grid > 0)")
+        Qc = np.zeros((12, 12))
+        Qc[0:3, 0:3] = np.eye(3) * self.gyro_noise; Qc[3:6, 3:6] = np.eye(3) * self.acc_noise
+        Qc[6:9, 6:9] = np.eye(3) * self.gyro_bias_noise; Qc[9:12, 9:12] = np.eye(3) * self.acc_bias_noise
+        self.Qc = Qc
+        self.if_FEJ = False; self.if_ZUPT = False; self.bFirstFeatures = False
+        self.is_gravity_set = False
+        self.chi2 = {i: float(chi2.ppf(0.05, i)) for i in range(1, 100)}
+        self.aug = {}                     # id -> AugState (iteration = sorted ids)
+        self.map_server = {}              # id -> Feature
+        self.FEJ_now = self.imu_state.copy(); self.FEJ_old = self.imu_state.copy()
+        self.imu_old = self.imu_state.copy()
+        self.m_gyro_old = None; self.m_acc_old = None
+        self.next_state_id = 0
+        self.tracking_rate = 0.0
+        self.coarse_feature_dis = []
+        self.take_off_stamp = 0.0
+        self.stats = {}                   # per-call counters (rows, r, d, ...) for flop accounting
+        self.zupt_events = 0
+
+    # what FlexibleInitializer::tryIncInit leaves behind (larvio.cpp:376-386)
+    def set_initial_state(self, t, q_xyzw, p, v, bg, ba):
+        s = self.imu_state
+        s.time = float(t); s.q = np.array(q_xyzw, float); s.p = np.array(p, float); s.v = np.array(v, float)
+        s.bg = np.array(bg, float); s.ba = np.array(ba, float)
+        self.is_gravity_set = True
+        self.take_off_stamp = s.time
+        self.FEJ_now = s.copy()
+
+    # ---- larvio.cpp:363-461.  imu: list of rows [t,w(3),a(3)] (mutated like the reference)
+    def process_features(self, msg, imu: list) -> bool:
+        if not self.bFirstFeatures:
+            if len(imu) > 0 and imu[0][0] - msg.t - self.td <= 0.0:
+                self.bFirstFeatures = True
+            else:
+                return False
+        if not self.is_gravity_set:
+            return False
+        self.stats = {}
+        self._batch_imu(msg.t + self.td, imu)
+        self._add_observations(msg)
+        self._augment()
+        if self.if_ZUPT_valid:
+            self.if_ZUPT = self._check_zupt()
+        self._remove_lost_features()
+        self._prune()
+        if self.if_FEJ_config and not self.if_FEJ and self.imu_state.time - self.take_off_stamp >= 0:
+            self.if_FEJ = True
+        return True
+
+    # ---- :464-517
+    def _batch_imu(self, time_bound, imu):
+        used = 0
+        dt = 0.0
+        for row in imu:
+            t = row[0]
+            if t <= self.imu_state.time:
+                used += 1
+                continue
+            if t - time_bound > self.imu_img_timeTh:
+                break
+            dt = t - time_bound
+            g = np.array(row[1:4], float); a = np.array(row[4:7], float)
+            if self.m_gyro_old is None:
+                self.m_gyro_old = g.copy(); self.m_acc_old = a.copy()
+            self._process_model(t, g, a)
+            used += 1
+            self.m_gyro_old = g; self.m_acc_old = a
+        self.imu_state.id = self.next_state_id
+        self.next_state_id += 1
+        self.imu_state.dt = dt
+        del imu[:used]
+        self.stats["n_imu"] = used
+
+    # ---- :520-578
+    def _process_model(self, time, m_gyro, m_acc):
+        s = self.imu_state
+        f = m_acc - s.ba; acc = self.Ma @ f
+        w = m_gyro - self.As @ acc - s.bg; gyro = self.Tg @ w
+        f_old = self.m_acc_old - s.ba; acc_old = self.Ma @ f_old
+        w_old = self.m_gyro_old - self.As @ acc_old - s.bg; gyro_old = self.Tg @ w_old
+        dtime = time - s.time
+        self._predict_new_state(dtime, gyro, acc)
+        Phi = self._cal_phi(dtime, f, w, acc, gyro, f_old, w_old, acc_old, gyro_old)
+        C = quat_to_rot(self.imu_old.q)
+        L = self.LEG
+        G = np.zeros((L, 12))
+        G[0:3, 0:3] = -C; G[3:6, 3:6] = -C; G[9:12, 6:9] = np.eye(3); G[12:15, 9:12] = np.eye(3)
+        Q = Phi @ G @ self.Qc @ G.T @ Phi.T * dtime
+        P = self.P
+        P[:L, :L] = Phi @ P[:L, :L] @ Phi.T + Q
+        if P.shape[0] > L:
+            P[:L, L:] = Phi @ P[:L, L:]
+            P[L:, :L] = P[L:, :L] @ Phi.T
+        self.P = (P + P.T) / 2.0
+        s.time = time
+        self.FEJ_now.time = time
+
+    # ---- :581-649
+    def _predict_new_state(self, dt, gyro, acc):
+        gn = np.linalg.norm(gyro)
+        Om = np.zeros((4, 4))
+        Om[:3, :3] = -skew(gyro); Om[:3, 3] = gyro; Om[3, :3] = -gyro
+        self.imu_old = self.imu_state.copy()
+        s = self.imu_state
+        q, v, p = s.q, s.v, s.p
+        if gn > 1e-5:
+            dq_dt = (np.cos(gn * dt * 0.5) * np.eye(4) + 1 / gn * np.sin(gn * dt * 0.5) * Om) @ q
+            dq_dt2 = (np.cos(gn * dt * 0.25) * np.eye(4) + 1 / gn * np.sin(gn * dt * 0.25) * Om) @ q
+        else:
+            dq_dt = (np.eye(4) + 0.5 * dt * Om) * np.cos(gn * dt * 0.5) @ q
+            dq_dt2 = (np.eye(4) + 0.25 * dt * Om) * np.cos(gn * dt * 0.25) @ q
+        dR = quat_to_rot(dq_dt); dR2 = quat_to_rot(dq_dt2)
+        k1v = quat_to_rot(q) @ acc + GRAVITY; k1p = v
+        k1_v = v + k1v * dt / 2
+        k2v = dR2 @ acc + GRAVITY; k2p = k1_v
+        k2_v = v + k2v * dt / 2
+        k3v = dR2 @ acc + GRAVITY; k3p = k2_v
+        k3_v = v + k3v * dt
+        k4v = dR @ acc + GRAVITY; k4p = k3_v
+        s.q = dq_dt / np.linalg.norm(dq_dt)
+        s.v = v + dt / 6 * (k1v + 2 * k2v + 2 * k3v + k4v)
+        s.p = p + dt / 6 * (k1p + 2 * k2p + 2 * k3p + k4p)
+        self.FEJ_old = self.FEJ_now.copy()
+        self.FEJ_now = s.copy()
+
+    # ---- :3475-3530
+    def _cal_phi(self, dtime, f, w, acc, gyro, f_old, w_old, acc_old, gyro_old):
+        axis = dtime * (gyro_old + gyro) / 2 + dtime * dtime * np.cross(gyro_old, gyro) / 12
+        Ah = skew(axis)
+        C = quat_to_rot(self.imu_old.q)
+        L = self.LEG
+        Phi = np.eye(L)
+        TA = self.Tg @ self.As
+        if self.if_FEJ:
+            vk, pk, vk1, pk1 = self.FEJ_old.v, self.FEJ_old.p, self.FEJ_now.v, self.FEJ_now.p
+        else:
+            vk, pk, vk1, pk1 = self.imu_old.v, self.imu_old.p, self.imu_state.v, self.imu_state.p
+        g = GRAVITY
+        I3 = np.eye(3)
+        Phi[0:3, 9:12] = -0.5 * C @ (2 * I3 + Ah) * dtime @ self.Tg
+        Phi[0:3, 12:15] = 0.5 * C @ (2 * I3 + Ah) * dtime @ TA @ self.Ma
+        Phi[3:6, 0:3] = -skew(vk1 - vk - g * dtime)
+        Phi[3:6, 9:12] = (skew(-pk1 + pk + vk1 * dtime - 0.5 * g * dtime * dtime) @ C +
+                          skew(-0.5 * pk1 + 0.5 * pk + 0.5 * vk1 * dtime - g * dtime * dtime / 6) @ C @ Ah)
+        Phi[3:6, 12:15] = -0.5 * C @ (2 * I3 + Ah) * dtime @ self.Ma - Phi[3:6, 9:12] @ TA @ self.Ma
+        Phi[6:9, 0:3] = -skew(pk1 - pk - vk * dtime - 0.5 * g * dtime * dtime)
+        Phi[6:9, 3:6] = I3 * dtime
+        Phi[6:9, 9:12] = (-dtime * dtime * dtime * skew(g) @ C / 6 +
+                          dtime * skew(pk1 - pk - g * dtime * dtime / 6) @ C @ Ah / 4)
+        Phi[6:9, 12:15] = -C @ (3 * I3 + Ah) * dtime * dtime / 6 @ self.Ma - Phi[6:9, 9:12] @ TA @ self.Ma
+        return Phi
+
+    # ---- :720-801
+    def _augment(self):
+        s = self.imu_state
+        a = AugState(s.id)
+        a.time = s.time; a.dt = s.dt; a.q = s.q.copy(); a.p = s.p.copy(); a.p_FEJ = self.FEJ_now.p.copy()
+        a.R_imu_cam0 = s.R_imu_cam0.copy(); a.t_cam0_imu = s.t_cam0_imu.copy()
+        R_b2w = quat_to_rot(s.q)
+        R_w2c = s.R_imu_cam0 @ R_b2w.T
+        a.q_cam = rot_to_quat(R_w2c.T)
+        a.p_cam = s.p + R_b2w @ s.t_cam0_imu
+        self.aug[s.id] = a
+        P = self.P
+        d = P.shape[0]
+        sel = [0, 1, 2, 6, 7, 8]
+        P12 = P[sel, :]
+        P11 = P12[:, sel]
+        Pn = np.zeros((d + 6, d + 6))
+        Pn[:d, :d] = P
+        Pn[d:, :d] = P12; Pn[:d, d:] = P12.T; Pn[d:, d:] = P11
+        self.P = (Pn + Pn.T) / 2.0
+
+    # ---- :804-856
+    def _add_observations(self, msg):
+        sid = self.imu_state.id
+        curr_num = len(self.map_server)
+        tracked = 0
+        dt = self.imu_state.dt
+        for fid, f in zip(msg.ids, msg.data):
+            fid = int(fid)
+            u, v, u_init, v_init, u_vel, v_vel, u_init_vel, v_init_vel = f
+            if fid not in self.map_server:
+                ft = Feature(fid, self.feature_translation_threshold)
+                self.map_server[fid] = ft
+                ft.obs[sid] = np.array([u + u_vel * dt, v + v_vel * dt]); ft.obs_vel[sid] = np.array([u_vel, v_vel])
+                ft.totalObsNum += 1
+                if not (u_init == -1 and v_init == -1) and (sid - 1) in self.aug:
+                    dt_ = self.aug[sid - 1].dt
+                    ft.obs[sid - 1] = np.array([u_init + u_init_vel * dt_, v_init + v_init_vel * dt_])
+                    ft.obs_vel[sid - 1] = np.array([u_init_vel, v_init_vel])
+                    ft.totalObsNum += 1
+            else:
+                ft = self.map_server[fid]
+                ft.obs[sid] = np.array([u + u_vel * dt, v + v_vel * dt]); ft.obs_vel[sid] = np.array([u_vel, v_vel])
+                ft.totalObsNum += 1
+                tracked += 1
+                if self.if_ZUPT_valid and (sid - 1) in ft.obs:
+                    self.coarse_feature_dis.append(float(np.linalg.norm(np.array([u, v]) - ft.obs[sid - 1])))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            self.tracking_rate = float(np.float64(tracked) / np.float64(curr_num))
+
+    # ---- :2751-2788 (detection only)
+    def _check_zupt(self):
+        d = self.coarse_feature_dis
+        self.coarse_feature_dis = []
+        if len(d) < 20:
+            return False
+        d = sorted(d)
+        if d[-9] < self.zupt_max_feature_dis:
+            self.zupt_events += 1
+            raise NotImplementedError("ZUPT update triggered (static scene) — next row f-2")
+        return False
+
+    # ---- :859-921
+    def _meas_jacobian(self, sid, ft):
+        a = self.aug[sid]
+        R_b2c = a.R_imu_cam0; t_c_b = a.t_cam0_imu
+        R_b2w = quat_to_rot(a.q); R_w2b = R_b2w.T
+        R_w2c = R_b2c @ R_w2b
+        t_c_w = a.p + R_b2w @ t_c_b
+        p_w = ft.position
+        z = ft.obs[sid]
+        p_c = R_w2c @ (p_w - t_c_w)
+        p_bf_w = (p_w - a.p_FEJ) if self.if_FEJ else (p_w - a.p)
+        dz = np.zeros((2, 3))
+        dz[0, 0] = 1 / p_c[2]; dz[1, 1] = 1 / p_c[2]
+        dz[0, 2] = -p_c[0] / (p_c[2] * p_c[2]); dz[1, 2] = -p_c[1] / (p_c[2] * p_c[2])
+        dxb = np.zeros((3, 6)); dxb[:, :3] = R_w2c @ skew(p_bf_w); dxb[:, 3:] = -R_w2c
+        dxe = np.zeros((3, 6)); dxe[:, :3] = R_w2c @ skew(p_bf_w) @ R_b2w - R_b2c @ skew(t_c_b); dxe[:, 3:] = -R_b2c
+        H_x = dz @ dxb; H_e = dz @ dxe; H_f = dz @ R_w2c
+        r = z - np.array([p_c[0] / p_c[2], p_c[1] / p_c[2]])
+        return H_x, H_e, H_f, r
+
+    # ---- :924-981
+    def _feature_jacobian(self, ft, state_ids):
+        valid = [sid for sid in state_ids if sid in ft.obs]
+        rows = 2 * len(valid)
+        d = self.P.shape[1]
+        Hx = np.zeros((rows, d)); Hf = np.zeros((rows, 3)); r = np.zeros(rows)
+        order = sorted(self.aug.keys())
+        k = 0
+        for sid in valid:
+            H_xi, H_ei, H_fi, r_i = self._meas_jacobian(sid, ft)
+            cntr = order.index(sid)
+            Hx[k:k + 2, self.LEG + 6 * cntr:self.LEG + 6 * cntr + 6] = H_xi
+            Hx[k:k + 2, 15:21] = H_ei
+            if self.estimate_td:
+                Hx[k:k + 2, 21] = ft.obs_vel[sid]
+            Hf[k:k + 2] = H_fi
+            r[k:k + 2] = r_i
+            k += 2
+        U, _, _ = np.linalg.svd(Hf, full_matrices=True)
+        A = U[:, 3:]
+        return A.T @ Hx, A.T @ r
+
+    # ---- :1865-1880
+    def _gating(self, H, r, dof):
+        S = H @ self.P @ H.T + self.feature_noise * np.eye(H.shape[0])
+        gamma = float(r @ np.linalg.solve(S, r))
+        return gamma < self.chi2.get(dof, 0.0)
+
+    def _compress(self, H, r, cols):
+        if H.shape[0] == 0 or H.shape[0] <= H.shape[1]:
+            return H, r
+        Q, R = np.linalg.qr(H, mode="reduced")
+        return R[:cols], (Q.T @ r)[:cols]
+
+    # ---- :1883-2256 (pure MSCKF: in_state is always False)
+    def _remove_lost_features(self):
+        sid_now = self.imu_state.id
+        rows_msckf = 0
+        invalid = []; msckf_ids = []; lost_ids = []
+        for fid in sorted(self.map_server.keys()):
+            ft = self.map_server[fid]
+            tracked_now = sid_now in ft.obs
+            if not tracked_now:
+                if len(ft.obs) < self.least_obs:
+                    invalid.append(fid); continue
+                if not ft.is_initialized:
+                    if not ft.check_motion(self.aug, tracked_now):
+                        invalid.append(fid); continue
+                    if not ft.initialize_position(self.aug, sid_now):
+                        invalid.append(fid); continue
+                rows_msckf += 2 * len(ft.obs) - 3
+                msckf_ids.append(fid); lost_ids.append(fid)
+            else:
+                if not (len(ft.obs) >= self.max_track_len):
+                    continue
+                if not ft.is_initialized:
+                    if ft.check_motion(self.aug, tracked_now):
+                        ft.initialize_position(self.aug, sid_now)
+                if not ft.is_initialized:
+                    continue
+                rows_msckf += 2 * len(ft.obs) - 3
+                msckf_ids.append(fid); lost_ids.append(fid)
+        for fid in invalid:
+            del self.map_server[fid]
+        self.stats["n_msckf_features"] = len(msckf_ids)
+        if len(msckf_ids) == 0:
+            return
+        if not self.if_ZUPT:
+            cols = self.LEG + 6 * len(self.aug)
+            Hs = []; rs = []
+            m_hist = []
+            for fid in msckf_ids:
+                ft = self.map_server[fid]
+                sids = sorted(ft.obs.keys())
+                Hj, rj = self._feature_jacobian(ft, sids)
+                if self._gating(Hj, rj, 2 * len(sids) - 3):
+                    Hs.append(Hj[:, :cols]); rs.append(rj)
+                    m_hist.append(len(sids))
+            H = np.concatenate(Hs) if Hs else np.zeros((0, cols))
+            r = np.concatenate(rs) if rs else np.zeros(0)
+            self.stats["rows_msckf"] = H.shape[0]; self.stats["m_hist"] = m_hist
+            H, r = self._compress(H, r, cols)
+            Hfull = np.zeros((H.shape[0], self.P.shape[1])); Hfull[:, :H.shape[1]] = H
+            self._update(Hfull, r, "hybrid")
+        else:
+            for fid in msckf_ids:
+                self.map_server[fid].is_initialized = False
+        for fid in lost_ids:
+            del self.map_server[fid]
+
+    # ---- :1420-1602 / :1605-1862 with empty SLAM blocks
+    def _update(self, H, r, tag):
+        if H.shape[0] == 0 or r.shape[0] == 0:
+            return
+        P = self.P
+        S = H @ P @ H.T + self.feature_noise * np.eye(H.shape[0])
+        Kt = np.linalg.solve(S, H @ P)
+        K = Kt.T
+        dx = K @ r
+        self.stats.setdefault("updates", []).append(dict(tag=tag, r=H.shape[0], d=P.shape[0]))
+        s = self.imu_state
+        s.q = quat_mul(small_angle_quat(dx[0:3]), s.q)
+        s.v = s.v + dx[3:6]; s.p = s.p + dx[6:9]; s.bg = s.bg + dx[9:12]; s.ba = s.ba + dx[12:15]
+        dqe = small_angle_quat(dx[15:18])
+        s.R_imu_cam0 = s.R_imu_cam0 @ quat_to_rot(dqe).T
+        s.t_cam0_imu = s.t_cam0_imu + dx[18:21]
+        self.td += dx[21]
+        for i, sid in enumerate(sorted(self.aug.keys())):
+            a = self.aug[sid]
+            da = dx[self.LEG + 6 * i:self.LEG + 6 * i + 6]
+            a.q = quat_mul(small_angle_quat(da[0:3]), a.q)
+            a.p = a.p + da[3:6]
+            R_b2w = quat_to_rot(a.q)
+            a.q_cam = rot_to_quat(R_b2w @ s.R_imu_cam0.T)
+            a.p_cam = a.p + R_b2w @ s.t_cam0_imu
+        I_KH = np.eye(K.shape[0]) - K @ H
+        P = I_KH @ P
+        self.P = (P + P.T) / 2.0
+
+    # ---- :2259-2307
+    def _find_redundant(self):
+        ids = sorted(self.aug.keys())
+        key_i = len(ids) - 4
+        st_i = key_i + 1
+        first_i = 0
+        key = self.aug[ids[key_i]]
+        key_R = quat_to_rot(key.q_cam)
+        rm = []
+        for _ in range(2):
+            a = self.aug[ids[st_i]]
+            Rr = quat_to_rot(a.q_cam).T
+            dist = np.linalg.norm(a.p_cam - key.p_cam)
+            M = Rr @ key_R
+            # Eigen AngleAxisd(R).angle(): via quaternion, angle = 2*atan2(|vec|, |w|)
+            qq = rot_to_quat(M)
+            n = np.linalg.norm(qq[:3])
+            angle = 2 * np.arctan2(n, abs(qq[3]))
+            if angle < self.rotation_threshold and dist < self.translation_threshold and self.tracking_rate > self.tracking_rate_threshold:
+                rm.append(ids[st_i]); st_i += 1
+            else:
+                rm.append(ids[first_i]); first_i += 1
+                st_i -= 2
+        return sorted(rm)
+
+    # ---- :2310-2641 (pure MSCKF)
+    def _prune(self):
+        if not self.if_ZUPT:
+            if len(self.aug) < self.sw_size:
+                return
+            rm_ids = self._find_redundant()
+        else:
+            rm_ids = [self.imu_state.id - 1]
+        rows = 0
+        used = []
+        sid_now = self.imu_state.id
+        for fid in sorted(self.map_server.keys()):
+            ft = self.map_server[fid]
+            involved = [sid for sid in rm_ids if sid in ft.obs]
+            if len(involved) == 0:
+                continue
+            if ft.is_initialized and ft.id_anchor in involved:
+                new_id = self._new_anchor_id(ft, involved)
+                a = self.aug[new_id]
+                R_c2w = quat_to_rot(a.q_cam)
+                p_new = R_c2w.T @ (ft.position - a.p_cam)
+                ft.invDepth = 1 / p_new[2]
+                ft.obs_anchor = np.array([ft.obs[new_id][0], ft.obs[new_id][1], ft.obs_anchor[2]])
+                ft.id_anchor = new_id
+            if not self.if_ZUPT and not ft.ekf_feature and len(involved) > 1:
+                tracked = sid_now in ft.obs
+                if not ft.is_initialized:
+                    if not ft.check_motion(self.aug, tracked):
+                        continue
+                    if not ft.initialize_position(self.aug, None):
+                        continue
+                used.append(fid)
+                rows += 2 * len(involved) - 3
+        self.stats["prune_used"] = len(used)
+        if not self.if_ZUPT and len(used) != 0:
+            Hs = []; rs = []
+            for fid in sorted(self.map_server.keys()):
+                ft = self.map_server[fid]
+                involved = [sid for sid in rm_ids if sid in ft.obs]
+                if fid in used:
+                    Hj, rj = self._feature_jacobian(ft, involved)
+                    if self._gating(Hj, rj, 2 * len(involved) - 3):
+                        Hs.append(Hj); rs.append(rj)
+                for sid in involved:
+                    del ft.obs[sid]
+            H = np.concatenate(Hs) if Hs else np.zeros((0, self.P.shape[1]))
+            r = np.concatenate(rs) if rs else np.zeros(0)
+            if H.shape[0] > 0:
+                cols = self.LEG + 6 * len(self.aug)
+                if H.shape[0] > H.shape[1]:
+                    H, r = self._compress(H, r, cols)
+                self._update(H, r, "msckf")
+        else:
+            for fid in sorted(self.map_server.keys()):
+                ft = self.map_server[fid]
+                for sid in [sid for sid in rm_ids if sid in ft.obs]:
+                    del ft.obs[sid]
+        for sid in rm_ids:
+            order = sorted(self.aug.keys())
+            seq = order.index(sid)
+            a0 = self.LEG + 6 * seq
+            keep = [i for i in range(self.P.shape[0]) if not (a0 <= i < a0 + 6)]
+            self.P = self.P[np.ix_(keep, keep)]
+            del self.aug[sid]
+
+    # ---- getNewAnchorId :3412-3472
+    def _new_anchor_id(self, ft, involved):
+        order = sorted(self.aug.keys())
+        size = len(order)
+        if size <= 2:
+            return order[-1]
+        best = None; min_dis = 99999.0
+        for sid in order[:size - 2]:
+            if sid not in ft.obs or sid in involved:
+                continue
+            a = self.aug[sid]
+            p_new = quat_to_rot(a.q_cam).T @ (ft.position - a.p_cam)
+            dis = float(np.linalg.norm(np.array([p_new[0] / p_new[2], p_new[1] / p_new[2]]) - ft.obs[sid]))
+            if min_dis > dis:
+                min_dis = dis; best = sid
+        return best if best is not None else order[-1]

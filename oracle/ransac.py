@@ -87,14 +87,36 @@ def solve_cubic(c):
     return [(e + Q / e) - a1 * (1. / 3)]
 
 
+# OpenCV's JacobiSVD (core/src/lapack.cpp JacobiSVDImpl_) fills the two null-space rows of Vt from
+# +-1/9 sign vectors drawn from cv::RNG(0x12345678), Gram-Schmidt'ed against the singular vectors:
+# row 7 = unit projection of R1 onto null(A), row 8 = unit projection of R2 made orthogonal to row 7.
+# The order of the (up to three) candidate F matrices — which decides ties between equally good
+# models of one sample — depends on this basis, so it is part of the restatement.
+_NULL_R1 = np.array([-1, -1, 1, -1, -1, -1, -1, 1, 1], np.float64) / 9.0
+_NULL_R2 = np.array([1, -1, 1, 1, 1, 1, 1, -1, 1], np.float64) / 9.0
+
+
+def opencv_null_basis(n1, n2):
+    """n1, n2: any basis of the 2-D null space -> (Vt[7], Vt[8]) as cv::SVDecomp(FULL_UV) returns them."""
+    e1 = n1 / np.linalg.norm(n1)
+    e2 = n2 - (e1 @ n2) * e1
+    e2 = e2 / np.linalg.norm(e2)
+    p1 = (e1 @ _NULL_R1) * e1 + (e2 @ _NULL_R1) * e2
+    f1 = p1 / np.linalg.norm(p1)
+    p2 = (e1 @ _NULL_R2) * e1 + (e2 @ _NULL_R2) * e2
+    p2 = p2 - (f1 @ p2) * f1
+    f2 = p2 / np.linalg.norm(p2)
+    return f1, f2
+
+
 def run_7point(m1, m2):
     A = np.zeros((7, 9))
     for i in range(7):
         x0, y0 = float(m1[i][0]), float(m1[i][1]); x1, y1 = float(m2[i][0]), float(m2[i][1])
         A[i] = [x1 * x0, x1 * y0, x1, y1 * x0, y1 * y0, y1, x0, y0, 1]
     _, _, Vt = np.linalg.svd(A, full_matrices=True)
-    f1 = Vt[7].copy(); f2 = Vt[8].copy()
-    f1 -= f2
+    f1, f2 = opencv_null_basis(Vt[7], Vt[8])
+    f1 = f1 - f2
     t0 = f2[4] * f2[8] - f2[5] * f2[7]; t1 = f2[3] * f2[8] - f2[5] * f2[6]; t2 = f2[3] * f2[7] - f2[4] * f2[6]
     c = np.zeros(4)
     c[3] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2
@@ -145,6 +167,32 @@ def update_num_iters(p, ep, model_points, max_iters):
     return int(np.rint(num / denom))
 
 
+def _lmeds_mask(m1, m2, confidence, max_iters):
+    """LMeDSPointSetRegistrator::run — what findFundamentalMat(FM_RANSAC) uses for 8..14 points."""
+    count = len(m1)
+    rng = CvRNG()
+    niters = max(update_num_iters(confidence, 0.45, 7, max_iters), 3)
+    min_median = np.inf
+    best = None
+    for it in range(niters):
+        idx = get_subset(m1, m2, rng, max_attempts=1000)
+        if idx is None:
+            if it == 0:
+                return None
+            break
+        for F in run_7point(m1[idx], m2[idx]):
+            err = compute_error(m1, m2, F)
+            med = float(np.sort(err)[count // 2])
+            if med < min_median:
+                min_median = med; best = F
+    if best is None:
+        return None
+    sigma = 2.5 * 1.4826 * (1 + 5. / (count - 7)) * np.sqrt(min_median)
+    sigma = max(sigma, 0.001)
+    err = compute_error(m1, m2, best)
+    return (err <= np.float32(sigma * sigma)).astype(np.uint8)
+
+
 def find_fundamental_ransac_mask(p1, p2, threshold=1.0, confidence=0.99, max_iters=1000):
     """Returns the inlier mask (uint8) or None exactly where cv2 returns mask None."""
     m1 = np.asarray(p1, np.float32).reshape(-1, 2); m2 = np.asarray(p2, np.float32).reshape(-1, 2)
@@ -154,7 +202,7 @@ def find_fundamental_ransac_mask(p1, p2, threshold=1.0, confidence=0.99, max_ite
     if count == 7:
         return np.ones(7, np.uint8) if len(run_7point(m1, m2)) > 0 else None
     if count < 15:
-        raise NotImplementedError("cv2 switches to LMedS below 15 points")
+        return _lmeds_mask(m1, m2, confidence, max_iters)
     rng = CvRNG()
     niters = max(max_iters, 1)
     best_mask = None; max_good = 0
