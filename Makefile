@@ -1,7 +1,11 @@
 # Builds the in-tree C-ABI library (sm_100a only) and the C oracle helpers.
 NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3,-ffp-contract=off -Xptxas -v --fmad=false
+NVBASE := $(ARCH) -O3 -lineinfo -std=c++17 -Xptxas -v
+# front end: bit-exact parity with OpenCV's non-FMA float arithmetic -> no contraction anywhere
+NVFLAGS := $(NVBASE) -Xcompiler -fPIC,-O3,-ffp-contract=off --fmad=false
+# back end: FP64 linear algebra, FMA allowed
+NVFLAGS_BE := $(NVBASE) -Xcompiler -fPIC,-O3
 SRC_CU := $(wildcard larvio_b200/csrc/*.cu)
 SRC_CPP := $(wildcard larvio_b200/csrc/*.cpp)
 OBJ := $(SRC_CU:.cu=.o) $(SRC_CPP:.cpp=.o)
@@ -9,7 +13,10 @@ LIB := larvio_b200/lib/liblarvio_b200.so
 
 all: $(LIB)
 
-larvio_b200/csrc/%.o: larvio_b200/csrc/%.cu larvio_b200/csrc/*.h include/larvio_b200.h
+larvio_b200/csrc/be_%.o: larvio_b200/csrc/be_%.cu larvio_b200/csrc/*.h larvio_b200/csrc/*.cuh larvio_b200/csrc/*.inc include/larvio_b200.h
+	$(NVCC) $(NVFLAGS_BE) -c $< -o $@ 2> $@.log || (cat $@.log; false)
+
+larvio_b200/csrc/%.o: larvio_b200/csrc/%.cu larvio_b200/csrc/*.h larvio_b200/csrc/*.cuh larvio_b200/csrc/*.inc include/larvio_b200.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $@.log || (cat $@.log; false)
 
 larvio_b200/csrc/%.o: larvio_b200/csrc/%.cpp include/larvio_b200.h

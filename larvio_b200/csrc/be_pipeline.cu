@@ -1,10 +1,1611 @@
+// Batched LarVio::processFeatures (larvio.cpp:363-461), pure-MSCKF configuration, FP64.
+//   be_propagate_kernel   batchImuProcessing / processModel / predictNewState / calPhi (:464-649, :3475-3530)
+//   be_add_obs_kernel     addFeatureObservations (:804-856) + the checkZUPT detector (:2751-2766)
+//   be_augment_kernel     stateAugmentation (:720-801)
+//   be_classify_kernel    removeLostFeatures' classifier + Feature::checkMotion / initializePosition
+//                         (:1926-2005, feature.hpp:334-552) and pruneImuStateBuffer's selection (:2331-2489)
+//   be_feature_kernel     measurementJacobian_msckf / featureJacobian_msckf / gatingTest (:859-981, :1865-1880)
+//   be_stack_kernel       stacking of the gated blocks (:2185-2204, :2494-2536)
+//   be_qr_kernel          thin-QR measurement compression (:1430-1449, :2209-2229)
+//   be_update_*           measurementUpdate_hybrid / _msckf (:1420-1602, :1605-1862) as
+//                         T=HP, S=TH^T+s^2 I, S=LL^T, Y=L^-1 T, dx=Y^T L^-1 r, P-=Y^T Y
+//   be_prune_*            findRedundantImuStates / pruneImuStateBuffer (:2259-2307, :2310-2641)
+// One CTA per sequence for the sequential parts, (tiles x sequences) grids for the dense algebra.
+#include <math.h>
+#include <string.h>
 #include "be_state.h"
-int be_alloc(LvbHandle* h) { h->be = new LvbBackEnd(); return LVB_OK; }
-void be_free(LvbHandle* h) { delete h->be; h->be = nullptr; }
-extern "C" int lvb_process_features(LvbHandle*, const uint8_t*, const double*, const LvbFeature*, const int*, int, LvbImu*, int*, int, uint8_t*) { return lvb_set_err(LVB_E_UNSUPPORTED, "back end not built yet"); }
-extern "C" int lvb_step(LvbHandle*, const uint8_t*, int, const double*, LvbImu*, int*, int, uint8_t*) { return lvb_set_err(LVB_E_UNSUPPORTED, "back end not built yet"); }
-extern "C" int lvb_set_initial_state(LvbHandle*, int, double, const double*, const double*, const double*, const double*, const double*) { return lvb_set_err(LVB_E_UNSUPPORTED, "back end not built yet"); }
-extern "C" int lvb_get_state(LvbHandle*, int, double*, double*, double*, double*, double*, double*, double*, double*) { return lvb_set_err(LVB_E_UNSUPPORTED, "back end not built yet"); }
-extern "C" int lvb_get_states(LvbHandle*, double*) { return lvb_set_err(LVB_E_UNSUPPORTED, "back end not built yet"); }
-extern "C" int lvb_get_window(LvbHandle*, int, double*, int, int*) { return lvb_set_err(LVB_E_UNSUPPORTED, "back end not built yet"); }
-extern "C" int lvb_get_covariance(LvbHandle*, int, double*, int, int*) { return lvb_set_err(LVB_E_UNSUPPORTED, "back end not built yet"); }
+#include "be_math.cuh"
+
+#define RC(x) do { int rc_ = (x); if (rc_ != LVB_OK) return rc_; } while (0)
+
+namespace {
+
+__constant__ double c_chi2[100] = {
+#include "be_chi2.inc"
+};
+
+struct BeCfg {
+  double th_imu;              // imu_img_timeTh = 1/(2*imu_rate)
+  double sg2, sa2, sbg2, sba2, sfeat2;
+  double rot_thr, trans_thr, track_thr, feat_trans_thr, zupt_dis;
+  int max_track_len, sw_size, least_obs, if_FEJ_config, estimate_td, if_ZUPT_valid;
+};
+
+struct BeView {
+  LvbBackEnd be;     // by value: device pointers + dims
+  BeCfg cfg;
+  const LvbFeature* msg; const int* msg_n; const double* msg_t; const uint8_t* msg_valid; int msg_stride;
+  double* P;         // current covariance buffer
+  double* Pn;        // the other buffer
+};
+
+__device__ __forceinline__ double* core_of(const BeView& v, int s) { return v.be.core + (size_t)s * BE_CORE; }
+__device__ __forceinline__ int* icore_of(const BeView& v, int s) { return v.be.icore + (size_t)s * BE_ICORE; }
+__device__ __forceinline__ double* win_of(const BeView& v, int s, int slot) { return v.be.win + ((size_t)s * v.be.Wcap + slot) * BE_WIN; }
+__device__ __forceinline__ double* P_of(const BeView& v, int s) { return v.P + (size_t)s * v.be.LD * v.be.LD; }
+
+// ====================================================================== propagate
+__global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
+  __shared__ double Phi[BE_LEG][BE_LEG + 1], PLL[BE_LEG][BE_LEG + 1], Tmp[BE_LEG][BE_LEG + 1], PhiTot[BE_LEG][BE_LEG + 1];
+  __shared__ double Ddiag[BE_LEG];
+  __shared__ int s_ok, s_action, s_used;
+  __shared__ double s_dtime, s_dt;
+  const int s = blockIdx.x, tid = threadIdx.x;
+  double* core = core_of(v, s);
+  int* ic = icore_of(v, s);
+  const LvbImu* imu = v.be.imu + (size_t)s * v.be.imu_cap;
+  const int n_imu = v.be.n_imu[s];
+  const int L = BE_LEG, LD = v.be.LD;
+  double* P = P_of(v, s);
+  if (tid == 0) {
+    int ok = v.msg_valid[s] != 0;
+    if (ok && !ic[I_FIRST]) {                                   // larvio.cpp:366-372
+      if (n_imu > 0 && imu[0].t - v.msg_t[s] - core[C_TD] <= 0.0) ic[I_FIRST] = 1;
+      else ok = 0;
+    }
+    if (ok && !ic[I_GRAVITY]) ok = 0;                            // :375-391 (initialiser out of scope)
+    s_ok = ok; ic[I_OK] = ok; ic[I_CONSUMED] = 0; s_used = 0; s_dt = 0.0;
+    ic[I_UPDATES] = 0;
+  }
+  if (tid < L) {
+    double dv = 0.0;
+    if (tid < 3) dv = v.cfg.sg2; else if (tid < 6) dv = v.cfg.sa2;
+    else if (tid >= 9 && tid < 12) dv = v.cfg.sbg2; else if (tid >= 12 && tid < 15) dv = v.cfg.sba2;
+    Ddiag[tid] = dv;
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  for (int i = tid; i < L * L; i += blockDim.x) {
+    const int r = i / L, c = i - r * L;
+    PLL[r][c] = P[(size_t)r * LD + c];
+    PhiTot[r][c] = (r == c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  const double time_bound = v.msg_t[s] + core[C_TD];
+  for (int k = 0; k < n_imu; ++k) {
+    if (tid == 0) {
+      const double t = imu[k].t;
+      if (t <= core[C_TIME]) { s_action = 0; s_used++; }
+      else if (t - time_bound > v.cfg.th_imu) s_action = 2;
+      else {
+        s_action = 1; s_used++;
+        s_dt = t - time_bound;
+        const V3 m_gyro = v3(imu[k].gyro[0], imu[k].gyro[1], imu[k].gyro[2]);
+        const V3 m_acc = v3(imu[k].acc[0], imu[k].acc[1], imu[k].acc[2]);
+        if (!ic[I_HAVE_OLD]) { st3(core + C_GYRO_OLD, m_gyro); st3(core + C_ACC_OLD, m_acc); ic[I_HAVE_OLD] = 1; }
+        // ---- processModel (:520-578) with Ma = Tg = I, As = 0
+        const V3 bg = ld3(core + C_BG), ba = ld3(core + C_BA);
+        const V3 acc = m_acc - ba, gyro = m_gyro - bg;
+        const V3 gyro_old = ld3(core + C_GYRO_OLD) - bg;
+        const double dtime = t - core[C_TIME];
+        s_dtime = dtime;
+        // ---- predictNewState (:581-649)
+        const double gn = norm(gyro);
+        double q[4] = {core[C_Q], core[C_Q + 1], core[C_Q + 2], core[C_Q + 3]};
+        const V3 vel = ld3(core + C_V), pos = ld3(core + C_P);
+        for (int i = 0; i < 4; ++i) core[C_OLD_Q + i] = q[i];
+        st3(core + C_OLD_P, pos); st3(core + C_OLD_V, vel);
+        const V3 qv = v3(q[0], q[1], q[2]);
+        const V3 ov = cross(qv, gyro) + gyro * q[3];     // (Omega q).head<3>()
+        const double ow = -dot(gyro, qv);                // (Omega q)(3)
+        double dq[4], dq2[4];
+        if (gn > 1e-5) {
+          const double c1 = cos(gn * dtime * 0.5), s1 = 1 / gn * sin(gn * dtime * 0.5);
+          const double c2 = cos(gn * dtime * 0.25), s2 = 1 / gn * sin(gn * dtime * 0.25);
+          dq[0] = c1 * q[0] + s1 * ov.x; dq[1] = c1 * q[1] + s1 * ov.y; dq[2] = c1 * q[2] + s1 * ov.z; dq[3] = c1 * q[3] + s1 * ow;
+          dq2[0] = c2 * q[0] + s2 * ov.x; dq2[1] = c2 * q[1] + s2 * ov.y; dq2[2] = c2 * q[2] + s2 * ov.z; dq2[3] = c2 * q[3] + s2 * ow;
+        } else {
+          const double c1 = cos(gn * dtime * 0.5), c2 = cos(gn * dtime * 0.25);
+          dq[0] = (q[0] + 0.5 * dtime * ov.x) * c1; dq[1] = (q[1] + 0.5 * dtime * ov.y) * c1;
+          dq[2] = (q[2] + 0.5 * dtime * ov.z) * c1; dq[3] = (q[3] + 0.5 * dtime * ow) * c1;
+          dq2[0] = (q[0] + 0.25 * dtime * ov.x) * c2; dq2[1] = (q[1] + 0.25 * dtime * ov.y) * c2;
+          dq2[2] = (q[2] + 0.25 * dtime * ov.z) * c2; dq2[3] = (q[3] + 0.25 * dtime * ow) * c2;
+        }
+        const M3 dR = quat_to_rot(dq), dR2 = quat_to_rot(dq2), Rq = quat_to_rot(q);
+        const V3 g = v3(0, 0, -9.81);
+        const V3 k1v = m3_vec(Rq, acc) + g, k1p = vel;
+        const V3 k1_v = vel + k1v * dtime * 0.5;
+        const V3 k2v = m3_vec(dR2, acc) + g, k2p = k1_v;
+        const V3 k2_v = vel + k2v * dtime * 0.5;
+        const V3 k3v = m3_vec(dR2, acc) + g, k3p = k2_v;
+        const V3 k3_v = vel + k3v * dtime;
+        const V3 k4v = m3_vec(dR, acc) + g, k4p = k3_v;
+        const double qn = 1.0 / sqrt(dq[0] * dq[0] + dq[1] * dq[1] + dq[2] * dq[2] + dq[3] * dq[3]);
+        for (int i = 0; i < 4; ++i) core[C_Q + i] = dq[i] * qn;
+        const V3 vnew = vel + (k1v + 2.0 * k2v + 2.0 * k3v + k4v) * (dtime / 6);
+        const V3 pnew = pos + (k1p + 2.0 * k2p + 2.0 * k3p + k4p) * (dtime / 6);
+        st3(core + C_V, vnew); st3(core + C_P, pnew);
+        // FEJ bookkeeping (:644-646)
+        st3(core + C_FOLD_P, ld3(core + C_FNOW_P)); st3(core + C_FOLD_V, ld3(core + C_FNOW_V));
+        st3(core + C_FNOW_P, pnew); st3(core + C_FNOW_V, vnew);
+        // ---- calPhi (:3475-3530)
+        const V3 axis = (gyro_old + gyro) * (dtime * 0.5) + cross(gyro_old, gyro) * (dtime * dtime / 12);
+        const M3 Ah = skew(axis);
+        const M3 C = Rq;       // C_bk2w from imu_state_old.orientation
+        V3 vk, pk, vk1, pk1;
+        if (ic[I_FEJ]) { vk = ld3(core + C_FOLD_V); pk = ld3(core + C_FOLD_P); vk1 = ld3(core + C_FNOW_V); pk1 = ld3(core + C_FNOW_P); }
+        else { vk = vel; pk = pos; vk1 = vnew; pk1 = pnew; }
+        for (int r = 0; r < L; ++r) for (int c = 0; c < L; ++c) Phi[r][c] = (r == c) ? 1.0 : 0.0;
+        const M3 I3 = m3_identity();
+        const M3 twoIAh = m3_add(m3_scale(I3, 2.0), Ah);
+        const M3 Pqbg = m3_scale(m3_mul(C, twoIAh), -0.5 * dtime);
+        const M3 Pvq = m3_scale(skew(vk1 - vk - g * dtime), -1.0);
+        const M3 Pvbg = m3_add(m3_mul(skew(pk - pk1 + vk1 * dtime - g * (0.5 * dtime * dtime)), C),
+                               m3_mul(m3_mul(skew(pk * 0.5 - pk1 * 0.5 + vk1 * (0.5 * dtime) - g * (dtime * dtime / 6)), C), Ah));
+        const M3 Pvba = m3_scale(m3_mul(C, twoIAh), -0.5 * dtime);
+        const M3 Ppq = m3_scale(skew(pk1 - pk - vk * dtime - g * (0.5 * dtime * dtime)), -1.0);
+        const M3 Ppbg = m3_add(m3_scale(m3_mul(skew(g), C), -dtime * dtime * dtime / 6),
+                               m3_scale(m3_mul(m3_mul(skew(pk1 - pk - g * (dtime * dtime / 6)), C), Ah), dtime / 4));
+        const M3 Ppba = m3_scale(m3_mul(C, m3_add(m3_scale(I3, 3.0), Ah)), -dtime * dtime / 6);
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) {
+            Phi[r][9 + c] = Pqbg.m[r * 3 + c];
+            Phi[3 + r][c] = Pvq.m[r * 3 + c];
+            Phi[3 + r][9 + c] = Pvbg.m[r * 3 + c];
+            Phi[3 + r][12 + c] = Pvba.m[r * 3 + c];
+            Phi[6 + r][c] = Ppq.m[r * 3 + c];
+            Phi[6 + r][3 + c] = (r == c) ? dtime : 0.0;
+            Phi[6 + r][9 + c] = Ppbg.m[r * 3 + c];
+            Phi[6 + r][12 + c] = Ppba.m[r * 3 + c];
+          }
+        core[C_TIME] = t;
+        st3(core + C_GYRO_OLD, m_gyro); st3(core + C_ACC_OLD, m_acc);
+      }
+    }
+    __syncthreads();
+    const int action = s_action;
+    if (action == 2) break;
+    if (action == 0) { __syncthreads(); continue; }
+    const double dtime = s_dtime;
+    // Tmp = Phi * (PLL + D*dtime)
+    for (int i = tid; i < L * L; i += blockDim.x) {
+      const int r = i / L, c = i - r * L;
+      double acc = 0.0;
+      for (int k2 = 0; k2 < L; ++k2) acc += Phi[r][k2] * (PLL[k2][c] + (k2 == c ? Ddiag[c] * dtime : 0.0));
+      Tmp[r][c] = acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < L * L; i += blockDim.x) {
+      const int r = i / L, c = i - r * L;
+      double acc = 0.0;
+      for (int k2 = 0; k2 < L; ++k2) acc += Tmp[r][k2] * Phi[c][k2];
+      PLL[r][c] = acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < L * L; i += blockDim.x) {
+      const int r = i / L, c = i - r * L;
+      double acc = 0.0;
+      for (int k2 = 0; k2 < L; ++k2) acc += Phi[r][k2] * PhiTot[k2][c];
+      Tmp[r][c] = acc;
+      if (r < c) { const double m = 0.5 * (PLL[r][c] + PLL[c][r]); PLL[r][c] = m; PLL[c][r] = m; }
+    }
+    __syncthreads();
+    for (int i = tid; i < L * L; i += blockDim.x) { const int r = i / L, c = i - r * L; PhiTot[r][c] = Tmp[r][c]; }
+    __syncthreads();
+  }
+  __syncthreads();
+  // write back P_LL, apply the composed transition to the cross terms
+  const int d = ic[I_DIM];
+  for (int i = tid; i < L * L; i += blockDim.x) { const int r = i / L, c = i - r * L; P[(size_t)r * LD + c] = PLL[r][c]; }
+  for (int c = L + tid; c < d; c += blockDim.x) {
+    double col[BE_LEG];
+    for (int r = 0; r < L; ++r) col[r] = P[(size_t)r * LD + c];
+    for (int r = 0; r < L; ++r) {
+      double acc = 0.0;
+      for (int k2 = 0; k2 < L; ++k2) acc += PhiTot[r][k2] * col[k2];
+      P[(size_t)r * LD + c] = acc;
+      P[(size_t)c * LD + r] = acc;
+    }
+  }
+  if (tid == 0) {
+    ic[I_ID] = ic[I_NEXT_ID]; ic[I_NEXT_ID] += 1;     // :505
+    core[C_DT] = s_dt;                                 // :508
+    ic[I_CONSUMED] = s_used;                           // :510-512 (the host erases)
+  }
+}
+
+// ====================================================================== addFeatureObservations
+// One CTA per sequence, one thread per message feature.
+__global__ void __launch_bounds__(512) be_add_obs_kernel(BeView v) {
+  extern __shared__ unsigned long long sm_ids[];      // [T] table ids (0xfff.. = free)
+  __shared__ int s_free_cnt, s_new_cnt, s_tracked, s_nbefore, s_ndis;
+  __shared__ float s_dis[512];
+  const int s = blockIdx.x, tid = threadIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK]) return;
+  double* core = core_of(v, s);
+  const int T = v.be.T, Wcap = v.be.Wcap;
+  unsigned long long* ft_id = v.be.ft_id + (size_t)s * T;
+  int* ft_flags = v.be.ft_flags + (size_t)s * T;
+  unsigned long long* ft_mask = v.be.ft_mask + (size_t)s * T;
+  double* ft_obs = v.be.ft_obs + (size_t)s * T * Wcap * 4;
+  if (tid == 0) { s_free_cnt = 0; s_new_cnt = 0; s_tracked = 0; s_nbefore = 0; s_ndis = 0; }
+  __syncthreads();
+  int used_local = 0;
+  for (int i = tid; i < T; i += blockDim.x) {
+    const bool used = ft_flags[i] & 1;
+    sm_ids[i] = used ? ft_id[i] : ~0ull;
+    used_local += used;
+  }
+  atomicAdd(&s_nbefore, used_local);
+  __syncthreads();
+  const int n_msg = min(v.msg_n[s], v.be.N);
+  const int n_win = ic[I_NWIN];                       // slot the new state will occupy
+  const long long sid = ic[I_ID];
+  // slot of state id-1, if it is still in the window
+  int prev_slot = -1;
+  for (int w = n_win - 1; w >= 0; --w) if (v.be.win_id[(size_t)s * Wcap + w] == sid - 1) { prev_slot = w; break; }
+  const double dt = core[C_DT];
+  LvbFeature f; int slot = -1; bool is_new = false;
+  if (tid < n_msg) {
+    f = v.msg[(size_t)s * v.msg_stride + tid];
+    for (int i = 0; i < T; ++i) if (sm_ids[i] == f.id) { slot = i; break; }
+    is_new = slot < 0;
+  }
+  __syncthreads();
+  // allocate free slots for new features in message order (block-level exclusive scan by ballot)
+  __shared__ int warp_new[16];
+  const unsigned bal = __ballot_sync(0xffffffffu, is_new);
+  if ((tid & 31) == 0) warp_new[tid >> 5] = __popc(bal);
+  __syncthreads();
+  int rank = __popc(bal & ((1u << (tid & 31)) - 1));
+  for (int w = 0; w < (tid >> 5); ++w) rank += warp_new[w];
+  if (is_new) {
+    // rank-th free slot
+    int cnt = 0, found = -1;
+    for (int i = 0; i < T; ++i) if (sm_ids[i] == ~0ull) { if (cnt == rank) { found = i; break; } ++cnt; }
+    slot = found;
+    if (slot < 0) atomicExch(&ic[I_ERR], 1);           // feature table overflow
+  }
+  if (tid < n_msg && slot >= 0) {
+    double* o = ft_obs + ((size_t)slot * Wcap + n_win) * 4;
+    if (is_new) {
+      ft_id[slot] = f.id; ft_flags[slot] = 1;            // used, not initialised
+      unsigned long long m = 1ull << n_win;
+      o[0] = f.u + f.u_vel * dt; o[1] = f.v + f.v_vel * dt; o[2] = f.u_vel; o[3] = f.v_vel;
+      if (!(f.u_init == -1 && f.v_init == -1) && prev_slot >= 0) {      // :824-832
+        const double dt_ = win_of(v, s, prev_slot)[W_DT];
+        double* o2 = ft_obs + ((size_t)slot * Wcap + prev_slot) * 4;
+        o2[0] = f.u_init + f.u_init_vel * dt_; o2[1] = f.v_init + f.v_init_vel * dt_; o2[2] = f.u_init_vel; o2[3] = f.v_init_vel;
+        m |= 1ull << prev_slot;
+      }
+      ft_mask[slot] = m;
+      v.be.ft_pos[((size_t)s * T + slot) * 3 + 0] = 0; v.be.ft_pos[((size_t)s * T + slot) * 3 + 1] = 0; v.be.ft_pos[((size_t)s * T + slot) * 3 + 2] = 0;
+    } else {
+      const unsigned long long m = ft_mask[slot];
+      o[0] = f.u + f.u_vel * dt; o[1] = f.v + f.v_vel * dt; o[2] = f.u_vel; o[3] = f.v_vel;
+      ft_mask[slot] = m | (1ull << n_win);
+      atomicAdd(&s_tracked, 1);
+      if (v.cfg.if_ZUPT_valid && prev_slot >= 0 && (m >> prev_slot & 1)) {     // :842-847
+        const double* op = ft_obs + ((size_t)slot * Wcap + prev_slot) * 4;
+        const double dx = f.u - op[0], dy = f.v - op[1];
+        const int k = atomicAdd(&s_ndis, 1);
+        if (k < 512) s_dis[k] = (float)sqrt(dx * dx + dy * dy);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    core[C_TRACK_RATE] = (double)s_tracked / (double)s_nbefore;      // :851-853 (NaN when the map was empty)
+    // checkZUPT (:2751-2766): the 9th largest displacement
+    ic[I_ZUPT] = 0;
+    const int nd = min(s_ndis, 512);
+    if (v.cfg.if_ZUPT_valid && nd >= 20) {
+      // selection of the 9th largest by repeated max (nd <= 512, once per frame)
+      float cur = 3.0e38f; int taken = 0; float val = 0.f;
+      while (taken < 9) {
+        float best = -1.f; int cnt = 0;
+        for (int i = 0; i < nd; ++i) { const float d = s_dis[i]; if (d < cur) { if (d > best) { best = d; cnt = 1; } else if (d == best) ++cnt; } }
+        if (best < 0.f) break;
+        taken += cnt; val = best; cur = best;
+      }
+      if ((double)val < v.cfg.zupt_dis) { ic[I_ZUPT] = 1; ic[I_ZUPT_EVENTS] += 1; }
+    }
+  }
+}
+
+// ====================================================================== stateAugmentation
+__global__ void __launch_bounds__(256) be_augment_kernel(BeView v) {
+  const int s = blockIdx.x, tid = threadIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK]) return;
+  double* core = core_of(v, s);
+  const int LD = v.be.LD;
+  double* P = P_of(v, s);
+  const int d = ic[I_DIM];
+  const int n_win = ic[I_NWIN];
+  if (n_win >= v.be.Wcap || d + 6 > v.be.Dmax) { if (tid == 0) atomicExch(&ic[I_ERR], 2); return; }
+  if (tid == 0) {
+    double* w = win_of(v, s, n_win);
+    v.be.win_id[(size_t)s * v.be.Wcap + n_win] = ic[I_ID];
+    w[W_TIME] = core[C_TIME]; w[W_DT] = core[C_DT];
+    for (int i = 0; i < 4; ++i) w[W_Q + i] = core[C_Q + i];
+    for (int i = 0; i < 3; ++i) { w[W_P + i] = core[C_P + i]; w[W_PFEJ + i] = core[C_FNOW_P + i]; w[W_TCI + i] = core[C_TCI + i]; }
+    for (int i = 0; i < 9; ++i) w[W_RIC + i] = core[C_RIC + i];
+    const M3 R_b2w = quat_to_rot(core + C_Q);
+    const M3 R_b2c = m3_load(core + C_RIC);
+    const M3 R_c2w = m3_mul(R_b2w, m3_t(R_b2c));       // (R_b2c * R_w2b)^T
+    rot_to_quat(R_c2w, w + W_QCAM);
+    st3(w + W_PCAM, ld3(core + C_P) + m3_vec(R_b2w, ld3(core + C_TCI)));
+  }
+  const int sel[6] = {0, 1, 2, 6, 7, 8};
+  for (int j = tid; j < d; j += blockDim.x) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const double val = P[(size_t)sel[i] * LD + j];
+      P[(size_t)(d + i) * LD + j] = val;
+      P[(size_t)j * LD + d + i] = val;
+    }
+  }
+  if (tid < 36) {
+    const int i = tid / 6, k = tid - i * 6;
+    P[(size_t)(d + i) * LD + d + k] = P[(size_t)sel[i] * LD + sel[k]];
+  }
+  __syncthreads();
+  if (tid == 0) { ic[I_DIM] = d + 6; ic[I_NWIN] = n_win + 1; }
+}
+
+}  // namespace
+
+namespace {
+
+// ====================================================================== warp helpers
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ int nth_set_bit(unsigned long long m, int n) {   // index of the n-th (0-based) set bit
+  for (int k = 0; k < n; ++k) m &= m - 1;
+  return __ffsll((long long)m) - 1;
+}
+
+// ---------------------------------------------------------------- Feature::checkMotion (feature.hpp:334-381)
+__device__ bool check_motion(const BeView& v, int s, unsigned long long mask, const double* obs, int Wcap, bool if_tracked) {
+  const int first = __ffsll((long long)mask) - 1;
+  unsigned long long m2 = mask;
+  int last = 63 - __clzll((long long)m2);
+  if (if_tracked) { m2 &= ~(1ull << last); last = 63 - __clzll((long long)m2); }
+  const double* wf = win_of(v, s, first);
+  const double* wl = win_of(v, s, last);
+  const M3 Rf = quat_to_rot(wf + W_QCAM);
+  V3 dir = v3(obs[(size_t)first * 4 + 0], obs[(size_t)first * 4 + 1], 1.0);
+  dir = dir * (1.0 / norm(dir));
+  dir = m3_vec(Rf, dir);
+  const V3 tr = ld3(wl + W_PCAM) - ld3(wf + W_PCAM);
+  const double par = dot(tr, dir);
+  const V3 orth = tr - dir * par;
+  return norm(orth) > v.cfg.feat_trans_thr;
+}
+
+// ---------------------------------------------------------------- Feature::initializePosition[_AssignAnchor]
+// (feature.hpp:383-552 / :554-721).  One warp; lanes own observations (two per lane at most).
+// tri_mask: observations that take part.  Returns validity; on success writes the world position.
+__device__ bool triangulate_warp(const BeView& v, int s, unsigned long long tri_mask, const double* obs,
+                                 bool is_init, double* pos /*[3] in/out*/) {
+  const int lane = threadIdx.x & 31;
+  const int n = __popcll(tri_mask);
+  const int last = 63 - __clzll((long long)tri_mask);
+  const double* wl = win_of(v, s, last);
+  const M3 Rl = quat_to_rot(wl + W_QCAM);
+  const V3 tl = ld3(wl + W_PCAM);
+  // per-lane observations
+  double zx[2], zy[2]; M3 R[2]; V3 t[2]; bool have[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int k = lane + 32 * e;
+    have[e] = k < n;
+    zx[e] = zy[e] = 0; R[e] = m3_identity(); t[e] = v3(0, 0, 0);
+    if (have[e]) {
+      const int slot = nth_set_bit(tri_mask, k);
+      const double* w = win_of(v, s, slot);
+      const M3 Ri = quat_to_rot(w + W_QCAM);
+      R[e] = m3_mul(m3_t(Ri), Rl);                       // pose.inverse() * T_c_w_last
+      t[e] = m3_tvec(Ri, tl - ld3(w + W_PCAM));
+      zx[e] = obs[(size_t)slot * 4 + 0]; zy[e] = obs[(size_t)slot * 4 + 1];
+    }
+  }
+  // ---- initial guess
+  V3 init;
+  if (!is_init) {
+    // generateInitialGuess(cam_poses[0], measurements[last], measurements[0]) (feature.hpp:312-332)
+    M3 R0; V3 t0;
+    for (int i = 0; i < 9; ++i) R0.m[i] = shfl_d(R[0].m[i], 0);
+    t0 = v3(shfl_d(t[0].x, 0), shfl_d(t[0].y, 0), shfl_d(t[0].z, 0));
+    const double z2x = shfl_d(zx[0], 0), z2y = shfl_d(zy[0], 0);
+    const int lk = n - 1;
+    const double z1x = (lk < 32) ? shfl_d(zx[0], lk & 31) : shfl_d(zx[1], lk & 31);
+    const double z1y = (lk < 32) ? shfl_d(zy[0], lk & 31) : shfl_d(zy[1], lk & 31);
+    const V3 m = m3_vec(R0, v3(z1x, z1y, 1.0));
+    const double A0 = m.x - z2x * m.z, A1 = m.y - z2y * m.z;
+    const double b0 = z2x * t0.z - t0.x, b1 = z2y * t0.z - t0.y;
+    const double depth = (A0 * b0 + A1 * b1) / (A0 * A0 + A1 * A1);
+    init = v3(z1x * depth, z1y * depth, depth);
+  } else {
+    init = m3_tvec(Rl, ld3(pos) - tl);
+  }
+  double sol[3] = {init.x / init.z, init.y / init.z, 1.0 / init.z};
+  auto cost_of = [&](const double* x) {
+    double c = 0.0;
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      if (have[e]) {
+        const V3 h = m3_vec(R[e], v3(x[0], x[1], 1.0)) + t[e] * x[2];
+        const double dx = h.x / h.z - zx[e], dy = h.y / h.z - zy[e];
+        c += dx * dx + dy * dy;
+      }
+    return warp_sum_d(c);
+  };
+  double lambda = 1e-3;
+  int inner = 0, outer = 0;
+  bool reduced = false;
+  double delta_norm = 0.0;
+  double total = cost_of(sol);
+  const double huber = 0.01;
+  while (true) {
+    double A[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};     // A: xx xy xz yy yz zz
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      if (have[e]) {
+        const V3 h = m3_vec(R[e], v3(sol[0], sol[1], 1.0)) + t[e] * sol[2];
+        // W = [R(:,0) R(:,1) t]
+        const double W0[3] = {R[e].m[0], R[e].m[1], t[e].x}, W1[3] = {R[e].m[3], R[e].m[4], t[e].y}, W2[3] = {R[e].m[6], R[e].m[7], t[e].z};
+        double J0[3], J1[3];
+        for (int c = 0; c < 3; ++c) {
+          J0[c] = 1 / h.z * W0[c] - h.x / (h.z * h.z) * W2[c];
+          J1[c] = 1 / h.z * W1[c] - h.y / (h.z * h.z) * W2[c];
+        }
+        const double r0 = h.x / h.z - zx[e], r1 = h.y / h.z - zy[e];
+        const double en = sqrt(r0 * r0 + r1 * r1);
+        const double w = en <= huber ? 1.0 : sqrt(2.0 * huber / en);
+        const double w2 = (w == 1.0) ? 1.0 : w * w;
+        A[0] += w2 * (J0[0] * J0[0] + J1[0] * J1[0]); A[1] += w2 * (J0[0] * J0[1] + J1[0] * J1[1]);
+        A[2] += w2 * (J0[0] * J0[2] + J1[0] * J1[2]); A[3] += w2 * (J0[1] * J0[1] + J1[1] * J1[1]);
+        A[4] += w2 * (J0[1] * J0[2] + J1[1] * J1[2]); A[5] += w2 * (J0[2] * J0[2] + J1[2] * J1[2]);
+        b[0] += w2 * (J0[0] * r0 + J1[0] * r1); b[1] += w2 * (J0[1] * r0 + J1[1] * r1); b[2] += w2 * (J0[2] * r0 + J1[2] * r1);
+      }
+    for (int i = 0; i < 6; ++i) A[i] = warp_sum_d(A[i]);
+    for (int i = 0; i < 3; ++i) b[i] = warp_sum_d(b[i]);
+    while (true) {
+      // delta = (A + lambda I)^-1 b  (3x3 symmetric, LDL^T)
+      const double a00 = A[0] + lambda, a01 = A[1], a02 = A[2], a11 = A[3] + lambda, a12 = A[4], a22 = A[5] + lambda;
+      const double l10 = a01 / a00, l20 = a02 / a00;
+      const double d1 = a11 - l10 * a01;
+      const double l21 = (a12 - l20 * a01) / d1;
+      const double d2 = a22 - l20 * a02 - l21 * l21 * d1;
+      const double y0 = b[0], y1 = b[1] - l10 * y0, y2 = b[2] - l20 * y0 - l21 * y1;
+      const double x2 = y2 / d2;
+      const double x1 = y1 / d1 - l21 * x2;
+      const double x0 = y0 / a00 - l10 * x1 - l20 * x2;
+      const double ns[3] = {sol[0] - x0, sol[1] - x1, sol[2] - x2};
+      delta_norm = sqrt(x0 * x0 + x1 * x1 + x2 * x2);
+      const double nc = cost_of(ns);
+      if (nc < total) {
+        reduced = true; sol[0] = ns[0]; sol[1] = ns[1]; sol[2] = ns[2]; total = nc;
+        lambda = lambda / 10 > 1e-10 ? lambda / 10 : 1e-10;
+      } else {
+        reduced = false;
+        lambda = lambda * 10 < 1e12 ? lambda * 10 : 1e12;
+      }
+      const bool cont = (inner < 10) && !reduced;
+      ++inner;
+      if (!cont) break;
+    }
+    inner = 0;
+    const bool cont = (outer < 10) && (delta_norm > 5e-7);
+    ++outer;
+    if (!cont) break;
+  }
+  const V3 fin = v3(sol[0] / sol[2], sol[1] / sol[2], 1.0 / sol[2]);
+  int bad = 0;
+#pragma unroll
+  for (int e = 0; e < 2; ++e)
+    if (have[e]) { const V3 pp = m3_vec(R[e], fin) + t[e]; if (pp.z <= 0) bad = 1; }
+  bad = __any_sync(0xffffffffu, bad);
+  bool valid = !bad;
+  if (total / (2.0 * n * n) > 4.7673e-04) valid = false;
+  if (!(total == total)) valid = false;   // NaN guard
+  if (valid && lane == 0) st3(pos, m3_vec(Rl, fin) + tl);
+  return valid;
+}
+
+// ====================================================================== classification
+// mode 0: removeLostFeatures (:1926-2005); mode 1: pruneImuStateBuffer selection (:2331-2489).
+// one warp per table slot.  ft_action: 0 keep, 1 erase, 2 use in the update (mode 0: then erase).
+__global__ void __launch_bounds__(128) be_classify_kernel(BeView v, int mode) {
+  const int s = blockIdx.y;
+  const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  int* ic = icore_of(v, s);
+  const int T = v.be.T, Wcap = v.be.Wcap;
+  if (slot >= T) return;
+  const size_t fi = (size_t)s * T + slot;
+  if (lane == 0) { v.be.ft_action[fi] = 0; v.be.ft_nrows[fi] = 0; v.be.ft_accept[fi] = 0; }
+  if (!ic[I_OK]) return;
+  if (mode == 1 && !ic[I_DO_PRUNE]) return;
+  const int flags = v.be.ft_flags[fi];
+  if (!(flags & 1)) return;
+  const unsigned long long mask = v.be.ft_mask[fi];
+  const double* obs = v.be.ft_obs + fi * Wcap * 4;
+  double* pos = v.be.ft_pos + fi * 3;
+  const int cur = ic[I_NWIN] - 1;
+  const bool tracked = (mask >> cur) & 1;
+  const int nobs = __popcll(mask);
+  bool is_init = (flags & 2) != 0;
+  const bool zupt = ic[I_ZUPT] != 0;
+  int action = 0;
+  unsigned long long usemask = 0;
+  if (mode == 0) {
+    const unsigned long long tri = mask & ~(1ull << cur);     // initializePosition skips the current camera
+    if (!tracked) {
+      if (nobs < v.cfg.least_obs) action = 1;
+      else {
+        if (!is_init) {
+          if (!check_motion(v, s, mask, obs, Wcap, tracked)) action = 1;
+          else if (!triangulate_warp(v, s, tri, obs, false, pos)) action = 1;
+          else is_init = true;
+        }
+        if (action == 0) { action = 2; usemask = mask; }
+      }
+    } else if (nobs >= v.cfg.max_track_len) {
+      if (!is_init) {
+        if (check_motion(v, s, mask, obs, Wcap, tracked))
+          if (triangulate_warp(v, s, tri, obs, false, pos)) is_init = true;
+      }
+      if (is_init) { action = 2; usemask = mask; }
+    }
+    if (zupt && action == 2) { is_init = false; usemask = 0; }   // :2241-2246: no update, features dropped
+  } else {
+    unsigned long long rm = 0;
+    for (int k = 0; k < ic[I_NRM]; ++k) rm |= 1ull << ic[I_RM0 + k];
+    const unsigned long long involved = mask & rm;
+    if (involved && !zupt && __popcll(involved) > 1) {
+      bool ok = true;
+      if (!is_init) {
+        if (!check_motion(v, s, mask, obs, Wcap, tracked)) ok = false;
+        else if (!triangulate_warp(v, s, mask, obs, false, pos)) ok = false;     // _AssignAnchor: all observations
+        else is_init = true;
+      }
+      if (ok) { action = 2; usemask = involved; }
+    }
+  }
+  if (lane == 0) {
+    v.be.ft_flags[fi] = (flags & ~2) | (is_init ? 2 : 0);
+    v.be.ft_action[fi] = action;
+    v.be.ft_usemask[fi] = usemask;
+    v.be.ft_nrows[fi] = (action == 2 && usemask) ? 2 * __popcll(usemask) : 0;
+  }
+}
+
+// exclusive scan of raw row counts over the table (one CTA per sequence, 512 threads, T <= 1024)
+__global__ void __launch_bounds__(512) be_scan_rows_kernel(BeView v, int which /*0: raw rows -> ft_rowofs, I_RAWROWS*/) {
+  __shared__ int part[512];
+  const int s = blockIdx.x, tid = threadIdx.x;
+  int* ic = icore_of(v, s);
+  const int T = v.be.T;
+  const int per = (T + 511) / 512;
+  int loc = 0;
+  for (int k = 0; k < per; ++k) { const int i = tid * per + k; if (i < T) loc += v.be.ft_nrows[(size_t)s * T + i]; }
+  part[tid] = loc;
+  __syncthreads();
+  for (int o = 1; o < 512; o <<= 1) { int x = tid >= o ? part[tid - o] : 0; __syncthreads(); part[tid] += x; __syncthreads(); }
+  int run = part[tid] - loc;
+  for (int k = 0; k < per; ++k) {
+    const int i = tid * per + k;
+    if (i < T) {
+      const int nr = v.be.ft_nrows[(size_t)s * T + i];
+      v.be.ft_rowofs[(size_t)s * T + i] = run;
+      if (nr && run + nr > v.be.RAWMAX) {        // capacity: the feature is not used this frame (reported)
+        v.be.ft_nrows[(size_t)s * T + i] = 0; v.be.ft_usemask[(size_t)s * T + i] = 0; atomicExch(&ic[I_ERR], 3);
+      }
+      run += nr;
+    }
+  }
+  if (tid == 511) ic[I_RAWROWS] = part[511];
+}
+
+}  // namespace
+
+namespace {
+
+// ====================================================================== per-feature Jacobian + gating
+// One warp (one CTA) per table slot with action 2.  Raw rows live in Hraw[s][rowofs .. rowofs+2m) (dense,
+// width LD); after three Householder reflections that annihilate H_f the rows 3..2m-1 are the projected
+// block A^T H_x, A^T r (featureJacobian_msckf, larvio.cpp:972-978; any orthonormal basis of the left null
+// space gives the same gate value and the same update).  dynamic smem: (2*Wcap)^2 + 8*Wcap doubles.
+__global__ void __launch_bounds__(32) be_feature_kernel(BeView v, double* Traw) {
+  extern __shared__ double fsm[];
+  const int s = blockIdx.y, slot = blockIdx.x, lane = threadIdx.x;
+  const int T = v.be.T, Wcap = v.be.Wcap, LD = v.be.LD;
+  const size_t fi = (size_t)s * T + slot;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK]) return;
+  const int nrows = v.be.ft_nrows[fi];
+  if (nrows == 0 || v.be.ft_action[fi] != 2) return;
+  const unsigned long long um = v.be.ft_usemask[fi];
+  const int m = nrows / 2;
+  const int ofs = v.be.ft_rowofs[fi];
+  double* H = v.be.Hraw + ((size_t)s * v.be.RAWMAX + ofs) * LD;
+  double* rr = v.be.rraw + (size_t)s * v.be.RAWMAX + ofs;
+  double* Tj = Traw + ((size_t)s * v.be.RAWMAX + ofs) * LD;
+  const double* core = core_of(v, s);
+  const double* P = P_of(v, s);
+  const double* obs = v.be.ft_obs + fi * Wcap * 4;
+  const V3 p_w = ld3(v.be.ft_pos + fi * 3);
+  const int d = ic[I_DIM];
+  const bool fej = ic[I_FEJ] != 0;
+  double* Hf = fsm;                         // [2m][3]
+  double* Ssm = fsm + 6 * Wcap + 8;         // [(2m-3)^2]
+  double* vv = fsm + 6 * Wcap + 8 + 4 * Wcap * Wcap;   // [2m] reflector / rhs scratch
+  // zero the raw rows
+  for (int i = lane; i < nrows * LD; i += 32) H[i] = 0.0;
+  __syncwarp();
+  // ---- measurementJacobian_msckf per observation (:859-921)
+  for (int k = lane; k < m; k += 32) {
+    const int ws = nth_set_bit(um, k);
+    const double* w = win_of(v, s, ws);
+    const M3 R_b2c = m3_load(w + W_RIC);
+    const V3 t_c_b = ld3(w + W_TCI);
+    const M3 R_b2w = quat_to_rot(w + W_Q);
+    const M3 R_w2c = m3_mul(R_b2c, m3_t(R_b2w));
+    const V3 t_b_w = ld3(w + W_P);
+    const V3 t_c_w = t_b_w + m3_vec(R_b2w, t_c_b);
+    const V3 p_c = m3_vec(R_w2c, p_w - t_c_w);
+    const V3 p_bf_w = fej ? (p_w - ld3(w + W_PFEJ)) : (p_w - t_b_w);
+    double dz[2][3] = {{1 / p_c.z, 0, -p_c.x / (p_c.z * p_c.z)}, {0, 1 / p_c.z, -p_c.y / (p_c.z * p_c.z)}};
+    const M3 A1 = m3_mul(R_w2c, skew(p_bf_w));                       // dpc_dxb.leftCols(3)
+    const M3 E1 = m3_sub(m3_mul(A1, R_b2w), m3_mul(R_b2c, skew(t_c_b)));   // dpc_dxe.leftCols(3)
+    double* r0 = H + (size_t)(2 * k) * LD;
+    double* r1 = r0 + LD;
+    const int cp = BE_LEG + 6 * ws;
+    for (int c = 0; c < 3; ++c) {
+      double hx0 = 0, hx1 = 0, hp0 = 0, hp1 = 0, he0 = 0, he1 = 0, ht0 = 0, ht1 = 0, hf0 = 0, hf1 = 0;
+      for (int q = 0; q < 3; ++q) {
+        hx0 += dz[0][q] * A1.m[q * 3 + c]; hx1 += dz[1][q] * A1.m[q * 3 + c];
+        hp0 += dz[0][q] * -R_w2c.m[q * 3 + c]; hp1 += dz[1][q] * -R_w2c.m[q * 3 + c];
+        he0 += dz[0][q] * E1.m[q * 3 + c]; he1 += dz[1][q] * E1.m[q * 3 + c];
+        ht0 += dz[0][q] * -R_b2c.m[q * 3 + c]; ht1 += dz[1][q] * -R_b2c.m[q * 3 + c];
+        hf0 += dz[0][q] * R_w2c.m[q * 3 + c]; hf1 += dz[1][q] * R_w2c.m[q * 3 + c];
+      }
+      r0[cp + c] = hx0; r1[cp + c] = hx1; r0[cp + 3 + c] = hp0; r1[cp + 3 + c] = hp1;
+      r0[15 + c] = he0; r1[15 + c] = he1; r0[18 + c] = ht0; r1[18 + c] = ht1;
+      Hf[(2 * k) * 3 + c] = hf0; Hf[(2 * k + 1) * 3 + c] = hf1;
+    }
+    if (v.cfg.estimate_td) { r0[21] = obs[(size_t)ws * 4 + 2]; r1[21] = obs[(size_t)ws * 4 + 3]; }
+    rr[2 * k] = obs[(size_t)ws * 4 + 0] - p_c.x / p_c.z;
+    rr[2 * k + 1] = obs[(size_t)ws * 4 + 1] - p_c.y / p_c.z;
+  }
+  __syncwarp();
+  // nonzero column list: 15..21 and the pose blocks of the used window slots
+  const int nz = 7 + 6 * m;
+  auto nzcol = [&](int j) { if (j < 7) return 15 + j; const int q = j - 7; return BE_LEG + 6 * nth_set_bit(um, q / 6) + (q % 6); };
+  // ---- three Householder reflections on H_f, applied to the nonzero columns of H and to r
+  for (int k = 0; k < 3; ++k) {
+    double nrm = 0.0;
+    for (int i = k + lane; i < nrows; i += 32) { const double x = Hf[i * 3 + k]; nrm += x * x; }
+    nrm = sqrt(warp_sum_d(nrm));
+    const double x0 = Hf[k * 3 + k];
+    const double alpha = x0 >= 0 ? -nrm : nrm;
+    for (int i = k + lane; i < nrows; i += 32) vv[i] = Hf[i * 3 + k] - (i == k ? alpha : 0.0);
+    __syncwarp();
+    double vtv = 0.0;
+    for (int i = k + lane; i < nrows; i += 32) vtv += vv[i] * vv[i];
+    vtv = warp_sum_d(vtv);
+    if (vtv > 0.0) {
+      const double beta = 2.0 / vtv;
+      // remaining H_f columns (sequential per column, lanes over rows)
+      for (int c = k; c < 3; ++c) {
+        double dt_ = 0.0;
+        for (int i = k + lane; i < nrows; i += 32) dt_ += vv[i] * Hf[i * 3 + c];
+        dt_ = warp_sum_d(dt_) * beta;
+        for (int i = k + lane; i < nrows; i += 32) Hf[i * 3 + c] -= dt_ * vv[i];
+      }
+      // H columns: lanes over nonzero columns
+      for (int j = lane; j < nz + 1; j += 32) {
+        if (j < nz) {
+          const int c = nzcol(j);
+          double dt_ = 0.0;
+          for (int i = k; i < nrows; ++i) dt_ += vv[i] * H[(size_t)i * LD + c];
+          dt_ *= beta;
+          for (int i = k; i < nrows; ++i) H[(size_t)i * LD + c] -= dt_ * vv[i];
+        } else {
+          double dt_ = 0.0;
+          for (int i = k; i < nrows; ++i) dt_ += vv[i] * rr[i];
+          dt_ *= beta;
+          for (int i = k; i < nrows; ++i) rr[i] -= dt_ * vv[i];
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // ---- gating test (:1865-1880) on rows 3..nrows-1
+  const int R = nrows - 3;
+  bool pass = false;
+  if (R > 0 && R < 100) {
+    const double* Hj = H + (size_t)3 * LD;
+    double* Tp = Tj + (size_t)3 * LD;
+    for (int j = lane; j < nz; j += 32) {           // T = H_nz * P[nz, nz]
+      const int c2 = nzcol(j);
+      for (int a = 0; a < R; ++a) {
+        double acc = 0.0;
+        for (int q = 0; q < nz; ++q) { const int c1 = nzcol(q); acc += Hj[(size_t)a * LD + c1] * P[(size_t)c1 * LD + c2]; }
+        Tp[(size_t)a * LD + c2] = acc;
+      }
+    }
+    __syncwarp();
+    for (int e = lane; e < R * R; e += 32) {        // S = T H^T + sigma^2 I
+      const int a = e / R, b = e - a * R;
+      double acc = (a == b) ? v.cfg.sfeat2 : 0.0;
+      for (int q = 0; q < nz; ++q) { const int c1 = nzcol(q); acc += Tp[(size_t)a * LD + c1] * Hj[(size_t)b * LD + c1]; }
+      Ssm[e] = acc;
+    }
+    __syncwarp();
+    // Cholesky S = L L^T (in place, lower), then gamma = |L^-1 r|^2
+    bool spd = true;
+    for (int j = 0; j < R; ++j) {
+      double djj = Ssm[j * R + j];
+      if (!(djj > 0.0)) { spd = false; break; }
+      djj = sqrt(djj);
+      __syncwarp();
+      if (lane == 0) Ssm[j * R + j] = djj;
+      for (int i = j + 1 + lane; i < R; i += 32) Ssm[i * R + j] /= djj;
+      __syncwarp();
+      for (int e = lane; e < (R - j - 1) * (R - j - 1); e += 32) {
+        const int a = j + 1 + e / (R - j - 1), b = j + 1 + e % (R - j - 1);
+        if (b <= a) Ssm[a * R + b] -= Ssm[a * R + j] * Ssm[b * R + j];
+      }
+      __syncwarp();
+    }
+    if (spd) {
+      if (lane == 0) {
+        double gamma = 0.0;
+        for (int i = 0; i < R; ++i) {
+          double x = rr[3 + i];
+          for (int q = 0; q < i; ++q) x -= Ssm[i * R + q] * vv[q];
+          x /= Ssm[i * R + i];
+          vv[i] = x;
+          gamma += x * x;
+        }
+        vv[0] = gamma;
+      }
+      __syncwarp();
+      const double gamma = vv[0];
+      pass = gamma < c_chi2[R];
+    }
+  }
+  if (lane == 0) v.be.ft_accept[fi] = pass ? R : 0;
+}
+
+// ====================================================================== stacking (column-major Hs)
+__global__ void __launch_bounds__(512) be_stack_kernel(BeView v) {
+  __shared__ int part[512];
+  __shared__ int s_total;
+  const int s = blockIdx.x, tid = threadIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK]) return;
+  const int T = v.be.T, LD = v.be.LD, RMAX = v.be.RMAX;
+  const int per = (T + 511) / 512;
+  int loc = 0;
+  for (int k = 0; k < per; ++k) { const int i = tid * per + k; if (i < T) loc += v.be.ft_accept[(size_t)s * T + i]; }
+  part[tid] = loc;
+  __syncthreads();
+  for (int o = 1; o < 512; o <<= 1) { int x = tid >= o ? part[tid - o] : 0; __syncthreads(); part[tid] += x; __syncthreads(); }
+  if (tid == 511) { s_total = part[511]; }
+  __syncthreads();
+  int total = s_total;
+  if (total > RMAX) { if (tid == 0) atomicExch(&ic[I_ERR], 4); total = RMAX; }
+  // per-feature offsets into ft_rowofs is still needed below -> reuse ft_nrows to hold the stack offset
+  int run = part[tid] - loc;
+  for (int k = 0; k < per; ++k) {
+    const int i = tid * per + k;
+    if (i < T) { const int a = v.be.ft_accept[(size_t)s * T + i]; v.be.ft_nrows[(size_t)s * T + i] = run; run += a; }
+  }
+  __syncthreads();
+  const int d = ic[I_DIM];
+  double* Hs = v.be.Hs + (size_t)s * LD * RMAX;
+  double* rs = v.be.rs + (size_t)s * RMAX;
+  // copy: one warp per accepted feature row block
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int i = warp; i < T; i += 16) {
+    const int a = v.be.ft_accept[(size_t)s * T + i];
+    if (!a) continue;
+    const int dst = v.be.ft_nrows[(size_t)s * T + i];
+    if (dst + a > RMAX) continue;
+    const int src = v.be.ft_rowofs[(size_t)s * T + i] + 3;
+    const double* H = v.be.Hraw + ((size_t)s * v.be.RAWMAX + src) * LD;
+    const double* rr = v.be.rraw + (size_t)s * v.be.RAWMAX + src;
+    for (int e = lane; e < a * d; e += 32) {
+      const int row = e / d, col = e - row * d;
+      Hs[(size_t)col * RMAX + dst + row] = H[(size_t)row * LD + col];
+    }
+    for (int e = lane; e < a; e += 32) rs[dst + e] = rr[e];
+  }
+  if (tid == 0) { ic[I_ROWS] = total; ic[I_R] = total; }
+}
+
+// ====================================================================== thin QR compression (Householder)
+// Only when rows > cols (:1430, :2209).  Column-major Hs, one CTA per sequence.
+__global__ void __launch_bounds__(512) be_qr_kernel(BeView v) {
+  extern __shared__ double qsm[];      // reflector [RMAX]
+  __shared__ double red[16];
+  __shared__ double s_alpha, s_beta;
+  const int s = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK]) return;
+  const int R = ic[I_ROWS], c = ic[I_DIM];
+  if (R <= c || R == 0) return;
+  const int RMAX = v.be.RMAX, LD = v.be.LD;
+  double* Hs = v.be.Hs + (size_t)s * LD * RMAX;
+  double* rs = v.be.rs + (size_t)s * RMAX;
+  for (int j = 0; j < c; ++j) {
+    double* cj = Hs + (size_t)j * RMAX;
+    double part = 0.0;
+    for (int i = j + tid; i < R; i += 512) { const double x = cj[i]; part += x * x; }
+    part = warp_sum_d(part);
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+      double n2 = 0.0;
+      for (int w = 0; w < 16; ++w) n2 += red[w];
+      const double nrm = sqrt(n2);
+      const double x0 = cj[j];
+      const double alpha = x0 >= 0 ? -nrm : nrm;
+      const double v0 = x0 - alpha;
+      const double vtv = n2 - x0 * x0 + v0 * v0;
+      s_alpha = alpha;
+      s_beta = vtv > 0.0 ? 2.0 / vtv : 0.0;
+    }
+    __syncthreads();
+    const double alpha = s_alpha, beta = s_beta;
+    for (int i = j + tid; i < R; i += 512) qsm[i] = cj[i] - (i == j ? alpha : 0.0);
+    __syncthreads();
+    if (beta != 0.0) {
+      // each warp owns columns j+1+warp, j+1+warp+16, ... and (column index c) the residual vector
+      for (int k = j + 1 + warp; k <= c; k += 16) {
+        double* ck = (k < c) ? Hs + (size_t)k * RMAX : rs;
+        double dt_ = 0.0;
+        for (int i = j + lane; i < R; i += 32) dt_ += qsm[i] * ck[i];
+        dt_ = warp_sum_d(dt_) * beta;
+        for (int i = j + lane; i < R; i += 32) ck[i] -= dt_ * qsm[i];
+      }
+    }
+    __syncthreads();
+    for (int i = j + tid; i < R; i += 512) cj[i] = (i == j) ? alpha : 0.0;
+    __syncthreads();
+  }
+  if (tid == 0) ic[I_R] = c;
+}
+
+}  // namespace
+
+namespace {
+
+// ====================================================================== batched FP64 GEMM (generic strides)
+// C[M x N] = alpha * A[M x K] * B[K x N] + beta * C (+ diag on the diagonal), dims from icore.
+struct GemmArgs {
+  const double* A; size_t sA; int rsA, csA;
+  const double* B; size_t sB; int rsB, csB;
+  double* C; size_t sC; int rsC, csC;
+  const int* icore; int m_idx, n_idx, k_idx;
+  double alpha, beta, diag;
+};
+
+constexpr int GT = 64, GK = 16;
+__global__ void __launch_bounds__(256) be_gemm_kernel(GemmArgs g) {
+  __shared__ double As[GK][GT + 1], Bs[GK][GT + 1];
+  const int s = blockIdx.z;
+  const int* ic = g.icore + (size_t)s * BE_ICORE;
+  if (!ic[I_OK]) return;
+  const int M = ic[g.m_idx], N = ic[g.n_idx], K = ic[g.k_idx];
+  const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+  if (m0 >= M || n0 >= N || K <= 0) return;
+  const double* A = g.A + (size_t)s * g.sA;
+  const double* B = g.B + (size_t)s * g.sB;
+  double* C = g.C + (size_t)s * g.sC;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int k0 = 0; k0 < K; k0 += GK) {
+    for (int i = tid; i < GT * GK; i += 256) {
+      int mm, kk;
+      if (g.rsA == 1) { mm = i % GT; kk = i / GT; } else { kk = i % GK; mm = i / GK; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < M && gk < K) ? A[(size_t)gm * g.rsA + (size_t)gk * g.csA] : 0.0;
+    }
+    for (int i = tid; i < GT * GK; i += 256) {
+      int nn, kk;
+      if (g.csB == 1) { nn = i % GT; kk = i / GT; } else { kk = i % GK; nn = i / GK; }
+      const int gn = n0 + nn, gk = k0 + kk;
+      Bs[kk][nn] = (gn < N && gk < K) ? B[(size_t)gk * g.rsB + (size_t)gn * g.csB] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+      if (gm < M && gn < N) {
+        double* c = C + (size_t)gm * g.rsC + (size_t)gn * g.csC;
+        double val = g.alpha * acc[i][j];
+        if (g.beta != 0.0) val += g.beta * *c;
+        if (gm == gn) val += g.diag;
+        *c = val;
+      }
+    }
+}
+
+// ====================================================================== Cholesky S = L L^T (lower, in place) + z = L^-1 r
+__global__ void __launch_bounds__(512) be_chol_kernel(BeView v) {
+  extern __shared__ double csm[];   // column cache [LD]
+  const int s = blockIdx.x, tid = threadIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK]) return;
+  const int r = ic[I_R];
+  if (r <= 0) return;
+  const int LD = v.be.LD;
+  double* S = v.be.Sm + (size_t)s * LD * LD;
+  for (int j = 0; j < r; ++j) {
+    const double djj = sqrt(S[(size_t)j * LD + j]);
+    __syncthreads();
+    for (int i = j + tid; i < r; i += 512) {
+      const double x = (i == j) ? djj : S[(size_t)i * LD + j] / djj;
+      S[(size_t)i * LD + j] = x;
+      csm[i] = x;
+    }
+    __syncthreads();
+    const int n = r - j - 1;
+    for (int e = tid; e < n * n; e += 512) {
+      const int a = j + 1 + e / n, b = j + 1 + e % n;
+      if (b <= a) S[(size_t)a * LD + b] -= csm[a] * csm[b];
+    }
+    __syncthreads();
+  }
+  // z = L^-1 r  (warp 0, row oriented)
+  if (tid < 32) {
+    double* z = v.be.zvec + (size_t)s * LD;
+    const double* rs = v.be.rs + (size_t)s * v.be.RMAX;
+    for (int i = 0; i < r; ++i) {
+      double part = 0.0;
+      for (int q = tid; q < i; q += 32) part += S[(size_t)i * LD + q] * z[q];
+      part = warp_sum_d(part);
+      if (tid == 0) z[i] = (rs[i] - part) / S[(size_t)i * LD + i];
+      __syncwarp();
+    }
+  }
+}
+
+// ====================================================================== Y = L^-1 T (in place on Tm), 64 columns per CTA
+__global__ void __launch_bounds__(64) be_trsm_kernel(BeView v) {
+  __shared__ double Lt[32][33];
+  const int s = blockIdx.y, tid = threadIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK]) return;
+  const int r = ic[I_R], d = ic[I_DIM];
+  if (r <= 0) return;
+  const int c = blockIdx.x * 64 + tid;
+  if (blockIdx.x * 64 >= d) return;
+  const bool act = c < d;
+  const int LD = v.be.LD;
+  const double* L = v.be.Sm + (size_t)s * LD * LD;
+  double* Tm = v.be.Tm + (size_t)s * v.be.RAWMAX * LD;
+  const int nb = (r + 31) / 32;
+  for (int ib = 0; ib < nb; ++ib) {
+    const int i0 = ib * 32;
+    for (int e = tid; e < 32 * 32; e += 64) {
+      const int a = e / 32, b = e % 32;
+      Lt[a][b] = (i0 + a < r && i0 + b < r) ? L[(size_t)(i0 + a) * LD + i0 + b] : ((a == b) ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    double y[32];
+    if (act) {
+#pragma unroll
+      for (int a = 0; a < 32; ++a) y[a] = (i0 + a < r) ? Tm[(size_t)(i0 + a) * LD + c] : 0.0;
+#pragma unroll
+      for (int a = 0; a < 32; ++a) {
+        double x = y[a];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) if (q < a) x -= Lt[a][q] * y[q];
+        y[a] = x / Lt[a][a];
+      }
+#pragma unroll
+      for (int a = 0; a < 32; ++a) if (i0 + a < r) Tm[(size_t)(i0 + a) * LD + c] = y[a];
+    }
+    for (int jb = ib + 1; jb < nb; ++jb) {
+      const int j0 = jb * 32;
+      __syncthreads();
+      for (int e = tid; e < 32 * 32; e += 64) {
+        const int a = e / 32, b = e % 32;
+        Lt[a][b] = (j0 + a < r && i0 + b < r) ? L[(size_t)(j0 + a) * LD + i0 + b] : 0.0;
+      }
+      __syncthreads();
+      if (act) {
+#pragma unroll 4
+        for (int a = 0; a < 32; ++a) {
+          if (j0 + a >= r) break;
+          double x = 0.0;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) x += Lt[a][q] * y[q];
+          Tm[(size_t)(j0 + a) * LD + c] -= x;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ====================================================================== dx = Y^T z, state correction (:1476-1534, :1692-1750)
+__global__ void __launch_bounds__(256) be_correct_kernel(BeView v) {
+  const int s = blockIdx.x, tid = threadIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK]) return;
+  const int r = ic[I_R], d = ic[I_DIM];
+  if (r <= 0) return;
+  const int LD = v.be.LD;
+  const double* Y = v.be.Tm + (size_t)s * v.be.RAWMAX * LD;
+  const double* z = v.be.zvec + (size_t)s * LD;
+  double* dx = v.be.dx + (size_t)s * LD;
+  for (int c = tid; c < d; c += blockDim.x) {
+    double acc = 0.0;
+    for (int i = 0; i < r; ++i) acc += Y[(size_t)i * LD + c] * z[i];
+    dx[c] = acc;
+  }
+  __syncthreads();
+  double* core = core_of(v, s);
+  if (tid == 0) {
+    double dq[4], qn[4];
+    small_angle_quat(v3(dx[0], dx[1], dx[2]), dq);
+    quat_mul(dq, core + C_Q, qn);
+    for (int i = 0; i < 4; ++i) core[C_Q + i] = qn[i];
+    for (int i = 0; i < 3; ++i) { core[C_V + i] += dx[3 + i]; core[C_P + i] += dx[6 + i]; core[C_BG + i] += dx[9 + i]; core[C_BA + i] += dx[12 + i]; }
+    small_angle_quat(v3(dx[15], dx[16], dx[17]), dq);
+    const M3 Rn = m3_mul(m3_load(core + C_RIC), m3_t(quat_to_rot(dq)));
+    m3_store(core + C_RIC, Rn);
+    for (int i = 0; i < 3; ++i) core[C_TCI + i] += dx[18 + i];
+    core[C_TD] += dx[21];
+    ic[I_UPDATES] += 1;
+  }
+  __syncthreads();
+  const int n_win = ic[I_NWIN];
+  const M3 R_c2b = m3_t(m3_load(core + C_RIC));
+  const V3 t_c_b = ld3(core + C_TCI);
+  for (int i = tid; i < n_win; i += blockDim.x) {
+    double* w = win_of(v, s, i);
+    const double* da = dx + BE_LEG + 6 * i;
+    double dq[4], qn[4];
+    small_angle_quat(v3(da[0], da[1], da[2]), dq);
+    quat_mul(dq, w + W_Q, qn);
+    for (int k = 0; k < 4; ++k) w[W_Q + k] = qn[k];
+    for (int k = 0; k < 3; ++k) w[W_P + k] += da[3 + k];
+    const M3 R_b2w = quat_to_rot(w + W_Q);
+    rot_to_quat(m3_mul(R_b2w, R_c2b), w + W_QCAM);
+    st3(w + W_PCAM, ld3(w + W_P) + m3_vec(R_b2w, t_c_b));
+  }
+}
+
+// erase processed / invalid features (:2007-2009, :2248-2253)
+__global__ void be_apply_actions_kernel(BeView v) {
+  const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK] || i >= v.be.T) return;
+  const size_t fi = (size_t)s * v.be.T + i;
+  if (v.be.ft_action[fi] != 0) { v.be.ft_flags[fi] = 0; v.be.ft_mask[fi] = 0; v.be.ft_action[fi] = 0; }
+}
+
+// ====================================================================== pruning
+// findRedundantImuStates (:2259-2307) -> window slots to drop
+__global__ void be_prune_select_kernel(BeView v) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= v.be.S) return;
+  int* ic = icore_of(v, s);
+  ic[I_DO_PRUNE] = 0; ic[I_NRM] = 0;
+  if (!ic[I_OK]) return;
+  const int n = ic[I_NWIN];
+  if (ic[I_ZUPT]) return;                               // ZUPT branch (:2321-2325) is a "next" row; flagged elsewhere
+  if (n < v.cfg.sw_size) return;
+  const double* core = core_of(v, s);
+  int key = n - 4, st = key + 1, first = 0;
+  const double* wk = win_of(v, s, key);
+  const M3 key_R = quat_to_rot(wk + W_QCAM);
+  const V3 key_p = ld3(wk + W_PCAM);
+  int rm[2];
+  for (int k = 0; k < 2; ++k) {
+    const double* w = win_of(v, s, st);
+    const M3 Rr = m3_t(quat_to_rot(w + W_QCAM));
+    const double dist = norm(ld3(w + W_PCAM) - key_p);
+    double q[4];
+    rot_to_quat(m3_mul(Rr, key_R), q);
+    const double nv = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    const double angle = 2.0 * atan2(nv, fabs(q[3]));
+    if (angle < v.cfg.rot_thr && dist < v.cfg.trans_thr && core[C_TRACK_RATE] > v.cfg.track_thr) { rm[k] = st; ++st; }
+    else { rm[k] = first; ++first; st -= 2; }
+  }
+  if (rm[0] > rm[1]) { const int t = rm[0]; rm[0] = rm[1]; rm[1] = t; }
+  ic[I_RM0] = rm[0]; ic[I_RM1] = rm[1]; ic[I_NRM] = 2; ic[I_DO_PRUNE] = 1;
+}
+
+// drop the observations of the removed states from every feature and re-pack slots (:2530-2532, :2556-2558),
+// then re-pack the window arrays (:2636-2637)
+__global__ void __launch_bounds__(256) be_prune_tables_kernel(BeView v) {
+  const int s = blockIdx.x, tid = threadIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK] || !ic[I_DO_PRUNE]) return;
+  const int T = v.be.T, Wcap = v.be.Wcap;
+  const int n = ic[I_NWIN];
+  const int r0 = ic[I_RM0], r1 = ic[I_RM1];
+  for (int i = tid; i < T; i += blockDim.x) {
+    const size_t fi = (size_t)s * T + i;
+    if (!(v.be.ft_flags[fi] & 1)) continue;
+    const unsigned long long m = v.be.ft_mask[fi];
+    unsigned long long nm = 0;
+    double* obs = v.be.ft_obs + fi * Wcap * 4;
+    int dst = 0;
+    for (int w = 0; w < n; ++w) {
+      if (w == r0 || w == r1) continue;
+      if ((m >> w) & 1) {
+        nm |= 1ull << dst;
+        if (dst != w) for (int k = 0; k < 4; ++k) obs[(size_t)dst * 4 + k] = obs[(size_t)w * 4 + k];
+      }
+      ++dst;
+    }
+    v.be.ft_mask[fi] = nm;
+  }
+  __syncthreads();
+  if (tid < BE_WIN + 1) {
+    int dst = 0;
+    for (int w = 0; w < n; ++w) {
+      if (w == r0 || w == r1) continue;
+      if (dst != w) {
+        if (tid < BE_WIN) win_of(v, s, dst)[tid] = win_of(v, s, w)[tid];
+        else v.be.win_id[(size_t)s * Wcap + dst] = v.be.win_id[(size_t)s * Wcap + w];
+      }
+      ++dst;
+    }
+  }
+}
+
+// covariance re-pack (:2563-2634): gather the kept rows/cols into Sm, then copy back
+__global__ void __launch_bounds__(256) be_prune_cov_gather_kernel(BeView v) {
+  const int s = blockIdx.y, row = blockIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK] || !ic[I_DO_PRUNE]) return;
+  const int d = ic[I_DIM], LD = v.be.LD;
+  const int nd = d - 12;
+  if (row >= nd) return;
+  const int a0 = BE_LEG + 6 * ic[I_RM0], a1 = BE_LEG + 6 * ic[I_RM1];
+  auto src = [&](int i) { int x = i; if (x >= a0) x += 6; if (x >= a1) x += 6; return x; };
+  const double* P = P_of(v, s);
+  double* Sd = v.be.Sm + (size_t)s * LD * LD;
+  const int sr = src(row);
+  for (int c = threadIdx.x; c < nd; c += blockDim.x) Sd[(size_t)row * LD + c] = P[(size_t)sr * LD + src(c)];
+}
+__global__ void __launch_bounds__(256) be_prune_cov_scatter_kernel(BeView v) {
+  const int s = blockIdx.y, row = blockIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK] || !ic[I_DO_PRUNE]) return;
+  const int d = ic[I_DIM], LD = v.be.LD;
+  const int nd = d - 12;
+  if (row >= nd) return;
+  double* P = P_of(v, s);
+  const double* Sd = v.be.Sm + (size_t)s * LD * LD;
+  for (int c = threadIdx.x; c < nd; c += blockDim.x) P[(size_t)row * LD + c] = Sd[(size_t)row * LD + c];
+}
+
+// end of processFeatures: shrink dims after pruning, FEJ switch (:414-419)
+__global__ void be_frame_end_kernel(BeView v) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= v.be.S) return;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK]) return;
+  if (ic[I_DO_PRUNE]) { ic[I_DIM] -= 12; ic[I_NWIN] -= 2; }
+  const double* core = core_of(v, s);
+  if (v.cfg.if_FEJ_config && !ic[I_FEJ] && core[C_TIME] - core[C_TAKEOFF] >= 0) ic[I_FEJ] = 1;
+}
+
+}  // namespace
+
+// ====================================================================== host side
+template <typename T>
+static int bdalloc(LvbHandle* h, T** p, size_t count) {
+  void* q = nullptr;
+  size_t bytes = count * sizeof(T);
+  if (bytes == 0) bytes = sizeof(T);
+  LVB_CUDA(cudaMalloc(&q, bytes));
+  LVB_CUDA(cudaMemsetAsync(q, 0, bytes, h->stream));
+  h->allocs.push_back(q);
+  *p = (T*)q;
+  return LVB_OK;
+}
+#define BDA(ptr, n) do { int rc_ = bdalloc(h, &(ptr), (size_t)(n)); if (rc_ != LVB_OK) return rc_; } while (0)
+#define BPIN(ptr, T, n) do { void* q_ = nullptr; LVB_CUDA(cudaHostAlloc(&q_, sizeof(T) * (size_t)(n), cudaHostAllocDefault)); memset(q_, 0, sizeof(T) * (size_t)(n)); ptr = (T*)q_; } while (0)
+
+static const char* be_unsupported_reason(const LvbConfig& c) {
+  if (c.calib_imu_instrinsic) return "calib_imu_instrinsic: 1 (IMU-intrinsic calibration, LEG_DIM 46) is not built yet";
+  if (c.max_features_in_one_grid > 0 && c.aug_grid_rows * c.aug_grid_cols != 0)
+    return "hybrid EKF-SLAM features (max_features_in_one_grid > 0) are not built yet; set it to 0 for pure MSCKF";
+  if (c.sw_size + 1 > 64) return "sw_size > 63";
+  return nullptr;
+}
+
+__global__ void be_init_kernel(BeView v, double c_ori, double c_vel, double c_pos, double c_bg, double c_ba, double c_er,
+                               double c_et, int est_ext, int est_td, double td, const double* T_cam_imu) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= v.be.S) return;
+  double* core = core_of(v, s);
+  int* ic = icore_of(v, s);
+  for (int i = 0; i < BE_CORE; ++i) core[i] = 0.0;
+  for (int i = 0; i < BE_ICORE; ++i) ic[i] = 0;
+  core[C_Q + 3] = 1.0;
+  core[C_TD] = td;
+  // R_imu_cam0 = R_file, t_cam0_imu = -R_file^T t_file (larvio.cpp:189-203)
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) core[C_RIC + r * 3 + c] = T_cam_imu[r * 4 + c];
+  for (int r = 0; r < 3; ++r) {
+    double a = 0; for (int k = 0; k < 3; ++k) a += T_cam_imu[k * 4 + r] * T_cam_imu[k * 4 + 3];
+    core[C_TCI + r] = -a;
+  }
+  ic[I_DIM] = BE_LEG;
+  double* P = P_of(v, s);
+  const int LD = v.be.LD;
+  for (int i = 0; i < BE_LEG; ++i) for (int j = 0; j < BE_LEG; ++j) P[(size_t)i * LD + j] = 0.0;
+  for (int i = 0; i < 3; ++i) {
+    P[(size_t)i * LD + i] = c_ori; P[(size_t)(3 + i) * LD + 3 + i] = c_vel; P[(size_t)(6 + i) * LD + 6 + i] = c_pos;
+    P[(size_t)(9 + i) * LD + 9 + i] = c_bg; P[(size_t)(12 + i) * LD + 12 + i] = c_ba;
+    if (est_ext) { P[(size_t)(15 + i) * LD + 15 + i] = c_er; P[(size_t)(18 + i) * LD + 18 + i] = c_et; }
+  }
+  if (est_td) P[(size_t)21 * LD + 21] = 4e-6;
+}
+
+static BeView make_beview(LvbHandle* h) {
+  BeView v;
+  v.be = *h->be;
+  const LvbConfig& c = h->cfg;
+  v.cfg.th_imu = 1.0 / (2.0 * c.imu_rate);
+  v.cfg.sg2 = c.noise_gyro * c.noise_gyro; v.cfg.sa2 = c.noise_acc * c.noise_acc;
+  v.cfg.sbg2 = c.noise_gyro_bias * c.noise_gyro_bias; v.cfg.sba2 = c.noise_acc_bias * c.noise_acc_bias;
+  v.cfg.sfeat2 = c.noise_feature * c.noise_feature;
+  v.cfg.rot_thr = c.rotation_threshold; v.cfg.trans_thr = c.translation_threshold; v.cfg.track_thr = c.tracking_rate_threshold;
+  v.cfg.feat_trans_thr = c.feature_translation_threshold; v.cfg.zupt_dis = c.zupt_max_feature_dis;
+  v.cfg.max_track_len = c.max_track_len; v.cfg.sw_size = c.sw_size; v.cfg.least_obs = c.least_observation_number;
+  v.cfg.if_FEJ_config = c.if_FEJ; v.cfg.estimate_td = c.estimate_td; v.cfg.if_ZUPT_valid = c.if_ZUPT_valid;
+  v.msg = nullptr; v.msg_n = nullptr; v.msg_t = nullptr; v.msg_valid = nullptr; v.msg_stride = 0;
+  v.P = h->be->P[0]; v.Pn = h->be->P[1];
+  return v;
+}
+
+int be_alloc(LvbHandle* h) {
+  LvbBackEnd* be = new LvbBackEnd();
+  memset(be, 0, sizeof(*be));
+  h->be = be;
+  const LvbConfig& c = h->cfg;
+  be->S = h->S; be->N = h->fe.N;
+  int sw = c.sw_size; if (sw < 5) sw = 5; if (sw > 63) sw = 63;
+  be->Wcap = sw + 1;
+  be->T = 2 * be->N;
+  be->Dmax = BE_LEG + 6 * be->Wcap;
+  be->LD = ((be->Dmax + 7) / 8) * 8;
+  be->RAWMAX = 4096; be->RMAX = 2048;
+  be->imu_cap = 64;
+  const size_t S = be->S, T = be->T, LD = be->LD;
+  BDA(be->core, S * BE_CORE); BDA(be->icore, S * BE_ICORE);
+  BDA(be->win_id, S * be->Wcap); BDA(be->win, S * be->Wcap * BE_WIN);
+  BDA(be->P[0], S * LD * LD); BDA(be->P[1], 8);
+  BDA(be->ft_id, S * T); BDA(be->ft_flags, S * T); BDA(be->ft_pos, S * T * 3); BDA(be->ft_mask, S * T);
+  BDA(be->ft_obs, S * T * be->Wcap * 4);
+  BDA(be->ft_action, S * T); BDA(be->ft_rowofs, S * T); BDA(be->ft_nrows, S * T); BDA(be->ft_accept, S * T); BDA(be->ft_usemask, S * T);
+  BDA(be->Hraw, S * (size_t)be->RAWMAX * LD); BDA(be->rraw, S * (size_t)be->RAWMAX);
+  BDA(be->Hs, S * LD * (size_t)be->RMAX); BDA(be->rs, S * (size_t)be->RMAX);
+  BDA(be->Tm, S * (size_t)be->RAWMAX * LD);      // doubles as the per-feature H*P scratch of the gate
+  BDA(be->Sm, S * LD * LD); BDA(be->zvec, S * LD); BDA(be->dx, S * LD);
+  BDA(be->imu, S * be->imu_cap); BDA(be->n_imu, S);
+  BDA(be->msg_in, S * be->N); BDA(be->msg_in_n, S); BDA(be->msg_in_t, S); BDA(be->msg_in_valid, S);
+  BPIN(be->pin_imu, LvbImu, S * be->imu_cap); BPIN(be->pin_n_imu, int, S); BPIN(be->pin_icore, int, S * BE_ICORE);
+  BPIN(be->pin_feat, LvbFeature, S * be->N); BPIN(be->pin_feat_n, int, S); BPIN(be->pin_feat_t, double, S); BPIN(be->pin_valid, uint8_t, S);
+  double* d_T = nullptr;
+  BDA(d_T, 16);
+  LVB_CUDA(cudaMemcpyAsync(d_T, c.T_cam_imu, sizeof(double) * 16, cudaMemcpyHostToDevice, h->stream));
+  BeView v = make_beview(h);
+  be_init_kernel<<<(be->S + 63) / 64, 64, 0, h->stream>>>(v, c.cov_orientation, c.cov_velocity, c.cov_position, c.cov_gyro_bias,
+                                                          c.cov_acc_bias, c.cov_extrin_rot, c.cov_extrin_trans, c.estimate_extrin,
+                                                          c.estimate_td, c.td, d_T);
+  LVB_LAUNCH_CHECK(h);
+  // dynamic shared memory opt-ins
+  const int fsm_bytes = (int)sizeof(double) * (6 * be->Wcap + 8 + 4 * be->Wcap * be->Wcap + 2 * be->Wcap);
+  LVB_CUDA(cudaFuncSetAttribute(be_feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm_bytes));
+  return LVB_OK;
+}
+
+void be_free(LvbHandle* h) {
+  if (!h->be) return;
+  LvbBackEnd* be = h->be;
+  void* pins[] = {be->pin_imu, be->pin_n_imu, be->pin_icore, be->pin_feat, be->pin_feat_n, be->pin_feat_t, be->pin_valid};
+  for (void* p : pins) if (p) cudaFreeHost(p);
+  delete be;
+  h->be = nullptr;
+}
+
+static int launch_gemm(LvbHandle* h, const GemmArgs& g) {
+  LvbBackEnd* be = h->be;
+  const int tiles = (be->Dmax + GT - 1) / GT;
+  be_gemm_kernel<<<dim3(tiles, tiles, be->S), 256, 0, h->stream>>>(g);
+  LVB_LAUNCH_CHECK(h);
+  return LVB_OK;
+}
+
+// compression + EKF update on the stacked system currently in Hs/rs
+static int be_update(LvbHandle* h, BeView& v) {
+  LvbBackEnd* be = h->be;
+  cudaStream_t st = h->stream;
+  const size_t LD = be->LD;
+  be_qr_kernel<<<be->S, 512, sizeof(double) * be->RMAX, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  GemmArgs g;
+  g.icore = be->icore;
+  // T = H P
+  g.A = be->Hs; g.sA = LD * be->RMAX; g.rsA = 1; g.csA = be->RMAX;
+  g.B = v.P; g.sB = LD * LD; g.rsB = (int)LD; g.csB = 1;
+  g.C = be->Tm; g.sC = (size_t)be->RAWMAX * LD; g.rsC = (int)LD; g.csC = 1;
+  g.m_idx = I_R; g.n_idx = I_DIM; g.k_idx = I_DIM; g.alpha = 1.0; g.beta = 0.0; g.diag = 0.0;
+  RC(launch_gemm(h, g));
+  // S = T H^T + sigma^2 I
+  g.A = be->Tm; g.sA = (size_t)be->RAWMAX * LD; g.rsA = (int)LD; g.csA = 1;
+  g.B = be->Hs; g.sB = LD * be->RMAX; g.rsB = be->RMAX; g.csB = 1;
+  g.C = be->Sm; g.sC = LD * LD; g.rsC = (int)LD; g.csC = 1;
+  g.m_idx = I_R; g.n_idx = I_R; g.k_idx = I_DIM; g.alpha = 1.0; g.beta = 0.0; g.diag = v.cfg.sfeat2;
+  RC(launch_gemm(h, g));
+  be_chol_kernel<<<be->S, 512, sizeof(double) * LD, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  BeView vt = v;
+  be_trsm_kernel<<<dim3((be->Dmax + 63) / 64, be->S), 64, 0, st>>>(vt);
+  LVB_LAUNCH_CHECK(h);
+  be_correct_kernel<<<be->S, 256, 0, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  // P -= Y^T Y
+  g.A = be->Tm; g.sA = (size_t)be->RAWMAX * LD; g.rsA = 1; g.csA = (int)LD;
+  g.B = be->Tm; g.sB = (size_t)be->RAWMAX * LD; g.rsB = (int)LD; g.csB = 1;
+  g.C = v.P; g.sC = LD * LD; g.rsC = (int)LD; g.csC = 1;
+  g.m_idx = I_DIM; g.n_idx = I_DIM; g.k_idx = I_R; g.alpha = -1.0; g.beta = 1.0; g.diag = 0.0;
+  RC(launch_gemm(h, g));
+  return LVB_OK;
+}
+
+static int be_measurement_pass(LvbHandle* h, BeView& v, int mode) {
+  LvbBackEnd* be = h->be;
+  cudaStream_t st = h->stream;
+  be_classify_kernel<<<dim3((be->T + 3) / 4, be->S), 128, 0, st>>>(v, mode);
+  LVB_LAUNCH_CHECK(h);
+  be_scan_rows_kernel<<<be->S, 512, 0, st>>>(v, 0);
+  LVB_LAUNCH_CHECK(h);
+  const int fsm_bytes = (int)sizeof(double) * (6 * be->Wcap + 8 + 4 * be->Wcap * be->Wcap + 2 * be->Wcap);
+  be_feature_kernel<<<dim3(be->T, be->S), 32, fsm_bytes, st>>>(v, be->Tm);
+  LVB_LAUNCH_CHECK(h);
+  be_stack_kernel<<<be->S, 512, 0, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  return be_update(h, v);
+}
+
+// msg arrays are device pointers. imu/n_imu: caller's host buffers (mutated).
+int be_process(LvbHandle* h, const LvbFeature* d_msg, const int* d_msg_n, const double* d_msg_t, const uint8_t* d_valid,
+               int msg_stride, LvbImu* imu, int* n_imu, int imu_stride, uint8_t* ok_out) {
+  LvbBackEnd* be = h->be;
+  if (const char* why = be_unsupported_reason(h->cfg)) return lvb_set_err(LVB_E_UNSUPPORTED, "%s", why);
+  cudaStream_t st = h->stream;
+  const int S = be->S;
+  for (int s = 0; s < S; ++s) {
+    int n = n_imu[s];
+    if (n > be->imu_cap) n = be->imu_cap;        // only the oldest samples can be consumed this frame
+    be->pin_n_imu[s] = n;
+    memcpy(be->pin_imu + (size_t)s * be->imu_cap, imu + (size_t)s * imu_stride, sizeof(LvbImu) * n);
+  }
+  LVB_CUDA(cudaMemcpyAsync(be->imu, be->pin_imu, sizeof(LvbImu) * (size_t)S * be->imu_cap, cudaMemcpyHostToDevice, st));
+  LVB_CUDA(cudaMemcpyAsync(be->n_imu, be->pin_n_imu, sizeof(int) * S, cudaMemcpyHostToDevice, st));
+  BeView v = make_beview(h);
+  v.msg = d_msg; v.msg_n = d_msg_n; v.msg_t = d_msg_t; v.msg_valid = d_valid; v.msg_stride = msg_stride;
+  be_propagate_kernel<<<S, 256, 0, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  const int nthr = be->N <= 256 ? 256 : 512;
+  if (be->N > 512) return lvb_set_err(LVB_E_UNSUPPORTED, "max_features_num > 512");
+  be_add_obs_kernel<<<S, nthr, sizeof(unsigned long long) * be->T, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  be_augment_kernel<<<S, 256, 0, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  RC(be_measurement_pass(h, v, 0));                  // removeLostFeatures
+  be_apply_actions_kernel<<<dim3((be->T + 127) / 128, S), 128, 0, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  be_prune_select_kernel<<<(S + 63) / 64, 64, 0, st>>>(v);   // pruneImuStateBuffer
+  LVB_LAUNCH_CHECK(h);
+  RC(be_measurement_pass(h, v, 1));
+  be_prune_tables_kernel<<<S, 256, 0, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  be_prune_cov_gather_kernel<<<dim3(be->Dmax, S), 256, 0, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  be_prune_cov_scatter_kernel<<<dim3(be->Dmax, S), 256, 0, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  be_frame_end_kernel<<<(S + 63) / 64, 64, 0, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  LVB_CUDA(cudaMemcpyAsync(be->pin_icore, be->icore, sizeof(int) * (size_t)S * BE_ICORE, cudaMemcpyDeviceToHost, st));
+  LVB_CUDA(cudaStreamSynchronize(st));
+  int err = 0, zupt = 0;
+  for (int s = 0; s < S; ++s) {
+    const int* ic = be->pin_icore + (size_t)s * BE_ICORE;
+    if (ok_out) ok_out[s] = (uint8_t)ic[I_OK];
+    if (ic[I_OK]) {
+      const int used = ic[I_CONSUMED];
+      if (used > 0) {                                  // larvio.cpp:510-512: erase consumed samples in place
+        LvbImu* b = imu + (size_t)s * imu_stride;
+        memmove(b, b + used, sizeof(LvbImu) * (n_imu[s] - used));
+        n_imu[s] -= used;
+      }
+      if (ic[I_ERR]) err = ic[I_ERR];
+      if (ic[I_ZUPT]) zupt = 1;
+    }
+  }
+  if (err) return lvb_set_err(LVB_E_CAPACITY, "back-end capacity exceeded (code %d: 1 feature table, 2 window, 3 raw rows, 4 stacked rows)", err);
+  if (zupt) return lvb_set_err(LVB_E_UNSUPPORTED, "static scene detected: the ZUPT update (larvio.cpp:2791-2962) is not built yet");
+  return LVB_OK;
+}
+
+extern "C" int lvb_process_features(LvbHandle* h, const uint8_t* valid, const double* t_msg, const LvbFeature* feat,
+                                    const int* n_feat, int feat_stride, LvbImu* imu, int* n_imu, int imu_stride,
+                                    uint8_t* ok) {
+  if (!h || !valid || !t_msg || !feat || !n_feat || !imu || !n_imu) return lvb_set_err(LVB_E_ARG, "lvb_process_features: null argument");
+  LVB_CUDA(cudaSetDevice(h->device));
+  LvbBackEnd* be = h->be;
+  const int S = be->S, N = be->N;
+  LVB_CUDA(cudaStreamSynchronize(h->stream));
+  for (int s = 0; s < S; ++s) {
+    int n = valid[s] ? n_feat[s] : 0;
+    if (n > N) return lvb_set_err(LVB_E_CAPACITY, "feature message of %d entries exceeds capacity %d", n, N);
+    be->pin_feat_n[s] = n; be->pin_feat_t[s] = t_msg[s]; be->pin_valid[s] = valid[s];
+    if (n) memcpy(be->pin_feat + (size_t)s * N, feat + (size_t)s * feat_stride, sizeof(LvbFeature) * n);
+  }
+  LVB_CUDA(cudaMemcpyAsync(be->msg_in, be->pin_feat, sizeof(LvbFeature) * (size_t)S * N, cudaMemcpyHostToDevice, h->stream));
+  LVB_CUDA(cudaMemcpyAsync(be->msg_in_n, be->pin_feat_n, sizeof(int) * S, cudaMemcpyHostToDevice, h->stream));
+  LVB_CUDA(cudaMemcpyAsync(be->msg_in_t, be->pin_feat_t, sizeof(double) * S, cudaMemcpyHostToDevice, h->stream));
+  LVB_CUDA(cudaMemcpyAsync(be->msg_in_valid, be->pin_valid, S, cudaMemcpyHostToDevice, h->stream));
+  return be_process(h, be->msg_in, be->msg_in_n, be->msg_in_t, be->msg_in_valid, N, imu, n_imu, imu_stride, ok);
+}
+
+extern "C" int lvb_step(LvbHandle* h, const uint8_t* images, int images_on_device, const double* t_img, LvbImu* imu,
+                        int* n_imu, int imu_stride, uint8_t* published) {
+  if (!h || !images || !t_img || !imu || !n_imu) return lvb_set_err(LVB_E_ARG, "lvb_step: null argument");
+  LVB_CUDA(cudaSetDevice(h->device));
+  RC(fe_process(h, images, images_on_device, t_img, imu, n_imu, imu_stride));
+  LvbFrontEnd& fe = h->fe;
+  // the message stays in HBM: fe.msg / msg_n / msg_t / has_msg feed processFeatures directly
+  return be_process(h, fe.msg, fe.msg_n, fe.msg_t, fe.has_msg, fe.N, imu, n_imu, imu_stride, published);
+}
+
+__global__ void be_set_state_kernel(BeView v, int s, double t, const double* vals /*q4 p3 v3 bg3 ba3*/) {
+  double* core = core_of(v, s);
+  int* ic = icore_of(v, s);
+  core[C_TIME] = t;
+  for (int i = 0; i < 4; ++i) core[C_Q + i] = vals[i];
+  for (int i = 0; i < 3; ++i) {
+    core[C_P + i] = vals[4 + i]; core[C_V + i] = vals[7 + i]; core[C_BG + i] = vals[10 + i]; core[C_BA + i] = vals[13 + i];
+    core[C_FNOW_P + i] = vals[4 + i]; core[C_FNOW_V + i] = vals[7 + i];
+  }
+  core[C_TAKEOFF] = t;
+  ic[I_GRAVITY] = 1;
+}
+
+extern "C" int lvb_set_initial_state(LvbHandle* h, int seq, double t, const double* q_xyzw, const double* p,
+                                     const double* vel, const double* bg, const double* ba) {
+  if (!h || seq < 0 || seq >= h->S || !q_xyzw || !p || !vel || !bg || !ba) return lvb_set_err(LVB_E_ARG, "lvb_set_initial_state: bad argument");
+  LVB_CUDA(cudaSetDevice(h->device));
+  double vals[16];
+  for (int i = 0; i < 4; ++i) vals[i] = q_xyzw[i];
+  for (int i = 0; i < 3; ++i) { vals[4 + i] = p[i]; vals[7 + i] = vel[i]; vals[10 + i] = bg[i]; vals[13 + i] = ba[i]; }
+  double* d = h->be->dx;   // scratch
+  LVB_CUDA(cudaMemcpyAsync(d, vals, sizeof(vals), cudaMemcpyHostToDevice, h->stream));
+  BeView v = make_beview(h);
+  be_set_state_kernel<<<1, 1, 0, h->stream>>>(v, seq, t, d);
+  LVB_LAUNCH_CHECK(h);
+  LVB_CUDA(cudaStreamSynchronize(h->stream));
+  return LVB_OK;
+}
+
+extern "C" int lvb_get_states(LvbHandle* h, double* out) {
+  if (!h || !out) return lvb_set_err(LVB_E_ARG, "lvb_get_states: null argument");
+  LVB_CUDA(cudaSetDevice(h->device));
+  std::vector<double> core((size_t)h->S * BE_CORE);
+  LVB_CUDA(cudaMemcpyAsync(core.data(), h->be->core, sizeof(double) * core.size(), cudaMemcpyDeviceToHost, h->stream));
+  LVB_CUDA(cudaStreamSynchronize(h->stream));
+  for (int s = 0; s < h->S; ++s) {
+    const double* c = core.data() + (size_t)s * BE_CORE;
+    double* o = out + (size_t)s * 17;
+    o[0] = c[C_TIME];
+    for (int i = 0; i < 4; ++i) o[1 + i] = c[C_Q + i];
+    for (int i = 0; i < 3; ++i) { o[5 + i] = c[C_P + i]; o[8 + i] = c[C_V + i]; o[11 + i] = c[C_BG + i]; o[14 + i] = c[C_BA + i]; }
+  }
+  return LVB_OK;
+}
+
+extern "C" int lvb_get_covariance(LvbHandle* h, int seq, double* P, int cap_dim, int* dim) {
+  if (!h || seq < 0 || seq >= h->S || !P || !dim) return lvb_set_err(LVB_E_ARG, "lvb_get_covariance: bad argument");
+  LVB_CUDA(cudaSetDevice(h->device));
+  LvbBackEnd* be = h->be;
+  int ic[BE_ICORE];
+  LVB_CUDA(cudaMemcpyAsync(ic, be->icore + (size_t)seq * BE_ICORE, sizeof(ic), cudaMemcpyDeviceToHost, h->stream));
+  LVB_CUDA(cudaStreamSynchronize(h->stream));
+  const int d = ic[I_DIM];
+  *dim = d;
+  if (d > cap_dim) return lvb_set_err(LVB_E_CAPACITY, "covariance is %d x %d, caller capacity %d", d, d, cap_dim);
+  std::vector<double> tmp((size_t)be->LD * be->LD);
+  LVB_CUDA(cudaMemcpyAsync(tmp.data(), be->P[0] + (size_t)seq * be->LD * be->LD, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, h->stream));
+  LVB_CUDA(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) P[(size_t)i * d + j] = tmp[(size_t)i * be->LD + j];
+  return LVB_OK;
+}
+
+extern "C" int lvb_get_state(LvbHandle* h, int seq, double* t, double* q, double* p, double* vel, double* bg, double* ba,
+                             double* P_pose36, double* P_vel9) {
+  if (!h || seq < 0 || seq >= h->S) return lvb_set_err(LVB_E_ARG, "lvb_get_state: bad argument");
+  LVB_CUDA(cudaSetDevice(h->device));
+  LvbBackEnd* be = h->be;
+  double c[BE_CORE];
+  LVB_CUDA(cudaMemcpyAsync(c, be->core + (size_t)seq * BE_CORE, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  std::vector<double> rows((size_t)9 * be->LD);
+  LVB_CUDA(cudaMemcpyAsync(rows.data(), be->P[0] + (size_t)seq * be->LD * be->LD, sizeof(double) * rows.size(), cudaMemcpyDeviceToHost, h->stream));
+  LVB_CUDA(cudaStreamSynchronize(h->stream));
+  if (t) *t = c[C_TIME];
+  for (int i = 0; i < 4; ++i) if (q) q[i] = c[C_Q + i];
+  for (int i = 0; i < 3; ++i) { if (p) p[i] = c[C_P + i]; if (vel) vel[i] = c[C_V + i]; if (bg) bg[i] = c[C_BG + i]; if (ba) ba[i] = c[C_BA + i]; }
+  // getPpose (larvio.cpp: rows/cols {0-2, 6-8}), getPvel (3-5)
+  const int sel[6] = {0, 1, 2, 6, 7, 8};
+  if (P_pose36) for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) P_pose36[i * 6 + j] = rows[(size_t)sel[i] * be->LD + sel[j]];
+  if (P_vel9) for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) P_vel9[i * 3 + j] = rows[(size_t)(3 + i) * be->LD + 3 + j];
+  return LVB_OK;
+}
+
+extern "C" int lvb_get_window(LvbHandle* h, int seq, double* qp, int cap, int* n) {
+  if (!h || seq < 0 || seq >= h->S || !qp || !n) return lvb_set_err(LVB_E_ARG, "lvb_get_window: bad argument");
+  LVB_CUDA(cudaSetDevice(h->device));
+  LvbBackEnd* be = h->be;
+  int ic[BE_ICORE];
+  std::vector<double> w((size_t)be->Wcap * BE_WIN);
+  LVB_CUDA(cudaMemcpyAsync(ic, be->icore + (size_t)seq * BE_ICORE, sizeof(ic), cudaMemcpyDeviceToHost, h->stream));
+  LVB_CUDA(cudaMemcpyAsync(w.data(), be->win + (size_t)seq * be->Wcap * BE_WIN, sizeof(double) * w.size(), cudaMemcpyDeviceToHost, h->stream));
+  LVB_CUDA(cudaStreamSynchronize(h->stream));
+  const int k = ic[I_NWIN] < cap ? ic[I_NWIN] : cap;
+  for (int i = 0; i < k; ++i) {
+    for (int j = 0; j < 4; ++j) qp[i * 7 + j] = w[(size_t)i * BE_WIN + W_Q + j];
+    for (int j = 0; j < 3; ++j) qp[i * 7 + 4 + j] = w[(size_t)i * BE_WIN + W_P + j];
+  }
+  *n = k;
+  return LVB_OK;
+}

@@ -1,6 +1,48 @@
-// Back-end (LarVio) device state — see be_pipeline.cu.
+// Back-end (LarVio) device state: StateServer + MapServer (larvio.h:99-142,199; imu_state.h:29-148;
+// feature.hpp:34-250) as fixed-capacity SoA tables, one slice per sequence, FP64 throughout.
 #pragma once
 #include "lvb_internal.h"
+
+#define BE_LEG 22            // legacy error-state size without IMU-intrinsic calibration (larvio.cpp:158-161)
+
+// ---- core[s][BE_CORE] doubles
+enum {
+  C_TIME = 0, C_Q = 1, C_P = 5, C_V = 8, C_BG = 11, C_BA = 14, C_RIC = 17 /*R_imu_cam0 row-major*/, C_TCI = 26,
+  C_TD = 29, C_DT = 30, C_FNOW_P = 31, C_FNOW_V = 34, C_FOLD_P = 37, C_FOLD_V = 40, C_OLD_Q = 43, C_OLD_P = 47,
+  C_OLD_V = 50, C_GYRO_OLD = 53, C_ACC_OLD = 56, C_TRACK_RATE = 59, C_TAKEOFF = 60, BE_CORE = 64
+};
+// ---- icore[s][BE_ICORE] ints
+enum {
+  I_ID = 0, I_NEXT_ID = 1, I_NWIN = 2, I_GRAVITY = 3, I_FIRST = 4, I_FEJ = 5, I_HAVE_OLD = 6, I_DIM = 7,
+  I_ZUPT = 8, I_OK = 9 /*processFeatures return of this frame*/, I_CONSUMED = 10, I_ROWS = 11 /*stacked rows*/,
+  I_R = 12 /*rows after compression*/, I_NUSED = 13, I_RAWROWS = 14, I_ERR = 15, I_RM0 = 16, I_RM1 = 17, I_NRM = 18,
+  I_DO_PRUNE = 19, I_ZUPT_EVENTS = 20, I_UPDATES = 21, BE_ICORE = 32
+};
+// ---- win[s][slot][BE_WIN] doubles (IMUState_Aug)
+enum { W_TIME = 0, W_DT = 1, W_Q = 2, W_P = 6, W_PFEJ = 9, W_RIC = 12, W_TCI = 21, W_QCAM = 24, W_PCAM = 28, BE_WIN = 32 };
+
 struct LvbBackEnd {
-  int dummy;
+  int S, N;            // sequences, message capacity per sequence
+  int Wcap;            // window capacity (sw_size + 1)
+  int T;               // feature-table capacity per sequence
+  int LD;              // leading dimension of P / row length of stacked Jacobians (>= Dmax, multiple of 8)
+  int Dmax;
+  int RAWMAX;          // raw (unprojected) Jacobian rows per sequence per pass
+  int RMAX;            // stacked (projected, gated) rows per sequence per pass
+  int imu_cap;         // IMU samples per sequence per call
+  double* core; int* icore;
+  long long* win_id; double* win;
+  double* P[2]; int pcur;                     // ping-pong covariance [S][LD][LD], row-major
+  unsigned long long* ft_id; int* ft_flags; double* ft_pos; unsigned long long* ft_mask; double* ft_obs;  // [S][T]...
+  int* ft_action; int* ft_rowofs; int* ft_nrows; int* ft_accept; unsigned long long* ft_usemask;
+  double* Hraw; double* rraw;                 // [S][RAWMAX][LD], [S][RAWMAX]
+  double* Hs; double* rs;                     // stacked, COLUMN-major [S][LD cols][RMAX rows], [S][RMAX]
+  double* Tm;                                 // H*P   [S][RMAX? -> Dmax rows][LD]   (rows <= Dmax after compression)
+  double* Sm;                                 // [S][LD][LD]
+  double* zvec; double* dx;                   // [S][LD]
+  LvbImu* imu; int* n_imu;                    // per-call IMU staging [S][imu_cap]
+  LvbFeature* msg_in; int* msg_in_n; double* msg_in_t; uint8_t* msg_in_valid;   // host-provided messages
+  double chi2[100];
+  // host pinned
+  LvbImu* pin_imu; int* pin_n_imu; int* pin_icore; LvbFeature* pin_feat; int* pin_feat_n; double* pin_feat_t; uint8_t* pin_valid;
 };
