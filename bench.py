@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the batched VIO hot path (BASELINE.json metric: batched VIO image frames/s).
+
+  python bench.py --gpus 1 --steps 40 --warmup 6            # this repo's CUDA path
+  python bench.py --impl reference --steps 40 --warmup 6     # the CPU path (oracle port) on all host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...          # one rank per GPU, sequences sharded (weak scaling)
+
+A "step" = one 752x480 image per sequence through processImage (+ processFeatures on published frames)
+for all S sequences of the rank (app/larvioMain.cpp:107-114).  Workload = BASELINE.json configs[2]:
+64 batched synthetic sequences per GPU, 200 tracks, 30-pose window, MSCKF-only.
+Prints ONE JSON line on rank 0 (contract in the task statement).
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from larvio_b200.config import Config          # noqa: E402
+from larvio_b200 import synth                  # noqa: E402
+
+W_IMG, H_IMG = 752, 480
+B0 = W_IMG * H_IMG
+
+
+def load_cfg(args):
+    return Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), max_features_in_one_grid=0,
+                       sw_size=args.window, max_features_num=args.tracks)
+
+
+# ----------------------------------------------------------------------------- data generation (fork pool)
+_GEN_CFG = None
+
+
+def _gen_one(a):
+    seq_index, n_frames = a
+    import cv2
+    cv2.setNumThreads(1)
+    return synth.make_sequence(_GEN_CFG, seq_index, n_frames)
+
+
+def generate(cfg_raw, seq_ids, n_frames, procs):
+    global _GEN_CFG
+    _GEN_CFG = cfg_raw
+    with mp.get_context("fork").Pool(min(procs, len(seq_ids))) as pool:
+        return pool.map(_gen_one, [(s, n_frames) for s in seq_ids], chunksize=1)
+
+
+# ----------------------------------------------------------------------------- CPU arm: oracle port, one worker per core
+def _cpu_worker(conn, cfg_raw, seqs):
+    import cv2
+    cv2.setNumThreads(1)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)          # one BLAS thread per worker: one sequence per core
+    except Exception:
+        pass
+    from oracle.frontend import ImageProcessorOracle
+    from oracle.backend import LarVioOracle
+    st = []
+    for sq in seqs:
+        st.append(dict(fe=ImageProcessorOracle(cfg_raw), be=LarVioOracle(cfg_raw), imu=[], k=0, seq=sq, t_fe=0.0, t_be=0.0, n_be=0))
+        st[-1]["be"].set_initial_state(sq.img_t[0], sq.gt_q[0], sq.gt_p[0], sq.gt_v[0], np.zeros(3), np.zeros(3))
+    conn.send("ready")
+    while True:
+        cmd = conn.recv()
+        if cmd[0] == "quit":
+            break
+        a, b = cmd[1], cmd[2]
+        for j in range(a, b):
+            for s in st:
+                sq = s["seq"]
+                k2 = synth.imu_window(sq, s["k"], sq.img_t[j])
+                s["imu"].extend(sq.imu[s["k"]:k2].tolist()); s["k"] = k2
+                t0 = time.perf_counter()
+                msg = s["fe"].process_image(sq.images[j], sq.img_t[j], np.array(s["imu"]).reshape(-1, 7))
+                t1 = time.perf_counter()
+                s["t_fe"] += t1 - t0
+                if msg is not None:
+                    try:
+                        s["be"].process_features(msg, s["imu"])
+                    except NotImplementedError:
+                        pass
+                    s["t_be"] += time.perf_counter() - t1; s["n_be"] += 1
+        conn.send(("done", sum(s["t_fe"] for s in st), sum(s["t_be"] for s in st), sum(s["n_be"] for s in st)))
+        for s in st:
+            s["t_fe"] = s["t_be"] = 0.0; s["n_be"] = 0
+
+
+class CpuArm:
+    def __init__(self, cfg_raw, seqs, cores):
+        ctx = mp.get_context("fork")
+        self.cores = min(cores, len(seqs))
+        self.conns = []; self.procs = []
+        for w in range(self.cores):
+            pa, ch = ctx.Pipe()
+            p = ctx.Process(target=_cpu_worker, args=(ch, cfg_raw, seqs[w::self.cores]), daemon=True)
+            p.start()
+            self.conns.append(pa); self.procs.append(p)
+        for c in self.conns:
+            c.recv()
+
+    def run(self, a, b):
+        t0 = time.perf_counter()
+        for c in self.conns:
+            c.send(("run", a, b))
+        res = [c.recv() for c in self.conns]
+        dt = time.perf_counter() - t0
+        return dt, sum(r[1] for r in res), sum(r[2] for r in res), sum(r[3] for r in res)
+
+    def close(self):
+        for c in self.conns:
+            c.send(("quit",))
+        for p in self.procs:
+            p.join(timeout=5)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=3)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(",") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm = []; mx = []; reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for i, nm in enumerate(names):
+                    if r[3 + i].strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if sm:
+            out = dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------- roofline models
+def kernel_models(S, N, d, frames_per_launchset=1):
+    """Algorithmic bytes (HBM-bound kernels) or flops (FP64 kernels) per LAUNCH, per DESIGN.md §Kernels.
+    Front-end figures are SURVEY.md §8(d)'s per-frame-per-sequence bytes x S sequences per launch."""
+    m = {}
+    m["clahe_lut_kernel"] = ("hbm", B0 * S)
+    m["clahe_apply_kernel"] = ("hbm", 2 * B0 * S)
+    m["pad_reflect_kernel"] = ("hbm", None)
+    m["pyrdown_kernel"] = ("hbm", None)
+    m["blur7_kernel"] = ("hbm", 2 * B0 * S)
+    m["mineig_kernel"] = ("hbm", (B0 + 4 * B0) * S)        # u8 in, f32 response map out (half the sequences publish)
+    m["candidates_kernel"] = ("hbm", 4 * B0 * S)
+    m["lk_kernel"] = ("hbm", None)                           # filled from the measured point counts
+    m["orb_kernel"] = ("hbm", None)
+    return m
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seqs", type=int, default=64, help="sequences per GPU (BASELINE configs[2]: 64)")
+    ap.add_argument("--tracks", type=int, default=200)
+    ap.add_argument("--window", type=int, default=30)
+    ap.add_argument("--cpu-frames", type=int, default=16, help="frames per sequence of the bounded cpu_baseline sample")
+    ap.add_argument("--profile-steps", type=int, default=8)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3:
+        args.warmup = 3
+    S, K, Wm = args.seqs, args.steps, args.warmup
+    cfg = load_cfg(args)
+    workload = "configs[2]: %d batched synthetic 752x480@20Hz+200Hz-IMU sequences per GPU, %d tracks, %d-pose window, MSCKF-only" % (S, args.tracks, args.window)
+    config = dict(workload=workload, sequences_per_gpu=S, tracks=args.tracks, window=args.window, image="752x480 u8",
+                  l2_policy="each step reads a fresh %.1f MB image batch and touches >250 MB of per-sequence state (> 126 MB L2)" % (S * B0 / 1e6))
+    ncores = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        n_frames = Wm + K
+        seqs = generate(cfg.raw, list(range(S)), n_frames, ncores)
+        arm = CpuArm(cfg.raw, seqs, ncores)
+        arm.run(0, Wm)
+        dt, tfe, tbe, nbe = arm.run(Wm, Wm + K)
+        arm.close()
+        val = S * K / dt
+        line = dict(metric="batched VIO frames/sec", value=val, unit="frames/s", n_gpus=args.gpus, steps=K, warmup=Wm,
+                    ms_per_step=1e3 * dt / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8+f32 front end, f64 filter",
+                    data="synthetic", config=config, impl="reference",
+                    cpu_baseline=dict(value=val, unit="frames/s", cores=arm.cores, kind="port",
+                                      sample="%d sequences x %d frames, cv2 4.13 front end + numpy f64 back end (oracle/), one sequence per process" % (S, K),
+                                      fe_ms_per_frame=1e3 * tfe / (S * K), be_ms_per_update=1e3 * tbe / max(nbe, 1)),
+                    e2e=dict(value=val, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    n_frames = Wm + K + args.profile_steps
+    seq_ids = [rank * S + s for s in range(S)]
+    t_gen = time.time()
+    seqs = generate(cfg.raw, seq_ids, n_frames, max(1, ncores // max(world, 1)))
+    t_gen = time.time() - t_gen
+    cpu_baseline = None
+    if rank == 0 and world == 1:
+        nf = min(args.cpu_frames, n_frames)
+        arm = CpuArm(cfg.raw, seqs, ncores)
+        arm.run(0, 4)
+        dt, tfe, tbe, nbe = arm.run(4, nf)
+        arm.close()
+        cpu_baseline = dict(value=S * (nf - 4) / dt, unit="frames/s", cores=arm.cores, kind="port",
+                            sample="%d sequences x %d frames of the same workload; cv2 4.13 front end + numpy f64 back end (oracle/)" % (S, nf - 4),
+                            fe_ms_per_frame=1e3 * tfe / (S * (nf - 4)), be_ms_per_update=1e3 * tbe / max(nbe, 1))
+
+    import torch
+    import torch.distributed as dist
+    from larvio_b200 import api
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    b = api.Batch(cfg, n_seq=S, device=local_rank)
+    for s in range(S):
+        b.set_initial_state(s, seqs[s].img_t[0], seqs[s].gt_q[0], seqs[s].gt_p[0], seqs[s].gt_v[0], np.zeros(3), np.zeros(3))
+    frames_host = np.stack([np.stack([seqs[s].images[j] for s in range(S)]) for j in range(n_frames)])   # [F][S][H][W]
+    pinned = torch.from_numpy(frames_host).pin_memory()
+    t_img = np.stack([[seqs[s].img_t[j] for s in range(S)] for j in range(n_frames)])
+    # per-frame IMU increments per sequence
+    k = [0] * S
+    incr = []
+    for j in range(n_frames):
+        row = []
+        for s in range(S):
+            k2 = synth.imu_window(seqs[s], k[s], seqs[s].img_t[j]); row.append(seqs[s].imu[k[s]:k2]); k[s] = k2
+        incr.append(row)
+    IMU_STRIDE = 96
+
+    def run_pass(mode, lo, hi, state):
+        """mode 'dev': images resident in HBM; 'e2e': pinned host images, H2D + state read-back inside the step."""
+        imu, n_imu = state
+        for j in range(lo, hi):
+            for s in range(S):
+                r = incr[j][s]; n = n_imu[s]; m = len(r)
+                imu["t"][s, n:n + m] = r[:, 0]; imu["gyro"][s, n:n + m] = r[:, 1:4]; imu["acc"][s, n:n + m] = r[:, 4:7]
+                n_imu[s] = n + m
+            if mode == "dev":
+                b.step(dev_frames[j].data_ptr(), t_img[j], imu, n_imu, images_on_device=True)
+            else:
+                b.step(pinned[j].numpy(), t_img[j], imu, n_imu)
+                b.get_states()
+
+    def fresh_state():
+        return np.zeros((S, IMU_STRIDE), api.IMU_DTYPE), np.zeros(S, np.int32)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reset_batch():
+        nonlocal b
+        b.close()
+        b = api.Batch(cfg, n_seq=S, device=local_rank)
+        for s in range(S):
+            b.set_initial_state(s, seqs[s].img_t[0], seqs[s].gt_q[0], seqs[s].gt_p[0], seqs[s].gt_v[0], np.zeros(3), np.zeros(3))
+
+    # ---- device-resident pass: `value`
+    dev_frames = pinned.to("cuda", non_blocking=False)
+    st = fresh_state()
+    run_pass("dev", 0, Wm, st)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = b.launches
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); t0 = time.perf_counter()
+    run_pass("dev", Wm, Wm + K, st)
+    e1.record(); torch.cuda.synchronize(); wall = time.perf_counter() - t0
+    ms_dev = max(e0.elapsed_time(e1), 1e3 * wall * 0.0)     # each step ends with a stream sync, so events == wall
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = b.launches - l0
+    # ---- per-kernel profile on the next frames (not part of the timed region)
+    b.profile(True)
+    run_pass("dev", Wm + K, n_frames, st)
+    prof = b.profile_get()
+    b.profile(False)
+    states_dev = b.get_states()
+    # ---- end-to-end pass: `e2e` (fresh filters, same frames, host buffers)
+    reset_batch()
+    st = fresh_state()
+    run_pass("e2e", 0, Wm, st)
+    barrier()
+    e2 = torch.cuda.Event(enable_timing=True); e3 = torch.cuda.Event(enable_timing=True)
+    e2.record(); t0 = time.perf_counter()
+    run_pass("e2e", Wm, Wm + K, st)
+    e3.record(); torch.cuda.synchronize(); wall_e2e = time.perf_counter() - t0
+    ms_e2e = max(e2.elapsed_time(e3), 0.0)
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # trajectory gather: final states of every rank to all ranks over NCCL
+        mine = torch.from_numpy(b.get_states()).cuda()
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    if rank == 0:
+        value = world * S * K / (ms_dev / 1e3)
+        e2e_val = world * S * K / (ms_e2e / 1e3)
+        # roofline of the dominant kernel
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        tot = sum(v[0] for v in prof.values()) or 1.0
+        top = sorted(prof.items(), key=lambda kv: -kv[1][0])
+        kernel_share = {kname: dict(ms_per_launch=v[0] / max(v[1], 1), launches=v[1], share=v[0] / tot) for kname, v in top[:12]}
+        dom, (dom_ms, dom_n) = top[0]
+        n_tr = float(np.mean([np.isfinite(x) for x in states_dev[:, 0]]))  # placeholder use
+        models = kernel_models(S, args.tracks, 22 + 6 * args.window)
+        roof = dict(kernel=dom, bound="hbm", achieved=None, peak=hbm_peak, unit="GB/s", frac=None, traffic=None, peak_source=peak_src,
+                    ms_per_launch=dom_ms / max(dom_n, 1))
+        mdl = models.get(dom)
+        if mdl and mdl[1]:
+            ach = mdl[1] / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9
+            roof.update(achieved=ach, frac=ach / hbm_peak)
+        line = dict(metric="batched VIO frames/sec", value=value, unit="frames/s", n_gpus=world, steps=K, warmup=Wm,
+                    ms_per_step=ms_dev / K, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="u8+f32 front end, f64 filter", data="synthetic", config=config,
+                    e2e=dict(value=e2e_val, unit="frames/s", h2d_bytes_per_step=int(S * B0 + S * 10 * 56), d2h_bytes_per_step=int(S * 17 * 8 + S * 32 * 4 + S)),
+                    gpu_launches=int(launches), clocks=clocks, roofline=roof, kernels=kernel_share,
+                    ekf_update_ms_per_seq=None, cpu_baseline=cpu_baseline, gen_seconds=t_gen, wall_dev_s=wall, wall_e2e_s=wall_e2e)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -155,6 +155,13 @@ int lvbk_undistort(LvbHandle* h, const float* pts, int m, int to_pixels, float* 
 int lvbk_ransac(LvbHandle* h, const float* p1, const float* p2, int n, const int* m, int stride,
                 uint8_t* mask);
 
+/* Per-kernel device timing: while enabled every kernel launch is bracketed by CUDA events on the
+ * launching stream (bench.py's roofline figures come from here).  lvb_profile_get returns the number
+ * of distinct kernels and fills names / accumulated ms / launch counts. */
+int lvb_profile_enable(LvbHandle* h, int on);
+int lvb_profile_reset(LvbHandle* h);
+int lvb_profile_get(LvbHandle* h, const char** names, double* total_ms, long long* counts, int cap);
+
 /* number of kernel launches issued through this handle so far (bench.py gpu_launches). */
 long long lvb_launch_count(const LvbHandle* h);
 

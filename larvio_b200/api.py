@@ -60,6 +60,9 @@ _lib.lvb_destroy.restype = None
 _lib.lvb_feature_capacity.argtypes = [_vp]
 _lib.lvb_n_seq.argtypes = [_vp]
 _lib.lvb_synchronize.argtypes = [_vp]
+_lib.lvb_profile_enable.argtypes = [_vp, C.c_int]
+_lib.lvb_profile_reset.argtypes = [_vp]
+_lib.lvb_profile_get.argtypes = [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
 for _name in ("lvbk_pyramid", "lvbk_lk", "lvbk_orb", "lvbk_detect", "lvbk_undistort", "lvbk_ransac",
               "lvb_process_images", "lvb_process_features", "lvb_step", "lvb_set_initial_state",
               "lvb_get_state", "lvb_get_states", "lvb_get_window", "lvb_get_covariance"):
@@ -71,7 +74,7 @@ EXPORTED_SYMBOLS = [
     "lvb_feature_capacity", "lvb_n_seq", "lvb_process_images", "lvb_process_features", "lvb_step",
     "lvb_synchronize", "lvb_set_initial_state", "lvb_get_state", "lvb_get_states", "lvb_get_window",
     "lvb_get_covariance", "lvbk_pyramid", "lvbk_lk", "lvbk_orb", "lvbk_detect", "lvbk_undistort",
-    "lvbk_ransac", "lvb_launch_count",
+    "lvbk_ransac", "lvb_launch_count", "lvb_profile_enable", "lvb_profile_reset", "lvb_profile_get",
 ]
 
 
@@ -117,6 +120,18 @@ class Batch:
     @property
     def launches(self) -> int:
         return int(_lib.lvb_launch_count(self._h))
+
+    def profile(self, on: bool):
+        _check(_lib.lvb_profile_enable(self._h, int(on)))
+
+    def profile_reset(self):
+        _check(_lib.lvb_profile_reset(self._h))
+
+    def profile_get(self):
+        cap = 128
+        names = (C.c_char_p * cap)(); ms = (C.c_double * cap)(); cnt = (C.c_longlong * cap)()
+        n = _lib.lvb_profile_get(self._h, names, ms, cnt, cap)
+        return {names[i].decode(): (ms[i], int(cnt[i])) for i in range(min(n, cap))}
 
     def synchronize(self):
         _check(_lib.lvb_synchronize(self._h))

@@ -1339,6 +1339,7 @@ int be_alloc(LvbHandle* h) {
   BDA(d_T, 16);
   LVB_CUDA(cudaMemcpyAsync(d_T, c.T_cam_imu, sizeof(double) * 16, cudaMemcpyHostToDevice, h->stream));
   BeView v = make_beview(h);
+  LVB_PROF(h, "be_init_kernel");
   be_init_kernel<<<(be->S + 63) / 64, 64, 0, h->stream>>>(v, c.cov_orientation, c.cov_velocity, c.cov_position, c.cov_gyro_bias,
                                                           c.cov_acc_bias, c.cov_extrin_rot, c.cov_extrin_trans, c.estimate_extrin,
                                                           c.estimate_td, c.td, d_T);
@@ -1361,6 +1362,7 @@ void be_free(LvbHandle* h) {
 static int launch_gemm(LvbHandle* h, const GemmArgs& g) {
   LvbBackEnd* be = h->be;
   const int tiles = (be->Dmax + GT - 1) / GT;
+  LVB_PROF(h, "be_gemm_kernel");
   be_gemm_kernel<<<dim3(tiles, tiles, be->S), 256, 0, h->stream>>>(g);
   LVB_LAUNCH_CHECK(h);
   return LVB_OK;
@@ -1371,6 +1373,7 @@ static int be_update(LvbHandle* h, BeView& v) {
   LvbBackEnd* be = h->be;
   cudaStream_t st = h->stream;
   const size_t LD = be->LD;
+  LVB_PROF(h, "be_qr_kernel");
   be_qr_kernel<<<be->S, 512, sizeof(double) * be->RMAX, st>>>(v);
   LVB_LAUNCH_CHECK(h);
   GemmArgs g;
@@ -1387,11 +1390,14 @@ static int be_update(LvbHandle* h, BeView& v) {
   g.C = be->Sm; g.sC = LD * LD; g.rsC = (int)LD; g.csC = 1;
   g.m_idx = I_R; g.n_idx = I_R; g.k_idx = I_DIM; g.alpha = 1.0; g.beta = 0.0; g.diag = v.cfg.sfeat2;
   RC(launch_gemm(h, g));
+  LVB_PROF(h, "be_chol_kernel");
   be_chol_kernel<<<be->S, 512, sizeof(double) * LD, st>>>(v);
   LVB_LAUNCH_CHECK(h);
   BeView vt = v;
+  LVB_PROF(h, "be_trsm_kernel");
   be_trsm_kernel<<<dim3((be->Dmax + 63) / 64, be->S), 64, 0, st>>>(vt);
   LVB_LAUNCH_CHECK(h);
+  LVB_PROF(h, "be_correct_kernel");
   be_correct_kernel<<<be->S, 256, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
   // P -= Y^T Y
@@ -1406,13 +1412,17 @@ static int be_update(LvbHandle* h, BeView& v) {
 static int be_measurement_pass(LvbHandle* h, BeView& v, int mode) {
   LvbBackEnd* be = h->be;
   cudaStream_t st = h->stream;
+  LVB_PROF(h, "be_classify_kernel");
   be_classify_kernel<<<dim3((be->T + 3) / 4, be->S), 128, 0, st>>>(v, mode);
   LVB_LAUNCH_CHECK(h);
+  LVB_PROF(h, "be_scan_rows_kernel");
   be_scan_rows_kernel<<<be->S, 512, 0, st>>>(v, 0);
   LVB_LAUNCH_CHECK(h);
   const int fsm_bytes = (int)sizeof(double) * (6 * be->Wcap + 8 + 4 * be->Wcap * be->Wcap + 2 * be->Wcap);
+  LVB_PROF(h, "be_feature_kernel");
   be_feature_kernel<<<dim3(be->T, be->S), 32, fsm_bytes, st>>>(v, be->Tm);
   LVB_LAUNCH_CHECK(h);
+  LVB_PROF(h, "be_stack_kernel");
   be_stack_kernel<<<be->S, 512, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
   return be_update(h, v);
@@ -1435,26 +1445,35 @@ int be_process(LvbHandle* h, const LvbFeature* d_msg, const int* d_msg_n, const 
   LVB_CUDA(cudaMemcpyAsync(be->n_imu, be->pin_n_imu, sizeof(int) * S, cudaMemcpyHostToDevice, st));
   BeView v = make_beview(h);
   v.msg = d_msg; v.msg_n = d_msg_n; v.msg_t = d_msg_t; v.msg_valid = d_valid; v.msg_stride = msg_stride;
+  LVB_PROF(h, "be_propagate_kernel");
   be_propagate_kernel<<<S, 256, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
   const int nthr = be->N <= 256 ? 256 : 512;
   if (be->N > 512) return lvb_set_err(LVB_E_UNSUPPORTED, "max_features_num > 512");
+  LVB_PROF(h, "be_add_obs_kernel");
   be_add_obs_kernel<<<S, nthr, sizeof(unsigned long long) * be->T, st>>>(v);
   LVB_LAUNCH_CHECK(h);
+  LVB_PROF(h, "be_augment_kernel");
   be_augment_kernel<<<S, 256, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
   RC(be_measurement_pass(h, v, 0));                  // removeLostFeatures
+  LVB_PROF(h, "be_apply_actions_kernel");
   be_apply_actions_kernel<<<dim3((be->T + 127) / 128, S), 128, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
+  LVB_PROF(h, "be_prune_select_kernel");
   be_prune_select_kernel<<<(S + 63) / 64, 64, 0, st>>>(v);   // pruneImuStateBuffer
   LVB_LAUNCH_CHECK(h);
   RC(be_measurement_pass(h, v, 1));
+  LVB_PROF(h, "be_prune_tables_kernel");
   be_prune_tables_kernel<<<S, 256, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
+  LVB_PROF(h, "be_prune_cov_gather_kernel");
   be_prune_cov_gather_kernel<<<dim3(be->Dmax, S), 256, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
+  LVB_PROF(h, "be_prune_cov_scatter_kernel");
   be_prune_cov_scatter_kernel<<<dim3(be->Dmax, S), 256, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
+  LVB_PROF(h, "be_frame_end_kernel");
   be_frame_end_kernel<<<(S + 63) / 64, 64, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
   LVB_CUDA(cudaMemcpyAsync(be->pin_icore, be->icore, sizeof(int) * (size_t)S * BE_ICORE, cudaMemcpyDeviceToHost, st));
@@ -1533,6 +1552,7 @@ extern "C" int lvb_set_initial_state(LvbHandle* h, int seq, double t, const doub
   double* d = h->be->dx;   // scratch
   LVB_CUDA(cudaMemcpyAsync(d, vals, sizeof(vals), cudaMemcpyHostToDevice, h->stream));
   BeView v = make_beview(h);
+  LVB_PROF(h, "be_set_state_kernel");
   be_set_state_kernel<<<1, 1, 0, h->stream>>>(v, seq, t, d);
   LVB_LAUNCH_CHECK(h);
   LVB_CUDA(cudaStreamSynchronize(h->stream));

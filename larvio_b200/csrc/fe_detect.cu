@@ -326,25 +326,31 @@ int fe_detect_launch(LvbHandle* h, const uint8_t* pyr, int n_seq, const int* ena
   cudaStream_t st = h->stream;
   const int W = fe.W, H = fe.H;
   const uint8_t* mask = nullptr;
+  LVB_PROF(h, "reset_detect_kernel");
   reset_detect_kernel<<<(n_seq + 127) / 128, 128, 0, st>>>(fe.eig_max, fe.n_cand, n_seq);
   LVB_LAUNCH_CHECK(h);
   if (ext_mask) mask = ext_mask;
   else if (use_mask) {
+    LVB_PROF(h, "fill_kernel");
     fill_kernel<<<dim3(64, n_seq), 256, 0, st>>>(fe.mask, (size_t)W * H, enable, 255);
     LVB_LAUNCH_CHECK(h);
+    LVB_PROF(h, "mask_kernel");
     mask_kernel<<<dim3(fe.N, n_seq), 128, 0, st>>>(fe.mask, W, H, mask_pts, mask_n, fe.N, h->cfg.min_distance, enable);
     LVB_LAUNCH_CHECK(h);
     mask = fe.mask;
   }
   EigArgs ea; ea.pyr = pyr; ea.L = fe.L; ea.mask = mask; ea.eig = fe.eig; ea.eig_max_key = fe.eig_max; ea.enable = enable;
+  LVB_PROF(h, "mineig_kernel");
   mineig_kernel<<<dim3((W + TW - 1) / TW, (H + TH - 1) / TH, n_seq), 256, 0, st>>>(ea);
   LVB_LAUNCH_CHECK(h);
   CandArgs ca; ca.eig = fe.eig; ca.mask = mask; ca.eig_max_key = fe.eig_max; ca.cand = fe.cand; ca.n_cand = fe.n_cand;
   ca.cap = fe.cand_cap; ca.W = W; ca.H = H; ca.enable = enable;
+  LVB_PROF(h, "candidates_kernel");
   candidates_kernel<<<dim3((W + 31) / 32, (H + 7) / 8, n_seq), 256, 0, st>>>(ca);
   LVB_LAUNCH_CHECK(h);
   SelArgs sa; sa.cand = fe.cand; sa.n_cand = fe.n_cand; sa.cap = fe.cand_cap; sa.want = want; sa.W = W;
   sa.min_dist = h->cfg.min_distance; sa.stride = fe.N; sa.out = out; sa.out_n = out_n; sa.overflow = fe.overflow; sa.enable = enable;
+  LVB_PROF(h, "select_kernel");
   select_kernel<<<n_seq, 1024, 0, st>>>(sa);
   LVB_LAUNCH_CHECK(h);
   return LVB_OK;

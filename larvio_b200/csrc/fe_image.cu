@@ -226,12 +226,14 @@ int fe_build_pyramid(LvbHandle* h, const uint8_t* d_images, int n, uint8_t* pyr,
     const int tile_total = (W / kTiles) * (H / kTiles);
     int clip = (int)(3.0 * tile_total / 256);   // CLAHE clipLimit 3.0, histSize 256
     if (clip < 1) clip = 1;
+    LVB_PROF(h, "clahe_lut_kernel");
     clahe_lut_kernel<<<dim3(64, n), 256, 0, st>>>(d_images, W, H, fe.lut, clip);
     LVB_LAUNCH_CHECK(h);
   }
   {
     dim3 blk(32, 8);
     dim3 grd((W / 4 + 31) / 32, (H + 7) / 8, n);
+    LVB_PROF(h, "clahe_apply_kernel");
     clahe_apply_kernel<<<grd, blk, 0, st>>>(d_images, W, H, fe.lut, pyr, fe.L, h->cfg.flag_equalize);
     LVB_LAUNCH_CHECK(h);
   }
@@ -239,17 +241,20 @@ int fe_build_pyramid(LvbHandle* h, const uint8_t* d_images, int n, uint8_t* pyr,
     const LvbLevel& lv = fe.L.lv[l];
     dim3 blk(32, 8);
     dim3 grd((lv.w + 2 * LVB_PAD + 31) / 32, (lv.h + 2 * LVB_PAD + 7) / 8, n);
+    LVB_PROF(h, "pad_reflect_kernel");
     pad_reflect_kernel<<<grd, blk, 0, st>>>(pyr, fe.L, l);
     LVB_LAUNCH_CHECK(h);
     if (l + 1 < fe.L.n_levels) {
       const LvbLevel& ld = fe.L.lv[l + 1];
       dim3 g2((ld.w + 31) / 32, (ld.h + 7) / 8, n);
+      LVB_PROF(h, "pyrdown_kernel");
       pyrdown_kernel<<<g2, blk, 0, st>>>(pyr, fe.L, l);
       LVB_LAUNCH_CHECK(h);
     }
   }
   if (blur) {
     dim3 grd((W + BT_W - 1) / BT_W, (H + BT_H - 1) / BT_H, n);
+    LVB_PROF(h, "blur7_kernel");
     blur7_kernel<<<grd, 256, 0, st>>>(pyr, fe.L, blur);
     LVB_LAUNCH_CHECK(h);
   }

@@ -226,6 +226,7 @@ int fe_lk_launch(LvbHandle* h, const uint8_t* pyrA, const uint8_t* pyrB, int n_s
   a.max_iter = mi; a.eps2 = eps * eps; a.min_eig = 1e-4;
   a.max_level = h->cfg.pyramid_levels;
   dim3 grd((stride + WARPS - 1) / WARPS, n_seq);
+  LVB_PROF(h, "lk_kernel");
   lk_kernel<<<grd, WARPS * 32, 0, h->stream>>>(a);
   LVB_LAUNCH_CHECK(h);
   return LVB_OK;

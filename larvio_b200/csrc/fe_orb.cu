@@ -149,6 +149,7 @@ int fe_orb_launch(LvbHandle* h, const uint8_t* pyr, const uint8_t* blur, int n_s
   a.angles = angles; a.desc_out = desc_out; a.out_by_slot = out_by_slot; a.desc_ref = desc_ref;
   a.status = status; a.dist_out = dist_out; a.max_dist = 58;
   dim3 grd((stride + 3) / 4, n_seq);
+  LVB_PROF(h, "orb_kernel");
   orb_kernel<<<grd, 128, 0, h->stream>>>(a);
   LVB_LAUNCH_CHECK(h);
   return LVB_OK;
@@ -160,6 +161,7 @@ int fe_undistort_launch(LvbHandle* h, int n_seq, int stride, const float2* pts, 
   a.cam = lvb_camera(h->cfg); a.stride = stride; a.pts = pts; a.perm = perm; a.n_pts = n_pts; a.out = out;
   a.to_pixels = to_pixels;
   dim3 grd((stride + 127) / 128, n_seq);
+  LVB_PROF(h, "undistort_kernel");
   undistort_kernel<<<grd, 128, 0, h->stream>>>(a);
   LVB_LAUNCH_CHECK(h);
   return LVB_OK;

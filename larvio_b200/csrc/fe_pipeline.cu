@@ -55,6 +55,7 @@ int fe_alloc(LvbHandle* h) {
   DA(fe.det_pts, S * N); DA(fe.det_n, S);
   DA(fe.msg, S * N); DA(fe.msg_n, S); DA(fe.has_msg, S); DA(fe.msg_t, S);
   fe.cur = 0;
+  LVB_PROF(h, "init_state_kernel");
   init_state_kernel<<<(fe.S + 127) / 128, 128, 0, h->stream>>>(fe.image_state, fe.S);
   LVB_LAUNCH_CHECK(h);
   PIN(h->pin_H, float, S * 9); PIN(h->pin_active, int, S); PIN(h->pin_t, double, S);
@@ -392,6 +393,7 @@ static int run_compaction(LvbHandle* h, int stage) {
   ca.min_keep[1] = (stage == 2) ? 20 : 1;      // trackNewFeatures: "<20" only after the descriptor gate (:941)
   ca.store_curr = (stage == 0);
   ca.second = fe.do_second; ca.min_keep_second = 20;   // initializeFirstFeatures: "<20" after every gate
+  LVB_PROF(h, "compact_kernel");
   compact_kernel<<<dim3(fe.S, 2), fe.N, 0, h->stream>>>(ca);
   LVB_LAUNCH_CHECK(h);
   return LVB_OK;
@@ -434,8 +436,10 @@ int fe_process(LvbHandle* h, const uint8_t* images, int on_device, const double*
   const int cur = fe.cur, prv = cur ^ 1;
   RC(fe_build_pyramid(h, d_images, S, fe.pyr[cur], fe.blur[cur]));
   FeView v = make_view(h);
+  LVB_PROF(h, "frame_begin_kernel");
   frame_begin_kernel<<<(S + 127) / 128, 128, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
+  LVB_PROF(h, "iota_perm_kernel");
   iota_perm_kernel<<<dim3((N + 127) / 128, S), 128, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
   const float2* src[2] = {fe.trk[prv].curr, fe.new_pts};
@@ -464,9 +468,11 @@ int fe_process(LvbHandle* h, const uint8_t* images, int on_device, const double*
     RC(fe_ransac_launch(h, S, N, fe.ch[c].uprev, fe.ch[c].ucurr, fe.ch[c].n, fe.ch[c].status, nullptr, fe.ch[c].fail));
   }
   RC(run_compaction(h, 3));
+  LVB_PROF(h, "finalize_kernel");
   finalize_kernel<<<S, 256, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
   RC(fe_detect_launch(h, fe.pyr[cur], S, fe.do_detect, 1, nullptr, fe.trk[cur].curr, fe.mask_n, fe.want, fe.det_pts, fe.det_n));
+  LVB_PROF(h, "publish_kernel");
   publish_kernel<<<S, 256, 0, st>>>(v, lvb_camera(h->cfg));
   LVB_LAUNCH_CHECK(h);
   fe.cur ^= 1;

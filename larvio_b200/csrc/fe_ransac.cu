@@ -351,6 +351,7 @@ int fe_ransac_launch(LvbHandle* h, int n_seq, int stride, const float2* p1, cons
   RansacArgs a;
   a.p1 = p1; a.p2 = p2; a.n = n; a.stride = stride; a.mask = mask; a.enable = enable; a.fail = fail;
   a.threshold = 1.0; a.confidence = 0.99; a.max_iters = 1000;
+  LVB_PROF(h, "ransac_kernel");
   ransac_kernel<<<n_seq, 256, 0, h->stream>>>(a);
   LVB_LAUNCH_CHECK(h);
   return LVB_OK;

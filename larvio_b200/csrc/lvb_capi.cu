@@ -161,6 +161,7 @@ extern "C" int lvbk_pyramid(LvbHandle* h, const uint8_t* images, int n, uint8_t*
     if (!outs[l]) continue;
     const LvbLevel& lv = fe.L.lv[l];
     dim3 blk(32, 8), grd((lv.w + 31) / 32, (lv.h + 7) / 8, n);
+    LVB_PROF(h, "unpad_kernel");
     unpad_kernel<<<grd, blk, 0, h->stream>>>(d_pyr, fe.L, l, d_out);
     LVB_LAUNCH_CHECK(h);
     LVB_CUDA(cudaMemcpyAsync(outs[l], d_out, (size_t)lv.w * lv.h * n, cudaMemcpyDeviceToHost, h->stream));
@@ -313,4 +314,58 @@ extern "C" int lvbk_ransac(LvbHandle* h, const float* p1, const float* p2, int n
   LVB_CUDA(cudaMemcpyAsync(mask, dm, tot, cudaMemcpyDeviceToHost, h->stream));
   LVB_CUDA(cudaStreamSynchronize(h->stream));
   return LVB_OK;
+}
+
+// ------------------------------------------------------------------ per-kernel timing
+void lvb_prof_begin(LvbHandle* h, const char* name) {
+  LvbProfiler& p = h->prof;
+  int id = -1;
+  for (size_t i = 0; i < p.names.size(); ++i) if (p.names[i] == name) { id = (int)i; break; }
+  if (id < 0) { id = (int)p.names.size(); p.names.push_back(name); p.total_ms.push_back(0.0); p.count.push_back(0); }
+  if ((size_t)(2 * p.used + 2) > p.ev.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    p.ev.push_back(a); p.ev.push_back(b); p.ev_name.push_back(id);
+  } else p.ev_name[p.used] = id;
+  cudaEventRecord(p.ev[2 * p.used], h->stream);
+  p.open_name = id;
+}
+void lvb_prof_end(LvbHandle* h) {
+  LvbProfiler& p = h->prof;
+  if (p.open_name < 0) return;
+  cudaEventRecord(p.ev[2 * p.used + 1], h->stream);
+  p.used++;
+  p.open_name = -1;
+}
+static void lvb_prof_collect(LvbHandle* h) {
+  LvbProfiler& p = h->prof;
+  cudaStreamSynchronize(h->stream);
+  for (int i = 0; i < p.used; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.ev[2 * i], p.ev[2 * i + 1]) == cudaSuccess) { p.total_ms[p.ev_name[i]] += ms; p.count[p.ev_name[i]]++; }
+  }
+  p.used = 0;
+}
+extern "C" int lvb_profile_enable(LvbHandle* h, int on) {
+  if (!h) return LVB_E_ARG;
+  cudaSetDevice(h->device);
+  if (!on && h->prof.on) lvb_prof_collect(h);
+  h->prof.on = on != 0;
+  return LVB_OK;
+}
+extern "C" int lvb_profile_reset(LvbHandle* h) {
+  if (!h) return LVB_E_ARG;
+  lvb_prof_collect(h);
+  for (auto& x : h->prof.total_ms) x = 0.0;
+  for (auto& x : h->prof.count) x = 0;
+  return LVB_OK;
+}
+// Fills up to cap entries; names[i] points into handle-owned storage. Returns the number of kernels.
+extern "C" int lvb_profile_get(LvbHandle* h, const char** names, double* total_ms, long long* counts, int cap) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  lvb_prof_collect(h);
+  const int n = (int)h->prof.names.size();
+  for (int i = 0; i < n && i < cap; ++i) { names[i] = h->prof.names[i].c_str(); total_ms[i] = h->prof.total_ms[i]; counts[i] = h->prof.count[i]; }
+  return n;
 }

@@ -98,6 +98,16 @@ struct LvbFrontEnd {
 
 struct LvbBackEnd;   // be_state.h
 
+// optional per-kernel timing (CUDA events on the launching stream), see lvb_profile_* in the C ABI
+struct LvbProfiler {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;          // pairs (start, stop)
+  std::vector<int> ev_name;             // name id per pair
+  std::vector<std::string> names;
+  std::vector<double> total_ms; std::vector<long long> count;
+  int used = 0; int open_name = -1;
+};
+
 struct LvbHandle {
   LvbConfig cfg;
   int S;
@@ -106,6 +116,7 @@ struct LvbHandle {
   LvbFrontEnd fe;
   LvbBackEnd* be;
   long long launches;
+  LvbProfiler prof;
   // host-side per-sequence bookkeeping (mirrors ImageProcessor members that only the host needs)
   std::vector<uint8_t> h_first_img;      // bFirstImg
   std::vector<double> h_prev_img_time;
@@ -127,9 +138,14 @@ int lvb_set_err(int code, const char* fmt, ...);
       return lvb_set_err(LVB_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
   } while (0)
 
+void lvb_prof_begin(LvbHandle* h, const char* name);
+void lvb_prof_end(LvbHandle* h);
+#define LVB_PROF(h, name) do { if ((h)->prof.on) lvb_prof_begin((h), (name)); } while (0)
+
 #define LVB_LAUNCH_CHECK(h)                                                                \
   do {                                                                                     \
     (h)->launches++;                                                                       \
+    if ((h)->prof.on) lvb_prof_end(h);                                                     \
     cudaError_t e_ = cudaGetLastError();                                                   \
     if (e_ != cudaSuccess)                                                                 \
       return lvb_set_err(LVB_E_CUDA, "%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \

@@ -13,7 +13,7 @@ from __future__ import annotations
 import numpy as np
 import cv2
 
-from .orb import OrbOracle, hamming
+from .orb import OrbOracle, hamming, hamming_rows
 
 f32 = np.float32
 
@@ -262,7 +262,7 @@ class ImageProcessorOracle:
         if len(prev2) < min_after_lk or len(prev2) <= 0:
             return None
         dprev = self.prev_orb.compute(prev2); dcurr = self.curr_orb.compute(curr2)
-        dis = np.array([hamming(dprev[j], dcurr[j]) for j in range(len(dprev))], np.int32)
+        dis = hamming_rows(dprev, dcurr)
         dm = (dis <= 58).astype(np.uint8)
         self.trace["new_desc"] = dm.copy(); self.trace["new_hamming"] = dis
         prev3 = self._keep(prev2, dm); curr3 = self._keep(curr2, dm); desc3 = dprev[dm != 0]
@@ -313,7 +313,7 @@ class ImageProcessorOracle:
         if len(curr2) == 0:
             self._clear_tracks(); return
         dcurr = self.curr_orb.compute(curr2)
-        dis = np.array([hamming(desc2[j], dcurr[j]) for j in range(len(dcurr))], np.int32)
+        dis = hamming_rows(desc2, dcurr)
         dm = (dis <= 58).astype(np.uint8)
         self.trace["trk_desc"] = dm.copy(); self.trace["trk_hamming"] = dis
         ids = self._keep(ids, dm); life = self._keep(life, dm)

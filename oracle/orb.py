@@ -34,6 +34,9 @@ def _umax():
 
 
 UMAX = _umax()
+# offsets of the radius-15 disc (rows v = -15..15, |u| <= umax[|v|])
+_DISC_V = np.concatenate([np.full(2 * UMAX[abs(v)] + 1, v) for v in range(-HALF_PATCH, HALF_PATCH + 1)]).astype(np.int64)
+_DISC_U = np.concatenate([np.arange(-UMAX[abs(v)], UMAX[abs(v)] + 1) for v in range(-HALF_PATCH, HALF_PATCH + 1)]).astype(np.int64)
 
 
 class OrbOracle:
@@ -79,12 +82,46 @@ class OrbOracle:
         bits = (val[:, 0] < val[:, 1]).astype(np.uint8)
         return np.packbits(bits.reshape(32, 8), axis=1, bitorder="little").reshape(32)
 
-    def compute(self, pts: np.ndarray) -> np.ndarray:
+    def compute_loop(self, pts: np.ndarray) -> np.ndarray:
+        """Literal per-point restatement (slow); ``compute`` is the vectorised equivalent."""
         out = np.zeros((len(pts), 32), np.uint8)
         for i, p in enumerate(pts):
             out[i] = self.descriptor(p, self.ic_angle(p))
         return out
 
+    def angles(self, pts: np.ndarray) -> np.ndarray:
+        pts = np.asarray(pts, np.float32).reshape(-1, 2)
+        cx = np.rint(pts[:, 0]).astype(np.int64) + BORDER
+        cy = np.rint(pts[:, 1]).astype(np.int64) + BORDER
+        val = self.raw[cy[:, None] + _DISC_V[None, :], cx[:, None] + _DISC_U[None, :]].astype(np.int64)
+        m10 = (val * _DISC_U[None, :]).sum(1)
+        m01 = (val * _DISC_V[None, :]).sum(1)
+        y = m01.astype(np.float32); x = m10.astype(np.float32)
+        return np.array([cv2.fastAtan2(float(a), float(b)) for a, b in zip(y, x)], np.float32)
+
+    def compute(self, pts: np.ndarray) -> np.ndarray:
+        pts = np.asarray(pts, np.float32).reshape(-1, 2)
+        n = len(pts)
+        if n == 0:
+            return np.zeros((0, 32), np.uint8)
+        ang = (self.angles(pts) * FACTOR_PI).astype(np.float32)
+        a = np.cos(ang.astype(np.float64)).astype(np.float32)[:, None, None]
+        b = np.sin(ang.astype(np.float64)).astype(np.float32)[:, None, None]
+        cx = (np.rint(pts[:, 0]).astype(np.int64) + BORDER)[:, None, None]
+        cy = (np.rint(pts[:, 1]).astype(np.int64) + BORDER)[:, None, None]
+        px = _PATTERN[:, [0, 2]].astype(np.float32)[None]
+        py = _PATTERN[:, [1, 3]].astype(np.float32)[None]
+        x = (px * a).astype(np.float32) - (py * b).astype(np.float32)
+        y = (px * b).astype(np.float32) + (py * a).astype(np.float32)
+        ix = np.rint(x).astype(np.int64); iy = np.rint(y).astype(np.int64)
+        val = self.blur[cy + iy, cx + ix].astype(np.int32)
+        bits = (val[:, :, 0] < val[:, :, 1]).astype(np.uint8)
+        return np.packbits(bits.reshape(n, 32, 8), axis=2, bitorder="little").reshape(n, 32)
+
 
 def hamming(a: np.ndarray, b: np.ndarray) -> int:
     return int(np.unpackbits(np.bitwise_xor(a, b)).sum())
+
+
+def hamming_rows(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    return np.unpackbits(np.bitwise_xor(a, b), axis=1).sum(1).astype(np.int32)
