@@ -252,24 +252,34 @@ def main():
     frames_host = np.stack([np.stack([seqs[s].images[j] for s in range(S)]) for j in range(n_frames)])   # [F][S][H][W]
     pinned = torch.from_numpy(frames_host).pin_memory()
     t_img = np.stack([[seqs[s].img_t[j] for s in range(S)] for j in range(n_frames)])
-    # per-frame IMU increments per sequence
+    # per-frame IMU increments per sequence (app/larvioMain.cpp:98-102), pre-packed so that the timed loop
+    # appends them to the caller-owned buffers with one vectorised assignment
     k = [0] * S
-    incr = []
+    inc = []
     for j in range(n_frames):
-        row = []
+        rows = []
         for s in range(S):
-            k2 = synth.imu_window(seqs[s], k[s], seqs[s].img_t[j]); row.append(seqs[s].imu[k[s]:k2]); k[s] = k2
-        incr.append(row)
+            k2 = synth.imu_window(seqs[s], k[s], seqs[s].img_t[j]); rows.append(seqs[s].imu[k[s]:k2]); k[s] = k2
+        m = np.array([len(r) for r in rows])
+        mm = int(m.max()) if len(m) else 0
+        arr = np.zeros((S, max(mm, 1), 7))
+        for s, r in enumerate(rows):
+            arr[s, :len(r)] = r
+        inc.append((m, arr))
     IMU_STRIDE = 96
+    ar_s = np.arange(S)
 
     def run_pass(mode, lo, hi, state):
         """mode 'dev': images resident in HBM; 'e2e': pinned host images, H2D + state read-back inside the step."""
         imu, n_imu = state
         for j in range(lo, hi):
-            for s in range(S):
-                r = incr[j][s]; n = n_imu[s]; m = len(r)
-                imu["t"][s, n:n + m] = r[:, 0]; imu["gyro"][s, n:n + m] = r[:, 1:4]; imu["acc"][s, n:n + m] = r[:, 4:7]
-                n_imu[s] = n + m
+            m, arr = inc[j]
+            mm = arr.shape[1]
+            cols = n_imu[:, None] + np.arange(mm)[None, :]
+            valid = np.arange(mm)[None, :] < m[:, None]
+            rr = np.broadcast_to(ar_s[:, None], cols.shape)[valid]; cc = cols[valid]
+            imu["t"][rr, cc] = arr[:, :, 0][valid]; imu["gyro"][rr, cc] = arr[:, :, 1:4][valid]; imu["acc"][rr, cc] = arr[:, :, 4:7][valid]
+            n_imu += m.astype(np.int32)
             if mode == "dev":
                 b.step(dev_frames[j].data_ptr(), t_img[j], imu, n_imu, images_on_device=True)
             else:

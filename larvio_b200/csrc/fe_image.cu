@@ -137,16 +137,26 @@ __device__ __forceinline__ int reflect101(int p, int n) {
   return p;
 }
 
-// one thread per padded pixel outside the interior (simple 2-D sweep over the padded level)
+// one thread per PAD pixel: indices 0..2*PAD*PW-1 are the top/bottom bands, the rest the left/right strips
 __global__ void pad_reflect_kernel(uint8_t* __restrict__ pyr, LvbPyramidLayout L, int level) {
-  const int s = blockIdx.z;
+  const int s = blockIdx.y;
   const LvbLevel lv = L.lv[level];
-  const int px = blockIdx.x * blockDim.x + threadIdx.x;   // padded coords
-  const int py = blockIdx.y * blockDim.y + threadIdx.y;
-  const int PW = lv.w + 2 * LVB_PAD, PH = lv.h + 2 * LVB_PAD;
-  if (px >= PW || py >= PH) return;
-  const int x = px - LVB_PAD, y = py - LVB_PAD;
-  if (x >= 0 && x < lv.w && y >= 0 && y < lv.h) return;
+  const int PW = lv.w + 2 * LVB_PAD;
+  const int band = LVB_PAD * PW;
+  const int total = 2 * band + lv.h * 2 * LVB_PAD;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int x, y;
+  if (idx < 2 * band) {
+    const int r = idx / PW;
+    x = idx - r * PW - LVB_PAD;
+    y = (r < LVB_PAD) ? (r - LVB_PAD) : (lv.h + r - LVB_PAD);
+  } else {
+    const int rem = idx - 2 * band;
+    y = rem / (2 * LVB_PAD);
+    const int c = rem - y * 2 * LVB_PAD;
+    x = (c < LVB_PAD) ? (c - LVB_PAD) : (lv.w + c - LVB_PAD);
+  }
   uint8_t* org = lvb_level_origin(pyr, L, s, level);
   const int sx = reflect101(x, lv.w), sy = reflect101(y, lv.h);
   org[(ptrdiff_t)y * lv.pitch + x] = org[(ptrdiff_t)sy * lv.pitch + sx];
@@ -240,9 +250,9 @@ int fe_build_pyramid(LvbHandle* h, const uint8_t* d_images, int n, uint8_t* pyr,
   for (int l = 0; l < fe.L.n_levels; ++l) {
     const LvbLevel& lv = fe.L.lv[l];
     dim3 blk(32, 8);
-    dim3 grd((lv.w + 2 * LVB_PAD + 31) / 32, (lv.h + 2 * LVB_PAD + 7) / 8, n);
+    const int pad_total = 2 * LVB_PAD * (lv.w + 2 * LVB_PAD) + lv.h * 2 * LVB_PAD;
     LVB_PROF(h, "pad_reflect_kernel");
-    pad_reflect_kernel<<<grd, blk, 0, st>>>(pyr, fe.L, l);
+    pad_reflect_kernel<<<dim3((pad_total + 255) / 256, n), 256, 0, st>>>(pyr, fe.L, l);
     LVB_LAUNCH_CHECK(h);
     if (l + 1 < fe.L.n_levels) {
       const LvbLevel& ld = fe.L.lv[l + 1];

@@ -18,12 +18,44 @@ constexpr int DT = WIN + 1;                // 22: derivative grid
 constexpr int WARPS = 4;
 constexpr int W_BITS = 14;
 
+// OpenCV's SSE path accumulates the normal equations in 4 float lanes + a scalar tail (pixels 16..20 of each
+// window row); to be BIT-identical we replay exactly that order (oracle/lk_exact.py): per sum, accumulator p < 4
+// receives, row by row, the terms of pixels p, 4+p, 8+p, 12+p (A) resp. the int-pair terms of both 8-pixel
+// chunks (b); accumulator 4 receives pixels 16..20.  Terms are produced by all lanes, the 15 (A) / 10 (b)
+// sequential chains run on one lane each.
+constexpr int NTERM_A = WIN * 16 + WIN * 5;   // per sum: 336 lane terms + 105 tail terms = 441
+constexpr int NTERM_B = WIN * 8 + WIN * 5;    // per sum: 168 pair terms + 105 tail terms = 273
 struct WarpSmem {
-  uint8_t tile[TILE * TILE];               // 576
-  short2 dtile[DT * DT];                   // 1936
   short Iw[NPIX + 7];                      // 896
   short2 dIw[NPIX];                        // 1764
+  short dd[NPIX + 7];                      // 896  I_t per iteration
+  union {
+    struct { uint8_t tile[TILE * TILE]; short2 dtile[DT * DT]; } st;   // 576 + 1936 (window set-up only)
+    float termA[3 * NTERM_A];              // 5292
+    float termB[2 * NTERM_B];              // 2184
+  } u;
 };
+
+// chain c of a sum with `nterm_lane` terms per row for accumulators 0..3 (stored [row][k][p]) and 5 tail terms per
+// row (stored after all lane terms, [row][x]).  Returns the accumulator value; acc in 0..4.
+__device__ __forceinline__ float run_chain(const float* T, int k_per_row, int acc) {
+  float a = 0.f;
+  if (acc < 4) {
+    const float* q = T + acc;
+    for (int i = 0; i < WIN * k_per_row; ++i) a = __fadd_rn(a, q[i * 4]);
+  } else {
+    const float* q = T + WIN * k_per_row * 4;
+    for (int i = 0; i < WIN * 5; ++i) a = __fadd_rn(a, q[i]);
+  }
+  return a;
+}
+// total = tail + ((l0 + l2) + (l1 + l3)); chains of this sum live on lanes base..base+4
+__device__ __forceinline__ float combine_chains(float mine, int base) {
+  const float l0 = __shfl_sync(0xffffffffu, mine, base), l1 = __shfl_sync(0xffffffffu, mine, base + 1);
+  const float l2 = __shfl_sync(0xffffffffu, mine, base + 2), l3 = __shfl_sync(0xffffffffu, mine, base + 3);
+  const float tl = __shfl_sync(0xffffffffu, mine, base + 4);
+  return __fadd_rn(tl, __fadd_rn(__fadd_rn(l0, l2), __fadd_rn(l1, l3)));
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -97,7 +129,7 @@ __global__ void __launch_bounds__(WARPS * 32) lk_kernel(LkArgs a) {
     // ---- stage the 24x24 source tile (origin ipx-1, ipy-1)
     for (int t = lane; t < TILE * TILE; t += 32) {
       const int ty = t / TILE, tx = t - ty * TILE;
-      w.tile[t] = __ldg(orgA + (ptrdiff_t)(ipy - 1 + ty) * lv.pitch + (ipx - 1 + tx));
+      w.u.st.tile[t] = __ldg(orgA + (ptrdiff_t)(ipy - 1 + ty) * lv.pitch + (ipx - 1 + tx));
     }
     __syncwarp();
     // ---- Scharr derivatives on the 22x22 grid (zero outside the image)
@@ -106,14 +138,14 @@ __global__ void __launch_bounds__(WARPS * 32) lk_kernel(LkArgs a) {
       const int gx = ipx + dx, gy = ipy + dy;
       short2 d = make_short2(0, 0);
       if (gx >= 0 && gx < lv.w && gy >= 0 && gy < lv.h) {
-        const uint8_t* c = &w.tile[(dy + 1) * TILE + (dx + 1)];
+        const uint8_t* c = &w.u.st.tile[(dy + 1) * TILE + (dx + 1)];
         const int tl = c[-TILE - 1], tc = c[-TILE], tr = c[-TILE + 1];
         const int ml = c[-1], mr = c[1];
         const int bl = c[TILE - 1], bc = c[TILE], br = c[TILE + 1];
         d.x = (short)(3 * (tr + br - tl - bl) + 10 * (mr - ml));
         d.y = (short)(3 * (bl + br - tl - tr) + 10 * (bc - tc));
       }
-      w.dtile[t] = d;
+      w.u.st.dtile[t] = d;
     }
     __syncwarp();
     // ---- window of the previous image
@@ -122,25 +154,36 @@ __global__ void __launch_bounds__(WARPS * 32) lk_kernel(LkArgs a) {
     int iw01 = __float2int_rn(__fmul_rn(__fmul_rn(fa, __fsub_rn(1.f, fb)), (float)(1 << W_BITS)));
     int iw10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, fa), fb), (float)(1 << W_BITS)));
     int iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
-    float A11 = 0.f, A12 = 0.f, A22 = 0.f;
     for (int p = lane; p < NPIX; p += 32) {
       const int y = p / WIN, x = p - y * WIN;
-      const uint8_t* c = &w.tile[(y + 1) * TILE + (x + 1)];
+      const uint8_t* c = &w.u.st.tile[(y + 1) * TILE + (x + 1)];
       const int ival = (c[0] * iw00 + c[1] * iw01 + c[TILE] * iw10 + c[TILE + 1] * iw11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-      const short2 d00 = w.dtile[y * DT + x], d01 = w.dtile[y * DT + x + 1];
-      const short2 d10 = w.dtile[(y + 1) * DT + x], d11 = w.dtile[(y + 1) * DT + x + 1];
+      const short2 d00 = w.u.st.dtile[y * DT + x], d01 = w.u.st.dtile[y * DT + x + 1];
+      const short2 d10 = w.u.st.dtile[(y + 1) * DT + x], d11 = w.u.st.dtile[(y + 1) * DT + x + 1];
       const int ix = (d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
       const int iy = (d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
       w.Iw[p] = (short)ival;
       w.dIw[p] = make_short2((short)ix, (short)iy);
-      A11 = __fadd_rn(A11, (float)(ix * ix));
-      A12 = __fadd_rn(A12, (float)(ix * iy));
-      A22 = __fadd_rn(A22, (float)(iy * iy));
     }
+    __syncwarp();
+    // terms of A11, A12, A22 in OpenCV's lane order (the tile/dtile staging area is dead from here on)
+    for (int p = lane; p < NPIX; p += 32) {
+      const int y = p / WIN, x = p - y * WIN;
+      const short2 d = w.dIw[p];
+      const float fx = (float)d.x, fy = (float)d.y;
+      const int slot = (x < 16) ? (y * 16 + (x >> 2) * 4 + (x & 3)) : (WIN * 16 + y * 5 + (x - 16));
+      w.u.termA[slot] = __fmul_rn(fx, fx);
+      w.u.termA[NTERM_A + slot] = __fmul_rn(fx, fy);
+      w.u.termA[2 * NTERM_A + slot] = __fmul_rn(fy, fy);
+    }
+    __syncwarp();
+    float chainv = 0.f;
+    if (lane < 15) chainv = run_chain(w.u.termA + (lane / 5) * NTERM_A, 4, lane % 5);
     const float FLT_SCALE = 1.f / (float)(1 << 20);
-    A11 = __fmul_rn(warp_sum(A11), FLT_SCALE);
-    A12 = __fmul_rn(warp_sum(A12), FLT_SCALE);
-    A22 = __fmul_rn(warp_sum(A22), FLT_SCALE);
+    float A11 = __fmul_rn(combine_chains(chainv, 0), FLT_SCALE);
+    float A12 = __fmul_rn(combine_chains(chainv, 5), FLT_SCALE);
+    float A22 = __fmul_rn(combine_chains(chainv, 10), FLT_SCALE);
+    __syncwarp();
     float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
     const float dif = __fsub_rn(A11, A22);
     const float rad = __fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.f, A12), A12));
@@ -152,7 +195,6 @@ __global__ void __launch_bounds__(WARPS * 32) lk_kernel(LkArgs a) {
     D = __fdiv_rn(1.f, D);
     float2 np = make_float2(__fsub_rn(nxt.x, halfWin), __fsub_rn(nxt.y, halfWin));
     float2 prevDelta = make_float2(0.f, 0.f);
-    __syncwarp();
     for (int j = 0; j < a.max_iter; ++j) {
       const int inx = (int)floorf(np.x), iny = (int)floorf(np.y);
       if (inx < -WIN || inx >= lv.w || iny < -WIN || iny >= lv.h) {
@@ -165,19 +207,41 @@ __global__ void __launch_bounds__(WARPS * 32) lk_kernel(LkArgs a) {
       iw01 = __float2int_rn(__fmul_rn(__fmul_rn(fa, __fsub_rn(1.f, fb)), (float)(1 << W_BITS)));
       iw10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, fa), fb), (float)(1 << W_BITS)));
       iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
-      float b1 = 0.f, b2 = 0.f;
       const uint8_t* jbase = orgB + (ptrdiff_t)iny * lv.pitch + inx;
       for (int p = lane; p < NPIX; p += 32) {
         const int y = p / WIN, x = p - y * WIN;
         const uint8_t* c = jbase + (ptrdiff_t)y * lv.pitch + x;
         const int j00 = __ldg(c), j01 = __ldg(c + 1), j10 = __ldg(c + lv.pitch), j11 = __ldg(c + lv.pitch + 1);
-        const int diff = ((j00 * iw00 + j01 * iw01 + j10 * iw10 + j11 * iw11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5)) - (int)w.Iw[p];
-        const short2 d = w.dIw[p];
-        b1 = __fadd_rn(b1, (float)(diff * d.x));
-        b2 = __fadd_rn(b2, (float)(diff * d.y));
+        w.dd[p] = (short)(((j00 * iw00 + j01 * iw01 + j10 * iw10 + j11 * iw11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5)) - (int)w.Iw[p]);
       }
-      b1 = __fmul_rn(warp_sum(b1), FLT_SCALE);
-      b2 = __fmul_rn(warp_sum(b2), FLT_SCALE);
+      __syncwarp();
+      // pair terms (both 8-pixel chunks of every row) and tail terms, then the 10 chains
+      for (int t = lane; t < NTERM_B; t += 32) {
+        float t1, t2;
+        if (t < WIN * 8) {
+          const int y = t >> 3, ch = (t >> 2) & 1, p = t & 3;
+          const int i0 = y * WIN + 8 * ch + p, i1 = i0 + 4;
+          const int d0 = w.dd[i0], d1 = w.dd[i1];
+          const short2 g0 = w.dIw[i0], g1 = w.dIw[i1];
+          t1 = (float)(d0 * g0.x + d1 * g1.x);
+          t2 = (float)(d0 * g0.y + d1 * g1.y);
+        } else {
+          const int q = t - WIN * 8, y = q / 5, x = 16 + q - y * 5;
+          const int i0 = y * WIN + x;
+          const int d0 = w.dd[i0];
+          const short2 g0 = w.dIw[i0];
+          t1 = (float)(d0 * g0.x);
+          t2 = (float)(d0 * g0.y);
+        }
+        w.u.termB[t] = t1;
+        w.u.termB[NTERM_B + t] = t2;
+      }
+      __syncwarp();
+      float cv = 0.f;
+      if (lane < 10) cv = run_chain(w.u.termB + (lane / 5) * NTERM_B, 2, lane % 5);
+      const float b1 = __fmul_rn(combine_chains(cv, 0), FLT_SCALE);
+      const float b2 = __fmul_rn(combine_chains(cv, 5), FLT_SCALE);
+      __syncwarp();
       float2 delta;
       delta.x = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
       delta.y = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);

@@ -426,8 +426,11 @@ int fe_process(LvbHandle* h, const uint8_t* images, int on_device, const double*
   }
   const uint8_t* d_images = images;
   if (!on_device) {
-    memcpy(h->pin_images, images, S * npx);
-    LVB_CUDA(cudaMemcpyAsync(fe.img_in, h->pin_images, S * npx, cudaMemcpyHostToDevice, st));
+    // caller buffers that are already page-locked are copied directly; pageable ones go through pinned staging
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, images) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    if (!pinned) { cudaGetLastError(); memcpy(h->pin_images, images, S * npx); }
+    LVB_CUDA(cudaMemcpyAsync(fe.img_in, pinned ? images : h->pin_images, S * npx, cudaMemcpyHostToDevice, st));
     d_images = fe.img_in;
   }
   LVB_CUDA(cudaMemcpyAsync(fe.Hmat, h->pin_H, sizeof(float) * 9 * S, cudaMemcpyHostToDevice, st));

@@ -1,0 +1,313 @@
+"""GPU parity suite (-m gpu): every stage and the whole path through the C ABI against the CPU oracle
+(cv2 4.13 for the OpenCV pieces, numpy f64 for the filter) and against the committed golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "oracle_seq.npz")
+
+
+@pytest.fixture(scope="module")
+def batch(cfg, lib_built):
+    from larvio_b200 import api
+    b = api.Batch(cfg, n_seq=2)
+    yield b
+    b.close()
+
+
+@pytest.fixture(scope="module")
+def clahe_imgs(seqs):
+    import cv2
+    cl = cv2.createCLAHE(3.0, (8, 8))
+    return np.stack([cl.apply(seqs[s].images[j]) for s in range(2) for j in range(2)])   # s0f0 s0f1 s1f0 s1f1
+
+
+def test_pyramid_bit_exact(batch, seqs):
+    import cv2
+    imgs = np.stack([seqs[0].images[0], seqs[1].images[0], seqs[0].images[3], seqs[1].images[5]])
+    clahe, l1, l2, blur = batch.k_pyramid(imgs)
+    cl = cv2.createCLAHE(3.0, (8, 8))
+    for i in range(4):
+        ref = cl.apply(imgs[i]); r1 = cv2.pyrDown(ref); r2 = cv2.pyrDown(r1)
+        rb = cv2.GaussianBlur(ref, (7, 7), 2, sigmaY=2, borderType=cv2.BORDER_REFLECT_101)
+        assert np.array_equal(ref, clahe[i]) and np.array_equal(r1, l1[i]) and np.array_equal(r2, l2[i])
+        assert np.array_equal(rb, blur[i])
+
+
+def test_pyramid_edge_images(batch):
+    """constant, saturated and checkerboard inputs (CLAHE clip/redistribution corner cases)."""
+    import cv2
+    imgs = np.zeros((4, 480, 752), np.uint8)
+    imgs[1] = 255
+    imgs[2] = ((np.indices((480, 752)).sum(0) % 2) * 255).astype(np.uint8)
+    imgs[3] = np.random.default_rng(0).integers(0, 256, (480, 752)).astype(np.uint8)
+    clahe, l1, l2, blur = batch.k_pyramid(imgs)
+    cl = cv2.createCLAHE(3.0, (8, 8))
+    for i in range(4):
+        ref = cl.apply(imgs[i])
+        assert np.array_equal(ref, clahe[i]), i
+        assert np.array_equal(cv2.pyrDown(cv2.pyrDown(ref)), l2[i]), i
+
+
+def test_lk_matches_opencv(batch, clahe_imgs):
+    import cv2
+    A = clahe_imgs[[0, 2]]; B = clahe_imgs[[1, 3]]
+    rng = np.random.default_rng(0)
+    P = []
+    for s in range(2):
+        p = cv2.goodFeaturesToTrack(A[s], 200, 0.01, 20).reshape(-1, 2)
+        extra = np.array([[0.3, 0.2], [751.0, 479.0], [5.5, 470.2], [745.1, 3.9], [-3.0, 100.0], [760.0, 200.0]], np.float32)
+        p = np.concatenate([p, extra])[:206]
+        while len(p) < 206:
+            p = np.concatenate([p, rng.uniform(0, 470, (206 - len(p), 2)).astype(np.float32)])
+        P.append(p)
+    P = np.stack(P).astype(np.float32)
+    init = P + rng.normal(0, 1.5, P.shape).astype(np.float32)
+    out, st = batch.k_lk(A, B, P, init)
+    crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
+    for s in range(2):
+        ref, rst, _ = cv2.calcOpticalFlowPyrLK(A[s], B[s], P[s].reshape(-1, 1, 2), init[s].reshape(-1, 1, 2).copy(), winSize=(21, 21),
+                                               maxLevel=2, criteria=crit, flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+        ref = ref.reshape(-1, 2); rst = rst.reshape(-1)
+        assert np.array_equal(rst, st[s])                              # status bit-exact
+        ok = rst == 1
+        # positions bit-exact: the kernel replays OpenCV's SSE accumulation order (oracle/lk_exact.py)
+        assert np.array_equal(ref[ok], out[s][ok])
+
+
+def test_orb_bit_exact(batch, clahe_imgs):
+    import cv2
+    from oracle.orb import OrbOracle
+    img = clahe_imgs[0]
+    rng = np.random.default_rng(1)
+    pts = cv2.goodFeaturesToTrack(img, 196, 0.01, 20).reshape(-1, 2)
+    pts = pts + rng.uniform(-0.5, 0.5, pts.shape).astype(np.float32)
+    pts = np.concatenate([pts, np.array([[0.2, 0.3], [751, 479], [3.4, 476.5], [748.2, 2.2]], np.float32)])
+    ang, desc = batch.k_orb(img[None], pts[None])
+    o = OrbOracle(img)
+    assert np.array_equal(o.angles(pts), ang[0])
+    assert np.array_equal(o.compute(pts), desc[0])
+
+
+def test_detector_identical_corners(batch, clahe_imgs):
+    import cv2
+    imgs = clahe_imgs[[1, 3]]
+    det, eig = batch.k_detect(imgs, None, 200, return_eig=True)
+    mask = np.full(imgs.shape, 255, np.uint8)
+    for s in range(2):
+        ref = cv2.goodFeaturesToTrack(imgs[s], 200, 0.01, 20).reshape(-1, 2)
+        assert np.array_equal(ref, det[s])                            # same corners, same order
+        re = cv2.cornerMinEigenVal(imgs[s], 3, ksize=3)
+        # response map: OpenCV sums the 3x3 box in a running double; we sum 9 terms -> <=1 ulp on a few pixels
+        assert (re != eig[s]).mean() < 1e-4 and np.abs(re - eig[s]).max() < 1e-7
+        for p in ref[:120]:
+            x, y = int(round(p[0])), int(round(p[1]))
+            mask[s, max(y - 20, 0):min(y + 20, 479) + 1, max(x - 20, 0):min(x + 20, 751) + 1] = 0
+    det = batch.k_detect(imgs, mask, [80, 57])
+    for s, want in enumerate([80, 57]):
+        ref = cv2.goodFeaturesToTrack(imgs[s], want, 0.01, 20, mask=mask[s]).reshape(-1, 2)
+        assert np.array_equal(ref, det[s])
+    empty = batch.k_detect(imgs, np.zeros(imgs.shape, np.uint8), 50)     # fully masked image
+    assert all(len(e) == 0 for e in empty)
+
+
+def test_undistort_bit_exact(batch, cfg):
+    import cv2
+    K = np.array([[cfg['intrinsics']['fx'], 0, cfg['intrinsics']['cx']], [0, cfg['intrinsics']['fy'], cfg['intrinsics']['cy']], [0, 0, 1.0]])
+    D = np.array([cfg['distortion_coeffs'][k] for k in ('k1', 'k2', 'p1', 'p2')])
+    p = np.random.default_rng(2).uniform([0, 0], [752, 480], (500, 2)).astype(np.float32)
+    for to_px in (False, True):
+        ref = cv2.undistortPoints(p.reshape(-1, 1, 2), K, D, R=np.eye(3), P=(K if to_px else np.eye(3))).reshape(-1, 2)
+        assert np.array_equal(ref, batch.k_undistort(p, to_px))
+
+
+def test_ransac_masks_match_opencv(batch):
+    import cv2
+    rng = np.random.default_rng(5)
+    K = np.array([[458.654, 0, 367.215], [0, 457.296, 248.375], [0, 0, 1]])
+    P1, P2, REF = [], [], []
+    for trial in range(150):
+        n = int(rng.integers(15, 220)) if trial % 5 else int(rng.integers(1, 8))
+        X = np.stack([rng.uniform(-4, 4, n), rng.uniform(-3, 3, n), rng.uniform(2, 9, n)], 1)
+        R, _ = cv2.Rodrigues(rng.normal(0, 0.03, 3)); t = rng.normal(0, 0.08, 3)
+        x1 = (K @ X.T).T; x1 = x1[:, :2] / x1[:, 2:]
+        x2 = (K @ ((R @ X.T).T + t).T).T; x2 = x2[:, :2] / x2[:, 2:]
+        x1 += rng.normal(0, 0.15, x1.shape); x2 += rng.normal(0, 0.15, x2.shape)
+        oi = rng.choice(n, int(n * rng.uniform(0, 0.3)), replace=False)
+        x2[oi] += rng.uniform(-15, 15, (len(oi), 2))
+        p1, p2 = x1.astype(np.float32), x2.astype(np.float32)
+        m = None
+        if n >= 7:
+            _, m = cv2.findFundamentalMat(p1, p2, cv2.FM_RANSAC, 1.0, 0.99)
+        REF.append(np.ones(n, np.uint8) if m is None else m.reshape(-1))     # no mask => the reference keeps all
+        P1.append(p1); P2.append(p2)
+    masks = batch.k_ransac(P1, P2)
+    bad = sum(not np.array_equal(a, b) for a, b in zip(REF, masks))
+    assert bad <= 1, bad          # same RNG stream, same acceptance rule, same tie-breaking basis as OpenCV
+
+
+def _drive(cfg, seqs, nf, mode, S=2):
+    """Run oracle and GPU side by side. mode: 'fe' (processImage only), 'be' (oracle messages -> GPU back end),
+    'step' (fused)."""
+    from larvio_b200 import api, harness
+    from oracle.frontend import ImageProcessorOracle
+    from oracle.backend import LarVioOracle
+    b = api.Batch(cfg, n_seq=S)
+    fes = [ImageProcessorOracle(cfg.raw) for _ in range(S)]
+    bes = [LarVioOracle(cfg.raw) for _ in range(S)]
+    feed = harness.ImuFeeder(seqs[:S])
+    imu_o = [[] for _ in range(S)]; k = [0] * S
+    inited = [False] * S
+    rep = dict(msgs=0, id_mismatch=0, uv=0.0, vel=0.0, p=0.0, v=0.0, q=0.0, Prel=0.0, steps=0, ok_mismatch=0, imu_mismatch=0)
+    from larvio_b200 import synth
+    for j in range(nf):
+        feed.push_until(j)
+        msgs = []
+        for s in range(S):
+            k2 = synth.imu_window(seqs[s], k[s], seqs[s].img_t[j]); imu_o[s].extend(seqs[s].imu[k[s]:k2].tolist()); k[s] = k2
+            msgs.append(fes[s].process_image(seqs[s].images[j], seqs[s].img_t[j], np.array(imu_o[s]).reshape(-1, 7)))
+            if msgs[s] is not None and not inited[s]:
+                a = (seqs[s].img_t[j], seqs[s].gt_q[j], seqs[s].gt_p[j], seqs[s].gt_v[j], np.zeros(3), np.zeros(3))
+                bes[s].set_initial_state(*a); b.set_initial_state(s, *a); inited[s] = True
+        imgs = np.stack([seqs[s].images[j] for s in range(S)]); t_img = np.array([seqs[s].img_t[j] for s in range(S)])
+        ok = np.zeros(S, np.uint8)
+        if mode == 'fe':
+            feat, out_n, has = b.process_images(imgs, t_img, feed.buf, feed.n)
+            for s in range(S):
+                assert bool(has[s]) == (msgs[s] is not None)
+                if msgs[s] is None:
+                    continue
+                rep['msgs'] += 1
+                g = feat[s, :out_n[s]]
+                if len(g) != len(msgs[s].ids) or not np.array_equal(g['id'], msgs[s].ids):
+                    rep['id_mismatch'] += 1
+                    continue
+                uv = np.stack([g['u'], g['v'], g['u_init'], g['v_init']], 1); vel = np.stack([g['u_vel'], g['v_vel'], g['u_init_vel'], g['v_init_vel']], 1)
+                rep['uv'] = max(rep['uv'], float(np.abs(uv - msgs[s].data[:, :4]).max())); rep['vel'] = max(rep['vel'], float(np.abs(vel - msgs[s].data[:, 4:]).max()))
+            continue
+        if mode == 'be':
+            valid = np.array([m is not None for m in msgs], np.uint8)
+            if valid.any():
+                feat = np.zeros((S, b.cap), api.FEATURE_DTYPE); n_feat = np.zeros(S, np.int32); t_msg = np.zeros(S)
+                for s, m in enumerate(msgs):
+                    if m is None:
+                        continue
+                    n = len(m.ids); n_feat[s] = n; t_msg[s] = m.t; feat['id'][s, :n] = m.ids
+                    for c, name in enumerate(['u', 'v', 'u_init', 'v_init', 'u_vel', 'v_vel', 'u_init_vel', 'v_init_vel']):
+                        feat[name][s, :n] = m.data[:, c]
+                ok = b.process_features(valid, t_msg, feat, n_feat, feed.buf, feed.n)
+        else:
+            ok = b.step(imgs, t_img, feed.buf, feed.n)
+        for s in range(S):
+            oko = bes[s].process_features(msgs[s], imu_o[s]) if msgs[s] is not None else False
+            rep['ok_mismatch'] += bool(ok[s]) != bool(oko)
+            rep['imu_mismatch'] += len(imu_o[s]) != int(feed.n[s])           # consumed samples erased like larvio.cpp:510-512
+            if not oko:
+                continue
+            rep['steps'] += 1
+            st = b.get_state(s); o = bes[s].imu_state
+            rep['p'] = max(rep['p'], float(np.abs(st['p'] - o.p).max())); rep['v'] = max(rep['v'], float(np.abs(st['v'] - o.v).max()))
+            rep['q'] = max(rep['q'], float(min(np.abs(st['q'] - o.q).max(), np.abs(st['q'] + o.q).max())))
+            P = b.get_covariance(s)
+            assert P.shape == bes[s].P.shape
+            assert np.abs(P - P.T).max() == 0.0                               # symmetric by construction
+            rep['Prel'] = max(rep['Prel'], float(np.linalg.norm(P - bes[s].P) / np.linalg.norm(bes[s].P)))
+    b.close()
+    return rep
+
+
+def test_frontend_ids_bit_exact_short_sequences(cfg, seqs):
+    rep = _drive(cfg, seqs, 14, 'fe')
+    assert rep['msgs'] >= 10
+    assert rep['id_mismatch'] == 0                    # feature ids and their order: bit-exact
+    assert rep['uv'] == 0.0 and rep['vel'] == 0.0     # every stage bit-exact => identical messages
+
+
+def test_backend_matches_oracle(cfg, seqs):
+    rep = _drive(cfg, seqs, 14, 'be')
+    assert rep['steps'] >= 10 and rep['ok_mismatch'] == 0 and rep['imu_mismatch'] == 0
+    # identical feature messages in: FP64 filter agrees to rounding (stated tolerance: 1e-9 relative per step)
+    assert rep['p'] < 1e-9 and rep['v'] < 1e-9 and rep['q'] < 1e-9 and rep['Prel'] < 1e-9
+
+
+def test_fused_step_tracks_oracle(cfg, seqs):
+    rep = _drive(cfg, seqs, 14, 'step')
+    assert rep['steps'] >= 10 and rep['ok_mismatch'] == 0 and rep['imu_mismatch'] == 0
+    # GPU front end (bit-exact messages) feeds the GPU filter
+    assert rep['p'] < 1e-9 and rep['q'] < 1e-9 and rep['Prel'] < 1e-9
+
+
+def test_gpu_against_committed_golden(cfg, seqs):
+    from larvio_b200 import api, harness
+    g = np.load(GOLD)
+    b = api.Batch(cfg, n_seq=2)
+    feed = harness.ImuFeeder(seqs)
+    inited = [False, False]
+    checked = 0
+    for j in range(14):
+        feed.push_until(j)
+        imgs = np.stack([seqs[s].images[j] for s in range(2)]); t_img = np.array([seqs[s].img_t[j] for s in range(2)])
+        feat, out_n, has = b.process_images(imgs, t_img, feed.buf, feed.n)
+        for s in range(2):
+            key = "ids_%d_%d" % (s, j)
+            assert bool(has[s]) == (key in g.files)
+            if has[s]:
+                assert np.array_equal(feat[s, :out_n[s]]['id'], g[key])
+                if not inited[s]:
+                    b.set_initial_state(s, seqs[s].img_t[j], seqs[s].gt_q[j], seqs[s].gt_p[j], seqs[s].gt_v[j], np.zeros(3), np.zeros(3)); inited[s] = True
+        if has.any():
+            t_msg = np.where(has, t_img, 0.0)
+            ok = b.process_features(has, t_msg, feat, out_n, feed.buf, feed.n)
+            for s in range(2):
+                key = "state_%d_%d" % (s, j)
+                assert bool(ok[s]) == (key in g.files)
+                if ok[s]:
+                    st = b.get_state(s)
+                    got = np.concatenate([st['q'], st['p'], st['v'], st['bg'], st['ba']])
+                    assert np.abs(got - g[key]).max() < 1e-9
+                    P = b.get_covariance(s)
+                    assert P.shape[0] == int(g["Pfro_%d_%d" % (s, j)][1])
+                    assert abs(np.linalg.norm(P) / g["Pfro_%d_%d" % (s, j)][0] - 1) < 1e-9
+                    assert np.allclose(np.diag(P), g["Pdiag_%d_%d" % (s, j)], rtol=1e-8, atol=1e-14)
+                    checked += 1
+    b.close()
+    assert checked >= 16
+
+
+def test_batch_invariance_and_properties_at_full_batch(cfg, seqs):
+    """Size-independent properties at BASELINE's batch size: 64 sequences (the same two inputs replicated)
+    must give bit-identical results per replica; P stays symmetric PSD; quaternions stay unit."""
+    from larvio_b200 import api, harness
+    S = 64
+    rep_seqs = [seqs[s % 2] for s in range(S)]
+    b = api.Batch(cfg, n_seq=S)
+    feed = harness.ImuFeeder(rep_seqs)
+    for s in range(S):
+        b.set_initial_state(s, rep_seqs[s].img_t[0], rep_seqs[s].gt_q[0], rep_seqs[s].gt_p[0], rep_seqs[s].gt_v[0], np.zeros(3), np.zeros(3))
+    for j in range(12):
+        feed.push_until(j)
+        imgs = np.stack([rep_seqs[s].images[j] for s in range(S)]); t_img = np.array([rep_seqs[s].img_t[j] for s in range(S)])
+        b.step(imgs, t_img, feed.buf, feed.n)
+    st = b.get_states()
+    for s in range(2, S):
+        assert np.array_equal(st[s], st[s % 2]), s
+    for s in (0, 1, 63):
+        P = b.get_covariance(s)
+        assert np.abs(P - P.T).max() == 0.0 and np.linalg.eigvalsh(P).min() > -1e-12
+        assert abs(np.linalg.norm(st[s, 1:5]) - 1) < 1e-9
+    b.close()
+
+
+def test_unsupported_configs_fail_loudly(lib_built):
+    from larvio_b200 import api
+    from larvio_b200.config import Config
+    c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"))      # hybrid SLAM features on (max_features_in_one_grid: 1)
+    b = api.Batch(c, n_seq=1)
+    imu = np.zeros((1, 8), api.IMU_DTYPE); n = np.zeros(1, np.int32)
+    with pytest.raises(api.LarvioB200Error) as e:
+        b.step(np.zeros((1, 480, 752), np.uint8), np.array([0.1]), imu, n)
+    assert "not built yet" in str(e.value)
+    b.close()
