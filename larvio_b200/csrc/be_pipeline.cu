@@ -971,7 +971,60 @@ __global__ void __launch_bounds__(256) be_gemm_kernel(GemmArgs g) {
 }
 
 // ====================================================================== Cholesky S = L L^T (lower, in place) + z = L^-1 r
-__global__ void __launch_bounds__(512) be_chol_kernel(BeView v) {
+// The packed lower triangle (r <= 208 -> <= 174 KB) lives in shared memory for the whole factorisation; the
+// right-looking update runs out of smem, L is written back to Sm (TRSM reads it) at the end.
+__global__ void __launch_bounds__(1024) be_chol_kernel(BeView v) {
+  extern __shared__ double csm[];   // packed lower triangle [r(r+1)/2] + column cache [r] + z [r]
+  const int s = blockIdx.x, tid = threadIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK]) return;
+  const int r = ic[I_R];
+  if (r <= 0) return;
+  const int LD = v.be.LD;
+  double* S = v.be.Sm + (size_t)s * LD * LD;
+  double* Lp = csm;
+  double* col = csm + (size_t)v.be.Dmax * (v.be.Dmax + 1) / 2;
+  double* z = col + v.be.Dmax;
+#define LP(i, j) Lp[(size_t)(i) * ((i) + 1) / 2 + (j)]
+  for (int e = tid; e < r * r; e += 1024) { const int i = e / r, j = e - i * r; if (j <= i) LP(i, j) = S[(size_t)i * LD + j]; }
+  __syncthreads();
+  for (int j = 0; j < r; ++j) {
+    const double djj = sqrt(LP(j, j));
+    const double inv = 1.0 / djj;
+    __syncthreads();
+    for (int i = j + tid; i < r; i += 1024) {
+      const double x = (i == j) ? djj : LP(i, j) * inv;
+      LP(i, j) = x;
+      col[i] = x;
+    }
+    __syncthreads();
+    const int n = r - j - 1;
+    // trailing update of the lower triangle: rows a in (j, r), columns b in (j, a]
+    for (int e = tid; e < n * n; e += 1024) {
+      const int a = j + 1 + e / n, b2 = j + 1 + e % n;
+      if (b2 <= a) LP(a, b2) -= col[a] * col[b2];
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < r * r; e += 1024) { const int i = e / r, j = e - i * r; if (j <= i) S[(size_t)i * LD + j] = LP(i, j); }
+  // z = L^-1 r  (warp 0, row oriented, out of smem)
+  if (tid < 32) {
+    const double* rs = v.be.rs + (size_t)s * v.be.RMAX;
+    for (int i = 0; i < r; ++i) {
+      double part = 0.0;
+      for (int q = tid; q < i; q += 32) part += LP(i, q) * z[q];
+      part = warp_sum_d(part);
+      if (tid == 0) z[i] = (rs[i] - part) / LP(i, i);
+      __syncwarp();
+    }
+    double* zg = v.be.zvec + (size_t)s * LD;
+    for (int i = tid; i < r; i += 32) zg[i] = z[i];
+  }
+#undef LP
+}
+
+// global-memory variant for windows whose packed S does not fit in shared memory (sw_size > ~33)
+__global__ void __launch_bounds__(512) be_chol_gmem_kernel(BeView v) {
   extern __shared__ double csm[];   // column cache [LD]
   const int s = blockIdx.x, tid = threadIdx.x;
   int* ic = icore_of(v, s);
@@ -1347,6 +1400,8 @@ int be_alloc(LvbHandle* h) {
   // dynamic shared memory opt-ins
   const int fsm_bytes = (int)sizeof(double) * (6 * be->Wcap + 8 + 4 * be->Wcap * be->Wcap + 2 * be->Wcap);
   LVB_CUDA(cudaFuncSetAttribute(be_feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm_bytes));
+  const size_t chol_bytes = sizeof(double) * ((size_t)be->Dmax * (be->Dmax + 1) / 2 + 2 * be->Dmax);
+  if (chol_bytes <= 227 * 1024) LVB_CUDA(cudaFuncSetAttribute(be_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_bytes));
   return LVB_OK;
 }
 
@@ -1390,8 +1445,10 @@ static int be_update(LvbHandle* h, BeView& v) {
   g.C = be->Sm; g.sC = LD * LD; g.rsC = (int)LD; g.csC = 1;
   g.m_idx = I_R; g.n_idx = I_R; g.k_idx = I_DIM; g.alpha = 1.0; g.beta = 0.0; g.diag = v.cfg.sfeat2;
   RC(launch_gemm(h, g));
+  const size_t chol_bytes = sizeof(double) * ((size_t)be->Dmax * (be->Dmax + 1) / 2 + 2 * be->Dmax);
   LVB_PROF(h, "be_chol_kernel");
-  be_chol_kernel<<<be->S, 512, sizeof(double) * LD, st>>>(v);
+  if (chol_bytes <= 227 * 1024) be_chol_kernel<<<be->S, 1024, chol_bytes, st>>>(v);
+  else be_chol_gmem_kernel<<<be->S, 512, sizeof(double) * LD, st>>>(v);
   LVB_LAUNCH_CHECK(h);
   BeView vt = v;
   LVB_PROF(h, "be_trsm_kernel");

@@ -81,8 +81,10 @@ struct LkArgs {
   int max_level;
 };
 
-__global__ void __launch_bounds__(WARPS * 32) lk_kernel(LkArgs a) {
+struct LkArgs2 { LkArgs a[2]; };
+__global__ void __launch_bounds__(WARPS * 32) lk_kernel(const __grid_constant__ LkArgs2 aa) {
   __shared__ WarpSmem sm[WARPS];
+  const LkArgs& a = aa.a[blockIdx.z];
   const int s = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * WARPS + warp;
@@ -277,11 +279,9 @@ __global__ void __launch_bounds__(WARPS * 32) lk_kernel(LkArgs a) {
 
 }  // namespace
 
-int fe_lk_launch(LvbHandle* h, const uint8_t* pyrA, const uint8_t* pyrB, int n_seq, int stride,
-                 const float2* ptsA, const int* perm, const int* n_pts, const float2* init, int init_by_slot,
-                 const float* Hmat, float2* out, uint8_t* status, int gate_mode, const float2* ref) {
-  if (h->cfg.patch_size != WIN) return lvb_set_err(LVB_E_UNSUPPORTED, "patch_size %d (kernel is built for 21)", h->cfg.patch_size);
-  LkArgs a;
+static void fill_lk_args(LvbHandle* h, LkArgs& a, const uint8_t* pyrA, const uint8_t* pyrB, int stride, const float2* ptsA,
+                         const int* perm, const int* n_pts, const float2* init, int init_by_slot, const float* Hmat, float2* out,
+                         uint8_t* status, int gate_mode, const float2* ref) {
   a.pyrA = pyrA; a.pyrB = pyrB; a.L = h->fe.L; a.stride = stride; a.ptsA = ptsA; a.perm = perm;
   a.n_pts = n_pts; a.init = init; a.init_by_slot = init_by_slot; a.Hmat = Hmat; a.out = out; a.status = status;
   a.gate_mode = gate_mode; a.ref = ref;
@@ -289,9 +289,34 @@ int fe_lk_launch(LvbHandle* h, const uint8_t* pyrA, const uint8_t* pyrB, int n_s
   double eps = h->cfg.track_precision; if (eps < 0) eps = 0; if (eps > 10) eps = 10;
   a.max_iter = mi; a.eps2 = eps * eps; a.min_eig = 1e-4;
   a.max_level = h->cfg.pyramid_levels;
-  dim3 grd((stride + WARPS - 1) / WARPS, n_seq);
+}
+
+int fe_lk_launch(LvbHandle* h, const uint8_t* pyrA, const uint8_t* pyrB, int n_seq, int stride,
+                 const float2* ptsA, const int* perm, const int* n_pts, const float2* init, int init_by_slot,
+                 const float* Hmat, float2* out, uint8_t* status, int gate_mode, const float2* ref) {
+  if (h->cfg.patch_size != WIN) return lvb_set_err(LVB_E_UNSUPPORTED, "patch_size %d (kernel is built for 21)", h->cfg.patch_size);
+  LkArgs2 aa;
+  fill_lk_args(h, aa.a[0], pyrA, pyrB, stride, ptsA, perm, n_pts, init, init_by_slot, Hmat, out, status, gate_mode, ref);
+  aa.a[1] = aa.a[0];
+  dim3 grd((stride + WARPS - 1) / WARPS, n_seq, 1);
   LVB_PROF(h, "lk_kernel");
-  lk_kernel<<<grd, WARPS * 32, 0, h->stream>>>(a);
+  lk_kernel<<<grd, WARPS * 32, 0, h->stream>>>(aa);
+  LVB_LAUNCH_CHECK(h);
+  return LVB_OK;
+}
+
+// both chains (tracked + new) of one direction in a single launch (gridDim.z = 2)
+int fe_lk_launch2(LvbHandle* h, const uint8_t* pyrA, const uint8_t* pyrB, int n_seq, int stride,
+                  const float2* const ptsA[2], int* const perm[2], int* const n_pts[2], const float2* const init[2],
+                  int init_by_slot, const float* Hmat, float2* const out[2], uint8_t* const status[2], int gate_mode,
+                  const float2* const ref[2]) {
+  LkArgs2 aa;
+  for (int c = 0; c < 2; ++c)
+    fill_lk_args(h, aa.a[c], pyrA, pyrB, stride, ptsA[c], perm[c], n_pts[c], init ? init[c] : nullptr, init_by_slot, Hmat, out[c],
+                 status[c], gate_mode, ref ? ref[c] : nullptr);
+  dim3 grd((stride + WARPS - 1) / WARPS, n_seq, 2);
+  LVB_PROF(h, "lk_kernel");
+  lk_kernel<<<grd, WARPS * 32, 0, h->stream>>>(aa);
   LVB_LAUNCH_CHECK(h);
   return LVB_OK;
 }

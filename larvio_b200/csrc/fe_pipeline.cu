@@ -446,15 +446,16 @@ int fe_process(LvbHandle* h, const uint8_t* images, int on_device, const double*
   iota_perm_kernel<<<dim3((N + 127) / 128, S), 128, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
   const float2* src[2] = {fe.trk[prv].curr, fe.new_pts};
-  // forward LK (+ in-image gate)
-  for (int c = 0; c < 2; ++c)
-    RC(fe_lk_launch(h, fe.pyr[prv], fe.pyr[cur], S, N, src[c], fe.ch[c].perm, fe.ch[c].n, nullptr, 0, fe.Hmat,
-                    fe.ch[c].out, fe.ch[c].status, 1, nullptr));
+  int* perm2[2] = {fe.ch[0].perm, fe.ch[1].perm};
+  int* n2[2] = {fe.ch[0].n, fe.ch[1].n};
+  float2* out2[2] = {fe.ch[0].out, fe.ch[1].out};
+  uint8_t* st2[2] = {fe.ch[0].status, fe.ch[1].status};
+  const float2* cur2[2] = {fe.ch[0].slot_curr, fe.ch[1].slot_curr};
+  // forward LK (+ in-image gate), tracked and new chains in one launch
+  RC(fe_lk_launch2(h, fe.pyr[prv], fe.pyr[cur], S, N, src, perm2, n2, nullptr, 0, fe.Hmat, out2, st2, 1, nullptr));
   RC(run_compaction(h, 0));
   // backward LK (+ in-image + 1-px consistency gate)
-  for (int c = 0; c < 2; ++c)
-    RC(fe_lk_launch(h, fe.pyr[cur], fe.pyr[prv], S, N, fe.ch[c].slot_curr, fe.ch[c].perm, fe.ch[c].n, src[c], 1,
-                    nullptr, fe.ch[c].out, fe.ch[c].status, 2, src[c]));
+  RC(fe_lk_launch2(h, fe.pyr[cur], fe.pyr[prv], S, N, cur2, perm2, n2, src, 1, nullptr, out2, st2, 2, src));
   RC(run_compaction(h, 1));
   // descriptor gate: tracked features against the descriptor stored at birth, new ones prev vs curr
   RC(fe_orb_launch(h, fe.pyr[cur], fe.blur[cur], S, N, fe.ch[0].slot_curr, fe.ch[0].perm, fe.ch[0].n, nullptr, nullptr, 0,

@@ -157,6 +157,10 @@ int fe_build_pyramid(LvbHandle* h, const uint8_t* d_images /*[n][H][W]*/, int n,
 int fe_lk_launch(LvbHandle* h, const uint8_t* pyrA, const uint8_t* pyrB, int n_seq, int stride,
                  const float2* ptsA, const int* perm, const int* n_pts, const float2* init, int init_by_slot,
                  const float* Hmat, float2* out, uint8_t* status, int gate_mode, const float2* ref);
+int fe_lk_launch2(LvbHandle* h, const uint8_t* pyrA, const uint8_t* pyrB, int n_seq, int stride,
+                  const float2* const ptsA[2], int* const perm[2], int* const n_pts[2], const float2* const init[2],
+                  int init_by_slot, const float* Hmat, float2* const out[2], uint8_t* const status[2], int gate_mode,
+                  const float2* const ref[2]);
 int fe_orb_launch(LvbHandle* h, const uint8_t* pyr, const uint8_t* blur, int n_seq, int stride,
                   const float2* pts, const int* perm, const int* n_pts, float* angles, uint8_t* desc_out,
                   int out_by_slot, const uint8_t* desc_ref, uint8_t* status, int* dist_out);

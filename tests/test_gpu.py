@@ -158,7 +158,7 @@ def _drive(cfg, seqs, nf, mode, S=2):
     b = api.Batch(cfg, n_seq=S)
     fes = [ImageProcessorOracle(cfg.raw) for _ in range(S)]
     bes = [LarVioOracle(cfg.raw) for _ in range(S)]
-    feed = harness.ImuFeeder(seqs[:S])
+    feed = harness.ImuFeeder(seqs[:S], stride=256)     # 'fe' mode never erases consumed samples
     imu_o = [[] for _ in range(S)]; k = [0] * S
     inited = [False] * S
     rep = dict(msgs=0, id_mismatch=0, uv=0.0, vel=0.0, p=0.0, v=0.0, q=0.0, Prel=0.0, steps=0, ok_mismatch=0, imu_mismatch=0)
@@ -244,7 +244,7 @@ def test_gpu_against_committed_golden(cfg, seqs):
     from larvio_b200 import api, harness
     g = np.load(GOLD)
     b = api.Batch(cfg, n_seq=2)
-    feed = harness.ImuFeeder(seqs)
+    feed = harness.ImuFeeder(seqs, stride=256)
     inited = [False, False]
     checked = 0
     for j in range(14):
