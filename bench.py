@@ -30,6 +30,10 @@ from larvio_b200 import synth                  # noqa: E402
 
 W_IMG, H_IMG = 752, 480
 B0 = W_IMG * H_IMG
+# FP64 peak is not in MEASURED_PEAKS.json (bf16 + HBM only): nominal B200 FP64 vector rate, stated as such.
+FP64_PEAK_TF = 37.0
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
+NCU_TRAFFIC = {}
 
 
 def load_cfg(args):
@@ -163,19 +167,24 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- roofline models
-def kernel_models(S, N, d, frames_per_launchset=1):
-    """Algorithmic bytes (HBM-bound kernels) or flops (FP64 kernels) per LAUNCH, per DESIGN.md §Kernels.
-    Front-end figures are SURVEY.md §8(d)'s per-frame-per-sequence bytes x S sequences per launch."""
+def kernel_models(S_sub, stats, n_frames, n_sub):
+    """ALGORITHMIC bytes (HBM-bound kernels) or FP64 flops per LAUNCH, DESIGN.md §4 / SURVEY.md §8(d):
+    per-unit figure x the units one launch processes.  `stats` are the device-side work counters of the profiled
+    frames summed over sub-batches (lvb_get_stats), so point/row counts are measured, not assumed.  A launch covers
+    one sub-batch of S_sub sequences; there are n_sub sub-batches and n_frames profiled frames."""
+    lk_pts, orb_desc, det_runs, msgs, upd, sum_r, sum_rdd, sum_rows, qr_runs, sum_rcc = [float(x) for x in stats[:10]]
+    nl = max(n_frames * n_sub, 1)          # launch-sets
     m = {}
-    m["clahe_lut_kernel"] = ("hbm", B0 * S)
-    m["clahe_apply_kernel"] = ("hbm", 2 * B0 * S)
-    m["pad_reflect_kernel"] = ("hbm", None)
-    m["pyrdown_kernel"] = ("hbm", None)
-    m["blur7_kernel"] = ("hbm", 2 * B0 * S)
-    m["mineig_kernel"] = ("hbm", (B0 + 4 * B0) * S)        # u8 in, f32 response map out (half the sequences publish)
-    m["candidates_kernel"] = ("hbm", 4 * B0 * S)
-    m["lk_kernel"] = ("hbm", None)                           # filled from the measured point counts
-    m["orb_kernel"] = ("hbm", None)
+    m["clahe_lut_kernel"] = ("hbm", B0 * S_sub, "read 752x480 u8 per sequence")
+    m["clahe_apply_kernel"] = ("hbm", 2 * B0 * S_sub, "read + write 752x480 u8 per sequence")
+    m["pyrdown_kernel"] = ("hbm", (B0 + B0 // 4 + B0 // 4 + B0 // 16) // 2 * S_sub, "SURVEY F3 over its 2 launches")
+    m["blur7_kernel"] = ("hbm", 2 * B0 * S_sub, "SURVEY F4")
+    m["mineig_kernel"] = ("hbm", (B0 + 4 * B0) * det_runs / nl, "u8 in + f32 response out, sequences that detect")
+    m["candidates_kernel"] = ("hbm", (4 * B0 + B0) * det_runs / nl, "f32 response + u8 mask in")
+    m["lk_kernel"] = ("hbm", 6060.0 * lk_pts / (2 * nl), "6060 B per point-track (SURVEY F6), 2 launches per frame")
+    m["orb_kernel"] = ("hbm", 2986.0 * orb_desc / (3 * nl), "2986 B per descriptor (SURVEY F7), 3 launches per frame")
+    m["be_gemm_kernel"] = ("fp64", (4.0 * sum_rdd / (6 * nl)) if upd else None, "T=HP and P-=Y^TY: 2rd^2 each (S=TH^T not counted), 6 launches per frame")
+    m["be_qr_kernel"] = ("fp64", (2.0 * sum_rcc / (2 * nl)) if qr_runs else None, "2Rc^2 per compression, 2 launches per frame")
     return m
 
 
@@ -190,6 +199,8 @@ def main():
     ap.add_argument("--window", type=int, default=30)
     ap.add_argument("--cpu-frames", type=int, default=16, help="frames per sequence of the bounded cpu_baseline sample")
     ap.add_argument("--profile-steps", type=int, default=8)
+    ap.add_argument("--streams", type=int, default=2,
+                    help="sub-batches per GPU, each an independent handle/stream driven by its own host thread")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -198,7 +209,7 @@ def main():
     S, K, Wm = args.seqs, args.steps, args.warmup
     cfg = load_cfg(args)
     workload = "configs[2]: %d batched synthetic 752x480@20Hz+200Hz-IMU sequences per GPU, %d tracks, %d-pose window, MSCKF-only" % (S, args.tracks, args.window)
-    config = dict(workload=workload, sequences_per_gpu=S, tracks=args.tracks, window=args.window, image="752x480 u8",
+    config = dict(workload=workload, sequences_per_gpu=S, sub_batches_per_gpu=args.streams, tracks=args.tracks, window=args.window, image="752x480 u8",
                   l2_policy="each step reads a fresh %.1f MB image batch and touches >250 MB of per-sequence state (> 126 MB L2)" % (S * B0 / 1e6))
     ncores = os.cpu_count() or 1
 
@@ -246,9 +257,20 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    b = api.Batch(cfg, n_seq=S, device=local_rank)
-    for s in range(S):
-        b.set_initial_state(s, seqs[s].img_t[0], seqs[s].gt_q[0], seqs[s].gt_p[0], seqs[s].gt_v[0], np.zeros(3), np.zeros(3))
+    NSUB = max(1, min(args.streams, S))
+    bounds = [(S * i) // NSUB for i in range(NSUB + 1)]          # sub-batch i owns sequences [bounds[i], bounds[i+1])
+
+    def make_batches():
+        bs = []
+        for i in range(NSUB):
+            lo, hi = bounds[i], bounds[i + 1]
+            bb = api.Batch(cfg, n_seq=hi - lo, device=local_rank)
+            for s in range(lo, hi):
+                bb.set_initial_state(s - lo, seqs[s].img_t[0], seqs[s].gt_q[0], seqs[s].gt_p[0], seqs[s].gt_v[0], np.zeros(3), np.zeros(3))
+            bs.append(bb)
+        return bs
+
+    batches = make_batches()
     frames_host = np.stack([np.stack([seqs[s].images[j] for s in range(S)]) for j in range(n_frames)])   # [F][S][H][W]
     pinned = torch.from_numpy(frames_host).pin_memory()
     t_img = np.stack([[seqs[s].img_t[j] for s in range(S)] for j in range(n_frames)])
@@ -267,27 +289,47 @@ def main():
             arr[s, :len(r)] = r
         inc.append((m, arr))
     IMU_STRIDE = 96
-    ar_s = np.arange(S)
 
-    def run_pass(mode, lo, hi, state):
-        """mode 'dev': images resident in HBM; 'e2e': pinned host images, H2D + state read-back inside the step."""
-        imu, n_imu = state
-        for j in range(lo, hi):
+    def sub_pass(i, mode, lo_f, hi_f, state):
+        """Driver loop of sub-batch i over frames [lo_f, hi_f) (app/larvioMain.cpp:87-117 for its sequences)."""
+        bb = batches[i]
+        lo, hi = bounds[i], bounds[i + 1]
+        n = hi - lo
+        imu, n_imu = state[i]
+        ar = np.arange(n)
+        for j in range(lo_f, hi_f):
             m, arr = inc[j]
+            m = m[lo:hi]; arr = arr[lo:hi]
             mm = arr.shape[1]
             cols = n_imu[:, None] + np.arange(mm)[None, :]
             valid = np.arange(mm)[None, :] < m[:, None]
-            rr = np.broadcast_to(ar_s[:, None], cols.shape)[valid]; cc = cols[valid]
+            rr = np.broadcast_to(ar[:, None], cols.shape)[valid]; cc = cols[valid]
             imu["t"][rr, cc] = arr[:, :, 0][valid]; imu["gyro"][rr, cc] = arr[:, :, 1:4][valid]; imu["acc"][rr, cc] = arr[:, :, 4:7][valid]
             n_imu += m.astype(np.int32)
             if mode == "dev":
-                b.step(dev_frames[j].data_ptr(), t_img[j], imu, n_imu, images_on_device=True)
+                bb.step(dev_frames[j, lo:hi].data_ptr(), t_img[j, lo:hi], imu, n_imu, images_on_device=True)
             else:
-                b.step(pinned[j].numpy(), t_img[j], imu, n_imu)
-                b.get_states()
+                bb.step(pinned[j, lo:hi].numpy(), t_img[j, lo:hi], imu, n_imu)
+                bb.get_states()
+
+    def run_pass(mode, lo_f, hi_f, state):
+        if NSUB == 1:
+            sub_pass(0, mode, lo_f, hi_f, state)
+            return
+        ths = [threading.Thread(target=sub_pass, args=(i, mode, lo_f, hi_f, state)) for i in range(NSUB)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
 
     def fresh_state():
-        return np.zeros((S, IMU_STRIDE), api.IMU_DTYPE), np.zeros(S, np.int32)
+        return [(np.zeros((bounds[i + 1] - bounds[i], IMU_STRIDE), api.IMU_DTYPE), np.zeros(bounds[i + 1] - bounds[i], np.int32)) for i in range(NSUB)]
+
+    def launches_total():
+        return sum(bb.launches for bb in batches)
+
+    def all_states():
+        return np.concatenate([bb.get_states() for bb in batches], 0)
 
     def barrier():
         torch.cuda.synchronize()
@@ -296,11 +338,10 @@ def main():
         torch.cuda.synchronize()
 
     def reset_batch():
-        nonlocal b
-        b.close()
-        b = api.Batch(cfg, n_seq=S, device=local_rank)
-        for s in range(S):
-            b.set_initial_state(s, seqs[s].img_t[0], seqs[s].gt_q[0], seqs[s].gt_p[0], seqs[s].gt_v[0], np.zeros(3), np.zeros(3))
+        nonlocal batches
+        for bb in batches:
+            bb.close()
+        batches = make_batches()
 
     # ---- device-resident pass: `value`
     dev_frames = pinned.to("cuda", non_blocking=False)
@@ -308,7 +349,7 @@ def main():
     run_pass("dev", 0, Wm, st)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    l0 = b.launches
+    l0 = launches_total()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(); t0 = time.perf_counter()
     run_pass("dev", Wm, Wm + K, st)
@@ -316,13 +357,23 @@ def main():
     ms_dev = max(e0.elapsed_time(e1), 1e3 * wall * 0.0)     # each step ends with a stream sync, so events == wall
     barrier()
     clocks = sampler.stop() if sampler else None
-    launches = b.launches - l0
+    launches = launches_total() - l0
     # ---- per-kernel profile on the next frames (not part of the timed region)
-    b.profile(True)
-    run_pass("dev", Wm + K, n_frames, st)
-    prof = b.profile_get()
-    b.profile(False)
-    states_dev = b.get_states()
+    prof = {}
+    prof_stats = []
+    if args.profile_steps > 0:
+        stats0 = [bb.stats() for bb in batches]
+        for bb in batches:
+            bb.profile(True)
+        for i in range(NSUB):                      # one sub-batch at a time: per-kernel times without co-running streams
+            sub_pass(i, "dev", Wm + K, n_frames, st)
+        for bb in batches:
+            for kname, (ms, cnt) in bb.profile_get().items():
+                a0, c0 = prof.get(kname, (0.0, 0))
+                prof[kname] = (a0 + ms, c0 + cnt)
+            bb.profile(False)
+        prof_stats = [[a1 - a0 for a0, a1 in zip(s0, bb.stats())] for s0, bb in zip(stats0, batches)]
+    states_dev = all_states()
     # ---- end-to-end pass: `e2e` (fresh filters, same frames, host buffers)
     reset_batch()
     st = fresh_state()
@@ -337,7 +388,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         # trajectory gather: final states of every rank to all ranks over NCCL
-        mine = torch.from_numpy(b.get_states()).cuda()
+        mine = torch.from_numpy(all_states()).cuda()
         gathered = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine)
     ms_dev, ms_e2e = float(t[0]), float(t[1])
@@ -352,22 +403,33 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         tot = sum(v[0] for v in prof.values()) or 1.0
-        top = sorted(prof.items(), key=lambda kv: -kv[1][0])
+        top = sorted(prof.items(), key=lambda kv: -kv[1][0]) or [("none", (0.0, 0))]
         kernel_share = {kname: dict(ms_per_launch=v[0] / max(v[1], 1), launches=v[1], share=v[0] / tot) for kname, v in top[:12]}
         dom, (dom_ms, dom_n) = top[0]
-        n_tr = float(np.mean([np.isfinite(x) for x in states_dev[:, 0]]))  # placeholder use
-        models = kernel_models(S, args.tracks, 22 + 6 * args.window)
-        roof = dict(kernel=dom, bound="hbm", achieved=None, peak=hbm_peak, unit="GB/s", frac=None, traffic=None, peak_source=peak_src,
+        pstats = [sum(x) for x in zip(*prof_stats)] if prof_stats else [0] * 16
+        models = kernel_models(S // NSUB, pstats, args.profile_steps, NSUB)
+        roofs = {}
+        for kname, v in top[:14]:
+            mdl = models.get(kname)
+            if not mdl or not mdl[1]:
+                continue
+            per_launch_ms = v[0] / max(v[1], 1)
+            if mdl[0] == "hbm":
+                ach = mdl[1] / (per_launch_ms * 1e-3) / 1e9
+                roofs[kname] = dict(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, algorithmic_bytes_per_launch=mdl[1], basis=mdl[2])
+            else:
+                ach = mdl[1] / (per_launch_ms * 1e-3) / 1e12
+                roofs[kname] = dict(bound="fp64", achieved=ach, peak=FP64_PEAK_TF, unit="TFLOP/s", frac=ach / FP64_PEAK_TF, flops_per_launch=mdl[1], basis=mdl[2])
+        roof = dict(kernel=dom, bound="hbm", achieved=None, peak=hbm_peak, unit="GB/s", frac=None, traffic=NCU_TRAFFIC.get(dom), peak_source=peak_src,
                     ms_per_launch=dom_ms / max(dom_n, 1))
-        mdl = models.get(dom)
-        if mdl and mdl[1]:
-            ach = mdl[1] / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9
-            roof.update(achieved=ach, frac=ach / hbm_peak)
+        if dom in roofs:
+            roof.update({kk: roofs[dom][kk] for kk in ("bound", "achieved", "peak", "unit", "frac")})
+            roof["basis"] = roofs[dom]["basis"]
         line = dict(metric="batched VIO frames/sec", value=value, unit="frames/s", n_gpus=world, steps=K, warmup=Wm,
                     ms_per_step=ms_dev / K, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="u8+f32 front end, f64 filter", data="synthetic", config=config,
                     e2e=dict(value=e2e_val, unit="frames/s", h2d_bytes_per_step=int(S * B0 + S * 10 * 56), d2h_bytes_per_step=int(S * 17 * 8 + S * 32 * 4 + S)),
-                    gpu_launches=int(launches), clocks=clocks, roofline=roof, kernels=kernel_share,
+                    gpu_launches=int(launches), clocks=clocks, roofline=roof, kernels=kernel_share, kernel_rooflines=roofs, work_counters=pstats,
                     ekf_update_ms_per_seq=None, cpu_baseline=cpu_baseline, gen_seconds=t_gen, wall_dev_s=wall, wall_e2e_s=wall_e2e)
         print(json.dumps(line))
     if world > 1:

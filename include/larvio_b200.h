@@ -162,6 +162,10 @@ int lvb_profile_enable(LvbHandle* h, int on);
 int lvb_profile_reset(LvbHandle* h);
 int lvb_profile_get(LvbHandle* h, const char** names, double* total_ms, long long* counts, int cap);
 
+/* Cumulative work counters (device-side): [0] LK point-tracks, [1] ORB descriptors, [2] detector runs,
+ * [3] published messages, [4] EKF updates, [5] sum r, [6] sum r*d*d, [7] sum stacked rows, [8] QR runs, [9] sum R*c*c. */
+int lvb_get_stats(LvbHandle* h, unsigned long long* out16);
+
 /* number of kernel launches issued through this handle so far (bench.py gpu_launches). */
 long long lvb_launch_count(const LvbHandle* h);
 

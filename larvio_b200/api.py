@@ -62,6 +62,8 @@ _lib.lvb_n_seq.argtypes = [_vp]
 _lib.lvb_synchronize.argtypes = [_vp]
 _lib.lvb_profile_enable.argtypes = [_vp, C.c_int]
 _lib.lvb_profile_reset.argtypes = [_vp]
+_lib.lvb_get_stats.argtypes = [_vp, C.POINTER(C.c_ulonglong)]
+_lib.lvb_get_stats.restype = C.c_int
 _lib.lvb_profile_get.argtypes = [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
 for _name in ("lvbk_pyramid", "lvbk_lk", "lvbk_orb", "lvbk_detect", "lvbk_undistort", "lvbk_ransac",
               "lvb_process_images", "lvb_process_features", "lvb_step", "lvb_set_initial_state",
@@ -74,7 +76,7 @@ EXPORTED_SYMBOLS = [
     "lvb_feature_capacity", "lvb_n_seq", "lvb_process_images", "lvb_process_features", "lvb_step",
     "lvb_synchronize", "lvb_set_initial_state", "lvb_get_state", "lvb_get_states", "lvb_get_window",
     "lvb_get_covariance", "lvbk_pyramid", "lvbk_lk", "lvbk_orb", "lvbk_detect", "lvbk_undistort",
-    "lvbk_ransac", "lvb_launch_count", "lvb_profile_enable", "lvb_profile_reset", "lvb_profile_get",
+    "lvbk_ransac", "lvb_launch_count", "lvb_profile_enable", "lvb_profile_reset", "lvb_profile_get", "lvb_get_stats",
 ]
 
 
@@ -132,6 +134,11 @@ class Batch:
         names = (C.c_char_p * cap)(); ms = (C.c_double * cap)(); cnt = (C.c_longlong * cap)()
         n = _lib.lvb_profile_get(self._h, names, ms, cnt, cap)
         return {names[i].decode(): (ms[i], int(cnt[i])) for i in range(min(n, cap))}
+
+    def stats(self):
+        out = (C.c_ulonglong * 16)()
+        _check(_lib.lvb_get_stats(self._h, out))
+        return [int(x) for x in out]
 
     def synchronize(self):
         _check(_lib.lvb_synchronize(self._h))

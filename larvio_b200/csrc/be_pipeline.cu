@@ -745,12 +745,24 @@ __global__ void __launch_bounds__(32) be_feature_kernel(BeView v, double* Traw) 
   if (R > 0 && R < 100) {
     const double* Hj = H + (size_t)3 * LD;
     double* Tp = Tj + (size_t)3 * LD;
-    for (int j = lane; j < nz; j += 32) {           // T = H_nz * P[nz, nz]
+    // T = H_nz * P[nz, nz]: one column of T per lane; each P element is loaded once and reused for a chunk of
+    // 16 rows held in registers (the H entries are warp-uniform broadcasts)
+    for (int j = lane; j < nz; j += 32) {
       const int c2 = nzcol(j);
-      for (int a = 0; a < R; ++a) {
-        double acc = 0.0;
-        for (int q = 0; q < nz; ++q) { const int c1 = nzcol(q); acc += Hj[(size_t)a * LD + c1] * P[(size_t)c1 * LD + c2]; }
-        Tp[(size_t)a * LD + c2] = acc;
+      for (int a0 = 0; a0 < R; a0 += 16) {
+        double acc[16];
+#pragma unroll
+        for (int a = 0; a < 16; ++a) acc[a] = 0.0;
+        for (int q = 0; q < nz; ++q) {
+          const int c1 = nzcol(q);
+          const double pv = P[(size_t)c1 * LD + c2];
+#pragma unroll
+          for (int a = 0; a < 16; ++a)
+            if (a0 + a < R) acc[a] += Hj[(size_t)(a0 + a) * LD + c1] * pv;
+        }
+#pragma unroll
+        for (int a = 0; a < 16; ++a)
+          if (a0 + a < R) Tp[(size_t)(a0 + a) * LD + c2] = acc[a];
       }
     }
     __syncwarp();
@@ -894,7 +906,10 @@ __global__ void __launch_bounds__(512) be_qr_kernel(BeView v) {
     for (int i = j + tid; i < R; i += 512) cj[i] = (i == j) ? alpha : 0.0;
     __syncthreads();
   }
-  if (tid == 0) ic[I_R] = c;
+  if (tid == 0) {
+    ic[I_R] = c;
+    if (v.be.stats) { atomicAdd(&v.be.stats[8], 1ull); atomicAdd(&v.be.stats[9], (unsigned long long)R * c * c); }
+  }
 }
 
 }  // namespace
@@ -1152,6 +1167,10 @@ __global__ void __launch_bounds__(256) be_correct_kernel(BeView v) {
     for (int i = 0; i < 3; ++i) core[C_TCI + i] += dx[18 + i];
     core[C_TD] += dx[21];
     ic[I_UPDATES] += 1;
+    if (v.be.stats) {
+      atomicAdd(&v.be.stats[4], 1ull); atomicAdd(&v.be.stats[5], (unsigned long long)r);
+      atomicAdd(&v.be.stats[6], (unsigned long long)r * d * d); atomicAdd(&v.be.stats[7], (unsigned long long)ic[I_ROWS]);
+    }
   }
   __syncthreads();
   const int n_win = ic[I_NWIN];
@@ -1373,6 +1392,7 @@ int be_alloc(LvbHandle* h) {
   be->LD = ((be->Dmax + 7) / 8) * 8;
   be->RAWMAX = 4096; be->RMAX = 2048;
   be->imu_cap = 64;
+  be->stats = h->fe.stats;
   const size_t S = be->S, T = be->T, LD = be->LD;
   BDA(be->core, S * BE_CORE); BDA(be->icore, S * BE_ICORE);
   BDA(be->win_id, S * be->Wcap); BDA(be->win, S * be->Wcap * BE_WIN);

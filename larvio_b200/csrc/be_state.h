@@ -43,6 +43,7 @@ struct LvbBackEnd {
   LvbImu* imu; int* n_imu;                    // per-call IMU staging [S][imu_cap]
   LvbFeature* msg_in; int* msg_in_n; double* msg_in_t; uint8_t* msg_in_valid;   // host-provided messages
   double chi2[100];
+  unsigned long long* stats;                  // shared with the front end's counter block (fe.stats)
   // host pinned
   LvbImu* pin_imu; int* pin_n_imu; int* pin_icore; LvbFeature* pin_feat; int* pin_feat_n; double* pin_feat_t; uint8_t* pin_valid;
 };

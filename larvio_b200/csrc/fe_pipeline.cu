@@ -51,7 +51,7 @@ int fe_alloc(LvbHandle* h) {
   DA(fe.want, S); DA(fe.mask_n, S);
   DA(fe.eig, S * npx); DA(fe.mask, S * npx); DA(fe.eig_max, S);
   fe.cand_cap = 32768;
-  DA(fe.cand, S * (size_t)fe.cand_cap); DA(fe.n_cand, S); DA(fe.overflow, 1);
+  DA(fe.cand, S * (size_t)fe.cand_cap); DA(fe.n_cand, S); DA(fe.overflow, 1); DA(fe.stats, 16);
   DA(fe.det_pts, S * N); DA(fe.det_n, S);
   DA(fe.msg, S * N); DA(fe.msg_n, S); DA(fe.has_msg, S); DA(fe.msg_t, S);
   fe.cur = 0;
@@ -172,7 +172,7 @@ __global__ void iota_perm_kernel(FeView v) {
 // order-preserving compaction of perm by status (removeUnmarkedElements, image_processor.h:215-230).
 // one CTA (N threads, N <= 1024) per (sequence, chain).  min_keep: chain aborts when fewer survive.
 struct CompactArgs {
-  LvbChain ch[2]; int N;
+  LvbChain ch[2]; int N; unsigned long long* stats; int stage;
   int min_keep[2];           // survivors < min_keep (or == 0) => fail
   int store_curr;            // 1: slot_curr[slot] = out[i] for survivors (after forward LK)
   const int* second;         // do_second flags: chain 1 uses min 20 everywhere in SECOND state
@@ -187,6 +187,10 @@ __global__ void compact_kernel(CompactArgs a) {
   if (ch.fail[s]) return;
   const int n = ch.n[s];
   const int i = threadIdx.x;
+  if (i == 0 && a.stats) {                       // work counters for the roofline accounting (bench.py)
+    if (a.stage <= 1) atomicAdd(&a.stats[0], (unsigned long long)n);
+    else if (a.stage == 2) atomicAdd(&a.stats[1], (unsigned long long)(c == 0 ? n : 2 * n));
+  }
   const size_t base = (size_t)s * a.N;
   const bool keep = i < n && ch.status[base + i] != 0;
   const int slot = i < n ? ch.perm[base + i] : 0;
@@ -325,6 +329,7 @@ __global__ void publish_kernel(FeView v, LvbCamera cam) {
   const int tid = threadIdx.x;
   const int first = fe.do_first[s], publish = fe.do_publish[s];
   if (fe.do_detect[s]) {
+    if (tid == 0) atomicAdd(&fe.stats[2], 1ull);
     const int nd = fe.det_n[s];
     for (int i = tid; i < nd; i += blockDim.x) fe.new_pts[base + i] = fe.det_pts[base + i];
     __syncthreads();
@@ -368,7 +373,7 @@ __global__ void publish_kernel(FeView v, LvbCamera cam) {
       fe.msg[base + i] = f;
     }
     __syncthreads();
-    if (tid == 0) { fe.msg_n[s] = n; fe.has_msg[s] = 1; fe.msg_t[s] = t; fe.last_pub_time[s] = t; }
+    if (tid == 0) { fe.msg_n[s] = n; fe.has_msg[s] = 1; fe.msg_t[s] = t; fe.last_pub_time[s] = t; atomicAdd(&fe.stats[3], 1ull); }
   }
   __syncthreads();
   if (tid == 0) fe.prev_img_time[s] = t;
@@ -388,7 +393,7 @@ static FeView make_view(LvbHandle* h) {
 static int run_compaction(LvbHandle* h, int stage) {
   LvbFrontEnd& fe = h->fe;
   CompactArgs ca;
-  ca.ch[0] = fe.ch[0]; ca.ch[1] = fe.ch[1]; ca.N = fe.N;
+  ca.ch[0] = fe.ch[0]; ca.ch[1] = fe.ch[1]; ca.N = fe.N; ca.stats = fe.stats; ca.stage = stage;
   ca.min_keep[0] = 1;
   ca.min_keep[1] = (stage == 2) ? 20 : 1;      // trackNewFeatures: "<20" only after the descriptor gate (:941)
   ca.store_curr = (stage == 0);

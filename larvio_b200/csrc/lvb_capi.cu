@@ -369,3 +369,11 @@ extern "C" int lvb_profile_get(LvbHandle* h, const char** names, double* total_m
   for (int i = 0; i < n && i < cap; ++i) { names[i] = h->prof.names[i].c_str(); total_ms[i] = h->prof.total_ms[i]; counts[i] = h->prof.count[i]; }
   return n;
 }
+
+extern "C" int lvb_get_stats(LvbHandle* h, unsigned long long* out16) {
+  if (!h || !out16) return lvb_set_err(LVB_E_ARG, "lvb_get_stats: null argument");
+  LVB_CUDA(cudaSetDevice(h->device));
+  LVB_CUDA(cudaMemcpyAsync(out16, h->fe.stats, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost, h->stream));
+  LVB_CUDA(cudaStreamSynchronize(h->stream));
+  return LVB_OK;
+}

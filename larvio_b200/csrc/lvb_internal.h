@@ -88,6 +88,8 @@ struct LvbFrontEnd {
   unsigned long long* cand;       // [S][cand_cap] packed (value bits<<32 | pixel index)
   int* n_cand; int cand_cap;
   int* overflow;                  // [1] sticky capacity-overflow flag
+  unsigned long long* stats;      // [16] work counters: 0 LK point-tracks, 1 ORB descriptors, 2 detector runs, 3 published msgs,
+                                  //      4 EKF updates, 5 sum r, 6 sum r*d*d, 7 sum stacked rows, 8 QR runs, 9 sum R*c*c
   float2* det_pts; int* det_n;    // [S][N], [S]
   // outputs
   LvbFeature* msg;                // [S][N]
