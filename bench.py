@@ -346,9 +346,9 @@ def main():
     # ---- device-resident pass: `value`
     dev_frames = pinned.to("cuda", non_blocking=False)
     st = fresh_state()
+    sampler = ClockSampler(local_rank) if rank == 0 else None      # samples warm-up + timed region (100 ms period)
     run_pass("dev", 0, Wm, st)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = launches_total()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(); t0 = time.perf_counter()
@@ -404,12 +404,12 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         tot = sum(v[0] for v in prof.values()) or 1.0
         top = sorted(prof.items(), key=lambda kv: -kv[1][0]) or [("none", (0.0, 0))]
-        kernel_share = {kname: dict(ms_per_launch=v[0] / max(v[1], 1), launches=v[1], share=v[0] / tot) for kname, v in top[:12]}
+        kernel_share = {kname: dict(ms_per_launch=v[0] / max(v[1], 1), launches=v[1], share=v[0] / tot) for kname, v in top}
         dom, (dom_ms, dom_n) = top[0]
         pstats = [sum(x) for x in zip(*prof_stats)] if prof_stats else [0] * 16
         models = kernel_models(S // NSUB, pstats, args.profile_steps, NSUB)
         roofs = {}
-        for kname, v in top[:14]:
+        for kname, v in top:
             mdl = models.get(kname)
             if not mdl or not mdl[1]:
                 continue

@@ -27,7 +27,7 @@ __constant__ double c_chi2[100] = {
 struct BeCfg {
   double th_imu;              // imu_img_timeTh = 1/(2*imu_rate)
   double sg2, sa2, sbg2, sba2, sfeat2;
-  double rot_thr, trans_thr, track_thr, feat_trans_thr, zupt_dis;
+  double rot_thr, trans_thr, track_thr, feat_trans_thr, zupt_dis, zupt_nv, zupt_np, zupt_nq;
   int max_track_len, sw_size, least_obs, if_FEJ_config, estimate_td, if_ZUPT_valid;
 };
 
@@ -924,6 +924,7 @@ struct GemmArgs {
   double* C; size_t sC; int rsC, csC;
   const int* icore; int m_idx, n_idx, k_idx;
   double alpha, beta, diag;
+  const double* diag_vec; size_t sD;     // optional per-row diagonal term (ZUPT's block-diagonal R), else `diag`
 };
 
 constexpr int GT = 64, GK = 16;
@@ -979,7 +980,7 @@ __global__ void __launch_bounds__(256) be_gemm_kernel(GemmArgs g) {
         double* c = C + (size_t)gm * g.rsC + (size_t)gn * g.csC;
         double val = g.alpha * acc[i][j];
         if (g.beta != 0.0) val += g.beta * *c;
-        if (gm == gn) val += g.diag;
+        if (gm == gn) val += g.diag_vec ? g.diag_vec[(size_t)s * g.sD + gm] : g.diag;
         *c = val;
       }
     }
@@ -1190,6 +1191,42 @@ __global__ void __launch_bounds__(256) be_correct_kernel(BeView v) {
   }
 }
 
+// measurementUpdate_ZUPT_vpq (:2791-2830): the 9-row system [v; dp; dq] of a detected standstill, written into the
+// stacked-Jacobian buffers so that the common update kernels apply it; sequences without ZUPT get an empty system.
+__global__ void __launch_bounds__(256) be_zupt_build_kernel(BeView v) {
+  const int s = blockIdx.x, tid = threadIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK]) return;
+  if (!ic[I_ZUPT]) { if (tid == 0) { ic[I_ROWS] = 0; ic[I_R] = 0; } return; }
+  const int RMAX = v.be.RMAX, LD = v.be.LD;
+  const int d = ic[I_DIM], N = ic[I_NWIN];
+  double* Hs = v.be.Hs + (size_t)s * LD * RMAX;
+  double* rs = v.be.rs + (size_t)s * RMAX;
+  double* dg = v.be.dx + (size_t)s * LD;             // per-row measurement variances (dx is free until be_correct)
+  for (int e = tid; e < 9 * d; e += blockDim.x) { const int col = e / 9, row = e - col * 9; Hs[(size_t)col * RMAX + row] = 0.0; }
+  __syncthreads();
+  if (tid < 3) {
+    const int L = BE_LEG;
+    Hs[(size_t)(3 + tid) * RMAX + tid] = 1.0;                                   // zupt_v
+    Hs[(size_t)(L + 6 * N - 3 + tid) * RMAX + 3 + tid] = 1.0;                   // zupt_p current
+    Hs[(size_t)(L + 6 * N - 9 + tid) * RMAX + 3 + tid] = -1.0;                  // zupt_p previous
+    Hs[(size_t)(L + 6 * N - 6 + tid) * RMAX + 6 + tid] = -0.5;                  // zupt_q current
+    Hs[(size_t)(L + 6 * N - 12 + tid) * RMAX + 6 + tid] = 0.5;                  // zupt_q previous
+    dg[tid] = v.cfg.zupt_nv; dg[3 + tid] = v.cfg.zupt_np; dg[6 + tid] = v.cfg.zupt_nq;
+  }
+  if (tid == 0) {
+    const double* core = core_of(v, s);
+    const double* wc = win_of(v, s, N - 1);
+    const double* wp = win_of(v, s, N - 2);
+    for (int i = 0; i < 3; ++i) { rs[i] = -core[C_V + i]; rs[3 + i] = -(wc[W_P + i] - wp[W_P + i]); }
+    const double qpc[4] = {-wp[W_Q], -wp[W_Q + 1], -wp[W_Q + 2], wp[W_Q + 3]};
+    double dq[4];
+    quat_mul(wc + W_Q, qpc, dq);
+    rs[6] = dq[0]; rs[7] = dq[1]; rs[8] = dq[2];
+    ic[I_ROWS] = 9; ic[I_R] = 9;
+  }
+}
+
 // erase processed / invalid features (:2007-2009, :2248-2253)
 __global__ void be_apply_actions_kernel(BeView v) {
   const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1208,7 +1245,10 @@ __global__ void be_prune_select_kernel(BeView v) {
   ic[I_DO_PRUNE] = 0; ic[I_NRM] = 0;
   if (!ic[I_OK]) return;
   const int n = ic[I_NWIN];
-  if (ic[I_ZUPT]) return;                               // ZUPT branch (:2321-2325) is a "next" row; flagged elsewhere
+  if (ic[I_ZUPT]) {                                       // :2321-2325: the previous state goes, whatever the window size
+    ic[I_RM0] = n - 2; ic[I_RM1] = -1; ic[I_NRM] = 1; ic[I_DO_PRUNE] = 1;
+    return;
+  }
   if (n < v.cfg.sw_size) return;
   const double* core = core_of(v, s);
   int key = n - 4, st = key + 1, first = 0;
@@ -1277,9 +1317,10 @@ __global__ void __launch_bounds__(256) be_prune_cov_gather_kernel(BeView v) {
   int* ic = icore_of(v, s);
   if (!ic[I_OK] || !ic[I_DO_PRUNE]) return;
   const int d = ic[I_DIM], LD = v.be.LD;
-  const int nd = d - 12;
+  const int nrm = ic[I_NRM];
+  const int nd = d - 6 * nrm;
   if (row >= nd) return;
-  const int a0 = BE_LEG + 6 * ic[I_RM0], a1 = BE_LEG + 6 * ic[I_RM1];
+  const int a0 = BE_LEG + 6 * ic[I_RM0], a1 = (nrm > 1) ? BE_LEG + 6 * ic[I_RM1] : (1 << 30);
   auto src = [&](int i) { int x = i; if (x >= a0) x += 6; if (x >= a1) x += 6; return x; };
   const double* P = P_of(v, s);
   double* Sd = v.be.Sm + (size_t)s * LD * LD;
@@ -1291,7 +1332,7 @@ __global__ void __launch_bounds__(256) be_prune_cov_scatter_kernel(BeView v) {
   int* ic = icore_of(v, s);
   if (!ic[I_OK] || !ic[I_DO_PRUNE]) return;
   const int d = ic[I_DIM], LD = v.be.LD;
-  const int nd = d - 12;
+  const int nd = d - 6 * ic[I_NRM];
   if (row >= nd) return;
   double* P = P_of(v, s);
   const double* Sd = v.be.Sm + (size_t)s * LD * LD;
@@ -1304,7 +1345,7 @@ __global__ void be_frame_end_kernel(BeView v) {
   if (s >= v.be.S) return;
   int* ic = icore_of(v, s);
   if (!ic[I_OK]) return;
-  if (ic[I_DO_PRUNE]) { ic[I_DIM] -= 12; ic[I_NWIN] -= 2; }
+  if (ic[I_DO_PRUNE]) { ic[I_DIM] -= 6 * ic[I_NRM]; ic[I_NWIN] -= ic[I_NRM]; }
   const double* core = core_of(v, s);
   if (v.cfg.if_FEJ_config && !ic[I_FEJ] && core[C_TIME] - core[C_TAKEOFF] >= 0) ic[I_FEJ] = 1;
 }
@@ -1372,6 +1413,7 @@ static BeView make_beview(LvbHandle* h) {
   v.cfg.sfeat2 = c.noise_feature * c.noise_feature;
   v.cfg.rot_thr = c.rotation_threshold; v.cfg.trans_thr = c.translation_threshold; v.cfg.track_thr = c.tracking_rate_threshold;
   v.cfg.feat_trans_thr = c.feature_translation_threshold; v.cfg.zupt_dis = c.zupt_max_feature_dis;
+  v.cfg.zupt_nv = c.zupt_noise_v * c.zupt_noise_v; v.cfg.zupt_np = c.zupt_noise_p * c.zupt_noise_p; v.cfg.zupt_nq = c.zupt_noise_q * c.zupt_noise_q;
   v.cfg.max_track_len = c.max_track_len; v.cfg.sw_size = c.sw_size; v.cfg.least_obs = c.least_observation_number;
   v.cfg.if_FEJ_config = c.if_FEJ; v.cfg.estimate_td = c.estimate_td; v.cfg.if_ZUPT_valid = c.if_ZUPT_valid;
   v.msg = nullptr; v.msg_n = nullptr; v.msg_t = nullptr; v.msg_valid = nullptr; v.msg_stride = 0;
@@ -1444,7 +1486,7 @@ static int launch_gemm(LvbHandle* h, const GemmArgs& g) {
 }
 
 // compression + EKF update on the stacked system currently in Hs/rs
-static int be_update(LvbHandle* h, BeView& v) {
+static int be_update(LvbHandle* h, BeView& v, bool zupt_rows = false) {
   LvbBackEnd* be = h->be;
   cudaStream_t st = h->stream;
   const size_t LD = be->LD;
@@ -1452,7 +1494,7 @@ static int be_update(LvbHandle* h, BeView& v) {
   be_qr_kernel<<<be->S, 512, sizeof(double) * be->RMAX, st>>>(v);
   LVB_LAUNCH_CHECK(h);
   GemmArgs g;
-  g.icore = be->icore;
+  g.icore = be->icore; g.diag_vec = nullptr; g.sD = LD;
   // T = H P
   g.A = be->Hs; g.sA = LD * be->RMAX; g.rsA = 1; g.csA = be->RMAX;
   g.B = v.P; g.sB = LD * LD; g.rsB = (int)LD; g.csB = 1;
@@ -1464,7 +1506,9 @@ static int be_update(LvbHandle* h, BeView& v) {
   g.B = be->Hs; g.sB = LD * be->RMAX; g.rsB = be->RMAX; g.csB = 1;
   g.C = be->Sm; g.sC = LD * LD; g.rsC = (int)LD; g.csC = 1;
   g.m_idx = I_R; g.n_idx = I_R; g.k_idx = I_DIM; g.alpha = 1.0; g.beta = 0.0; g.diag = v.cfg.sfeat2;
+  if (zupt_rows) g.diag_vec = be->dx;
   RC(launch_gemm(h, g));
+  g.diag_vec = nullptr;
   const size_t chol_bytes = sizeof(double) * ((size_t)be->Dmax * (be->Dmax + 1) / 2 + 2 * be->Dmax);
   LVB_PROF(h, "be_chol_kernel");
   if (chol_bytes <= 227 * 1024) be_chol_kernel<<<be->S, 1024, chol_bytes, st>>>(v);
@@ -1533,6 +1577,12 @@ int be_process(LvbHandle* h, const LvbFeature* d_msg, const int* d_msg_n, const 
   LVB_PROF(h, "be_augment_kernel");
   be_augment_kernel<<<S, 256, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
+  if (h->cfg.if_ZUPT_valid) {                        // checkZUPT -> measurementUpdate_ZUPT_vpq (:405-406)
+    LVB_PROF(h, "be_zupt_build_kernel");
+    be_zupt_build_kernel<<<S, 256, 0, st>>>(v);
+    LVB_LAUNCH_CHECK(h);
+    RC(be_update(h, v, true));
+  }
   RC(be_measurement_pass(h, v, 0));                  // removeLostFeatures
   LVB_PROF(h, "be_apply_actions_kernel");
   be_apply_actions_kernel<<<dim3((be->T + 127) / 128, S), 128, 0, st>>>(v);
@@ -1555,7 +1605,7 @@ int be_process(LvbHandle* h, const LvbFeature* d_msg, const int* d_msg_n, const 
   LVB_LAUNCH_CHECK(h);
   LVB_CUDA(cudaMemcpyAsync(be->pin_icore, be->icore, sizeof(int) * (size_t)S * BE_ICORE, cudaMemcpyDeviceToHost, st));
   LVB_CUDA(cudaStreamSynchronize(st));
-  int err = 0, zupt = 0;
+  int err = 0;
   for (int s = 0; s < S; ++s) {
     const int* ic = be->pin_icore + (size_t)s * BE_ICORE;
     if (ok_out) ok_out[s] = (uint8_t)ic[I_OK];
@@ -1567,11 +1617,9 @@ int be_process(LvbHandle* h, const LvbFeature* d_msg, const int* d_msg_n, const 
         n_imu[s] -= used;
       }
       if (ic[I_ERR]) err = ic[I_ERR];
-      if (ic[I_ZUPT]) zupt = 1;
     }
   }
   if (err) return lvb_set_err(LVB_E_CAPACITY, "back-end capacity exceeded (code %d: 1 feature table, 2 window, 3 raw rows, 4 stacked rows)", err);
-  if (zupt) return lvb_set_err(LVB_E_UNSUPPORTED, "static scene detected: the ZUPT update (larvio.cpp:2791-2962) is not built yet");
   return LVB_OK;
 }
 

@@ -164,64 +164,101 @@ __global__ void pad_reflect_kernel(uint8_t* __restrict__ pyr, LvbPyramidLayout L
 
 // ---------------------------------------------------------------- pyrDown (5x5 binomial, (x+128)>>8)
 // source level must already have a valid REFLECT_101 pad (>= 2 px). App. A.2.
+// each thread produces 4 adjacent destination pixels from 5 source rows x 16 bytes (four aligned 32-bit loads per row)
 __global__ void __launch_bounds__(256) pyrdown_kernel(uint8_t* __restrict__ pyr, LvbPyramidLayout L, int src_level) {
   const int s = blockIdx.z;
   const LvbLevel ls = L.lv[src_level], ld = L.lv[src_level + 1];
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= ld.w || y >= ld.h) return;
+  const int x4 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;       // first of 4 destination columns
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x4 >= ld.w || y >= ld.h) return;
   const uint8_t* so = lvb_level_origin((const uint8_t*)pyr, L, s, src_level);
   uint8_t* dorg = lvb_level_origin(pyr, L, s, src_level + 1);
-  int acc = 0;
+  int acc[4] = {0, 0, 0, 0};
   const int wv[5] = {1, 4, 6, 4, 1};
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
-    const uint8_t* row = so + (ptrdiff_t)(2 * y - 2 + j) * ls.pitch + (2 * x - 2);
-    const int r = row[0] + 4 * row[1] + 6 * row[2] + 4 * row[3] + row[4];
-    acc += wv[j] * r;
+    // bytes [2*x4 - 4, 2*x4 + 12) of source row 2y-2+j; the level origin is 8-byte aligned and 2*x4 is a multiple of 8
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(so + (ptrdiff_t)(2 * y - 2 + j) * ls.pitch + (2 * x4 - 4));
+    const uint32_t w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3];
+    uint8_t b[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { b[q] = (w0 >> (8 * q)) & 255; b[4 + q] = (w1 >> (8 * q)) & 255; b[8 + q] = (w2 >> (8 * q)) & 255; b[12 + q] = (w3 >> (8 * q)) & 255; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = 4 + 2 * k;      // byte index of source column 2*(x4+k)
+      acc[k] += wv[j] * (b[c - 2] + 4 * b[c - 1] + 6 * b[c] + 4 * b[c + 1] + b[c + 2]);
+    }
   }
-  dorg[(ptrdiff_t)y * ld.pitch + x] = (uint8_t)((acc + 128) >> 8);
+  uint8_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[k] = (uint8_t)((acc[k] + 128) >> 8);
+  uint8_t* dst = dorg + (ptrdiff_t)y * ld.pitch + x4;
+  if (x4 + 3 < ld.w) *reinterpret_cast<uchar4*>(dst) = make_uchar4(o[0], o[1], o[2], o[3]);
+  else for (int k = 0; k < 4 && x4 + k < ld.w; ++k) dst[k] = o[k];
 }
 
 // ---------------------------------------------------------------- 7x7 sigma=2 fixed-point blur of L0
 // App. A.4: kernel [18 34 48 56 48 34 18]/256 in both directions, out = (acc + 32768) >> 16.
 // CTA tile 64x16 output, staged with a 3-px apron in shared memory.
-constexpr int BT_W = 64, BT_H = 16;
+// CTA tile 128x32 output; input staged as aligned 32-bit words with a 4-byte / 3-row apron; each thread filters
+// 4 adjacent pixels horizontally (u16 partial sums in shared memory) and a 4x4 block vertically.
+constexpr int BT_W = 128, BT_H = 32;
 __global__ void __launch_bounds__(256) blur7_kernel(const uint8_t* __restrict__ pyr, LvbPyramidLayout L,
                                                      uint8_t* __restrict__ blur) {
-  __shared__ uint8_t tile[BT_H + 6][BT_W + 8];
-  __shared__ unsigned short hsum[BT_H + 6][BT_W];
+  __shared__ uint32_t tin[BT_H + 6][(BT_W + 8) / 4 + 1];
+  __shared__ unsigned short hs[BT_H + 6][BT_W + 4];
   const int s = blockIdx.z;
   const LvbLevel lv = L.lv[0];
   const int bx = blockIdx.x * BT_W, by = blockIdx.y * BT_H;
   const uint8_t* org = lvb_level_origin(pyr, L, s, 0);
   const int tid = threadIdx.x;
-  for (int i = tid; i < (BT_H + 6) * (BT_W + 6); i += 256) {
-    int ty = i / (BT_W + 6), tx = i - ty * (BT_W + 6);
-    int gx = bx + tx - 3, gy = by + ty - 3;
-    // the 24-px reflect pad covers the 3-px apron; clamp only protects the ragged last tile
-    gx = min(gx, lv.w + LVB_PAD - 1);
+  constexpr int WPR = (BT_W + 8) / 4;      // 34 words per staged row: bytes [bx-4, bx+BT_W+4)
+  for (int i = tid; i < (BT_H + 6) * WPR; i += 256) {
+    const int r = i / WPR, wq = i - r * WPR;
+    int gy = by - 3 + r;
     gy = min(gy, lv.h + LVB_PAD - 1);
-    tile[ty][tx] = org[(ptrdiff_t)gy * lv.pitch + gx];
+    int gx = bx - 4 + 4 * wq;
+    gx = min(gx, lv.pitch - LVB_PAD - 4);   // stay inside the padded row
+    tin[r][wq] = *reinterpret_cast<const uint32_t*>(org + (ptrdiff_t)gy * lv.pitch + gx);
   }
   __syncthreads();
-  const int k[7] = {18, 34, 48, 56, 48, 34, 18};
-  for (int i = tid; i < (BT_H + 6) * BT_W; i += 256) {
-    int ty = i / BT_W, tx = i - ty * BT_W;
-    int a = 0;
+  const int k7[7] = {18, 34, 48, 56, 48, 34, 18};
+  for (int it = tid; it < (BT_H + 6) * (BT_W / 4); it += 256) {
+    const int r = it / (BT_W / 4), g = it - r * (BT_W / 4);
+    const uint32_t w0 = tin[r][g], w1 = tin[r][g + 1], w2 = tin[r][g + 2];
+    int b[12];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) a += k[j] * tile[ty][tx + j];
-    hsum[ty][tx] = (unsigned short)a;
+    for (int q = 0; q < 4; ++q) { b[q] = (w0 >> (8 * q)) & 255; b[4 + q] = (w1 >> (8 * q)) & 255; b[8 + q] = (w2 >> (8 * q)) & 255; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int a = 0;
+#pragma unroll
+      for (int t = 0; t < 7; ++t) a += k7[t] * b[k + 1 + t];     // pixel 4g+k sits at byte 4+k; taps at 1+k .. 7+k
+      hs[r][4 * g + k] = (unsigned short)a;
+    }
   }
   __syncthreads();
-  for (int i = tid; i < BT_H * BT_W; i += 256) {
-    int ty = i / BT_W, tx = i - ty * BT_W;
-    int gx = bx + tx, gy = by + ty;
-    if (gx >= lv.w || gy >= lv.h) continue;
-    int a = 0;
+  const int g = tid & 31, rg = tid >> 5;         // 4 columns x 4 rows per thread
+  const int gx = bx + 4 * g;
+  if (gx >= lv.w) return;
+  int hv[10][4];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) a += k[j] * (int)hsum[ty + j][tx];
-    blur[(size_t)s * lv.w * lv.h + (size_t)gy * lv.w + gx] = (uint8_t)((a + 32768) >> 16);
+  for (int r = 0; r < 10; ++r)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hv[r][k] = hs[rg * 4 + r][4 * g + k];
+#pragma unroll
+  for (int ry = 0; ry < 4; ++ry) {
+    const int gy = by + rg * 4 + ry;
+    if (gy >= lv.h) break;
+    uint8_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int a = 0;
+#pragma unroll
+      for (int t = 0; t < 7; ++t) a += k7[t] * hv[ry + t][k];
+      o[k] = (uint8_t)((a + 32768) >> 16);
+    }
+    *reinterpret_cast<uchar4*>(blur + (size_t)s * lv.w * lv.h + (size_t)gy * lv.w + gx) = make_uchar4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -256,7 +293,7 @@ int fe_build_pyramid(LvbHandle* h, const uint8_t* d_images, int n, uint8_t* pyr,
     LVB_LAUNCH_CHECK(h);
     if (l + 1 < fe.L.n_levels) {
       const LvbLevel& ld = fe.L.lv[l + 1];
-      dim3 g2((ld.w + 31) / 32, (ld.h + 7) / 8, n);
+      dim3 g2(((ld.w + 3) / 4 + 31) / 32, (ld.h + 7) / 8, n);
       LVB_PROF(h, "pyrdown_kernel");
       pyrdown_kernel<<<g2, blk, 0, st>>>(pyr, fe.L, l);
       LVB_LAUNCH_CHECK(h);

@@ -23,29 +23,41 @@ constexpr int W_BITS = 14;
 // receives, row by row, the terms of pixels p, 4+p, 8+p, 12+p (A) resp. the int-pair terms of both 8-pixel
 // chunks (b); accumulator 4 receives pixels 16..20.  Terms are produced by all lanes, the 15 (A) / 10 (b)
 // sequential chains run on one lane each.
-constexpr int NTERM_A = WIN * 16 + WIN * 5;   // per sum: 336 lane terms + 105 tail terms = 441
-constexpr int NTERM_B = WIN * 8 + WIN * 5;    // per sum: 168 pair terms + 105 tail terms = 273
-struct WarpSmem {
+constexpr int NTERM_A = WIN * 16 + WIN * 5 + 3;   // per sum: 336 lane terms + 105 tail terms (+3 pad -> 16-B aligned sums)
+constexpr int NTERM_B = WIN * 8 + WIN * 5 + 3;    // per sum: 168 pair terms + 105 tail terms (+3 pad)
+struct alignas(16) WarpSmem {
   short Iw[NPIX + 7];                      // 896
   short2 dIw[NPIX];                        // 1764
   short dd[NPIX + 7];                      // 896  I_t per iteration
   union {
     struct { uint8_t tile[TILE * TILE]; short2 dtile[DT * DT]; } st;   // 576 + 1936 (window set-up only)
-    float termA[3 * NTERM_A];              // 5292
-    float termB[2 * NTERM_B];              // 2184
+    alignas(16) float termA[3 * NTERM_A];  // 5328
+    alignas(16) float termB[2 * NTERM_B];  // 2208
   } u;
 };
 
-// chain c of a sum with `nterm_lane` terms per row for accumulators 0..3 (stored [row][k][p]) and 5 tail terms per
-// row (stored after all lane terms, [row][x]).  Returns the accumulator value; acc in 0..4.
-__device__ __forceinline__ float run_chain(const float* T, int k_per_row, int acc) {
+// Term layout per sum: accumulator p (0..3) owns WIN*K consecutive floats (row-major over (row, k)), followed by the
+// WIN*5 tail terms; K = 4 for the A sums, 2 for the b sums.  Each chain adds its terms strictly in order, reading
+// them as float4 (all segment lengths are multiples of 4 except the 105-term tail, padded by one zero... 105 = 26*4+1).
+template <int K>
+__device__ __forceinline__ float run_chain(const float* T, int acc) {
   float a = 0.f;
   if (acc < 4) {
-    const float* q = T + acc;
-    for (int i = 0; i < WIN * k_per_row; ++i) a = __fadd_rn(a, q[i * 4]);
+    const float4* q = reinterpret_cast<const float4*>(T + acc * (WIN * K));
+#pragma unroll
+    for (int i = 0; i < WIN * K / 4; ++i) {
+      const float4 v = q[i];
+      a = __fadd_rn(a, v.x); a = __fadd_rn(a, v.y); a = __fadd_rn(a, v.z); a = __fadd_rn(a, v.w);
+    }
   } else {
-    const float* q = T + WIN * k_per_row * 4;
-    for (int i = 0; i < WIN * 5; ++i) a = __fadd_rn(a, q[i]);
+    const float* qt = T + 4 * (WIN * K);
+    const float4* q = reinterpret_cast<const float4*>(qt);
+#pragma unroll
+    for (int i = 0; i < (WIN * 5) / 4; ++i) {
+      const float4 v = q[i];
+      a = __fadd_rn(a, v.x); a = __fadd_rn(a, v.y); a = __fadd_rn(a, v.z); a = __fadd_rn(a, v.w);
+    }
+    a = __fadd_rn(a, qt[WIN * 5 - 1]);
   }
   return a;
 }
@@ -173,14 +185,14 @@ __global__ void __launch_bounds__(WARPS * 32) lk_kernel(const __grid_constant__ 
       const int y = p / WIN, x = p - y * WIN;
       const short2 d = w.dIw[p];
       const float fx = (float)d.x, fy = (float)d.y;
-      const int slot = (x < 16) ? (y * 16 + (x >> 2) * 4 + (x & 3)) : (WIN * 16 + y * 5 + (x - 16));
+      const int slot = (x < 16) ? ((x & 3) * (WIN * 4) + y * 4 + (x >> 2)) : (WIN * 16 + y * 5 + (x - 16));
       w.u.termA[slot] = __fmul_rn(fx, fx);
       w.u.termA[NTERM_A + slot] = __fmul_rn(fx, fy);
       w.u.termA[2 * NTERM_A + slot] = __fmul_rn(fy, fy);
     }
     __syncwarp();
     float chainv = 0.f;
-    if (lane < 15) chainv = run_chain(w.u.termA + (lane / 5) * NTERM_A, 4, lane % 5);
+    if (lane < 15) chainv = run_chain<4>(w.u.termA + (lane / 5) * NTERM_A, lane % 5);
     const float FLT_SCALE = 1.f / (float)(1 << 20);
     float A11 = __fmul_rn(combine_chains(chainv, 0), FLT_SCALE);
     float A12 = __fmul_rn(combine_chains(chainv, 5), FLT_SCALE);
@@ -196,6 +208,9 @@ __global__ void __launch_bounds__(WARPS * 32) lk_kernel(const __grid_constant__ 
     }
     D = __fdiv_rn(1.f, D);
     float2 np = make_float2(__fsub_rn(nxt.x, halfWin), __fsub_rn(nxt.y, halfWin));
+    int poff[14];            // byte offset of this lane's window pixels inside level B (pixel p = lane + 32k)
+#pragma unroll
+    for (int k2 = 0; k2 < 14; ++k2) { const int p = lane + 32 * k2; const int y = p / WIN; poff[k2] = y * lv.pitch + (p - y * WIN); }
     float2 prevDelta = make_float2(0.f, 0.f);
     for (int j = 0; j < a.max_iter; ++j) {
       const int inx = (int)floorf(np.x), iny = (int)floorf(np.y);
@@ -210,16 +225,20 @@ __global__ void __launch_bounds__(WARPS * 32) lk_kernel(const __grid_constant__ 
       iw10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, fa), fb), (float)(1 << W_BITS)));
       iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
       const uint8_t* jbase = orgB + (ptrdiff_t)iny * lv.pitch + inx;
-      for (int p = lane; p < NPIX; p += 32) {
-        const int y = p / WIN, x = p - y * WIN;
-        const uint8_t* c = jbase + (ptrdiff_t)y * lv.pitch + x;
-        const int j00 = __ldg(c), j01 = __ldg(c + 1), j10 = __ldg(c + lv.pitch), j11 = __ldg(c + lv.pitch + 1);
-        w.dd[p] = (short)(((j00 * iw00 + j01 * iw01 + j10 * iw10 + j11 * iw11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5)) - (int)w.Iw[p]);
+#pragma unroll
+      for (int k2 = 0; k2 < 14; ++k2) {
+        const int p = lane + 32 * k2;
+        if (p < NPIX) {
+          const uint8_t* c = jbase + poff[k2];
+          const int j00 = __ldg(c), j01 = __ldg(c + 1), j10 = __ldg(c + lv.pitch), j11 = __ldg(c + lv.pitch + 1);
+          w.dd[p] = (short)(((j00 * iw00 + j01 * iw01 + j10 * iw10 + j11 * iw11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5)) - (int)w.Iw[p]);
+        }
       }
       __syncwarp();
       // pair terms (both 8-pixel chunks of every row) and tail terms, then the 10 chains
-      for (int t = lane; t < NTERM_B; t += 32) {
+      for (int t = lane; t < WIN * 13; t += 32) {
         float t1, t2;
+        int slot;
         if (t < WIN * 8) {
           const int y = t >> 3, ch = (t >> 2) & 1, p = t & 3;
           const int i0 = y * WIN + 8 * ch + p, i1 = i0 + 4;
@@ -227,6 +246,7 @@ __global__ void __launch_bounds__(WARPS * 32) lk_kernel(const __grid_constant__ 
           const short2 g0 = w.dIw[i0], g1 = w.dIw[i1];
           t1 = (float)(d0 * g0.x + d1 * g1.x);
           t2 = (float)(d0 * g0.y + d1 * g1.y);
+          slot = p * (WIN * 2) + y * 2 + ch;
         } else {
           const int q = t - WIN * 8, y = q / 5, x = 16 + q - y * 5;
           const int i0 = y * WIN + x;
@@ -234,13 +254,14 @@ __global__ void __launch_bounds__(WARPS * 32) lk_kernel(const __grid_constant__ 
           const short2 g0 = w.dIw[i0];
           t1 = (float)(d0 * g0.x);
           t2 = (float)(d0 * g0.y);
+          slot = t;
         }
-        w.u.termB[t] = t1;
-        w.u.termB[NTERM_B + t] = t2;
+        w.u.termB[slot] = t1;
+        w.u.termB[NTERM_B + slot] = t2;
       }
       __syncwarp();
       float cv = 0.f;
-      if (lane < 10) cv = run_chain(w.u.termB + (lane / 5) * NTERM_B, 2, lane % 5);
+      if (lane < 10) cv = run_chain<2>(w.u.termB + (lane / 5) * NTERM_B, lane % 5);
       const float b1 = __fmul_rn(combine_chains(cv, 0), FLT_SCALE);
       const float b2 = __fmul_rn(combine_chains(cv, 5), FLT_SCALE);
       __syncwarp();

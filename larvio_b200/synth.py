@@ -118,7 +118,8 @@ class Sequence:
 
 
 class Trajectory:
-    def __init__(self, seed: int, R_b2c: np.ndarray):
+    def __init__(self, seed: int, R_b2c: np.ndarray, static_until: float = None):
+        self.static_until = static_until
         rng = np.random.default_rng(seed)
         self.amp_p = np.array([1.3, 1.1, 0.35]) * rng.uniform(0.8, 1.2, 3)
         self.f_p = np.array([0.13, 0.17, 0.23]) * rng.uniform(0.85, 1.15, 3)
@@ -132,19 +133,40 @@ class Trajectory:
         self.R_wb0 = R_wc0 @ R_b2c
         self.center = np.array([0.0, 0.0, 0.1]) + rng.uniform(-0.3, 0.3, 3)
 
+    def _gate(self, t):
+        """0 while the platform stands still (t < static_until), smooth ramp to 1 over the next second."""
+        if self.static_until is None:
+            return 1.0
+        x = min(max((t - self.static_until) / 1.0, 0.0), 1.0)
+        return x * x * x * (x * (6 * x - 15) + 10)
+
     def p(self, t):
-        return self.center + self.amp_p * np.sin(2 * np.pi * self.f_p * t + self.ph_p)
+        g = self._gate(t)
+        if self.static_until is None:
+            return self.center + self.amp_p * np.sin(2 * np.pi * self.f_p * t + self.ph_p)
+        s0 = np.sin(2 * np.pi * self.f_p * self.static_until + self.ph_p)
+        return self.center + g * self.amp_p * (np.sin(2 * np.pi * self.f_p * t + self.ph_p) - s0)
 
     def v(self, t):
+        if self.static_until is not None:
+            h = 1e-4
+            return (self.p(t + h) - self.p(t - h)) / (2 * h)
         w = 2 * np.pi * self.f_p
         return self.amp_p * w * np.cos(w * t + self.ph_p)
 
     def a(self, t):
+        if self.static_until is not None:
+            h = 1e-3
+            return (self.p(t + h) - 2 * self.p(t) + self.p(t - h)) / (h * h)
         w = 2 * np.pi * self.f_p
         return -self.amp_p * w * w * np.sin(w * t + self.ph_p)
 
     def R(self, t):
-        th = self.amp_r * np.sin(2 * np.pi * self.f_r * t + self.ph_r)
+        if self.static_until is not None:
+            s0 = np.sin(2 * np.pi * self.f_r * self.static_until + self.ph_r)
+            th = self._gate(t) * self.amp_r * (np.sin(2 * np.pi * self.f_r * t + self.ph_r) - s0)
+        else:
+            th = self.amp_r * np.sin(2 * np.pi * self.f_r * t + self.ph_r)
         return self.R_wb0 @ _so3_exp(th)
 
     def omega_body(self, t, h=1e-5):
@@ -212,12 +234,12 @@ def _renderer(cfg_raw):
 
 
 def make_sequence(cfg_raw: dict, seq_index: int, n_frames: int, t0: float = 0.05,
-                  imu_noise: bool = True, image_noise: float = 0.8) -> Sequence:
+                  imu_noise: bool = True, image_noise: float = 0.8, static_until: float = None) -> Sequence:
     """Generate sequence ``seq_index`` (seed 1234+seq_index) with ``n_frames`` images."""
     rend = _renderer(cfg_raw)
     seed = 1234 + seq_index
     rng = np.random.default_rng(seed)
-    traj = Trajectory(seed, rend.R_b2c)
+    traj = Trajectory(seed, rend.R_b2c, static_until)
     img_rate, imu_rate = float(cfg_raw["img_rate"]), float(cfg_raw["imu_rate"])
     img_t = t0 + np.arange(n_frames) / img_rate
     n_imu = int(round((img_t[-1] + 0.1) * imu_rate)) + 1

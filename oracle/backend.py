@@ -120,6 +120,7 @@ class Feature:
         self.in_state = False
         self.ekf_feature = False
         self.totalObsNum = 0
+        self.position_FEJ = np.zeros(3)
         self.translation_threshold = translation_threshold
 
     @staticmethod
@@ -162,7 +163,15 @@ class Feature:
         orth = tr - par * d
         return np.linalg.norm(orth) > self.translation_threshold
 
-    def initialize_position(self, aug, curr_id=None):
+    def initialize_inv_param(self, aug, curr_id):
+        """initializeInvParamPosition (feature.hpp:723-890): like initializePosition but always starts from the
+        two-view guess and marks the feature as a potential EKF-SLAM feature."""
+        ok = self.initialize_position(aug, curr_id, force_guess=True)
+        if ok:
+            self.ekf_feature = True
+        return ok
+
+    def initialize_position(self, aug, curr_id=None, force_guess=False):
         """initializePosition (curr_id given: skip the current camera) / _AssignAnchor (curr_id None)."""
         poses = []; meas = []; cam_ids = []
         for sid in sorted(self.obs.keys()):
@@ -179,7 +188,7 @@ class Feature:
             # pose.inverse() * T_c_w_last
             Ri = R.T
             rel.append((Ri @ Rl, Ri @ (tl - t)))
-        if not self.is_initialized:
+        if not self.is_initialized or force_guess:
             init = self._initial_guess(rel[0][0], rel[0][1], meas[-1], meas[0])
         else:
             init = Rl.T @ (self.position - tl)
@@ -228,6 +237,8 @@ class Feature:
         if total / (2 * n * n) > 4.7673e-04:
             valid = False
         if valid:
+            if not self.is_initialized:
+                self.position_FEJ = self.position.copy()      # feature.hpp:538-539 (the PREVIOUS estimate, literal)
             self.is_initialized = True
             self.position = Rl @ final + tl
             self.id_anchor = cam_ids[-1]
@@ -275,10 +286,26 @@ class LarVioOracle:
         self.sw_size = int(r["sw_size"]); self.if_FEJ_config = bool(int(r["if_FEJ"]))
         self.least_obs = int(r["least_observation_number"])
         self.if_ZUPT_valid = bool(int(r["if_ZUPT_valid"])); self.zupt_max_feature_dis = float(r["zupt_max_feature_dis"])
+        self.zupt_noise_v = float(r["zupt_noise_v"]) ** 2; self.zupt_noise_p = float(r["zupt_noise_p"]) ** 2
+        self.zupt_noise_q = float(r["zupt_noise_q"]) ** 2
         self.max_features = max(int(r["max_features_in_one_grid"]), 0)
         self.grid_rows = int(r["aug_grid_rows"]); self.grid_cols = int(r["aug_grid_cols"])
-        if self.max_features * self.grid_rows * self.grid_cols != 0:
-            raise NotImplementedError("hybrid EKF-SLAM features (max_features_in_one_grid > 0)")
+        self.feature_idp_dim = int(r["feature_idp_dim"])
+        self.use_schmidt = bool(int(r["use_schmidt"]))
+        self.hybrid = self.max_features * self.grid_rows * self.grid_cols != 0
+        if self.hybrid and (self.feature_idp_dim != 1 or self.use_schmidt):
+            raise NotImplementedError("hybrid mode is restated for feature_idp_dim 1 without Schmidt only")
+        it = r["intrinsics"]
+        fx, fy, cx, cy = float(it["fx"]), float(it["fy"]), float(it["cx"]), float(it["cy"])
+        U, V = int(r["resolution_width"]), int(r["resolution_height"])
+        self.x_min = -cx / fx; self.y_min = -cy / fy; self.x_max = (U - cx) / fx; self.y_max = (V - cy) / fy
+        if self.grid_rows * self.grid_cols != 0:
+            self.grid_width = (self.x_max - self.x_min) / self.grid_cols; self.grid_height = (self.y_max - self.y_min) / self.grid_rows
+        else:
+            self.grid_width = self.x_max - self.x_min; self.grid_height = self.y_max - self.y_min
+        self.grid_map = {i: [] for i in range(self.grid_rows * self.grid_cols)}
+        self.feature_states = []          # ids of EKF-SLAM features, in state order
+        self.last_ZUPT_time = 0.0
         Qc = np.zeros((12, 12))
         Qc[0:3, 0:3] = np.eye(3) * self.gyro_noise; Qc[3:6, 3:6] = np.eye(3) * self.acc_noise
         Qc[6:9, 6:9] = np.eye(3) * self.gyro_bias_noise; Qc[9:12, 9:12] = np.eye(3) * self.acc_bias_noise
@@ -305,6 +332,7 @@ class LarVioOracle:
         s.bg = np.array(bg, float); s.ba = np.array(ba, float)
         self.is_gravity_set = True
         self.take_off_stamp = s.time
+        self.last_ZUPT_time = s.time
         self.FEJ_now = s.copy()
 
     # ---- larvio.cpp:363-461.  imu: list of rows [t,w(3),a(3)] (mutated like the reference)
@@ -447,9 +475,13 @@ class LarVioOracle:
         sel = [0, 1, 2, 6, 7, 8]
         P12 = P[sel, :]
         P11 = P12[:, sel]
+        nf = len(self.feature_states)
+        pe = d - nf                        # end of the pose block; SLAM features follow (larvio.cpp:768-793)
+        order = list(range(pe)) + list(range(d, d + 6)) + list(range(pe, d))
         Pn = np.zeros((d + 6, d + 6))
         Pn[:d, :d] = P
         Pn[d:, :d] = P12; Pn[:d, d:] = P12.T; Pn[d:, d:] = P11
+        Pn = Pn[np.ix_(order, order)]
         self.P = (Pn + Pn.T) / 2.0
 
     # ---- :804-856
@@ -481,7 +513,7 @@ class LarVioOracle:
         with np.errstate(divide="ignore", invalid="ignore"):
             self.tracking_rate = float(np.float64(tracked) / np.float64(curr_num))
 
-    # ---- :2751-2788 (detection only)
+    # ---- checkZUPT :2751-2788 (pure MSCKF: no SLAM features to drop)
     def _check_zupt(self):
         d = self.coarse_feature_dis
         self.coarse_feature_dis = []
@@ -490,8 +522,38 @@ class LarVioOracle:
         d = sorted(d)
         if d[-9] < self.zupt_max_feature_dis:
             self.zupt_events += 1
-            raise NotImplementedError("ZUPT update triggered (static scene) — next row f-2")
+            if self.feature_states:                       # :2770-2782
+                nf = len(self.feature_states)
+                self.P = self.P[:-nf, :-nf]
+                for fid in self.feature_states:
+                    ft = self.map_server[fid]
+                    ft.is_initialized = False; ft.ekf_feature = False; ft.in_state = False
+                self.feature_states = []
+            self._zupt_update()
+            self.last_ZUPT_time = self.imu_state.time
+            return True
         return False
+
+    # ---- measurementUpdate_ZUPT_vpq :2791-2962
+    def _zupt_update(self):
+        N = len(self.aug)
+        d = self.P.shape[1]
+        L = self.LEG
+        H = np.zeros((9, d))
+        H[0:3, 3:6] = np.eye(3)
+        H[3:6, L + 6 * N - 3:L + 6 * N] = np.eye(3)          # (SLAM features were dropped: d == L + 6N)
+        H[3:6, L + 6 * N - 9:L + 6 * N - 6] = -np.eye(3)
+        H[6:9, L + 6 * N - 6:L + 6 * N - 3] = -0.5 * np.eye(3)
+        H[6:9, L + 6 * N - 12:L + 6 * N - 9] = 0.5 * np.eye(3)
+        sid = self.imu_state.id
+        cur, prv = self.aug[sid], self.aug[sid - 1]
+        r = np.zeros(9)
+        r[0:3] = -self.imu_state.v
+        r[3:6] = -(cur.p - prv.p)
+        qp_conj = np.array([-prv.q[0], -prv.q[1], -prv.q[2], prv.q[3]])
+        r[6:9] = quat_mul(cur.q, qp_conj)[:3]
+        Rz = np.diag([self.zupt_noise_v] * 3 + [self.zupt_noise_p] * 3 + [self.zupt_noise_q] * 3)
+        self._update(H, r, "zupt", Rz)
 
     # ---- :859-921
     def _meas_jacobian(self, sid, ft):
@@ -604,11 +666,11 @@ class LarVioOracle:
             del self.map_server[fid]
 
     # ---- :1420-1602 / :1605-1862 with empty SLAM blocks
-    def _update(self, H, r, tag):
+    def _update(self, H, r, tag, Rn=None):
         if H.shape[0] == 0 or r.shape[0] == 0:
             return
         P = self.P
-        S = H @ P @ H.T + self.feature_noise * np.eye(H.shape[0])
+        S = H @ P @ H.T + (self.feature_noise * np.eye(H.shape[0]) if Rn is None else Rn)
         Kt = np.linalg.solve(S, H @ P)
         K = Kt.T
         dx = K @ r
@@ -628,8 +690,157 @@ class LarVioOracle:
             R_b2w = quat_to_rot(a.q)
             a.q_cam = rot_to_quat(R_b2w @ s.R_imu_cam0.T)
             a.p_cam = a.p + R_b2w @ s.t_cam0_imu
+        self._update_feature_states(dx, self.LEG + 6 * len(self.aug))
         I_KH = np.eye(K.shape[0]) - K @ H
         P = I_KH @ P
+        self.P = (P + P.T) / 2.0
+
+    # inverse-depth correction of the in-state features + recomputed world positions (:1536-1575, :1752-1801)
+    def _update_feature_states(self, dx, base):
+        for i, fid in enumerate(self.feature_states):
+            ft = self.map_server[fid]
+            a = self.aug[ft.id_anchor]
+            ft.invDepth += dx[base + i]
+            p_c = np.array([ft.obs_anchor[0] / ft.invDepth, ft.obs_anchor[1] / ft.invDepth, 1 / ft.invDepth])
+            ft.position = quat_to_rot(a.q_cam) @ p_c + a.p_cam
+
+    # ---- measurementJacobian_ekf_1didp :1117-1244
+    def _meas_jacobian_1didp(self, sid, ft):
+        k = self.aug[sid]; a = self.aug[ft.id_anchor]
+        R_b2c = k.R_imu_cam0; t_c_b = k.t_cam0_imu
+        f_an = ft.obs_anchor
+        R_bk2w = quat_to_rot(k.q); R_w2bk = R_bk2w.T
+        R_w2ck = R_b2c @ R_w2bk; t_ck_w = k.p + R_bk2w @ t_c_b
+        R_ba2w = quat_to_rot(a.q); R_w2ba = R_ba2w.T
+        R_w2ca = R_b2c @ R_w2ba
+        if self.if_FEJ:
+            p_ca = R_b2c @ (R_w2ba @ (ft.position_FEJ - a.p_FEJ) - t_c_b)
+        else:
+            p_ca = np.array([f_an[0] / ft.invDepth, f_an[1] / ft.invDepth, 1 / ft.invDepth])
+        p_w = ft.position
+        z = ft.obs[sid]
+        p_ck = R_w2ck @ (p_w - t_ck_w)
+        r = z - np.array([p_ck[0] / p_ck[2], p_ck[1] / p_ck[2]])
+        J_k = np.zeros((2, 3))
+        J_k[0, 0] = 1 / p_ck[2]; J_k[1, 1] = 1 / p_ck[2]
+        J_k[0, 2] = -p_ck[0] / (p_ck[2] * p_ck[2]); J_k[1, 2] = -p_ck[1] / (p_ck[2] * p_ck[2])
+        J_d = R_w2ck @ R_w2ca.T @ f_an
+        p_baf_w = (ft.position_FEJ - a.p_FEJ) if self.if_FEJ else (p_w - a.p)
+        p_bkf_w = (ft.position_FEJ - k.p_FEJ) if self.if_FEJ else (p_w - k.p)
+        J_xa = np.zeros((3, 6)); J_xa[:, :3] = -R_w2ck @ skew(p_baf_w); J_xa[:, 3:] = R_w2ck
+        J_xk = np.zeros((3, 6)); J_xk[:, :3] = R_w2ck @ skew(p_bkf_w); J_xk[:, 3:] = -R_w2ck
+        J_e = np.zeros((3, 6))
+        Sk = skew(R_w2bk @ p_bkf_w - t_c_b)
+        Mx = R_w2bk @ R_w2ba.T @ skew(R_b2c.T @ p_ca)
+        J_e[:, :3] = R_b2c @ (Sk - Mx); J_e[:, 3:] = R_b2c @ (R_w2bk @ R_w2ba.T - np.eye(3))
+        J_rho = -1 / (ft.invDepth * ft.invDepth)
+        return (J_k @ J_d * J_rho), J_k @ J_xa, J_k @ J_xk, J_k @ J_e, r
+
+    # ---- featureJacobian_ekf_new :1247-1338 (columns: current state + one per feature in feature_states)
+    def _feature_jacobian_ekf_new(self, ft, state_ids):
+        valid = [sid for sid in state_ids if sid in ft.obs and sid != ft.id_anchor]
+        ncol = self.LEG + 6 * len(self.aug) + len(self.feature_states)
+        H = np.zeros((2 * len(valid), ncol)); r = np.zeros(2 * len(valid))
+        order = sorted(self.aug.keys())
+        a_idx = self.LEG + 6 * order.index(ft.id_anchor)
+        f_idx = self.LEG + 6 * len(self.aug) + self.feature_states.index(ft.id)
+        k = 0
+        for sid in valid:
+            H_f, H_a, H_x, H_e, r_i = self._meas_jacobian_1didp(sid, ft)
+            H[k:k + 2, f_idx] = H_f
+            H[k:k + 2, a_idx:a_idx + 6] = H_a
+            c = self.LEG + 6 * order.index(sid)
+            H[k:k + 2, c:c + 6] = H_x
+            H[k:k + 2, 15:21] = H_e
+            if self.estimate_td:
+                H[k:k + 2, 21] = ft.obs_vel[sid]
+            r[k:k + 2] = r_i
+            k += 2
+        return H, r
+
+    # ---- featureJacobian_ekf :1341-1417
+    def _feature_jacobian_ekf(self, ft):
+        sid = self.imu_state.id
+        order = sorted(self.aug.keys())
+        H = np.zeros((2, self.P.shape[1]))
+        H_f, H_a, H_x, H_e, r = self._meas_jacobian_1didp(sid, ft)
+        H[:, self.LEG + 6 * len(self.aug) + self.feature_states.index(ft.id)] = H_f
+        a_idx = self.LEG + 6 * order.index(ft.id_anchor)
+        H[:, a_idx:a_idx + 6] = H_a
+        c = self.LEG + 6 * order.index(sid)
+        H[:, c:c + 6] = H_x
+        H[:, 15:21] = H_e
+        if self.estimate_td:
+            H[:, 21] = ft.obs_vel[sid]
+        return H, r
+
+    # ---- rmLostFeaturesCov :3296-3348
+    def _rm_lost_features_cov(self, lost_ids):
+        for fid in lost_ids:
+            seq = self.feature_states.index(fid)
+            i0 = self.LEG + 6 * len(self.aug) + seq
+            keep = [i for i in range(self.P.shape[0]) if i != i0]
+            self.P = self.P[np.ix_(keep, keep)]
+            self.feature_states.pop(seq)
+            del self.map_server[fid]
+
+    # ---- updateGridMap :3351-3370
+    def _grid_code(self, xy):
+        row = int((xy[1] - self.y_min) / self.grid_height); col = int((xy[0] - self.x_min) / self.grid_width)
+        return row * self.grid_cols + col
+
+    def _update_grid_map(self):
+        if self.grid_rows * self.grid_cols == 0:
+            return
+        self.grid_map = {i: [] for i in range(self.grid_rows * self.grid_cols)}
+        for fid in self.feature_states:
+            code = self._grid_code(self.map_server[fid].obs[self.imu_state.id])
+            self.grid_map.setdefault(code, []).append(fid)
+
+    # ---- updateFeatureCov_1didp :3125-3293
+    def _update_feature_cov_1didp(self, ft, old_id, new_id):
+        N = len(self.aug)
+        p_w = ft.position
+        R_b2c = self.imu_state.R_imu_cam0; t_c_b = self.imu_state.t_cam0_imu
+        o = self.aug[old_id]; n = self.aug[new_id]
+        R_b2w_old = quat_to_rot(o.q); R_c2w_old = quat_to_rot(o.q_cam)
+        if self.if_FEJ:
+            p_old = R_b2c @ (R_b2w_old.T @ (ft.position_FEJ - o.p_FEJ) - t_c_b)
+        else:
+            p_old = R_c2w_old.T @ (p_w - o.p_cam)
+        p_old_ = R_c2w_old.T @ (p_w - o.p_cam)
+        invDepth_old = 1 / p_old_[2]
+        f_old = np.array([p_old_[0] / p_old_[2], p_old_[1] / p_old_[2], 1.0])
+        R_b2w_new = quat_to_rot(n.q); R_w2b_new = R_b2w_new.T
+        R_w2c_new = quat_to_rot(n.q_cam).T
+        invDepth_new = ft.invDepth
+        if self.if_FEJ:
+            p_bf_old = ft.position_FEJ - o.p_FEJ; p_bf_new = ft.position_FEJ - n.p_FEJ
+        else:
+            p_bf_old = p_w - o.p; p_bf_new = p_w - n.p
+        J_rho_d_new = -invDepth_new * invDepth_new
+        J_d = (R_w2c_new @ R_c2w_old @ f_old)[2]
+        J_theta_old = (-R_w2c_new @ skew(p_bf_old))[2]; J_p_old = R_w2c_new[2]
+        J_theta_new = (R_w2c_new @ skew(p_bf_new))[2]; J_p_new = (-R_w2c_new)[2]
+        Sk = skew(R_w2b_new @ p_bf_new - t_c_b)
+        Mx = R_w2b_new @ R_b2w_old @ skew(R_b2c.T @ p_old)
+        J_e_theta = (R_b2c @ (Sk - Mx))[2]; J_e_p = (R_b2c @ (R_w2b_new @ R_b2w_old - np.eye(3)))[2]
+        J_d_rho_old = -1 / (invDepth_old * invDepth_old)
+        J = np.zeros(self.P.shape[1])
+        order = sorted(self.aug.keys())
+        oc = order.index(old_id); nc = order.index(new_id); fc = self.feature_states.index(ft.id)
+        fi = self.LEG + 6 * N + fc
+        J[fi] = J_rho_d_new * J_d * J_d_rho_old
+        J[self.LEG + 6 * oc:self.LEG + 6 * oc + 3] = J_rho_d_new * J_theta_old
+        J[self.LEG + 6 * oc + 3:self.LEG + 6 * oc + 6] = J_rho_d_new * J_p_old
+        J[self.LEG + 6 * nc:self.LEG + 6 * nc + 3] = J_rho_d_new * J_theta_new
+        J[self.LEG + 6 * nc + 3:self.LEG + 6 * nc + 6] = J_rho_d_new * J_p_new
+        J[15:18] = J_rho_d_new * J_e_theta; J[18:21] = J_rho_d_new * J_e_p
+        Pfl = J @ self.P
+        Pff = float(Pfl @ J)
+        P = self.P
+        P[fi, :] = Pfl; P[:, fi] = Pfl
+        P[fi, fi] = Pff
         self.P = (P + P.T) / 2.0
 
     # ---- :2259-2307

@@ -175,6 +175,18 @@ def test_backend_oracle_invariants(cfg, seqs):
     assert seen >= 5
 
 
+def test_oracle_zupt_holds_still_then_moves(cfg):
+    from larvio_b200 import synth, harness
+    seq = synth.make_sequence(cfg.raw, 5, 30, static_until=1.0)
+    recs = harness.run_oracle(cfg.raw, seq, 30)
+    still = [r for r in recs if r["ok"] and seq.img_t[r["frame"]] < 0.95 and r["frame"] > 4]
+    assert len(still) >= 5
+    for r in still:
+        assert r["n_win"] == 1                      # ZUPT drops the previous pose every step (larvio.cpp:2321-2325)
+        assert np.linalg.norm(r["v"]) < 5e-3 and np.linalg.norm(r["p"] - seq.gt_p[r["frame"]]) < 5e-3
+    assert [r for r in recs if r["ok"]][-1]["n_win"] > 3
+
+
 def test_update_invariant_to_orthogonal_row_transform(cfg):
     """What legitimises Householder/Givens QR on the GPU vs SPQR on the CPU."""
     from oracle.backend import LarVioOracle

@@ -240,6 +240,15 @@ def test_fused_step_tracks_oracle(cfg, seqs):
     assert rep['p'] < 1e-9 and rep['q'] < 1e-9 and rep['Prel'] < 1e-9
 
 
+def test_zupt_static_start_matches_oracle(cfg):
+    """checkZUPT / measurementUpdate_ZUPT_vpq (larvio.cpp:2751-2962): one second of standstill, then motion."""
+    from larvio_b200 import synth
+    zs = [synth.make_sequence(cfg.raw, 5 + s, 34, static_until=1.0) for s in range(2)]
+    rep = _drive(cfg, zs, 34, 'step')
+    assert rep['steps'] >= 14 and rep['ok_mismatch'] == 0 and rep['imu_mismatch'] == 0
+    assert rep['p'] < 1e-9 and rep['v'] < 1e-9 and rep['q'] < 1e-9 and rep['Prel'] < 1e-9
+
+
 def test_gpu_against_committed_golden(cfg, seqs):
     from larvio_b200 import api, harness
     g = np.load(GOLD)
