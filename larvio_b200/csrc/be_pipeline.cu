@@ -29,6 +29,8 @@ struct BeCfg {
   double sg2, sa2, sbg2, sba2, sfeat2;
   double rot_thr, trans_thr, track_thr, feat_trans_thr, zupt_dis, zupt_nv, zupt_np, zupt_nq;
   int max_track_len, sw_size, least_obs, if_FEJ_config, estimate_td, if_ZUPT_valid;
+  int hybrid;                 // EKF-SLAM features enabled (1-D inverse depth)
+  double x_min, y_min, grid_w, grid_h;
 };
 
 struct BeView {
@@ -281,6 +283,7 @@ __global__ void __launch_bounds__(512) be_add_obs_kernel(BeView v) {
     double* o = ft_obs + ((size_t)slot * Wcap + n_win) * 4;
     if (is_new) {
       ft_id[slot] = f.id; ft_flags[slot] = 1;            // used, not initialised
+      v.be.ft_anchor[(size_t)s * T + slot] = -1;
       unsigned long long m = 1ull << n_win;
       o[0] = f.u + f.u_vel * dt; o[1] = f.v + f.v_vel * dt; o[2] = f.u_vel; o[3] = f.v_vel;
       if (!(f.u_init == -1 && f.v_init == -1) && prev_slot >= 0) {      // :824-832
@@ -349,6 +352,17 @@ __global__ void __launch_bounds__(256) be_augment_kernel(BeView v) {
     st3(w + W_PCAM, ld3(core + C_P) + m3_vec(R_b2w, ld3(core + C_TCI)));
   }
   const int sel[6] = {0, 1, 2, 6, 7, 8};
+  const int nf = ic[I_NF];
+  if (nf > 0) {
+    // SLAM-feature columns follow the pose block: the new pose is INSERTED before them (larvio.cpp:768-793).
+    // P_aug[i][j] = P[m(i)][m(j)] with m = identity / selection rows / shifted feature indices -> generic re-map.
+    int* cm = v.be.cmap + (size_t)s * LD;
+    const int pe = d - nf;
+    for (int i = tid; i < d + 6; i += blockDim.x) cm[i] = (i < pe) ? i : (i < pe + 6 ? sel[i - pe] : i - 6);
+    __syncthreads();
+    if (tid == 0) { ic[I_REMAP] = 1; ic[I_NEWDIM] = d + 6; ic[I_NWIN] = n_win + 1; }
+    return;
+  }
   for (int j = tid; j < d; j += blockDim.x) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -403,7 +417,7 @@ __device__ bool check_motion(const BeView& v, int s, unsigned long long mask, co
 // (feature.hpp:383-552 / :554-721).  One warp; lanes own observations (two per lane at most).
 // tri_mask: observations that take part.  Returns validity; on success writes the world position.
 __device__ bool triangulate_warp(const BeView& v, int s, unsigned long long tri_mask, const double* obs,
-                                 bool is_init, double* pos /*[3] in/out*/) {
+                                 bool is_init, double* pos /*[3] in/out*/, double* spec = nullptr /*[8]: ok, pos_w, p_lastcam*/) {
   const int lane = threadIdx.x & 31;
   const int n = __popcll(tri_mask);
   const int last = 63 - __clzll((long long)tri_mask);
@@ -526,7 +540,12 @@ __device__ bool triangulate_warp(const BeView& v, int s, unsigned long long tri_
   bool valid = !bad;
   if (total / (2.0 * n * n) > 4.7673e-04) valid = false;
   if (!(total == total)) valid = false;   // NaN guard
-  if (valid && lane == 0) st3(pos, m3_vec(Rl, fin) + tl);
+  if (lane == 0) {
+    if (spec) {
+      spec[0] = valid ? 1.0 : 0.0;
+      if (valid) { st3(spec + 1, m3_vec(Rl, fin) + tl); st3(spec + 4, fin); }
+    } else if (valid) st3(pos, m3_vec(Rl, fin) + tl);
+  }
   return valid;
 }
 
@@ -556,7 +575,19 @@ __global__ void __launch_bounds__(128) be_classify_kernel(BeView v, int mode) {
   const bool zupt = ic[I_ZUPT] != 0;
   int action = 0;
   unsigned long long usemask = 0;
-  if (mode == 0) {
+  int nrows_override = -1;
+  if (flags & 4) {                                            // EKF-SLAM feature in the state
+    if (mode == 0 && tracked) { action = 4; usemask = 1ull << cur; nrows_override = 2; }
+  } else if (mode == 0 && v.cfg.hybrid && tracked && nobs >= v.cfg.max_track_len) {
+    // promotion candidate: the sequential rule (be_slam_decide_kernel) needs a two-view-initialised triangulation
+    // without the current camera (initializeInvParamPosition / initializePosition), prepared here speculatively
+    double* sp = v.be.ft_spec + fi * 8;
+    if (lane == 0) sp[0] = 0.0;
+    __syncwarp();
+    if (!(flags & 8) && check_motion(v, s, mask, obs, Wcap, tracked))
+      triangulate_warp(v, s, mask & ~(1ull << cur), obs, false, pos, sp);
+    action = 5;
+  } else if (mode == 0) {
     const unsigned long long tri = mask & ~(1ull << cur);     // initializePosition skips the current camera
     if (!tracked) {
       if (nobs < v.cfg.least_obs) action = 1;
@@ -580,7 +611,7 @@ __global__ void __launch_bounds__(128) be_classify_kernel(BeView v, int mode) {
     unsigned long long rm = 0;
     for (int k = 0; k < ic[I_NRM]; ++k) rm |= 1ull << ic[I_RM0 + k];
     const unsigned long long involved = mask & rm;
-    if (involved && !zupt && __popcll(involved) > 1) {
+    if (involved && !zupt && !(flags & 8) && __popcll(involved) > 1) {     // potential EKF features are not used (:2465)
       bool ok = true;
       if (!is_init) {
         if (!check_motion(v, s, mask, obs, Wcap, tracked)) ok = false;
@@ -594,7 +625,7 @@ __global__ void __launch_bounds__(128) be_classify_kernel(BeView v, int mode) {
     v.be.ft_flags[fi] = (flags & ~2) | (is_init ? 2 : 0);
     v.be.ft_action[fi] = action;
     v.be.ft_usemask[fi] = usemask;
-    v.be.ft_nrows[fi] = (action == 2 && usemask) ? 2 * __popcll(usemask) : 0;
+    v.be.ft_nrows[fi] = nrows_override >= 0 ? nrows_override : ((action == 2 && usemask) ? 2 * __popcll(usemask) : 0);
   }
 }
 
@@ -629,11 +660,129 @@ __global__ void __launch_bounds__(512) be_scan_rows_kernel(BeView v, int which /
 
 namespace {
 
+// ---------------------------------------------------------------- measurementJacobian_ekf_1didp (:1117-1244)
+// Observation of an EKF-SLAM feature (1-D inverse depth in its anchor camera) from window slot ws.
+struct Jac1d { double hf[2], ha[2][6], hx[2][6], he[2][6], r[2]; };
+__device__ void meas_jac_1didp(const BeView& v, int s, size_t fi, int ws, bool fej, Jac1d& J) {
+  const int Wcap = v.be.Wcap;
+  const double* wk = win_of(v, s, ws);
+  const int as = v.be.ft_anchor[fi];
+  const double* wa = win_of(v, s, as);
+  const M3 R_b2c = m3_load(wk + W_RIC);
+  const V3 t_c_b = ld3(wk + W_TCI);
+  const V3 f_an = v3(v.be.ft_oa[fi * 2], v.be.ft_oa[fi * 2 + 1], 1.0);
+  const double inv = v.be.ft_inv[fi];
+  const M3 R_bk2w = quat_to_rot(wk + W_Q), R_w2bk = m3_t(R_bk2w);
+  const M3 R_w2ck = m3_mul(R_b2c, R_w2bk);
+  const V3 t_bk_w = ld3(wk + W_P);
+  const V3 t_ck_w = t_bk_w + m3_vec(R_bk2w, t_c_b);
+  const M3 R_ba2w = quat_to_rot(wa + W_Q), R_w2ba = m3_t(R_ba2w);
+  const V3 t_ba_w = ld3(wa + W_P);
+  const M3 R_w2ca = m3_mul(R_b2c, R_w2ba);
+  const V3 p_w = ld3(v.be.ft_pos + fi * 3), p_fej = ld3(v.be.ft_pfej + fi * 3);
+  V3 p_ca;
+  if (fej) p_ca = m3_vec(R_b2c, m3_vec(R_w2ba, p_fej - ld3(wa + W_PFEJ)) - t_c_b);
+  else p_ca = v3(f_an.x / inv, f_an.y / inv, 1.0 / inv);
+  const double* z = v.be.ft_obs + (fi * Wcap + ws) * 4;
+  const V3 p_ck = m3_vec(R_w2ck, p_w - t_ck_w);
+  J.r[0] = z[0] - p_ck.x / p_ck.z; J.r[1] = z[1] - p_ck.y / p_ck.z;
+  const double Jk[2][3] = {{1 / p_ck.z, 0, -p_ck.x / (p_ck.z * p_ck.z)}, {0, 1 / p_ck.z, -p_ck.y / (p_ck.z * p_ck.z)}};
+  const V3 J_d = m3_vec(R_w2ck, m3_tvec(R_w2ca, f_an));              // R_w2ck * R_w2ca^T * f_an
+  const V3 p_baf_w = fej ? (p_fej - ld3(wa + W_PFEJ)) : (p_w - t_ba_w);
+  const V3 p_bkf_w = fej ? (p_fej - ld3(wk + W_PFEJ)) : (p_w - t_bk_w);
+  const M3 Jxa_l = m3_scale(m3_mul(R_w2ck, skew(p_baf_w)), -1.0);    // J_xa = [-R skew(p_baf) | R]
+  const M3 Jxk_l = m3_mul(R_w2ck, skew(p_bkf_w));                   // J_xk = [R skew(p_bkf) | -R]
+  const M3 Rka = m3_mul(R_w2bk, R_ba2w);                            // R_w2bk * R_w2ba^T
+  const M3 Sk = skew(m3_vec(R_w2bk, p_bkf_w) - t_c_b);
+  const M3 Mx = m3_mul(Rka, skew(m3_tvec(R_b2c, p_ca)));
+  const M3 Je_l = m3_mul(R_b2c, m3_sub(Sk, Mx));
+  const M3 Je_r = m3_mul(R_b2c, m3_sub(Rka, m3_identity()));
+  const double J_rho = -1.0 / (inv * inv);
+  const double jd[3] = {J_d.x, J_d.y, J_d.z};
+  for (int a = 0; a < 2; ++a) {
+    J.hf[a] = (Jk[a][0] * jd[0] + Jk[a][1] * jd[1] + Jk[a][2] * jd[2]) * J_rho;
+    for (int c = 0; c < 3; ++c) {
+      double xa = 0, xr = 0, kl = 0, kr = 0, el = 0, er = 0;
+      for (int q = 0; q < 3; ++q) {
+        xa += Jk[a][q] * Jxa_l.m[q * 3 + c]; xr += Jk[a][q] * R_w2ck.m[q * 3 + c];
+        kl += Jk[a][q] * Jxk_l.m[q * 3 + c]; kr += Jk[a][q] * -R_w2ck.m[q * 3 + c];
+        el += Jk[a][q] * Je_l.m[q * 3 + c]; er += Jk[a][q] * Je_r.m[q * 3 + c];
+      }
+      J.ha[a][c] = xa; J.ha[a][3 + c] = xr; J.hx[a][c] = kl; J.hx[a][3 + c] = kr; J.he[a][c] = el; J.he[a][3 + c] = er;
+    }
+  }
+}
+
 // ====================================================================== per-feature Jacobian + gating
-// One warp (one CTA) per table slot with action 2.  Raw rows live in Hraw[s][rowofs .. rowofs+2m) (dense,
-// width LD); after three Householder reflections that annihilate H_f the rows 3..2m-1 are the projected
-// block A^T H_x, A^T r (featureJacobian_msckf, larvio.cpp:972-978; any orthonormal basis of the left null
-// space gives the same gate value and the same update).  dynamic smem: (2*Wcap)^2 + 8*Wcap doubles.
+// One warp (one CTA) per table slot.  action 2: MSCKF feature (featureJacobian_msckf + gatingTest); action 3: new EKF-SLAM
+// feature (same gate, then featureJacobian_ekf_new and the split of its block into null-space rows and the row that
+// defines the new state, larvio.cpp:2033-2125); action 4: EKF-SLAM feature already in the state (featureJacobian_ekf +
+// gate with dof 2).  Raw rows live in Hraw[s][rowofs ..) (dense, width LD).  For MSCKF blocks three Householder
+// reflections annihilate H_f; rows 3.. are A^T H_x, A^T r (any orthonormal basis of the left null space gives the same
+// gate value and the same update).  dynamic smem: see be_feature_smem_bytes().
+__device__ __forceinline__ int be_feature_smem_doubles(int Wcap) { return 6 * Wcap + 8 + 4 * Wcap * Wcap + 2 * Wcap + (8 + 6 * Wcap) / 2 + 4; }
+
+// gamma = r^T (H P H^T + sigma^2 I)^-1 r over the listed nonzero columns; returns pass/fail against chi2[dof = R]
+__device__ bool gate_block(const BeView& v, const double* P, int LD, const double* Hj, double* Tp, const double* rj, int R,
+                           const int* nzl, int nz, double* Ssm, double* vv, int lane) {
+  if (R <= 0 || R >= 100) return false;
+  for (int j = lane; j < nz; j += 32) {
+    const int c2 = nzl[j];
+    for (int a0 = 0; a0 < R; a0 += 16) {
+      double acc[16];
+#pragma unroll
+      for (int a = 0; a < 16; ++a) acc[a] = 0.0;
+      for (int q = 0; q < nz; ++q) {
+        const int c1 = nzl[q];
+        const double pv = P[(size_t)c1 * LD + c2];
+#pragma unroll
+        for (int a = 0; a < 16; ++a)
+          if (a0 + a < R) acc[a] += Hj[(size_t)(a0 + a) * LD + c1] * pv;
+      }
+#pragma unroll
+      for (int a = 0; a < 16; ++a)
+        if (a0 + a < R) Tp[(size_t)(a0 + a) * LD + c2] = acc[a];
+    }
+  }
+  __syncwarp();
+  for (int e = lane; e < R * R; e += 32) {
+    const int a = e / R, b = e - a * R;
+    double acc = (a == b) ? v.cfg.sfeat2 : 0.0;
+    for (int q = 0; q < nz; ++q) { const int c1 = nzl[q]; acc += Tp[(size_t)a * LD + c1] * Hj[(size_t)b * LD + c1]; }
+    Ssm[e] = acc;
+  }
+  __syncwarp();
+  for (int j = 0; j < R; ++j) {
+    double djj = Ssm[j * R + j];
+    if (!(djj > 0.0)) return false;
+    djj = sqrt(djj);
+    __syncwarp();
+    if (lane == 0) Ssm[j * R + j] = djj;
+    for (int i = j + 1 + lane; i < R; i += 32) Ssm[i * R + j] /= djj;
+    __syncwarp();
+    for (int e = lane; e < (R - j - 1) * (R - j - 1); e += 32) {
+      const int a = j + 1 + e / (R - j - 1), b = j + 1 + e % (R - j - 1);
+      if (b <= a) Ssm[a * R + b] -= Ssm[a * R + j] * Ssm[b * R + j];
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    double gamma = 0.0;
+    for (int i = 0; i < R; ++i) {
+      double x = rj[i];
+      for (int q = 0; q < i; ++q) x -= Ssm[i * R + q] * vv[q];
+      x /= Ssm[i * R + i];
+      vv[i] = x;
+      gamma += x * x;
+    }
+    vv[0] = gamma;
+  }
+  __syncwarp();
+  const double gamma = vv[0];
+  __syncwarp();
+  return gamma < c_chi2[R];
+}
+
 __global__ void __launch_bounds__(32) be_feature_kernel(BeView v, double* Traw) {
   extern __shared__ double fsm[];
   const int s = blockIdx.y, slot = blockIdx.x, lane = threadIdx.x;
@@ -641,27 +790,57 @@ __global__ void __launch_bounds__(32) be_feature_kernel(BeView v, double* Traw) 
   const size_t fi = (size_t)s * T + slot;
   int* ic = icore_of(v, s);
   if (!ic[I_OK]) return;
-  const int nrows = v.be.ft_nrows[fi];
-  if (nrows == 0 || v.be.ft_action[fi] != 2) return;
+  const int nrows_all = v.be.ft_nrows[fi];
+  const int action = v.be.ft_action[fi];
+  if (nrows_all == 0 || action < 2 || action > 4) return;
   const unsigned long long um = v.be.ft_usemask[fi];
-  const int m = nrows / 2;
   const int ofs = v.be.ft_rowofs[fi];
   double* H = v.be.Hraw + ((size_t)s * v.be.RAWMAX + ofs) * LD;
   double* rr = v.be.rraw + (size_t)s * v.be.RAWMAX + ofs;
   double* Tj = Traw + ((size_t)s * v.be.RAWMAX + ofs) * LD;
-  const double* core = core_of(v, s);
   const double* P = P_of(v, s);
   const double* obs = v.be.ft_obs + fi * Wcap * 4;
   const V3 p_w = ld3(v.be.ft_pos + fi * 3);
-  const int d = ic[I_DIM];
   const bool fej = ic[I_FEJ] != 0;
-  double* Hf = fsm;                         // [2m][3]
-  double* Ssm = fsm + 6 * Wcap + 8;         // [(2m-3)^2]
-  double* vv = fsm + 6 * Wcap + 8 + 4 * Wcap * Wcap;   // [2m] reflector / rhs scratch
-  // zero the raw rows
-  for (int i = lane; i < nrows * LD; i += 32) H[i] = 0.0;
+  const int n_win = ic[I_NWIN];
+  double* Hf = fsm;                                        // [2m][3]
+  double* Ssm = fsm + 6 * Wcap + 8;                        // [(2m-3)^2]
+  double* vv = Ssm + 4 * Wcap * Wcap;                      // [2m] reflector / rhs scratch
+  int* nzl = reinterpret_cast<int*>(vv + 2 * Wcap);        // nonzero column list
+  for (int i = lane; i < nrows_all * LD; i += 32) H[i] = 0.0;
   __syncwarp();
-  // ---- measurementJacobian_msckf per observation (:859-921)
+
+  if (action == 4) {
+    // ---- featureJacobian_ekf (:1341-1417): 2 rows, gate with dof 2 (:2133-2143)
+    const int cur = n_win - 1;
+    const int as = v.be.ft_anchor[fi];
+    int fidx = -1;
+    const int* fs = v.be.fs_slot + (size_t)s * 64;
+    for (int i = 0; i < ic[I_NF]; ++i) if (fs[i] == slot) fidx = BE_LEG + 6 * n_win + i;
+    if (lane == 0) {
+      Jac1d J;
+      meas_jac_1didp(v, s, fi, cur, fej, J);
+      for (int a = 0; a < 2; ++a) {
+        double* row = H + (size_t)a * LD;
+        for (int c = 0; c < 6; ++c) { row[BE_LEG + 6 * as + c] = J.ha[a][c]; row[15 + c] = J.he[a][c]; }
+        for (int c = 0; c < 6; ++c) row[BE_LEG + 6 * cur + c] = J.hx[a][c];
+        row[fidx] = J.hf[a];
+        if (v.cfg.estimate_td) row[21] = obs[(size_t)cur * 4 + 2 + a];
+        rr[a] = J.r[a];
+      }
+      for (int j = 0; j < 7; ++j) nzl[j] = 15 + j;
+      for (int c = 0; c < 6; ++c) { nzl[7 + c] = BE_LEG + 6 * as + c; nzl[13 + c] = BE_LEG + 6 * cur + c; }
+      nzl[19] = fidx;
+    }
+    __syncwarp();
+    const bool pass = fidx >= 0 && gate_block(v, P, LD, H, Tj, rr, 2, nzl, 20, Ssm, vv, lane);
+    if (lane == 0) v.be.ft_accept[fi] = pass ? 2 : 0;
+    return;
+  }
+
+  // ---- measurementJacobian_msckf per observation (:859-921) into rows [0, 2m)
+  const int m = __popcll(um);
+  const int nrows = 2 * m;
   for (int k = lane; k < m; k += 32) {
     const int ws = nth_set_bit(um, k);
     const double* w = win_of(v, s, ws);
@@ -696,10 +875,10 @@ __global__ void __launch_bounds__(32) be_feature_kernel(BeView v, double* Traw) 
     rr[2 * k] = obs[(size_t)ws * 4 + 0] - p_c.x / p_c.z;
     rr[2 * k + 1] = obs[(size_t)ws * 4 + 1] - p_c.y / p_c.z;
   }
-  __syncwarp();
   // nonzero column list: 15..21 and the pose blocks of the used window slots
   const int nz = 7 + 6 * m;
-  auto nzcol = [&](int j) { if (j < 7) return 15 + j; const int q = j - 7; return BE_LEG + 6 * nth_set_bit(um, q / 6) + (q % 6); };
+  for (int j = lane; j < nz; j += 32) nzl[j] = (j < 7) ? 15 + j : BE_LEG + 6 * nth_set_bit(um, (j - 7) / 6) + ((j - 7) % 6);
+  __syncwarp();
   // ---- three Householder reflections on H_f, applied to the nonzero columns of H and to r
   for (int k = 0; k < 3; ++k) {
     double nrm = 0.0;
@@ -714,17 +893,15 @@ __global__ void __launch_bounds__(32) be_feature_kernel(BeView v, double* Traw) 
     vtv = warp_sum_d(vtv);
     if (vtv > 0.0) {
       const double beta = 2.0 / vtv;
-      // remaining H_f columns (sequential per column, lanes over rows)
       for (int c = k; c < 3; ++c) {
         double dt_ = 0.0;
         for (int i = k + lane; i < nrows; i += 32) dt_ += vv[i] * Hf[i * 3 + c];
         dt_ = warp_sum_d(dt_) * beta;
         for (int i = k + lane; i < nrows; i += 32) Hf[i * 3 + c] -= dt_ * vv[i];
       }
-      // H columns: lanes over nonzero columns
       for (int j = lane; j < nz + 1; j += 32) {
         if (j < nz) {
-          const int c = nzcol(j);
+          const int c = nzl[j];
           double dt_ = 0.0;
           for (int i = k; i < nrows; ++i) dt_ += vv[i] * H[(size_t)i * LD + c];
           dt_ *= beta;
@@ -741,76 +918,83 @@ __global__ void __launch_bounds__(32) be_feature_kernel(BeView v, double* Traw) 
   }
   // ---- gating test (:1865-1880) on rows 3..nrows-1
   const int R = nrows - 3;
-  bool pass = false;
-  if (R > 0 && R < 100) {
-    const double* Hj = H + (size_t)3 * LD;
-    double* Tp = Tj + (size_t)3 * LD;
-    // T = H_nz * P[nz, nz]: one column of T per lane; each P element is loaded once and reused for a chunk of
-    // 16 rows held in registers (the H entries are warp-uniform broadcasts)
-    for (int j = lane; j < nz; j += 32) {
-      const int c2 = nzcol(j);
-      for (int a0 = 0; a0 < R; a0 += 16) {
-        double acc[16];
-#pragma unroll
-        for (int a = 0; a < 16; ++a) acc[a] = 0.0;
-        for (int q = 0; q < nz; ++q) {
-          const int c1 = nzcol(q);
-          const double pv = P[(size_t)c1 * LD + c2];
-#pragma unroll
-          for (int a = 0; a < 16; ++a)
-            if (a0 + a < R) acc[a] += Hj[(size_t)(a0 + a) * LD + c1] * pv;
-        }
-#pragma unroll
-        for (int a = 0; a < 16; ++a)
-          if (a0 + a < R) Tp[(size_t)(a0 + a) * LD + c2] = acc[a];
-      }
-    }
-    __syncwarp();
-    for (int e = lane; e < R * R; e += 32) {        // S = T H^T + sigma^2 I
-      const int a = e / R, b = e - a * R;
-      double acc = (a == b) ? v.cfg.sfeat2 : 0.0;
-      for (int q = 0; q < nz; ++q) { const int c1 = nzcol(q); acc += Tp[(size_t)a * LD + c1] * Hj[(size_t)b * LD + c1]; }
-      Ssm[e] = acc;
-    }
-    __syncwarp();
-    // Cholesky S = L L^T (in place, lower), then gamma = |L^-1 r|^2
-    bool spd = true;
-    for (int j = 0; j < R; ++j) {
-      double djj = Ssm[j * R + j];
-      if (!(djj > 0.0)) { spd = false; break; }
-      djj = sqrt(djj);
-      __syncwarp();
-      if (lane == 0) Ssm[j * R + j] = djj;
-      for (int i = j + 1 + lane; i < R; i += 32) Ssm[i * R + j] /= djj;
-      __syncwarp();
-      for (int e = lane; e < (R - j - 1) * (R - j - 1); e += 32) {
-        const int a = j + 1 + e / (R - j - 1), b = j + 1 + e % (R - j - 1);
-        if (b <= a) Ssm[a * R + b] -= Ssm[a * R + j] * Ssm[b * R + j];
-      }
-      __syncwarp();
-    }
-    if (spd) {
-      if (lane == 0) {
-        double gamma = 0.0;
-        for (int i = 0; i < R; ++i) {
-          double x = rr[3 + i];
-          for (int q = 0; q < i; ++q) x -= Ssm[i * R + q] * vv[q];
-          x /= Ssm[i * R + i];
-          vv[i] = x;
-          gamma += x * x;
-        }
-        vv[0] = gamma;
-      }
-      __syncwarp();
-      const double gamma = vv[0];
-      pass = gamma < c_chi2[R];
+  const bool pass = gate_block(v, P, LD, H + (size_t)3 * LD, Tj + (size_t)3 * LD, rr + 3, R, nzl, nz, Ssm, vv, lane);
+  if (action == 2) { if (lane == 0) v.be.ft_accept[fi] = pass ? R : 0; return; }
+
+  // ---- action 3: new EKF-SLAM feature
+  if (!pass) {                                   // :2053-2059, :2084-2092: stays in the map, not in the state
+    if (lane == 0) { v.be.ft_accept[fi] = 0; v.be.ft_action[fi] = 0; }
+    return;
+  }
+  // featureJacobian_ekf_new (:1247-1338): every observation except the anchor's, rows [2m, 2m + 2(m-1))
+  const int as = v.be.ft_anchor[fi];
+  const unsigned long long um2 = um & ~(1ull << as);
+  const int m2 = __popcll(um2), nr2 = 2 * m2;
+  double* H2 = H + (size_t)nrows * LD;
+  double* r2 = rr + nrows;
+  double* hf = Hf;                               // own inverse-depth column [2(m-1)]
+  for (int k = lane; k < m2; k += 32) {
+    const int ws = nth_set_bit(um2, k);
+    Jac1d J;
+    meas_jac_1didp(v, s, fi, ws, fej, J);
+    for (int a = 0; a < 2; ++a) {
+      double* row = H2 + (size_t)(2 * k + a) * LD;
+      for (int c = 0; c < 6; ++c) { row[BE_LEG + 6 * as + c] = J.ha[a][c]; row[15 + c] = J.he[a][c]; }
+      for (int c = 0; c < 6; ++c) row[BE_LEG + 6 * ws + c] = J.hx[a][c];
+      if (v.cfg.estimate_td) row[21] = obs[(size_t)ws * 4 + 2 + a];
+      hf[2 * k + a] = J.hf[a];
+      r2[2 * k + a] = J.r[a];
     }
   }
-  if (lane == 0) v.be.ft_accept[fi] = pass ? R : 0;
+  __syncwarp();
+  // one Householder reflection on the own column: row 0 <- column space (H_1, h2, r_1), rows 1.. <- left null space
+  {
+    double nrm = 0.0;
+    for (int i = lane; i < nr2; i += 32) nrm += hf[i] * hf[i];
+    nrm = sqrt(warp_sum_d(nrm));
+    const double x0 = hf[0];
+    const double alpha = x0 >= 0 ? -nrm : nrm;
+    for (int i = lane; i < nr2; i += 32) vv[i] = hf[i] - (i == 0 ? alpha : 0.0);
+    __syncwarp();
+    double vtv = 0.0;
+    for (int i = lane; i < nr2; i += 32) vtv += vv[i] * vv[i];
+    vtv = warp_sum_d(vtv);
+    if (vtv > 0.0) {
+      const double beta = 2.0 / vtv;
+      for (int j = lane; j < nz + 1; j += 32) {
+        if (j < nz) {
+          const int c = nzl[j];
+          double dt_ = 0.0;
+          for (int i = 0; i < nr2; ++i) dt_ += vv[i] * H2[(size_t)i * LD + c];
+          dt_ *= beta;
+          for (int i = 0; i < nr2; ++i) H2[(size_t)i * LD + c] -= dt_ * vv[i];
+        } else {
+          double dt_ = 0.0;
+          for (int i = 0; i < nr2; ++i) dt_ += vv[i] * r2[i];
+          dt_ *= beta;
+          for (int i = 0; i < nr2; ++i) r2[i] -= dt_ * vv[i];
+        }
+      }
+    }
+    __syncwarp();
+    // (H_1, h2, r_1) of this feature -> Hnew[s][rank], rank = position among this frame's candidates
+    const int* cand = v.be.cand + (size_t)s * 128;
+    int rank = -1;
+    for (int k = 0; k < ic[I_NCAND]; ++k) if (cand[k] == slot) rank = k;
+    if (rank >= 0) {
+      double* hn = v.be.Hnew + ((size_t)s * 64 + rank) * (LD + 4);
+      for (int c = lane; c < LD; c += 32) hn[c] = H2[c];
+      if (lane == 0) { hn[LD] = alpha; hn[LD + 1] = r2[0]; }
+    }
+    if (lane == 0) v.be.ft_accept[fi] = (rank >= 0) ? nr2 - 1 : 0;
+  }
 }
 
 // ====================================================================== stacking (column-major Hs)
-__global__ void __launch_bounds__(512) be_stack_kernel(BeView v) {
+// phase 0: gated MSCKF blocks (action 2) from row 0 -> I_ROWS = I_R = total (then be_qr_kernel compresses them);
+// phase 1: gated in-state SLAM rows (action 4) and the null-space rows of new SLAM features (action 3) appended after
+//          the (possibly compressed) MSCKF block, exactly like H_o in measurementUpdate_hybrid (:1616-1628).
+__global__ void __launch_bounds__(512) be_stack_kernel(BeView v, int phase) {
   __shared__ int part[512];
   __shared__ int s_total;
   const int s = blockIdx.x, tid = threadIdx.x;
@@ -818,42 +1002,153 @@ __global__ void __launch_bounds__(512) be_stack_kernel(BeView v) {
   if (!ic[I_OK]) return;
   const int T = v.be.T, LD = v.be.LD, RMAX = v.be.RMAX;
   const int per = (T + 511) / 512;
+  auto rows_of = [&](int i) {
+    const size_t fi = (size_t)s * T + i;
+    const int act = v.be.ft_action[fi];
+    const bool mine = (phase == 0) ? (act == 2) : (act == 3 || act == 4);
+    return mine ? v.be.ft_accept[fi] : 0;
+  };
   int loc = 0;
-  for (int k = 0; k < per; ++k) { const int i = tid * per + k; if (i < T) loc += v.be.ft_accept[(size_t)s * T + i]; }
+  for (int k = 0; k < per; ++k) { const int i = tid * per + k; if (i < T) loc += rows_of(i); }
   part[tid] = loc;
   __syncthreads();
   for (int o = 1; o < 512; o <<= 1) { int x = tid >= o ? part[tid - o] : 0; __syncthreads(); part[tid] += x; __syncthreads(); }
   if (tid == 511) { s_total = part[511]; }
   __syncthreads();
+  const int base = (phase == 0) ? 0 : ic[I_R];
   int total = s_total;
-  if (total > RMAX) { if (tid == 0) atomicExch(&ic[I_ERR], 4); total = RMAX; }
-  // per-feature offsets into ft_rowofs is still needed below -> reuse ft_nrows to hold the stack offset
-  int run = part[tid] - loc;
+  const int cap = min(RMAX, v.be.LDS);
+  if (base + total > cap) { if (tid == 0) atomicExch(&ic[I_ERR], 4); total = max(cap - base, 0); }
+  int run = base + part[tid] - loc;
   for (int k = 0; k < per; ++k) {
     const int i = tid * per + k;
-    if (i < T) { const int a = v.be.ft_accept[(size_t)s * T + i]; v.be.ft_nrows[(size_t)s * T + i] = run; run += a; }
+    if (i < T) { const int a = rows_of(i); if (a) v.be.ft_nrows[(size_t)s * T + i] = run; run += a; }
   }
   __syncthreads();
   const int d = ic[I_DIM];
   double* Hs = v.be.Hs + (size_t)s * LD * RMAX;
   double* rs = v.be.rs + (size_t)s * RMAX;
-  // copy: one warp per accepted feature row block
   const int warp = tid >> 5, lane = tid & 31;
   for (int i = warp; i < T; i += 16) {
-    const int a = v.be.ft_accept[(size_t)s * T + i];
+    const int a = rows_of(i);
     if (!a) continue;
-    const int dst = v.be.ft_nrows[(size_t)s * T + i];
-    if (dst + a > RMAX) continue;
-    const int src = v.be.ft_rowofs[(size_t)s * T + i] + 3;
-    const double* H = v.be.Hraw + ((size_t)s * v.be.RAWMAX + src) * LD;
-    const double* rr = v.be.rraw + (size_t)s * v.be.RAWMAX + src;
+    const size_t fi = (size_t)s * T + i;
+    const int dst = v.be.ft_nrows[fi];
+    if (dst + a > cap) continue;
+    const int act = v.be.ft_action[fi];
+    // first raw row of the block that goes into H_o: MSCKF skips the 3 rows that carry H_f; a new SLAM feature keeps
+    // the rows after its 2m gating rows and after the one row that defines the new state
+    int first = v.be.ft_rowofs[fi];
+    if (act == 2) first += 3;
+    else if (act == 3) first += 2 * __popcll(v.be.ft_usemask[fi]) + 1;
+    const double* H = v.be.Hraw + ((size_t)s * v.be.RAWMAX + first) * LD;
+    const double* rr = v.be.rraw + (size_t)s * v.be.RAWMAX + first;
     for (int e = lane; e < a * d; e += 32) {
       const int row = e / d, col = e - row * d;
       Hs[(size_t)col * RMAX + dst + row] = H[(size_t)row * LD + col];
     }
     for (int e = lane; e < a; e += 32) rs[dst + e] = rr[e];
   }
-  if (tid == 0) { ic[I_ROWS] = total; ic[I_R] = total; }
+  if (tid == 0) {
+    if (phase == 0) { ic[I_ROWS] = total; ic[I_R] = total; }
+    else ic[I_R] = base + total;
+  }
+}
+
+// new SLAM features that passed the gate, in candidate (= id) order: state indices, fs_slot, compact Hnew (:2019-2093)
+__global__ void be_slam_accept_kernel(BeView v) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= v.be.S) return;
+  int* ic = icore_of(v, s);
+  ic[I_NNEW] = 0;
+  if (!ic[I_OK]) return;
+  const int T = v.be.T, LD = v.be.LD;
+  int* cand = v.be.cand + (size_t)s * 128;
+  int* fs = v.be.fs_slot + (size_t)s * 64;
+  const int nf = ic[I_NF];
+  int k2 = 0;
+  for (int k = 0; k < ic[I_NCAND]; ++k) {
+    const int slot = cand[k];
+    const size_t fi = (size_t)s * T + slot;
+    if (v.be.ft_action[fi] != 3) continue;                 // rejected by the gate (action reset to 0)
+    if (k2 != k) {
+      const double* src = v.be.Hnew + ((size_t)s * 64 + k) * (LD + 4);
+      double* dst = v.be.Hnew + ((size_t)s * 64 + k2) * (LD + 4);
+      for (int c = 0; c < LD + 2; ++c) dst[c] = src[c];
+    }
+    fs[nf + k2] = slot;
+    v.be.ft_flags[fi] |= 4;                                // in_state
+    ++k2;
+  }
+  ic[I_NNEW] = k2;
+}
+
+// second half of measurementUpdate_hybrid (:1661-1676, :1821-1854): the states of the new SLAM features and the grown
+// covariance.  H_2 is diagonal for 1-D inverse depth (App. C-13), so HH = H_1 / h2 row by row.
+__global__ void __launch_bounds__(256) be_slam_grow_kernel(BeView v) {
+  extern __shared__ double gsm[];          // HH [n_new][d]
+  const int s = blockIdx.x, tid = threadIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK]) return;
+  const int n_new = ic[I_NNEW];
+  if (n_new == 0) return;
+  const int d = ic[I_DIM], LD = v.be.LD, T = v.be.T;
+  double* P = P_of(v, s);
+  const double* dx = v.be.dx + (size_t)s * v.be.LDS;
+  const bool have_dx = ic[I_R] > 0;
+  const int* fs = v.be.fs_slot + (size_t)s * 64;
+  const int nf = ic[I_NF];
+  double* HH = gsm;
+  for (int e = tid; e < n_new * d; e += blockDim.x) {
+    const int k = e / d, c = e - k * d;
+    const double* hn = v.be.Hnew + ((size_t)s * 64 + k) * (LD + 4);
+    HH[e] = hn[c] / hn[LD];
+  }
+  __syncthreads();
+  // new rows/cols of P: nHHP = -HH P (P already updated), P22 = -nHHP HH^T + sigma^2 / h2^2
+  double* Sd = v.be.Sm + (size_t)s * v.be.LDS * v.be.LDS;          // scratch for nHHP [n_new][d]
+  for (int e = tid; e < n_new * d; e += blockDim.x) {
+    const int k = e / d, c = e - k * d;
+    double acc = 0.0;
+    for (int q = 0; q < d; ++q) acc += HH[k * d + q] * P[(size_t)q * LD + c];
+    Sd[(size_t)k * LD + c] = -acc;
+  }
+  __syncthreads();
+  for (int e = tid; e < n_new * d; e += blockDim.x) {
+    const int k = e / d, c = e - k * d;
+    const double val = Sd[(size_t)k * LD + c];
+    P[(size_t)(d + k) * LD + c] = val;
+    P[(size_t)c * LD + d + k] = val;
+  }
+  for (int e = tid; e < n_new * n_new; e += blockDim.x) {
+    const int a = e / n_new, b = e - a * n_new;
+    double acc = 0.0;
+    for (int q = 0; q < d; ++q) acc += Sd[(size_t)a * LD + q] * HH[b * d + q];
+    acc = -acc;
+    if (a == b) { const double h2 = v.be.Hnew[((size_t)s * 64 + a) * (LD + 4) + LD]; acc += v.cfg.sfeat2 / (h2 * h2); }
+    P[(size_t)(d + a) * LD + d + b] = acc;
+  }
+  __syncthreads();
+  for (int e = tid; e < n_new * n_new; e += blockDim.x) {             // symmetrise the new block (:1852-1853)
+    const int a = e / n_new, b = e - a * n_new;
+    if (a < b) { const double mval = 0.5 * (P[(size_t)(d + a) * LD + d + b] + P[(size_t)(d + b) * LD + d + a]); P[(size_t)(d + a) * LD + d + b] = mval; P[(size_t)(d + b) * LD + d + a] = mval; }
+  }
+  // dx_new = -HH dx_leg + r_1 / h2, inverse depth and world position of the new features
+  if (tid < n_new) {
+    const int k = tid;
+    const double* hn = v.be.Hnew + ((size_t)s * 64 + k) * (LD + 4);
+    double acc = 0.0;
+    if (have_dx) for (int q = 0; q < d; ++q) acc += HH[k * d + q] * dx[q];
+    const double dxn = -acc + hn[LD + 1] / hn[LD];
+    const size_t fi = (size_t)s * T + fs[nf + k];
+    const double inv = v.be.ft_inv[fi] + dxn;
+    v.be.ft_inv[fi] = inv;
+    const double* wa = win_of(v, s, v.be.ft_anchor[fi]);
+    const V3 p_c = v3(v.be.ft_oa[fi * 2] / inv, v.be.ft_oa[fi * 2 + 1] / inv, 1.0 / inv);
+    st3(v.be.ft_pos + fi * 3, m3_vec(quat_to_rot(wa + W_QCAM), p_c) + ld3(wa + W_PCAM));
+  }
+  __syncthreads();
+  if (tid == 0) { ic[I_DIM] = d + n_new; ic[I_NF] = nf + n_new; ic[I_NNEW] = 0; }
 }
 
 // ====================================================================== thin QR compression (Householder)
@@ -995,8 +1290,8 @@ __global__ void __launch_bounds__(1024) be_chol_kernel(BeView v) {
   int* ic = icore_of(v, s);
   if (!ic[I_OK]) return;
   const int r = ic[I_R];
-  if (r <= 0) return;
-  const int LD = v.be.LD;
+  if (r <= 0 || r > v.be.Dmax) return;          // larger systems (hybrid mode) go through be_chol_gmem_kernel
+  const int LD = v.be.LDS;
   double* S = v.be.Sm + (size_t)s * LD * LD;
   double* Lp = csm;
   double* col = csm + (size_t)v.be.Dmax * (v.be.Dmax + 1) / 2;
@@ -1040,14 +1335,14 @@ __global__ void __launch_bounds__(1024) be_chol_kernel(BeView v) {
 }
 
 // global-memory variant for windows whose packed S does not fit in shared memory (sw_size > ~33)
-__global__ void __launch_bounds__(512) be_chol_gmem_kernel(BeView v) {
-  extern __shared__ double csm[];   // column cache [LD]
+__global__ void __launch_bounds__(512) be_chol_gmem_kernel(BeView v, int min_r) {
+  extern __shared__ double csm[];   // column cache [LDS]
   const int s = blockIdx.x, tid = threadIdx.x;
   int* ic = icore_of(v, s);
   if (!ic[I_OK]) return;
   const int r = ic[I_R];
-  if (r <= 0) return;
-  const int LD = v.be.LD;
+  if (r <= min_r) return;
+  const int LD = v.be.LDS;
   double* S = v.be.Sm + (size_t)s * LD * LD;
   for (int j = 0; j < r; ++j) {
     const double djj = sqrt(S[(size_t)j * LD + j]);
@@ -1090,15 +1385,15 @@ __global__ void __launch_bounds__(64) be_trsm_kernel(BeView v) {
   const int c = blockIdx.x * 64 + tid;
   if (blockIdx.x * 64 >= d) return;
   const bool act = c < d;
-  const int LD = v.be.LD;
-  const double* L = v.be.Sm + (size_t)s * LD * LD;
+  const int LD = v.be.LD, LS = v.be.LDS;
+  const double* L = v.be.Sm + (size_t)s * LS * LS;
   double* Tm = v.be.Tm + (size_t)s * v.be.RAWMAX * LD;
   const int nb = (r + 31) / 32;
   for (int ib = 0; ib < nb; ++ib) {
     const int i0 = ib * 32;
     for (int e = tid; e < 32 * 32; e += 64) {
       const int a = e / 32, b = e % 32;
-      Lt[a][b] = (i0 + a < r && i0 + b < r) ? L[(size_t)(i0 + a) * LD + i0 + b] : ((a == b) ? 1.0 : 0.0);
+      Lt[a][b] = (i0 + a < r && i0 + b < r) ? L[(size_t)(i0 + a) * LS + i0 + b] : ((a == b) ? 1.0 : 0.0);
     }
     __syncthreads();
     double y[32];
@@ -1120,7 +1415,7 @@ __global__ void __launch_bounds__(64) be_trsm_kernel(BeView v) {
       __syncthreads();
       for (int e = tid; e < 32 * 32; e += 64) {
         const int a = e / 32, b = e % 32;
-        Lt[a][b] = (j0 + a < r && i0 + b < r) ? L[(size_t)(j0 + a) * LD + i0 + b] : 0.0;
+        Lt[a][b] = (j0 + a < r && i0 + b < r) ? L[(size_t)(j0 + a) * LS + i0 + b] : 0.0;
       }
       __syncthreads();
       if (act) {
@@ -1147,8 +1442,8 @@ __global__ void __launch_bounds__(256) be_correct_kernel(BeView v) {
   if (r <= 0) return;
   const int LD = v.be.LD;
   const double* Y = v.be.Tm + (size_t)s * v.be.RAWMAX * LD;
-  const double* z = v.be.zvec + (size_t)s * LD;
-  double* dx = v.be.dx + (size_t)s * LD;
+  const double* z = v.be.zvec + (size_t)s * v.be.LDS;
+  double* dx = v.be.dx + (size_t)s * v.be.LDS;
   for (int c = tid; c < d; c += blockDim.x) {
     double acc = 0.0;
     for (int i = 0; i < r; ++i) acc += Y[(size_t)i * LD + c] * z[i];
@@ -1189,6 +1484,18 @@ __global__ void __launch_bounds__(256) be_correct_kernel(BeView v) {
     rot_to_quat(m3_mul(R_b2w, R_c2b), w + W_QCAM);
     st3(w + W_PCAM, ld3(w + W_P) + m3_vec(R_b2w, t_c_b));
   }
+  __syncthreads();
+  // inverse depth of the SLAM features already in the state and their world positions (:1536-1575, :1752-1801)
+  const int nf = ic[I_NF];
+  const int base = BE_LEG + 6 * n_win;
+  for (int i = tid; i < nf; i += blockDim.x) {
+    const size_t fi = (size_t)s * v.be.T + v.be.fs_slot[(size_t)s * 64 + i];
+    const double inv = v.be.ft_inv[fi] + dx[base + i];
+    v.be.ft_inv[fi] = inv;
+    const double* wa = win_of(v, s, v.be.ft_anchor[fi]);
+    const V3 p_c = v3(v.be.ft_oa[fi * 2] / inv, v.be.ft_oa[fi * 2 + 1] / inv, 1.0 / inv);
+    st3(v.be.ft_pos + fi * 3, m3_vec(quat_to_rot(wa + W_QCAM), p_c) + ld3(wa + W_PCAM));
+  }
 }
 
 // measurementUpdate_ZUPT_vpq (:2791-2830): the 9-row system [v; dp; dq] of a detected standstill, written into the
@@ -1199,10 +1506,19 @@ __global__ void __launch_bounds__(256) be_zupt_build_kernel(BeView v) {
   if (!ic[I_OK]) return;
   if (!ic[I_ZUPT]) { if (tid == 0) { ic[I_ROWS] = 0; ic[I_R] = 0; } return; }
   const int RMAX = v.be.RMAX, LD = v.be.LD;
-  const int d = ic[I_DIM], N = ic[I_NWIN];
+  const int nf0 = ic[I_NF];
+  if (nf0 > 0) {                                        // :2770-2782: every SLAM feature leaves the state
+    for (int i = tid; i < nf0; i += blockDim.x) {
+      const size_t fi = (size_t)s * v.be.T + v.be.fs_slot[(size_t)s * 64 + i];
+      v.be.ft_flags[fi] &= ~(2 | 4 | 8);
+    }
+  }
+  __syncthreads();
+  const int d = ic[I_DIM] - nf0, N = ic[I_NWIN];
+  if (tid == 0) { ic[I_DIM] = d; ic[I_NF] = 0; core_of(v, s)[C_LAST_ZUPT] = core_of(v, s)[C_TIME]; }
   double* Hs = v.be.Hs + (size_t)s * LD * RMAX;
   double* rs = v.be.rs + (size_t)s * RMAX;
-  double* dg = v.be.dx + (size_t)s * LD;             // per-row measurement variances (dx is free until be_correct)
+  double* dg = v.be.dx + (size_t)s * v.be.LDS;        // per-row measurement variances (dx is free until be_correct)
   for (int e = tid; e < 9 * d; e += blockDim.x) { const int col = e / 9, row = e - col * 9; Hs[(size_t)col * RMAX + row] = 0.0; }
   __syncthreads();
   if (tid < 3) {
@@ -1233,7 +1549,9 @@ __global__ void be_apply_actions_kernel(BeView v) {
   int* ic = icore_of(v, s);
   if (!ic[I_OK] || i >= v.be.T) return;
   const size_t fi = (size_t)s * v.be.T + i;
-  if (v.be.ft_action[fi] != 0) { v.be.ft_flags[fi] = 0; v.be.ft_mask[fi] = 0; v.be.ft_action[fi] = 0; }
+  const int act = v.be.ft_action[fi];
+  if (act == 1 || act == 2) { v.be.ft_flags[fi] = 0; v.be.ft_mask[fi] = 0; }   // SLAM features (3, 4) stay in the map
+  v.be.ft_action[fi] = 0;
 }
 
 // ====================================================================== pruning
@@ -1271,6 +1589,138 @@ __global__ void be_prune_select_kernel(BeView v) {
   ic[I_RM0] = rm[0]; ic[I_RM1] = rm[1]; ic[I_NRM] = 2; ic[I_DO_PRUNE] = 1;
 }
 
+// getNewAnchorId (:3412-3472): among the first n-2 window states that observed the feature and stay, the one with the
+// smallest reprojection distance; otherwise the newest state
+__device__ int new_anchor_slot(const BeView& v, int s, size_t fi, int n_win, int r0, int r1) {
+  if (n_win <= 2) return n_win - 1;
+  const unsigned long long mask = v.be.ft_mask[fi];
+  const V3 p_w = ld3(v.be.ft_pos + fi * 3);
+  const double* obs = v.be.ft_obs + fi * v.be.Wcap * 4;
+  int best = -1; double min_dis = 99999;
+  for (int i = 0; i < n_win - 2; ++i) {
+    if (!((mask >> i) & 1) || i == r0 || i == r1) continue;
+    const double* w = win_of(v, s, i);
+    const V3 pn = m3_tvec(quat_to_rot(w + W_QCAM), p_w - ld3(w + W_PCAM));
+    const double dx = pn.x / pn.z - obs[(size_t)i * 4], dy = pn.y / pn.z - obs[(size_t)i * 4 + 1];
+    const double dis = sqrt(dx * dx + dy * dy);
+    if (min_dis > dis) { min_dis = dis; best = i; }
+  }
+  return best >= 0 ? best : n_win - 1;
+}
+
+// anchor changes of pruneImuStateBuffer (:2345-2461) for features whose anchor pose is about to leave the window:
+// in-state SLAM features get updateFeatureCov_1didp (:3125-3293), one after the other in feature-id order (each rewrites
+// one row/column of P that the next one reads); potential SLAM features outside the state are only re-anchored.
+__global__ void __launch_bounds__(256) be_anchor_kernel(BeView v) {
+  __shared__ double Jv[20]; __shared__ int Jc[20];
+  __shared__ int s_list[64]; __shared__ int s_n, s_new;
+  extern __shared__ double pfl[];          // [LD]
+  const int s = blockIdx.x, tid = threadIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK] || !ic[I_DO_PRUNE]) return;
+  const int T = v.be.T, LD = v.be.LD, Wcap = v.be.Wcap;
+  const int n_win = ic[I_NWIN], r0 = ic[I_RM0], r1 = (ic[I_NRM] > 1) ? ic[I_RM1] : -1;
+  const bool fej = ic[I_FEJ] != 0;
+  double* P = P_of(v, s);
+  const double* core = core_of(v, s);
+  const int d = ic[I_DIM];
+  if (tid == 0) {
+    // potential SLAM features outside the state (ekf flag, initialised): plain re-anchoring (:2408-2461)
+    for (int i = 0; i < T; ++i) {
+      const size_t fi = (size_t)s * T + i;
+      const int fl = v.be.ft_flags[fi];
+      if (!(fl & 1) || (fl & 4) || !(fl & 8) || !(fl & 2)) continue;
+      const int as = v.be.ft_anchor[fi];
+      if (as != r0 && as != r1) continue;
+      if (!((v.be.ft_mask[fi] >> as) & 1)) continue;
+      const int ns = new_anchor_slot(v, s, fi, n_win, r0, r1);
+      const double* w = win_of(v, s, ns);
+      const V3 pn = m3_tvec(quat_to_rot(w + W_QCAM), ld3(v.be.ft_pos + fi * 3) - ld3(w + W_PCAM));
+      v.be.ft_inv[fi] = 1.0 / pn.z;
+      v.be.ft_oa[fi * 2] = v.be.ft_obs[(fi * Wcap + ns) * 4]; v.be.ft_oa[fi * 2 + 1] = v.be.ft_obs[(fi * Wcap + ns) * 4 + 1];
+      v.be.ft_anchor[fi] = ns;
+    }
+    // in-state features to re-anchor, sorted by feature id
+    const int* fs = v.be.fs_slot + (size_t)s * 64;
+    int n = 0;
+    for (int i = 0; i < ic[I_NF]; ++i) {
+      const size_t fi = (size_t)s * T + fs[i];
+      const int as = v.be.ft_anchor[fi];
+      if (as != r0 && as != r1) continue;
+      int k = n++;
+      while (k > 0 && v.be.ft_id[(size_t)s * T + fs[s_list[k - 1]]] > v.be.ft_id[fi]) { s_list[k] = s_list[k - 1]; --k; }
+      s_list[k] = i;
+    }
+    s_n = n;
+  }
+  __syncthreads();
+  const int n = s_n;
+  const int* fs = v.be.fs_slot + (size_t)s * 64;
+  for (int it = 0; it < n; ++it) {
+    const int fcnt = s_list[it];
+    const size_t fi = (size_t)s * T + fs[fcnt];
+    const int fidx = BE_LEG + 6 * n_win + fcnt;
+    if (tid == 0) {
+      const int os = v.be.ft_anchor[fi];
+      const int ns = new_anchor_slot(v, s, fi, n_win, r0, r1);
+      s_new = ns;
+      const double* wo = win_of(v, s, os);
+      const double* wn = win_of(v, s, ns);
+      const V3 p_w = ld3(v.be.ft_pos + fi * 3), p_fej = ld3(v.be.ft_pfej + fi * 3);
+      const M3 R_c2w_new = quat_to_rot(wn + W_QCAM);
+      const V3 pnew = m3_tvec(R_c2w_new, p_w - ld3(wn + W_PCAM));
+      v.be.ft_inv[fi] = 1.0 / pnew.z;                                 // :2393-2397
+      v.be.ft_oa[fi * 2] = pnew.x / pnew.z; v.be.ft_oa[fi * 2 + 1] = pnew.y / pnew.z;
+      // ---- updateFeatureCov_1didp
+      const M3 R_b2c = m3_load(core + C_RIC); const V3 t_c_b = ld3(core + C_TCI);
+      const M3 R_b2w_old = quat_to_rot(wo + W_Q), R_c2w_old = quat_to_rot(wo + W_QCAM);
+      V3 p_old;
+      if (fej) p_old = m3_vec(R_b2c, m3_tvec(R_b2w_old, p_fej - ld3(wo + W_PFEJ)) - t_c_b);
+      else p_old = m3_tvec(R_c2w_old, p_w - ld3(wo + W_PCAM));
+      const V3 p_old_ = m3_tvec(R_c2w_old, p_w - ld3(wo + W_PCAM));
+      const double inv_old = 1.0 / p_old_.z;
+      const V3 f_old = v3(p_old_.x / p_old_.z, p_old_.y / p_old_.z, 1.0);
+      const M3 R_b2w_new = quat_to_rot(wn + W_Q), R_w2b_new = m3_t(R_b2w_new);
+      const M3 R_w2c_new = m3_t(R_c2w_new);
+      const double inv_new = v.be.ft_inv[fi];
+      V3 pbo, pbn;
+      if (fej) { pbo = p_fej - ld3(wo + W_PFEJ); pbn = p_fej - ld3(wn + W_PFEJ); }
+      else { pbo = p_w - ld3(wo + W_P); pbn = p_w - ld3(wn + W_P); }
+      const double Jr = -inv_new * inv_new;
+      const double J_d = m3_vec(R_w2c_new, m3_vec(R_c2w_old, f_old)).z;
+      const M3 Jto = m3_scale(m3_mul(R_w2c_new, skew(pbo)), -1.0);
+      const M3 Jtn = m3_mul(R_w2c_new, skew(pbn));
+      const M3 Sk = skew(m3_vec(R_w2b_new, pbn) - t_c_b);
+      const M3 Rno = m3_mul(R_w2b_new, R_b2w_old);
+      const M3 Mx = m3_mul(Rno, skew(m3_tvec(R_b2c, p_old)));
+      const M3 Jet = m3_mul(R_b2c, m3_sub(Sk, Mx));
+      const M3 Jep = m3_mul(R_b2c, m3_sub(Rno, m3_identity()));
+      int k = 0;
+      Jc[k] = fidx; Jv[k++] = Jr * J_d * (-1.0 / (inv_old * inv_old));
+      for (int c = 0; c < 3; ++c) { Jc[k] = BE_LEG + 6 * os + c; Jv[k++] = Jr * Jto.m[6 + c]; }
+      for (int c = 0; c < 3; ++c) { Jc[k] = BE_LEG + 6 * os + 3 + c; Jv[k++] = Jr * R_w2c_new.m[6 + c]; }
+      for (int c = 0; c < 3; ++c) { Jc[k] = BE_LEG + 6 * ns + c; Jv[k++] = Jr * Jtn.m[6 + c]; }
+      for (int c = 0; c < 3; ++c) { Jc[k] = BE_LEG + 6 * ns + 3 + c; Jv[k++] = Jr * -R_w2c_new.m[6 + c]; }
+      for (int c = 0; c < 3; ++c) { Jc[k] = 15 + c; Jv[k++] = Jr * Jet.m[6 + c]; }
+      for (int c = 0; c < 3; ++c) { Jc[k] = 18 + c; Jv[k++] = Jr * Jep.m[6 + c]; }
+      v.be.ft_anchor[fi] = ns;
+    }
+    __syncthreads();
+    for (int c = tid; c < d; c += blockDim.x) {
+      double acc = 0.0;
+      for (int k = 0; k < 19; ++k) acc += Jv[k] * P[(size_t)Jc[k] * LD + c];
+      pfl[c] = acc;
+    }
+    __syncthreads();
+    double pff = 0.0;
+    if (tid == 0) for (int k = 0; k < 19; ++k) pff += pfl[Jc[k]] * Jv[k];
+    __syncthreads();
+    for (int c = tid; c < d; c += blockDim.x) if (c != fidx) { P[(size_t)fidx * LD + c] = pfl[c]; P[(size_t)c * LD + fidx] = pfl[c]; }
+    if (tid == 0) P[(size_t)fidx * LD + fidx] = pff;
+    __syncthreads();
+  }
+}
+
 // drop the observations of the removed states from every feature and re-pack slots (:2530-2532, :2556-2558),
 // then re-pack the window arrays (:2636-2637)
 __global__ void __launch_bounds__(256) be_prune_tables_kernel(BeView v) {
@@ -1279,7 +1729,7 @@ __global__ void __launch_bounds__(256) be_prune_tables_kernel(BeView v) {
   if (!ic[I_OK] || !ic[I_DO_PRUNE]) return;
   const int T = v.be.T, Wcap = v.be.Wcap;
   const int n = ic[I_NWIN];
-  const int r0 = ic[I_RM0], r1 = ic[I_RM1];
+  const int r0 = ic[I_RM0], r1 = (ic[I_NRM] > 1) ? ic[I_RM1] : -1;
   for (int i = tid; i < T; i += blockDim.x) {
     const size_t fi = (size_t)s * T + i;
     if (!(v.be.ft_flags[fi] & 1)) continue;
@@ -1296,6 +1746,8 @@ __global__ void __launch_bounds__(256) be_prune_tables_kernel(BeView v) {
       ++dst;
     }
     v.be.ft_mask[fi] = nm;
+    const int as = v.be.ft_anchor[fi];                 // anchors are window slots: follow the re-pack
+    if (as >= 0) v.be.ft_anchor[fi] = as - (as > r0 ? 1 : 0) - ((r1 >= 0 && as > r1) ? 1 : 0);
   }
   __syncthreads();
   if (tid < BE_WIN + 1) {
@@ -1323,7 +1775,7 @@ __global__ void __launch_bounds__(256) be_prune_cov_gather_kernel(BeView v) {
   const int a0 = BE_LEG + 6 * ic[I_RM0], a1 = (nrm > 1) ? BE_LEG + 6 * ic[I_RM1] : (1 << 30);
   auto src = [&](int i) { int x = i; if (x >= a0) x += 6; if (x >= a1) x += 6; return x; };
   const double* P = P_of(v, s);
-  double* Sd = v.be.Sm + (size_t)s * LD * LD;
+  double* Sd = v.be.Sm + (size_t)s * v.be.LDS * v.be.LDS;
   const int sr = src(row);
   for (int c = threadIdx.x; c < nd; c += blockDim.x) Sd[(size_t)row * LD + c] = P[(size_t)sr * LD + src(c)];
 }
@@ -1335,7 +1787,7 @@ __global__ void __launch_bounds__(256) be_prune_cov_scatter_kernel(BeView v) {
   const int nd = d - 6 * ic[I_NRM];
   if (row >= nd) return;
   double* P = P_of(v, s);
-  const double* Sd = v.be.Sm + (size_t)s * LD * LD;
+  const double* Sd = v.be.Sm + (size_t)s * v.be.LDS * v.be.LDS;
   for (int c = threadIdx.x; c < nd; c += blockDim.x) P[(size_t)row * LD + c] = Sd[(size_t)row * LD + c];
 }
 
@@ -1348,6 +1800,156 @@ __global__ void be_frame_end_kernel(BeView v) {
   if (ic[I_DO_PRUNE]) { ic[I_DIM] -= 6 * ic[I_NRM]; ic[I_NWIN] -= ic[I_NRM]; }
   const double* core = core_of(v, s);
   if (v.cfg.if_FEJ_config && !ic[I_FEJ] && core[C_TIME] - core[C_TAKEOFF] >= 0) ic[I_FEJ] = 1;
+}
+
+}  // namespace
+
+namespace {
+
+// ---------------------------------------------------------------- generic covariance re-map P'[i][j] = P[m(i)][m(j)]
+// used by stateAugmentation with SLAM features in the state (:768-793), rmLostFeaturesCov (:3296-3348) and the drop of all
+// SLAM features on ZUPT.  Gather into the Sm scratch, copy back, commit the new dimension.
+__global__ void __launch_bounds__(256) be_remap_gather_kernel(BeView v) {
+  const int s = blockIdx.y, row = blockIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK] || !ic[I_REMAP]) return;
+  const int nd = ic[I_NEWDIM], LD = v.be.LD;
+  if (row >= nd) return;
+  const int* cm = v.be.cmap + (size_t)s * LD;
+  const double* P = P_of(v, s);
+  double* Sd = v.be.Sm + (size_t)s * v.be.LDS * v.be.LDS;
+  const int sr = cm[row];
+  for (int c = threadIdx.x; c < nd; c += blockDim.x) Sd[(size_t)row * LD + c] = P[(size_t)sr * LD + cm[c]];
+}
+__global__ void __launch_bounds__(256) be_remap_scatter_kernel(BeView v) {
+  const int s = blockIdx.y, row = blockIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK] || !ic[I_REMAP]) return;
+  const int nd = ic[I_NEWDIM], LD = v.be.LD;
+  if (row >= nd) return;
+  double* P = P_of(v, s);
+  const double* Sd = v.be.Sm + (size_t)s * v.be.LDS * v.be.LDS;
+  for (int c = threadIdx.x; c < nd; c += blockDim.x) P[(size_t)row * LD + c] = Sd[(size_t)row * LD + c];
+}
+__global__ void be_remap_commit_kernel(BeView v) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= v.be.S) return;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK] || !ic[I_REMAP]) return;
+  ic[I_DIM] = ic[I_NEWDIM]; ic[I_REMAP] = 0;
+}
+
+__device__ __forceinline__ int grid_code(const BeView& v, double x, double y) {
+  const int row = (int)((y - v.cfg.y_min) / v.cfg.grid_h), col = (int)((x - v.cfg.x_min) / v.cfg.grid_w);
+  return row * v.be.grid_cols + col;
+}
+
+// ---------------------------------------------------------------- in-state SLAM features at the start of removeLostFeatures
+// (:1896-1924): lost ones leave the state (covariance re-map, feature erased); grid occupancy of the rest (updateGridMap).
+// grid counts live in cand[s][64..127].
+__global__ void __launch_bounds__(64) be_slam_pre_kernel(BeView v) {
+  const int s = blockIdx.x, tid = threadIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK]) return;
+  const int T = v.be.T, Wcap = v.be.Wcap, LD = v.be.LD;
+  int* grid = v.be.cand + (size_t)s * 128 + 64;
+  if (tid < 64) grid[tid] = 0;
+  __syncthreads();
+  if (tid != 0) return;
+  const int nf = ic[I_NF];
+  if (nf == 0) return;
+  int* fs = v.be.fs_slot + (size_t)s * 64;
+  const int cur = ic[I_NWIN] - 1, d = ic[I_DIM];
+  const int base = d - nf;
+  int* cm = v.be.cmap + (size_t)s * LD;
+  int keep = 0;
+  for (int i = 0; i < base; ++i) cm[i] = i;
+  for (int i = 0; i < nf; ++i) {
+    const int slot = fs[i];
+    const size_t fi = (size_t)s * T + slot;
+    if ((v.be.ft_mask[fi] >> cur) & 1) {
+      cm[base + keep] = base + i;
+      fs[keep++] = slot;
+      const double* o = v.be.ft_obs + (fi * Wcap + cur) * 4;
+      const int code = grid_code(v, o[0], o[1]);
+      if (code >= 0 && code < 64) grid[code]++;
+    } else {
+      v.be.ft_flags[fi] = 0; v.be.ft_mask[fi] = 0;              // rmLostFeaturesCov erases the feature
+    }
+  }
+  if (keep != nf) { ic[I_REMAP] = 1; ic[I_NEWDIM] = base + keep; ic[I_NF] = keep; }
+}
+
+// ---------------------------------------------------------------- sequential part of the promotion rule (:1968-2002)
+// Candidates = tracked, not in state, observed >= max_track_len times; processed in ascending feature id like the
+// reference's std::map; the classify kernel left a speculative two-view-initialised triangulation in ft_spec.
+__global__ void be_slam_decide_kernel(BeView v) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= v.be.S) return;
+  int* ic = icore_of(v, s);
+  ic[I_NCAND] = 0; ic[I_NNEW] = 0;
+  if (!ic[I_OK]) return;
+  const int T = v.be.T, Wcap = v.be.Wcap;
+  const double* core = core_of(v, s);
+  int* cand = v.be.cand + (size_t)s * 128;
+  int* grid = cand + 64;
+  // collect candidates (action 5) sorted by id (insertion sort, at most 64; the rest falls back to the MSCKF rule)
+  int n = 0;
+  for (int i = 0; i < T; ++i) {
+    const size_t fi = (size_t)s * T + i;
+    if (v.be.ft_action[fi] != 5) continue;
+    if (n == 64) { v.be.ft_action[fi] = 0; atomicExch(&ic[I_ERR], 5); continue; }
+    const unsigned long long id = v.be.ft_id[fi];
+    int k = n++;
+    while (k > 0 && v.be.ft_id[(size_t)s * T + cand[k - 1]] > id) { cand[k] = cand[k - 1]; --k; }
+    cand[k] = i;
+  }
+  const int cur = ic[I_NWIN] - 1;
+  const bool zupt = ic[I_ZUPT] != 0;
+  int n_new = 0;
+  const int nf = ic[I_NF];
+  int newlist[64];
+  for (int k = 0; k < n; ++k) {
+    const int slot = cand[k];
+    const size_t fi = (size_t)s * T + slot;
+    int flags = v.be.ft_flags[fi];
+    const unsigned long long mask = v.be.ft_mask[fi];
+    const double* o = v.be.ft_obs + (fi * Wcap + cur) * 4;
+    const int code = grid_code(v, o[0], o[1]);
+    const double* sp = v.be.ft_spec + fi * 8;
+    const bool spec_ok = sp[0] != 0.0;
+    const bool slam = v.cfg.hybrid && code >= 0 && code < 64 && grid[code] < v.be.max_per_cell &&
+                      core[C_TIME] - core[C_LAST_ZUPT] > 5 && (nf + n_new) < v.be.NFmax;
+    auto commit_spec = [&](bool ekf) {
+      double* pos = v.be.ft_pos + fi * 3;
+      if (!(flags & 2)) { v.be.ft_pfej[fi * 3] = pos[0]; v.be.ft_pfej[fi * 3 + 1] = pos[1]; v.be.ft_pfej[fi * 3 + 2] = pos[2]; }
+      pos[0] = sp[1]; pos[1] = sp[2]; pos[2] = sp[3];
+      const double inv = 1.0 / sp[6];
+      v.be.ft_inv[fi] = inv; v.be.ft_oa[fi * 2] = sp[4] * inv; v.be.ft_oa[fi * 2 + 1] = sp[5] * inv;
+      v.be.ft_anchor[fi] = 63 - __clzll((long long)(mask & ~(1ull << cur)));
+      flags |= 2;
+      if (ekf) flags |= 8;
+    };
+    int action = 0; unsigned long long usemask = 0; int nrows = 0;
+    const int m = __popcll(mask);
+    if (slam) {
+      if (!(flags & 8)) {               // not yet a potential EKF feature: re-initialise from scratch (:1977-1981)
+        flags &= ~2;
+        if (spec_ok) commit_spec(true);
+      }
+      if (flags & 2) {
+        action = 3; usemask = mask; nrows = 2 * m + 2 * (m - 1);
+        grid[code]++; newlist[n_new++] = slot;
+      }
+    } else {
+      if (!(flags & 2) && spec_ok) commit_spec(false);
+      if (flags & 2) { action = 2; usemask = mask; nrows = 2 * m; }
+    }
+    if (zupt && action == 2) { flags &= ~2; usemask = 0; nrows = 0; }      // :2241-2246
+    v.be.ft_flags[fi] = flags; v.be.ft_action[fi] = action; v.be.ft_usemask[fi] = usemask; v.be.ft_nrows[fi] = nrows;
+  }
+  for (int k = 0; k < n_new; ++k) cand[k] = newlist[k];     // new SLAM features in id order = their future state order
+  ic[I_NCAND] = n_new;
 }
 
 }  // namespace
@@ -1369,8 +1971,11 @@ static int bdalloc(LvbHandle* h, T** p, size_t count) {
 
 static const char* be_unsupported_reason(const LvbConfig& c) {
   if (c.calib_imu_instrinsic) return "calib_imu_instrinsic: 1 (IMU-intrinsic calibration, LEG_DIM 46) is not built yet";
-  if (c.max_features_in_one_grid > 0 && c.aug_grid_rows * c.aug_grid_cols != 0)
-    return "hybrid EKF-SLAM features (max_features_in_one_grid > 0) are not built yet; set it to 0 for pure MSCKF";
+  if (c.max_features_in_one_grid > 0 && c.aug_grid_rows * c.aug_grid_cols != 0) {
+    if (c.feature_idp_dim != 1) return "feature_idp_dim: 3 (3-D inverse-depth SLAM features) is not built yet; use 1";
+    if (c.use_schmidt) return "use_schmidt: 1 (Schmidt nuisance states) is not built yet";
+    if (c.max_features_in_one_grid * c.aug_grid_rows * c.aug_grid_cols > 64) return "more than 64 EKF-SLAM features";
+  }
   if (c.sw_size + 1 > 64) return "sw_size > 63";
   return nullptr;
 }
@@ -1416,6 +2021,14 @@ static BeView make_beview(LvbHandle* h) {
   v.cfg.zupt_nv = c.zupt_noise_v * c.zupt_noise_v; v.cfg.zupt_np = c.zupt_noise_p * c.zupt_noise_p; v.cfg.zupt_nq = c.zupt_noise_q * c.zupt_noise_q;
   v.cfg.max_track_len = c.max_track_len; v.cfg.sw_size = c.sw_size; v.cfg.least_obs = c.least_observation_number;
   v.cfg.if_FEJ_config = c.if_FEJ; v.cfg.estimate_td = c.estimate_td; v.cfg.if_ZUPT_valid = c.if_ZUPT_valid;
+  v.cfg.hybrid = h->be->NFmax > 0;
+  {
+    const double x_max = (c.width - c.cx) / c.fx, y_max = (c.height - c.cy) / c.fy;
+    v.cfg.x_min = -c.cx / c.fx; v.cfg.y_min = -c.cy / c.fy;
+    const int cells = c.aug_grid_rows * c.aug_grid_cols;
+    v.cfg.grid_w = cells ? (x_max - v.cfg.x_min) / c.aug_grid_cols : (x_max - v.cfg.x_min);
+    v.cfg.grid_h = cells ? (y_max - v.cfg.y_min) / c.aug_grid_rows : (y_max - v.cfg.y_min);
+  }
   v.msg = nullptr; v.msg_n = nullptr; v.msg_t = nullptr; v.msg_valid = nullptr; v.msg_stride = 0;
   v.P = h->be->P[0]; v.Pn = h->be->P[1];
   return v;
@@ -1430,8 +2043,12 @@ int be_alloc(LvbHandle* h) {
   int sw = c.sw_size; if (sw < 5) sw = 5; if (sw > 63) sw = 63;
   be->Wcap = sw + 1;
   be->T = 2 * be->N;
-  be->Dmax = BE_LEG + 6 * be->Wcap;
+  be->grid_rows = c.aug_grid_rows; be->grid_cols = c.aug_grid_cols; be->max_per_cell = c.max_features_in_one_grid > 0 ? c.max_features_in_one_grid : 0;
+  be->NFmax = be->max_per_cell * be->grid_rows * be->grid_cols;
+  if (be->NFmax > 64 || c.feature_idp_dim != 1 || c.use_schmidt) be->NFmax = 0;   // such configs are refused at the first back-end call
+  be->Dmax = BE_LEG + 6 * be->Wcap + be->NFmax;
   be->LD = ((be->Dmax + 7) / 8) * 8;
+  be->LDS = be->NFmax ? ((be->Dmax + 2 * be->NFmax + 16 * be->NFmax + 7) / 8) * 8 : be->LD;
   be->RAWMAX = 4096; be->RMAX = 2048;
   be->imu_cap = 64;
   be->stats = h->fe.stats;
@@ -1445,7 +2062,9 @@ int be_alloc(LvbHandle* h) {
   BDA(be->Hraw, S * (size_t)be->RAWMAX * LD); BDA(be->rraw, S * (size_t)be->RAWMAX);
   BDA(be->Hs, S * LD * (size_t)be->RMAX); BDA(be->rs, S * (size_t)be->RMAX);
   BDA(be->Tm, S * (size_t)be->RAWMAX * LD);      // doubles as the per-feature H*P scratch of the gate
-  BDA(be->Sm, S * LD * LD); BDA(be->zvec, S * LD); BDA(be->dx, S * LD);
+  BDA(be->Sm, S * (size_t)be->LDS * be->LDS); BDA(be->zvec, S * (size_t)be->LDS); BDA(be->dx, S * (size_t)be->LDS);
+  BDA(be->ft_inv, S * T); BDA(be->ft_oa, S * T * 2); BDA(be->ft_anchor, S * T); BDA(be->ft_pfej, S * T * 3); BDA(be->ft_spec, S * T * 8);
+  BDA(be->fs_slot, S * 64); BDA(be->cmap, S * LD); BDA(be->cand, S * 128); BDA(be->Hnew, S * 64 * (LD + 4));
   BDA(be->imu, S * be->imu_cap); BDA(be->n_imu, S);
   BDA(be->msg_in, S * be->N); BDA(be->msg_in_n, S); BDA(be->msg_in_t, S); BDA(be->msg_in_valid, S);
   BPIN(be->pin_imu, LvbImu, S * be->imu_cap); BPIN(be->pin_n_imu, int, S); BPIN(be->pin_icore, int, S * BE_ICORE);
@@ -1460,8 +2079,9 @@ int be_alloc(LvbHandle* h) {
                                                           c.estimate_td, c.td, d_T);
   LVB_LAUNCH_CHECK(h);
   // dynamic shared memory opt-ins
-  const int fsm_bytes = (int)sizeof(double) * (6 * be->Wcap + 8 + 4 * be->Wcap * be->Wcap + 2 * be->Wcap);
+  const int fsm_bytes = (int)sizeof(double) * (6 * be->Wcap + 8 + 4 * be->Wcap * be->Wcap + 2 * be->Wcap + (8 + 6 * be->Wcap) / 2 + 4);
   LVB_CUDA(cudaFuncSetAttribute(be_feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm_bytes));
+  if (be->NFmax > 0) LVB_CUDA(cudaFuncSetAttribute(be_slam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 64 * be->LD)));
   const size_t chol_bytes = sizeof(double) * ((size_t)be->Dmax * (be->Dmax + 1) / 2 + 2 * be->Dmax);
   if (chol_bytes <= 227 * 1024) LVB_CUDA(cudaFuncSetAttribute(be_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_bytes));
   return LVB_OK;
@@ -1486,15 +2106,19 @@ static int launch_gemm(LvbHandle* h, const GemmArgs& g) {
 }
 
 // compression + EKF update on the stacked system currently in Hs/rs
+static int be_qr(LvbHandle* h, BeView& v) {
+  LVB_PROF(h, "be_qr_kernel");
+  be_qr_kernel<<<h->be->S, 512, sizeof(double) * h->be->RMAX, h->stream>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  return LVB_OK;
+}
+
 static int be_update(LvbHandle* h, BeView& v, bool zupt_rows = false) {
   LvbBackEnd* be = h->be;
   cudaStream_t st = h->stream;
   const size_t LD = be->LD;
-  LVB_PROF(h, "be_qr_kernel");
-  be_qr_kernel<<<be->S, 512, sizeof(double) * be->RMAX, st>>>(v);
-  LVB_LAUNCH_CHECK(h);
   GemmArgs g;
-  g.icore = be->icore; g.diag_vec = nullptr; g.sD = LD;
+  g.icore = be->icore; g.diag_vec = nullptr; g.sD = be->LDS;
   // T = H P
   g.A = be->Hs; g.sA = LD * be->RMAX; g.rsA = 1; g.csA = be->RMAX;
   g.B = v.P; g.sB = LD * LD; g.rsB = (int)LD; g.csB = 1;
@@ -1504,15 +2128,22 @@ static int be_update(LvbHandle* h, BeView& v, bool zupt_rows = false) {
   // S = T H^T + sigma^2 I
   g.A = be->Tm; g.sA = (size_t)be->RAWMAX * LD; g.rsA = (int)LD; g.csA = 1;
   g.B = be->Hs; g.sB = LD * be->RMAX; g.rsB = be->RMAX; g.csB = 1;
-  g.C = be->Sm; g.sC = LD * LD; g.rsC = (int)LD; g.csC = 1;
+  g.C = be->Sm; g.sC = (size_t)be->LDS * be->LDS; g.rsC = be->LDS; g.csC = 1;
   g.m_idx = I_R; g.n_idx = I_R; g.k_idx = I_DIM; g.alpha = 1.0; g.beta = 0.0; g.diag = v.cfg.sfeat2;
   if (zupt_rows) g.diag_vec = be->dx;
   RC(launch_gemm(h, g));
   g.diag_vec = nullptr;
   const size_t chol_bytes = sizeof(double) * ((size_t)be->Dmax * (be->Dmax + 1) / 2 + 2 * be->Dmax);
-  LVB_PROF(h, "be_chol_kernel");
-  if (chol_bytes <= 227 * 1024) be_chol_kernel<<<be->S, 1024, chol_bytes, st>>>(v);
-  else be_chol_gmem_kernel<<<be->S, 512, sizeof(double) * LD, st>>>(v);
+  const bool smem_ok = chol_bytes <= 227 * 1024;
+  if (smem_ok) {
+    LVB_PROF(h, "be_chol_kernel");
+    be_chol_kernel<<<be->S, 1024, chol_bytes, st>>>(v);
+    LVB_LAUNCH_CHECK(h);
+  }
+  if (!smem_ok || be->NFmax > 0) {               // systems larger than the packed-smem capacity (hybrid mode, big windows)
+    LVB_PROF(h, "be_chol_gmem_kernel");
+    be_chol_gmem_kernel<<<be->S, 512, sizeof(double) * be->LDS, st>>>(v, smem_ok ? be->Dmax : 0);
+  }
   LVB_LAUNCH_CHECK(h);
   BeView vt = v;
   LVB_PROF(h, "be_trsm_kernel");
@@ -1530,23 +2161,71 @@ static int be_update(LvbHandle* h, BeView& v, bool zupt_rows = false) {
   return LVB_OK;
 }
 
+static int be_remap(LvbHandle* h, BeView& v) {
+  LvbBackEnd* be = h->be;
+  LVB_PROF(h, "be_remap_gather_kernel");
+  be_remap_gather_kernel<<<dim3(be->Dmax, be->S), 256, 0, h->stream>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  LVB_PROF(h, "be_remap_scatter_kernel");
+  be_remap_scatter_kernel<<<dim3(be->Dmax, be->S), 256, 0, h->stream>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  LVB_PROF(h, "be_remap_commit_kernel");
+  be_remap_commit_kernel<<<(be->S + 63) / 64, 64, 0, h->stream>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  return LVB_OK;
+}
+
 static int be_measurement_pass(LvbHandle* h, BeView& v, int mode) {
   LvbBackEnd* be = h->be;
   cudaStream_t st = h->stream;
+  const bool hybrid = be->NFmax > 0;
+  if (hybrid && mode == 0) {
+    LVB_PROF(h, "be_slam_pre_kernel");
+    be_slam_pre_kernel<<<be->S, 64, 0, st>>>(v);
+    LVB_LAUNCH_CHECK(h);
+    RC(be_remap(h, v));
+  }
+  if (hybrid && mode == 1) {
+    LVB_PROF(h, "be_anchor_kernel");
+    be_anchor_kernel<<<be->S, 256, sizeof(double) * be->LD, st>>>(v);
+    LVB_LAUNCH_CHECK(h);
+  }
   LVB_PROF(h, "be_classify_kernel");
   be_classify_kernel<<<dim3((be->T + 3) / 4, be->S), 128, 0, st>>>(v, mode);
   LVB_LAUNCH_CHECK(h);
+  if (hybrid && mode == 0) {
+    LVB_PROF(h, "be_slam_decide_kernel");
+    be_slam_decide_kernel<<<(be->S + 31) / 32, 32, 0, st>>>(v);
+    LVB_LAUNCH_CHECK(h);
+  }
   LVB_PROF(h, "be_scan_rows_kernel");
   be_scan_rows_kernel<<<be->S, 512, 0, st>>>(v, 0);
   LVB_LAUNCH_CHECK(h);
-  const int fsm_bytes = (int)sizeof(double) * (6 * be->Wcap + 8 + 4 * be->Wcap * be->Wcap + 2 * be->Wcap);
+  const int fsm_bytes = (int)sizeof(double) * (6 * be->Wcap + 8 + 4 * be->Wcap * be->Wcap + 2 * be->Wcap + (8 + 6 * be->Wcap) / 2 + 4);
   LVB_PROF(h, "be_feature_kernel");
   be_feature_kernel<<<dim3(be->T, be->S), 32, fsm_bytes, st>>>(v, be->Tm);
   LVB_LAUNCH_CHECK(h);
+  if (hybrid && mode == 0) {
+    LVB_PROF(h, "be_slam_accept_kernel");
+    be_slam_accept_kernel<<<(be->S + 31) / 32, 32, 0, st>>>(v);
+    LVB_LAUNCH_CHECK(h);
+  }
   LVB_PROF(h, "be_stack_kernel");
-  be_stack_kernel<<<be->S, 512, 0, st>>>(v);
+  be_stack_kernel<<<be->S, 512, 0, st>>>(v, 0);
   LVB_LAUNCH_CHECK(h);
-  return be_update(h, v);
+  RC(be_qr(h, v));
+  if (hybrid && mode == 0) {
+    LVB_PROF(h, "be_stack_kernel");
+    be_stack_kernel<<<be->S, 512, 0, st>>>(v, 1);
+    LVB_LAUNCH_CHECK(h);
+  }
+  RC(be_update(h, v));
+  if (hybrid && mode == 0) {
+    LVB_PROF(h, "be_slam_grow_kernel");
+    be_slam_grow_kernel<<<be->S, 256, sizeof(double) * 64 * be->LD, st>>>(v);
+    LVB_LAUNCH_CHECK(h);
+  }
+  return LVB_OK;
 }
 
 // msg arrays are device pointers. imu/n_imu: caller's host buffers (mutated).
@@ -1577,6 +2256,7 @@ int be_process(LvbHandle* h, const LvbFeature* d_msg, const int* d_msg_n, const 
   LVB_PROF(h, "be_augment_kernel");
   be_augment_kernel<<<S, 256, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
+  if (be->NFmax > 0) RC(be_remap(h, v));
   if (h->cfg.if_ZUPT_valid) {                        // checkZUPT -> measurementUpdate_ZUPT_vpq (:405-406)
     LVB_PROF(h, "be_zupt_build_kernel");
     be_zupt_build_kernel<<<S, 256, 0, st>>>(v);
@@ -1664,6 +2344,7 @@ __global__ void be_set_state_kernel(BeView v, int s, double t, const double* val
     core[C_FNOW_P + i] = vals[4 + i]; core[C_FNOW_V + i] = vals[7 + i];
   }
   core[C_TAKEOFF] = t;
+  core[C_LAST_ZUPT] = t;
   ic[I_GRAVITY] = 1;
 }
 

@@ -9,14 +9,15 @@
 enum {
   C_TIME = 0, C_Q = 1, C_P = 5, C_V = 8, C_BG = 11, C_BA = 14, C_RIC = 17 /*R_imu_cam0 row-major*/, C_TCI = 26,
   C_TD = 29, C_DT = 30, C_FNOW_P = 31, C_FNOW_V = 34, C_FOLD_P = 37, C_FOLD_V = 40, C_OLD_Q = 43, C_OLD_P = 47,
-  C_OLD_V = 50, C_GYRO_OLD = 53, C_ACC_OLD = 56, C_TRACK_RATE = 59, C_TAKEOFF = 60, BE_CORE = 64
+  C_OLD_V = 50, C_GYRO_OLD = 53, C_ACC_OLD = 56, C_TRACK_RATE = 59, C_TAKEOFF = 60, C_LAST_ZUPT = 61, BE_CORE = 64
 };
 // ---- icore[s][BE_ICORE] ints
 enum {
   I_ID = 0, I_NEXT_ID = 1, I_NWIN = 2, I_GRAVITY = 3, I_FIRST = 4, I_FEJ = 5, I_HAVE_OLD = 6, I_DIM = 7,
   I_ZUPT = 8, I_OK = 9 /*processFeatures return of this frame*/, I_CONSUMED = 10, I_ROWS = 11 /*stacked rows*/,
   I_R = 12 /*rows after compression*/, I_NUSED = 13, I_RAWROWS = 14, I_ERR = 15, I_RM0 = 16, I_RM1 = 17, I_NRM = 18,
-  I_DO_PRUNE = 19, I_ZUPT_EVENTS = 20, I_UPDATES = 21, BE_ICORE = 32
+  I_DO_PRUNE = 19, I_ZUPT_EVENTS = 20, I_UPDATES = 21, I_NF = 22 /*EKF-SLAM features in state*/, I_REMAP = 23, I_NEWDIM = 24,
+  I_NNEW = 25 /*new SLAM features accepted this frame*/, I_NCAND = 26, I_RO = 27 /*rows of H_o before the new-feature rows*/, BE_ICORE = 32
 };
 // ---- win[s][slot][BE_WIN] doubles (IMUState_Aug)
 enum { W_TIME = 0, W_DT = 1, W_Q = 2, W_P = 6, W_PFEJ = 9, W_RIC = 12, W_TCI = 21, W_QCAM = 24, W_PCAM = 28, BE_WIN = 32 };
@@ -30,11 +31,18 @@ struct LvbBackEnd {
   int RAWMAX;          // raw (unprojected) Jacobian rows per sequence per pass
   int RMAX;            // stacked (projected, gated) rows per sequence per pass
   int imu_cap;         // IMU samples per sequence per call
+  int NFmax;           // EKF-SLAM feature capacity (max_features_in_one_grid * grid cells), 0 = pure MSCKF
+  int LDS;             // leading dimension of Sm (rows of the stacked H_o can exceed the state dimension in hybrid mode)
+  int grid_rows, grid_cols, max_per_cell;
   double* core; int* icore;
   long long* win_id; double* win;
   double* P[2]; int pcur;                     // ping-pong covariance [S][LD][LD], row-major
   unsigned long long* ft_id; int* ft_flags; double* ft_pos; unsigned long long* ft_mask; double* ft_obs;  // [S][T]...
   int* ft_action; int* ft_rowofs; int* ft_nrows; int* ft_accept; unsigned long long* ft_usemask;
+  // EKF-SLAM (1-D inverse depth) bookkeeping per table slot: invDepth, corrected anchor observation (x,y), anchor window slot,
+  // first-estimate position; speculative triangulation results of this frame; state order list
+  double* ft_inv; double* ft_oa; int* ft_anchor; double* ft_pfej; double* ft_spec; int* fs_slot; int* cmap; int* cand;
+  double* Hnew;                               // [S][NFmax][LD + 4]: (H_1 row, h2, r_1) of the features added this frame
   double* Hraw; double* rraw;                 // [S][RAWMAX][LD], [S][RAWMAX]
   double* Hs; double* rs;                     // stacked, COLUMN-major [S][LD cols][RMAX rows], [S][RMAX]
   double* Tm;                                 // H*P   [S][RMAX? -> Dmax rows][LD]   (rows <= Dmax after compression)

@@ -168,8 +168,8 @@ __global__ void pad_reflect_kernel(uint8_t* __restrict__ pyr, LvbPyramidLayout L
 __global__ void __launch_bounds__(256) pyrdown_kernel(uint8_t* __restrict__ pyr, LvbPyramidLayout L, int src_level) {
   const int s = blockIdx.z;
   const LvbLevel ls = L.lv[src_level], ld = L.lv[src_level + 1];
-  const int x4 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;       // first of 4 destination columns
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;              // first of 4 destination columns (block = 32 x 8)
+  const int y = blockIdx.y * 8 + threadIdx.y;
   if (x4 >= ld.w || y >= ld.h) return;
   const uint8_t* so = lvb_level_origin((const uint8_t*)pyr, L, s, src_level);
   uint8_t* dorg = lvb_level_origin(pyr, L, s, src_level + 1);

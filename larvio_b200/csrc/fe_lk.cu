@@ -43,14 +43,15 @@ template <int K>
 __device__ __forceinline__ float run_chain(const float* T, int acc) {
   float a = 0.f;
   if (acc < 4) {
-    const float4* q = reinterpret_cast<const float4*>(T + acc * (WIN * K));
+    // WIN*K floats per accumulator: 84 (16-byte multiples) for K = 4, 42 (8-byte multiples) for K = 2 -> float2 loads
+    const float2* q = reinterpret_cast<const float2*>(T + acc * (WIN * K));
 #pragma unroll
-    for (int i = 0; i < WIN * K / 4; ++i) {
-      const float4 v = q[i];
-      a = __fadd_rn(a, v.x); a = __fadd_rn(a, v.y); a = __fadd_rn(a, v.z); a = __fadd_rn(a, v.w);
+    for (int i = 0; i < WIN * K / 2; ++i) {
+      const float2 v = q[i];
+      a = __fadd_rn(a, v.x); a = __fadd_rn(a, v.y);
     }
   } else {
-    const float* qt = T + 4 * (WIN * K);
+    const float* qt = T + 4 * (WIN * K);          // 336 / 168 floats: 16-byte aligned
     const float4* q = reinterpret_cast<const float4*>(qt);
 #pragma unroll
     for (int i = 0; i < (WIN * 5) / 4; ++i) {

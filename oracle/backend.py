@@ -609,13 +609,21 @@ class LarVioOracle:
         Q, R = np.linalg.qr(H, mode="reduced")
         return R[:cols], (Q.T @ r)[:cols]
 
-    # ---- :1883-2256 (pure MSCKF: in_state is always False)
+    # ---- removeLostFeatures :1883-2256
     def _remove_lost_features(self):
         sid_now = self.imu_state.id
-        rows_msckf = 0
         invalid = []; msckf_ids = []; lost_ids = []
+        ekf_new_ids = []; ekf_lost = []; ekf_ids = []
         for fid in sorted(self.map_server.keys()):
             ft = self.map_server[fid]
+            if ft.in_state:
+                (ekf_ids if sid_now in ft.obs else ekf_lost).append(fid)
+        self._rm_lost_features_cov(ekf_lost)
+        self._update_grid_map()
+        for fid in sorted(self.map_server.keys()):
+            ft = self.map_server[fid]
+            if ft.in_state:
+                continue
             tracked_now = sid_now in ft.obs
             if not tracked_now:
                 if len(ft.obs) < self.least_obs:
@@ -625,45 +633,141 @@ class LarVioOracle:
                         invalid.append(fid); continue
                     if not ft.initialize_position(self.aug, sid_now):
                         invalid.append(fid); continue
-                rows_msckf += 2 * len(ft.obs) - 3
                 msckf_ids.append(fid); lost_ids.append(fid)
             else:
                 if not (len(ft.obs) >= self.max_track_len):
                     continue
-                if not ft.is_initialized:
-                    if ft.check_motion(self.aug, tracked_now):
-                        ft.initialize_position(self.aug, sid_now)
-                if not ft.is_initialized:
-                    continue
-                rows_msckf += 2 * len(ft.obs) - 3
-                msckf_ids.append(fid); lost_ids.append(fid)
+                code = self._grid_code(ft.obs[sid_now]) if self.hybrid else 0
+                if (self.hybrid and len(self.grid_map.get(code, [])) < self.max_features and
+                        self.imu_state.time - self.last_ZUPT_time > 5 and
+                        (len(self.feature_states) + len(ekf_new_ids)) < self.max_features * self.grid_rows * self.grid_cols):
+                    if not ft.ekf_feature:
+                        ft.is_initialized = False
+                        if ft.check_motion(self.aug, tracked_now):
+                            ft.initialize_inv_param(self.aug, sid_now)
+                    if not ft.is_initialized:
+                        continue
+                    ekf_new_ids.append(fid)
+                    self.grid_map.setdefault(code, []).append(fid)
+                else:
+                    if not ft.is_initialized:
+                        if ft.check_motion(self.aug, tracked_now):
+                            ft.initialize_position(self.aug, sid_now)
+                    if not ft.is_initialized:
+                        continue
+                    msckf_ids.append(fid); lost_ids.append(fid)
         for fid in invalid:
             del self.map_server[fid]
-        self.stats["n_msckf_features"] = len(msckf_ids)
-        if len(msckf_ids) == 0:
+        self.stats["n_msckf_features"] = len(msckf_ids); self.stats["n_ekf_new"] = len(ekf_new_ids); self.stats["n_ekf"] = len(ekf_ids)
+        if len(msckf_ids) == 0 and len(ekf_new_ids) == 0 and len(ekf_ids) == 0:
             return
         if not self.if_ZUPT:
-            cols = self.LEG + 6 * len(self.aug)
+            d = self.P.shape[1]
+            # ---- new EKF-SLAM features (:2019-2125)
+            for fid in ekf_new_ids:
+                self.map_server[fid].in_state = True
+                self.feature_states.append(fid)
+            blocks = []
+            for fid in list(ekf_new_ids):
+                ft = self.map_server[fid]
+                sids = sorted(ft.obs.keys())
+                Hj, rj = self._feature_jacobian_ekf_new(ft, sids)
+                Hm, rm = self._feature_jacobian(ft, sids)
+                if self._gating(Hm, rm, 2 * len(sids) - 3):
+                    blocks.append((fid, Hj, rj))
+                else:
+                    ft.in_state = False
+            # drop the features that failed the gate: their state columns disappear
+            kept = [b[0] for b in blocks]
+            old_fs = list(self.feature_states)
+            n_old = len(old_fs) - len(ekf_new_ids)
+            self.feature_states = old_fs[:n_old] + kept
+            if kept:
+                keep_cols = list(range(d)) + [d + ekf_new_ids.index(fid) for fid in kept]
+                H_new = np.concatenate([b[1][:, keep_cols] for b in blocks]); r_new = np.concatenate([b[2] for b in blocks])
+                n_new = len(kept)
+                Hf = H_new[:, d:]
+                U_, _, _ = np.linalg.svd(Hf, full_matrices=True)
+                Vn = U_[:, n_new:]
+                Q, _ = np.linalg.qr(Hf, mode="complete")
+                W = np.concatenate([Vn, Q[:, :n_new]], 1)
+                H_new = W.T @ H_new; r_new = W.T @ r_new
+            else:
+                H_new = np.zeros((0, d)); r_new = np.zeros(0); n_new = 0
+            # ---- in-state EKF-SLAM features (:2127-2177)
             Hs = []; rs = []
-            m_hist = []
+            for fid in ekf_ids:
+                Hj, rj = self._feature_jacobian_ekf(self.map_server[fid])
+                if self._gating(Hj, rj, 2):
+                    Hs.append(Hj); rs.append(rj)
+            H_ekf = np.concatenate(Hs) if Hs else np.zeros((0, d)); r_ekf = np.concatenate(rs) if rs else np.zeros(0)
+            H_ekf, r_ekf = self._compress(H_ekf, r_ekf, d)
+            # ---- MSCKF features (:2179-2233)
+            cols = self.LEG + 6 * len(self.aug)
+            Hs = []; rs = []; m_hist = []
             for fid in msckf_ids:
                 ft = self.map_server[fid]
                 sids = sorted(ft.obs.keys())
                 Hj, rj = self._feature_jacobian(ft, sids)
                 if self._gating(Hj, rj, 2 * len(sids) - 3):
-                    Hs.append(Hj[:, :cols]); rs.append(rj)
-                    m_hist.append(len(sids))
-            H = np.concatenate(Hs) if Hs else np.zeros((0, cols))
-            r = np.concatenate(rs) if rs else np.zeros(0)
+                    Hs.append(Hj[:, :cols]); rs.append(rj); m_hist.append(len(sids))
+            H = np.concatenate(Hs) if Hs else np.zeros((0, cols)); r = np.concatenate(rs) if rs else np.zeros(0)
             self.stats["rows_msckf"] = H.shape[0]; self.stats["m_hist"] = m_hist
             H, r = self._compress(H, r, cols)
-            Hfull = np.zeros((H.shape[0], self.P.shape[1])); Hfull[:, :H.shape[1]] = H
-            self._update(Hfull, r, "hybrid")
+            H_msckf = np.zeros((H.shape[0], d)); H_msckf[:, :H.shape[1]] = H
+            self._update_hybrid(H_new, r_new, n_new, H_ekf, r_ekf, H_msckf, r)
         else:
             for fid in msckf_ids:
                 self.map_server[fid].is_initialized = False
         for fid in lost_ids:
             del self.map_server[fid]
+
+    # ---- measurementUpdate_hybrid :1605-1862 (no Schmidt)
+    def _update_hybrid(self, H_new, r_new, n_new, H_ekf, r_ekf, H_msckf, r_msckf):
+        d = self.P.shape[1]
+        sz_r = len(r_new) + len(r_ekf) + len(r_msckf)
+        if sz_r == 0:
+            return
+        k = H_new.shape[0] - n_new
+        H_o = np.concatenate([H_msckf, H_ekf, H_new[:k, :d]]); r_o = np.concatenate([r_msckf, r_ekf, r_new[:k]])
+        H_1 = H_new[k:, :d]; H_2 = H_new[k:, d:]; r_1 = r_new[k:]
+        P = self.P
+        S = H_o @ P @ H_o.T + self.feature_noise * np.eye(H_o.shape[0])
+        K = np.linalg.solve(S, H_o @ P).T if H_o.shape[0] else np.zeros((d, 0))
+        dx_leg = K @ r_o if H_o.shape[0] else np.zeros(d)
+        self.stats.setdefault("updates", []).append(dict(tag="hybrid", r=H_o.shape[0], d=d, n_new=n_new))
+        if n_new:
+            h2 = np.diag(H_2).copy()           # Eigen LDLT reads the lower triangle of the triangular factor (App. C-13)
+            HH = H_1 / h2[:, None]
+            dx_new = -HH @ dx_leg + r_1 / h2
+            dx = np.concatenate([dx_leg, dx_new])
+        else:
+            dx = dx_leg
+        s = self.imu_state
+        s.q = quat_mul(small_angle_quat(dx[0:3]), s.q)
+        s.v = s.v + dx[3:6]; s.p = s.p + dx[6:9]; s.bg = s.bg + dx[9:12]; s.ba = s.ba + dx[12:15]
+        s.R_imu_cam0 = s.R_imu_cam0 @ quat_to_rot(small_angle_quat(dx[15:18])).T
+        s.t_cam0_imu = s.t_cam0_imu + dx[18:21]
+        self.td += dx[21]
+        for i, sid in enumerate(sorted(self.aug.keys())):
+            a = self.aug[sid]
+            da = dx[self.LEG + 6 * i:self.LEG + 6 * i + 6]
+            a.q = quat_mul(small_angle_quat(da[0:3]), a.q)
+            a.p = a.p + da[3:6]
+            R_b2w = quat_to_rot(a.q)
+            a.q_cam = rot_to_quat(R_b2w @ s.R_imu_cam0.T)
+            a.p_cam = a.p + R_b2w @ s.t_cam0_imu
+        self._update_feature_states(dx, self.LEG + 6 * len(self.aug))
+        if H_o.shape[0]:
+            P = (np.eye(d) - K @ H_o) @ P
+            P = (P + P.T) / 2.0
+        if n_new:
+            nHHP = -HH @ P
+            P22 = -nHHP @ HH.T + self.feature_noise * np.diag(1.0 / (h2 * h2))
+            Pn = np.zeros((d + n_new, d + n_new))
+            Pn[:d, :d] = P; Pn[d:, :d] = nHHP; Pn[:d, d:] = nHHP.T; Pn[d:, d:] = P22
+            P = (Pn + Pn.T) / 2.0
+        self.P = P
 
     # ---- :1420-1602 / :1605-1862 with empty SLAM blocks
     def _update(self, H, r, tag, Rn=None):
@@ -883,6 +987,16 @@ class LarVioOracle:
             ft = self.map_server[fid]
             involved = [sid for sid in rm_ids if sid in ft.obs]
             if len(involved) == 0:
+                continue
+            if ft.in_state:
+                if ft.id_anchor in involved:                       # :2345-2405, 1-D IDP branch
+                    new_id = self._new_anchor_id(ft, involved)
+                    a = self.aug[new_id]
+                    p_new = quat_to_rot(a.q_cam).T @ (ft.position - a.p_cam)
+                    ft.invDepth = 1 / p_new[2]
+                    ft.obs_anchor = np.array([p_new[0] / p_new[2], p_new[1] / p_new[2], ft.obs_anchor[2]])
+                    self._update_feature_cov_1didp(ft, ft.id_anchor, new_id)
+                    ft.id_anchor = new_id
                 continue
             if ft.is_initialized and ft.id_anchor in involved:
                 new_id = self._new_anchor_id(ft, involved)

@@ -1,0 +1,45 @@
+"""GPU check: hybrid MSCKF + EKF-SLAM (euroc defaults) fused step against the oracle, with per-frame diagnostics."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from larvio_b200.config import Config
+from larvio_b200 import synth, api, harness
+from oracle.frontend import ImageProcessorOracle
+from oracle.backend import LarVioOracle
+
+NF = int(os.environ.get('NF', '130')); S = 2
+cfg = Config.load('configs/euroc_mono.yaml', sw_size=16)
+seqs = [synth.make_sequence(cfg.raw, s, NF) for s in range(S)]
+b = api.Batch(cfg, n_seq=S)
+fes = [ImageProcessorOracle(cfg.raw) for _ in range(S)]; bes = [LarVioOracle(cfg.raw) for _ in range(S)]
+feed = harness.ImuFeeder(seqs, stride=128)
+imu_o = [[] for _ in range(S)]; k = [0] * S; inited = [False] * S
+worst = 0.0
+for j in range(NF):
+    feed.push_until(j)
+    msgs = []
+    for s in range(S):
+        k2 = synth.imu_window(seqs[s], k[s], seqs[s].img_t[j]); imu_o[s].extend(seqs[s].imu[k[s]:k2].tolist()); k[s] = k2
+        msgs.append(fes[s].process_image(seqs[s].images[j], seqs[s].img_t[j], np.array(imu_o[s]).reshape(-1, 7)))
+        if msgs[s] is not None and not inited[s]:
+            a = (seqs[s].img_t[j], seqs[s].gt_q[j], seqs[s].gt_p[j], seqs[s].gt_v[j], np.zeros(3), np.zeros(3))
+            bes[s].set_initial_state(*a); b.set_initial_state(s, *a); inited[s] = True
+    imgs = np.stack([seqs[s].images[j] for s in range(S)]); t_img = np.array([seqs[s].img_t[j] for s in range(S)])
+    try:
+        ok = b.step(imgs, t_img, feed.buf, feed.n)
+    except Exception as e:
+        print('frame', j, 'GPU error', e); break
+    for s in range(S):
+        oko = bes[s].process_features(msgs[s], imu_o[s]) if msgs[s] is not None else False
+        if not oko: continue
+        st = b.get_state(s); P = b.get_covariance(s)
+        dp = float(np.abs(st['p'] - bes[s].imu_state.p).max())
+        same = P.shape == bes[s].P.shape
+        rel = float(np.linalg.norm(P - bes[s].P) / np.linalg.norm(bes[s].P)) if same else -1
+        worst = max(worst, dp)
+        if j > 98 and (j % 2 == 0) and s == 0 or not same or dp > 1e-7:
+            print('frame', j, 'seq', s, 'dp %.2e' % dp, 'Prel %.2e' % rel, 'dims', P.shape[0], bes[s].P.shape[0], 'nslam', len(bes[s].feature_states),
+                  {a: c for a, c in bes[s].stats.items() if a in ('n_ekf_new', 'n_ekf', 'n_msckf_features')}, flush=True)
+        if not same or dp > 1e-3:
+            print('DIVERGED'); sys.exit(0)
+print(json.dumps(dict(worst_dp=worst)))

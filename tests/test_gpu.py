@@ -249,6 +249,18 @@ def test_zupt_static_start_matches_oracle(cfg):
     assert rep['p'] < 1e-9 and rep['v'] < 1e-9 and rep['q'] < 1e-9 and rep['Prel'] < 1e-9
 
 
+def test_hybrid_slam_features_match_oracle(lib_built):
+    """euroc defaults: hybrid MSCKF + 1-D inverse-depth EKF-SLAM features (one per cell of a 5x6 grid).  SLAM features
+    enter the state 5 s after the start (larvio.cpp:1974), so the run is 130 frames long."""
+    from larvio_b200 import synth
+    from larvio_b200.config import Config
+    hc = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), sw_size=16)
+    hs = [synth.make_sequence(hc.raw, s, 130) for s in range(2)]
+    rep = _drive(hc, hs, 130, 'step')
+    assert rep['steps'] >= 60 and rep['ok_mismatch'] == 0 and rep['imu_mismatch'] == 0
+    assert rep['p'] < 1e-8 and rep['v'] < 1e-8 and rep['q'] < 1e-8 and rep['Prel'] < 1e-8
+
+
 def test_gpu_against_committed_golden(cfg, seqs):
     from larvio_b200 import api, harness
     g = np.load(GOLD)
@@ -313,7 +325,7 @@ def test_batch_invariance_and_properties_at_full_batch(cfg, seqs):
 def test_unsupported_configs_fail_loudly(lib_built):
     from larvio_b200 import api
     from larvio_b200.config import Config
-    c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"))      # hybrid SLAM features on (max_features_in_one_grid: 1)
+    c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), feature_idp_dim=3)      # 3-D inverse depth: not built
     b = api.Batch(c, n_seq=1)
     imu = np.zeros((1, 8), api.IMU_DTYPE); n = np.zeros(1, np.int32)
     with pytest.raises(api.LarvioB200Error) as e:
