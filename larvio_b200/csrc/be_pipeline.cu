@@ -1017,7 +1017,7 @@ __global__ void __launch_bounds__(512) be_stack_kernel(BeView v, int phase) {
   __syncthreads();
   const int base = (phase == 0) ? 0 : ic[I_R];
   int total = s_total;
-  const int cap = min(RMAX, v.be.LDS);
+  const int cap = (phase == 0) ? RMAX : min(RMAX, v.be.LDS);   // the MSCKF block is compressed to <= cols rows before the update
   if (base + total > cap) { if (tid == 0) atomicExch(&ic[I_ERR], 4); total = max(cap - base, 0); }
   int run = base + part[tid] - loc;
   for (int k = 0; k < per; ++k) {
@@ -1883,34 +1883,39 @@ __global__ void __launch_bounds__(64) be_slam_pre_kernel(BeView v) {
 // ---------------------------------------------------------------- sequential part of the promotion rule (:1968-2002)
 // Candidates = tracked, not in state, observed >= max_track_len times; processed in ascending feature id like the
 // reference's std::map; the classify kernel left a speculative two-view-initialised triangulation in ft_spec.
-__global__ void be_slam_decide_kernel(BeView v) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= v.be.S) return;
+__global__ void __launch_bounds__(256) be_slam_decide_kernel(BeView v) {
+  __shared__ int unsorted[1024], sorted[1024];
+  __shared__ int s_n;
+  const int s = blockIdx.x, tid = threadIdx.x;
   int* ic = icore_of(v, s);
-  ic[I_NCAND] = 0; ic[I_NNEW] = 0;
+  if (tid == 0) { ic[I_NCAND] = 0; ic[I_NNEW] = 0; s_n = 0; }
   if (!ic[I_OK]) return;
+  __syncthreads();
   const int T = v.be.T, Wcap = v.be.Wcap;
   const double* core = core_of(v, s);
   int* cand = v.be.cand + (size_t)s * 128;
   int* grid = cand + 64;
-  // collect candidates (action 5) sorted by id (insertion sort, at most 64; the rest falls back to the MSCKF rule)
-  int n = 0;
-  for (int i = 0; i < T; ++i) {
-    const size_t fi = (size_t)s * T + i;
-    if (v.be.ft_action[fi] != 5) continue;
-    if (n == 64) { v.be.ft_action[fi] = 0; atomicExch(&ic[I_ERR], 5); continue; }
-    const unsigned long long id = v.be.ft_id[fi];
-    int k = n++;
-    while (k > 0 && v.be.ft_id[(size_t)s * T + cand[k - 1]] > id) { cand[k] = cand[k - 1]; --k; }
-    cand[k] = i;
+  // candidates (action 5) sorted by feature id: unordered gather, then rank by counting smaller ids
+  for (int i = tid; i < T; i += blockDim.x)
+    if (v.be.ft_action[(size_t)s * T + i] == 5) { const int k = atomicAdd(&s_n, 1); if (k < 1024) unsorted[k] = i; }
+  __syncthreads();
+  const int n = min(s_n, 1024);
+  for (int k = tid; k < n; k += blockDim.x) {
+    const unsigned long long id = v.be.ft_id[(size_t)s * T + unsorted[k]];
+    int rank = 0;
+    for (int q = 0; q < n; ++q) rank += v.be.ft_id[(size_t)s * T + unsorted[q]] < id;
+    sorted[rank] = unsorted[k];
   }
+  __syncthreads();
+  if (tid != 0) return;
+  const int* cand_sorted = sorted;
   const int cur = ic[I_NWIN] - 1;
   const bool zupt = ic[I_ZUPT] != 0;
   int n_new = 0;
   const int nf = ic[I_NF];
   int newlist[64];
   for (int k = 0; k < n; ++k) {
-    const int slot = cand[k];
+    const int slot = cand_sorted[k];
     const size_t fi = (size_t)s * T + slot;
     int flags = v.be.ft_flags[fi];
     const unsigned long long mask = v.be.ft_mask[fi];
@@ -2195,7 +2200,7 @@ static int be_measurement_pass(LvbHandle* h, BeView& v, int mode) {
   LVB_LAUNCH_CHECK(h);
   if (hybrid && mode == 0) {
     LVB_PROF(h, "be_slam_decide_kernel");
-    be_slam_decide_kernel<<<(be->S + 31) / 32, 32, 0, st>>>(v);
+    be_slam_decide_kernel<<<be->S, 256, 0, st>>>(v);
     LVB_LAUNCH_CHECK(h);
   }
   LVB_PROF(h, "be_scan_rows_kernel");
