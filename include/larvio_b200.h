@@ -166,6 +166,9 @@ int lvb_profile_get(LvbHandle* h, const char** names, double* total_ms, long lon
  * [3] published messages, [4] EKF updates, [5] sum r, [6] sum r*d*d, [7] sum stacked rows, [8] QR runs, [9] sum R*c*c. */
 int lvb_get_stats(LvbHandle* h, unsigned long long* out16);
 
+/* debug: the 32 per-sequence integers of the filter (dimension, window size, SLAM feature count, flags ...). */
+int lvb_debug_icore(LvbHandle* h, int seq, int* out32);
+
 /* number of kernel launches issued through this handle so far (bench.py gpu_launches). */
 long long lvb_launch_count(const LvbHandle* h);
 

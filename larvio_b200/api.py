@@ -64,6 +64,8 @@ _lib.lvb_profile_enable.argtypes = [_vp, C.c_int]
 _lib.lvb_profile_reset.argtypes = [_vp]
 _lib.lvb_get_stats.argtypes = [_vp, C.POINTER(C.c_ulonglong)]
 _lib.lvb_get_stats.restype = C.c_int
+_lib.lvb_debug_icore.argtypes = [_vp, C.c_int, C.POINTER(C.c_int)]
+_lib.lvb_debug_icore.restype = C.c_int
 _lib.lvb_profile_get.argtypes = [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
 for _name in ("lvbk_pyramid", "lvbk_lk", "lvbk_orb", "lvbk_detect", "lvbk_undistort", "lvbk_ransac",
               "lvb_process_images", "lvb_process_features", "lvb_step", "lvb_set_initial_state",
@@ -76,7 +78,7 @@ EXPORTED_SYMBOLS = [
     "lvb_feature_capacity", "lvb_n_seq", "lvb_process_images", "lvb_process_features", "lvb_step",
     "lvb_synchronize", "lvb_set_initial_state", "lvb_get_state", "lvb_get_states", "lvb_get_window",
     "lvb_get_covariance", "lvbk_pyramid", "lvbk_lk", "lvbk_orb", "lvbk_detect", "lvbk_undistort",
-    "lvbk_ransac", "lvb_launch_count", "lvb_profile_enable", "lvb_profile_reset", "lvb_profile_get", "lvb_get_stats",
+    "lvbk_ransac", "lvb_launch_count", "lvb_profile_enable", "lvb_profile_reset", "lvb_profile_get", "lvb_get_stats", "lvb_debug_icore",
 ]
 
 
@@ -138,6 +140,11 @@ class Batch:
     def stats(self):
         out = (C.c_ulonglong * 16)()
         _check(_lib.lvb_get_stats(self._h, out))
+        return [int(x) for x in out]
+
+    def debug_icore(self, seq):
+        out = (C.c_int * 32)()
+        _check(_lib.lvb_debug_icore(self._h, seq, out))
         return [int(x) for x in out]
 
     def synchronize(self):

@@ -2101,16 +2101,17 @@ void be_free(LvbHandle* h) {
   h->be = nullptr;
 }
 
-static int launch_gemm(LvbHandle* h, const GemmArgs& g) {
+static int launch_gemm(LvbHandle* h, const GemmArgs& g, int max_m, int max_n) {
   LvbBackEnd* be = h->be;
-  const int tiles = (be->Dmax + GT - 1) / GT;
   LVB_PROF(h, "be_gemm_kernel");
-  be_gemm_kernel<<<dim3(tiles, tiles, be->S), 256, 0, h->stream>>>(g);
+  be_gemm_kernel<<<dim3((max_n + GT - 1) / GT, (max_m + GT - 1) / GT, be->S), 256, 0, h->stream>>>(g);
   LVB_LAUNCH_CHECK(h);
   return LVB_OK;
 }
 
 // compression + EKF update on the stacked system currently in Hs/rs
+static int be_debug_check(LvbHandle* h, const char* stage);
+#define DBG(name) RC(be_debug_check(h, name))
 static int be_qr(LvbHandle* h, BeView& v) {
   LVB_PROF(h, "be_qr_kernel");
   be_qr_kernel<<<h->be->S, 512, sizeof(double) * h->be->RMAX, h->stream>>>(v);
@@ -2129,14 +2130,15 @@ static int be_update(LvbHandle* h, BeView& v, bool zupt_rows = false) {
   g.B = v.P; g.sB = LD * LD; g.rsB = (int)LD; g.csB = 1;
   g.C = be->Tm; g.sC = (size_t)be->RAWMAX * LD; g.rsC = (int)LD; g.csC = 1;
   g.m_idx = I_R; g.n_idx = I_DIM; g.k_idx = I_DIM; g.alpha = 1.0; g.beta = 0.0; g.diag = 0.0;
-  RC(launch_gemm(h, g));
+  RC(launch_gemm(h, g, be->LDS, be->Dmax));
+  DBG("gemm T=HP");
   // S = T H^T + sigma^2 I
   g.A = be->Tm; g.sA = (size_t)be->RAWMAX * LD; g.rsA = (int)LD; g.csA = 1;
   g.B = be->Hs; g.sB = LD * be->RMAX; g.rsB = be->RMAX; g.csB = 1;
   g.C = be->Sm; g.sC = (size_t)be->LDS * be->LDS; g.rsC = be->LDS; g.csC = 1;
   g.m_idx = I_R; g.n_idx = I_R; g.k_idx = I_DIM; g.alpha = 1.0; g.beta = 0.0; g.diag = v.cfg.sfeat2;
   if (zupt_rows) g.diag_vec = be->dx;
-  RC(launch_gemm(h, g));
+  RC(launch_gemm(h, g, be->LDS, be->LDS));
   g.diag_vec = nullptr;
   const size_t chol_bytes = sizeof(double) * ((size_t)be->Dmax * (be->Dmax + 1) / 2 + 2 * be->Dmax);
   const bool smem_ok = chol_bytes <= 227 * 1024;
@@ -2144,25 +2146,71 @@ static int be_update(LvbHandle* h, BeView& v, bool zupt_rows = false) {
     LVB_PROF(h, "be_chol_kernel");
     be_chol_kernel<<<be->S, 1024, chol_bytes, st>>>(v);
     LVB_LAUNCH_CHECK(h);
+    DBG("be_chol_kernel");
   }
   if (!smem_ok || be->NFmax > 0) {               // systems larger than the packed-smem capacity (hybrid mode, big windows)
     LVB_PROF(h, "be_chol_gmem_kernel");
     be_chol_gmem_kernel<<<be->S, 512, sizeof(double) * be->LDS, st>>>(v, smem_ok ? be->Dmax : 0);
   }
   LVB_LAUNCH_CHECK(h);
+  DBG("be_chol_gmem_kernel");
   BeView vt = v;
   LVB_PROF(h, "be_trsm_kernel");
   be_trsm_kernel<<<dim3((be->Dmax + 63) / 64, be->S), 64, 0, st>>>(vt);
   LVB_LAUNCH_CHECK(h);
+  DBG("be_trsm_kernel");
   LVB_PROF(h, "be_correct_kernel");
   be_correct_kernel<<<be->S, 256, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
+  DBG("be_correct_kernel");
   // P -= Y^T Y
   g.A = be->Tm; g.sA = (size_t)be->RAWMAX * LD; g.rsA = 1; g.csA = (int)LD;
   g.B = be->Tm; g.sB = (size_t)be->RAWMAX * LD; g.rsB = (int)LD; g.csB = 1;
   g.C = v.P; g.sC = LD * LD; g.rsC = (int)LD; g.csC = 1;
   g.m_idx = I_DIM; g.n_idx = I_DIM; g.k_idx = I_R; g.alpha = -1.0; g.beta = 1.0; g.diag = 0.0;
-  RC(launch_gemm(h, g));
+  RC(launch_gemm(h, g, be->Dmax, be->Dmax));
+  DBG("gemm P-=YtY");
+  return LVB_OK;
+}
+
+// LVB_DEBUG_NAN=1: after every back-end launch, pull P / H / T / S of every sequence and report the first non-finite value
+static int be_debug_check(LvbHandle* h, const char* stage) {
+  if (!getenv("LVB_DEBUG_NAN")) return LVB_OK;
+  LvbBackEnd* be = h->be;
+  LVB_CUDA(cudaStreamSynchronize(h->stream));
+  std::vector<int> ic((size_t)be->S * BE_ICORE);
+  LVB_CUDA(cudaMemcpy(ic.data(), be->icore, sizeof(int) * ic.size(), cudaMemcpyDeviceToHost));
+  std::vector<double> P((size_t)be->LD * be->LD);
+  for (int s = 0; s < be->S; ++s) {
+    const int* c = ic.data() + (size_t)s * BE_ICORE;
+    if (!c[I_OK]) continue;
+    LVB_CUDA(cudaMemcpy(P.data(), be->P[0] + (size_t)s * be->LD * be->LD, sizeof(double) * P.size(), cudaMemcpyDeviceToHost));
+    const int d = c[I_DIM];
+    int bad = 0;
+    for (int i = 0; i < d && !bad; ++i) for (int j = 0; j < d; ++j) if (!std::isfinite(P[(size_t)i * be->LD + j])) { bad = 1; fprintf(stderr, "[lvb debug] %s: seq %d P[%d][%d] not finite (d=%d nwin=%d nf=%d R=%d rows=%d nnew=%d)\n", stage, s, i, j, d, c[I_NWIN], c[I_NF], c[I_R], c[I_ROWS], c[I_NNEW]); break; }
+    if (!bad) fprintf(stderr, "[lvb debug] %s: seq %d ok (d=%d nwin=%d nf=%d R=%d rows=%d nnew=%d ncand=%d)\n", stage, s, d, c[I_NWIN], c[I_NF], c[I_R], c[I_ROWS], c[I_NNEW], c[I_NCAND]);
+    // stacked system, T, S, z, dx, Hnew
+    const int r = c[I_R];
+    if (r > 0) {
+      std::vector<double> Hs((size_t)be->LD * be->RMAX), Tm((size_t)r * be->LD), Sm((size_t)be->LDS * be->LDS), zz(be->LDS), dxx(be->LDS), rs(be->RMAX);
+      cudaMemcpy(Hs.data(), be->Hs + (size_t)s * be->LD * be->RMAX, sizeof(double) * Hs.size(), cudaMemcpyDeviceToHost);
+      cudaMemcpy(rs.data(), be->rs + (size_t)s * be->RMAX, sizeof(double) * rs.size(), cudaMemcpyDeviceToHost);
+      cudaMemcpy(Tm.data(), be->Tm + (size_t)s * be->RAWMAX * be->LD, sizeof(double) * Tm.size(), cudaMemcpyDeviceToHost);
+      cudaMemcpy(Sm.data(), be->Sm + (size_t)s * be->LDS * be->LDS, sizeof(double) * Sm.size(), cudaMemcpyDeviceToHost);
+      cudaMemcpy(zz.data(), be->zvec + (size_t)s * be->LDS, sizeof(double) * zz.size(), cudaMemcpyDeviceToHost);
+      cudaMemcpy(dxx.data(), be->dx + (size_t)s * be->LDS, sizeof(double) * dxx.size(), cudaMemcpyDeviceToHost);
+      int bh = -1, bt = -1, bs = -1, bz = -1, bd = -1, br = -1; double mindiag = 1e300;
+      for (int i = 0; i < r; ++i) {
+        for (int j = 0; j < d; ++j) { if (bh < 0 && !std::isfinite(Hs[(size_t)j * be->RMAX + i])) bh = i; if (bt < 0 && !std::isfinite(Tm[(size_t)i * be->LD + j])) bt = i; }
+        for (int j = 0; j <= i; ++j) if (bs < 0 && !std::isfinite(Sm[(size_t)i * be->LDS + j])) bs = i;
+        if (std::isfinite(Sm[(size_t)i * be->LDS + i])) mindiag = std::min(mindiag, Sm[(size_t)i * be->LDS + i]);
+        if (bz < 0 && !std::isfinite(zz[i])) bz = i;
+        if (br < 0 && !std::isfinite(rs[i])) br = i;
+      }
+      for (int j = 0; j < d; ++j) if (bd < 0 && !std::isfinite(dxx[j])) bd = j;
+      fprintf(stderr, "[lvb debug]     seq %d first non-finite row: H %d r %d T %d S %d z %d dx %d ; min diag(S) %.3e\n", s, bh, br, bt, bs, bz, bd, mindiag);
+    }
+  }
   return LVB_OK;
 }
 
@@ -2188,47 +2236,57 @@ static int be_measurement_pass(LvbHandle* h, BeView& v, int mode) {
     LVB_PROF(h, "be_slam_pre_kernel");
     be_slam_pre_kernel<<<be->S, 64, 0, st>>>(v);
     LVB_LAUNCH_CHECK(h);
+    DBG("be_slam_pre_kernel");
     RC(be_remap(h, v));
   }
   if (hybrid && mode == 1) {
     LVB_PROF(h, "be_anchor_kernel");
     be_anchor_kernel<<<be->S, 256, sizeof(double) * be->LD, st>>>(v);
     LVB_LAUNCH_CHECK(h);
+    DBG("be_anchor_kernel");
   }
   LVB_PROF(h, "be_classify_kernel");
   be_classify_kernel<<<dim3((be->T + 3) / 4, be->S), 128, 0, st>>>(v, mode);
   LVB_LAUNCH_CHECK(h);
+  DBG("be_classify_kernel");
   if (hybrid && mode == 0) {
     LVB_PROF(h, "be_slam_decide_kernel");
     be_slam_decide_kernel<<<be->S, 256, 0, st>>>(v);
     LVB_LAUNCH_CHECK(h);
+    DBG("be_slam_decide_kernel");
   }
   LVB_PROF(h, "be_scan_rows_kernel");
   be_scan_rows_kernel<<<be->S, 512, 0, st>>>(v, 0);
   LVB_LAUNCH_CHECK(h);
+  DBG("be_scan_rows_kernel");
   const int fsm_bytes = (int)sizeof(double) * (6 * be->Wcap + 8 + 4 * be->Wcap * be->Wcap + 2 * be->Wcap + (8 + 6 * be->Wcap) / 2 + 4);
   LVB_PROF(h, "be_feature_kernel");
   be_feature_kernel<<<dim3(be->T, be->S), 32, fsm_bytes, st>>>(v, be->Tm);
   LVB_LAUNCH_CHECK(h);
+  DBG("be_feature_kernel");
   if (hybrid && mode == 0) {
     LVB_PROF(h, "be_slam_accept_kernel");
     be_slam_accept_kernel<<<(be->S + 31) / 32, 32, 0, st>>>(v);
     LVB_LAUNCH_CHECK(h);
+    DBG("be_slam_accept_kernel");
   }
   LVB_PROF(h, "be_stack_kernel");
   be_stack_kernel<<<be->S, 512, 0, st>>>(v, 0);
   LVB_LAUNCH_CHECK(h);
+  DBG("be_stack_kernel");
   RC(be_qr(h, v));
   if (hybrid && mode == 0) {
     LVB_PROF(h, "be_stack_kernel");
     be_stack_kernel<<<be->S, 512, 0, st>>>(v, 1);
     LVB_LAUNCH_CHECK(h);
+    DBG("be_stack_kernel");
   }
   RC(be_update(h, v));
   if (hybrid && mode == 0) {
     LVB_PROF(h, "be_slam_grow_kernel");
     be_slam_grow_kernel<<<be->S, 256, sizeof(double) * 64 * be->LD, st>>>(v);
     LVB_LAUNCH_CHECK(h);
+    DBG("be_slam_grow_kernel");
   }
   return LVB_OK;
 }

@@ -377,3 +377,12 @@ extern "C" int lvb_get_stats(LvbHandle* h, unsigned long long* out16) {
   LVB_CUDA(cudaStreamSynchronize(h->stream));
   return LVB_OK;
 }
+
+// debug: raw per-sequence integer state of the back end (be_state.h I_* indices)
+extern "C" int lvb_debug_icore(LvbHandle* h, int seq, int* out32) {
+  if (!h || !out32 || seq < 0 || seq >= h->S) return lvb_set_err(LVB_E_ARG, "lvb_debug_icore: bad argument");
+  LVB_CUDA(cudaSetDevice(h->device));
+  LVB_CUDA(cudaMemcpyAsync(out32, h->be->icore + (size_t)seq * BE_ICORE, sizeof(int) * BE_ICORE, cudaMemcpyDeviceToHost, h->stream));
+  LVB_CUDA(cudaStreamSynchronize(h->stream));
+  return LVB_OK;
+}

@@ -618,6 +618,7 @@ class LarVioOracle:
             ft = self.map_server[fid]
             if ft.in_state:
                 (ekf_ids if sid_now in ft.obs else ekf_lost).append(fid)
+        self.stats["n_ekf_lost"] = len(ekf_lost)
         self._rm_lost_features_cov(ekf_lost)
         self._update_grid_map()
         for fid in sorted(self.map_server.keys()):
@@ -997,6 +998,7 @@ class LarVioOracle:
                     ft.obs_anchor = np.array([p_new[0] / p_new[2], p_new[1] / p_new[2], ft.obs_anchor[2]])
                     self._update_feature_cov_1didp(ft, ft.id_anchor, new_id)
                     ft.id_anchor = new_id
+                    self.stats["anchor_changes"] = self.stats.get("anchor_changes", 0) + 1
                 continue
             if ft.is_initialized and ft.id_anchor in involved:
                 new_id = self._new_anchor_id(ft, involved)

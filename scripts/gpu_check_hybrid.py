@@ -25,6 +25,9 @@ for j in range(NF):
             a = (seqs[s].img_t[j], seqs[s].gt_q[j], seqs[s].gt_p[j], seqs[s].gt_v[j], np.zeros(3), np.zeros(3))
             bes[s].set_initial_state(*a); b.set_initial_state(s, *a); inited[s] = True
     imgs = np.stack([seqs[s].images[j] for s in range(S)]); t_img = np.array([seqs[s].img_t[j] for s in range(S)])
+    if j >= int(os.environ.get('DBG_FROM', '10000')):
+        os.environ['LVB_DEBUG_NAN'] = '1'
+        print('--- frame', j, flush=True)
     try:
         ok = b.step(imgs, t_img, feed.buf, feed.n)
     except Exception as e:
@@ -37,9 +40,10 @@ for j in range(NF):
         same = P.shape == bes[s].P.shape
         rel = float(np.linalg.norm(P - bes[s].P) / np.linalg.norm(bes[s].P)) if same else -1
         worst = max(worst, dp)
-        if j > 98 and (j % 2 == 0) and s == 0 or not same or dp > 1e-7:
+        if j > 98 and (j % 2 == 0) or not same or not (dp <= 1e-7):
             print('frame', j, 'seq', s, 'dp %.2e' % dp, 'Prel %.2e' % rel, 'dims', P.shape[0], bes[s].P.shape[0], 'nslam', len(bes[s].feature_states),
-                  {a: c for a, c in bes[s].stats.items() if a in ('n_ekf_new', 'n_ekf', 'n_msckf_features')}, flush=True)
-        if not same or dp > 1e-3:
+                  {a: c for a, c in bes[s].stats.items() if a in ('n_ekf_new', 'n_ekf', 'n_msckf_features', 'n_ekf_lost', 'anchor_changes', 'prune_used')},
+                  'icore', b.debug_icore(s)[:28], 'nanP', int(np.isnan(P).sum()), flush=True)
+        if not same or not (dp <= 1e-3):
             print('DIVERGED'); sys.exit(0)
 print(json.dumps(dict(worst_dp=worst)))
