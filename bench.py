@@ -49,6 +49,11 @@ def _gen_one(a):
     seq_index, n_frames = a
     import cv2
     cv2.setNumThreads(1)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)          # one BLAS thread per generator process (one process per core)
+    except Exception:
+        pass
     return synth.make_sequence(_GEN_CFG, seq_index, n_frames)
 
 
@@ -130,39 +135,43 @@ class CpuArm:
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock / throttle-reason samples DURING the timed region: an NVML polling thread (5 ms period; the timed
+    region of a default run is a few hundred ms, too short for an `nvidia-smi -lms` child to even start)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, gpu_index, period=0.005):
+        self.sm = []; self.bits = 0; self.mx = None; self.ok = False; self.stop_flag = False; self.period = period
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
         except Exception:
-            self.p = None
+            return
+        self.th = threading.Thread(target=self._loop, daemon=True)
+        self.th.start()
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
-        if self.p is None:
+        if not self.ok:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=3)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [l.strip().split(",") for l in open(self.f.name) if l.strip()]
-        os.unlink(self.f.name)
-        sm = []; mx = []; reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for i, nm in enumerate(names):
-                    if r[3 + i].strip().lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                pass
-        if sm:
-            out = dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        self.stop_flag = True
+        self.th.join(timeout=2)
+        if self.sm:
+            out = dict(sm_mhz=float(np.median(self.sm)), sm_min_mhz=float(min(self.sm)), sm_max_mhz=self.mx,
+                       reasons=sorted(v for k, v in self.REASONS.items() if self.bits & k), samples=len(self.sm))
         return out
 
 
@@ -191,7 +200,7 @@ def kernel_models(S_sub, stats, n_frames, n_sub):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=120)
     ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seqs", type=int, default=64, help="sequences per GPU (BASELINE configs[2]: 64)")
@@ -346,9 +355,9 @@ def main():
     # ---- device-resident pass: `value`
     dev_frames = pinned.to("cuda", non_blocking=False)
     st = fresh_state()
-    sampler = ClockSampler(local_rank) if rank == 0 else None      # samples warm-up + timed region (100 ms period)
     run_pass("dev", 0, Wm, st)
     barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None      # NVML samples over the timed region (5 ms period)
     l0 = launches_total()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(); t0 = time.perf_counter()

@@ -131,6 +131,11 @@ int lvb_get_state(LvbHandle* h, int seq, double* t, double* q_xyzw, double* p, d
 int lvb_get_states(LvbHandle* h, double* out);
 /* getSwPoses: window poses (IMU frame) [n][7] = q(4) p(3); returns count in *n. */
 int lvb_get_window(LvbHandle* h, int seq, double* qp, int cap, int* n);
+/* Online-calibrated quantities of one sequence (StateServer / IMUState members the reference logs, larvio.h:99-142,
+ * imu_state.h:70-77): R_imu_cam0[9] row-major, t_cam0_imu[3], td, and the IMU intrinsics Tg[9], As[9], Ma[9]
+ * (identity / zero / identity unless calib_imu_instrinsic, larvio.cpp:127-155, 3803-3847). */
+int lvb_get_calibration(LvbHandle* h, int seq, double* R_imu_cam9, double* t_cam_imu3, double* td,
+                        double* Tg9, double* As9, double* Ma9);
 /* Full covariance of one sequence, row-major dim x dim (dim returned). */
 int lvb_get_covariance(LvbHandle* h, int seq, double* P, int cap_dim, int* dim);
 

@@ -69,7 +69,7 @@ _lib.lvb_debug_icore.restype = C.c_int
 _lib.lvb_profile_get.argtypes = [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
 for _name in ("lvbk_pyramid", "lvbk_lk", "lvbk_orb", "lvbk_detect", "lvbk_undistort", "lvbk_ransac",
               "lvb_process_images", "lvb_process_features", "lvb_step", "lvb_set_initial_state",
-              "lvb_get_state", "lvb_get_states", "lvb_get_window", "lvb_get_covariance"):
+              "lvb_get_state", "lvb_get_states", "lvb_get_window", "lvb_get_covariance", "lvb_get_calibration"):
     if hasattr(_lib, _name):
         getattr(_lib, _name).restype = C.c_int
 
@@ -77,7 +77,7 @@ EXPORTED_SYMBOLS = [
     "lvb_parse_config", "lvb_create", "lvb_create_from_file", "lvb_destroy", "lvb_last_error",
     "lvb_feature_capacity", "lvb_n_seq", "lvb_process_images", "lvb_process_features", "lvb_step",
     "lvb_synchronize", "lvb_set_initial_state", "lvb_get_state", "lvb_get_states", "lvb_get_window",
-    "lvb_get_covariance", "lvbk_pyramid", "lvbk_lk", "lvbk_orb", "lvbk_detect", "lvbk_undistort",
+    "lvb_get_covariance", "lvb_get_calibration", "lvbk_pyramid", "lvbk_lk", "lvbk_orb", "lvbk_detect", "lvbk_undistort",
     "lvbk_ransac", "lvb_launch_count", "lvb_profile_enable", "lvb_profile_reset", "lvb_profile_get", "lvb_get_stats", "lvb_debug_icore",
 ]
 
@@ -263,6 +263,11 @@ class Batch:
         Pp = np.zeros((6, 6)); Pv = np.zeros((3, 3))
         _check(_lib.lvb_get_state(self._h, seq, C.byref(t), _p(q), _p(p), _p(v), _p(bg), _p(ba), _p(Pp), _p(Pv)))
         return dict(t=t.value, q=q, p=p, v=v, bg=bg, ba=ba, P_pose=Pp, P_vel=Pv)
+
+    def get_calibration(self, seq):
+        R = np.zeros((3, 3)); t = np.zeros(3); td = C.c_double(); Tg = np.zeros((3, 3)); As = np.zeros((3, 3)); Ma = np.zeros((3, 3))
+        _check(_lib.lvb_get_calibration(self._h, seq, _p(R), _p(t), C.byref(td), _p(Tg), _p(As), _p(Ma)))
+        return dict(R_imu_cam0=R, t_cam0_imu=t, td=td.value, Tg=Tg, As=As, Ma=Ma)
 
     def get_states(self):
         out = np.zeros((self.S, 17))

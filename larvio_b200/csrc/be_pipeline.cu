@@ -41,15 +41,23 @@ struct BeView {
   double* Pn;        // the other buffer
 };
 
+#define LEGD (v.be.LEG)
 __device__ __forceinline__ double* core_of(const BeView& v, int s) { return v.be.core + (size_t)s * BE_CORE; }
 __device__ __forceinline__ int* icore_of(const BeView& v, int s) { return v.be.icore + (size_t)s * BE_ICORE; }
 __device__ __forceinline__ double* win_of(const BeView& v, int s, int slot) { return v.be.win + ((size_t)s * v.be.Wcap + slot) * BE_WIN; }
 __device__ __forceinline__ double* P_of(const BeView& v, int s) { return v.P + (size_t)s * v.be.LD * v.be.LD; }
 
 // ====================================================================== propagate
+// selector matrices of calPhi's IMU-intrinsic blocks (larvio.cpp:3534-3629): lower / diagonal / upper placement of a vector
+__device__ __forceinline__ M3 imu_selector(int kind, V3 x) {
+  M3 r; for (int i = 0; i < 9; ++i) r.m[i] = 0.0;
+  if (kind == 0) { r.m[3] = x.x; r.m[7] = x.x; r.m[8] = x.y; }
+  else if (kind == 1) { r.m[0] = x.x; r.m[4] = x.y; r.m[8] = x.z; }
+  else { r.m[0] = x.y; r.m[1] = x.z; r.m[5] = x.z; }
+  return r;
+}
 __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
-  __shared__ double Phi[BE_LEG][BE_LEG + 1], PLL[BE_LEG][BE_LEG + 1], Tmp[BE_LEG][BE_LEG + 1], PhiTot[BE_LEG][BE_LEG + 1];
-  __shared__ double Ddiag[BE_LEG];
+  extern __shared__ double psm[];                      // Phi, PLL, Tmp, PhiTot: [L][L+1] each; Ddiag [L]
   __shared__ int s_ok, s_action, s_used;
   __shared__ double s_dtime, s_dt;
   const int s = blockIdx.x, tid = threadIdx.x;
@@ -57,7 +65,13 @@ __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
   int* ic = icore_of(v, s);
   const LvbImu* imu = v.be.imu + (size_t)s * v.be.imu_cap;
   const int n_imu = v.be.n_imu[s];
-  const int L = BE_LEG, LD = v.be.LD;
+  const int L = LEGD, LD = v.be.LD, LP = L + 1;
+  double* const Phi_ = psm; double* const PLL_ = psm + L * LP; double* const Tmp_ = psm + 2 * L * LP; double* const PhiTot_ = psm + 3 * L * LP;
+  double* const Ddiag = psm + 4 * L * LP;
+#define Phi(r, c) Phi_[(r) * LP + (c)]
+#define PLL(r, c) PLL_[(r) * LP + (c)]
+#define Tmp(r, c) Tmp_[(r) * LP + (c)]
+#define PhiTot(r, c) PhiTot_[(r) * LP + (c)]
   double* P = P_of(v, s);
   if (tid == 0) {
     int ok = v.msg_valid[s] != 0;
@@ -79,8 +93,8 @@ __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
   if (!s_ok) return;
   for (int i = tid; i < L * L; i += blockDim.x) {
     const int r = i / L, c = i - r * L;
-    PLL[r][c] = P[(size_t)r * LD + c];
-    PhiTot[r][c] = (r == c) ? 1.0 : 0.0;
+    PLL(r, c) = P[(size_t)r * LD + c];
+    PhiTot(r, c) = (r == c) ? 1.0 : 0.0;
   }
   __syncthreads();
   const double time_bound = v.msg_t[s] + core[C_TD];
@@ -95,10 +109,13 @@ __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
         const V3 m_gyro = v3(imu[k].gyro[0], imu[k].gyro[1], imu[k].gyro[2]);
         const V3 m_acc = v3(imu[k].acc[0], imu[k].acc[1], imu[k].acc[2]);
         if (!ic[I_HAVE_OLD]) { st3(core + C_GYRO_OLD, m_gyro); st3(core + C_ACC_OLD, m_acc); ic[I_HAVE_OLD] = 1; }
-        // ---- processModel (:520-578) with Ma = Tg = I, As = 0
+        // ---- processModel (:520-578): acc = Ma f, w = m_gyro - As acc - bg, gyro = Tg w
         const V3 bg = ld3(core + C_BG), ba = ld3(core + C_BA);
-        const V3 acc = m_acc - ba, gyro = m_gyro - bg;
-        const V3 gyro_old = ld3(core + C_GYRO_OLD) - bg;
+        const M3 Tg = m3_load(core + C_TG), As = m3_load(core + C_AS), Ma = m3_load(core + C_MA);
+        const V3 f = m_acc - ba, acc = m3_vec(Ma, f);
+        const V3 w = m_gyro - m3_vec(As, acc) - bg, gyro = m3_vec(Tg, w);
+        const V3 f_old = ld3(core + C_ACC_OLD) - ba, acc_old = m3_vec(Ma, f_old);
+        const V3 w_old = ld3(core + C_GYRO_OLD) - m3_vec(As, acc_old) - bg, gyro_old = m3_vec(Tg, w_old);
         const double dtime = t - core[C_TIME];
         s_dtime = dtime;
         // ---- predictNewState (:581-649)
@@ -147,29 +164,68 @@ __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
         V3 vk, pk, vk1, pk1;
         if (ic[I_FEJ]) { vk = ld3(core + C_FOLD_V); pk = ld3(core + C_FOLD_P); vk1 = ld3(core + C_FNOW_V); pk1 = ld3(core + C_FNOW_P); }
         else { vk = vel; pk = pos; vk1 = vnew; pk1 = pnew; }
-        for (int r = 0; r < L; ++r) for (int c = 0; c < L; ++c) Phi[r][c] = (r == c) ? 1.0 : 0.0;
+        for (int r = 0; r < L; ++r) for (int c = 0; c < L; ++c) Phi(r, c) = (r == c) ? 1.0 : 0.0;
         const M3 I3 = m3_identity();
         const M3 twoIAh = m3_add(m3_scale(I3, 2.0), Ah);
-        const M3 Pqbg = m3_scale(m3_mul(C, twoIAh), -0.5 * dtime);
+        const M3 TA = m3_mul(Tg, As), TAM = m3_mul(TA, Ma);
+        const M3 CtA = m3_scale(m3_mul(C, twoIAh), 0.5 * dtime);       // 0.5*C*(2I+Ah)*dtime
+        const M3 Pqbg = m3_scale(m3_mul(CtA, Tg), -1.0);
+        const M3 Pqba = m3_mul(CtA, TAM);
         const M3 Pvq = m3_scale(skew(vk1 - vk - g * dtime), -1.0);
         const M3 Pvbg = m3_add(m3_mul(skew(pk - pk1 + vk1 * dtime - g * (0.5 * dtime * dtime)), C),
                                m3_mul(m3_mul(skew(pk * 0.5 - pk1 * 0.5 + vk1 * (0.5 * dtime) - g * (dtime * dtime / 6)), C), Ah));
-        const M3 Pvba = m3_scale(m3_mul(C, twoIAh), -0.5 * dtime);
+        const M3 Pvba = m3_sub(m3_scale(m3_mul(CtA, Ma), -1.0), m3_mul(Pvbg, TAM));
         const M3 Ppq = m3_scale(skew(pk1 - pk - vk * dtime - g * (0.5 * dtime * dtime)), -1.0);
         const M3 Ppbg = m3_add(m3_scale(m3_mul(skew(g), C), -dtime * dtime * dtime / 6),
                                m3_scale(m3_mul(m3_mul(skew(pk1 - pk - g * (dtime * dtime / 6)), C), Ah), dtime / 4));
-        const M3 Ppba = m3_scale(m3_mul(C, m3_add(m3_scale(I3, 3.0), Ah)), -dtime * dtime / 6);
+        const M3 Ppba = m3_sub(m3_mul(m3_scale(m3_mul(C, m3_add(m3_scale(I3, 3.0), Ah)), -dtime * dtime / 6), Ma), m3_mul(Ppbg, TAM));
         for (int r = 0; r < 3; ++r)
           for (int c = 0; c < 3; ++c) {
-            Phi[r][9 + c] = Pqbg.m[r * 3 + c];
-            Phi[3 + r][c] = Pvq.m[r * 3 + c];
-            Phi[3 + r][9 + c] = Pvbg.m[r * 3 + c];
-            Phi[3 + r][12 + c] = Pvba.m[r * 3 + c];
-            Phi[6 + r][c] = Ppq.m[r * 3 + c];
-            Phi[6 + r][3 + c] = (r == c) ? dtime : 0.0;
-            Phi[6 + r][9 + c] = Ppbg.m[r * 3 + c];
-            Phi[6 + r][12 + c] = Ppba.m[r * 3 + c];
+            Phi(r, 9 + c) = Pqbg.m[r * 3 + c];
+            Phi(r, 12 + c) = Pqba.m[r * 3 + c];
+            Phi(3 + r, c) = Pvq.m[r * 3 + c];
+            Phi(3 + r, 9 + c) = Pvbg.m[r * 3 + c];
+            Phi(3 + r, 12 + c) = Pvba.m[r * 3 + c];
+            Phi(6 + r, c) = Ppq.m[r * 3 + c];
+            Phi(6 + r, 3 + c) = (r == c) ? dtime : 0.0;
+            Phi(6 + r, 9 + c) = Ppbg.m[r * 3 + c];
+            Phi(6 + r, 12 + c) = Ppba.m[r * 3 + c];
           }
+        if (L > 22) {
+          // ---- IMU-intrinsic columns (:3532-3797): 8 groups of 3 columns; selectors Lo/Di/Up place the components of
+          // (w | acc | f) sampled at k, k+1/2, k+1; Simpson weights for q, the reference's RK4 weights for v and p
+          const V3 f_mid = (f + f_old) * 0.5, acc_mid = (acc + acc_old) * 0.5;
+          const V3 w_mid = (w_old + w) * 0.5 + cross(w_old, w) * (dtime / 12);
+          const M3 R_mid = m3_add(I3, m3_scale(Ah, 0.5)), R_kp1 = m3_add(I3, Ah);
+          const M3 S_mid = m3_scale(skew(m3_vec(R_mid, acc_mid)), dtime * 0.5), S_kp1 = skew(m3_vec(R_kp1, acc));
+          for (int gi = 0; gi < 8; ++gi) {
+            const int kind = (gi < 6) ? gi % 3 : gi - 6;                 // 0 Lo, 1 Di, 2 Up
+            const V3 xk = gi < 3 ? w_old : (gi < 6 ? acc_old : f_old);
+            const V3 xh = gi < 3 ? w_mid : (gi < 6 ? acc_mid : f_mid);
+            const V3 xp = gi < 3 ? w : (gi < 6 ? acc : f);
+            const M3 Lf = gi < 3 ? I3 : (gi < 6 ? Tg : TA);
+            const double sgn = gi < 3 ? 1.0 : -1.0;
+            const bool direct = gi >= 6;
+            const M3 sk = imu_selector(kind, xk), sh = imu_selector(kind, xh), sp = imu_selector(kind, xp);
+            const M3 kq1 = m3_mul(Lf, sk), kq2 = m3_mul(R_mid, m3_mul(Lf, sh)), kq4 = m3_mul(R_kp1, m3_mul(Lf, sp));
+            const M3 Rq = m3_scale(m3_add(m3_add(kq1, m3_scale(kq2, 4.0)), kq4), dtime / 6);
+            M3 kv1, kv2, kv3, kv4;
+            if (!direct) {
+              kv1 = m3_scale(I3, 0.0); kv2 = m3_mul(S_mid, kq1); kv3 = m3_mul(S_mid, kq2); kv4 = m3_mul(S_kp1, Rq);
+            } else {
+              const M3 Rh = m3_mul(R_mid, sh);
+              kv1 = sk; kv2 = m3_add(Rh, m3_mul(S_mid, kq1)); kv3 = m3_add(Rh, m3_mul(S_mid, kq2));
+              kv4 = m3_add(m3_mul(R_kp1, sp), m3_mul(S_kp1, Rq));
+            }
+            const M3 fR = m3_scale(m3_add(m3_add(kv1, m3_scale(m3_add(kv2, kv3), 2.0)), kv4), dtime / 6);
+            const double vs = direct ? 1.0 : -sgn;
+            const M3 kp = m3_scale(m3_add(m3_scale(m3_add(kv1, kv2), dtime), fR), dtime / 6);   // kp1=0, kp2=dt kv1/2, kp3=dt kv2/2, kp4=fR
+            const M3 Bq = m3_scale(m3_mul(C, Rq), sgn), Bv = m3_scale(m3_mul(C, fR), vs), Bp = m3_scale(m3_mul(C, kp), vs);
+            const int col = 22 + 3 * gi;
+            for (int r = 0; r < 3; ++r)
+              for (int c = 0; c < 3; ++c) { Phi(r, col + c) = Bq.m[r * 3 + c]; Phi(3 + r, col + c) = Bv.m[r * 3 + c]; Phi(6 + r, col + c) = Bp.m[r * 3 + c]; }
+          }
+        }
         core[C_TIME] = t;
         st3(core + C_GYRO_OLD, m_gyro); st3(core + C_ACC_OLD, m_acc);
       }
@@ -183,42 +239,46 @@ __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
     for (int i = tid; i < L * L; i += blockDim.x) {
       const int r = i / L, c = i - r * L;
       double acc = 0.0;
-      for (int k2 = 0; k2 < L; ++k2) acc += Phi[r][k2] * (PLL[k2][c] + (k2 == c ? Ddiag[c] * dtime : 0.0));
-      Tmp[r][c] = acc;
+      for (int k2 = 0; k2 < L; ++k2) acc += Phi(r, k2) * (PLL(k2, c) + (k2 == c ? Ddiag[c] * dtime : 0.0));
+      Tmp(r, c) = acc;
     }
     __syncthreads();
     for (int i = tid; i < L * L; i += blockDim.x) {
       const int r = i / L, c = i - r * L;
       double acc = 0.0;
-      for (int k2 = 0; k2 < L; ++k2) acc += Tmp[r][k2] * Phi[c][k2];
-      PLL[r][c] = acc;
+      for (int k2 = 0; k2 < L; ++k2) acc += Tmp(r, k2) * Phi(c, k2);
+      PLL(r, c) = acc;
     }
     __syncthreads();
     for (int i = tid; i < L * L; i += blockDim.x) {
       const int r = i / L, c = i - r * L;
       double acc = 0.0;
-      for (int k2 = 0; k2 < L; ++k2) acc += Phi[r][k2] * PhiTot[k2][c];
-      Tmp[r][c] = acc;
-      if (r < c) { const double m = 0.5 * (PLL[r][c] + PLL[c][r]); PLL[r][c] = m; PLL[c][r] = m; }
+      for (int k2 = 0; k2 < L; ++k2) acc += Phi(r, k2) * PhiTot(k2, c);
+      Tmp(r, c) = acc;
+      if (r < c) { const double m = 0.5 * (PLL(r, c) + PLL(c, r)); PLL(r, c) = m; PLL(c, r) = m; }
     }
     __syncthreads();
-    for (int i = tid; i < L * L; i += blockDim.x) { const int r = i / L, c = i - r * L; PhiTot[r][c] = Tmp[r][c]; }
+    for (int i = tid; i < L * L; i += blockDim.x) { const int r = i / L, c = i - r * L; PhiTot(r, c) = Tmp(r, c); }
     __syncthreads();
   }
   __syncthreads();
   // write back P_LL, apply the composed transition to the cross terms
   const int d = ic[I_DIM];
-  for (int i = tid; i < L * L; i += blockDim.x) { const int r = i / L, c = i - r * L; P[(size_t)r * LD + c] = PLL[r][c]; }
+  for (int i = tid; i < L * L; i += blockDim.x) { const int r = i / L, c = i - r * L; P[(size_t)r * LD + c] = PLL(r, c); }
   for (int c = L + tid; c < d; c += blockDim.x) {
-    double col[BE_LEG];
+    double col[BE_LEG_MAX];
     for (int r = 0; r < L; ++r) col[r] = P[(size_t)r * LD + c];
     for (int r = 0; r < L; ++r) {
       double acc = 0.0;
-      for (int k2 = 0; k2 < L; ++k2) acc += PhiTot[r][k2] * col[k2];
+      for (int k2 = 0; k2 < L; ++k2) acc += PhiTot(r, k2) * col[k2];
       P[(size_t)r * LD + c] = acc;
       P[(size_t)c * LD + r] = acc;
     }
   }
+#undef Phi
+#undef PLL
+#undef Tmp
+#undef PhiTot
   if (tid == 0) {
     ic[I_ID] = ic[I_NEXT_ID]; ic[I_NEXT_ID] += 1;     // :505
     core[C_DT] = s_dt;                                 // :508
@@ -816,20 +876,20 @@ __global__ void __launch_bounds__(32) be_feature_kernel(BeView v, double* Traw) 
     const int as = v.be.ft_anchor[fi];
     int fidx = -1;
     const int* fs = v.be.fs_slot + (size_t)s * 64;
-    for (int i = 0; i < ic[I_NF]; ++i) if (fs[i] == slot) fidx = BE_LEG + 6 * n_win + i;
+    for (int i = 0; i < ic[I_NF]; ++i) if (fs[i] == slot) fidx = LEGD + 6 * n_win + i;
     if (lane == 0) {
       Jac1d J;
       meas_jac_1didp(v, s, fi, cur, fej, J);
       for (int a = 0; a < 2; ++a) {
         double* row = H + (size_t)a * LD;
-        for (int c = 0; c < 6; ++c) { row[BE_LEG + 6 * as + c] = J.ha[a][c]; row[15 + c] = J.he[a][c]; }
-        for (int c = 0; c < 6; ++c) row[BE_LEG + 6 * cur + c] = J.hx[a][c];
+        for (int c = 0; c < 6; ++c) { row[LEGD + 6 * as + c] = J.ha[a][c]; row[15 + c] = J.he[a][c]; }
+        for (int c = 0; c < 6; ++c) row[LEGD + 6 * cur + c] = J.hx[a][c];
         row[fidx] = J.hf[a];
         if (v.cfg.estimate_td) row[21] = obs[(size_t)cur * 4 + 2 + a];
         rr[a] = J.r[a];
       }
       for (int j = 0; j < 7; ++j) nzl[j] = 15 + j;
-      for (int c = 0; c < 6; ++c) { nzl[7 + c] = BE_LEG + 6 * as + c; nzl[13 + c] = BE_LEG + 6 * cur + c; }
+      for (int c = 0; c < 6; ++c) { nzl[7 + c] = LEGD + 6 * as + c; nzl[13 + c] = LEGD + 6 * cur + c; }
       nzl[19] = fidx;
     }
     __syncwarp();
@@ -857,7 +917,7 @@ __global__ void __launch_bounds__(32) be_feature_kernel(BeView v, double* Traw) 
     const M3 E1 = m3_sub(m3_mul(A1, R_b2w), m3_mul(R_b2c, skew(t_c_b)));   // dpc_dxe.leftCols(3)
     double* r0 = H + (size_t)(2 * k) * LD;
     double* r1 = r0 + LD;
-    const int cp = BE_LEG + 6 * ws;
+    const int cp = LEGD + 6 * ws;
     for (int c = 0; c < 3; ++c) {
       double hx0 = 0, hx1 = 0, hp0 = 0, hp1 = 0, he0 = 0, he1 = 0, ht0 = 0, ht1 = 0, hf0 = 0, hf1 = 0;
       for (int q = 0; q < 3; ++q) {
@@ -877,7 +937,7 @@ __global__ void __launch_bounds__(32) be_feature_kernel(BeView v, double* Traw) 
   }
   // nonzero column list: 15..21 and the pose blocks of the used window slots
   const int nz = 7 + 6 * m;
-  for (int j = lane; j < nz; j += 32) nzl[j] = (j < 7) ? 15 + j : BE_LEG + 6 * nth_set_bit(um, (j - 7) / 6) + ((j - 7) % 6);
+  for (int j = lane; j < nz; j += 32) nzl[j] = (j < 7) ? 15 + j : LEGD + 6 * nth_set_bit(um, (j - 7) / 6) + ((j - 7) % 6);
   __syncwarp();
   // ---- three Householder reflections on H_f, applied to the nonzero columns of H and to r
   for (int k = 0; k < 3; ++k) {
@@ -939,8 +999,8 @@ __global__ void __launch_bounds__(32) be_feature_kernel(BeView v, double* Traw) 
     meas_jac_1didp(v, s, fi, ws, fej, J);
     for (int a = 0; a < 2; ++a) {
       double* row = H2 + (size_t)(2 * k + a) * LD;
-      for (int c = 0; c < 6; ++c) { row[BE_LEG + 6 * as + c] = J.ha[a][c]; row[15 + c] = J.he[a][c]; }
-      for (int c = 0; c < 6; ++c) row[BE_LEG + 6 * ws + c] = J.hx[a][c];
+      for (int c = 0; c < 6; ++c) { row[LEGD + 6 * as + c] = J.ha[a][c]; row[15 + c] = J.he[a][c]; }
+      for (int c = 0; c < 6; ++c) row[LEGD + 6 * ws + c] = J.hx[a][c];
       if (v.cfg.estimate_td) row[21] = obs[(size_t)ws * 4 + 2 + a];
       hf[2 * k + a] = J.hf[a];
       r2[2 * k + a] = J.r[a];
@@ -1462,6 +1522,14 @@ __global__ void __launch_bounds__(256) be_correct_kernel(BeView v) {
     m3_store(core + C_RIC, Rn);
     for (int i = 0; i < 3; ++i) core[C_TCI + i] += dx[18 + i];
     core[C_TD] += dx[21];
+    if (LEGD > 22) {            // T1 T2 T3 A1 A2 A3 M1 M2 += dx(22:46), then updateImuMx (:1497-1507, 3803-3847)
+      const int lo[3] = {3, 6, 7}, di[3] = {0, 4, 8}, up[3] = {1, 2, 5};      // (1,0)(2,0)(2,1) / diagonal / (0,1)(0,2)(1,2)
+      for (int i = 0; i < 3; ++i) {
+        core[C_TG + lo[i]] += dx[22 + i]; core[C_TG + di[i]] += dx[25 + i]; core[C_TG + up[i]] += dx[28 + i];
+        core[C_AS + lo[i]] += dx[31 + i]; core[C_AS + di[i]] += dx[34 + i]; core[C_AS + up[i]] += dx[37 + i];
+        core[C_MA + lo[i]] += dx[40 + i]; core[C_MA + di[i]] += dx[43 + i];
+      }
+    }
     ic[I_UPDATES] += 1;
     if (v.be.stats) {
       atomicAdd(&v.be.stats[4], 1ull); atomicAdd(&v.be.stats[5], (unsigned long long)r);
@@ -1474,7 +1542,7 @@ __global__ void __launch_bounds__(256) be_correct_kernel(BeView v) {
   const V3 t_c_b = ld3(core + C_TCI);
   for (int i = tid; i < n_win; i += blockDim.x) {
     double* w = win_of(v, s, i);
-    const double* da = dx + BE_LEG + 6 * i;
+    const double* da = dx + LEGD + 6 * i;
     double dq[4], qn[4];
     small_angle_quat(v3(da[0], da[1], da[2]), dq);
     quat_mul(dq, w + W_Q, qn);
@@ -1487,7 +1555,7 @@ __global__ void __launch_bounds__(256) be_correct_kernel(BeView v) {
   __syncthreads();
   // inverse depth of the SLAM features already in the state and their world positions (:1536-1575, :1752-1801)
   const int nf = ic[I_NF];
-  const int base = BE_LEG + 6 * n_win;
+  const int base = LEGD + 6 * n_win;
   for (int i = tid; i < nf; i += blockDim.x) {
     const size_t fi = (size_t)s * v.be.T + v.be.fs_slot[(size_t)s * 64 + i];
     const double inv = v.be.ft_inv[fi] + dx[base + i];
@@ -1522,7 +1590,7 @@ __global__ void __launch_bounds__(256) be_zupt_build_kernel(BeView v) {
   for (int e = tid; e < 9 * d; e += blockDim.x) { const int col = e / 9, row = e - col * 9; Hs[(size_t)col * RMAX + row] = 0.0; }
   __syncthreads();
   if (tid < 3) {
-    const int L = BE_LEG;
+    const int L = LEGD;
     Hs[(size_t)(3 + tid) * RMAX + tid] = 1.0;                                   // zupt_v
     Hs[(size_t)(L + 6 * N - 3 + tid) * RMAX + 3 + tid] = 1.0;                   // zupt_p current
     Hs[(size_t)(L + 6 * N - 9 + tid) * RMAX + 3 + tid] = -1.0;                  // zupt_p previous
@@ -1659,7 +1727,7 @@ __global__ void __launch_bounds__(256) be_anchor_kernel(BeView v) {
   for (int it = 0; it < n; ++it) {
     const int fcnt = s_list[it];
     const size_t fi = (size_t)s * T + fs[fcnt];
-    const int fidx = BE_LEG + 6 * n_win + fcnt;
+    const int fidx = LEGD + 6 * n_win + fcnt;
     if (tid == 0) {
       const int os = v.be.ft_anchor[fi];
       const int ns = new_anchor_slot(v, s, fi, n_win, r0, r1);
@@ -1697,10 +1765,10 @@ __global__ void __launch_bounds__(256) be_anchor_kernel(BeView v) {
       const M3 Jep = m3_mul(R_b2c, m3_sub(Rno, m3_identity()));
       int k = 0;
       Jc[k] = fidx; Jv[k++] = Jr * J_d * (-1.0 / (inv_old * inv_old));
-      for (int c = 0; c < 3; ++c) { Jc[k] = BE_LEG + 6 * os + c; Jv[k++] = Jr * Jto.m[6 + c]; }
-      for (int c = 0; c < 3; ++c) { Jc[k] = BE_LEG + 6 * os + 3 + c; Jv[k++] = Jr * R_w2c_new.m[6 + c]; }
-      for (int c = 0; c < 3; ++c) { Jc[k] = BE_LEG + 6 * ns + c; Jv[k++] = Jr * Jtn.m[6 + c]; }
-      for (int c = 0; c < 3; ++c) { Jc[k] = BE_LEG + 6 * ns + 3 + c; Jv[k++] = Jr * -R_w2c_new.m[6 + c]; }
+      for (int c = 0; c < 3; ++c) { Jc[k] = LEGD + 6 * os + c; Jv[k++] = Jr * Jto.m[6 + c]; }
+      for (int c = 0; c < 3; ++c) { Jc[k] = LEGD + 6 * os + 3 + c; Jv[k++] = Jr * R_w2c_new.m[6 + c]; }
+      for (int c = 0; c < 3; ++c) { Jc[k] = LEGD + 6 * ns + c; Jv[k++] = Jr * Jtn.m[6 + c]; }
+      for (int c = 0; c < 3; ++c) { Jc[k] = LEGD + 6 * ns + 3 + c; Jv[k++] = Jr * -R_w2c_new.m[6 + c]; }
       for (int c = 0; c < 3; ++c) { Jc[k] = 15 + c; Jv[k++] = Jr * Jet.m[6 + c]; }
       for (int c = 0; c < 3; ++c) { Jc[k] = 18 + c; Jv[k++] = Jr * Jep.m[6 + c]; }
       v.be.ft_anchor[fi] = ns;
@@ -1772,7 +1840,7 @@ __global__ void __launch_bounds__(256) be_prune_cov_gather_kernel(BeView v) {
   const int nrm = ic[I_NRM];
   const int nd = d - 6 * nrm;
   if (row >= nd) return;
-  const int a0 = BE_LEG + 6 * ic[I_RM0], a1 = (nrm > 1) ? BE_LEG + 6 * ic[I_RM1] : (1 << 30);
+  const int a0 = LEGD + 6 * ic[I_RM0], a1 = (nrm > 1) ? LEGD + 6 * ic[I_RM1] : (1 << 30);
   auto src = [&](int i) { int x = i; if (x >= a0) x += 6; if (x >= a1) x += 6; return x; };
   const double* P = P_of(v, s);
   double* Sd = v.be.Sm + (size_t)s * v.be.LDS * v.be.LDS;
@@ -1975,7 +2043,6 @@ static int bdalloc(LvbHandle* h, T** p, size_t count) {
 #define BPIN(ptr, T, n) do { void* q_ = nullptr; LVB_CUDA(cudaHostAlloc(&q_, sizeof(T) * (size_t)(n), cudaHostAllocDefault)); memset(q_, 0, sizeof(T) * (size_t)(n)); ptr = (T*)q_; } while (0)
 
 static const char* be_unsupported_reason(const LvbConfig& c) {
-  if (c.calib_imu_instrinsic) return "calib_imu_instrinsic: 1 (IMU-intrinsic calibration, LEG_DIM 46) is not built yet";
   if (c.max_features_in_one_grid > 0 && c.aug_grid_rows * c.aug_grid_cols != 0) {
     if (c.feature_idp_dim != 1) return "feature_idp_dim: 3 (3-D inverse-depth SLAM features) is not built yet; use 1";
     if (c.use_schmidt) return "use_schmidt: 1 (Schmidt nuisance states) is not built yet";
@@ -1995,22 +2062,24 @@ __global__ void be_init_kernel(BeView v, double c_ori, double c_vel, double c_po
   for (int i = 0; i < BE_ICORE; ++i) ic[i] = 0;
   core[C_Q + 3] = 1.0;
   core[C_TD] = td;
+  for (int i = 0; i < 3; ++i) { core[C_TG + 4 * i] = 1.0; core[C_MA + 4 * i] = 1.0; }      // Ma = Tg = I, As = 0 (:129-131)
   // R_imu_cam0 = R_file, t_cam0_imu = -R_file^T t_file (larvio.cpp:189-203)
   for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) core[C_RIC + r * 3 + c] = T_cam_imu[r * 4 + c];
   for (int r = 0; r < 3; ++r) {
     double a = 0; for (int k = 0; k < 3; ++k) a += T_cam_imu[k * 4 + r] * T_cam_imu[k * 4 + 3];
     core[C_TCI + r] = -a;
   }
-  ic[I_DIM] = BE_LEG;
+  ic[I_DIM] = LEGD;
   double* P = P_of(v, s);
   const int LD = v.be.LD;
-  for (int i = 0; i < BE_LEG; ++i) for (int j = 0; j < BE_LEG; ++j) P[(size_t)i * LD + j] = 0.0;
+  for (int i = 0; i < LEGD; ++i) for (int j = 0; j < LEGD; ++j) P[(size_t)i * LD + j] = 0.0;
   for (int i = 0; i < 3; ++i) {
     P[(size_t)i * LD + i] = c_ori; P[(size_t)(3 + i) * LD + 3 + i] = c_vel; P[(size_t)(6 + i) * LD + 6 + i] = c_pos;
     P[(size_t)(9 + i) * LD + 9 + i] = c_bg; P[(size_t)(12 + i) * LD + 12 + i] = c_ba;
     if (est_ext) { P[(size_t)(15 + i) * LD + 15 + i] = c_er; P[(size_t)(18 + i) * LD + 18 + i] = c_et; }
   }
   if (est_td) P[(size_t)21 * LD + 21] = 4e-6;
+  for (int i = 22; i < LEGD; ++i) P[(size_t)i * LD + i] = 1e-4;                              // :183-186
 }
 
 static BeView make_beview(LvbHandle* h) {
@@ -2051,7 +2120,8 @@ int be_alloc(LvbHandle* h) {
   be->grid_rows = c.aug_grid_rows; be->grid_cols = c.aug_grid_cols; be->max_per_cell = c.max_features_in_one_grid > 0 ? c.max_features_in_one_grid : 0;
   be->NFmax = be->max_per_cell * be->grid_rows * be->grid_cols;
   if (be->NFmax > 64 || c.feature_idp_dim != 1 || c.use_schmidt) be->NFmax = 0;   // such configs are refused at the first back-end call
-  be->Dmax = BE_LEG + 6 * be->Wcap + be->NFmax;
+  be->LEG = h->cfg.calib_imu_instrinsic ? 46 : 22;
+  be->Dmax = be->LEG + 6 * be->Wcap + be->NFmax;
   be->LD = ((be->Dmax + 7) / 8) * 8;
   be->LDS = be->NFmax ? ((be->Dmax + 2 * be->NFmax + 16 * be->NFmax + 7) / 8) * 8 : be->LD;
   be->RAWMAX = 4096; be->RMAX = 2048;
@@ -2086,6 +2156,7 @@ int be_alloc(LvbHandle* h) {
   // dynamic shared memory opt-ins
   const int fsm_bytes = (int)sizeof(double) * (6 * be->Wcap + 8 + 4 * be->Wcap * be->Wcap + 2 * be->Wcap + (8 + 6 * be->Wcap) / 2 + 4);
   LVB_CUDA(cudaFuncSetAttribute(be_feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm_bytes));
+  LVB_CUDA(cudaFuncSetAttribute(be_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (4 * be->LEG * (be->LEG + 1) + be->LEG))));
   if (be->NFmax > 0) LVB_CUDA(cudaFuncSetAttribute(be_slam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 64 * be->LD)));
   const size_t chol_bytes = sizeof(double) * ((size_t)be->Dmax * (be->Dmax + 1) / 2 + 2 * be->Dmax);
   if (chol_bytes <= 227 * 1024) LVB_CUDA(cudaFuncSetAttribute(be_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_bytes));
@@ -2309,7 +2380,7 @@ int be_process(LvbHandle* h, const LvbFeature* d_msg, const int* d_msg_n, const 
   BeView v = make_beview(h);
   v.msg = d_msg; v.msg_n = d_msg_n; v.msg_t = d_msg_t; v.msg_valid = d_valid; v.msg_stride = msg_stride;
   LVB_PROF(h, "be_propagate_kernel");
-  be_propagate_kernel<<<S, 256, 0, st>>>(v);
+  be_propagate_kernel<<<S, 256, sizeof(double) * (4 * be->LEG * (be->LEG + 1) + be->LEG), st>>>(v);
   LVB_LAUNCH_CHECK(h);
   const int nthr = be->N <= 256 ? 256 : 512;
   if (be->N > 512) return lvb_set_err(LVB_E_UNSUPPORTED, "max_features_num > 512");
@@ -2441,6 +2512,24 @@ extern "C" int lvb_get_states(LvbHandle* h, double* out) {
     for (int i = 0; i < 4; ++i) o[1 + i] = c[C_Q + i];
     for (int i = 0; i < 3; ++i) { o[5 + i] = c[C_P + i]; o[8 + i] = c[C_V + i]; o[11 + i] = c[C_BG + i]; o[14 + i] = c[C_BA + i]; }
   }
+  return LVB_OK;
+}
+
+extern "C" int lvb_get_calibration(LvbHandle* h, int seq, double* R_imu_cam9, double* t_cam_imu3, double* td,
+                                   double* Tg9, double* As9, double* Ma9) {
+  if (!h || seq < 0 || seq >= h->S) return lvb_set_err(LVB_E_ARG, "lvb_get_calibration: bad argument");
+  LVB_CUDA(cudaSetDevice(h->device));
+  double c[BE_CORE];
+  LVB_CUDA(cudaMemcpyAsync(c, h->be->core + (size_t)seq * BE_CORE, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  LVB_CUDA(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < 9; ++i) {
+    if (R_imu_cam9) R_imu_cam9[i] = c[C_RIC + i];
+    if (Tg9) Tg9[i] = c[C_TG + i];
+    if (As9) As9[i] = c[C_AS + i];
+    if (Ma9) Ma9[i] = c[C_MA + i];
+  }
+  for (int i = 0; i < 3; ++i) if (t_cam_imu3) t_cam_imu3[i] = c[C_TCI + i];
+  if (td) *td = c[C_TD];
   return LVB_OK;
 }
 

@@ -3,13 +3,14 @@
 #pragma once
 #include "lvb_internal.h"
 
-#define BE_LEG 22            // legacy error-state size without IMU-intrinsic calibration (larvio.cpp:158-161)
+#define BE_LEG_MAX 46        // legacy error-state size with IMU-intrinsic calibration (larvio.cpp:158-161); 22 without (LvbBackEnd::LEG)
 
 // ---- core[s][BE_CORE] doubles
 enum {
   C_TIME = 0, C_Q = 1, C_P = 5, C_V = 8, C_BG = 11, C_BA = 14, C_RIC = 17 /*R_imu_cam0 row-major*/, C_TCI = 26,
   C_TD = 29, C_DT = 30, C_FNOW_P = 31, C_FNOW_V = 34, C_FOLD_P = 37, C_FOLD_V = 40, C_OLD_Q = 43, C_OLD_P = 47,
-  C_OLD_V = 50, C_GYRO_OLD = 53, C_ACC_OLD = 56, C_TRACK_RATE = 59, C_TAKEOFF = 60, C_LAST_ZUPT = 61, BE_CORE = 64
+  C_OLD_V = 50, C_GYRO_OLD = 53, C_ACC_OLD = 56, C_TRACK_RATE = 59, C_TAKEOFF = 60, C_LAST_ZUPT = 61,
+  C_TG = 64, C_AS = 73, C_MA = 82 /*IMU intrinsics Tg, As, Ma row-major (larvio.cpp:129-155); T1..M2 are their entries*/, BE_CORE = 96
 };
 // ---- icore[s][BE_ICORE] ints
 enum {
@@ -24,6 +25,7 @@ enum { W_TIME = 0, W_DT = 1, W_Q = 2, W_P = 6, W_PFEJ = 9, W_RIC = 12, W_TCI = 2
 
 struct LvbBackEnd {
   int S, N;            // sequences, message capacity per sequence
+  int LEG;             // legacy error-state size: 22, or 46 with calib_imu_instrinsic
   int Wcap;            // window capacity (sw_size + 1)
   int T;               // feature-table capacity per sequence
   int LD;              // leading dimension of P / row length of stacked Jacobians (>= Dmax, multiple of 8)

@@ -49,6 +49,8 @@ def run_oracle(cfg_raw, seq, n_frames, init_from_truth=True):
             rec["ok"] = be.process_features(msg, imu)
             if rec["ok"]:
                 s = be.imu_state
-                rec.update(q=s.q.copy(), p=s.p.copy(), v=s.v.copy(), bg=s.bg.copy(), ba=s.ba.copy(), P=be.P.copy(), n_win=len(be.aug))
+                rec.update(q=s.q.copy(), p=s.p.copy(), v=s.v.copy(), bg=s.bg.copy(), ba=s.ba.copy(), P=be.P.copy(), n_win=len(be.aug),
+                           t=float(seq.img_t[j]), n_slam=len(getattr(be, "feature_states", [])), dim=be.P.shape[0],
+                           pos_err=float(np.linalg.norm(s.p - seq.gt_p[j])))
         out.append(rec)
     return out

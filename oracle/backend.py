@@ -263,10 +263,10 @@ class LarVioOracle:
         self.gyro_bias_noise = float(r["noise_gyro_bias"]) ** 2; self.acc_bias_noise = float(r["noise_acc_bias"]) ** 2
         self.feature_noise = float(r["noise_feature"]) ** 2
         self.calib_imu = bool(int(r["calib_imu_instrinsic"]))
-        if self.calib_imu:
-            raise NotImplementedError("calib_imu_instrinsic")
-        self.LEG = 22
-        self.Ma = np.eye(3); self.Tg = np.eye(3); self.As = np.zeros((3, 3))
+        self.LEG = 46 if self.calib_imu else 22                    # larvio.cpp:158-161
+        self.Ma = np.eye(3); self.Tg = np.eye(3); self.As = np.zeros((3, 3))      # :129-131
+        # T1/A1/M1 = strictly lower entries (1,0) (2,0) (2,1); T2/A2/M2 = diagonals; T3/A3 = upper (0,1) (0,2) (1,2)  (:132-155)
+        self.imu_intr = np.concatenate([[0, 0, 0], [1, 1, 1], [0, 0, 0], np.zeros(9), [0, 0, 0], [1, 1, 1]]).astype(np.float64)
         P = np.zeros((self.LEG, self.LEG))
         P[0:3, 0:3] = np.eye(3) * float(r["initial_covariance_orientation"])
         P[3:6, 3:6] = np.eye(3) * float(r["initial_covariance_velocity"])
@@ -278,6 +278,8 @@ class LarVioOracle:
             P[18:21, 18:21] = np.eye(3) * float(r["initial_covariance_extrin_trans"])
         if self.estimate_td:
             P[21, 21] = 4e-6
+        if self.calib_imu:
+            P[22:46, 22:46] = 1e-4 * np.eye(24)                   # :183-186
         self.P = P
         T = np.array(r["T_cam_imu"]["data"], np.float64).reshape(4, 4)
         self.imu_state = ImuState()
@@ -457,7 +459,61 @@ class LarVioOracle:
         Phi[6:9, 9:12] = (-dtime * dtime * dtime * skew(g) @ C / 6 +
                           dtime * skew(pk1 - pk - g * dtime * dtime / 6) @ C @ Ah / 4)
         Phi[6:9, 12:15] = -C @ (3 * I3 + Ah) * dtime * dtime / 6 @ self.Ma - Phi[6:9, 9:12] @ TA @ self.Ma
+        if not self.calib_imu:
+            return Phi
+        # ---- IMU-intrinsic columns (:3532-3797).  For a 3-vector x the selectors are
+        #   Lo(x): (1,0)=x0 (2,1)=x0 (2,2)=x1    Di(x) = diag(x)    Up(x): (0,0)=x1 (0,1)=x2 (1,2)=x2
+        def Lo(x):
+            m = np.zeros((3, 3)); m[1, 0] = x[0]; m[2, 1] = x[0]; m[2, 2] = x[1]; return m
+
+        def Di(x):
+            return np.diag(x)
+
+        def Up(x):
+            m = np.zeros((3, 3)); m[0, 0] = x[1]; m[0, 1] = x[2]; m[1, 2] = x[2]; return m
+        f_mid = (f + f_old) / 2; acc_mid = (acc + acc_old) / 2
+        w_mid = (w_old + w) / 2 + dtime * np.cross(w_old, w) / 12
+        R_mid = I3 + 0.5 * Ah; R_kp1 = I3 + Ah
+        S_mid = skew(R_mid @ acc_mid); S_kp1 = skew(R_kp1 @ acc)
+        Tg = self.Tg
+        # (column, selector, samples at k / k+1/2 / k+1, left factor, sign of the q block, direct-v term?)
+        groups = [(22, Lo, (w_old, w_mid, w), I3, +1, False), (25, Di, (w_old, w_mid, w), I3, +1, False),
+                  (28, Up, (w_old, w_mid, w), I3, +1, False),
+                  (31, Lo, (acc_old, acc_mid, acc), Tg, -1, False), (34, Di, (acc_old, acc_mid, acc), Tg, -1, False),
+                  (37, Up, (acc_old, acc_mid, acc), Tg, -1, False),
+                  (40, Lo, (f_old, f_mid, f), TA, -1, True), (43, Di, (f_old, f_mid, f), TA, -1, True)]
+        for col, sel, (xk, xh, xp), Lf, sgn, direct in groups:
+            kq1 = Lf @ sel(xk); kq2 = R_mid @ Lf @ sel(xh); kq4 = R_kp1 @ Lf @ sel(xp)
+            Rq = dtime * (kq1 + 4 * kq2 + kq4) / 6
+            Phi[0:3, col:col + 3] = sgn * C @ Rq
+            if not direct:
+                kv1 = np.zeros((3, 3))
+                kv2 = S_mid * dtime @ kq1 / 2
+                kv3 = S_mid * dtime @ kq2 / 2
+                kv4 = S_kp1 @ Rq
+            else:
+                kv1 = sel(xk)
+                kv2 = R_mid @ sel(xh) + S_mid * dtime @ kq1 / 2
+                kv3 = R_mid @ sel(xh) + S_mid * dtime @ kq2 / 2
+                kv4 = R_kp1 @ sel(xp) + S_kp1 @ Rq
+            fR = dtime * (kv1 + 2 * kv2 + 2 * kv3 + kv4) / 6
+            vs = +1 if direct else -sgn            # Phi_v: -C f for T, +C f for A, +C v for M
+            Phi[3:6, col:col + 3] = vs * C @ fR
+            kp1 = np.zeros((3, 3)); kp2 = dtime * kv1 / 2; kp3 = dtime * kv2 / 2; kp4 = fR
+            Phi[6:9, col:col + 3] = vs * C @ (dtime * (kp1 + 2 * kp2 + 2 * kp3 + kp4) / 6)
         return Phi
+
+    # ---- :1497-1507, 1713-1723, 2858-2868 + updateImuMx :3803-3847
+    def _inject_imu_intrinsics(self, dx):
+        if not self.calib_imu:
+            return
+        self.imu_intr = self.imu_intr + dx[22:46]
+        T1, T2, T3, A1, A2, A3, M1, M2 = [self.imu_intr[3 * i:3 * i + 3] for i in range(8)]
+        self.Tg = np.array([[T2[0], T3[0], T3[1]], [T1[0], T2[1], T3[2]], [T1[1], T1[2], T2[2]]])
+        self.As = np.array([[A2[0], A3[0], A3[1]], [A1[0], A2[1], A3[2]], [A1[1], A1[2], A2[2]]])
+        Ma = self.Ma.copy()                                      # the upper triangle of Ma is never written (:3839-3844)
+        Ma[0, 0] = M2[0]; Ma[1, 0] = M1[0]; Ma[1, 1] = M2[1]; Ma[2, 0] = M1[1]; Ma[2, 1] = M1[2]; Ma[2, 2] = M2[2]
+        self.Ma = Ma
 
     # ---- :720-801
     def _augment(self):
@@ -750,6 +806,7 @@ class LarVioOracle:
         s.R_imu_cam0 = s.R_imu_cam0 @ quat_to_rot(small_angle_quat(dx[15:18])).T
         s.t_cam0_imu = s.t_cam0_imu + dx[18:21]
         self.td += dx[21]
+        self._inject_imu_intrinsics(dx)
         for i, sid in enumerate(sorted(self.aug.keys())):
             a = self.aug[sid]
             da = dx[self.LEG + 6 * i:self.LEG + 6 * i + 6]
@@ -787,6 +844,7 @@ class LarVioOracle:
         s.R_imu_cam0 = s.R_imu_cam0 @ quat_to_rot(dqe).T
         s.t_cam0_imu = s.t_cam0_imu + dx[18:21]
         self.td += dx[21]
+        self._inject_imu_intrinsics(dx)
         for i, sid in enumerate(sorted(self.aug.keys())):
             a = self.aug[sid]
             da = dx[self.LEG + 6 * i:self.LEG + 6 * i + 6]

@@ -8,7 +8,8 @@ from oracle.frontend import ImageProcessorOracle
 from oracle.backend import LarVioOracle
 
 NF = int(sys.argv[1]) if len(sys.argv) > 1 else 100
-cfg = Config.load('configs/euroc_mono.yaml', max_features_in_one_grid=0, sw_size=int(os.environ.get('SW', '30'))).raw
+cfg = Config.load('configs/euroc_mono.yaml', max_features_in_one_grid=int(os.environ.get('GRID', '0')), sw_size=int(os.environ.get('SW', '30')),
+                  calib_imu_instrinsic=int(os.environ.get('CALIB', '0'))).raw
 seq = synth.make_sequence(cfg, int(os.environ.get('SEQ', '0')), NF)
 fe = ImageProcessorOracle(cfg); be = LarVioOracle(cfg)
 imu = []; k = 0

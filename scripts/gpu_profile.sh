@@ -1,26 +1,22 @@
 #!/bin/bash
 # ncu evidence for profiles/: launch list (shares) + full captures of the dominant kernels. Run via gpurun.
-# Frame 66 of a 70-frame replay is a publishing frame with a full 30-pose window (QR + both EKF updates active).
+# Frames 66-67 of a 70-frame replay: a full 30-pose window, one publishing frame (QR + both EKF updates active).
+# The replay brackets those frames with cuProfilerStart/Stop, so ncu (--profile-from-start off) sees nothing else.
 TAG=${1:-r1}
-export S=64 NF=70
+export S=64 NF=70 PF=66 PN=2
 python scripts/profile_driver.py gen
-LPF=$(python - <<'PY'
-# launches per frame, counted from a dry run with the library's own counter
-import subprocess, re, os
-out = subprocess.run(["python", "scripts/profile_driver.py", "run"], capture_output=True, text=True, env=dict(os.environ, NF="4")).stdout
-m = re.search(r"(\d+) launches", out)
-print((int(m.group(1)) - 3) // 4 if m else 75)
-PY
-)
-echo "launches per frame: $LPF"
-ncu --metrics gpu__time_duration.sum --clock-control none -s $((LPF * 66 + 3)) -c $((LPF * 2)) --csv --log-file gpurun_out/launches_${TAG}.csv \
+ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv \
     python scripts/profile_driver.py run > gpurun_out/ncu_launches_${TAG}.log 2>&1
 tail -2 gpurun_out/ncu_launches_${TAG}.log
-# kernel : launches per frame
-for KL in lk_kernel:2 be_feature_kernel:2 mineig_kernel:1 blur7_kernel:1 be_gemm_kernel:9 be_qr_kernel:3 clahe_apply_kernel:1 be_chol_kernel:3 ransac_kernel:1 orb_kernel:3; do
-  K=${KL%%:*}; L=${KL##*:}
-  ncu --set full --clock-control none --import-source on -k regex:^$K -s $((L * 66)) -c $L -o gpurun_out/prof_${K}_${TAG} -f \
+for K in ${KERNELS:-lk_kernel be_qr_kernel be_chol_kernel ransac_kernel be_gemm_kernel be_trsm_kernel orb_kernel be_feature_kernel mineig_kernel be_propagate_kernel candidates_kernel select_kernel clahe_apply_kernel blur7_kernel}; do
+  ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:^$K -c ${NCAP:-6} -o gpurun_out/prof_${K}_${TAG} -f \
       python scripts/profile_driver.py run > gpurun_out/ncu_${K}_${TAG}.log 2>&1
   tail -1 gpurun_out/ncu_${K}_${TAG}.log
 done
-ls -la gpurun_out/ | grep -E "ncu-rep|launches"
+# summarise on the box (gpurun_out/ has a 64 MiB return limit), keep only the reports named in KEEP
+OUT=gpurun_out/profiles_${TAG} python scripts/ncu_summary.py ${TAG} > gpurun_out/ncu_summary_${TAG}.log 2>&1
+for K in $(ls gpurun_out/prof_*_${TAG}.ncu-rep); do
+  keep=0; for W in ${KEEP:-lk_kernel be_qr_kernel be_chol_kernel}; do [[ $K == *prof_${W}_${TAG}* ]] && keep=1; done
+  [[ $keep == 0 ]] && rm -f $K
+done
+ls -la gpurun_out/ | grep -E "ncu-rep|launches"; du -sh gpurun_out

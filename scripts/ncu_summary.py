@@ -40,8 +40,9 @@ out.append("\n## launch list — two consecutive steady-state frames (one publis
 out.append("total %.1f us over %d launches (cold-cache, serialised: compare SHARES)\n\n| kernel | launches | us/launch | share |\n|---|---|---|---|" % (tot / 1e3, sum(v[1] for v in agg.values())))
 for k, (v, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     out.append("| %s | %d | %.1f | %.3f |" % (k, n, v / 1e3 / n, v / tot))
-os.makedirs("profiles", exist_ok=True)
-open("profiles/%s_ncu_summary.md" % tag, "w").write("\n".join(out) + "\n")
+OUT = os.environ.get("OUT", "profiles")
+os.makedirs(OUT, exist_ok=True)
+open(OUT + "/%s_ncu_summary.md" % tag, "w").write("\n".join(out) + "\n")
 import shutil
-shutil.copy("gpurun_out/launches_%s.csv" % tag, "profiles/%s_launches.csv" % tag)
+shutil.copy("gpurun_out/launches_%s.csv" % tag, OUT + "/%s_launches.csv" % tag)
 print("\n".join(out[:120]))

@@ -29,7 +29,15 @@ else:
     for s in range(S):
         b.set_initial_state(s, img_t[s, 0], d["q"][s], d["p"][s], d["v"][s], np.zeros(3), np.zeros(3))
     imu = np.zeros((S, 96), api.IMU_DTYPE); n_imu = np.zeros(S, np.int32); k = np.zeros(S, np.int64)
+    # ncu --profile-from-start off: only frames [PF, PF+PN) are profiled (driver-API range, independent of the runtime in use)
+    import ctypes
+    PF = int(os.environ.get("PF", "-1")); PN = int(os.environ.get("PN", "2"))
+    cuda = ctypes.CDLL("libcuda.so.1")
     for j in range(NF):
+        if j == PF:
+            b.synchronize(); cuda.cuProfilerStart()
+        if j == PF + PN:
+            b.synchronize(); cuda.cuProfilerStop()
         for s in range(S):
             k2 = int(k[s])
             while k2 < imu_all.shape[1] and imu_all[s, k2, 0] - img_t[s, j] < 0.05:

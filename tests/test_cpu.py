@@ -187,6 +187,61 @@ def test_oracle_zupt_holds_still_then_moves(cfg):
     assert [r for r in recs if r["ok"]][-1]["n_win"] > 3
 
 
+def test_oracle_imu_intrinsic_phi_columns_match_finite_differences():
+    """calPhi's 24 IMU-intrinsic columns (larvio.cpp:3532-3797) are first-order sensitivities of (theta, v, p) after one
+    IMU step to T1..M2.  The reference integrates them with mid-sample approximations, so agreement with a finite
+    difference of the restated process model is ~10 %, but a wrong sign / selector / left factor shows up as >= 100 %."""
+    from larvio_b200.config import Config
+    from oracle.backend import LarVioOracle, quat_mul
+    c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), calib_imu_instrinsic=1, if_FEJ=0)
+    rng = np.random.default_rng(0)
+    base = np.concatenate([[0.01, -0.02, 0.015], [1.01, 0.99, 1.02], [0.02, 0.01, -0.01], rng.normal(0, 0.003, 9),
+                           [0.01, -0.015, 0.02], [0.98, 1.01, 1.02]])
+    g0, a0, g1, a1 = np.array([0.3, -0.2, 0.5]), np.array([0.5, 9.6, 1.0]), np.array([0.32, -0.18, 0.47]), np.array([0.6, 9.5, 1.2])
+
+    def run(intr, grab=None):
+        o = LarVioOracle(c.raw)
+        assert o.LEG == 46 and o.P.shape == (46, 46) and np.allclose(np.diag(o.P)[22:], 1e-4)
+        o.set_initial_state(0.0, np.array([0.1, -0.2, 0.3, 0.9]), np.array([0.1, 0.2, 0.3]), np.array([0.5, -0.3, 0.2]),
+                            np.array([0.01, -0.02, 0.005]), np.array([0.05, 0.02, -0.03]))
+        o.imu_intr = intr.copy(); o._inject_imu_intrinsics(np.zeros(46)); o.if_FEJ = False
+        o.m_gyro_old, o.m_acc_old = g0, a0
+        if grab is not None:
+            orig = o._cal_phi
+            o._cal_phi = lambda *a: grab.append(orig(*a)) or grab[-1]
+        o._process_model(0.005, g1, a1)
+        return o.imu_state
+    phis = []
+    s0 = run(base, phis)
+    Phi = phis[0]
+    assert np.array_equal(Phi[9:, :], np.eye(46)[9:, :])             # biases, extrinsics, td and intrinsics are constant states
+    eps = 1e-5
+    for j in range(24):
+        d = base.copy(); d[j] += eps
+        s1 = run(d)
+        dq = quat_mul(s1.q, np.array([-s0.q[0], -s0.q[1], -s0.q[2], s0.q[3]]))
+        num = np.concatenate([2 * dq[:3], s1.v - s0.v, s1.p - s0.p]) / eps
+        ana = Phi[0:9, 22 + j]
+        assert np.linalg.norm(num - ana) < 0.2 * np.linalg.norm(ana), j
+
+
+def test_oracle_hybrid_promotes_slam_features(cfg):
+    """euroc defaults (5x6 grid, one 1-D inverse-depth feature per cell): features enter the state only 5 s after the
+    first frame (larvio.cpp:1974) and the state dimension then follows LEG + 6 n_win + n_slam."""
+    from larvio_b200 import synth, harness
+    from larvio_b200.config import Config
+    hc = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), sw_size=12)
+    seq = synth.make_sequence(hc.raw, 0, 116)
+    recs = harness.run_oracle(hc.raw, seq, 116)
+    ok = [r for r in recs if r.get("ok")]
+    early = [r for r in ok if r["t"] - ok[0]["t"] < 4.9]
+    late = [r for r in ok if r["t"] - ok[0]["t"] > 5.3]
+    assert early and late
+    assert all(r["n_slam"] == 0 for r in early) and max(r["n_slam"] for r in late) >= 3
+    assert all(r["dim"] == 22 + 6 * r["n_win"] + r["n_slam"] for r in ok)
+    assert max(r["pos_err"] for r in ok) < 0.25
+
+
 def test_update_invariant_to_orthogonal_row_transform(cfg):
     """What legitimises Householder/Givens QR on the GPU vs SPQR on the CPU."""
     from oracle.backend import LarVioOracle

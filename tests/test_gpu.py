@@ -215,6 +215,10 @@ def _drive(cfg, seqs, nf, mode, S=2):
             assert P.shape == bes[s].P.shape
             assert np.abs(P - P.T).max() == 0.0                               # symmetric by construction
             rep['Prel'] = max(rep['Prel'], float(np.linalg.norm(P - bes[s].P) / np.linalg.norm(bes[s].P)))
+            cal = b.get_calibration(s)
+            rep['calib'] = max(rep.get('calib', 0.0), float(max(np.abs(cal['Tg'] - bes[s].Tg).max(), np.abs(cal['As'] - bes[s].As).max(),
+                               np.abs(cal['Ma'] - bes[s].Ma).max(), np.abs(cal['R_imu_cam0'] - o.R_imu_cam0).max(),
+                               np.abs(cal['t_cam0_imu'] - o.t_cam0_imu).max(), abs(cal['td'] - bes[s].td))))
     b.close()
     return rep
 
@@ -259,6 +263,29 @@ def test_hybrid_slam_features_match_oracle(lib_built):
     rep = _drive(hc, hs, 130, 'step')
     assert rep['steps'] >= 60 and rep['ok_mismatch'] == 0 and rep['imu_mismatch'] == 0
     assert rep['p'] < 1e-8 and rep['v'] < 1e-8 and rep['q'] < 1e-8 and rep['Prel'] < 1e-8
+
+
+def test_imu_intrinsic_calibration_matches_oracle(lib_built):
+    """calib_imu_instrinsic: 1 -> LEG_DIM 46 (larvio.cpp:158-161): the 24 Tg/As/Ma states are propagated (calPhi
+    :3532-3797) and corrected (:1497-1507) exactly like the oracle's, in pure-MSCKF mode."""
+    from larvio_b200 import synth
+    from larvio_b200.config import Config
+    cc = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), sw_size=16, max_features_in_one_grid=0, calib_imu_instrinsic=1)
+    cs = [synth.make_sequence(cc.raw, s, 70) for s in range(2)]
+    rep = _drive(cc, cs, 70, 'step')
+    assert rep['steps'] >= 40 and rep['ok_mismatch'] == 0 and rep['imu_mismatch'] == 0
+    assert rep['p'] < 1e-8 and rep['v'] < 1e-8 and rep['q'] < 1e-8 and rep['Prel'] < 1e-8 and rep['calib'] < 1e-9
+
+
+def test_config_d_hybrid_with_online_calibration(lib_built):
+    """BASELINE configs[3] per sequence: 1-D IDP hybrid + estimate_extrin/td + IMU-intrinsic calibration."""
+    from larvio_b200 import synth
+    from larvio_b200.config import Config
+    cc = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), sw_size=16, calib_imu_instrinsic=1)
+    cs = [synth.make_sequence(cc.raw, s, 124) for s in range(2)]
+    rep = _drive(cc, cs, 124, 'step')
+    assert rep['steps'] >= 58 and rep['ok_mismatch'] == 0 and rep['imu_mismatch'] == 0
+    assert rep['p'] < 1e-8 and rep['v'] < 1e-8 and rep['q'] < 1e-8 and rep['Prel'] < 1e-8 and rep['calib'] < 1e-9
 
 
 def test_gpu_against_committed_golden(cfg, seqs):
