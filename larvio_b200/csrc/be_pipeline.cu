@@ -14,6 +14,7 @@
 #include <math.h>
 #include <string.h>
 #include "be_state.h"
+#include <cstring>
 #include "be_math.cuh"
 
 #define RC(x) do { int rc_ = (x); if (rc_ != LVB_OK) return rc_; } while (0)
@@ -56,6 +57,7 @@ __device__ __forceinline__ M3 imu_selector(int kind, V3 x) {
   else { r.m[0] = x.y; r.m[1] = x.z; r.m[5] = x.z; }
   return r;
 }
+template <int L>
 __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
   extern __shared__ double psm[];                      // Phi, PLL, Tmp, PhiTot: [L][L+1] each; Ddiag [L]
   __shared__ int s_ok, s_action, s_used;
@@ -65,7 +67,8 @@ __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
   int* ic = icore_of(v, s);
   const LvbImu* imu = v.be.imu + (size_t)s * v.be.imu_cap;
   const int n_imu = v.be.n_imu[s];
-  const int L = LEGD, LD = v.be.LD, LP = L + 1;
+  constexpr int LP = L + 1;
+  const int LD = v.be.LD;
   double* const Phi_ = psm; double* const PLL_ = psm + L * LP; double* const Tmp_ = psm + 2 * L * LP; double* const PhiTot_ = psm + 3 * L * LP;
   double* const Ddiag = psm + 4 * L * LP;
 #define Phi(r, c) Phi_[(r) * LP + (c)]
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
             Phi(6 + r, 9 + c) = Ppbg.m[r * 3 + c];
             Phi(6 + r, 12 + c) = Ppba.m[r * 3 + c];
           }
-        if (L > 22) {
+        if constexpr (L > 22) {
           // ---- IMU-intrinsic columns (:3532-3797): 8 groups of 3 columns; selectors Lo/Di/Up place the components of
           // (w | acc | f) sampled at k, k+1/2, k+1; Simpson weights for q, the reference's RK4 weights for v and p
           const V3 f_mid = (f + f_old) * 0.5, acc_mid = (acc + acc_old) * 0.5;
@@ -784,7 +787,7 @@ __device__ __forceinline__ int be_feature_smem_doubles(int Wcap) { return 6 * Wc
 
 // gamma = r^T (H P H^T + sigma^2 I)^-1 r over the listed nonzero columns; returns pass/fail against chi2[dof = R]
 __device__ bool gate_block(const BeView& v, const double* P, int LD, const double* Hj, double* Tp, const double* rj, int R,
-                           const int* nzl, int nz, double* Ssm, double* vv, int lane) {
+                           const int* nzl, int nz, double* Ssm, double* vv, int lane, double* gamma_out = nullptr) {
   if (R <= 0 || R >= 100) return false;
   for (int j = lane; j < nz; j += 32) {
     const int c2 = nzl[j];
@@ -840,6 +843,7 @@ __device__ bool gate_block(const BeView& v, const double* P, int LD, const doubl
   __syncwarp();
   const double gamma = vv[0];
   __syncwarp();
+  if (gamma_out && lane == 0) *gamma_out = gamma;
   return gamma < c_chi2[R];
 }
 
@@ -978,7 +982,7 @@ __global__ void __launch_bounds__(32) be_feature_kernel(BeView v, double* Traw) 
   }
   // ---- gating test (:1865-1880) on rows 3..nrows-1
   const int R = nrows - 3;
-  const bool pass = gate_block(v, P, LD, H + (size_t)3 * LD, Tj + (size_t)3 * LD, rr + 3, R, nzl, nz, Ssm, vv, lane);
+  const bool pass = gate_block(v, P, LD, H + (size_t)3 * LD, Tj + (size_t)3 * LD, rr + 3, R, nzl, nz, Ssm, vv, lane, v.be.ft_gamma + fi);
   if (action == 2) { if (lane == 0) v.be.ft_accept[fi] = pass ? R : 0; return; }
 
   // ---- action 3: new EKF-SLAM feature
@@ -2139,7 +2143,7 @@ int be_alloc(LvbHandle* h) {
   BDA(be->Tm, S * (size_t)be->RAWMAX * LD);      // doubles as the per-feature H*P scratch of the gate
   BDA(be->Sm, S * (size_t)be->LDS * be->LDS); BDA(be->zvec, S * (size_t)be->LDS); BDA(be->dx, S * (size_t)be->LDS);
   BDA(be->ft_inv, S * T); BDA(be->ft_oa, S * T * 2); BDA(be->ft_anchor, S * T); BDA(be->ft_pfej, S * T * 3); BDA(be->ft_spec, S * T * 8);
-  BDA(be->fs_slot, S * 64); BDA(be->cmap, S * LD); BDA(be->cand, S * 128); BDA(be->Hnew, S * 64 * (LD + 4));
+  BDA(be->ft_gamma, S * T); BDA(be->fs_slot, S * 64); BDA(be->cmap, S * LD); BDA(be->cand, S * 128); BDA(be->Hnew, S * 64 * (LD + 4));
   BDA(be->imu, S * be->imu_cap); BDA(be->n_imu, S);
   BDA(be->msg_in, S * be->N); BDA(be->msg_in_n, S); BDA(be->msg_in_t, S); BDA(be->msg_in_valid, S);
   BPIN(be->pin_imu, LvbImu, S * be->imu_cap); BPIN(be->pin_n_imu, int, S); BPIN(be->pin_icore, int, S * BE_ICORE);
@@ -2156,7 +2160,7 @@ int be_alloc(LvbHandle* h) {
   // dynamic shared memory opt-ins
   const int fsm_bytes = (int)sizeof(double) * (6 * be->Wcap + 8 + 4 * be->Wcap * be->Wcap + 2 * be->Wcap + (8 + 6 * be->Wcap) / 2 + 4);
   LVB_CUDA(cudaFuncSetAttribute(be_feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm_bytes));
-  LVB_CUDA(cudaFuncSetAttribute(be_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (4 * be->LEG * (be->LEG + 1) + be->LEG))));
+  LVB_CUDA(cudaFuncSetAttribute(be_propagate_kernel<46>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (4 * 46 * 47 + 46))));
   if (be->NFmax > 0) LVB_CUDA(cudaFuncSetAttribute(be_slam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 64 * be->LD)));
   const size_t chol_bytes = sizeof(double) * ((size_t)be->Dmax * (be->Dmax + 1) / 2 + 2 * be->Dmax);
   if (chol_bytes <= 227 * 1024) LVB_CUDA(cudaFuncSetAttribute(be_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_bytes));
@@ -2260,6 +2264,16 @@ static int be_debug_check(LvbHandle* h, const char* stage) {
     int bad = 0;
     for (int i = 0; i < d && !bad; ++i) for (int j = 0; j < d; ++j) if (!std::isfinite(P[(size_t)i * be->LD + j])) { bad = 1; fprintf(stderr, "[lvb debug] %s: seq %d P[%d][%d] not finite (d=%d nwin=%d nf=%d R=%d rows=%d nnew=%d)\n", stage, s, i, j, d, c[I_NWIN], c[I_NF], c[I_R], c[I_ROWS], c[I_NNEW]); break; }
     if (!bad) fprintf(stderr, "[lvb debug] %s: seq %d ok (d=%d nwin=%d nf=%d R=%d rows=%d nnew=%d ncand=%d)\n", stage, s, d, c[I_NWIN], c[I_NF], c[I_R], c[I_ROWS], c[I_NNEW], c[I_NCAND]);
+    if (getenv("LVB_DEBUG_FEAT") && !strcmp(stage, "be_feature_kernel")) {
+      const int T = be->T;
+      std::vector<unsigned long long> ids(T); std::vector<int> act(T), acc(T), nr(T); std::vector<double> gm(T);
+      cudaMemcpy(ids.data(), be->ft_id + (size_t)s * T, sizeof(unsigned long long) * T, cudaMemcpyDeviceToHost);
+      cudaMemcpy(act.data(), be->ft_action + (size_t)s * T, sizeof(int) * T, cudaMemcpyDeviceToHost);
+      cudaMemcpy(acc.data(), be->ft_accept + (size_t)s * T, sizeof(int) * T, cudaMemcpyDeviceToHost);
+      cudaMemcpy(nr.data(), be->ft_nrows + (size_t)s * T, sizeof(int) * T, cudaMemcpyDeviceToHost);
+      cudaMemcpy(gm.data(), be->ft_gamma + (size_t)s * T, sizeof(double) * T, cudaMemcpyDeviceToHost);
+      for (int i = 0; i < T; ++i) if (act[i] >= 2) fprintf(stderr, "[lvb feat] seq %d id %llu action %d nrows %d accept %d gamma %.9e\n", s, ids[i], act[i], nr[i], acc[i], gm[i]);
+    }
     // stacked system, T, S, z, dx, Hnew
     const int r = c[I_R];
     if (r > 0) {
@@ -2380,7 +2394,8 @@ int be_process(LvbHandle* h, const LvbFeature* d_msg, const int* d_msg_n, const 
   BeView v = make_beview(h);
   v.msg = d_msg; v.msg_n = d_msg_n; v.msg_t = d_msg_t; v.msg_valid = d_valid; v.msg_stride = msg_stride;
   LVB_PROF(h, "be_propagate_kernel");
-  be_propagate_kernel<<<S, 256, sizeof(double) * (4 * be->LEG * (be->LEG + 1) + be->LEG), st>>>(v);
+  if (be->LEG == 22) be_propagate_kernel<22><<<S, 256, sizeof(double) * (4 * 22 * 23 + 22), st>>>(v);
+  else be_propagate_kernel<46><<<S, 256, sizeof(double) * (4 * 46 * 47 + 46), st>>>(v);
   LVB_LAUNCH_CHECK(h);
   const int nthr = be->N <= 256 ? 256 : 512;
   if (be->N > 512) return lvb_set_err(LVB_E_UNSUPPORTED, "max_features_num > 512");

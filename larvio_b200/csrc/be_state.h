@@ -44,6 +44,7 @@ struct LvbBackEnd {
   // EKF-SLAM (1-D inverse depth) bookkeeping per table slot: invDepth, corrected anchor observation (x,y), anchor window slot,
   // first-estimate position; speculative triangulation results of this frame; state order list
   double* ft_inv; double* ft_oa; int* ft_anchor; double* ft_pfej; double* ft_spec; int* fs_slot; int* cmap; int* cand;
+  double* ft_gamma;                           // [S][T] last gating statistic of each slot (diagnostics)
   double* Hnew;                               // [S][NFmax][LD + 4]: (H_1 row, h2, r_1) of the features added this frame
   double* Hraw; double* rraw;                 // [S][RAWMAX][LD], [S][RAWMAX]
   double* Hs; double* rs;                     // stacked, COLUMN-major [S][LD cols][RMAX rows], [S][RMAX]

@@ -95,8 +95,24 @@ __device__ int solve_cubic(const double* c, double* x) {
 // 7-point solver of one lane. A lives in shared memory, element-major: A[e*32 + lane].
 __device__ int seven_point(double* A, const float2* p1, const float2* p2, const int* idx, double* F /*[3][9]*/) {
 #define AA(r, c) A[((r) * 9 + (c)) * 32]
+  // Hartley normalisation of the seven pairs, as run7Point does in the OpenCV (4.13) the oracle runs: centroid to the
+  // origin, mean distance sqrt(2).  The candidate set is the same as for the raw-pixel system; the ORDER of the
+  // candidates (which decides ties between equally good models of one sample) follows the normalised system.
+  double m1cx = 0, m1cy = 0, m2cx = 0, m2cy = 0;
+  for (int i = 0; i < 7; ++i) { m1cx += (double)p1[idx[i]].x; m1cy += (double)p1[idx[i]].y; m2cx += (double)p2[idx[i]].x; m2cy += (double)p2[idx[i]].y; }
+  const double tcnt = 1. / 7;
+  m1cx *= tcnt; m1cy *= tcnt; m2cx *= tcnt; m2cy *= tcnt;
+  double scale1 = 0, scale2 = 0;
   for (int i = 0; i < 7; ++i) {
-    const double x0 = p1[idx[i]].x, y0 = p1[idx[i]].y, x1 = p2[idx[i]].x, y1 = p2[idx[i]].y;
+    const double ax = (double)p1[idx[i]].x - m1cx, ay = (double)p1[idx[i]].y - m1cy, bx = (double)p2[idx[i]].x - m2cx, by = (double)p2[idx[i]].y - m2cy;
+    scale1 += sqrt(ax * ax + ay * ay); scale2 += sqrt(bx * bx + by * by);
+  }
+  scale1 *= tcnt; scale2 *= tcnt;
+  if (scale1 < (double)FLT_EPSILON || scale2 < (double)FLT_EPSILON) return 0;
+  scale1 = sqrt(2.) / scale1; scale2 = sqrt(2.) / scale2;
+  for (int i = 0; i < 7; ++i) {
+    const double x0 = ((double)p1[idx[i]].x - m1cx) * scale1, y0 = ((double)p1[idx[i]].y - m1cy) * scale1;
+    const double x1 = ((double)p2[idx[i]].x - m2cx) * scale2, y1 = ((double)p2[idx[i]].y - m2cy) * scale2;
     AA(i, 0) = x1 * x0; AA(i, 1) = x1 * y0; AA(i, 2) = x1;
     AA(i, 3) = y1 * x0; AA(i, 4) = y1 * y0; AA(i, 5) = y1;
     AA(i, 6) = x0; AA(i, 7) = y0; AA(i, 8) = 1.0;
@@ -174,6 +190,18 @@ __device__ int seven_point(double* A, const float2* p1, const float2* p2, const 
     if (fabs(s) > DBL_EPSILON) { mu = 1. / s; lambda *= mu; Fk[8] = 1.; }
     else Fk[8] = 0.;
     for (int i = 0; i < 8; ++i) Fk[i] = f1[i] * lambda + f2[i] * mu;
+    // de-normalise: T2^T F T1, T = [[s, 0, -s cx], [0, s, -s cy], [0, 0, 1]]; then F(3,3) = 1
+    double M[9], G[9];
+    for (int j = 0; j < 3; ++j) {
+      M[j] = scale2 * Fk[j]; M[3 + j] = scale2 * Fk[3 + j];
+      M[6 + j] = (-scale2 * m2cx) * Fk[j] + (-scale2 * m2cy) * Fk[3 + j] + Fk[6 + j];
+    }
+    for (int i = 0; i < 3; ++i) {
+      G[3 * i] = M[3 * i] * scale1; G[3 * i + 1] = M[3 * i + 1] * scale1;
+      G[3 * i + 2] = M[3 * i] * (-scale1 * m1cx) + M[3 * i + 1] * (-scale1 * m1cy) + M[3 * i + 2];
+    }
+    if (fabs(G[8]) > (double)FLT_EPSILON) { const double ig = 1. / G[8]; for (int i = 0; i < 9; ++i) G[i] *= ig; }
+    for (int i = 0; i < 9; ++i) Fk[i] = G[i];
   }
   return n;
 }

@@ -657,6 +657,7 @@ class LarVioOracle:
     def _gating(self, H, r, dof):
         S = H @ self.P @ H.T + self.feature_noise * np.eye(H.shape[0])
         gamma = float(r @ np.linalg.solve(S, r))
+        self.stats.setdefault("gates", []).append((dof, gamma, self.chi2.get(dof, 0.0)))      # diagnostics only
         return gamma < self.chi2.get(dof, 0.0)
 
     def _compress(self, H, r, cols):

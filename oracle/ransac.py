@@ -110,9 +110,28 @@ def opencv_null_basis(n1, n2):
 
 
 def run_7point(m1, m2):
+    """calib3d/src/fundam.cpp run7Point as shipped in the OpenCV 4.13 of this container: the seven pairs are
+    Hartley-normalised (centroid to the origin, mean distance sqrt(2)) before the 7x9 system is formed, and every
+    candidate F is mapped back with T2^T F T1 and rescaled to F(3,3) = 1.  (OpenCV <= 4.5 solved the raw-pixel
+    system; the candidate SET is the same, their ORDER - which decides ties - is not.)"""
+    m1d = np.asarray(m1, np.float32).astype(np.float64); m2d = np.asarray(m2, np.float32).astype(np.float64)
+    m1c = np.zeros(2); m2c = np.zeros(2)
+    for i in range(7):
+        m1c = m1c + m1d[i]; m2c = m2c + m2d[i]
+    t = 1. / 7
+    m1c = m1c * t; m2c = m2c * t
+    scale1 = 0.0; scale2 = 0.0
+    for i in range(7):
+        scale1 += np.sqrt((m1d[i][0] - m1c[0]) * (m1d[i][0] - m1c[0]) + (m1d[i][1] - m1c[1]) * (m1d[i][1] - m1c[1]))
+        scale2 += np.sqrt((m2d[i][0] - m2c[0]) * (m2d[i][0] - m2c[0]) + (m2d[i][1] - m2c[1]) * (m2d[i][1] - m2c[1]))
+    scale1 *= t; scale2 *= t
+    if scale1 < 1.1920928955078125e-07 or scale2 < 1.1920928955078125e-07:
+        return []
+    scale1 = np.sqrt(2.) / scale1; scale2 = np.sqrt(2.) / scale2
     A = np.zeros((7, 9))
     for i in range(7):
-        x0, y0 = float(m1[i][0]), float(m1[i][1]); x1, y1 = float(m2[i][0]), float(m2[i][1])
+        x0 = (m1d[i][0] - m1c[0]) * scale1; y0 = (m1d[i][1] - m1c[1]) * scale1
+        x1 = (m2d[i][0] - m2c[0]) * scale2; y1 = (m2d[i][1] - m2c[1]) * scale2
         A[i] = [x1 * x0, x1 * y0, x1, y1 * x0, y1 * y0, y1, x0, y0, 1]
     _, _, Vt = np.linalg.svd(A, full_matrices=True)
     f1, f2 = opencv_null_basis(Vt[7], Vt[8])
@@ -141,7 +160,18 @@ def run_7point(m1, m2):
         else:
             F[8] = 0.0
         F[:8] = f1[:8] * lam + f2[:8] * mu
-        Fs.append(F)
+        # de-normalise: T2^T F T1 with T = [[s, 0, -s cx], [0, s, -s cy], [0, 0, 1]], then F(3,3) = 1
+        M = np.zeros(9)
+        for j in range(3):
+            M[j] = scale2 * F[j]; M[3 + j] = scale2 * F[3 + j]
+            M[6 + j] = (-scale2 * m2c[0]) * F[j] + (-scale2 * m2c[1]) * F[3 + j] + F[6 + j]
+        G = np.zeros(9)
+        for i in range(3):
+            G[3 * i] = M[3 * i] * scale1; G[3 * i + 1] = M[3 * i + 1] * scale1
+            G[3 * i + 2] = M[3 * i] * (-scale1 * m1c[0]) + M[3 * i + 1] * (-scale1 * m1c[1]) + M[3 * i + 2]
+        if abs(G[8]) > 1.1920928955078125e-07:
+            G = G * (1. / G[8])
+        Fs.append(G)
     return Fs
 
 

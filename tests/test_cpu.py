@@ -91,7 +91,26 @@ def test_ransac_restatement_matches_cv2():
         p1, p2 = x1.astype(np.float32), x2.astype(np.float32)
         _, m = cv2.findFundamentalMat(p1, p2, cv2.FM_RANSAC, 1.0, 0.99)
         bad += not np.array_equal(m.reshape(-1), find_fundamental_ransac_mask(p1, p2))
-    assert bad <= 1          # ties between equally good models of one sample are resolved like OpenCV
+    assert bad == 0          # ties between equally good models of one sample are resolved like OpenCV
+
+
+def test_ransac_tie_between_roots_of_one_sample_resolved_like_cv2():
+    """tests/golden/ransac_tie_case.npz: a tracked-feature set (sequence 1, frame 13 of a 124-frame run) whose first
+    RANSAC sample has two roots with 157 inliers each.  OpenCV 4.13's run7Point Hartley-normalises the sample, which fixes
+    the ORDER of the roots; the first one wins.  (cv2 mask stored in the fixture, regenerated here as a cross-check.)"""
+    import cv2
+    from oracle.ransac import find_fundamental_ransac_mask, run_7point
+    d = np.load(os.path.join(ROOT, "tests", "golden", "ransac_tie_case.npz"))
+    p1, p2 = d["p1"].astype(np.float32), d["p2"].astype(np.float32)
+    _, m = cv2.findFundamentalMat(p1, p2, cv2.FM_RANSAC, 1.0, 0.99)
+    assert np.array_equal(m.reshape(-1), d["cv"].reshape(-1))
+    assert np.array_equal(find_fundamental_ransac_mask(p1, p2).reshape(-1), d["cv"].reshape(-1))
+    idx = [15, 64, 11, 120, 90, 71, 29]
+    Fc, _ = cv2.findFundamentalMat(p1[idx], p2[idx], cv2.FM_7POINT)
+    Fs = run_7point(p1[idx], p2[idx])
+    assert Fc.shape[0] == 3 * len(Fs)
+    for k, F in enumerate(Fs):
+        assert np.allclose(Fc[3 * k:3 * k + 3].ravel(), F, rtol=1e-7, atol=1e-10)
 
 
 def test_opencv_null_basis_matches_svdecomp():
