@@ -33,7 +33,13 @@ B0 = W_IMG * H_IMG
 # FP64 peak is not in MEASURED_PEAKS.json (bf16 + HBM only): nominal B200 FP64 vector rate, stated as such.
 FP64_PEAK_TF = 37.0
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
-NCU_TRAFFIC = {}
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch over 64 sequences, from the `ncu --set full` captures summarised
+# in profiles/r1g_ncu_summary.md (scripts/gpu_profile.sh); bytes per SEQUENCE per launch, scaled by the sequences a launch covers
+NCU_TRAFFIC_PER_SEQ = {"lk_kernel": (55.305472e6 + 1.048832e6) / 64, "be_chol_kernel": 1.491712e6 / 64, "be_gemm_kernel": 24.881408e6 / 64,
+                       "orb_kernel": (37.840128e6 + 0.019968e6) / 64, "mineig_kernel": (47.904e6 + 45.15072e6) / 64,
+                       "candidates_kernel": (115.406592e6 + 4.700416e6) / 64, "clahe_apply_kernel": (24.376576e6 + 0.219904e6) / 64,
+                       "blur7_kernel": (24.89728e6 + 0.01664e6) / 64, "ransac_kernel": 0.26752e6 / 64, "be_feature_kernel": (1.123072e6 + 0.026368e6) / 64,
+                       "be_trsm_kernel": 6.039296e6 / 64, "be_propagate_kernel": 2.5344e6 / 64, "select_kernel": 3.261184e6 / 64}
 
 
 def load_cfg(args):
@@ -429,17 +435,32 @@ def main():
             else:
                 ach = mdl[1] / (per_launch_ms * 1e-3) / 1e12
                 roofs[kname] = dict(bound="fp64", achieved=ach, peak=FP64_PEAK_TF, unit="TFLOP/s", frac=ach / FP64_PEAK_TF, flops_per_launch=mdl[1], basis=mdl[2])
-        roof = dict(kernel=dom, bound="hbm", achieved=None, peak=hbm_peak, unit="GB/s", frac=None, traffic=NCU_TRAFFIC.get(dom), peak_source=peak_src,
+        roof = dict(kernel=dom, bound="hbm", achieved=None, peak=hbm_peak, unit="GB/s", frac=None, traffic=(NCU_TRAFFIC_PER_SEQ[dom] * (S // NSUB) if dom in NCU_TRAFFIC_PER_SEQ else None),
+                    traffic_source="profiles/r1g_ncu_summary.md (ncu --set full, cold cache, per launch)", peak_source=peak_src,
                     ms_per_launch=dom_ms / max(dom_n, 1))
         if dom in roofs:
             roof.update({kk: roofs[dom][kk] for kk in ("bound", "achieved", "peak", "unit", "frac")})
             roof["basis"] = roofs[dom]["basis"]
+        # step-level roofline = sum_k launches_k * max(bytes_k / BW_hbm, flops_k / peak_fp64) over the measured kernel time
+        bound_ms = 0.0
+        for kname, v in top:
+            if kname in roofs:
+                rk = roofs[kname]
+                per = (rk["algorithmic_bytes_per_launch"] / (hbm_peak * 1e9) if rk["bound"] == "hbm" else rk["flops_per_launch"] / (FP64_PEAK_TF * 1e12)) * 1e3
+                bound_ms += per * v[1]
+        step_roof = dict(bound_ms=bound_ms, measured_kernel_ms=tot, frac=bound_ms / tot,
+                         note="kernels without a byte/flop model (bookkeeping, <10% of the time) contribute 0 to bound_ms")
+        # per-frame EKF-update time (BASELINE metric, second half): back-end kernels of the profiled frames per published batch frame
+        be_ms = sum(v[0] for kname, v in prof.items() if kname.startswith("be_"))
+        n_pub = max(pstats[3] / float(S), 1e-9)                      # published (sequence, frame) messages / sequences
+        ekf_ms = dict(batch_ms_per_published_frame=be_ms / n_pub, per_sequence_ms=be_ms / n_pub / S,
+                      note="sum of be_* kernel durations over the profiled frames; batch of %d sequences in %d sub-batches" % (S, NSUB))
         line = dict(metric="batched VIO frames/sec", value=value, unit="frames/s", n_gpus=world, steps=K, warmup=Wm,
                     ms_per_step=ms_dev / K, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="u8+f32 front end, f64 filter", data="synthetic", config=config,
                     e2e=dict(value=e2e_val, unit="frames/s", h2d_bytes_per_step=int(S * B0 + S * 10 * 56), d2h_bytes_per_step=int(S * 17 * 8 + S * 32 * 4 + S)),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, kernels=kernel_share, kernel_rooflines=roofs, work_counters=pstats,
-                    ekf_update_ms_per_seq=None, cpu_baseline=cpu_baseline, gen_seconds=t_gen, wall_dev_s=wall, wall_e2e_s=wall_e2e)
+                    ekf_update_ms=ekf_ms, step_roofline=step_roof, cpu_baseline=cpu_baseline, gen_seconds=t_gen, wall_dev_s=wall, wall_e2e_s=wall_e2e)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -1,9 +1,9 @@
 #!/bin/bash
 # ncu evidence for profiles/: launch list (shares) + full captures of the dominant kernels. Run via gpurun.
-# Frames 66-67 of a 70-frame replay: a full 30-pose window, one publishing frame (QR + both EKF updates active).
+# Frames 64-71 of a 74-frame replay: a full 30-pose window, four publishing frames (QR + both EKF updates + pruning active).
 # The replay brackets those frames with cuProfilerStart/Stop, so ncu (--profile-from-start off) sees nothing else.
 TAG=${1:-r1}
-export S=64 NF=70 PF=66 PN=2
+export S=64 NF=74 PF=64 PN=8
 python scripts/profile_driver.py gen
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv \
     python scripts/profile_driver.py run > gpurun_out/ncu_launches_${TAG}.log 2>&1

@@ -36,7 +36,7 @@ for row in csv.DictReader(lines):
     k = row["Kernel Name"].split("(")[0].replace("<unnamed>::", "")
     v = float(row["Metric Value"].replace(",", "")) * {"ns": 1, "us": 1e3, "ms": 1e6}.get(row["Metric Unit"], 1)
     agg.setdefault(k, [0.0, 0]); agg[k][0] += v; agg[k][1] += 1; tot += v
-out.append("\n## launch list — two consecutive steady-state frames (one publishing), 64 sequences, `--metrics gpu__time_duration.sum`\n")
+out.append("\n## launch list — eight consecutive steady-state frames (four publishing), 64 sequences, `--metrics gpu__time_duration.sum`\n")
 out.append("total %.1f us over %d launches (cold-cache, serialised: compare SHARES)\n\n| kernel | launches | us/launch | share |\n|---|---|---|---|" % (tot / 1e3, sum(v[1] for v in agg.values())))
 for k, (v, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     out.append("| %s | %d | %.1f | %.3f |" % (k, n, v / 1e3 / n, v / tot))
