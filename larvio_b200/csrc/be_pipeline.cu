@@ -1373,11 +1373,11 @@ __global__ void __launch_bounds__(1024) be_chol_kernel(BeView v) {
       col[i] = x;
     }
     __syncthreads();
-    const int n = r - j - 1;
-    // trailing update of the lower triangle: rows a in (j, r), columns b in (j, a]
-    for (int e = tid; e < n * n; e += 1024) {
-      const int a = j + 1 + e / n, b2 = j + 1 + e % n;
-      if (b2 <= a) LP(a, b2) -= col[a] * col[b2];
+    // trailing update of the lower triangle: rows a in (j, r) over the warps, columns b in (j, a] over the lanes
+    for (int a = j + 1 + (tid >> 5); a < r; a += 32) {
+      const double ca = col[a];
+      double* row = &LP(a, 0);
+      for (int b2 = j + 1 + (tid & 31); b2 <= a; b2 += 32) row[b2] -= ca * col[b2];
     }
     __syncthreads();
   }
@@ -1417,10 +1417,10 @@ __global__ void __launch_bounds__(512) be_chol_gmem_kernel(BeView v, int min_r) 
       csm[i] = x;
     }
     __syncthreads();
-    const int n = r - j - 1;
-    for (int e = tid; e < n * n; e += 512) {
-      const int a = j + 1 + e / n, b = j + 1 + e % n;
-      if (b <= a) S[(size_t)a * LD + b] -= csm[a] * csm[b];
+    for (int a = j + 1 + (tid >> 5); a < r; a += 16) {
+      const double ca = csm[a];
+      double* row = S + (size_t)a * LD;
+      for (int b = j + 1 + (tid & 31); b <= a; b += 32) row[b] -= ca * csm[b];
     }
     __syncthreads();
   }
