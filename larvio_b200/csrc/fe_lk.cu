@@ -31,6 +31,7 @@ struct alignas(16) WarpSmem {
   short dd[NPIX + 7];                      // 896  I_t per iteration
   union {
     struct { uint8_t tile[TILE * TILE]; short2 dtile[DT * DT]; } st;   // 576 + 1936 (window set-up only)
+    alignas(16) float termA[3 * NTERM_A];  // 5328
     alignas(16) float termB[2 * NTERM_B];  // 2208
   } u;
 };
@@ -94,7 +95,7 @@ struct LkArgs {
 };
 
 struct LkArgs2 { LkArgs a[2]; };
-__global__ void __launch_bounds__(WARPS * 32, 8) lk_kernel(const __grid_constant__ LkArgs2 aa) {
+__global__ void __launch_bounds__(WARPS * 32) lk_kernel(const __grid_constant__ LkArgs2 aa) {
   __shared__ WarpSmem sm[WARPS];
   const LkArgs& a = aa.a[blockIdx.z];
   const int s = blockIdx.y;
@@ -180,33 +181,19 @@ __global__ void __launch_bounds__(WARPS * 32, 8) lk_kernel(const __grid_constant
       w.dIw[p] = make_short2((short)ix, (short)iy);
     }
     __syncwarp();
-    // A11, A12, A22 in OpenCV's lane order: chain lane L < 15 owns accumulator L % 5 of sum L / 5 and forms its terms
-    // on the fly from dIw (set-up runs once per level, so the 15 serial chains need no staged term buffer)
-    float chainv = 0.f;
-    if (lane < 15) {
-      const int which = lane / 5, acc = lane % 5;
-      if (acc < 4) {
-        for (int y = 0; y < WIN; ++y) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const short2 d = w.dIw[y * WIN + acc + 4 * q];
-            const float fx = (float)d.x, fy = (float)d.y;
-            const float t = which == 0 ? __fmul_rn(fx, fx) : (which == 1 ? __fmul_rn(fx, fy) : __fmul_rn(fy, fy));
-            chainv = __fadd_rn(chainv, t);
-          }
-        }
-      } else {
-        for (int y = 0; y < WIN; ++y) {
-#pragma unroll
-          for (int x = 16; x < WIN; ++x) {
-            const short2 d = w.dIw[y * WIN + x];
-            const float fx = (float)d.x, fy = (float)d.y;
-            const float t = which == 0 ? __fmul_rn(fx, fx) : (which == 1 ? __fmul_rn(fx, fy) : __fmul_rn(fy, fy));
-            chainv = __fadd_rn(chainv, t);
-          }
-        }
-      }
+    // terms of A11, A12, A22 in OpenCV's lane order (the tile/dtile staging area is dead from here on)
+    for (int p = lane; p < NPIX; p += 32) {
+      const int y = p / WIN, x = p - y * WIN;
+      const short2 d = w.dIw[p];
+      const float fx = (float)d.x, fy = (float)d.y;
+      const int slot = (x < 16) ? ((x & 3) * (WIN * 4) + y * 4 + (x >> 2)) : (WIN * 16 + y * 5 + (x - 16));
+      w.u.termA[slot] = __fmul_rn(fx, fx);
+      w.u.termA[NTERM_A + slot] = __fmul_rn(fx, fy);
+      w.u.termA[2 * NTERM_A + slot] = __fmul_rn(fy, fy);
     }
+    __syncwarp();
+    float chainv = 0.f;
+    if (lane < 15) chainv = run_chain<4>(w.u.termA + (lane / 5) * NTERM_A, lane % 5);
     const float FLT_SCALE = 1.f / (float)(1 << 20);
     float A11 = __fmul_rn(combine_chains(chainv, 0), FLT_SCALE);
     float A12 = __fmul_rn(combine_chains(chainv, 5), FLT_SCALE);
