@@ -214,7 +214,7 @@ def main():
     ap.add_argument("--window", type=int, default=30)
     ap.add_argument("--cpu-frames", type=int, default=16, help="frames per sequence of the bounded cpu_baseline sample")
     ap.add_argument("--profile-steps", type=int, default=8)
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=4,
                     help="sub-batches per GPU, each an independent handle/stream driven by its own host thread")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -225,7 +225,9 @@ def main():
     cfg = load_cfg(args)
     workload = "configs[2]: %d batched synthetic 752x480@20Hz+200Hz-IMU sequences per GPU, %d tracks, %d-pose window, MSCKF-only" % (S, args.tracks, args.window)
     config = dict(workload=workload, sequences_per_gpu=S, sub_batches_per_gpu=args.streams, tracks=args.tracks, window=args.window, image="752x480 u8",
-                  l2_policy="each step reads a fresh %.1f MB image batch and touches >250 MB of per-sequence state (> 126 MB L2)" % (S * B0 / 1e6))
+                  l2_policy="each step reads a fresh %.1f MB image batch and touches >250 MB of per-sequence state (> 126 MB L2)" % (S * B0 / 1e6),
+                  inputs=("one pool of %d seeded sequences (seed 1234+i)" % S) + ("" if world == 1 else
+                          ", rendered cooperatively by the %d ranks, exchanged over NCCL, replayed on every GPU rotated by rank*%d/%d" % (world, S, world)))
     ncores = os.cpu_count() or 1
 
     # ------------------------------------------------------------------ reference arm
@@ -251,9 +253,14 @@ def main():
 
     # ------------------------------------------------------------------ our arm
     n_frames = Wm + K + args.profile_steps
-    seq_ids = [rank * S + s for s in range(S)]
+    # One pool of S seeded sequences per job.  With N ranks every rank renders S/N of them on its share of the host
+    # cores (before CUDA is touched: the generator forks), the pool is exchanged with one NCCL all_gather per field,
+    # and rank r replays the pool rotated by r*S/N - so host-side image synthesis does not grow with the GPU count
+    # while every GPU still steps S distinct sequences.
+    from larvio_b200 import dist as ldist
+    seq_ids = ldist.shard_sequences(S, rank, world) if world > 1 else list(range(S))
     t_gen = time.time()
-    seqs = generate(cfg.raw, seq_ids, n_frames, max(1, ncores // max(world, 1)))
+    seqs = generate(cfg.raw, seq_ids, n_frames, max(1, ncores // max(world, 1))) if seq_ids else []
     t_gen = time.time() - t_gen
     cpu_baseline = None
     if rank == 0 and world == 1:
@@ -272,6 +279,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        pool = ldist.share_sequences(seqs, S, rank, world, device=torch.device("cuda", local_rank))
+        rot = (rank * S) // world
+        seqs = pool[rot:] + pool[:rot]
     NSUB = max(1, min(args.streams, S))
     bounds = [(S * i) // NSUB for i in range(NSUB + 1)]          # sub-batch i owns sequences [bounds[i], bounds[i+1])
 

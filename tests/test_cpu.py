@@ -292,7 +292,17 @@ def _dist_worker(rank, world, port, q):
     states = torch.tensor([[float(i)] * 17 for i in ids], dtype=torch.float64)
     allst = ld.gather_states(states, 10, rank, world)
     cfgt = ld.broadcast_config_bytes(b"abc" if rank == 0 else None, rank)
-    q.put((rank, ids, None if allst is None else allst[:, 0].tolist(), cfgt))
+    # cooperative pool of 5 tiny "sequences" (ragged IMU lengths, uneven shards 3 + 2)
+    from types import SimpleNamespace
+    import numpy as np
+    def mk(i):
+        return SimpleNamespace(images=np.full((2, 4, 6), i, np.uint8), img_t=np.array([i, i + 0.05]), imu=np.full((3 + i, 7), float(i)),
+                               gt_p=np.full((2, 3), float(i)), gt_q=np.tile([0., 0., 0., 1.], (2, 1)), gt_v=np.zeros((2, 3)),
+                               gyro_bias=np.full(3, float(i)), acc_bias=np.zeros(3))
+    pool = ld.share_sequences([mk(i) for i in ld.shard_sequences(5, rank, world)], 5, rank, world)
+    pool_ok = len(pool) == 5 and all(int(s.images[0, 0, 0]) == i and s.imu.shape == (3 + i, 7) and float(s.imu[-1, 0]) == i
+                                     and float(s.gyro_bias[0]) == i for i, s in enumerate(pool))
+    q.put((rank, ids, None if allst is None else allst[:, 0].tolist(), cfgt, pool_ok))
     dist.destroy_process_group()
 
 
@@ -310,3 +320,4 @@ def test_shard_and_gather_two_ranks_gloo():
     assert out[0][1] == [0, 1, 2, 3, 4] and out[1][1] == [5, 6, 7, 8, 9]
     assert out[0][2] == [float(i) for i in range(10)] and out[1][2] is None
     assert out[0][3] == b"abc" and out[1][3] == b"abc"
+    assert out[0][4] and out[1][4]
