@@ -124,6 +124,20 @@ int lvb_synchronize(LvbHandle* h);
 int lvb_set_initial_state(LvbHandle* h, int seq, double t, const double* q_xyzw, const double* p,
                           const double* v, const double* bg, const double* ba);
 
+/* Inclinometer (static-scene) initialiser, HOST side, one object per sequence: StaticInitializer::tryIncInit +
+ * assignInitialState (src/StaticInitializer.cpp:13-161) as FlexibleInitializer::tryIncInit runs them from
+ * LarVio::processFeatures until gravity is set (src/larvio.cpp:375-391; the dynamic initialiser is out of scope).
+ * Feed it every published feature message (lvb_process_images output) with the caller's IMU buffer.  Returns 1 once
+ * static_duration*pub_frequency consecutive static messages were seen: state17 = t, q(4), p(3), v(3), bg(3), ba(3)
+ * goes to lvb_set_initial_state, *n_consumed leading IMU samples are to be erased from the caller's buffer
+ * (StaticInitializer.cpp:149-150) and gyro_old/acc_old are the sample the propagation will start from.
+ * Returns 0 while not initialised, <0 on error.  Needs no GPU. */
+typedef struct LvbStaticInit LvbStaticInit;
+LvbStaticInit* lvb_static_init_create(const LvbConfig* cfg);
+void lvb_static_init_destroy(LvbStaticInit* s);
+int lvb_static_init_try(LvbStaticInit* s, const LvbFeature* feat, int n_feat, double t_msg, const LvbImu* imu,
+                        int n_imu, double* state17, double* gyro_old3, double* acc_old3, int* n_consumed);
+
 /* getTbw/getVel/getPpose/getPvel: q[4] p[3] v[3] bg[3] ba[3] P_pose[36] P_vel[9], plus time. */
 int lvb_get_state(LvbHandle* h, int seq, double* t, double* q_xyzw, double* p, double* v, double* bg,
                   double* ba, double* P_pose36, double* P_vel9);

@@ -77,9 +77,15 @@ EXPORTED_SYMBOLS = [
     "lvb_parse_config", "lvb_create", "lvb_create_from_file", "lvb_destroy", "lvb_last_error",
     "lvb_feature_capacity", "lvb_n_seq", "lvb_process_images", "lvb_process_features", "lvb_step",
     "lvb_synchronize", "lvb_set_initial_state", "lvb_get_state", "lvb_get_states", "lvb_get_window",
-    "lvb_get_covariance", "lvb_get_calibration", "lvbk_pyramid", "lvbk_lk", "lvbk_orb", "lvbk_detect", "lvbk_undistort",
+    "lvb_get_covariance", "lvb_get_calibration", "lvb_static_init_create", "lvb_static_init_destroy", "lvb_static_init_try", "lvbk_pyramid", "lvbk_lk", "lvbk_orb", "lvbk_detect", "lvbk_undistort",
     "lvbk_ransac", "lvb_launch_count", "lvb_profile_enable", "lvb_profile_reset", "lvb_profile_get", "lvb_get_stats", "lvb_debug_icore",
 ]
+
+
+if hasattr(_lib, "lvb_static_init_create"):
+    _lib.lvb_static_init_create.restype = C.c_void_p
+    _lib.lvb_static_init_destroy.restype = None
+    _lib.lvb_static_init_try.restype = C.c_int
 
 
 def _check(rc: int):
@@ -95,6 +101,39 @@ def parse_config(path: str) -> LvbConfig:
     c = LvbConfig()
     _check(_lib.lvb_parse_config(path.encode(), C.byref(c)))
     return c
+
+
+class StaticInitializer:
+    """Host-side inclinometer initialiser of ONE sequence (StaticInitializer.cpp behind larvio.cpp:375-391); needs no GPU.
+    try_init returns None until the scene was static for static_duration, then the start state for
+    Batch.set_initial_state plus the number of IMU samples the caller erases from its buffer."""
+
+    def __init__(self, cfg):
+        st = cfg.to_struct() if hasattr(cfg, "to_struct") else cfg
+        self._s = C.c_void_p(_lib.lvb_static_init_create(C.byref(st)))
+        if not self._s:
+            raise LarvioB200Error("lvb_static_init_create failed: " + _lib.lvb_last_error().decode())
+
+    def try_init(self, feat: np.ndarray, t_msg: float, imu: np.ndarray):
+        feat = np.ascontiguousarray(feat, FEATURE_DTYPE); imu = np.ascontiguousarray(imu, IMU_DTYPE)
+        st = np.zeros(17); g = np.zeros(3); a = np.zeros(3); n = C.c_int()
+        rc = _lib.lvb_static_init_try(self._s, _p(feat), len(feat), C.c_double(t_msg), _p(imu), len(imu), _p(st), _p(g), _p(a), C.byref(n))
+        if rc < 0:
+            _check(rc)
+        if rc == 0:
+            return None
+        return dict(t=st[0], q=st[1:5].copy(), p=st[5:8].copy(), v=st[8:11].copy(), bg=st[11:14].copy(), ba=st[14:17].copy(),
+                    gyro_old=g, acc_old=a, n_consumed=n.value)
+
+    def close(self):
+        if self._s:
+            _lib.lvb_static_init_destroy(self._s); self._s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Batch:

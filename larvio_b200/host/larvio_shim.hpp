@@ -79,11 +79,19 @@ class ImageProcessor {
 class LarVio {
  public:
   LarVio(std::string& config_file, std::shared_ptr<Session> s = nullptr)
-      : s_(s ? s : std::make_shared<Session>(config_file)) {}
-  bool initialize() { return s_->open(); }
-  // what FlexibleInitializer::tryIncInit leaves behind (larvio.cpp:376-386); the initialisers are out of scope
+      : s_(s ? s : std::make_shared<Session>(config_file)), cfg_(config_file) {}
+  ~LarVio() { if (init_) lvb_static_init_destroy(init_); }
+  bool initialize() {
+    if (!s_->open()) return false;
+    LvbConfig c;
+    if (lvb_parse_config(cfg_.c_str(), &c) != LVB_OK) return false;
+    init_ = lvb_static_init_create(&c);
+    return init_ != nullptr;
+  }
+  // what FlexibleInitializer::tryIncInit leaves behind (larvio.cpp:376-386), for callers that start the filter themselves
   bool setInitialState(double t, const Pose& T_b_w, const double v[3], const double bg[3], const double ba[3]) {
-    return lvb_set_initial_state(s_->h(), 0, t, T_b_w.q_xyzw, T_b_w.p, v, bg, ba) == LVB_OK;
+    gravity_set_ = lvb_set_initial_state(s_->h(), 0, t, T_b_w.q_xyzw, T_b_w.p, v, bg, ba) == LVB_OK;
+    return gravity_set_;
   }
   // processFeatures(msg, imu_buffer): consumed samples are erased from the caller's vector (larvio.cpp:510-512)
   bool processFeatures(MonoCameraMeasurementPtr msg, std::vector<ImuData>& imu) {
@@ -95,6 +103,15 @@ class LarVio {
     std::vector<LvbFeature> f(msg->features.size() ? msg->features.size() : 1);
     for (size_t i = 0; i < msg->features.size(); ++i) std::memcpy(&f[i], &msg->features[i], sizeof(LvbFeature));
     int n_imu = (int)imu.size(), n_feat = (int)msg->features.size(); uint8_t valid = 1, ok = 0; double t = msg->timeStampToSec;
+    if (!gravity_set_) {                                            // larvio.cpp:375-391 (static initialiser only)
+      double st[17], g0[3], a0[3]; int used = 0;
+      if (lvb_static_init_try(init_, f.data(), n_feat, t, b.data(), n_imu, st, g0, a0, &used) != 1) return false;
+      if (lvb_set_initial_state(s_->h(), 0, st[0], st + 1, st + 5, st + 8, st + 11, st + 14) != LVB_OK) return false;
+      gravity_set_ = true;
+      imu.erase(imu.begin(), imu.begin() + used);                   // StaticInitializer.cpp:149-150
+      b.erase(b.begin(), b.begin() + used); n_imu -= used;
+      if (b.empty()) b.resize(1);
+    }
     if (lvb_process_features(s_->h(), &valid, &t, f.data(), &n_feat, (int)f.size(), b.data(), &n_imu, (int)b.size(), &ok) != LVB_OK) return false;
     imu.erase(imu.begin(), imu.begin() + ((int)imu.size() - n_imu));
     return ok != 0;
@@ -111,6 +128,9 @@ class LarVio {
   }
  private:
   std::shared_ptr<Session> s_;
+  std::string cfg_;
+  LvbStaticInit* init_ = nullptr;
+  bool gravity_set_ = false;
 };
 
 }  // namespace larvio

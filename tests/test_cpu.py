@@ -261,6 +261,102 @@ def test_oracle_hybrid_promotes_slam_features(cfg):
     assert max(r["pos_err"] for r in ok) < 0.25
 
 
+def test_static_initialiser_host_matches_oracle_and_truth(lib_built):
+    """the inclinometer initialiser (StaticInitializer.cpp) as host C++ behind the C ABI vs its numpy
+    restatement, on the feature messages of a sequence that stands still for 1.4 s: same decision frame, same state
+    (<= 1e-14), same consumed-IMU count; and against the truth: roll/pitch within the accelerometer noise/bias, gyro bias
+    within noise, zero velocity."""
+    from larvio_b200 import api, synth
+    from larvio_b200.config import Config
+    from oracle.frontend import ImageProcessorOracle
+    from oracle.initializer import StaticInitializerOracle
+    from oracle.backend import quat_to_rot
+    c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"))
+    seq = synth.make_sequence(c.raw, 3, 30, static_until=1.4)
+    fe = ImageProcessorOracle(c.raw)
+    host = api.StaticInitializer(c); orc = StaticInitializerOracle(c.raw)
+    assert orc.static_num == 10
+    imu = []; k = 0; done = None; n_msgs = 0
+    for j in range(30):
+        k2 = synth.imu_window(seq, k, seq.img_t[j]); imu.extend(seq.imu[k:k2].tolist()); k = k2
+        msg = fe.process_image(seq.images[j], seq.img_t[j], np.array(imu).reshape(-1, 7))
+        if msg is None:
+            continue
+        n_msgs += 1
+        feat = np.zeros(len(msg.ids), api.FEATURE_DTYPE)
+        feat["id"] = msg.ids
+        for ci, name in enumerate(["u", "v", "u_init", "v_init", "u_vel", "v_vel", "u_init_vel", "v_init_vel"]):
+            feat[name] = msg.data[:, ci]
+        rows = np.array(imu).reshape(-1, 7)
+        packed = np.zeros(len(rows), api.IMU_DTYPE); packed["t"] = rows[:, 0]; packed["gyro"] = rows[:, 1:4]; packed["acc"] = rows[:, 4:7]
+        a = host.try_init(feat, msg.t, packed)
+        b = orc.try_inc_init(msg.ids, msg.data[:, :2], msg.t, rows)
+        assert (a is None) == (b is None)
+        if a is not None:
+            done = (j, a, b); break
+    assert done is not None and n_msgs == 10            # the 10th published message of the standstill
+    j, a, b = done
+    for key in ("q", "p", "v", "bg", "ba", "gyro_old", "acc_old"):
+        assert np.abs(np.asarray(a[key]) - np.asarray(b[key])).max() < 1e-14, key
+    assert a["t"] == b["t"] and a["n_consumed"] == b["n_consumed"] and a["n_consumed"] > 150
+    # truth: the body z axis seen from the world agrees with the true attitude up to yaw (gravity gives roll/pitch only)
+    R_est = quat_to_rot(a["q"]); R_true = quat_to_rot(seq.gt_q[j])
+    assert np.degrees(np.arccos(np.clip(R_est[2] @ R_true[2], -1, 1))) < 0.5
+    assert np.abs(a["bg"] - seq.gyro_bias).max() < 2e-3 and np.abs(a["v"]).max() == 0.0
+    host.close()
+
+
+def test_euroc_ingest_and_trajectory_log_round_trip(tmp_path, cfg):
+    """a synthetic sequence written in the EuRoC ASL layout is read back like the reference's replay
+    driver reads it (DataReader.hpp, larvioMain.cpp:87-102), and the trajectory log has the reference's columns."""
+    import cv2
+    from larvio_b200 import synth, euroc
+    seq = synth.make_sequence(cfg.raw, 0, 6)
+    mav = tmp_path / "mav0"
+    (mav / "cam0" / "data").mkdir(parents=True); (mav / "imu0").mkdir(parents=True)
+    # EuRoC stamps are integer ns; start the IMU stream two samples before the first image like a real recording
+    img_ns = [int(round(t * 1e9)) for t in seq.img_t]
+    with open(mav / "cam0" / "data.csv", "w") as f:
+        f.write("#timestamp [ns],filename\n")
+        for ns, im in zip(img_ns, seq.images):
+            cv2.imwrite(str(mav / "cam0" / "data" / ("%d.png" % ns)), im)
+            f.write("%d,%d.png\n" % (ns, ns))
+    with open(mav / "imu0" / "data.csv", "w") as f:
+        f.write("#timestamp [ns],w_RS_S_x [rad s^-1],w_RS_S_y,w_RS_S_z,a_RS_S_x [m s^-2],a_RS_S_y,a_RS_S_z\n")
+        for r in seq.imu:
+            f.write("%d,%.17g,%.17g,%.17g,%.17g,%.17g,%.17g\n" % (int(round(r[0] * 1e9)), *r[1:]))
+    imu = euroc.load_imu_file(str(mav / "imu0" / "data.csv")); imgs = euroc.load_image_list(str(mav / "cam0" / "data.csv"))
+    assert len(imgs) == 6 and imu.shape == seq.imu.shape and np.abs(imu[:, 1:] - seq.imu[:, 1:]).max() == 0.0
+    al = euroc.find_first_align(imu, imgs)
+    assert al is not None and imu[al[1], 0] == imgs[al[0]][0]
+    got = list(euroc.Replay(str(mav)))
+    assert len(got) == 6 - al[0]
+    k = al[1]                                        # the 0.05 s rule of larvioMain.cpp:98-102 on the ns-quantised stamps
+    for (t, im, rows), j in zip(got, range(al[0], 6)):
+        assert np.array_equal(im, seq.images[j]) and abs(t - seq.img_t[j]) < 1e-9
+        k2 = k
+        while k2 < len(imu) and imu[k2, 0] - t < 0.05:
+            k2 += 1
+        assert np.array_equal(rows, imu[k:k2]) and 9 <= len(rows) <= 21
+        k = k2
+    log = euroc.TrajectoryLog(str(tmp_path / "out"))
+    log.set_take_off(1.25)
+    st = dict(t=2.5, q=np.array([0.1, -0.2, 0.3, 0.9]) / np.linalg.norm([0.1, -0.2, 0.3, 0.9]), p=np.array([1., 2., 3.]), v=np.array([.1, .2, .3]),
+              bg=np.array([1e-3, 2e-3, 3e-3]), ba=np.array([.01, .02, .03]))
+    T = np.array(cfg.raw["T_cam_imu"]["data"], np.float64).reshape(4, 4)
+    log.append(st, dict(R_imu_cam0=T[:3, :3], t_cam0_imu=-T[:3, :3].T @ T[:3, 3])); log.close()
+    rec = euroc.read_state_log(str(tmp_path / "out" / "msckf_2_state.txt"))
+    assert rec.shape == (1, 24) and rec[0, 0] == 1.25 and abs(rec[0, 1] - st["q"][3]) < 1e-6 and np.allclose(rec[0, 8:11], st["p"])
+    assert open(tmp_path / "out" / "msckf_2_takeoff.txt").read() == "1.250000000\n"
+
+
+def test_shim_header_compiles_against_the_public_header():
+    import subprocess
+    src = '#include "larvio_b200/host/larvio_shim.hpp"\nint main() { std::string c = "x.yaml"; larvio::LarVio v(c); larvio::ImageProcessor ip(c); (void)v; (void)ip; return 0; }\n'
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", ROOT, "-x", "c++", "-"], input=src.encode(), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+
+
 def test_update_invariant_to_orthogonal_row_transform(cfg):
     """What legitimises Householder/Givens QR on the GPU vs SPQR on the CPU."""
     from oracle.backend import LarVioOracle

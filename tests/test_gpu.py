@@ -124,6 +124,27 @@ def test_undistort_bit_exact(batch, cfg):
         assert np.array_equal(ref, batch.k_undistort(p, to_px))
 
 
+def test_undistort_equidistant_matches_cv2_fisheye(lib_built):
+    """SURVEY 8(f-3): distortion_model "equidistant" (config/mynteye.yaml) -> cv::fisheye::undistortPoints
+    (image_processor.cpp:1063-1065).  Same Newton iteration, clamp and stop rule; double tan/sqrt of the device may differ
+    from glibc in the last bit before the float cast, hence "nearly all identical, none off by more than a float ulp"."""
+    import cv2
+    from larvio_b200 import api
+    from larvio_b200.config import Config
+    D = dict(k1=-0.015661749636940888, k2=0.0028974710951617955, p1=0.0034539528765559204, p2=-0.006466223707507623)
+    c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), distortion_model="equidistant", distortion_coeffs=D)
+    b = api.Batch(c, n_seq=1)
+    K = np.array([[c['intrinsics']['fx'], 0, c['intrinsics']['cx']], [0, c['intrinsics']['fy'], c['intrinsics']['cy']], [0, 0, 1.0]])
+    Dv = np.array([D[k] for k in ('k1', 'k2', 'p1', 'p2')])
+    p = np.random.default_rng(2).uniform([0, 0], [752, 480], (2000, 2)).astype(np.float32)
+    for to_px in (False, True):
+        ref = cv2.fisheye.undistortPoints(p.reshape(-1, 1, 2), K, Dv, R=np.eye(3), P=(K if to_px else np.eye(3))).reshape(-1, 2)
+        got = b.k_undistort(p, to_px)
+        assert (ref == got).all(1).mean() > 0.995
+        assert np.abs(ref - got).max() <= (1e-4 if to_px else 1e-6)
+    b.close()
+
+
 def test_ransac_masks_match_opencv(batch):
     import cv2
     rng = np.random.default_rng(5)
@@ -292,6 +313,78 @@ def test_config_d_hybrid_with_online_calibration(lib_built):
     rep = _drive(cc, cs, 124, 'step')
     assert rep['steps'] >= 58 and rep['ok_mismatch'] == 0 and rep['imu_mismatch'] == 0
     assert rep['p'] < 1e-8 and rep['v'] < 1e-8 and rep['q'] < 1e-8 and rep['Prel'] < 1e-8 and rep['calib'] < 1e-9
+
+
+def test_config_e_capacity_400_tracks_50_pose_window(lib_built):
+    """BASELINE configs[4] per sequence: 400 tracks, 50-pose window, 4x5 SLAM grid (20 features).  46 frames fill 23 window
+    slots; the run checks the capacities (feature table, raw/stacked Jacobian rows, d up to 22 + 6*51 + 20) and parity."""
+    from larvio_b200 import synth
+    from larvio_b200.config import Config
+    ec = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), max_features_num=400, sw_size=50, aug_grid_rows=4, aug_grid_cols=5,
+                     min_distance=14)
+    es = [synth.make_sequence(ec.raw, s, 46) for s in range(2)]
+    rep = _drive(ec, es, 46, 'step')
+    assert rep['steps'] >= 40 and rep['ok_mismatch'] == 0 and rep['imu_mismatch'] == 0
+    assert rep['p'] < 1e-8 and rep['v'] < 1e-8 and rep['q'] < 1e-8 and rep['Prel'] < 1e-8
+
+
+def test_self_start_with_the_static_initialiser(lib_built):
+    """no injected state.  The sequence stands still for 1.4 s; the host-side inclinometer initialiser
+    (lvb_static_init_*) watches the feature messages of lvb_process_images, starts the filter through
+    lvb_set_initial_state, erases the consumed IMU samples, and lvb_process_features takes over (larvio.cpp:375-391).
+    The oracle does the same with its own restatement of StaticInitializer.cpp."""
+    from larvio_b200 import api, synth
+    from larvio_b200.config import Config
+    from oracle.frontend import ImageProcessorOracle
+    from oracle.backend import LarVioOracle
+    from oracle.initializer import StaticInitializerOracle
+    c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), max_features_in_one_grid=0, sw_size=16)
+    NF = 56
+    seq = synth.make_sequence(c.raw, 3, NF, static_until=1.4)
+    b = api.Batch(c, n_seq=1)
+    host_init = api.StaticInitializer(c); orc_init = StaticInitializerOracle(c.raw)
+    fe = ImageProcessorOracle(c.raw); be = LarVioOracle(c.raw)
+    imu_o = []; k = 0
+    buf = np.zeros((1, 512), api.IMU_DTYPE); n_buf = np.zeros(1, np.int32)
+    started = False; steps = 0; worst = 0.0
+    for j in range(NF):
+        k2 = synth.imu_window(seq, k, seq.img_t[j])
+        new = seq.imu[k:k2]; k = k2
+        imu_o.extend(new.tolist())
+        m = len(new); n0 = int(n_buf[0])
+        buf["t"][0, n0:n0 + m] = new[:, 0]; buf["gyro"][0, n0:n0 + m] = new[:, 1:4]; buf["acc"][0, n0:n0 + m] = new[:, 4:7]; n_buf[0] = n0 + m
+        msg = fe.process_image(seq.images[j], seq.img_t[j], np.array(imu_o).reshape(-1, 7))
+        feat, out_n, has = b.process_images(seq.images[j][None], np.array([seq.img_t[j]]), buf, n_buf)
+        assert bool(has[0]) == (msg is not None)
+        if msg is None:
+            continue
+        assert np.array_equal(feat[0, :out_n[0]]['id'], msg.ids)
+        if not started:
+            a = host_init.try_init(feat[0, :out_n[0]], seq.img_t[j], buf[0, :n_buf[0]])
+            o = orc_init.try_inc_init(msg.ids, msg.data[:, :2], msg.t, np.array(imu_o).reshape(-1, 7))
+            assert (a is None) == (o is None)
+            if a is None:
+                continue
+            assert a["n_consumed"] == o["n_consumed"] and np.abs(a["q"] - o["q"]).max() < 1e-12
+            b.set_initial_state(0, a["t"], a["q"], a["p"], a["v"], a["bg"], a["ba"])
+            be.set_initial_state(o["t"], o["q"], o["p"], o["v"], o["bg"], o["ba"])
+            nc = a["n_consumed"]                                          # StaticInitializer.cpp:149-150
+            buf[0, :n_buf[0] - nc] = buf[0, nc:n_buf[0]].copy(); n_buf[0] -= nc
+            del imu_o[:nc]
+            started = True
+        ok = b.process_features(has, np.array([seq.img_t[j]]), feat, out_n, buf, n_buf)
+        oko = be.process_features(msg, imu_o)
+        assert bool(ok[0]) == bool(oko) and int(n_buf[0]) == len(imu_o)
+        if oko:
+            st = b.get_state(0)
+            worst = max(worst, float(np.abs(st['p'] - be.imu_state.p).max()), float(np.abs(st['v'] - be.imu_state.v).max()))
+            P = b.get_covariance(0)
+            assert P.shape == be.P.shape and np.linalg.norm(P - be.P) / np.linalg.norm(be.P) < 1e-8
+            steps += 1
+    assert started and steps >= 12 and worst < 1e-8
+    # the filter started from gravity alone stays near the truth (the truth frame differs by the unobservable yaw only)
+    assert abs(np.linalg.norm(be.imu_state.p) - np.linalg.norm(seq.gt_p[NF - 1] - seq.gt_p[0])) < 0.3
+    b.close(); host_init.close()
 
 
 def test_gpu_against_committed_golden(cfg, seqs):
