@@ -2128,7 +2128,14 @@ int be_alloc(LvbHandle* h) {
   be->Dmax = be->LEG + 6 * be->Wcap + be->NFmax;
   be->LD = ((be->Dmax + 7) / 8) * 8;
   be->LDS = be->NFmax ? ((be->Dmax + 2 * be->NFmax + 16 * be->NFmax + 7) / 8) * 8 : be->LD;
-  be->RAWMAX = 4096; be->RMAX = 2048;
+  // row capacities of one measurement pass: every track that reaches max_track_len in the same frame contributes
+  // 2m raw / 2m-3 stacked rows (all N tracks born in the first frame do so together); overflow is reported (LVB_E_CAPACITY)
+  {
+    const int mlen = c.max_track_len > 2 ? c.max_track_len : 2;
+    const int raw = 2 * (mlen + 1) * be->N, stk = (2 * mlen - 3) * be->N + 32;
+    be->RAWMAX = raw > 4096 ? ((raw + 255) / 256) * 256 : 4096;
+    be->RMAX = stk > 2048 ? ((stk + 255) / 256) * 256 : 2048;
+  }
   be->imu_cap = 64;
   be->stats = h->fe.stats;
   const size_t S = be->S, T = be->T, LD = be->LD;
