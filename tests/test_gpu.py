@@ -179,7 +179,7 @@ def _drive(cfg, seqs, nf, mode, S=2):
     b = api.Batch(cfg, n_seq=S)
     fes = [ImageProcessorOracle(cfg.raw) for _ in range(S)]
     bes = [LarVioOracle(cfg.raw) for _ in range(S)]
-    feed = harness.ImuFeeder(seqs[:S], stride=256)     # 'fe' mode never erases consumed samples
+    feed = harness.ImuFeeder(seqs[:S], stride=256 if mode != 'fe' else 1024)     # 'fe' mode never erases consumed samples
     imu_o = [[] for _ in range(S)]; k = [0] * S
     inited = [False] * S
     rep = dict(msgs=0, id_mismatch=0, uv=0.0, vel=0.0, p=0.0, v=0.0, q=0.0, Prel=0.0, steps=0, ok_mismatch=0, imu_mismatch=0)
@@ -206,6 +206,8 @@ def _drive(cfg, seqs, nf, mode, S=2):
                 if len(g) != len(msgs[s].ids) or not np.array_equal(g['id'], msgs[s].ids):
                     rep['id_mismatch'] += 1
                     continue
+                if len(g) == 0:
+                    continue                      # an empty message (every track lost): ids compared above, nothing else to compare
                 uv = np.stack([g['u'], g['v'], g['u_init'], g['v_init']], 1); vel = np.stack([g['u_vel'], g['v_vel'], g['u_init_vel'], g['v_init_vel']], 1)
                 rep['uv'] = max(rep['uv'], float(np.abs(uv - msgs[s].data[:, :4]).max())); rep['vel'] = max(rep['vel'], float(np.abs(vel - msgs[s].data[:, 4:]).max()))
             continue
@@ -385,6 +387,36 @@ def test_self_start_with_the_static_initialiser(lib_built):
     # the filter started from gravity alone stays near the truth (the truth frame differs by the unobservable yaw only)
     assert abs(np.linalg.norm(be.imu_state.p) - np.linalg.norm(seq.gt_p[NF - 1] - seq.gt_p[0])) < 0.3
     b.close(); host_init.close()
+
+
+def _blackout_sequences(cfg):
+    """Sequence A loses every track for four frames mid-run (uniform grey images: LK's min-eigenvalue test fails for all
+    points and the detector finds no corner), then has to repopulate from nothing; sequence B gets a grey SECOND image, so
+    initializeFirstFeatures fails and the state machine falls back to FIRST_IMAGE (image_processor.cpp:160-172)."""
+    import copy
+    from larvio_b200 import synth
+    a = synth.make_sequence(cfg.raw, 0, 44); b = synth.make_sequence(cfg.raw, 1, 44)
+    a = copy.copy(a); b = copy.copy(b)
+    a.images = a.images.copy(); b.images = b.images.copy()
+    a.images[20:24] = 117
+    b.images[1] = 117
+    return [a, b]
+
+
+def test_frontend_survives_blackout_and_failed_second_image(cfg):
+    seqs2 = _blackout_sequences(cfg)
+    rep = _drive(cfg, seqs2, 44, 'fe')
+    assert rep['msgs'] >= 36 and rep['id_mismatch'] == 0
+    assert rep['uv'] == 0.0 and rep['vel'] == 0.0
+
+
+def test_filter_runs_through_empty_feature_messages(cfg):
+    """Same inputs through the fused path: during the blackout the published messages carry no feature at all, the filter
+    keeps propagating and augmenting on IMU alone (larvio.cpp:394-461 with an empty message), then re-acquires."""
+    seqs2 = _blackout_sequences(cfg)
+    rep = _drive(cfg, seqs2, 44, 'step')
+    assert rep['steps'] >= 36 and rep['ok_mismatch'] == 0 and rep['imu_mismatch'] == 0
+    assert rep['p'] < 1e-8 and rep['v'] < 1e-8 and rep['q'] < 1e-8 and rep['Prel'] < 1e-8
 
 
 def test_gpu_against_committed_golden(cfg, seqs):
