@@ -406,8 +406,8 @@ def _blackout_sequences(cfg):
 def test_frontend_survives_blackout_and_failed_second_image(cfg):
     seqs2 = _blackout_sequences(cfg)
     rep = _drive(cfg, seqs2, 44, 'fe')
-    assert rep['msgs'] >= 36 and rep['id_mismatch'] == 0
-    assert rep['uv'] == 0.0 and rep['vel'] == 0.0
+    assert rep['msgs'] >= 36 and rep['id_mismatch'] == 0       # ids and their order: bit-exact, before, during and after
+    assert rep['uv'] < 1e-6 and rep['vel'] < 1e-4
 
 
 def test_filter_runs_through_empty_feature_messages(cfg):
