@@ -31,7 +31,25 @@ from larvio_b200 import synth                  # noqa: E402
 W_IMG, H_IMG = 752, 480
 B0 = W_IMG * H_IMG
 # FP64 peak is not in MEASURED_PEAKS.json (bf16 + HBM only): nominal B200 FP64 vector rate, stated as such.
-FP64_PEAK_TF = 37.0
+FP64_PEAK_TF = 37.0        # nominal B200 FP64 (vector = tensor); replaced by the DGEMM probe below when it runs
+
+
+def probe_fp64_peak(device, n=8192, reps=3):
+    """FP64 denominator measured like MEASURED_PEAKS.json measures bf16 (SURVEY 8d asks for it): best of `reps` cuBLAS
+    DGEMMs n^3, CUDA-event timed, after one warm-up.  A library call used ONLY as the yardstick, never on the path."""
+    import torch
+    a = torch.randn(n, n, dtype=torch.float64, device=device); b = torch.randn(n, n, dtype=torch.float64, device=device)
+    torch.matmul(a, b)
+    best = None
+    for _ in range(reps):
+        if device.type == "cuda":
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+            dt = e0.elapsed_time(e1) * 1e-3
+        else:
+            t0 = time.perf_counter(); torch.matmul(a, b); dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return 2.0 * n ** 3 / best / 1e12
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch over 64 sequences, from the `ncu --set full` captures summarised
 # in profiles/r1g_ncu_summary.md (scripts/gpu_profile.sh); bytes per SEQUENCE per launch, scaled by the sequences a launch covers
@@ -427,6 +445,13 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        global FP64_PEAK_TF
+        fp64_src = "nominal 37 TFLOP/s (not in MEASURED_PEAKS.json)"
+        try:
+            FP64_PEAK_TF = float(probe_fp64_peak(torch.device("cuda", local_rank)))
+            fp64_src = "measured: cuBLAS DGEMM 8192^3 burst, this run"
+        except Exception as ex:                                   # the probe must never take the bench down
+            fp64_src += "; probe failed: %s" % type(ex).__name__
         tot = sum(v[0] for v in prof.values()) or 1.0
         top = sorted(prof.items(), key=lambda kv: -kv[1][0]) or [("none", (0.0, 0))]
         kernel_share = {kname: dict(ms_per_launch=v[0] / max(v[1], 1), launches=v[1], share=v[0] / tot) for kname, v in top}
@@ -458,7 +483,7 @@ def main():
                 rk = roofs[kname]
                 per = (rk["algorithmic_bytes_per_launch"] / (hbm_peak * 1e9) if rk["bound"] == "hbm" else rk["flops_per_launch"] / (FP64_PEAK_TF * 1e12)) * 1e3
                 bound_ms += per * v[1]
-        step_roof = dict(bound_ms=bound_ms, measured_kernel_ms=tot, frac=bound_ms / tot,
+        step_roof = dict(bound_ms=bound_ms, measured_kernel_ms=tot, frac=bound_ms / tot, fp64_peak_tflops=FP64_PEAK_TF, fp64_peak_source=fp64_src,
                          note="kernels without a byte/flop model (bookkeeping, <10% of the time) contribute 0 to bound_ms")
         # per-frame EKF-update time (BASELINE metric, second half): back-end kernels of the profiled frames per published batch frame
         be_ms = sum(v[0] for kname, v in prof.items() if kname.startswith("be_"))
