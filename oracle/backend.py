@@ -117,6 +117,7 @@ class Feature:
         self.id_anchor = -1
         self.invDepth = 0.0
         self.obs_anchor = np.zeros(3)
+        self.invParam = np.zeros(3)        # (x/z, y/z, 1/z) in the anchor camera frame (feature.hpp:231, 542, 711, 880)
         self.in_state = False
         self.ekf_feature = False
         self.totalObsNum = 0
@@ -244,6 +245,7 @@ class Feature:
             self.id_anchor = cam_ids[-1]
             self.invDepth = 1 / final[2]
             self.obs_anchor = np.array([final[0] * self.invDepth, final[1] * self.invDepth, 1.0])
+            self.invParam = np.array([final[0] / final[2], final[1] / final[2], 1 / final[2]])
         return valid
 
 
@@ -295,8 +297,11 @@ class LarVioOracle:
         self.feature_idp_dim = int(r["feature_idp_dim"])
         self.use_schmidt = bool(int(r["use_schmidt"]))
         self.hybrid = self.max_features * self.grid_rows * self.grid_cols != 0
-        if self.hybrid and (self.feature_idp_dim != 1 or self.use_schmidt):
-            raise NotImplementedError("hybrid mode is restated for feature_idp_dim 1 without Schmidt only")
+        if self.feature_idp_dim not in (1, 3):
+            self.feature_idp_dim = 3                                   # larvio.cpp:270-274
+        self.idp = self.feature_idp_dim
+        if self.hybrid and self.use_schmidt:
+            raise NotImplementedError("hybrid mode is restated without Schmidt nuisance states only")
         it = r["intrinsics"]
         fx, fy, cx, cy = float(it["fx"]), float(it["fy"]), float(it["cx"]), float(it["cy"])
         U, V = int(r["resolution_width"]), int(r["resolution_height"])
@@ -531,7 +536,7 @@ class LarVioOracle:
         sel = [0, 1, 2, 6, 7, 8]
         P12 = P[sel, :]
         P11 = P12[:, sel]
-        nf = len(self.feature_states)
+        nf = self.idp * len(self.feature_states)
         pe = d - nf                        # end of the pose block; SLAM features follow (larvio.cpp:768-793)
         order = list(range(pe)) + list(range(d, d + 6)) + list(range(pe, d))
         Pn = np.zeros((d + 6, d + 6))
@@ -579,7 +584,7 @@ class LarVioOracle:
         if d[-9] < self.zupt_max_feature_dis:
             self.zupt_events += 1
             if self.feature_states:                       # :2770-2782
-                nf = len(self.feature_states)
+                nf = self.idp * len(self.feature_states)
                 self.P = self.P[:-nf, :-nf]
                 for fid in self.feature_states:
                     ft = self.map_server[fid]
@@ -740,10 +745,11 @@ class LarVioOracle:
             old_fs = list(self.feature_states)
             n_old = len(old_fs) - len(ekf_new_ids)
             self.feature_states = old_fs[:n_old] + kept
+            idp = self.idp
             if kept:
-                keep_cols = list(range(d)) + [d + ekf_new_ids.index(fid) for fid in kept]
+                keep_cols = list(range(d)) + [d + idp * ekf_new_ids.index(fid) + c for fid in kept for c in range(idp)]
                 H_new = np.concatenate([b[1][:, keep_cols] for b in blocks]); r_new = np.concatenate([b[2] for b in blocks])
-                n_new = len(kept)
+                n_new = idp * len(kept)                         # new state COLUMNS (sz_new)
                 Hf = H_new[:, d:]
                 U_, _, _ = np.linalg.svd(Hf, full_matrices=True)
                 Vn = U_[:, n_new:]
@@ -822,7 +828,8 @@ class LarVioOracle:
             P = (P + P.T) / 2.0
         if n_new:
             nHHP = -HH @ P
-            P22 = -nHHP @ HH.T + self.feature_noise * np.diag(1.0 / (h2 * h2))
+            H22 = H_2.T @ H_2                                    # :1823-1825 (the FULL triangular factor here, unlike HH)
+            P22 = -nHHP @ HH.T + self.feature_noise * np.linalg.solve(H22, np.eye(n_new))
             Pn = np.zeros((d + n_new, d + n_new))
             Pn[:d, :d] = P; Pn[d:, :d] = nHHP; Pn[:d, d:] = nHHP.T; Pn[d:, d:] = P22
             P = (Pn + Pn.T) / 2.0
@@ -864,9 +871,57 @@ class LarVioOracle:
         for i, fid in enumerate(self.feature_states):
             ft = self.map_server[fid]
             a = self.aug[ft.id_anchor]
-            ft.invDepth += dx[base + i]
-            p_c = np.array([ft.obs_anchor[0] / ft.invDepth, ft.obs_anchor[1] / ft.invDepth, 1 / ft.invDepth])
+            if self.idp == 3:
+                ft.invParam = ft.invParam + dx[base + 3 * i:base + 3 * i + 3]
+                p_c = np.array([ft.invParam[0] / ft.invParam[2], ft.invParam[1] / ft.invParam[2], 1 / ft.invParam[2]])
+            else:
+                ft.invDepth += dx[base + i]
+                p_c = np.array([ft.obs_anchor[0] / ft.invDepth, ft.obs_anchor[1] / ft.invDepth, 1 / ft.invDepth])
             ft.position = quat_to_rot(a.q_cam) @ p_c + a.p_cam
+
+    # ---- measurementJacobian_ekf_3didp :984-1114 (no Schmidt: the anchor is always a window state)
+    def _meas_jacobian_3didp(self, sid, ft):
+        k = self.aug[sid]; a = self.aug[ft.id_anchor]
+        R_b2c = k.R_imu_cam0; t_c_b = k.t_cam0_imu
+        R_bk2w = quat_to_rot(k.q); R_w2bk = R_bk2w.T
+        R_w2ck = R_b2c @ R_w2bk; t_ck_w = k.p + R_bk2w @ t_c_b
+        R_ba2w = quat_to_rot(a.q); R_w2ba = R_ba2w.T
+        R_w2ca = R_b2c @ R_w2ba
+        f_ca = ft.invParam
+        if self.if_FEJ:
+            p_ca = R_b2c @ (R_w2ba @ (ft.position_FEJ - a.p_FEJ) - t_c_b)
+        else:
+            p_ca = np.array([f_ca[0] / f_ca[2], f_ca[1] / f_ca[2], 1 / f_ca[2]])
+        p_w = ft.position
+        z = ft.obs[sid]
+        p_ck = R_w2ck @ (p_w - t_ck_w)
+        r = z - np.array([p_ck[0] / p_ck[2], p_ck[1] / p_ck[2]])
+        if sid == ft.id_anchor:                                  # :1065-1073
+            H_f = np.zeros((2, 3)); H_f[0, 0] = 1; H_f[1, 1] = 1
+            return H_f, np.zeros((2, 6)), np.zeros((2, 6)), np.zeros((2, 6)), r
+        J_k = np.zeros((2, 3))
+        J_k[0, 0] = 1 / p_ck[2]; J_k[1, 1] = 1 / p_ck[2]
+        J_k[0, 2] = -p_ck[0] / (p_ck[2] * p_ck[2]); J_k[1, 2] = -p_ck[1] / (p_ck[2] * p_ck[2])
+        J_p = R_w2ck @ R_w2ca.T
+        p_baf_w = (ft.position_FEJ - a.p_FEJ) if self.if_FEJ else (p_w - a.p)
+        p_bkf_w = (ft.position_FEJ - k.p_FEJ) if self.if_FEJ else (p_w - k.p)
+        J_xa = np.zeros((3, 6)); J_xa[:, :3] = -R_w2ck @ skew(p_baf_w); J_xa[:, 3:] = R_w2ck
+        J_xk = np.zeros((3, 6)); J_xk[:, :3] = R_w2ck @ skew(p_bkf_w); J_xk[:, 3:] = -R_w2ck
+        J_e = np.zeros((3, 6))
+        Sk = skew(R_w2bk @ p_bkf_w - t_c_b)
+        Mx = R_w2bk @ R_w2ba.T @ skew(R_b2c.T @ p_ca)
+        J_e[:, :3] = R_b2c @ (Sk - Mx); J_e[:, 3:] = R_b2c @ (R_w2bk @ R_w2ba.T - np.eye(3))
+        J_f = np.eye(3)
+        J_f[0, 2] = -f_ca[0] / f_ca[2]; J_f[1, 2] = -f_ca[1] / f_ca[2]; J_f[2, 2] = -1 / f_ca[2]
+        J_f = J_f / f_ca[2]
+        return J_k @ J_p @ J_f, J_k @ J_xa, J_k @ J_xk, J_k @ J_e, r
+
+    def _meas_jacobian_idp(self, sid, ft):
+        """(H_f [2 x idp], H_a, H_x, H_e, r) of one observation of an in-state feature."""
+        if self.idp == 3:
+            return self._meas_jacobian_3didp(sid, ft)
+        H_f, H_a, H_x, H_e, r = self._meas_jacobian_1didp(sid, ft)
+        return H_f.reshape(2, 1), H_a, H_x, H_e, r
 
     # ---- measurementJacobian_ekf_1didp :1117-1244
     def _meas_jacobian_1didp(self, sid, ft):
@@ -902,16 +957,18 @@ class LarVioOracle:
 
     # ---- featureJacobian_ekf_new :1247-1338 (columns: current state + one per feature in feature_states)
     def _feature_jacobian_ekf_new(self, ft, state_ids):
-        valid = [sid for sid in state_ids if sid in ft.obs and sid != ft.id_anchor]
-        ncol = self.LEG + 6 * len(self.aug) + len(self.feature_states)
+        idp = self.idp
+        # the anchor's own observation is not used with 1-D inverse depth (:1260-1262)
+        valid = [sid for sid in state_ids if sid in ft.obs and not (idp == 1 and sid == ft.id_anchor)]
+        ncol = self.LEG + 6 * len(self.aug) + idp * len(self.feature_states)
         H = np.zeros((2 * len(valid), ncol)); r = np.zeros(2 * len(valid))
         order = sorted(self.aug.keys())
         a_idx = self.LEG + 6 * order.index(ft.id_anchor)
-        f_idx = self.LEG + 6 * len(self.aug) + self.feature_states.index(ft.id)
+        f_idx = self.LEG + 6 * len(self.aug) + idp * self.feature_states.index(ft.id)
         k = 0
         for sid in valid:
-            H_f, H_a, H_x, H_e, r_i = self._meas_jacobian_1didp(sid, ft)
-            H[k:k + 2, f_idx] = H_f
+            H_f, H_a, H_x, H_e, r_i = self._meas_jacobian_idp(sid, ft)
+            H[k:k + 2, f_idx:f_idx + idp] = H_f
             H[k:k + 2, a_idx:a_idx + 6] = H_a
             c = self.LEG + 6 * order.index(sid)
             H[k:k + 2, c:c + 6] = H_x
@@ -927,8 +984,9 @@ class LarVioOracle:
         sid = self.imu_state.id
         order = sorted(self.aug.keys())
         H = np.zeros((2, self.P.shape[1]))
-        H_f, H_a, H_x, H_e, r = self._meas_jacobian_1didp(sid, ft)
-        H[:, self.LEG + 6 * len(self.aug) + self.feature_states.index(ft.id)] = H_f
+        H_f, H_a, H_x, H_e, r = self._meas_jacobian_idp(sid, ft)
+        f_idx = self.LEG + 6 * len(self.aug) + self.idp * self.feature_states.index(ft.id)
+        H[:, f_idx:f_idx + self.idp] = H_f
         a_idx = self.LEG + 6 * order.index(ft.id_anchor)
         H[:, a_idx:a_idx + 6] = H_a
         c = self.LEG + 6 * order.index(sid)
@@ -942,8 +1000,8 @@ class LarVioOracle:
     def _rm_lost_features_cov(self, lost_ids):
         for fid in lost_ids:
             seq = self.feature_states.index(fid)
-            i0 = self.LEG + 6 * len(self.aug) + seq
-            keep = [i for i in range(self.P.shape[0]) if i != i0]
+            i0 = self.LEG + 6 * len(self.aug) + self.idp * seq
+            keep = [i for i in range(self.P.shape[0]) if not (i0 <= i < i0 + self.idp)]
             self.P = self.P[np.ix_(keep, keep)]
             self.feature_states.pop(seq)
             del self.map_server[fid]
@@ -960,6 +1018,60 @@ class LarVioOracle:
         for fid in self.feature_states:
             code = self._grid_code(self.map_server[fid].obs[self.imu_state.id])
             self.grid_map.setdefault(code, []).append(fid)
+
+    # ---- updateFeatureCov_3didp :2965-3122.  Literal restatement INCLUDING the reference's slip at :3000 and :3066: the
+    # "new" pose and its column block are looked up with old_state_id, so H_x_new overwrites H_x_old in the old block and
+    # the Jacobian never touches the new anchor's columns.
+    def _update_feature_cov_3didp(self, ft, old_id, new_id):
+        N = len(self.aug)
+        p_w = ft.position
+        R_b2c = self.imu_state.R_imu_cam0; t_c_b = self.imu_state.t_cam0_imu
+        o = self.aug[old_id]
+        R_b2w_old = quat_to_rot(o.q); R_c2w_old = quat_to_rot(o.q_cam)
+        if self.if_FEJ:
+            p_old = R_b2c @ (R_b2w_old.T @ (ft.position_FEJ - o.p_FEJ) - t_c_b)
+        else:
+            p_old = R_c2w_old.T @ (p_w - o.p_cam)
+        n = self.aug[old_id]                                       # sic (:3000)
+        R_b2w_new = quat_to_rot(n.q); R_w2b_new = R_b2w_new.T
+        R_w2c_new = quat_to_rot(n.q_cam).T
+        inv_new = ft.invParam
+        if self.if_FEJ:
+            p_bf_old = ft.position_FEJ - o.p_FEJ; p_bf_new = ft.position_FEJ - n.p_FEJ
+        else:
+            p_bf_old = p_w - o.p; p_bf_new = p_w - n.p
+        J_fp_new = np.eye(3)
+        J_fp_new[0, 2] = -inv_new[0]; J_fp_new[1, 2] = -inv_new[1]; J_fp_new[2, 2] = -inv_new[2]
+        J_fp_new = inv_new[2] * J_fp_new
+        J_p = R_w2c_new @ R_c2w_old
+        J_x_old = np.zeros((3, 6)); J_x_old[:, :3] = -R_w2c_new @ skew(p_bf_old); J_x_old[:, 3:] = R_w2c_new
+        J_x_new = np.zeros((3, 6)); J_x_new[:, :3] = R_w2c_new @ skew(p_bf_new); J_x_new[:, 3:] = -R_w2c_new
+        J_e = np.zeros((3, 6))
+        Sk = skew(R_w2b_new @ p_bf_new - t_c_b)
+        Mx = R_w2b_new @ R_b2w_old @ skew(R_b2c.T @ p_old)
+        J_e[:, :3] = R_b2c @ (Sk - Mx); J_e[:, 3:] = R_b2c @ (R_w2b_new @ R_b2w_old - np.eye(3))
+        J_pf_old = np.eye(3)
+        J_pf_old[0, 2] = -p_old[0]; J_pf_old[1, 2] = -p_old[1]; J_pf_old[2, 2] = -p_old[2]
+        J_pf_old = p_old[2] * J_pf_old
+        H_f_new = J_fp_new @ J_p @ J_pf_old
+        H_x_old = J_fp_new @ J_x_old; H_x_new = J_fp_new @ J_x_new; H_e = J_fp_new @ J_e
+        J = np.zeros((3, self.P.shape[1]))
+        order = sorted(self.aug.keys())
+        oc = order.index(old_id); nc = order.index(old_id)         # sic (:3066)
+        fc = self.feature_states.index(ft.id)
+        fi = self.LEG + 6 * N + 3 * fc
+        J[:, fi:fi + 3] = H_f_new
+        J[:, self.LEG + 6 * oc:self.LEG + 6 * oc + 6] = H_x_old
+        J[:, self.LEG + 6 * nc:self.LEG + 6 * nc + 6] = H_x_new
+        J[:, 15:21] = H_e
+        Pfl = J @ self.P
+        Pff = Pfl @ J.T
+        P = self.P
+        left = Pfl[:, :fi].copy(); right = Pfl[:, fi + 3:].copy()
+        P[fi:fi + 3, fi:fi + 3] = Pff
+        P[fi:fi + 3, :fi] = left; P[:fi, fi:fi + 3] = left.T
+        P[fi:fi + 3, fi + 3:] = right; P[fi + 3:, fi:fi + 3] = right.T
+        self.P = (P + P.T) / 2.0
 
     # ---- updateFeatureCov_1didp :3125-3293
     def _update_feature_cov_1didp(self, ft, old_id, new_id):
@@ -1049,23 +1161,36 @@ class LarVioOracle:
             if len(involved) == 0:
                 continue
             if ft.in_state:
-                if ft.id_anchor in involved:                       # :2345-2405, 1-D IDP branch
-                    new_id = self._new_anchor_id(ft, involved)
-                    a = self.aug[new_id]
-                    p_new = quat_to_rot(a.q_cam).T @ (ft.position - a.p_cam)
-                    ft.invDepth = 1 / p_new[2]
-                    ft.obs_anchor = np.array([p_new[0] / p_new[2], p_new[1] / p_new[2], ft.obs_anchor[2]])
-                    self._update_feature_cov_1didp(ft, ft.id_anchor, new_id)
+                if ft.id_anchor in involved:                       # :2345-2405
+                    if self.idp == 3:                              # the newest state becomes the anchor (:2361-2378)
+                        new_id = self.imu_state.id
+                        a = self.aug[new_id]
+                        p_new = quat_to_rot(a.q_cam).T @ (ft.position - a.p_cam)
+                        ft.invParam = np.array([p_new[0] / p_new[2], p_new[1] / p_new[2], 1 / p_new[2]])
+                        self._update_feature_cov_3didp(ft, ft.id_anchor, new_id)
+                    else:
+                        new_id = self._new_anchor_id(ft, involved)
+                        a = self.aug[new_id]
+                        p_new = quat_to_rot(a.q_cam).T @ (ft.position - a.p_cam)
+                        ft.invDepth = 1 / p_new[2]
+                        ft.obs_anchor = np.array([p_new[0] / p_new[2], p_new[1] / p_new[2], ft.obs_anchor[2]])
+                        self._update_feature_cov_1didp(ft, ft.id_anchor, new_id)
                     ft.id_anchor = new_id
                     self.stats["anchor_changes"] = self.stats.get("anchor_changes", 0) + 1
                 continue
-            if ft.is_initialized and ft.id_anchor in involved:
-                new_id = self._new_anchor_id(ft, involved)
-                a = self.aug[new_id]
-                R_c2w = quat_to_rot(a.q_cam)
-                p_new = R_c2w.T @ (ft.position - a.p_cam)
-                ft.invDepth = 1 / p_new[2]
-                ft.obs_anchor = np.array([ft.obs[new_id][0], ft.obs[new_id][1], ft.obs_anchor[2]])
+            if ft.is_initialized and ft.id_anchor in involved:     # :2407-2460
+                if self.idp == 3:
+                    new_id = self.imu_state.id
+                    a = self.aug[new_id]
+                    p_new = quat_to_rot(a.q_cam).T @ (ft.position - a.p_cam)
+                    ft.invParam = np.array([p_new[0] / p_new[2], p_new[1] / p_new[2], 1 / p_new[2]])
+                else:
+                    new_id = self._new_anchor_id(ft, involved)
+                    a = self.aug[new_id]
+                    R_c2w = quat_to_rot(a.q_cam)
+                    p_new = R_c2w.T @ (ft.position - a.p_cam)
+                    ft.invDepth = 1 / p_new[2]
+                    ft.obs_anchor = np.array([ft.obs[new_id][0], ft.obs[new_id][1], ft.obs_anchor[2]])
                 ft.id_anchor = new_id
             if not self.if_ZUPT and not ft.ekf_feature and len(involved) > 1:
                 tracked = sid_now in ft.obs

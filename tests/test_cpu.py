@@ -357,6 +357,109 @@ def test_shim_header_compiles_against_the_public_header():
     assert r.returncode == 0, r.stderr.decode()
 
 
+def _two_view_scene(idp):
+    """A filter oracle with two window states and one in-state SLAM feature anchored at the first (no FEJ, so the
+    Jacobians linearise about the current estimates and can be checked by finite differences)."""
+    from larvio_b200.config import Config
+    from oracle.backend import LarVioOracle, Feature, AugState, quat_to_rot, rot_to_quat, small_angle_quat, quat_mul
+    c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), if_FEJ=0, feature_idp_dim=idp)
+    o = LarVioOracle(c.raw)
+    o.if_FEJ = False
+    s = o.imu_state
+    for sid, (dth, p) in enumerate([((0.02, -0.01, 0.03), (0.0, 0.0, 0.0)), ((-0.05, 0.08, 0.02), (0.35, -0.12, 0.08))]):
+        a = AugState(sid)
+        a.q = quat_mul(small_angle_quat(np.array(dth)), np.array([0.1, -0.2, 0.3, 0.9]) / np.linalg.norm([0.1, -0.2, 0.3, 0.9]))
+        a.p = np.array(p); a.p_FEJ = a.p.copy()
+        a.R_imu_cam0 = s.R_imu_cam0.copy(); a.t_cam0_imu = s.t_cam0_imu.copy()
+        R_b2w = quat_to_rot(a.q)
+        a.q_cam = rot_to_quat(R_b2w @ s.R_imu_cam0.T); a.p_cam = a.p + R_b2w @ s.t_cam0_imu
+        o.aug[sid] = a
+    ft = Feature(7, o.translation_threshold)
+    p_ca = np.array([0.4, -0.3, 3.2])
+    ft.id_anchor = 0
+    ft.invParam = np.array([p_ca[0] / p_ca[2], p_ca[1] / p_ca[2], 1 / p_ca[2]])
+    ft.invDepth = 1 / p_ca[2]; ft.obs_anchor = np.array([p_ca[0] / p_ca[2], p_ca[1] / p_ca[2], 1.0])
+    ft.position = quat_to_rot(o.aug[0].q_cam) @ p_ca + o.aug[0].p_cam
+    ft.position_FEJ = ft.position.copy()
+    ft.obs = {0: np.array([0.13, -0.09]), 1: np.array([0.05, -0.02])}
+    ft.obs_vel = {0: np.zeros(2), 1: np.zeros(2)}
+    o.map_server[7] = ft; o.feature_states = [7]
+    return o, ft
+
+
+def test_oracle_3didp_measurement_jacobian_matches_finite_differences():
+    """measurementJacobian_ekf_3didp (larvio.cpp:984-1114): r(x + dx) = r(x) - H dx to first order for the feature
+    block (3 inverse-depth parameters), the observing pose and the anchor pose."""
+    from oracle.backend import quat_to_rot, rot_to_quat, small_angle_quat, quat_mul
+    o, ft = _two_view_scene(3)
+    H_f, H_a, H_x, H_e, r0 = o._meas_jacobian_3didp(1, ft)
+    assert H_f.shape == (2, 3)
+
+    def residual(d_f=np.zeros(3), d_xk=np.zeros(6), d_xa=np.zeros(6)):
+        o2, f2 = _two_view_scene(3)
+        for sid, dxs in ((1, d_xk), (0, d_xa)):
+            a = o2.aug[sid]
+            a.q = quat_mul(small_angle_quat(dxs[:3]), a.q); a.p = a.p + dxs[3:]
+            R_b2w = quat_to_rot(a.q)
+            a.q_cam = rot_to_quat(R_b2w @ a.R_imu_cam0.T); a.p_cam = a.p + R_b2w @ a.t_cam0_imu
+        f2.invParam = f2.invParam + d_f
+        ip = f2.invParam
+        f2.position = quat_to_rot(o2.aug[0].q_cam) @ np.array([ip[0] / ip[2], ip[1] / ip[2], 1 / ip[2]]) + o2.aug[0].p_cam
+        return o2._meas_jacobian_3didp(1, f2)[4]
+    eps = 1e-6
+    for j in range(3):
+        d = np.zeros(3); d[j] = eps
+        assert np.abs((residual(d_f=d) - r0) / eps + H_f[:, j]).max() < 1e-4
+    for j in range(6):
+        d = np.zeros(6); d[j] = eps
+        assert np.abs((residual(d_xk=d) - r0) / eps + H_x[:, j]).max() < 1e-4
+        assert np.abs((residual(d_xa=d) - r0) / eps + H_a[:, j]).max() < 1e-4
+    # the anchor's own observation only sees the first two parameters (:1065-1073)
+    Hf0, Ha0, Hx0, He0, _ = o._meas_jacobian_3didp(0, ft)
+    assert np.array_equal(Hf0, np.array([[1., 0, 0], [0, 1., 0]])) and not Ha0.any() and not Hx0.any() and not He0.any()
+
+
+def test_oracle_1didp_measurement_jacobian_matches_finite_differences():
+    """measurementJacobian_ekf_1didp (larvio.cpp:1117-1244), the form the CUDA path implements: inverse depth along the
+    fixed anchor bearing."""
+    from oracle.backend import quat_to_rot, rot_to_quat, small_angle_quat, quat_mul
+    o, ft = _two_view_scene(1)
+    H_f, H_a, H_x, H_e, r0 = o._meas_jacobian_1didp(1, ft)
+
+    def residual(d_rho=0.0, d_xk=np.zeros(6), d_xa=np.zeros(6)):
+        o2, f2 = _two_view_scene(1)
+        for sid, dxs in ((1, d_xk), (0, d_xa)):
+            a = o2.aug[sid]
+            a.q = quat_mul(small_angle_quat(dxs[:3]), a.q); a.p = a.p + dxs[3:]
+            R_b2w = quat_to_rot(a.q)
+            a.q_cam = rot_to_quat(R_b2w @ a.R_imu_cam0.T); a.p_cam = a.p + R_b2w @ a.t_cam0_imu
+        f2.invDepth = f2.invDepth + d_rho
+        f2.position = quat_to_rot(o2.aug[0].q_cam) @ (f2.obs_anchor / f2.invDepth) + o2.aug[0].p_cam
+        return o2._meas_jacobian_1didp(1, f2)[4]
+    eps = 1e-6
+    assert np.abs((residual(d_rho=eps) - r0) / eps + np.asarray(H_f).reshape(2)).max() < 1e-4
+    for j in range(6):
+        d = np.zeros(6); d[j] = eps
+        assert np.abs((residual(d_xk=d) - r0) / eps + H_x[:, j]).max() < 1e-4
+        assert np.abs((residual(d_xa=d) - r0) / eps + H_a[:, j]).max() < 1e-4
+
+
+def test_oracle_3d_idp_hybrid_runs_and_keeps_the_state_layout(cfg):
+    """feature_idp_dim: 3 (oracle only so far): three columns per SLAM feature, anchors moved to the newest
+    state when their pose is pruned (:2361-2378), covariance stays symmetric PSD, accuracy like the 1-D filter."""
+    from larvio_b200 import synth, harness
+    from larvio_b200.config import Config
+    hc = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), sw_size=12, feature_idp_dim=3)
+    seq = synth.make_sequence(hc.raw, 0, 130)
+    recs = harness.run_oracle(hc.raw, seq, 130)
+    ok = [r for r in recs if r.get("ok")]
+    assert max(r["n_slam"] for r in ok) >= 3
+    assert all(r["dim"] == 22 + 6 * r["n_win"] + 3 * r["n_slam"] for r in ok)
+    assert max(r["pos_err"] for r in ok) < 0.25
+    P = ok[-1]["P"]
+    assert np.abs(P - P.T).max() == 0.0 and np.linalg.eigvalsh(P).min() > -1e-12
+
+
 def test_update_invariant_to_orthogonal_row_transform(cfg):
     """What legitimises Householder/Givens QR on the GPU vs SPQR on the CPU."""
     from oracle.backend import LarVioOracle
