@@ -2385,14 +2385,23 @@ static int be_measurement_pass(LvbHandle* h, BeView& v, int mode) {
 
 // msg arrays are device pointers. imu/n_imu: caller's host buffers (mutated).
 int be_process(LvbHandle* h, const LvbFeature* d_msg, const int* d_msg_n, const double* d_msg_t, const uint8_t* d_valid,
-               int msg_stride, LvbImu* imu, int* n_imu, int imu_stride, uint8_t* ok_out) {
+               int msg_stride, LvbImu* imu, int* n_imu, int imu_stride, uint8_t* ok_out, const double* h_msg_t = nullptr,
+               const uint8_t* h_msg_valid = nullptr) {
   LvbBackEnd* be = h->be;
   if (const char* why = be_unsupported_reason(h->cfg)) return lvb_set_err(LVB_E_UNSUPPORTED, "%s", why);
   cudaStream_t st = h->stream;
   const int S = be->S;
   for (int s = 0; s < S; ++s) {
     int n = n_imu[s];
-    if (n > be->imu_cap) n = be->imu_cap;        // only the oldest samples can be consumed this frame
+    if (n > be->imu_cap) {
+      // Only imu_cap samples are staged per call.  That is harmless while the first sample left behind is newer than
+      // anything batchImuProcessing could consume for this message (time bound = message time + td, larvio.cpp:464-512;
+      // td is estimated online, hence the 50 ms margin); otherwise the propagation would silently stop short.
+      const LvbImu* b = imu + (size_t)s * imu_stride;
+      if (h_msg_t && h_msg_valid && h_msg_valid[s] && b[be->imu_cap].t <= h_msg_t[s] + h->cfg.td + 0.05)
+        return lvb_set_err(LVB_E_CAPACITY, "sequence %d: %d pending IMU samples exceed the per-call staging capacity %d", s, n, be->imu_cap);
+      n = be->imu_cap;
+    }
     be->pin_n_imu[s] = n;
     memcpy(be->pin_imu + (size_t)s * be->imu_cap, imu + (size_t)s * imu_stride, sizeof(LvbImu) * n);
   }
@@ -2477,7 +2486,7 @@ extern "C" int lvb_process_features(LvbHandle* h, const uint8_t* valid, const do
   LVB_CUDA(cudaMemcpyAsync(be->msg_in_n, be->pin_feat_n, sizeof(int) * S, cudaMemcpyHostToDevice, h->stream));
   LVB_CUDA(cudaMemcpyAsync(be->msg_in_t, be->pin_feat_t, sizeof(double) * S, cudaMemcpyHostToDevice, h->stream));
   LVB_CUDA(cudaMemcpyAsync(be->msg_in_valid, be->pin_valid, S, cudaMemcpyHostToDevice, h->stream));
-  return be_process(h, be->msg_in, be->msg_in_n, be->msg_in_t, be->msg_in_valid, N, imu, n_imu, imu_stride, ok);
+  return be_process(h, be->msg_in, be->msg_in_n, be->msg_in_t, be->msg_in_valid, N, imu, n_imu, imu_stride, ok, t_msg, valid);
 }
 
 extern "C" int lvb_step(LvbHandle* h, const uint8_t* images, int images_on_device, const double* t_img, LvbImu* imu,
