@@ -11,7 +11,19 @@ SRC_CPP := $(wildcard larvio_b200/csrc/*.cpp)
 OBJ := $(SRC_CU:.cu=.o) $(SRC_CPP:.cpp=.o)
 LIB := larvio_b200/lib/liblarvio_b200.so
 
-all: $(LIB)
+IOLIB := larvio_b200/lib/liblarvio_io.so
+REPLAY := larvio_b200/bin/larvio_replay
+
+all: $(LIB) $(IOLIB) $(REPLAY)
+
+# host-side on-disk formats (PNG/CSV readers, links zlib) and the C++ batched replay driver (app/larvioMain.cpp's role)
+$(IOLIB): larvio_b200/host/lvb_io.cpp include/larvio_b200.h
+	mkdir -p larvio_b200/lib
+	g++ -O2 -std=c++17 -fPIC -shared -o $@ $< -lz
+
+$(REPLAY): larvio_b200/host/replay_main.cpp $(LIB) $(IOLIB) include/larvio_b200.h
+	mkdir -p larvio_b200/bin
+	g++ -O2 -std=c++17 -o $@ $< -Llarvio_b200/lib -llarvio_b200 -llarvio_io -Wl,-rpath,'$$ORIGIN/../lib'
 
 larvio_b200/csrc/be_%.o: larvio_b200/csrc/be_%.cu larvio_b200/csrc/*.h larvio_b200/csrc/*.cuh larvio_b200/csrc/*.inc include/larvio_b200.h
 	$(NVCC) $(NVFLAGS_BE) -c $< -o $@ 2> $@.log || (cat $@.log; false)
@@ -27,4 +39,4 @@ $(LIB): $(OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart
 
 clean:
-	rm -f larvio_b200/csrc/*.o larvio_b200/csrc/*.o.log $(LIB)
+	rm -f larvio_b200/csrc/*.o larvio_b200/csrc/*.o.log $(LIB) $(IOLIB) $(REPLAY)

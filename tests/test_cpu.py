@@ -350,6 +350,79 @@ def test_euroc_ingest_and_trajectory_log_round_trip(tmp_path, cfg):
     assert open(tmp_path / "out" / "msckf_2_takeoff.txt").read() == "1.250000000\n"
 
 
+def _write_asl(tmp_path, seq, n):
+    import cv2
+    mav = tmp_path / "mav0"
+    (mav / "cam0" / "data").mkdir(parents=True); (mav / "imu0").mkdir(parents=True)
+    with open(mav / "cam0" / "data.csv", "w") as f:
+        f.write("#timestamp [ns],filename\n")
+        for t, im in zip(seq.img_t[:n], seq.images[:n]):
+            ns = int(round(t * 1e9))
+            cv2.imwrite(str(mav / "cam0" / "data" / ("%d.png" % ns)), im)
+            f.write("%d,%d.png\r\n" % (ns, ns))                      # EuRoC files have CRLF line ends
+    with open(mav / "imu0" / "data.csv", "w") as f:
+        f.write("#timestamp [ns],w_RS_S_x [rad s^-1],w_RS_S_y,w_RS_S_z,a_RS_S_x [m s^-2],a_RS_S_y,a_RS_S_z\n")
+        for r in seq.imu:
+            f.write("%d,%.17g,%.17g,%.17g,%.17g,%.17g,%.17g\r\n" % (int(round(r[0] * 1e9)), *r[1:]))
+    return mav
+
+
+def test_host_io_library_png_and_csv_readers(tmp_path, cfg, lib_built):
+    """liblarvio_io.so (host C++, zlib only): 8-bit grey PNG decode identical to cv2.imread(path, 0), EuRoC csv readers
+    identical to the Python restatement of DataReader.hpp."""
+    import cv2
+    from larvio_b200 import synth, euroc, api
+    lib = ctypes.CDLL(os.path.join(ROOT, "larvio_b200", "lib", "liblarvio_io.so"))
+    lib.lvbio_last_error.restype = ctypes.c_char_p
+    seq = synth.make_sequence(cfg.raw, 0, 4)
+    mav = _write_asl(tmp_path, seq, 4)
+    for name in sorted(os.listdir(mav / "cam0" / "data")):
+        pth = str(mav / "cam0" / "data" / name)
+        w = ctypes.c_int(); h = ctypes.c_int(); out = np.zeros((480, 752), np.uint8)
+        assert lib.lvbio_png_read_gray8(pth.encode(), out.ctypes.data_as(ctypes.c_void_p), out.size, ctypes.byref(w), ctypes.byref(h)) == 0
+        assert (w.value, h.value) == (752, 480) and np.array_equal(out, cv2.imread(pth, 0))
+    rng = np.random.default_rng(1)
+    for comp, shape in ((9, (31, 17)), (1, (5, 64))):                   # other filters / tiny images
+        img = cv2.GaussianBlur(rng.integers(0, 256, shape).astype(np.uint8), (0, 0), 2)
+        pth = str(tmp_path / ("x%d.png" % comp)); cv2.imwrite(pth, img, [cv2.IMWRITE_PNG_COMPRESSION, comp])
+        w = ctypes.c_int(); h = ctypes.c_int(); out = np.zeros(shape, np.uint8)
+        assert lib.lvbio_png_read_gray8(pth.encode(), out.ctypes.data_as(ctypes.c_void_p), out.size, ctypes.byref(w), ctypes.byref(h)) == 0
+        assert np.array_equal(out, img)
+    colour = str(tmp_path / "c.png"); cv2.imwrite(colour, np.zeros((4, 4, 3), np.uint8))
+    w = ctypes.c_int(); h = ctypes.c_int()
+    assert lib.lvbio_png_read_gray8(colour.encode(), None, 0, ctypes.byref(w), ctypes.byref(h)) != 0
+    assert b"8-bit greyscale" in lib.lvbio_last_error()
+    n = ctypes.c_int()
+    imu_csv = str(mav / "imu0" / "data.csv").encode()
+    assert lib.lvbio_euroc_read_imu(imu_csv, None, 0, ctypes.byref(n)) == 0 and n.value == len(seq.imu)
+    buf = np.zeros(n.value, api.IMU_DTYPE)
+    assert lib.lvbio_euroc_read_imu(imu_csv, buf.ctypes.data_as(ctypes.c_void_p), n.value, ctypes.byref(n)) == 0
+    ref = euroc.load_imu_file(str(mav / "imu0" / "data.csv"))
+    assert np.array_equal(buf["t"], ref[:, 0]) and np.array_equal(buf["gyro"], ref[:, 1:4]) and np.array_equal(buf["acc"], ref[:, 4:7])
+    t = np.zeros(8); names = ctypes.create_string_buffer(8 * 64)
+    assert lib.lvbio_euroc_read_image_list(str(mav / "cam0" / "data.csv").encode(), t.ctypes.data_as(ctypes.c_void_p), names, 64, 8, ctypes.byref(n)) == 0
+    lst = euroc.load_image_list(str(mav / "cam0" / "data.csv"))
+    assert n.value == 4 and [names.raw[i * 64:(i + 1) * 64].split(b"\0")[0].decode() for i in range(4)] == [x[1] for x in lst]
+    assert np.array_equal(t[:4], [x[0] for x in lst])
+
+
+def test_replay_driver_reports_a_missing_gpu(tmp_path, cfg, lib_built):
+    """larvio_replay (host C++ over the C ABI, the role of app/larvioMain.cpp): on a box without a GPU it must stop at
+    lvb_create with the CUDA error, after having parsed the config and both csv files - never fall back to a CPU path."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box WITHOUT a GPU")
+    from larvio_b200 import synth
+    seq = synth.make_sequence(cfg.raw, 0, 3)
+    mav = _write_asl(tmp_path, seq, 3)
+    exe = os.path.join(ROOT, "larvio_b200", "bin", "larvio_replay")
+    r = subprocess.run([exe, os.path.join(ROOT, "configs", "euroc_mono.yaml"), str(tmp_path / "out"), str(mav)], capture_output=True, text=True)
+    assert r.returncode == 1 and "lvb_create" in r.stderr and "cuda" in r.stderr.lower()
+    r = subprocess.run([exe, "/nonexistent.yaml", str(tmp_path / "out"), str(mav)], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open" in r.stderr
+
+
 def test_shim_header_compiles_against_the_public_header():
     import subprocess
     src = '#include "larvio_b200/host/larvio_shim.hpp"\nint main() { std::string c = "x.yaml"; larvio::LarVio v(c); larvio::ImageProcessor ip(c); (void)v; (void)ip; return 0; }\n'

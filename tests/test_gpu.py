@@ -419,6 +419,59 @@ def test_filter_runs_through_empty_feature_messages(cfg):
     assert rep['p'] < 1e-8 and rep['v'] < 1e-8 and rep['q'] < 1e-8 and rep['Prel'] < 1e-8
 
 
+@pytest.mark.xfail(strict=False, reason="first GPU execution of the C++ replay driver (written after the GPU budget of round 1 was spent)")
+def test_cpp_replay_driver_matches_the_python_two_call_path(tmp_path, lib_built):
+    """larvio_b200/bin/larvio_replay on a synthetic EuRoC-layout directory (PNG + csv on disk, self-start from a
+    standstill) must write the trajectory the Python mirror of the same calls produces."""
+    import subprocess
+    import cv2
+    from larvio_b200 import api, synth, euroc
+    from larvio_b200.config import Config
+    cfg_path = os.path.join(ROOT, "configs", "euroc_mono.yaml")
+    c = Config.load(cfg_path)
+    NF = 40
+    seq = synth.make_sequence(c.raw, 3, NF, static_until=1.4)
+    mav = tmp_path / "mav0"
+    (mav / "cam0" / "data").mkdir(parents=True); (mav / "imu0").mkdir(parents=True)
+    with open(mav / "cam0" / "data.csv", "w") as f:
+        f.write("#timestamp [ns],filename\n")
+        for t, im in zip(seq.img_t, seq.images):
+            ns = int(round(t * 1e9)); cv2.imwrite(str(mav / "cam0" / "data" / ("%d.png" % ns)), im); f.write("%d,%d.png\r\n" % (ns, ns))
+    with open(mav / "imu0" / "data.csv", "w") as f:
+        f.write("#timestamp [ns],w_x,w_y,w_z,a_x,a_y,a_z\n")
+        for r in seq.imu:
+            f.write("%d,%.17g,%.17g,%.17g,%.17g,%.17g,%.17g\r\n" % (int(round(r[0] * 1e9)), *r[1:]))
+    exe = os.path.join(ROOT, "larvio_b200", "bin", "larvio_replay")
+    r = subprocess.run([exe, cfg_path, str(tmp_path / "out"), str(mav)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = euroc.read_state_log(str(tmp_path / "out" / "seq0" / "msckf_2_state.txt"))
+    # the same calls from Python, on the same files
+    b = api.Batch(c, n_seq=1); init = api.StaticInitializer(c)
+    buf = np.zeros((1, 4096), api.IMU_DTYPE); n_buf = np.zeros(1, np.int32)
+    started = False; take_off = 0.0; ref = []
+    for t, img, rows in euroc.Replay(str(mav)):
+        m = len(rows); n0 = int(n_buf[0])
+        buf["t"][0, n0:n0 + m] = rows[:, 0]; buf["gyro"][0, n0:n0 + m] = rows[:, 1:4]; buf["acc"][0, n0:n0 + m] = rows[:, 4:7]; n_buf[0] = n0 + m
+        feat, out_n, has = b.process_images(img[None], np.array([t]), buf, n_buf)
+        if not has[0]:
+            continue
+        if not started:
+            a = init.try_init(feat[0, :out_n[0]], t, buf[0, :n_buf[0]])
+            if a is None:
+                continue
+            b.set_initial_state(0, a["t"], a["q"], a["p"], a["v"], a["bg"], a["ba"])
+            nc = a["n_consumed"]; buf[0, :n_buf[0] - nc] = buf[0, nc:n_buf[0]].copy(); n_buf[0] -= nc
+            started = True; take_off = a["t"]
+        ok = b.process_features(has, np.array([t]), feat, out_n, buf, n_buf)
+        if ok[0]:
+            st = b.get_state(0)
+            ref.append(np.concatenate([[st["t"] - take_off, st["q"][3]], st["q"][:3], st["v"], st["p"], st["bg"], st["ba"]]))
+    b.close(); init.close()
+    ref = np.array(ref)
+    assert got.shape[0] == ref.shape[0] >= 6
+    assert np.allclose(got[:, :17], ref, rtol=2e-5, atol=2e-6)          # the log has 6 significant digits
+
+
 def test_gpu_against_committed_golden(cfg, seqs):
     from larvio_b200 import api, harness
     g = np.load(GOLD)
