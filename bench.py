@@ -61,6 +61,11 @@ NCU_TRAFFIC_PER_SEQ = {"lk_kernel": (55.305472e6 + 1.048832e6) / 64, "be_chol_ke
 
 
 def load_cfg(args):
+    if getattr(args, "workload", "C") == "D":
+        # BASELINE configs[3] per GPU: 1-D inverse-depth hybrid (5x6 grid, one SLAM feature per cell), online extrinsic / td /
+        # IMU-intrinsic calibration.  Not the headline workload; selectable for measurements of the hybrid path.
+        return Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), max_features_in_one_grid=1, feature_idp_dim=1,
+                           calib_imu_instrinsic=1, estimate_extrin=1, estimate_td=1, sw_size=args.window, max_features_num=args.tracks)
     return Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), max_features_in_one_grid=0,
                        sw_size=args.window, max_features_num=args.tracks)
 
@@ -232,6 +237,8 @@ def main():
     ap.add_argument("--window", type=int, default=30)
     ap.add_argument("--cpu-frames", type=int, default=16, help="frames per sequence of the bounded cpu_baseline sample")
     ap.add_argument("--profile-steps", type=int, default=8)
+    ap.add_argument("--workload", choices=["C", "D"], default="C",
+                    help="C = BASELINE configs[2] (MSCKF-only, the headline); D = configs[3] per GPU (1-D IDP hybrid + online calibration)")
     ap.add_argument("--streams", type=int, default=4,
                     help="sub-batches per GPU, each an independent handle/stream driven by its own host thread")
     args = ap.parse_args()
@@ -241,7 +248,8 @@ def main():
         args.warmup = 3
     S, K, Wm = args.seqs, args.steps, args.warmup
     cfg = load_cfg(args)
-    workload = "configs[2]: %d batched synthetic 752x480@20Hz+200Hz-IMU sequences per GPU, %d tracks, %d-pose window, MSCKF-only" % (S, args.tracks, args.window)
+    workload = ("configs[2]: %d batched synthetic 752x480@20Hz+200Hz-IMU sequences per GPU, %d tracks, %d-pose window, MSCKF-only" if args.workload == "C" else
+                "configs[3] per GPU: %d batched synthetic sequences, %d tracks, %d-pose window, 1-D IDP hybrid (5x6 grid) + online extrinsic/td/IMU-intrinsic calibration") % (S, args.tracks, args.window)
     config = dict(workload=workload, sequences_per_gpu=S, sub_batches_per_gpu=args.streams, tracks=args.tracks, window=args.window, image="752x480 u8",
                   l2_policy="each step reads a fresh %.1f MB image batch and touches >250 MB of per-sequence state (> 126 MB L2)" % (S * B0 / 1e6),
                   inputs=("one pool of %d seeded sequences (seed 1234+i)" % S) + ("" if world == 1 else
