@@ -533,6 +533,51 @@ def test_oracle_3d_idp_hybrid_runs_and_keeps_the_state_layout(cfg):
     assert np.abs(P - P.T).max() == 0.0 and np.linalg.eigvalsh(P).min() > -1e-12
 
 
+def test_gpu_test_harness_runs_against_the_mock(cfg, monkeypatch):
+    """The `-m gpu` tests drive the library through one Python harness (tests/test_gpu.py::_drive).  Here that harness
+    runs on CPU against tests/mock_batch.MockBatch - a second oracle behind the Batch interface - so that indexing,
+    buffer-stride and empty-message handling of the harness itself is checked without a GPU (every comparison must come
+    out exactly zero)."""
+    import importlib
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from larvio_b200 import api, synth
+    from mock_batch import MockBatch
+    tg = importlib.import_module("test_gpu")
+    monkeypatch.setattr(api, "Batch", MockBatch)
+    seqs2 = tg._blackout_sequences(cfg)
+    for q in seqs2:                                      # 30 frames are enough: blackout at 20-23, failed second image at 1
+        q.images = q.images[:30]
+    rep = tg._drive(cfg, seqs2, 30, 'fe')
+    assert rep['msgs'] >= 24 and rep['id_mismatch'] == 0 and rep['uv'] == 0.0 and rep['vel'] == 0.0
+    rep = tg._drive(cfg, seqs2, 30, 'step')
+    assert rep['steps'] >= 24 and rep['ok_mismatch'] == 0 and rep['imu_mismatch'] == 0
+    assert rep['p'] == 0.0 and rep['Prel'] == 0.0 and rep['calib'] == 0.0
+    assert rep['rmse_gpu'] == rep['rmse_cpu'] > 0.0
+    two = [synth.make_sequence(cfg.raw, s, 12) for s in range(2)]
+    rep = tg._drive(cfg, two, 12, 'be')
+    assert rep['steps'] >= 8 and rep['p'] == 0.0 and rep['imu_mismatch'] == 0
+
+
+def test_self_start_and_replay_harness_run_against_the_mock(tmp_path, monkeypatch, lib_built):
+    """Same idea for the two harnesses that start the filter with the static initialiser (real host C++, no GPU needed):
+    the self-start GPU test and the Python half of the replay-driver test."""
+    import importlib
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from larvio_b200 import api, synth
+    from larvio_b200.config import Config
+    from mock_batch import MockBatch
+    tg = importlib.import_module("test_gpu")
+    monkeypatch.setattr(api, "Batch", MockBatch)
+    tg.test_self_start_with_the_static_initialiser(lib_built)
+    c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"))
+    seq = synth.make_sequence(c.raw, 3, 34, static_until=1.4)
+    mav = _write_asl(tmp_path, seq, 34)
+    rows = tg._python_two_call_replay(c, str(mav))
+    assert rows.shape[1] == 17 and rows.shape[0] >= 5 and rows[0, 0] > 0.0 and np.all(np.diff(rows[:, 0]) > 0)
+
+
 def test_update_invariant_to_orthogonal_row_transform(cfg):
     """What legitimises Householder/Givens QR on the GPU vs SPQR on the CPU."""
     from oracle.backend import LarVioOracle
