@@ -1271,6 +1271,69 @@ __global__ void __launch_bounds__(512) be_qr_kernel(BeView v) {
   }
 }
 
+// ---- staged variant (LVB_EXPERIMENT=qr_lean): the same column-by-column Householder with 2 block barriers per column
+// instead of 5.  The warp that updates column j+1 also leaves its squared norm below the diagonal and its diagonal entry in
+// shared memory, so iteration j+1 starts without a reduction pass; every thread derives (alpha, beta) from those two
+// numbers itself (no single-thread section); the finished column is zeroed while the reflector is copied out.
+__global__ void __launch_bounds__(512) be_qr_lean_kernel(BeView v) {
+  extern __shared__ double qsm[];      // reflector [RMAX]
+  __shared__ double red[16];
+  __shared__ double s_n2, s_x0;
+  const int s = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK]) return;
+  const int R = ic[I_ROWS], c = ic[I_DIM];
+  if (R <= c || R == 0) return;
+  const int RMAX = v.be.RMAX, LD = v.be.LD;
+  double* Hs = v.be.Hs + (size_t)s * LD * RMAX;
+  double* rs = v.be.rs + (size_t)s * RMAX;
+  {                                                    // column 0: the only block-wide reduction
+    double part = 0.0;
+    for (int i = tid; i < R; i += 512) { const double x = Hs[i]; part += x * x; }
+    part = warp_sum_d(part);
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (tid == 0) { double n2 = 0.0; for (int w = 0; w < 16; ++w) n2 += red[w]; s_n2 = n2; s_x0 = Hs[0]; }
+    __syncthreads();
+  }
+  for (int j = 0; j < c; ++j) {
+    double* cj = Hs + (size_t)j * RMAX;
+    const double n2 = s_n2, x0 = s_x0;                 // squared norm of rows >= j of column j, and its diagonal entry
+    const double nrm = sqrt(n2);
+    const double alpha = x0 >= 0 ? -nrm : nrm;
+    const double v0 = x0 - alpha;
+    const double vtv = n2 - x0 * x0 + v0 * v0;
+    const double beta = vtv > 0.0 ? 2.0 / vtv : 0.0;
+    for (int i = j + tid; i < R; i += 512) {
+      const double x = cj[i];
+      qsm[i] = (i == j) ? v0 : x;
+      cj[i] = (i == j) ? alpha : 0.0;
+    }
+    __syncthreads();
+    for (int k = j + 1 + warp; k <= c; k += 16) {
+      double* ck = (k < c) ? Hs + (size_t)k * RMAX : rs;
+      if (beta != 0.0) {
+        double dt_ = 0.0;
+        for (int i = j + lane; i < R; i += 32) dt_ += qsm[i] * ck[i];
+        dt_ = warp_sum_d(dt_) * beta;
+        for (int i = j + lane; i < R; i += 32) ck[i] -= dt_ * qsm[i];
+      }
+      if (k == j + 1 && k < c) {                       // hand the next column's norm and diagonal to the next iteration
+        __syncwarp();
+        double part = 0.0;
+        for (int i = j + 1 + lane; i < R; i += 32) { const double x = ck[i]; part += x * x; }
+        part = warp_sum_d(part);
+        if (lane == 0) { s_n2 = part; s_x0 = ck[j + 1]; }
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    ic[I_R] = c;
+    if (v.be.stats) { atomicAdd(&v.be.stats[8], 1ull); atomicAdd(&v.be.stats[9], (unsigned long long)R * c * c); }
+  }
+}
+
 }  // namespace
 
 namespace {
@@ -1384,6 +1447,92 @@ __global__ void __launch_bounds__(1024) be_chol_kernel(BeView v) {
   for (int e = tid; e < r * r; e += 1024) { const int i = e / r, j = e - i * r; if (j <= i) S[(size_t)i * LD + j] = LP(i, j); }
   // z = L^-1 r  (warp 0, row oriented, out of smem)
   if (tid < 32) {
+    const double* rs = v.be.rs + (size_t)s * v.be.RMAX;
+    for (int i = 0; i < r; ++i) {
+      double part = 0.0;
+      for (int q = tid; q < i; q += 32) part += LP(i, q) * z[q];
+      part = warp_sum_d(part);
+      if (tid == 0) z[i] = (rs[i] - part) / LP(i, i);
+      __syncwarp();
+    }
+    double* zg = v.be.zvec + (size_t)s * LD;
+    for (int i = tid; i < r; i += 32) zg[i] = z[i];
+  }
+#undef LP
+}
+
+// ---- staged variant (LVB_EXPERIMENT=chol_blocked): right-looking BLOCKED Cholesky, panels of CH_NB columns.
+// Per panel: the CH_NB x CH_NB diagonal block is factored by one thread, every row below solves its CH_NB entries against
+// it (one thread per row, no barrier inside), and the trailing lower triangle receives ONE rank-CH_NB update
+// (CH_NB FMAs per shared-memory read-modify-write instead of 1) - 3 block barriers per CH_NB columns instead of 3 per
+// column.  Same factor as be_chol_kernel up to rounding (different summation order).
+constexpr int CH_NB = 8;
+__global__ void __launch_bounds__(512) be_chol_blocked_kernel(BeView v) {
+  extern __shared__ double csm[];   // packed lower triangle + z [Dmax] + panel [CH_NB][Dmax]
+  __shared__ double s_L11[CH_NB][CH_NB];
+  __shared__ int s_bad;
+  const int s = blockIdx.x, tid = threadIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK]) return;
+  const int r = ic[I_R];
+  if (r <= 0 || r > v.be.Dmax) return;
+  const int LD = v.be.LDS, Dm = v.be.Dmax;
+  double* S = v.be.Sm + (size_t)s * LD * LD;
+  double* Lp = csm;
+  double* z = csm + (size_t)Dm * (Dm + 1) / 2;
+  double* Pn = z + Dm;                                 // Pn[k * Dm + row]
+#define LP(i, j) Lp[(size_t)(i) * ((i) + 1) / 2 + (j)]
+  for (int e = tid; e < r * r; e += 512) { const int i = e / r, j = e - i * r; if (j <= i) LP(i, j) = S[(size_t)i * LD + j]; }
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  for (int j0 = 0; j0 < r; j0 += CH_NB) {
+    const int nb = min(CH_NB, r - j0);
+    if (tid == 0) {                                    // diagonal block; a short last panel is padded with the identity
+      for (int a = 0; a < CH_NB; ++a)
+        for (int b2 = 0; b2 < CH_NB; ++b2) s_L11[a][b2] = (a == b2) ? 1.0 : 0.0;
+      for (int a = 0; a < nb; ++a) {
+        for (int b2 = 0; b2 <= a; ++b2) {
+          double x = LP(j0 + a, j0 + b2);
+          for (int k = 0; k < b2; ++k) x -= s_L11[a][k] * s_L11[b2][k];
+          if (a == b2) x = sqrt(x); else x /= s_L11[b2][b2];
+          s_L11[a][b2] = x;
+          LP(j0 + a, j0 + b2) = x;
+        }
+      }
+    }
+    __syncthreads();
+    // rows below the block: x L11^T = a  (forward substitution over the panel columns), kept in Pn for the update
+    for (int i = j0 + nb + tid; i < r; i += 512) {
+      double x[CH_NB];
+#pragma unroll
+      for (int k = 0; k < CH_NB; ++k) {
+        double a = (k < nb) ? LP(i, j0 + k) : 0.0;
+#pragma unroll
+        for (int m = 0; m < k; ++m) a -= x[m] * s_L11[k][m];
+        a /= s_L11[k][k];
+        x[k] = a;
+        if (k < nb) LP(i, j0 + k) = a;
+        Pn[k * Dm + i] = a;
+      }
+    }
+    __syncthreads();
+    // trailing update: rows a over the warps, columns b in [j0+nb, a] over the lanes (padded panel columns hold zeros)
+    for (int a = j0 + nb + (tid >> 5); a < r; a += 16) {
+      double pa[CH_NB];
+#pragma unroll
+      for (int k = 0; k < CH_NB; ++k) pa[k] = Pn[k * Dm + a];
+      double* row = &LP(a, 0);
+      for (int b2 = j0 + nb + (tid & 31); b2 <= a; b2 += 32) {
+        double acc = row[b2];
+#pragma unroll
+        for (int k = 0; k < CH_NB; ++k) acc -= pa[k] * Pn[k * Dm + b2];
+        row[b2] = acc;
+      }
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < r * r; e += 512) { const int i = e / r, j = e - i * r; if (j <= i) S[(size_t)i * LD + j] = LP(i, j); }
+  if (tid < 32) {                                      // z = L^-1 r, as in be_chol_kernel
     const double* rs = v.be.rs + (size_t)s * v.be.RMAX;
     for (int i = 0; i < r; ++i) {
       double part = 0.0;
@@ -2171,6 +2320,13 @@ int be_alloc(LvbHandle* h) {
   if (be->NFmax > 0) LVB_CUDA(cudaFuncSetAttribute(be_slam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 64 * be->LD)));
   const size_t chol_bytes = sizeof(double) * ((size_t)be->Dmax * (be->Dmax + 1) / 2 + 2 * be->Dmax);
   if (chol_bytes <= 227 * 1024) LVB_CUDA(cudaFuncSetAttribute(be_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_bytes));
+  if (const char* ex = getenv("LVB_EXPERIMENT")) {             // staged kernel variants, off unless named
+    if (strstr(ex, "chol_blocked")) h->experiments |= LVB_EXP_CHOL_BLOCKED;
+    if (strstr(ex, "qr_lean")) h->experiments |= LVB_EXP_QR_LEAN;
+  }
+  const size_t cholb_bytes = chol_bytes + sizeof(double) * (size_t)(CH_NB - 1) * be->Dmax;
+  if ((h->experiments & LVB_EXP_CHOL_BLOCKED) && cholb_bytes <= 227 * 1024)
+    LVB_CUDA(cudaFuncSetAttribute(be_chol_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cholb_bytes));
   return LVB_OK;
 }
 
@@ -2195,6 +2351,12 @@ static int launch_gemm(LvbHandle* h, const GemmArgs& g, int max_m, int max_n) {
 static int be_debug_check(LvbHandle* h, const char* stage);
 #define DBG(name) RC(be_debug_check(h, name))
 static int be_qr(LvbHandle* h, BeView& v) {
+  if (h->experiments & LVB_EXP_QR_LEAN) {
+    LVB_PROF(h, "be_qr_lean_kernel");
+    be_qr_lean_kernel<<<h->be->S, 512, sizeof(double) * h->be->RMAX, h->stream>>>(v);
+    LVB_LAUNCH_CHECK(h);
+    return LVB_OK;
+  }
   LVB_PROF(h, "be_qr_kernel");
   be_qr_kernel<<<h->be->S, 512, sizeof(double) * h->be->RMAX, h->stream>>>(v);
   LVB_LAUNCH_CHECK(h);
@@ -2224,7 +2386,13 @@ static int be_update(LvbHandle* h, BeView& v, bool zupt_rows = false) {
   g.diag_vec = nullptr;
   const size_t chol_bytes = sizeof(double) * ((size_t)be->Dmax * (be->Dmax + 1) / 2 + 2 * be->Dmax);
   const bool smem_ok = chol_bytes <= 227 * 1024;
-  if (smem_ok) {
+  const size_t cholb_bytes = chol_bytes + sizeof(double) * (size_t)(CH_NB - 1) * be->Dmax;
+  if (smem_ok && (h->experiments & LVB_EXP_CHOL_BLOCKED) && cholb_bytes <= 227 * 1024) {
+    LVB_PROF(h, "be_chol_blocked_kernel");
+    be_chol_blocked_kernel<<<be->S, 512, cholb_bytes, st>>>(v);
+    LVB_LAUNCH_CHECK(h);
+    DBG("be_chol_blocked_kernel");
+  } else if (smem_ok) {
     LVB_PROF(h, "be_chol_kernel");
     be_chol_kernel<<<be->S, 1024, chol_bytes, st>>>(v);
     LVB_LAUNCH_CHECK(h);

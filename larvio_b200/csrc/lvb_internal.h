@@ -128,7 +128,11 @@ struct LvbHandle {
   float* pin_H; int* pin_active; double* pin_t;
   LvbFeature* pin_msg; int* pin_msg_n; uint8_t* pin_has;
   std::vector<void*> allocs;
+  // Staged kernel variants, OFF by default: comma-separated names in LVB_EXPERIMENT select them at lvb_create time
+  // (DESIGN.md 7); host-only, so the kernel argument layouts of the default path do not change.
+  unsigned experiments = 0;
 };
+enum { LVB_EXP_CHOL_BLOCKED = 1u, LVB_EXP_QR_LEAN = 2u };
 
 extern thread_local std::string g_lvb_err;
 int lvb_set_err(int code, const char* fmt, ...);

@@ -496,6 +496,19 @@ def test_cpp_replay_driver_matches_the_python_two_call_path(tmp_path, lib_built)
     assert np.allclose(got[:, :17], ref, rtol=2e-5, atol=2e-6)          # the log has 6 significant digits
 
 
+@pytest.mark.xfail(strict=False, reason="staged kernel variants (LVB_EXPERIMENT), written after the GPU budget of round 1 was spent; off by default")
+@pytest.mark.parametrize("variant", ["chol_blocked", "qr_lean", "chol_blocked,qr_lean"])
+def test_staged_kernel_variants_keep_parity(cfg, variant, monkeypatch):
+    """blocked Cholesky / 2-barrier QR selected by LVB_EXPERIMENT at lvb_create time must reproduce the oracle
+    like the default kernels do (60 frames: window full, QR compression and pruning active)."""
+    from larvio_b200 import synth
+    monkeypatch.setenv("LVB_EXPERIMENT", variant)
+    s60 = [synth.make_sequence(cfg.raw, s, 60) for s in range(2)]
+    rep = _drive(cfg, s60, 60, 'step')
+    assert rep['steps'] >= 50 and rep['ok_mismatch'] == 0
+    assert rep['p'] < 1e-8 and rep['q'] < 1e-8 and rep['Prel'] < 1e-8
+
+
 def test_gpu_against_committed_golden(cfg, seqs):
     from larvio_b200 import api, harness
     g = np.load(GOLD)
