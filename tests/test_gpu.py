@@ -1,6 +1,7 @@
 """GPU parity suite (-m gpu): every stage and the whole path through the C ABI against the CPU oracle
 (cv2 4.13 for the OpenCV pieces, numpy f64 for the filter) and against the committed golden vectors."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -498,13 +499,27 @@ def test_cpp_replay_driver_matches_the_python_two_call_path(tmp_path, lib_built)
 
 @pytest.mark.xfail(strict=False, reason="staged kernel variants (LVB_EXPERIMENT), written after the GPU budget of round 1 was spent; off by default")
 @pytest.mark.parametrize("variant", ["chol_blocked", "qr_lean", "chol_blocked,qr_lean"])
-def test_staged_kernel_variants_keep_parity(cfg, variant, monkeypatch):
+def test_staged_kernel_variants_keep_parity(variant):
     """blocked Cholesky / 2-barrier QR selected by LVB_EXPERIMENT at lvb_create time must reproduce the oracle
-    like the default kernels do (60 frames: window full, QR compression and pruning active)."""
-    from larvio_b200 import synth
-    monkeypatch.setenv("LVB_EXPERIMENT", variant)
-    s60 = [synth.make_sequence(cfg.raw, s, 60) for s in range(2)]
-    rep = _drive(cfg, s60, 60, 'step')
+    like the default kernels do (60 frames: window full, QR compression and pruning active).  Runs in a child process so
+    that a fault inside an unproven kernel cannot poison this process's CUDA context for the tests that follow."""
+    import subprocess
+    import json
+    code = (
+        "import os, sys, json\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import test_gpu as tg\n"
+        "from larvio_b200 import synth\n"
+        "from larvio_b200.config import Config\n"
+        "cfg = Config.load(os.path.join(%r, 'configs', 'euroc_mono.yaml'), max_features_in_one_grid=0, sw_size=12)\n"
+        "s60 = [synth.make_sequence(cfg.raw, s, 60) for s in range(2)]\n"
+        "rep = tg._drive(cfg, s60, 60, 'step')\n"
+        "print('REP ' + json.dumps({k: rep[k] for k in ('steps', 'ok_mismatch', 'p', 'q', 'Prel')}))\n"
+    ) % (ROOT, os.path.join(ROOT, "tests"), ROOT)
+    env = dict(os.environ, LVB_EXPERIMENT=variant)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rep = json.loads([l for l in r.stdout.splitlines() if l.startswith("REP ")][-1][4:])
     assert rep['steps'] >= 50 and rep['ok_mismatch'] == 0
     assert rep['p'] < 1e-8 and rep['q'] < 1e-8 and rep['Prel'] < 1e-8
 
