@@ -1408,6 +1408,81 @@ __global__ void __launch_bounds__(256) be_gemm_kernel(GemmArgs g) {
     }
 }
 
+// ---- staged variant (LVB_EXPERIMENT=gemm_dmma): the same batched GEMM on the FP64 tensor path.  tcgen05 has no f64
+// kind, so this is warp-level `mma.sync.m8n8k4.f64` (SASS: DMMA): 8 warps tile a 64x64 block as 4 (M) x 2 (N), each warp
+// owns 2 x 4 fragments of 8x8; per 4-deep k step a thread issues 6 shared-memory loads for 8 DMMAs (64 FMAs) where the
+// FMA kernel needs 8 loads for 16.  Operand staging, bounds handling and the epilogue are the FMA kernel's.
+constexpr int GTP = GT + 4;      // 68: (k % 4) * 68 + (m % 8) hits 16 distinct 8-byte banks per half warp
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(256) be_gemm_dmma_kernel(GemmArgs g) {
+  __shared__ double As[GK][GTP], Bs[GK][GTP];
+  const int s = blockIdx.z;
+  const int* ic = g.icore + (size_t)s * BE_ICORE;
+  if (!ic[I_OK]) return;
+  const int M = ic[g.m_idx], N = ic[g.n_idx], K = ic[g.k_idx];
+  const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+  if (m0 >= M || n0 >= N || K <= 0) return;
+  const double* A = g.A + (size_t)s * g.sA;
+  const double* B = g.B + (size_t)s * g.sB;
+  double* C = g.C + (size_t)s * g.sC;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, tig = lane & 3;                  // fragment coordinates: row/col group, index inside the group
+  const int wm = (warp >> 1) * 16, wn = (warp & 1) * 32;      // this warp's 16 x 32 patch of the 64 x 64 tile
+  double acc[2][4][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  for (int k0 = 0; k0 < K; k0 += GK) {
+    for (int i = tid; i < GT * GK; i += 256) {
+      int mm, kk;
+      if (g.rsA == 1) { mm = i % GT; kk = i / GT; } else { kk = i % GK; mm = i / GK; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < M && gk < K) ? A[(size_t)gm * g.rsA + (size_t)gk * g.csA] : 0.0;
+    }
+    for (int i = tid; i < GT * GK; i += 256) {
+      int nn, kk;
+      if (g.csB == 1) { nn = i % GT; kk = i / GT; } else { kk = i % GK; nn = i / GK; }
+      const int gn = n0 + nn, gk = k0 + kk;
+      Bs[kk][nn] = (gn < N && gk < K) ? B[(size_t)gk * g.rsB + (size_t)gn * g.csB] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; kk += 4) {
+      double a[2], b[4];
+      // A fragment (8 x 4, "row"): element (row = grp, k = tig); B fragment (4 x 8, "col"): element (k = tig, col = grp)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) a[i] = As[kk + tig][wm + 8 * i + grp];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk + tig][wn + 8 * j + grp];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    __syncthreads();
+  }
+  // C fragment (8 x 8): elements (row = grp, col = 2 * tig + {0, 1})
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int gm = m0 + wm + 8 * i + grp, gn = n0 + wn + 8 * j + 2 * tig + e;
+        if (gm < M && gn < N) {
+          double* c = C + (size_t)gm * g.rsC + (size_t)gn * g.csC;
+          double val = g.alpha * acc[i][j][e];
+          if (g.beta != 0.0) val += g.beta * *c;
+          if (gm == gn) val += g.diag_vec ? g.diag_vec[(size_t)s * g.sD + gm] : g.diag;
+          *c = val;
+        }
+      }
+}
+
 // ====================================================================== Cholesky S = L L^T (lower, in place) + z = L^-1 r
 // The packed lower triangle (r <= 208 -> <= 174 KB) lives in shared memory for the whole factorisation; the
 // right-looking update runs out of smem, L is written back to Sm (TRSM reads it) at the end.
@@ -2323,6 +2398,7 @@ int be_alloc(LvbHandle* h) {
   if (const char* ex = getenv("LVB_EXPERIMENT")) {             // staged kernel variants, off unless named
     if (strstr(ex, "chol_blocked")) h->experiments |= LVB_EXP_CHOL_BLOCKED;
     if (strstr(ex, "qr_lean")) h->experiments |= LVB_EXP_QR_LEAN;
+    if (strstr(ex, "gemm_dmma")) h->experiments |= LVB_EXP_GEMM_DMMA;
   }
   const size_t cholb_bytes = chol_bytes + sizeof(double) * (size_t)(CH_NB - 1) * be->Dmax;
   if ((h->experiments & LVB_EXP_CHOL_BLOCKED) && cholb_bytes <= 227 * 1024)
@@ -2341,6 +2417,12 @@ void be_free(LvbHandle* h) {
 
 static int launch_gemm(LvbHandle* h, const GemmArgs& g, int max_m, int max_n) {
   LvbBackEnd* be = h->be;
+  if (h->experiments & LVB_EXP_GEMM_DMMA) {
+    LVB_PROF(h, "be_gemm_dmma_kernel");
+    be_gemm_dmma_kernel<<<dim3((max_n + GT - 1) / GT, (max_m + GT - 1) / GT, be->S), 256, 0, h->stream>>>(g);
+    LVB_LAUNCH_CHECK(h);
+    return LVB_OK;
+  }
   LVB_PROF(h, "be_gemm_kernel");
   be_gemm_kernel<<<dim3((max_n + GT - 1) / GT, (max_m + GT - 1) / GT, be->S), 256, 0, h->stream>>>(g);
   LVB_LAUNCH_CHECK(h);

@@ -132,7 +132,7 @@ struct LvbHandle {
   // (DESIGN.md 7); host-only, so the kernel argument layouts of the default path do not change.
   unsigned experiments = 0;
 };
-enum { LVB_EXP_CHOL_BLOCKED = 1u, LVB_EXP_QR_LEAN = 2u };
+enum { LVB_EXP_CHOL_BLOCKED = 1u, LVB_EXP_QR_LEAN = 2u, LVB_EXP_GEMM_DMMA = 4u };
 
 extern thread_local std::string g_lvb_err;
 int lvb_set_err(int code, const char* fmt, ...);
