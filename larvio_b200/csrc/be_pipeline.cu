@@ -2399,6 +2399,7 @@ int be_alloc(LvbHandle* h) {
     if (strstr(ex, "chol_blocked")) h->experiments |= LVB_EXP_CHOL_BLOCKED;
     if (strstr(ex, "qr_lean")) h->experiments |= LVB_EXP_QR_LEAN;
     if (strstr(ex, "gemm_dmma")) h->experiments |= LVB_EXP_GEMM_DMMA;
+    if (strstr(ex, "graph")) h->experiments |= LVB_EXP_GRAPH;
   }
   const size_t cholb_bytes = chol_bytes + sizeof(double) * (size_t)(CH_NB - 1) * be->Dmax;
   if ((h->experiments & LVB_EXP_CHOL_BLOCKED) && cholb_bytes <= 227 * 1024)
@@ -2718,6 +2719,136 @@ int be_process(LvbHandle* h, const LvbFeature* d_msg, const int* d_msg_n, const 
   return LVB_OK;
 }
 
+// ---- staged variant (LVB_EXPERIMENT=graph): ONE graph launch per step.  The ~75 launches of a step do not
+// depend on data (grids follow capacities, every per-sequence decision is a device-side flag), so the enqueue halves of
+// fe_process / be_process are captured once per pyramid parity and replayed; host preparation (pinned staging of IMU,
+// homographies, stamps; the image copy, whose source pointer changes) and the read-back stay outside.  The three
+// functions below are the text of be_process cut at its two seams; they must stay in step with it until the split
+// replaces it.  Not used while the profiler or LVB_DEBUG_NAN is on (both synchronise between launches).
+static int be_graph_host_prep(LvbHandle* h, const LvbImu* imu, const int* n_imu, int imu_stride) {
+  LvbBackEnd* be = h->be;
+  const int S = be->S;
+  const double* h_msg_t = nullptr; const uint8_t* h_msg_valid = nullptr;
+  for (int s = 0; s < S; ++s) {
+    int n = n_imu[s];
+    if (n > be->imu_cap) {
+      // Only imu_cap samples are staged per call.  That is harmless while the first sample left behind is newer than
+      // anything batchImuProcessing could consume for this message (time bound = message time + td, larvio.cpp:464-512;
+      // td is estimated online, hence the 50 ms margin); otherwise the propagation would silently stop short.
+      const LvbImu* b = imu + (size_t)s * imu_stride;
+      if (h_msg_t && h_msg_valid && h_msg_valid[s] && b[be->imu_cap].t <= h_msg_t[s] + h->cfg.td + 0.05)
+        return lvb_set_err(LVB_E_CAPACITY, "sequence %d: %d pending IMU samples exceed the per-call staging capacity %d", s, n, be->imu_cap);
+      n = be->imu_cap;
+    }
+    be->pin_n_imu[s] = n;
+    memcpy(be->pin_imu + (size_t)s * be->imu_cap, imu + (size_t)s * imu_stride, sizeof(LvbImu) * n);
+  }
+  return LVB_OK;
+}
+
+static int be_graph_enqueue(LvbHandle* h) {
+  LvbBackEnd* be = h->be;
+  cudaStream_t st = h->stream;
+  const int S = be->S;
+  LVB_CUDA(cudaMemcpyAsync(be->imu, be->pin_imu, sizeof(LvbImu) * (size_t)S * be->imu_cap, cudaMemcpyHostToDevice, st));
+  LVB_CUDA(cudaMemcpyAsync(be->n_imu, be->pin_n_imu, sizeof(int) * S, cudaMemcpyHostToDevice, st));
+  BeView v = make_beview(h);
+  v.msg = h->fe.msg; v.msg_n = h->fe.msg_n; v.msg_t = h->fe.msg_t; v.msg_valid = h->fe.has_msg; v.msg_stride = h->fe.N;
+  LVB_PROF(h, "be_propagate_kernel");
+  if (be->LEG == 22) be_propagate_kernel<22><<<S, 256, sizeof(double) * (4 * 22 * 23 + 22), st>>>(v);
+  else be_propagate_kernel<46><<<S, 256, sizeof(double) * (4 * 46 * 47 + 46), st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  const int nthr = be->N <= 256 ? 256 : 512;
+  if (be->N > 512) return lvb_set_err(LVB_E_UNSUPPORTED, "max_features_num > 512");
+  LVB_PROF(h, "be_add_obs_kernel");
+  be_add_obs_kernel<<<S, nthr, sizeof(unsigned long long) * be->T, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  LVB_PROF(h, "be_augment_kernel");
+  be_augment_kernel<<<S, 256, 0, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  if (be->NFmax > 0) RC(be_remap(h, v));
+  if (h->cfg.if_ZUPT_valid) {                        // checkZUPT -> measurementUpdate_ZUPT_vpq (:405-406)
+    LVB_PROF(h, "be_zupt_build_kernel");
+    be_zupt_build_kernel<<<S, 256, 0, st>>>(v);
+    LVB_LAUNCH_CHECK(h);
+    RC(be_update(h, v, true));
+  }
+  RC(be_measurement_pass(h, v, 0));                  // removeLostFeatures
+  LVB_PROF(h, "be_apply_actions_kernel");
+  be_apply_actions_kernel<<<dim3((be->T + 127) / 128, S), 128, 0, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  LVB_PROF(h, "be_prune_select_kernel");
+  be_prune_select_kernel<<<(S + 63) / 64, 64, 0, st>>>(v);   // pruneImuStateBuffer
+  LVB_LAUNCH_CHECK(h);
+  RC(be_measurement_pass(h, v, 1));
+  LVB_PROF(h, "be_prune_tables_kernel");
+  be_prune_tables_kernel<<<S, 256, 0, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  LVB_PROF(h, "be_prune_cov_gather_kernel");
+  be_prune_cov_gather_kernel<<<dim3(be->Dmax, S), 256, 0, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  LVB_PROF(h, "be_prune_cov_scatter_kernel");
+  be_prune_cov_scatter_kernel<<<dim3(be->Dmax, S), 256, 0, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  LVB_PROF(h, "be_frame_end_kernel");
+  be_frame_end_kernel<<<(S + 63) / 64, 64, 0, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  LVB_CUDA(cudaMemcpyAsync(be->pin_icore, be->icore, sizeof(int) * (size_t)S * BE_ICORE, cudaMemcpyDeviceToHost, st));
+  return LVB_OK;
+}
+
+static int be_graph_finish(LvbHandle* h, LvbImu* imu, int* n_imu, int imu_stride, uint8_t* ok_out) {
+  LvbBackEnd* be = h->be;
+  cudaStream_t st = h->stream;
+  const int S = be->S;
+  LVB_CUDA(cudaStreamSynchronize(st));
+  int err = 0;
+  for (int s = 0; s < S; ++s) {
+    const int* ic = be->pin_icore + (size_t)s * BE_ICORE;
+    if (ok_out) ok_out[s] = (uint8_t)ic[I_OK];
+    if (ic[I_OK]) {
+      const int used = ic[I_CONSUMED];
+      if (used > 0) {                                  // larvio.cpp:510-512: erase consumed samples in place
+        LvbImu* b = imu + (size_t)s * imu_stride;
+        memmove(b, b + used, sizeof(LvbImu) * (n_imu[s] - used));
+        n_imu[s] -= used;
+      }
+      if (ic[I_ERR]) err = ic[I_ERR];
+    }
+  }
+  if (err) return lvb_set_err(LVB_E_CAPACITY, "back-end capacity exceeded (code %d: 1 feature table, 2 window, 3 raw rows, 4 stacked rows)", err);
+  return LVB_OK;
+}
+
+static int lvb_step_graph(LvbHandle* h, const uint8_t* images, int images_on_device, const double* t_img, LvbImu* imu,
+                          int* n_imu, int imu_stride, uint8_t* published) {
+  if (const char* why = be_unsupported_reason(h->cfg)) return lvb_set_err(LVB_E_UNSUPPORTED, "%s", why);
+  if (h->be->N > 512) return lvb_set_err(LVB_E_UNSUPPORTED, "max_features_num > 512");
+  cudaStream_t st = h->stream;
+  RC(fe_graph_host_prep(h, images, images_on_device, t_img, imu, n_imu, imu_stride));
+  RC(be_graph_host_prep(h, imu, n_imu, imu_stride));
+  const int par = h->fe.cur & 1;
+  if (!h->gexec[par]) {
+    cudaGraph_t graph = nullptr;
+    const long long l0 = h->launches;
+    LVB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = fe_graph_enqueue(h);
+    if (rc == LVB_OK) rc = be_graph_enqueue(h);
+    const cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc != LVB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return lvb_set_err(LVB_E_CUDA, "cudaStreamEndCapture -> %s", cudaGetErrorString(e));
+    const cudaError_t e2 = cudaGraphInstantiate(&h->gexec[par], graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) return lvb_set_err(LVB_E_CUDA, "cudaGraphInstantiate -> %s", cudaGetErrorString(e2));
+    h->glaunches[par] = h->launches - l0;
+  } else {
+    h->launches += h->glaunches[par];
+  }
+  LVB_CUDA(cudaGraphLaunch(h->gexec[par], st));
+  h->fe.cur ^= 1;
+  return be_graph_finish(h, imu, n_imu, imu_stride, published);
+}
+
 extern "C" int lvb_process_features(LvbHandle* h, const uint8_t* valid, const double* t_msg, const LvbFeature* feat,
                                     const int* n_feat, int feat_stride, LvbImu* imu, int* n_imu, int imu_stride,
                                     uint8_t* ok) {
@@ -2743,6 +2874,8 @@ extern "C" int lvb_step(LvbHandle* h, const uint8_t* images, int images_on_devic
                         int* n_imu, int imu_stride, uint8_t* published) {
   if (!h || !images || !t_img || !imu || !n_imu) return lvb_set_err(LVB_E_ARG, "lvb_step: null argument");
   LVB_CUDA(cudaSetDevice(h->device));
+  if ((h->experiments & LVB_EXP_GRAPH) && !h->prof.on && !getenv("LVB_DEBUG_NAN"))
+    return lvb_step_graph(h, images, images_on_device, t_img, imu, n_imu, imu_stride, published);
   RC(fe_process(h, images, images_on_device, t_img, imu, n_imu, imu_stride));
   LvbFrontEnd& fe = h->fe;
   // the message stays in HBM: fe.msg / msg_n / msg_t / has_msg feed processFeatures directly

@@ -94,6 +94,7 @@ extern "C" void lvb_destroy(LvbHandle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  for (int i = 0; i < 2; ++i) if (h->gexec[i]) cudaGraphExecDestroy(h->gexec[i]);
   be_free(h);
   for (void* p : h->allocs) cudaFree(p);
   if (h->pin_images) cudaFreeHost(h->pin_images);

@@ -131,8 +131,10 @@ struct LvbHandle {
   // Staged kernel variants, OFF by default: comma-separated names in LVB_EXPERIMENT select them at lvb_create time
   // (DESIGN.md 7); host-only, so the kernel argument layouts of the default path do not change.
   unsigned experiments = 0;
+  cudaGraphExec_t gexec[2] = {nullptr, nullptr};   // LVB_EXPERIMENT=graph: one captured step per pyramid parity
+  long long glaunches[2] = {0, 0};
 };
-enum { LVB_EXP_CHOL_BLOCKED = 1u, LVB_EXP_QR_LEAN = 2u, LVB_EXP_GEMM_DMMA = 4u };
+enum { LVB_EXP_CHOL_BLOCKED = 1u, LVB_EXP_QR_LEAN = 2u, LVB_EXP_GEMM_DMMA = 4u, LVB_EXP_GRAPH = 8u };
 
 extern thread_local std::string g_lvb_err;
 int lvb_set_err(int code, const char* fmt, ...);
@@ -180,3 +182,6 @@ int fe_ransac_launch(LvbHandle* h, int n_seq, int stride, const float2* p1, cons
 int fe_process(LvbHandle* h, const uint8_t* images, int on_device, const double* t_img, const LvbImu* imu,
                const int* n_imu, int imu_stride);
 int fe_fetch_messages(LvbHandle* h, LvbFeature* out_feat, int* out_n, uint8_t* has_features);
+int fe_graph_host_prep(LvbHandle* h, const uint8_t* images, int on_device, const double* t_img, const LvbImu* imu,
+                       const int* n_imu, int imu_stride);
+int fe_graph_enqueue(LvbHandle* h);
