@@ -254,6 +254,8 @@ def main():
                   l2_policy="each step reads a fresh %.1f MB image batch and touches >250 MB of per-sequence state (> 126 MB L2)" % (S * B0 / 1e6),
                   inputs=("one pool of %d seeded sequences (seed 1234+i)" % S) + ("" if world == 1 else
                           ", rendered cooperatively by the %d ranks, exchanged over NCCL, replayed on every GPU rotated by rank*%d/%d" % (world, S, world)))
+    if os.environ.get("LVB_EXPERIMENT"):
+        config["experiments"] = os.environ["LVB_EXPERIMENT"]         # staged kernel variants in effect; none by default
     ncores = os.cpu_count() or 1
 
     # ------------------------------------------------------------------ reference arm
