@@ -1721,6 +1721,79 @@ __global__ void __launch_bounds__(64) be_trsm_kernel(BeView v) {
   }
 }
 
+// ---- staged variant (LVB_EXPERIMENT=trsm_wide): Y = L^-1 T with 256 threads per 64 columns.  The 32-step dependent
+// solve of a diagonal block still runs on one thread per column, but the trailing updates - 97 % of the flops - are split
+// over four row groups (8 of the 32 tile rows each), so four times as many warps are in flight per column block.
+__global__ void __launch_bounds__(256) be_trsm_wide_kernel(BeView v) {
+  __shared__ double Lt[32][33];
+  __shared__ double Ys[32][64];
+  const int s = blockIdx.y, tid = threadIdx.x, tx = tid & 63, tg = tid >> 6;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK]) return;
+  const int r = ic[I_R], d = ic[I_DIM];
+  if (r <= 0) return;
+  const int c = blockIdx.x * 64 + tx;
+  if (blockIdx.x * 64 >= d) return;
+  const bool act = c < d;
+  const int LD = v.be.LD, LS = v.be.LDS;
+  const double* L = v.be.Sm + (size_t)s * LS * LS;
+  double* Tm = v.be.Tm + (size_t)s * v.be.RAWMAX * LD;
+  const int nb = (r + 31) / 32;
+  for (int ib = 0; ib < nb; ++ib) {
+    const int i0 = ib * 32;
+    for (int e = tid; e < 32 * 32; e += 256) {
+      const int a = e / 32, b = e % 32;
+      Lt[a][b] = (i0 + a < r && i0 + b < r) ? L[(size_t)(i0 + a) * LS + i0 + b] : ((a == b) ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    if (tg == 0) {
+      double y[32];
+#pragma unroll
+      for (int a = 0; a < 32; ++a) y[a] = (act && i0 + a < r) ? Tm[(size_t)(i0 + a) * LD + c] : 0.0;
+#pragma unroll
+      for (int a = 0; a < 32; ++a) {
+        double x = y[a];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) if (q < a) x -= Lt[a][q] * y[q];
+        y[a] = x / Lt[a][a];
+      }
+#pragma unroll
+      for (int a = 0; a < 32; ++a) {
+        if (act && i0 + a < r) Tm[(size_t)(i0 + a) * LD + c] = y[a];
+        Ys[a][tx] = y[a];
+      }
+    }
+    __syncthreads();
+    if (ib + 1 < nb) {
+      double ys[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) ys[q] = Ys[q][tx];
+      for (int jb = ib + 1; jb < nb; ++jb) {
+        const int j0 = jb * 32;
+        __syncthreads();
+        for (int e = tid; e < 32 * 32; e += 256) {
+          const int a = e / 32, b = e % 32;
+          Lt[a][b] = (j0 + a < r && i0 + b < r) ? L[(size_t)(j0 + a) * LS + i0 + b] : 0.0;
+        }
+        __syncthreads();
+        if (act) {
+#pragma unroll
+          for (int a8 = 0; a8 < 8; ++a8) {
+            const int a = tg * 8 + a8;
+            if (j0 + a < r) {
+              double x = 0.0;
+#pragma unroll
+              for (int q = 0; q < 32; ++q) x += Lt[a][q] * ys[q];
+              Tm[(size_t)(j0 + a) * LD + c] -= x;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ====================================================================== dx = Y^T z, state correction (:1476-1534, :1692-1750)
 __global__ void __launch_bounds__(256) be_correct_kernel(BeView v) {
   const int s = blockIdx.x, tid = threadIdx.x;
@@ -2400,6 +2473,7 @@ int be_alloc(LvbHandle* h) {
     if (strstr(ex, "qr_lean")) h->experiments |= LVB_EXP_QR_LEAN;
     if (strstr(ex, "gemm_dmma")) h->experiments |= LVB_EXP_GEMM_DMMA;
     if (strstr(ex, "graph")) h->experiments |= LVB_EXP_GRAPH;
+    if (strstr(ex, "trsm_wide")) h->experiments |= LVB_EXP_TRSM_WIDE;
   }
   const size_t cholb_bytes = chol_bytes + sizeof(double) * (size_t)(CH_NB - 1) * be->Dmax;
   if ((h->experiments & LVB_EXP_CHOL_BLOCKED) && cholb_bytes <= 227 * 1024)
@@ -2488,8 +2562,13 @@ static int be_update(LvbHandle* h, BeView& v, bool zupt_rows = false) {
   LVB_LAUNCH_CHECK(h);
   DBG("be_chol_gmem_kernel");
   BeView vt = v;
+  if (h->experiments & LVB_EXP_TRSM_WIDE) {
+    LVB_PROF(h, "be_trsm_wide_kernel");
+    be_trsm_wide_kernel<<<dim3((be->Dmax + 63) / 64, be->S), 256, 0, st>>>(vt);
+  } else {
   LVB_PROF(h, "be_trsm_kernel");
   be_trsm_kernel<<<dim3((be->Dmax + 63) / 64, be->S), 64, 0, st>>>(vt);
+  }
   LVB_LAUNCH_CHECK(h);
   DBG("be_trsm_kernel");
   LVB_PROF(h, "be_correct_kernel");
