@@ -141,6 +141,26 @@ def test_lk_restatement_bit_identical_to_cv2(seqs):
     assert np.array_equal(rst.reshape(-1), st)
     ok = st == 1
     assert np.array_equal(ref.reshape(-1, 2)[ok], out[ok])
+    # wider sweep: random / border points and large initial errors.  Positions stay bit-identical; status may differ only
+    # where cv2 (whose Python binding always asks for `err`) re-checks a converged point that ended >= 10 px outside the
+    # image - the reference passes noArray() and gates such points itself (see oracle/lk_exact.py).
+    rng = np.random.default_rng(5)
+    B2 = cl.apply(seqs[0].images[4])
+    P2 = np.concatenate([cv2.goodFeaturesToTrack(A, 200, 0.01, 8).reshape(-1, 2), rng.uniform([0, 0], [751, 479], (60, 2)),
+                         np.stack([rng.choice([0.0, 1.5, 750.0, 751.0], 40), rng.uniform(0, 479, 40)], 1)]).astype(np.float32)
+    for sigma in (0.3, 2.0, 8.0):
+        init2 = (P2 + rng.normal(0, sigma, P2.shape)).astype(np.float32)
+        ref2, rst2, _ = cv2.calcOpticalFlowPyrLK(A, B2, P2.reshape(-1, 1, 2), init2.reshape(-1, 1, 2).copy(), winSize=(21, 21), maxLevel=2,
+                                                 criteria=crit, flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+        out2, st2 = calc_optical_flow_pyr_lk(A, B2, P2, init2)
+        ref2 = ref2.reshape(-1, 2); rst2 = rst2.reshape(-1)
+        both = (st2 == 1) & (rst2 == 1)
+        assert np.array_equal(ref2[both], out2[both])
+        diff = np.nonzero(st2 != rst2)[0]
+        for i in diff:
+            assert st2[i] == 1 and rst2[i] == 0 and np.array_equal(ref2[i], out2[i])
+            x, y = out2[i]
+            assert x < -10 or x >= 752 + 10 or y < -10 or y >= 480 + 10
 
 
 def test_orb_vectorised_equals_literal(seqs):
