@@ -299,6 +299,208 @@ __global__ void __launch_bounds__(WARPS * 32) lk_kernel(const __grid_constant__ 
   }
 }
 
+// ---- staged variant (LVB_EXPERIMENT=lk_fused): identical arithmetic and summation order; the I_t pass and
+// the term pass of every iteration are one pass (each term's lane gathers its own 2 x 4 or 4 source bytes), which removes
+// the dd round trip through shared memory, one warp barrier and the per-pixel index arithmetic (~150 of ~640 issue slots).
+__global__ void __launch_bounds__(WARPS * 32) lk_fused_kernel(const __grid_constant__ LkArgs2 aa) {
+  __shared__ WarpSmem sm[WARPS];
+  const LkArgs& a = aa.a[blockIdx.z];
+  const int s = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * WARPS + warp;
+  if (i >= a.n_pts[s]) return;
+  WarpSmem& w = sm[warp];
+  const int slot = a.perm ? a.perm[(size_t)s * a.stride + i] : i;
+  const float2 pA = a.ptsA[(size_t)s * a.stride + slot];
+  float2 nxt;
+  if (a.Hmat) {
+    const float* H = a.Hmat + (size_t)s * 9;
+    // cv::Matx33f * Vec3f : s = 0; s += H(r,k)*v(k)   (image_processor.cpp:285-290)
+    float q[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      float acc = __fmul_rn(H[r * 3 + 0], pA.x);
+      acc = __fadd_rn(acc, __fmul_rn(H[r * 3 + 1], pA.y));
+      acc = __fadd_rn(acc, H[r * 3 + 2]);
+      q[r] = acc;
+    }
+    nxt.x = __fdiv_rn(q[0], q[2]);
+    nxt.y = __fdiv_rn(q[1], q[2]);
+  } else {
+    nxt = a.init[(size_t)s * a.stride + (a.init_by_slot ? slot : i)];
+  }
+  bool status = true;
+  const float halfWin = (WIN - 1) * 0.5f;
+
+  for (int level = a.max_level; level >= 0; --level) {
+    const LvbLevel lv = a.L.lv[level];
+    const float scale = 1.0f / (float)(1 << level);
+    float2 prevPt = make_float2(__fmul_rn(pA.x, scale), __fmul_rn(pA.y, scale));
+    if (level == a.max_level) nxt = make_float2(__fmul_rn(nxt.x, scale), __fmul_rn(nxt.y, scale));
+    else nxt = make_float2(__fmul_rn(nxt.x, 2.f), __fmul_rn(nxt.y, 2.f));
+    prevPt.x = __fsub_rn(prevPt.x, halfWin);
+    prevPt.y = __fsub_rn(prevPt.y, halfWin);
+    const int ipx = (int)floorf(prevPt.x), ipy = (int)floorf(prevPt.y);
+    if (ipx < -WIN || ipx >= lv.w || ipy < -WIN || ipy >= lv.h) {
+      if (level == 0) status = false;
+      continue;
+    }
+    const uint8_t* orgA = lvb_level_origin(a.pyrA, a.L, s, level);
+    const uint8_t* orgB = lvb_level_origin(a.pyrB, a.L, s, level);
+    __syncwarp();
+    // ---- stage the 24x24 source tile (origin ipx-1, ipy-1)
+    for (int t = lane; t < TILE * TILE; t += 32) {
+      const int ty = t / TILE, tx = t - ty * TILE;
+      w.u.st.tile[t] = __ldg(orgA + (ptrdiff_t)(ipy - 1 + ty) * lv.pitch + (ipx - 1 + tx));
+    }
+    __syncwarp();
+    // ---- Scharr derivatives on the 22x22 grid (zero outside the image)
+    for (int t = lane; t < DT * DT; t += 32) {
+      const int dy = t / DT, dx = t - dy * DT;
+      const int gx = ipx + dx, gy = ipy + dy;
+      short2 d = make_short2(0, 0);
+      if (gx >= 0 && gx < lv.w && gy >= 0 && gy < lv.h) {
+        const uint8_t* c = &w.u.st.tile[(dy + 1) * TILE + (dx + 1)];
+        const int tl = c[-TILE - 1], tc = c[-TILE], tr = c[-TILE + 1];
+        const int ml = c[-1], mr = c[1];
+        const int bl = c[TILE - 1], bc = c[TILE], br = c[TILE + 1];
+        d.x = (short)(3 * (tr + br - tl - bl) + 10 * (mr - ml));
+        d.y = (short)(3 * (bl + br - tl - tr) + 10 * (bc - tc));
+      }
+      w.u.st.dtile[t] = d;
+    }
+    __syncwarp();
+    // ---- window of the previous image
+    float fa = __fsub_rn(prevPt.x, (float)ipx), fb = __fsub_rn(prevPt.y, (float)ipy);
+    int iw00 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, fa), __fsub_rn(1.f, fb)), (float)(1 << W_BITS)));
+    int iw01 = __float2int_rn(__fmul_rn(__fmul_rn(fa, __fsub_rn(1.f, fb)), (float)(1 << W_BITS)));
+    int iw10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, fa), fb), (float)(1 << W_BITS)));
+    int iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+    for (int p = lane; p < NPIX; p += 32) {
+      const int y = p / WIN, x = p - y * WIN;
+      const uint8_t* c = &w.u.st.tile[(y + 1) * TILE + (x + 1)];
+      const int ival = (c[0] * iw00 + c[1] * iw01 + c[TILE] * iw10 + c[TILE + 1] * iw11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+      const short2 d00 = w.u.st.dtile[y * DT + x], d01 = w.u.st.dtile[y * DT + x + 1];
+      const short2 d10 = w.u.st.dtile[(y + 1) * DT + x], d11 = w.u.st.dtile[(y + 1) * DT + x + 1];
+      const int ix = (d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
+      const int iy = (d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
+      w.Iw[p] = (short)ival;
+      w.dIw[p] = make_short2((short)ix, (short)iy);
+    }
+    __syncwarp();
+    // terms of A11, A12, A22 in OpenCV's lane order (the tile/dtile staging area is dead from here on)
+    for (int p = lane; p < NPIX; p += 32) {
+      const int y = p / WIN, x = p - y * WIN;
+      const short2 d = w.dIw[p];
+      const float fx = (float)d.x, fy = (float)d.y;
+      const int slot = (x < 16) ? ((x & 3) * (WIN * 4) + y * 4 + (x >> 2)) : (WIN * 16 + y * 5 + (x - 16));
+      w.u.termA[slot] = __fmul_rn(fx, fx);
+      w.u.termA[NTERM_A + slot] = __fmul_rn(fx, fy);
+      w.u.termA[2 * NTERM_A + slot] = __fmul_rn(fy, fy);
+    }
+    __syncwarp();
+    float chainv = 0.f;
+    if (lane < 15) chainv = run_chain<4>(w.u.termA + (lane / 5) * NTERM_A, lane % 5);
+    const float FLT_SCALE = 1.f / (float)(1 << 20);
+    float A11 = __fmul_rn(combine_chains(chainv, 0), FLT_SCALE);
+    float A12 = __fmul_rn(combine_chains(chainv, 5), FLT_SCALE);
+    float A22 = __fmul_rn(combine_chains(chainv, 10), FLT_SCALE);
+    __syncwarp();
+    float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+    const float dif = __fsub_rn(A11, A22);
+    const float rad = __fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.f, A12), A12));
+    const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(rad)), (float)(2 * WIN * WIN));
+    if ((double)minEig < a.min_eig || D < 1.1920929e-07f) {
+      if (level == 0) status = false;
+      continue;
+    }
+    D = __fdiv_rn(1.f, D);
+    float2 np = make_float2(__fsub_rn(nxt.x, halfWin), __fsub_rn(nxt.y, halfWin));
+    float2 prevDelta = make_float2(0.f, 0.f);
+    for (int j = 0; j < a.max_iter; ++j) {
+      const int inx = (int)floorf(np.x), iny = (int)floorf(np.y);
+      if (inx < -WIN || inx >= lv.w || iny < -WIN || iny >= lv.h) {
+        if (level == 0) status = false;
+        break;
+      }
+      fa = __fsub_rn(np.x, (float)inx);
+      fb = __fsub_rn(np.y, (float)iny);
+      iw00 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, fa), __fsub_rn(1.f, fb)), (float)(1 << W_BITS)));
+      iw01 = __float2int_rn(__fmul_rn(__fmul_rn(fa, __fsub_rn(1.f, fb)), (float)(1 << W_BITS)));
+      iw10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, fa), fb), (float)(1 << W_BITS)));
+      iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+      const uint8_t* jbase = orgB + (ptrdiff_t)iny * lv.pitch + inx;
+      // fused I_t + term pass: work item t < 168 is a pair term of OpenCV's b sums (pixels i0 and i0 + 4 of one 8-pixel chunk),
+      // t >= 168 a scalar-tail term; the lane that owns the term gathers its own pixels, so I_t never goes through shared memory
+      const int pitch = lv.pitch;
+      for (int t = lane; t < WIN * 13; t += 32) {
+        float t1, t2;
+        if (t < WIN * 8) {
+          const int y = t >> 3, ch = (t >> 2) & 1, p = t & 3;
+          const int i0 = y * WIN + 8 * ch + p, i1 = i0 + 4;
+          const uint8_t* c0 = jbase + y * pitch + 8 * ch + p;
+          const int a00 = __ldg(c0), a01 = __ldg(c0 + 1), a10 = __ldg(c0 + pitch), a11 = __ldg(c0 + pitch + 1);
+          const int b00 = __ldg(c0 + 4), b01 = __ldg(c0 + 5), b10 = __ldg(c0 + pitch + 4), b11 = __ldg(c0 + pitch + 5);
+          const int d0 = (int)(short)(((a00 * iw00 + a01 * iw01 + a10 * iw10 + a11 * iw11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5)) - (int)w.Iw[i0]);
+          const int d1 = (int)(short)(((b00 * iw00 + b01 * iw01 + b10 * iw10 + b11 * iw11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5)) - (int)w.Iw[i1]);
+          const short2 g0 = w.dIw[i0], g1 = w.dIw[i1];
+          t1 = (float)(d0 * g0.x + d1 * g1.x);
+          t2 = (float)(d0 * g0.y + d1 * g1.y);
+          const int slot = p * (WIN * 2) + y * 2 + ch;
+          w.u.termB[slot] = t1;
+          w.u.termB[NTERM_B + slot] = t2;
+        } else {
+          const int q = t - WIN * 8, y = q / 5, x = 16 + q - y * 5;
+          const int i0 = y * WIN + x;
+          const uint8_t* c0 = jbase + y * pitch + x;
+          const int a00 = __ldg(c0), a01 = __ldg(c0 + 1), a10 = __ldg(c0 + pitch), a11 = __ldg(c0 + pitch + 1);
+          const int d0 = (int)(short)(((a00 * iw00 + a01 * iw01 + a10 * iw10 + a11 * iw11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5)) - (int)w.Iw[i0]);
+          const short2 g0 = w.dIw[i0];
+          t1 = (float)(d0 * g0.x);
+          t2 = (float)(d0 * g0.y);
+          w.u.termB[t] = t1;
+          w.u.termB[NTERM_B + t] = t2;
+        }
+      }
+      __syncwarp();
+      float cv = 0.f;
+      if (lane < 10) cv = run_chain<2>(w.u.termB + (lane / 5) * NTERM_B, lane % 5);
+      const float b1 = __fmul_rn(combine_chains(cv, 0), FLT_SCALE);
+      const float b2 = __fmul_rn(combine_chains(cv, 5), FLT_SCALE);
+      __syncwarp();
+      float2 delta;
+      delta.x = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+      delta.y = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+      np.x = __fadd_rn(np.x, delta.x);
+      np.y = __fadd_rn(np.y, delta.y);
+      nxt = make_float2(__fadd_rn(np.x, halfWin), __fadd_rn(np.y, halfWin));
+      const double dd = (double)delta.x * (double)delta.x + (double)delta.y * (double)delta.y;
+      if (dd <= a.eps2) break;
+      if (j > 0 && (double)fabsf(__fadd_rn(delta.x, prevDelta.x)) < 0.01 && (double)fabsf(__fadd_rn(delta.y, prevDelta.y)) < 0.01) {
+        nxt.x = __fsub_rn(nxt.x, __fmul_rn(delta.x, 0.5f));
+        nxt.y = __fsub_rn(nxt.y, __fmul_rn(delta.y, 0.5f));
+        break;
+      }
+      prevDelta = delta;
+    }
+  }
+
+  if (lane == 0) {
+    const LvbLevel l0 = a.L.lv[0];
+    if (status && a.gate_mode >= 1) {
+      if (nxt.y < 0.f || nxt.y > (float)(l0.h - 1) || nxt.x < 0.f || nxt.x > (float)(l0.w - 1)) status = false;
+    }
+    if (status && a.gate_mode == 2) {
+      const float2 r = a.ref[(size_t)s * a.stride + slot];
+      const float dx = __fsub_rn(nxt.x, r.x), dy = __fsub_rn(nxt.y, r.y);
+      const float dis = (float)sqrt((double)dx * (double)dx + (double)dy * (double)dy);
+      if (dis > 1.f) status = false;
+    }
+    a.out[(size_t)s * a.stride + i] = nxt;
+    a.status[(size_t)s * a.stride + i] = status ? 1 : 0;
+  }
+}
+
 }  // namespace
 
 static void fill_lk_args(LvbHandle* h, LkArgs& a, const uint8_t* pyrA, const uint8_t* pyrB, int stride, const float2* ptsA,
@@ -321,6 +523,12 @@ int fe_lk_launch(LvbHandle* h, const uint8_t* pyrA, const uint8_t* pyrB, int n_s
   fill_lk_args(h, aa.a[0], pyrA, pyrB, stride, ptsA, perm, n_pts, init, init_by_slot, Hmat, out, status, gate_mode, ref);
   aa.a[1] = aa.a[0];
   dim3 grd((stride + WARPS - 1) / WARPS, n_seq, 1);
+  if (h->experiments & LVB_EXP_LK_FUSED) {
+    LVB_PROF(h, "lk_fused_kernel");
+    lk_fused_kernel<<<grd, WARPS * 32, 0, h->stream>>>(aa);
+    LVB_LAUNCH_CHECK(h);
+    return LVB_OK;
+  }
   LVB_PROF(h, "lk_kernel");
   lk_kernel<<<grd, WARPS * 32, 0, h->stream>>>(aa);
   LVB_LAUNCH_CHECK(h);
@@ -337,6 +545,12 @@ int fe_lk_launch2(LvbHandle* h, const uint8_t* pyrA, const uint8_t* pyrB, int n_
     fill_lk_args(h, aa.a[c], pyrA, pyrB, stride, ptsA[c], perm[c], n_pts[c], init ? init[c] : nullptr, init_by_slot, Hmat, out[c],
                  status[c], gate_mode, ref ? ref[c] : nullptr);
   dim3 grd((stride + WARPS - 1) / WARPS, n_seq, 2);
+  if (h->experiments & LVB_EXP_LK_FUSED) {
+    LVB_PROF(h, "lk_fused_kernel");
+    lk_fused_kernel<<<grd, WARPS * 32, 0, h->stream>>>(aa);
+    LVB_LAUNCH_CHECK(h);
+    return LVB_OK;
+  }
   LVB_PROF(h, "lk_kernel");
   lk_kernel<<<grd, WARPS * 32, 0, h->stream>>>(aa);
   LVB_LAUNCH_CHECK(h);

@@ -134,7 +134,7 @@ struct LvbHandle {
   cudaGraphExec_t gexec[2] = {nullptr, nullptr};   // LVB_EXPERIMENT=graph: one captured step per pyramid parity
   long long glaunches[2] = {0, 0};
 };
-enum { LVB_EXP_CHOL_BLOCKED = 1u, LVB_EXP_QR_LEAN = 2u, LVB_EXP_GEMM_DMMA = 4u, LVB_EXP_GRAPH = 8u, LVB_EXP_TRSM_WIDE = 16u };
+enum { LVB_EXP_CHOL_BLOCKED = 1u, LVB_EXP_QR_LEAN = 2u, LVB_EXP_GEMM_DMMA = 4u, LVB_EXP_GRAPH = 8u, LVB_EXP_TRSM_WIDE = 16u, LVB_EXP_LK_FUSED = 32u };
 
 extern thread_local std::string g_lvb_err;
 int lvb_set_err(int code, const char* fmt, ...);

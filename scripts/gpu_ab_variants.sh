@@ -3,7 +3,7 @@
 #   gpurun --timeout 1500 -- 'bash scripts/gpu_ab_variants.sh'
 # Output: gpurun_out/ab_<variant>.json (bench JSON lines) and gpurun_out/ab_summary.txt.
 set -u
-VARIANTS=${VARIANTS:-"none chol_blocked qr_lean gemm_dmma trsm_wide graph chol_blocked,qr_lean,gemm_dmma,trsm_wide chol_blocked,qr_lean,gemm_dmma,trsm_wide,graph"}
+VARIANTS=${VARIANTS:-"none chol_blocked qr_lean gemm_dmma trsm_wide lk_fused graph chol_blocked,qr_lean,gemm_dmma,trsm_wide,lk_fused chol_blocked,qr_lean,gemm_dmma,trsm_wide,lk_fused,graph"}
 STEPS=${STEPS:-60}
 STREAMS=${STREAMS:-4}
 mkdir -p gpurun_out
