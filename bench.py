@@ -60,6 +60,30 @@ NCU_TRAFFIC_PER_SEQ = {"lk_kernel": (55.305472e6 + 1.048832e6) / 64, "be_chol_ke
                        "be_trsm_kernel": 6.039296e6 / 64, "be_propagate_kernel": 2.5344e6 / 64, "select_kernel": 3.261184e6 / 64}
 
 
+def effective_cores():
+    """Host cores this process may actually use: the scheduler affinity mask capped by the cgroup CPU quota (a container
+    can see 64 CPUs in os.cpu_count() and be allowed 16)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    if quota:
+        n = max(1, min(n, int(quota + 0.5)))
+    return n
+
+
 def load_cfg(args):
     if getattr(args, "workload", "C") == "D":
         # BASELINE configs[3] per GPU: 1-D inverse-depth hybrid (5x6 grid, one SLAM feature per cell), online extrinsic / td /
@@ -87,10 +111,35 @@ def _gen_one(a):
 
 
 def generate(cfg_raw, seq_ids, n_frames, procs):
+    """Render the seeded sequences on the host cores.  The result is cached on local disk (LVB_BENCH_CACHE, default
+    /tmp/lvb_bench_cache; "off" disables) keyed by config + ids + length, so the arms the driver runs back to back on one
+    box (reference first, then this repo's) replay byte-identical inputs without rendering them twice."""
     global _GEN_CFG
+    import hashlib
+    import pickle
+    cache = os.environ.get("LVB_BENCH_CACHE", "/tmp/lvb_bench_cache")
+    path = None
+    if cache != "off" and seq_ids:
+        key = hashlib.sha1(json.dumps([cfg_raw, list(seq_ids), n_frames], sort_keys=True, default=str).encode()).hexdigest()[:20]
+        path = os.path.join(cache, "seqs_%s.pkl" % key)
+        try:
+            with open(path, "rb") as f:
+                return pickle.load(f)
+        except Exception:
+            pass
     _GEN_CFG = cfg_raw
     with mp.get_context("fork").Pool(min(procs, len(seq_ids))) as pool:
-        return pool.map(_gen_one, [(s, n_frames) for s in seq_ids], chunksize=1)
+        out = pool.map(_gen_one, [(s, n_frames) for s in seq_ids], chunksize=1)
+    if path:
+        try:
+            os.makedirs(cache, exist_ok=True)
+            tmp = path + ".%d.tmp" % os.getpid()
+            with open(tmp, "wb") as f:
+                pickle.dump(out, f, protocol=4)
+            os.replace(tmp, path)
+        except Exception:
+            pass
+    return out
 
 
 # ----------------------------------------------------------------------------- CPU arm: oracle port, one worker per core
@@ -114,6 +163,7 @@ def _cpu_worker(conn, cfg_raw, seqs):
         if cmd[0] == "quit":
             break
         a, b = cmd[1], cmd[2]
+        cpu0 = time.process_time(); w0 = time.perf_counter()
         for j in range(a, b):
             for s in st:
                 sq = s["seq"]
@@ -129,7 +179,8 @@ def _cpu_worker(conn, cfg_raw, seqs):
                     except NotImplementedError:
                         pass
                     s["t_be"] += time.perf_counter() - t1; s["n_be"] += 1
-        conn.send(("done", sum(s["t_fe"] for s in st), sum(s["t_be"] for s in st), sum(s["n_be"] for s in st)))
+        util = (time.process_time() - cpu0) / max(time.perf_counter() - w0, 1e-9)
+        conn.send(("done", sum(s["t_fe"] for s in st), sum(s["t_be"] for s in st), sum(s["n_be"] for s in st), util))
         for s in st:
             s["t_fe"] = s["t_be"] = 0.0; s["n_be"] = 0
 
@@ -153,6 +204,7 @@ class CpuArm:
             c.send(("run", a, b))
         res = [c.recv() for c in self.conns]
         dt = time.perf_counter() - t0
+        self.last_util = float(np.mean([r[4] for r in res]))      # mean per-worker CPU utilisation (1.0 = a core to itself)
         return dt, sum(r[1] for r in res), sum(r[2] for r in res), sum(r[3] for r in res)
 
     def close(self):
@@ -217,8 +269,8 @@ def kernel_models(S_sub, stats, n_frames, n_sub):
     m["clahe_apply_kernel"] = ("hbm", 2 * B0 * S_sub, "read + write 752x480 u8 per sequence")
     m["pyrdown_kernel"] = ("hbm", (B0 + B0 // 4 + B0 // 4 + B0 // 16) // 2 * S_sub, "SURVEY F3 over its 2 launches")
     m["blur7_kernel"] = ("hbm", 2 * B0 * S_sub, "SURVEY F4")
-    m["mineig_kernel"] = ("hbm", (B0 + 4 * B0) * det_runs / nl, "u8 in + f32 response out, sequences that detect")
-    m["candidates_kernel"] = ("hbm", (4 * B0 + B0) * det_runs / nl, "f32 response + u8 mask in")
+    m["mineig_kernel"] = ("hbm", B0 * det_runs / nl, "SURVEY F5 pass 1: read 752x480 u8 of the sequences that detect")
+    m["candidates_kernel"] = ("hbm", B0 * det_runs / nl, "SURVEY F5 pass 2: one more pass over 752x480 per detecting sequence")
     m["lk_kernel"] = ("hbm", 6060.0 * lk_pts / (2 * nl), "6060 B per point-track (SURVEY F6), 2 launches per frame")
     m["orb_kernel"] = ("hbm", 2986.0 * orb_desc / (3 * nl), "2986 B per descriptor (SURVEY F7), 3 launches per frame")
     m["be_gemm_kernel"] = ("fp64", (4.0 * sum_rdd / (6 * nl)) if upd else None, "T=HP and P-=Y^TY: 2rd^2 each (S=TH^T not counted), 6 launches per frame")
@@ -235,7 +287,9 @@ def main():
     ap.add_argument("--seqs", type=int, default=64, help="sequences per GPU (BASELINE configs[2]: 64)")
     ap.add_argument("--tracks", type=int, default=200)
     ap.add_argument("--window", type=int, default=30)
-    ap.add_argument("--cpu-frames", type=int, default=16, help="frames per sequence of the bounded cpu_baseline sample")
+    ap.add_argument("--preroll", type=int, default=70,
+                    help="untimed frames every arm runs before --warmup so that the sliding window is full (30 poses at 10 Hz publishing = 60 frames)")
+    ap.add_argument("--cpu-frames", type=int, default=12, help="timed frames per sequence of the bounded cpu_baseline sample (after the pre-roll)")
     ap.add_argument("--profile-steps", type=int, default=8)
     ap.add_argument("--workload", choices=["C", "D"], default="C",
                     help="C = BASELINE configs[2] (MSCKF-only, the headline); D = configs[3] per GPU (1-D IDP hybrid + online calibration)")
@@ -247,40 +301,42 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     S, K, Wm = args.seqs, args.steps, args.warmup
+    PR = max(args.preroll, 0)
     cfg = load_cfg(args)
     workload = ("configs[2]: %d batched synthetic 752x480@20Hz+200Hz-IMU sequences per GPU, %d tracks, %d-pose window, MSCKF-only" if args.workload == "C" else
                 "configs[3] per GPU: %d batched synthetic sequences, %d tracks, %d-pose window, 1-D IDP hybrid (5x6 grid) + online extrinsic/td/IMU-intrinsic calibration") % (S, args.tracks, args.window)
-    config = dict(workload=workload, sequences_per_gpu=S, sub_batches_per_gpu=args.streams, tracks=args.tracks, window=args.window, image="752x480 u8",
+    config = dict(workload=workload, preroll_frames=PR, sequences_per_gpu=S, sub_batches_per_gpu=args.streams, tracks=args.tracks, window=args.window, image="752x480 u8",
                   l2_policy="each step reads a fresh %.1f MB image batch and touches >250 MB of per-sequence state (> 126 MB L2)" % (S * B0 / 1e6),
                   inputs=("one pool of %d seeded sequences (seed 1234+i)" % S) + ("" if world == 1 else
                           ", rendered cooperatively by the %d ranks, exchanged over NCCL, replayed on every GPU rotated by rank*%d/%d" % (world, S, world)))
     if os.environ.get("LVB_EXPERIMENT"):
         config["experiments"] = os.environ["LVB_EXPERIMENT"]         # staged kernel variants in effect; none by default
-    ncores = os.cpu_count() or 1
+    ncores = effective_cores()
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return 0
-        n_frames = Wm + K
+        n_frames = PR + Wm + K + args.profile_steps          # same length as the GPU arm renders (shared input cache)
         seqs = generate(cfg.raw, list(range(S)), n_frames, ncores)
         arm = CpuArm(cfg.raw, seqs, ncores)
-        arm.run(0, Wm)
-        dt, tfe, tbe, nbe = arm.run(Wm, Wm + K)
+        arm.run(0, PR + Wm)                      # untimed: fill the sliding window, then the warm-up steps
+        dt, tfe, tbe, nbe = arm.run(PR + Wm, PR + Wm + K)
+        util = arm.last_util
         arm.close()
         val = S * K / dt
         line = dict(metric="batched VIO frames/sec", value=val, unit="frames/s", n_gpus=args.gpus, steps=K, warmup=Wm,
                     ms_per_step=1e3 * dt / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8+f32 front end, f64 filter",
                     data="synthetic", config=config, impl="reference",
-                    cpu_baseline=dict(value=val, unit="frames/s", cores=arm.cores, kind="port",
-                                      sample="%d sequences x %d frames, cv2 4.13 front end + numpy f64 back end (oracle/), one sequence per process" % (S, K),
+                    cpu_baseline=dict(value=val, unit="frames/s", cores=arm.cores, kind="port", os_cpu_count=os.cpu_count(), worker_cpu_utilisation=util,
+                                      sample="%d sequences x %d frames after a %d-frame pre-roll, cv2 4.13 front end + numpy f64 back end (oracle/), one worker process per core" % (S, K, PR + Wm),
                                       fe_ms_per_frame=1e3 * tfe / (S * K), be_ms_per_update=1e3 * tbe / max(nbe, 1)),
                     e2e=dict(value=val, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return 0
 
     # ------------------------------------------------------------------ our arm
-    n_frames = Wm + K + args.profile_steps
+    n_frames = PR + Wm + K + args.profile_steps
     # One pool of S seeded sequences per job.  With N ranks every rank renders S/N of them on its share of the host
     # cores (before CUDA is touched: the generator forks), the pool is exchanged with one NCCL all_gather per field,
     # and rank r replays the pool rotated by r*S/N - so host-side image synthesis does not grow with the GPU count
@@ -291,15 +347,18 @@ def main():
     seqs = generate(cfg.raw, seq_ids, n_frames, max(1, ncores // max(world, 1))) if seq_ids else []
     t_gen = time.time() - t_gen
     cpu_baseline = None
-    if rank == 0 and world == 1:
-        nf = min(args.cpu_frames, n_frames)
-        arm = CpuArm(cfg.raw, seqs, ncores)
-        arm.run(0, 4)
-        dt, tfe, tbe, nbe = arm.run(4, nf)
+    if rank == 0 and world == 1 and args.cpu_frames > 0:
+        # bounded sample of the same workload at the same steady state: one sequence per usable core, pre-rolled like the GPU arm
+        ncpu = min(S, ncores)
+        nf = min(args.cpu_frames, n_frames - PR)
+        arm = CpuArm(cfg.raw, seqs[:ncpu], ncores)
+        arm.run(0, PR)
+        dt, tfe, tbe, nbe = arm.run(PR, PR + nf)
+        util = arm.last_util
         arm.close()
-        cpu_baseline = dict(value=S * (nf - 4) / dt, unit="frames/s", cores=arm.cores, kind="port",
-                            sample="%d sequences x %d frames of the same workload; cv2 4.13 front end + numpy f64 back end (oracle/)" % (S, nf - 4),
-                            fe_ms_per_frame=1e3 * tfe / (S * (nf - 4)), be_ms_per_update=1e3 * tbe / max(nbe, 1))
+        cpu_baseline = dict(value=ncpu * nf / dt, unit="frames/s", cores=arm.cores, kind="port", os_cpu_count=os.cpu_count(), worker_cpu_utilisation=util,
+                            sample="%d sequences (one per core) x %d frames after a %d-frame pre-roll of the same workload; cv2 4.13 front end + numpy f64 back end (oracle/)" % (ncpu, nf, PR),
+                            fe_ms_per_frame=1e3 * tfe / (ncpu * nf), be_ms_per_update=1e3 * tbe / max(nbe, 1))
 
     import torch
     import torch.distributed as dist
@@ -399,18 +458,22 @@ def main():
     # ---- device-resident pass: `value`
     dev_frames = pinned.to("cuda", non_blocking=False)
     st = fresh_state()
-    run_pass("dev", 0, Wm, st)
+    run_pass("dev", 0, PR + Wm, st)          # untimed: pre-roll to a full sliding window, then the warm-up steps
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None      # NVML samples over the timed region (5 ms period)
     l0 = launches_total()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(); t0 = time.perf_counter()
-    run_pass("dev", Wm, Wm + K, st)
+    run_pass("dev", PR + Wm, PR + Wm + K, st)
     e1.record(); torch.cuda.synchronize(); wall = time.perf_counter() - t0
     ms_dev = max(e0.elapsed_time(e1), 1e3 * wall * 0.0)     # each step ends with a stream sync, so events == wall
     barrier()
     clocks = sampler.stop() if sampler else None
     launches = launches_total() - l0
+    # steady-state evidence: sliding-window fill and state dimension of every sequence right after the timed region
+    ic = np.array([bb.debug_icore(q) for bb in batches for q in range(bb.S)])
+    steady = dict(window_poses_mean=float(ic[:, 2].mean()), window_poses_min=int(ic[:, 2].min()), state_dim_mean=float(ic[:, 7].mean()),
+                  window_capacity=int(args.window))
     # ---- per-kernel profile on the next frames (not part of the timed region)
     prof = {}
     prof_stats = []
@@ -419,7 +482,7 @@ def main():
         for bb in batches:
             bb.profile(True)
         for i in range(NSUB):                      # one sub-batch at a time: per-kernel times without co-running streams
-            sub_pass(i, "dev", Wm + K, n_frames, st)
+            sub_pass(i, "dev", PR + Wm + K, n_frames, st)
         for bb in batches:
             for kname, (ms, cnt) in bb.profile_get().items():
                 a0, c0 = prof.get(kname, (0.0, 0))
@@ -430,11 +493,12 @@ def main():
     # ---- end-to-end pass: `e2e` (fresh filters, same frames, host buffers)
     reset_batch()
     st = fresh_state()
-    run_pass("e2e", 0, Wm, st)
+    run_pass("dev", 0, PR, st)               # untimed pre-roll (device-resident frames), then warm-up through the host-buffer path
+    run_pass("e2e", PR, PR + Wm, st)
     barrier()
     e2 = torch.cuda.Event(enable_timing=True); e3 = torch.cuda.Event(enable_timing=True)
     e2.record(); t0 = time.perf_counter()
-    run_pass("e2e", Wm, Wm + K, st)
+    run_pass("e2e", PR + Wm, PR + Wm + K, st)
     e3.record(); torch.cuda.synchronize(); wall_e2e = time.perf_counter() - t0
     ms_e2e = max(e2.elapsed_time(e3), 0.0)
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
@@ -467,6 +531,10 @@ def main():
         kernel_share = {kname: dict(ms_per_launch=v[0] / max(v[1], 1), launches=v[1], share=v[0] / tot) for kname, v in top}
         dom, (dom_ms, dom_n) = top[0]
         pstats = [sum(x) for x in zip(*prof_stats)] if prof_stats else [0] * 16
+        if pstats[4]:
+            steady.update(mean_update_rows_r=pstats[5] / pstats[4], mean_stacked_rows=pstats[7] / pstats[4], qr_runs_per_update=pstats[8] / pstats[4])
+        lk_paths = dict(point_tracks=pstats[0], iterations=pstats[10], slow_path_iterations=pstats[11], slow_path_setups=pstats[12], tile_restages=pstats[13],
+                        iterations_per_point_track=(pstats[10] / pstats[0] if pstats[0] else None))
         models = kernel_models(S // NSUB, pstats, args.profile_steps, NSUB)
         roofs = {}
         for kname, v in top:
@@ -505,7 +573,7 @@ def main():
                     dtype="u8+f32 front end, f64 filter", data="synthetic", config=config,
                     e2e=dict(value=e2e_val, unit="frames/s", h2d_bytes_per_step=int(S * B0 + S * 10 * 56), d2h_bytes_per_step=int(S * 17 * 8 + S * 32 * 4 + S)),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, kernels=kernel_share, kernel_rooflines=roofs, work_counters=pstats,
-                    ekf_update_ms=ekf_ms, step_roofline=step_roof, cpu_baseline=cpu_baseline, gen_seconds=t_gen, wall_dev_s=wall, wall_e2e_s=wall_e2e)
+                    steady_state=steady, lk_paths=lk_paths, ekf_update_ms=ekf_ms, step_roofline=step_roof, cpu_baseline=cpu_baseline, gen_seconds=t_gen, wall_dev_s=wall, wall_e2e_s=wall_e2e)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

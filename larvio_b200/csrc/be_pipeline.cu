@@ -2474,7 +2474,6 @@ int be_alloc(LvbHandle* h) {
     if (strstr(ex, "gemm_dmma")) h->experiments |= LVB_EXP_GEMM_DMMA;
     if (strstr(ex, "graph")) h->experiments |= LVB_EXP_GRAPH;
     if (strstr(ex, "trsm_wide")) h->experiments |= LVB_EXP_TRSM_WIDE;
-    if (strstr(ex, "lk_fused")) h->experiments |= LVB_EXP_LK_FUSED;
   }
   const size_t cholb_bytes = chol_bytes + sizeof(double) * (size_t)(CH_NB - 1) * be->Dmax;
   if ((h->experiments & LVB_EXP_CHOL_BLOCKED) && cholb_bytes <= 227 * 1024)

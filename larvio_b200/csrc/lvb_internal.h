@@ -1,6 +1,7 @@
 // Internal layout of a larvio_b200 handle: every per-sequence container of the reference
 //  as fixed-capacity SoA arrays resident in HBM for the whole run.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -131,10 +132,12 @@ struct LvbHandle {
   // Staged kernel variants, OFF by default: comma-separated names in LVB_EXPERIMENT select them at lvb_create time
   // (DESIGN.md 7); host-only, so the kernel argument layouts of the default path do not change.
   unsigned experiments = 0;
+  CUtensorMap lk_maps[2][LVB_MAX_LEVELS];          // TMA descriptors of the two ping-pong pyramids (fe_lk.cu), built on first use
+  bool lk_maps_ok[2] = {false, false};
   cudaGraphExec_t gexec[2] = {nullptr, nullptr};   // LVB_EXPERIMENT=graph: one captured step per pyramid parity
   long long glaunches[2] = {0, 0};
 };
-enum { LVB_EXP_CHOL_BLOCKED = 1u, LVB_EXP_QR_LEAN = 2u, LVB_EXP_GEMM_DMMA = 4u, LVB_EXP_GRAPH = 8u, LVB_EXP_TRSM_WIDE = 16u, LVB_EXP_LK_FUSED = 32u };
+enum { LVB_EXP_CHOL_BLOCKED = 1u, LVB_EXP_QR_LEAN = 2u, LVB_EXP_GEMM_DMMA = 4u, LVB_EXP_GRAPH = 8u, LVB_EXP_TRSM_WIDE = 16u };
 
 extern thread_local std::string g_lvb_err;
 int lvb_set_err(int code, const char* fmt, ...);

@@ -239,6 +239,8 @@ def _drive(cfg, seqs, nf, mode, S=2):
             rep['q'] = max(rep['q'], float(min(np.abs(st['q'] - o.q).max(), np.abs(st['q'] + o.q).max())))
             P = b.get_covariance(s)
             assert P.shape == bes[s].P.shape
+            rep['max_dim'] = max(rep.get('max_dim', 0), int(P.shape[0]))
+            rep['max_slam'] = max(rep.get('max_slam', 0), len(getattr(bes[s], 'feature_states', [])))
             assert np.abs(P - P.T).max() == 0.0                               # symmetric by construction
             rep['Prel'] = max(rep['Prel'], float(np.linalg.norm(P - bes[s].P) / np.linalg.norm(bes[s].P)))
             cal = b.get_calibration(s)
@@ -498,7 +500,7 @@ def test_cpp_replay_driver_matches_the_python_two_call_path(tmp_path, lib_built)
 
 
 @pytest.mark.xfail(strict=False, reason="staged kernel variants (LVB_EXPERIMENT), written after the GPU budget of round 1 was spent; off by default")
-@pytest.mark.parametrize("variant", ["chol_blocked,qr_lean", "gemm_dmma,trsm_wide", "lk_fused", "graph"])
+@pytest.mark.parametrize("variant", ["chol_blocked,qr_lean", "gemm_dmma,trsm_wide", "graph"])
 def test_staged_kernel_variants_keep_parity(variant):
     """blocked Cholesky / 2-barrier QR / DMMA GEMM / one-graph-per-step selected by LVB_EXPERIMENT at lvb_create time must reproduce the oracle
     like the default kernels do (60 frames: window full, QR compression and pruning active).  Runs in a child process so
@@ -583,6 +585,79 @@ def test_batch_invariance_and_properties_at_full_batch(cfg, seqs):
         assert np.abs(P - P.T).max() == 0.0 and np.linalg.eigvalsh(P).min() > -1e-12
         assert abs(np.linalg.norm(st[s, 1:5]) - 1) < 1e-9
     b.close()
+
+
+def _pool_sequences(cfg_raw, ids, n_frames):
+    """Render sequences on all host cores (fork pool, as bench.py does)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    return bench.generate(cfg_raw, list(ids), n_frames, max(1, len(os.sched_getaffinity(0))))
+
+
+def test_baseline_config_c_full_window_matches_oracle(lib_built):
+    """BASELINE configs[1]/[2] at steady state: sw_size 30, 200 tracks, MSCKF-only, 4 DISTINCT sequences, 84 frames - the
+    30-pose window fills after ~60 frames, so QR compression and pruneImuStateBuffer (larvio.cpp:2310-2641) run on a
+    full window (d = 202) for the last ~10 published frames.  Ids bit-exact, filter within 1e-8 of the oracle."""
+    from larvio_b200.config import Config
+    c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), max_features_in_one_grid=0, sw_size=30)
+    sq = _pool_sequences(c.raw, range(10, 14), 84)
+    rep = _drive(c, sq, 84, 'step', S=4)
+    assert rep['steps'] >= 4 * 38 and rep['ok_mismatch'] == 0 and rep['imu_mismatch'] == 0
+    assert rep['max_dim'] >= 22 + 6 * 28                                # the window reached its capacity (pruned back to 28 after every second update)
+    assert rep['p'] < 1e-8 and rep['v'] < 1e-8 and rep['q'] < 1e-8 and rep['Prel'] < 1e-8
+    rep_fe = _drive(c, sq[:2], 30, 'fe', S=2)
+    assert rep_fe['id_mismatch'] == 0 and rep_fe['uv'] == 0.0
+
+
+def test_baseline_config_e_with_slam_features_in_the_state(lib_built):
+    """BASELINE configs[4] per sequence, long enough that it is what the config string says: 400 tracks, 50-pose window,
+    4x5 grid -> SLAM features are promoted 5 s after the start (larvio.cpp:1974) and the window passes 40 poses."""
+    from larvio_b200.config import Config
+    ec = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), max_features_num=400, sw_size=50, aug_grid_rows=4, aug_grid_cols=5,
+                     min_distance=14)
+    es = _pool_sequences(ec.raw, range(2), 132)
+    rep = _drive(ec, es, 132, 'step')
+    assert rep['steps'] >= 2 * 60 and rep['ok_mismatch'] == 0 and rep['imu_mismatch'] == 0
+    assert rep['max_slam'] >= 10 and rep['max_dim'] >= 22 + 6 * 40 + 10
+    assert rep['p'] < 1e-8 and rep['v'] < 1e-8 and rep['q'] < 1e-8 and rep['Prel'] < 1e-8
+
+
+def test_full_batch_of_distinct_sequences_matches_oracle_on_a_sample(cfg):
+    """BASELINE's batch size with 64 DISTINCT sequences: 24 frames through lvb_step, a sample of sequences spread over the
+    batch (first, last, sub-batch seams) is compared with its own oracle run; every sequence must publish like its oracle twin."""
+    from larvio_b200 import api, harness
+    from oracle.frontend import ImageProcessorOracle
+    from oracle.backend import LarVioOracle
+    from larvio_b200 import synth
+    S, NF = 64, 24
+    sq = _pool_sequences(cfg.raw, range(100, 100 + S), NF)
+    sample = [0, 15, 16, 31, 47, 63]
+    b = api.Batch(cfg, n_seq=S)
+    feed = harness.ImuFeeder(sq)
+    fes = {s: ImageProcessorOracle(cfg.raw) for s in sample}; bes = {s: LarVioOracle(cfg.raw) for s in sample}
+    imu_o = {s: [] for s in sample}; k = {s: 0 for s in sample}
+    for s in range(S):
+        b.set_initial_state(s, sq[s].img_t[0], sq[s].gt_q[0], sq[s].gt_p[0], sq[s].gt_v[0], np.zeros(3), np.zeros(3))
+    for s in sample:
+        bes[s].set_initial_state(sq[s].img_t[0], sq[s].gt_q[0], sq[s].gt_p[0], sq[s].gt_v[0], np.zeros(3), np.zeros(3))
+    worst = 0.0; steps = 0
+    for j in range(NF):
+        feed.push_until(j)
+        imgs = np.stack([sq[s].images[j] for s in range(S)]); t_img = np.array([sq[s].img_t[j] for s in range(S)])
+        ok = b.step(imgs, t_img, feed.buf, feed.n)
+        for s in sample:
+            k2 = synth.imu_window(sq[s], k[s], sq[s].img_t[j]); imu_o[s].extend(sq[s].imu[k[s]:k2].tolist()); k[s] = k2
+            msg = fes[s].process_image(sq[s].images[j], sq[s].img_t[j], np.array(imu_o[s]).reshape(-1, 7))
+            oko = bes[s].process_features(msg, imu_o[s]) if msg is not None else False
+            assert bool(ok[s]) == bool(oko), (j, s)
+            if oko:
+                st = b.get_state(s); o = bes[s].imu_state
+                worst = max(worst, float(np.abs(st['p'] - o.p).max()), float(np.abs(st['v'] - o.v).max()))
+                P = b.get_covariance(s)
+                worst = max(worst, float(np.linalg.norm(P - bes[s].P) / np.linalg.norm(bes[s].P)))
+                steps += 1
+    b.close()
+    assert steps >= len(sample) * 10 and worst < 1e-8
 
 
 def test_unsupported_configs_fail_loudly(lib_built):
