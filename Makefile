@@ -13,8 +13,9 @@ LIB := larvio_b200/lib/liblarvio_b200.so
 
 IOLIB := larvio_b200/lib/liblarvio_io.so
 REPLAY := larvio_b200/bin/larvio_replay
+SHIMDEMO := larvio_b200/bin/larvio_shim_demo
 
-all: $(LIB) $(IOLIB) $(REPLAY)
+all: $(LIB) $(IOLIB) $(REPLAY) $(SHIMDEMO)
 
 # host-side on-disk formats (PNG/CSV readers, links zlib) and the C++ batched replay driver (app/larvioMain.cpp's role)
 $(IOLIB): larvio_b200/host/lvb_io.cpp include/larvio_b200.h
@@ -22,6 +23,11 @@ $(IOLIB): larvio_b200/host/lvb_io.cpp include/larvio_b200.h
 	g++ -O2 -std=c++17 -fPIC -shared -o $@ $< -lz
 
 $(REPLAY): larvio_b200/host/replay_main.cpp $(LIB) $(IOLIB) include/larvio_b200.h
+	mkdir -p larvio_b200/bin
+	g++ -O2 -std=c++17 -o $@ $< -Llarvio_b200/lib -llarvio_b200 -llarvio_io -Wl,-rpath,'$$ORIGIN/../lib'
+
+# the drop-in facade (larvio_shim.hpp: the reference's two classes) linked and run as the reference's own main loop
+$(SHIMDEMO): larvio_b200/host/shim_main.cpp larvio_b200/host/larvio_shim.hpp $(LIB) $(IOLIB) include/larvio_b200.h
 	mkdir -p larvio_b200/bin
 	g++ -O2 -std=c++17 -o $@ $< -Llarvio_b200/lib -llarvio_b200 -llarvio_io -Wl,-rpath,'$$ORIGIN/../lib'
 
@@ -39,4 +45,4 @@ $(LIB): $(OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart
 
 clean:
-	rm -f larvio_b200/csrc/*.o larvio_b200/csrc/*.o.log $(LIB) $(IOLIB) $(REPLAY)
+	rm -f larvio_b200/csrc/*.o larvio_b200/csrc/*.o.log $(LIB) $(IOLIB) $(REPLAY) $(SHIMDEMO)

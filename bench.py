@@ -534,7 +534,8 @@ def main():
         if pstats[4]:
             steady.update(mean_update_rows_r=pstats[5] / pstats[4], mean_stacked_rows=pstats[7] / pstats[4], qr_runs_per_update=pstats[8] / pstats[4])
         lk_paths = dict(point_tracks=pstats[0], iterations=pstats[10], slow_path_iterations=pstats[11], slow_path_setups=pstats[12], tile_restages=pstats[13],
-                        iterations_per_point_track=(pstats[10] / pstats[0] if pstats[0] else None))
+                        iterations_per_point_track=(pstats[10] / pstats[0] if pstats[0] else None),
+                        ransac_runs_with_8_to_13_points=pstats[14])
         models = kernel_models(S // NSUB, pstats, args.profile_steps, NSUB)
         roofs = {}
         for kname, v in top:

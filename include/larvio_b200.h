@@ -19,7 +19,8 @@
  *   lvb_set_initial_state              <-  what FlexibleInitializer::tryIncInit leaves behind
  *                                          (larvio.cpp:375-391); the initialisers themselves are
  *                                          out of scope
- *   lvb_get_state / lvb_get_window     <-  getTbw/getVel/getPpose/getPvel/getSwPoses (larvio.h:66-87)
+ *   lvb_get_state / lvb_get_window     <-  getTbw/getVel/getPpose/getPvel/getSwPoses (larvio.h:66-85)
+ *   lvb_get_points                     <-  getStableMapPointPositions / getActiveeMapPointPositions (larvio.h:86-87)
  *
  * Plain pointers and sizes only; no torch / Eigen / OpenCV types.  All "host" pointers are
  * ordinary (preferably pinned) host memory; entry points ending in `_dev` take device pointers.
@@ -145,6 +146,13 @@ int lvb_get_state(LvbHandle* h, int seq, double* t, double* q_xyzw, double* p, d
 int lvb_get_states(LvbHandle* h, double* out);
 /* getSwPoses: window poses (IMU frame) [n][7] = q(4) p(3); returns count in *n. */
 int lvb_get_window(LvbHandle* h, int seq, double* qp, int cap, int* n);
+/* getStableMapPointPositions / getActiveeMapPointPositions (larvio.h:86-87, larvio.cpp:2719-2733) for one sequence:
+ * which = 0: EKF-SLAM features that left the state since the last read (lost_slam_features, larvio.cpp:3342);
+ * which = 1: features that were in the state at the end of a step since the last read, with their latest position
+ * (active_slam_features, larvio.cpp:455-458).  ids[cap], xyz[cap][3] (world frame) are caller-owned; *n entries are
+ * written and the list is cleared, like the reference's getters clear their map.  LVB_E_CAPACITY if cap is too small
+ * (nothing cleared) or if the device-side list overflowed since the last read (8 x the SLAM capacity, at least 64). */
+int lvb_get_points(LvbHandle* h, int seq, int which, unsigned long long* ids, double* xyz, int cap, int* n);
 /* Online-calibrated quantities of one sequence (StateServer / IMUState members the reference logs, larvio.h:99-142,
  * imu_state.h:70-77): R_imu_cam0[9] row-major, t_cam0_imu[3], td, and the IMU intrinsics Tg[9], As[9], Ma[9]
  * (identity / zero / identity unless calib_imu_instrinsic, larvio.cpp:127-155, 3803-3847). */
@@ -182,7 +190,10 @@ int lvb_profile_reset(LvbHandle* h);
 int lvb_profile_get(LvbHandle* h, const char** names, double* total_ms, long long* counts, int cap);
 
 /* Cumulative work counters (device-side): [0] LK point-tracks, [1] ORB descriptors, [2] detector runs,
- * [3] published messages, [4] EKF updates, [5] sum r, [6] sum r*d*d, [7] sum stacked rows, [8] QR runs, [9] sum R*c*c. */
+ * [3] published messages, [4] EKF updates, [5] sum r, [6] sum r*d*d, [7] sum stacked rows, [8] QR runs, [9] sum R*c*c,
+ * [10] LK iterations, [11] LK iterations on the chain-replay (slow) path, [12] LK window set-ups on the slow path, [13] LK search
+ * tile re-stages, [14] findFundamentalMat calls with 8..13 points (OpenCV switches to LMedS below 15 points and its winner is
+ * then decided by rounding noise: the one front-end regime where the inlier mask is not reproducible). */
 int lvb_get_stats(LvbHandle* h, unsigned long long* out16);
 
 /* debug: the 32 per-sequence integers of the filter (dimension, window size, SLAM feature count, flags ...). */

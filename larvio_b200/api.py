@@ -69,7 +69,7 @@ _lib.lvb_debug_icore.restype = C.c_int
 _lib.lvb_profile_get.argtypes = [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
 for _name in ("lvbk_pyramid", "lvbk_lk", "lvbk_orb", "lvbk_detect", "lvbk_undistort", "lvbk_ransac",
               "lvb_process_images", "lvb_process_features", "lvb_step", "lvb_set_initial_state",
-              "lvb_get_state", "lvb_get_states", "lvb_get_window", "lvb_get_covariance", "lvb_get_calibration"):
+              "lvb_get_state", "lvb_get_states", "lvb_get_window", "lvb_get_covariance", "lvb_get_calibration", "lvb_get_points"):
     if hasattr(_lib, _name):
         getattr(_lib, _name).restype = C.c_int
 
@@ -79,6 +79,7 @@ EXPORTED_SYMBOLS = [
     "lvb_synchronize", "lvb_set_initial_state", "lvb_get_state", "lvb_get_states", "lvb_get_window",
     "lvb_get_covariance", "lvb_get_calibration", "lvb_static_init_create", "lvb_static_init_destroy", "lvb_static_init_try", "lvbk_pyramid", "lvbk_lk", "lvbk_orb", "lvbk_detect", "lvbk_undistort",
     "lvbk_ransac", "lvb_launch_count", "lvb_profile_enable", "lvb_profile_reset", "lvb_profile_get", "lvb_get_stats", "lvb_debug_icore",
+    "lvb_get_points",
 ]
 
 
@@ -319,6 +320,12 @@ class Batch:
         _check(_lib.lvb_get_covariance(self._h, seq, _p(P), cap_dim, C.byref(d)))
         n = d.value
         return P.reshape(-1)[:n * n].reshape(n, n).copy()
+
+    def get_points(self, seq, which, cap=512):
+        """which 0: stable (lost) map points, 1: active ones; returns {id: xyz} and clears the list (larvio.cpp:2719-2733)."""
+        ids = np.zeros(cap, np.uint64); xyz = np.zeros((cap, 3)); n = C.c_int()
+        _check(_lib.lvb_get_points(self._h, seq, int(which), _p(ids), _p(xyz), cap, C.byref(n)))
+        return {int(ids[i]): xyz[i].copy() for i in range(n.value)}
 
     def get_window(self, seq, cap=64):
         qp = np.zeros((cap, 7)); n = C.c_int()

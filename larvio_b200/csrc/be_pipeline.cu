@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
 __global__ void __launch_bounds__(512) be_add_obs_kernel(BeView v) {
   extern __shared__ unsigned long long sm_ids[];      // [T] table ids (0xfff.. = free)
   __shared__ int s_free_cnt, s_new_cnt, s_tracked, s_nbefore, s_ndis;
-  __shared__ float s_dis[512];
+  __shared__ double s_dis[512];           // double like the reference's norms (larvio.cpp:842-847, 2751-2766)
   const int s = blockIdx.x, tid = threadIdx.x;
   int* ic = icore_of(v, s);
   if (!ic[I_OK]) return;
@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(512) be_add_obs_kernel(BeView v) {
   __syncthreads();
   const int n_msg = min(v.msg_n[s], v.be.N);
   const int n_win = ic[I_NWIN];                       // slot the new state will occupy
+  if (n_win >= Wcap) { if (tid == 0) ic[I_ERR] = 2; return; }   // window full: report before anything is written past its slots
   const long long sid = ic[I_ID];
   // slot of state id-1, if it is still in the window
   int prev_slot = -1;
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(512) be_add_obs_kernel(BeView v) {
         const double* op = ft_obs + ((size_t)slot * Wcap + prev_slot) * 4;
         const double dx = f.u - op[0], dy = f.v - op[1];
         const int k = atomicAdd(&s_ndis, 1);
-        if (k < 512) s_dis[k] = (float)sqrt(dx * dx + dy * dy);
+        if (k < 512) s_dis[k] = sqrt(dx * dx + dy * dy);
       }
     }
   }
@@ -378,14 +379,14 @@ __global__ void __launch_bounds__(512) be_add_obs_kernel(BeView v) {
     const int nd = min(s_ndis, 512);
     if (v.cfg.if_ZUPT_valid && nd >= 20) {
       // selection of the 9th largest by repeated max (nd <= 512, once per frame)
-      float cur = 3.0e38f; int taken = 0; float val = 0.f;
+      double cur = 1.0e300; int taken = 0; double val = 0.0;
       while (taken < 9) {
-        float best = -1.f; int cnt = 0;
-        for (int i = 0; i < nd; ++i) { const float d = s_dis[i]; if (d < cur) { if (d > best) { best = d; cnt = 1; } else if (d == best) ++cnt; } }
-        if (best < 0.f) break;
+        double best = -1.0; int cnt = 0;
+        for (int i = 0; i < nd; ++i) { const double d = s_dis[i]; if (d < cur) { if (d > best) { best = d; cnt = 1; } else if (d == best) ++cnt; } }
+        if (best < 0.0) break;
         taken += cnt; val = best; cur = best;
       }
-      if ((double)val < v.cfg.zupt_dis) { ic[I_ZUPT] = 1; ic[I_ZUPT_EVENTS] += 1; }
+      if (val < v.cfg.zupt_dis) { ic[I_ZUPT] = 1; ic[I_ZUPT_EVENTS] += 1; }
     }
   }
 }
@@ -1224,13 +1225,14 @@ __global__ void __launch_bounds__(512) be_qr_kernel(BeView v) {
   const int s = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int* ic = icore_of(v, s);
   if (!ic[I_OK]) return;
-  const int R = ic[I_ROWS], c = ic[I_DIM];
+  const int R = ic[I_ROWS], c = ic[I_NC];        // compression over the structurally nonzero columns only (be_colscan_kernel)
   if (R <= c || R == 0) return;
   const int RMAX = v.be.RMAX, LD = v.be.LD;
   double* Hs = v.be.Hs + (size_t)s * LD * RMAX;
   double* rs = v.be.rs + (size_t)s * RMAX;
+  const int* km = v.be.kmap + (size_t)s * LD;
   for (int j = 0; j < c; ++j) {
-    double* cj = Hs + (size_t)j * RMAX;
+    double* cj = Hs + (size_t)km[j] * RMAX;
     double part = 0.0;
     for (int i = j + tid; i < R; i += 512) { const double x = cj[i]; part += x * x; }
     part = warp_sum_d(part);
@@ -1254,7 +1256,7 @@ __global__ void __launch_bounds__(512) be_qr_kernel(BeView v) {
     if (beta != 0.0) {
       // each warp owns columns j+1+warp, j+1+warp+16, ... and (column index c) the residual vector
       for (int k = j + 1 + warp; k <= c; k += 16) {
-        double* ck = (k < c) ? Hs + (size_t)k * RMAX : rs;
+        double* ck = (k < c) ? Hs + (size_t)km[k] * RMAX : rs;
         double dt_ = 0.0;
         for (int i = j + lane; i < R; i += 32) dt_ += qsm[i] * ck[i];
         dt_ = warp_sum_d(dt_) * beta;
@@ -1282,22 +1284,23 @@ __global__ void __launch_bounds__(512) be_qr_lean_kernel(BeView v) {
   const int s = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int* ic = icore_of(v, s);
   if (!ic[I_OK]) return;
-  const int R = ic[I_ROWS], c = ic[I_DIM];
+  const int R = ic[I_ROWS], c = ic[I_NC];        // compression over the structurally nonzero columns only (be_colscan_kernel)
   if (R <= c || R == 0) return;
   const int RMAX = v.be.RMAX, LD = v.be.LD;
   double* Hs = v.be.Hs + (size_t)s * LD * RMAX;
   double* rs = v.be.rs + (size_t)s * RMAX;
+  const int* km = v.be.kmap + (size_t)s * LD;
   {                                                    // column 0: the only block-wide reduction
     double part = 0.0;
-    for (int i = tid; i < R; i += 512) { const double x = Hs[i]; part += x * x; }
+    for (int i = tid; i < R; i += 512) { const double x = Hs[(size_t)km[0] * RMAX + i]; part += x * x; }
     part = warp_sum_d(part);
     if (lane == 0) red[warp] = part;
     __syncthreads();
-    if (tid == 0) { double n2 = 0.0; for (int w = 0; w < 16; ++w) n2 += red[w]; s_n2 = n2; s_x0 = Hs[0]; }
+    if (tid == 0) { double n2 = 0.0; for (int w = 0; w < 16; ++w) n2 += red[w]; s_n2 = n2; s_x0 = Hs[(size_t)km[0] * RMAX]; }
     __syncthreads();
   }
   for (int j = 0; j < c; ++j) {
-    double* cj = Hs + (size_t)j * RMAX;
+    double* cj = Hs + (size_t)km[j] * RMAX;
     const double n2 = s_n2, x0 = s_x0;                 // squared norm of rows >= j of column j, and its diagonal entry
     const double nrm = sqrt(n2);
     const double alpha = x0 >= 0 ? -nrm : nrm;
@@ -1311,7 +1314,7 @@ __global__ void __launch_bounds__(512) be_qr_lean_kernel(BeView v) {
     }
     __syncthreads();
     for (int k = j + 1 + warp; k <= c; k += 16) {
-      double* ck = (k < c) ? Hs + (size_t)k * RMAX : rs;
+      double* ck = (k < c) ? Hs + (size_t)km[k] * RMAX : rs;
       if (beta != 0.0) {
         double dt_ = 0.0;
         for (int i = j + lane; i < R; i += 32) dt_ += qsm[i] * ck[i];
@@ -1338,6 +1341,37 @@ __global__ void __launch_bounds__(512) be_qr_lean_kernel(BeView v) {
 
 namespace {
 
+// ====================================================================== nonzero columns of the stacked Jacobian
+// The stacked H_x of an update is structurally sparse: tracks are consumed at max_track_len observations, so every block touches
+// the extrinsic/td columns 15..21 and the pose blocks of a handful of recent window slots only - at a full
+// 30-pose window ~50 of 202 columns.  Zero columns contribute nothing to H P H^T, to the gain or to P - K H P, and a thin QR of
+// H restricted to its nonzero columns spans the same row space; so compression and update run over the listed columns only
+// (kmap[0 .. I_NC)), which turns the 2Rc^2 / 2rd^2 terms of the reference's dense algebra into 2R nc^2 / 2 r nc d.  The zero
+// test is exact: structural zeros are never computed, they are the memset / stack-kernel zeros.
+__global__ void __launch_bounds__(256) be_colscan_kernel(BeView v, int rows_idx) {
+  __shared__ int flag[BE_DMAX_PAD];
+  const int s = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK]) return;
+  const int R = ic[rows_idx], d = ic[I_DIM];
+  const int RMAX = v.be.RMAX, LD = v.be.LD;
+  const double* Hs = v.be.Hs + (size_t)s * LD * RMAX;
+  int* km = v.be.kmap + (size_t)s * LD;
+  for (int j = warp; j < d; j += 8) {
+    const double* cj = Hs + (size_t)j * RMAX;
+    bool nz = false;
+    for (int i = lane; i < R; i += 32) nz |= (cj[i] != 0.0);
+    nz = __any_sync(0xffffffffu, nz);
+    if (lane == 0) flag[j] = nz ? 1 : 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int nc = 0;
+    for (int j = 0; j < d; ++j) if (flag[j]) km[nc++] = j;
+    ic[I_NC] = nc;
+  }
+}
+
 // ====================================================================== batched FP64 GEMM (generic strides)
 // C[M x N] = alpha * A[M x K] * B[K x N] + beta * C (+ diag on the diagonal), dims from icore.
 struct GemmArgs {
@@ -1347,6 +1381,7 @@ struct GemmArgs {
   const int* icore; int m_idx, n_idx, k_idx;
   double alpha, beta, diag;
   const double* diag_vec; size_t sD;     // optional per-row diagonal term (ZUPT's block-diagonal R), else `diag`
+  const int* kmap; size_t sK;            // optional: the contraction runs over the listed indices kmap[0 .. K) of A's and B's k axis
 };
 
 constexpr int GT = 64, GK = 16;
@@ -1361,6 +1396,7 @@ __global__ void __launch_bounds__(256) be_gemm_kernel(GemmArgs g) {
   const double* A = g.A + (size_t)s * g.sA;
   const double* B = g.B + (size_t)s * g.sB;
   double* C = g.C + (size_t)s * g.sC;
+  const int* km = g.kmap ? g.kmap + (size_t)s * g.sK : nullptr;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   double acc[4][4];
 #pragma unroll
@@ -1372,13 +1408,13 @@ __global__ void __launch_bounds__(256) be_gemm_kernel(GemmArgs g) {
       int mm, kk;
       if (g.rsA == 1) { mm = i % GT; kk = i / GT; } else { kk = i % GK; mm = i / GK; }
       const int gm = m0 + mm, gk = k0 + kk;
-      As[kk][mm] = (gm < M && gk < K) ? A[(size_t)gm * g.rsA + (size_t)gk * g.csA] : 0.0;
+      As[kk][mm] = (gm < M && gk < K) ? A[(size_t)gm * g.rsA + (size_t)(km ? km[gk] : gk) * g.csA] : 0.0;
     }
     for (int i = tid; i < GT * GK; i += 256) {
       int nn, kk;
       if (g.csB == 1) { nn = i % GT; kk = i / GT; } else { kk = i % GK; nn = i / GK; }
       const int gn = n0 + nn, gk = k0 + kk;
-      Bs[kk][nn] = (gn < N && gk < K) ? B[(size_t)gk * g.rsB + (size_t)gn * g.csB] : 0.0;
+      Bs[kk][nn] = (gn < N && gk < K) ? B[(size_t)(km ? km[gk] : gk) * g.rsB + (size_t)gn * g.csB] : 0.0;
     }
     __syncthreads();
 #pragma unroll
@@ -1428,6 +1464,7 @@ __global__ void __launch_bounds__(256) be_gemm_dmma_kernel(GemmArgs g) {
   const double* A = g.A + (size_t)s * g.sA;
   const double* B = g.B + (size_t)s * g.sB;
   double* C = g.C + (size_t)s * g.sC;
+  const int* km = g.kmap ? g.kmap + (size_t)s * g.sK : nullptr;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 2, tig = lane & 3;                  // fragment coordinates: row/col group, index inside the group
   const int wm = (warp >> 1) * 16, wn = (warp & 1) * 32;      // this warp's 16 x 32 patch of the 64 x 64 tile
@@ -1441,13 +1478,13 @@ __global__ void __launch_bounds__(256) be_gemm_dmma_kernel(GemmArgs g) {
       int mm, kk;
       if (g.rsA == 1) { mm = i % GT; kk = i / GT; } else { kk = i % GK; mm = i / GK; }
       const int gm = m0 + mm, gk = k0 + kk;
-      As[kk][mm] = (gm < M && gk < K) ? A[(size_t)gm * g.rsA + (size_t)gk * g.csA] : 0.0;
+      As[kk][mm] = (gm < M && gk < K) ? A[(size_t)gm * g.rsA + (size_t)(km ? km[gk] : gk) * g.csA] : 0.0;
     }
     for (int i = tid; i < GT * GK; i += 256) {
       int nn, kk;
       if (g.csB == 1) { nn = i % GT; kk = i / GT; } else { kk = i % GK; nn = i / GK; }
       const int gn = n0 + nn, gk = k0 + kk;
-      Bs[kk][nn] = (gn < N && gk < K) ? B[(size_t)gk * g.rsB + (size_t)gn * g.csB] : 0.0;
+      Bs[kk][nn] = (gn < N && gk < K) ? B[(size_t)(km ? km[gk] : gk) * g.rsB + (size_t)gn * g.csB] : 0.0;
     }
     __syncthreads();
 #pragma unroll
@@ -1876,6 +1913,7 @@ __global__ void __launch_bounds__(256) be_zupt_build_kernel(BeView v) {
   if (!ic[I_ZUPT]) { if (tid == 0) { ic[I_ROWS] = 0; ic[I_R] = 0; } return; }
   const int RMAX = v.be.RMAX, LD = v.be.LD;
   const int nf0 = ic[I_NF];
+  const int d = ic[I_DIM] - nf0, N = ic[I_NWIN];        // read before thread 0 rewrites I_DIM below
   if (nf0 > 0) {                                        // :2770-2782: every SLAM feature leaves the state
     for (int i = tid; i < nf0; i += blockDim.x) {
       const size_t fi = (size_t)s * v.be.T + v.be.fs_slot[(size_t)s * 64 + i];
@@ -1883,7 +1921,6 @@ __global__ void __launch_bounds__(256) be_zupt_build_kernel(BeView v) {
     }
   }
   __syncthreads();
-  const int d = ic[I_DIM] - nf0, N = ic[I_NWIN];
   if (tid == 0) { ic[I_DIM] = d; ic[I_NF] = 0; core_of(v, s)[C_LAST_ZUPT] = core_of(v, s)[C_TIME]; }
   double* Hs = v.be.Hs + (size_t)s * LD * RMAX;
   double* rs = v.be.rs + (size_t)s * RMAX;
@@ -2160,7 +2197,23 @@ __global__ void __launch_bounds__(256) be_prune_cov_scatter_kernel(BeView v) {
   for (int c = threadIdx.x; c < nd; c += blockDim.x) P[(size_t)row * LD + c] = Sd[(size_t)row * LD + c];
 }
 
-// end of processFeatures: shrink dims after pruning, FEJ switch (:414-419)
+// one map point into list `which` of sequence s (upsert by id: a std::map assignment in the reference)
+__device__ inline void pts_put(const BeView& v, int which, int s, unsigned long long id, const double* xyz) {
+  const int cap = v.be.PCAP;
+  const size_t b = ((size_t)which * v.be.S + s);
+  unsigned long long* ids = v.be.pts_id + b * cap;
+  double* pos = v.be.pts_xyz + b * cap * 3;
+  int n = v.be.pts_n[b];
+  int k = 0;
+  while (k < n && ids[k] != id) ++k;
+  if (k == n) {
+    if (n >= cap) { v.be.pts_drop[b] += 1; return; }
+    ids[k] = id; v.be.pts_n[b] = n + 1;
+  }
+  pos[k * 3] = xyz[0]; pos[k * 3 + 1] = xyz[1]; pos[k * 3 + 2] = xyz[2];
+}
+
+// end of processFeatures: shrink dims after pruning, FEJ switch (:414-419), active map points (:455-458)
 __global__ void be_frame_end_kernel(BeView v) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= v.be.S) return;
@@ -2169,6 +2222,13 @@ __global__ void be_frame_end_kernel(BeView v) {
   if (ic[I_DO_PRUNE]) { ic[I_DIM] -= 6 * ic[I_NRM]; ic[I_NWIN] -= ic[I_NRM]; }
   const double* core = core_of(v, s);
   if (v.cfg.if_FEJ_config && !ic[I_FEJ] && core[C_TIME] - core[C_TAKEOFF] >= 0) ic[I_FEJ] = 1;
+  if (v.be.PCAP > 0) {
+    const int* fs = v.be.fs_slot + (size_t)s * 64;
+    for (int i = 0; i < ic[I_NF]; ++i) {
+      const size_t fi = (size_t)s * v.be.T + fs[i];
+      pts_put(v, 1, s, v.be.ft_id[fi], v.be.ft_pos + fi * 3);
+    }
+  }
 }
 
 }  // namespace
@@ -2243,6 +2303,7 @@ __global__ void __launch_bounds__(64) be_slam_pre_kernel(BeView v) {
       const int code = grid_code(v, o[0], o[1]);
       if (code >= 0 && code < 64) grid[code]++;
     } else {
+      pts_put(v, 0, s, v.be.ft_id[fi], v.be.ft_pos + fi * 3);   // lost_slam_features[id] = map_server[id] (:3342)
       v.be.ft_flags[fi] = 0; v.be.ft_mask[fi] = 0;              // rmLostFeaturesCov erases the feature
     }
   }
@@ -2350,6 +2411,7 @@ static const char* be_unsupported_reason(const LvbConfig& c) {
     if (c.max_features_in_one_grid * c.aug_grid_rows * c.aug_grid_cols > 64) return "more than 64 EKF-SLAM features";
   }
   if (c.sw_size + 1 > 64) return "sw_size > 63";
+  if (c.sw_size < 5) return "sw_size < 5 (findRedundantImuStates needs four older poses, larvio.cpp:2259-2307)";
   return nullptr;
 }
 
@@ -2434,9 +2496,12 @@ int be_alloc(LvbHandle* h) {
     be->RMAX = stk > 2048 ? ((stk + 255) / 256) * 256 : 2048;
   }
   be->imu_cap = 64;
+  be->PCAP = be->NFmax > 0 ? (8 * be->NFmax > 64 ? 8 * be->NFmax : 64) : 0;
   be->stats = h->fe.stats;
   const size_t S = be->S, T = be->T, LD = be->LD;
   BDA(be->core, S * BE_CORE); BDA(be->icore, S * BE_ICORE);
+  BDA(be->kmap, S * LD);
+  BDA(be->pts_id, 2 * S * be->PCAP); BDA(be->pts_xyz, 2 * S * be->PCAP * 3); BDA(be->pts_n, 2 * S); BDA(be->pts_drop, 2 * S);
   BDA(be->win_id, S * be->Wcap); BDA(be->win, S * be->Wcap * BE_WIN);
   BDA(be->P[0], S * LD * LD); BDA(be->P[1], 8);
   BDA(be->ft_id, S * T); BDA(be->ft_flags, S * T); BDA(be->ft_pos, S * T * 3); BDA(be->ft_mask, S * T);
@@ -2468,12 +2533,20 @@ int be_alloc(LvbHandle* h) {
   if (be->NFmax > 0) LVB_CUDA(cudaFuncSetAttribute(be_slam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 64 * be->LD)));
   const size_t chol_bytes = sizeof(double) * ((size_t)be->Dmax * (be->Dmax + 1) / 2 + 2 * be->Dmax);
   if (chol_bytes <= 227 * 1024) LVB_CUDA(cudaFuncSetAttribute(be_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_bytes));
-  if (const char* ex = getenv("LVB_EXPERIMENT")) {             // staged kernel variants, off unless named
-    if (strstr(ex, "chol_blocked")) h->experiments |= LVB_EXP_CHOL_BLOCKED;
-    if (strstr(ex, "qr_lean")) h->experiments |= LVB_EXP_QR_LEAN;
-    if (strstr(ex, "gemm_dmma")) h->experiments |= LVB_EXP_GEMM_DMMA;
-    if (strstr(ex, "graph")) h->experiments |= LVB_EXP_GRAPH;
-    if (strstr(ex, "trsm_wide")) h->experiments |= LVB_EXP_TRSM_WIDE;
+  if (const char* ex = getenv("LVB_EXPERIMENT")) {             // staged kernel variants: exact comma-separated tokens
+    std::string tok;
+    for (const char* q = ex;; ++q) {
+      if (*q == ',' || *q == '\0') {
+        if (tok == "chol_blocked") h->experiments |= LVB_EXP_CHOL_BLOCKED;
+        else if (tok == "qr_lean") h->experiments |= LVB_EXP_QR_LEAN;
+        else if (tok == "gemm_dmma") h->experiments |= LVB_EXP_GEMM_DMMA;
+        else if (tok == "graph") h->experiments |= LVB_EXP_GRAPH;
+        else if (tok == "trsm_wide") h->experiments |= LVB_EXP_TRSM_WIDE;
+        else if (!tok.empty()) return lvb_set_err(LVB_E_CONFIG, "LVB_EXPERIMENT: unknown variant '%s'", tok.c_str());
+        tok.clear();
+        if (*q == '\0') break;
+      } else if (*q != ' ') tok.push_back(*q);
+    }
   }
   const size_t cholb_bytes = chol_bytes + sizeof(double) * (size_t)(CH_NB - 1) * be->Dmax;
   if ((h->experiments & LVB_EXP_CHOL_BLOCKED) && cholb_bytes <= 227 * 1024)
@@ -2507,7 +2580,15 @@ static int launch_gemm(LvbHandle* h, const GemmArgs& g, int max_m, int max_n) {
 // compression + EKF update on the stacked system currently in Hs/rs
 static int be_debug_check(LvbHandle* h, const char* stage);
 #define DBG(name) RC(be_debug_check(h, name))
+static int be_colscan(LvbHandle* h, BeView& v, int rows_idx) {
+  LVB_PROF(h, "be_colscan_kernel");
+  be_colscan_kernel<<<h->be->S, 256, 0, h->stream>>>(v, rows_idx);
+  LVB_LAUNCH_CHECK(h);
+  return LVB_OK;
+}
+
 static int be_qr(LvbHandle* h, BeView& v) {
+  RC(be_colscan(h, v, I_ROWS));
   if (h->experiments & LVB_EXP_QR_LEAN) {
     LVB_PROF(h, "be_qr_lean_kernel");
     be_qr_lean_kernel<<<h->be->S, 512, sizeof(double) * h->be->RMAX, h->stream>>>(v);
@@ -2520,24 +2601,27 @@ static int be_qr(LvbHandle* h, BeView& v) {
   return LVB_OK;
 }
 
-static int be_update(LvbHandle* h, BeView& v, bool zupt_rows = false) {
+// rescan: the stacked system changed since the last column scan (rows appended after the compression, or built directly)
+static int be_update(LvbHandle* h, BeView& v, bool zupt_rows = false, bool rescan = false) {
   LvbBackEnd* be = h->be;
+  if (zupt_rows || rescan) RC(be_colscan(h, v, I_R));
   cudaStream_t st = h->stream;
   const size_t LD = be->LD;
   GemmArgs g;
   g.icore = be->icore; g.diag_vec = nullptr; g.sD = be->LDS;
+  g.kmap = be->kmap; g.sK = LD;                     // T and S contract over the nonzero columns of H only (be_colscan_kernel)
   // T = H P
   g.A = be->Hs; g.sA = LD * be->RMAX; g.rsA = 1; g.csA = be->RMAX;
   g.B = v.P; g.sB = LD * LD; g.rsB = (int)LD; g.csB = 1;
   g.C = be->Tm; g.sC = (size_t)be->RAWMAX * LD; g.rsC = (int)LD; g.csC = 1;
-  g.m_idx = I_R; g.n_idx = I_DIM; g.k_idx = I_DIM; g.alpha = 1.0; g.beta = 0.0; g.diag = 0.0;
+  g.m_idx = I_R; g.n_idx = I_DIM; g.k_idx = I_NC; g.alpha = 1.0; g.beta = 0.0; g.diag = 0.0;
   RC(launch_gemm(h, g, be->LDS, be->Dmax));
   DBG("gemm T=HP");
   // S = T H^T + sigma^2 I
   g.A = be->Tm; g.sA = (size_t)be->RAWMAX * LD; g.rsA = (int)LD; g.csA = 1;
   g.B = be->Hs; g.sB = LD * be->RMAX; g.rsB = be->RMAX; g.csB = 1;
   g.C = be->Sm; g.sC = (size_t)be->LDS * be->LDS; g.rsC = be->LDS; g.csC = 1;
-  g.m_idx = I_R; g.n_idx = I_R; g.k_idx = I_DIM; g.alpha = 1.0; g.beta = 0.0; g.diag = v.cfg.sfeat2;
+  g.m_idx = I_R; g.n_idx = I_R; g.k_idx = I_NC; g.alpha = 1.0; g.beta = 0.0; g.diag = v.cfg.sfeat2;
   if (zupt_rows) g.diag_vec = be->dx;
   RC(launch_gemm(h, g, be->LDS, be->LDS));
   g.diag_vec = nullptr;
@@ -2558,9 +2642,9 @@ static int be_update(LvbHandle* h, BeView& v, bool zupt_rows = false) {
   if (!smem_ok || be->NFmax > 0) {               // systems larger than the packed-smem capacity (hybrid mode, big windows)
     LVB_PROF(h, "be_chol_gmem_kernel");
     be_chol_gmem_kernel<<<be->S, 512, sizeof(double) * be->LDS, st>>>(v, smem_ok ? be->Dmax : 0);
+    LVB_LAUNCH_CHECK(h);
+    DBG("be_chol_gmem_kernel");
   }
-  LVB_LAUNCH_CHECK(h);
-  DBG("be_chol_gmem_kernel");
   BeView vt = v;
   if (h->experiments & LVB_EXP_TRSM_WIDE) {
     LVB_PROF(h, "be_trsm_wide_kernel");
@@ -2576,6 +2660,7 @@ static int be_update(LvbHandle* h, BeView& v, bool zupt_rows = false) {
   LVB_LAUNCH_CHECK(h);
   DBG("be_correct_kernel");
   // P -= Y^T Y
+  g.kmap = nullptr;
   g.A = be->Tm; g.sA = (size_t)be->RAWMAX * LD; g.rsA = 1; g.csA = (int)LD;
   g.B = be->Tm; g.sB = (size_t)be->RAWMAX * LD; g.rsB = (int)LD; g.csB = 1;
   g.C = v.P; g.sC = LD * LD; g.rsC = (int)LD; g.csC = 1;
@@ -2703,7 +2788,7 @@ static int be_measurement_pass(LvbHandle* h, BeView& v, int mode) {
     LVB_LAUNCH_CHECK(h);
     DBG("be_stack_kernel");
   }
-  RC(be_update(h, v));
+  RC(be_update(h, v, false, hybrid && mode == 0));
   if (hybrid && mode == 0) {
     LVB_PROF(h, "be_slam_grow_kernel");
     be_slam_grow_kernel<<<be->S, 256, sizeof(double) * 64 * be->LD, st>>>(v);
@@ -2713,28 +2798,47 @@ static int be_measurement_pass(LvbHandle* h, BeView& v, int mode) {
   return LVB_OK;
 }
 
-// msg arrays are device pointers. imu/n_imu: caller's host buffers (mutated).
-int be_process(LvbHandle* h, const LvbFeature* d_msg, const int* d_msg_n, const double* d_msg_t, const uint8_t* d_valid,
-               int msg_stride, LvbImu* imu, int* n_imu, int imu_stride, uint8_t* ok_out, const double* h_msg_t = nullptr,
-               const uint8_t* h_msg_valid = nullptr) {
+// processFeatures for the whole batch in three pieces, shared by the plain path (be_process) and the one-graph-per-step
+// path (lvb_step_graph): host preparation (pinned staging of the IMU buffers), a capturable enqueue (fixed launch sequence:
+// grids follow capacities, every per-sequence decision is a device-side flag) and the read-back.
+//
+// The WHOLE caller buffer of every sequence is staged, as batchImuProcessing sees the whole buffer (larvio.cpp:464-512): the
+// staging capacity grows with the largest pending count (rounded up to 64) instead of truncating.
+static int be_grow_imu(LvbHandle* h, int need) {
   LvbBackEnd* be = h->be;
-  if (const char* why = be_unsupported_reason(h->cfg)) return lvb_set_err(LVB_E_UNSUPPORTED, "%s", why);
+  const int cap = ((need + 63) / 64) * 64;
+  LVB_CUDA(cudaStreamSynchronize(h->stream));
+  LvbImu* d = nullptr; void* pin = nullptr;
+  LVB_CUDA(cudaMalloc((void**)&d, sizeof(LvbImu) * (size_t)be->S * cap));
+  LVB_CUDA(cudaHostAlloc(&pin, sizeof(LvbImu) * (size_t)be->S * cap, cudaHostAllocDefault));
+  h->allocs.push_back(d);                       // the old device buffer stays on the handle's free list until lvb_destroy
+  if (be->pin_imu) cudaFreeHost(be->pin_imu);
+  be->imu = d; be->pin_imu = (LvbImu*)pin; be->imu_cap = cap;
+  for (int k = 0; k < 2; ++k) if (h->gexec[k]) { cudaGraphExecDestroy(h->gexec[k]); h->gexec[k] = nullptr; }   // captured pointers are stale
+  return LVB_OK;
+}
+
+static int be_host_prep(LvbHandle* h, const LvbImu* imu, const int* n_imu, int imu_stride) {
+  LvbBackEnd* be = h->be;
+  const int S = be->S;
+  int need = 0;
+  for (int s = 0; s < S; ++s) {
+    if (n_imu[s] < 0 || n_imu[s] > imu_stride) return lvb_set_err(LVB_E_ARG, "sequence %d: n_imu %d outside [0, imu_stride %d]", s, n_imu[s], imu_stride);
+    if (n_imu[s] > need) need = n_imu[s];
+  }
+  if (need > be->imu_cap) RC(be_grow_imu(h, need));
+  for (int s = 0; s < S; ++s) {
+    be->pin_n_imu[s] = n_imu[s];
+    memcpy(be->pin_imu + (size_t)s * be->imu_cap, imu + (size_t)s * imu_stride, sizeof(LvbImu) * n_imu[s]);
+  }
+  return LVB_OK;
+}
+
+// msg arrays are device pointers
+static int be_enqueue(LvbHandle* h, const LvbFeature* d_msg, const int* d_msg_n, const double* d_msg_t, const uint8_t* d_valid, int msg_stride) {
+  LvbBackEnd* be = h->be;
   cudaStream_t st = h->stream;
   const int S = be->S;
-  for (int s = 0; s < S; ++s) {
-    int n = n_imu[s];
-    if (n > be->imu_cap) {
-      // Only imu_cap samples are staged per call.  That is harmless while the first sample left behind is newer than
-      // anything batchImuProcessing could consume for this message (time bound = message time + td, larvio.cpp:464-512;
-      // td is estimated online, hence the 50 ms margin); otherwise the propagation would silently stop short.
-      const LvbImu* b = imu + (size_t)s * imu_stride;
-      if (h_msg_t && h_msg_valid && h_msg_valid[s] && b[be->imu_cap].t <= h_msg_t[s] + h->cfg.td + 0.05)
-        return lvb_set_err(LVB_E_CAPACITY, "sequence %d: %d pending IMU samples exceed the per-call staging capacity %d", s, n, be->imu_cap);
-      n = be->imu_cap;
-    }
-    be->pin_n_imu[s] = n;
-    memcpy(be->pin_imu + (size_t)s * be->imu_cap, imu + (size_t)s * imu_stride, sizeof(LvbImu) * n);
-  }
   LVB_CUDA(cudaMemcpyAsync(be->imu, be->pin_imu, sizeof(LvbImu) * (size_t)S * be->imu_cap, cudaMemcpyHostToDevice, st));
   LVB_CUDA(cudaMemcpyAsync(be->n_imu, be->pin_n_imu, sizeof(int) * S, cudaMemcpyHostToDevice, st));
   BeView v = make_beview(h);
@@ -2744,101 +2848,6 @@ int be_process(LvbHandle* h, const LvbFeature* d_msg, const int* d_msg_n, const 
   else be_propagate_kernel<46><<<S, 256, sizeof(double) * (4 * 46 * 47 + 46), st>>>(v);
   LVB_LAUNCH_CHECK(h);
   const int nthr = be->N <= 256 ? 256 : 512;
-  if (be->N > 512) return lvb_set_err(LVB_E_UNSUPPORTED, "max_features_num > 512");
-  LVB_PROF(h, "be_add_obs_kernel");
-  be_add_obs_kernel<<<S, nthr, sizeof(unsigned long long) * be->T, st>>>(v);
-  LVB_LAUNCH_CHECK(h);
-  LVB_PROF(h, "be_augment_kernel");
-  be_augment_kernel<<<S, 256, 0, st>>>(v);
-  LVB_LAUNCH_CHECK(h);
-  if (be->NFmax > 0) RC(be_remap(h, v));
-  if (h->cfg.if_ZUPT_valid) {                        // checkZUPT -> measurementUpdate_ZUPT_vpq (:405-406)
-    LVB_PROF(h, "be_zupt_build_kernel");
-    be_zupt_build_kernel<<<S, 256, 0, st>>>(v);
-    LVB_LAUNCH_CHECK(h);
-    RC(be_update(h, v, true));
-  }
-  RC(be_measurement_pass(h, v, 0));                  // removeLostFeatures
-  LVB_PROF(h, "be_apply_actions_kernel");
-  be_apply_actions_kernel<<<dim3((be->T + 127) / 128, S), 128, 0, st>>>(v);
-  LVB_LAUNCH_CHECK(h);
-  LVB_PROF(h, "be_prune_select_kernel");
-  be_prune_select_kernel<<<(S + 63) / 64, 64, 0, st>>>(v);   // pruneImuStateBuffer
-  LVB_LAUNCH_CHECK(h);
-  RC(be_measurement_pass(h, v, 1));
-  LVB_PROF(h, "be_prune_tables_kernel");
-  be_prune_tables_kernel<<<S, 256, 0, st>>>(v);
-  LVB_LAUNCH_CHECK(h);
-  LVB_PROF(h, "be_prune_cov_gather_kernel");
-  be_prune_cov_gather_kernel<<<dim3(be->Dmax, S), 256, 0, st>>>(v);
-  LVB_LAUNCH_CHECK(h);
-  LVB_PROF(h, "be_prune_cov_scatter_kernel");
-  be_prune_cov_scatter_kernel<<<dim3(be->Dmax, S), 256, 0, st>>>(v);
-  LVB_LAUNCH_CHECK(h);
-  LVB_PROF(h, "be_frame_end_kernel");
-  be_frame_end_kernel<<<(S + 63) / 64, 64, 0, st>>>(v);
-  LVB_LAUNCH_CHECK(h);
-  LVB_CUDA(cudaMemcpyAsync(be->pin_icore, be->icore, sizeof(int) * (size_t)S * BE_ICORE, cudaMemcpyDeviceToHost, st));
-  LVB_CUDA(cudaStreamSynchronize(st));
-  int err = 0;
-  for (int s = 0; s < S; ++s) {
-    const int* ic = be->pin_icore + (size_t)s * BE_ICORE;
-    if (ok_out) ok_out[s] = (uint8_t)ic[I_OK];
-    if (ic[I_OK]) {
-      const int used = ic[I_CONSUMED];
-      if (used > 0) {                                  // larvio.cpp:510-512: erase consumed samples in place
-        LvbImu* b = imu + (size_t)s * imu_stride;
-        memmove(b, b + used, sizeof(LvbImu) * (n_imu[s] - used));
-        n_imu[s] -= used;
-      }
-      if (ic[I_ERR]) err = ic[I_ERR];
-    }
-  }
-  if (err) return lvb_set_err(LVB_E_CAPACITY, "back-end capacity exceeded (code %d: 1 feature table, 2 window, 3 raw rows, 4 stacked rows)", err);
-  return LVB_OK;
-}
-
-// ---- staged variant (LVB_EXPERIMENT=graph): ONE graph launch per step.  The ~75 launches of a step do not
-// depend on data (grids follow capacities, every per-sequence decision is a device-side flag), so the enqueue halves of
-// fe_process / be_process are captured once per pyramid parity and replayed; host preparation (pinned staging of IMU,
-// homographies, stamps; the image copy, whose source pointer changes) and the read-back stay outside.  The three
-// functions below are the text of be_process cut at its two seams; they must stay in step with it until the split
-// replaces it.  Not used while the profiler or LVB_DEBUG_NAN is on (both synchronise between launches).
-static int be_graph_host_prep(LvbHandle* h, const LvbImu* imu, const int* n_imu, int imu_stride) {
-  LvbBackEnd* be = h->be;
-  const int S = be->S;
-  const double* h_msg_t = nullptr; const uint8_t* h_msg_valid = nullptr;
-  for (int s = 0; s < S; ++s) {
-    int n = n_imu[s];
-    if (n > be->imu_cap) {
-      // Only imu_cap samples are staged per call.  That is harmless while the first sample left behind is newer than
-      // anything batchImuProcessing could consume for this message (time bound = message time + td, larvio.cpp:464-512;
-      // td is estimated online, hence the 50 ms margin); otherwise the propagation would silently stop short.
-      const LvbImu* b = imu + (size_t)s * imu_stride;
-      if (h_msg_t && h_msg_valid && h_msg_valid[s] && b[be->imu_cap].t <= h_msg_t[s] + h->cfg.td + 0.05)
-        return lvb_set_err(LVB_E_CAPACITY, "sequence %d: %d pending IMU samples exceed the per-call staging capacity %d", s, n, be->imu_cap);
-      n = be->imu_cap;
-    }
-    be->pin_n_imu[s] = n;
-    memcpy(be->pin_imu + (size_t)s * be->imu_cap, imu + (size_t)s * imu_stride, sizeof(LvbImu) * n);
-  }
-  return LVB_OK;
-}
-
-static int be_graph_enqueue(LvbHandle* h) {
-  LvbBackEnd* be = h->be;
-  cudaStream_t st = h->stream;
-  const int S = be->S;
-  LVB_CUDA(cudaMemcpyAsync(be->imu, be->pin_imu, sizeof(LvbImu) * (size_t)S * be->imu_cap, cudaMemcpyHostToDevice, st));
-  LVB_CUDA(cudaMemcpyAsync(be->n_imu, be->pin_n_imu, sizeof(int) * S, cudaMemcpyHostToDevice, st));
-  BeView v = make_beview(h);
-  v.msg = h->fe.msg; v.msg_n = h->fe.msg_n; v.msg_t = h->fe.msg_t; v.msg_valid = h->fe.has_msg; v.msg_stride = h->fe.N;
-  LVB_PROF(h, "be_propagate_kernel");
-  if (be->LEG == 22) be_propagate_kernel<22><<<S, 256, sizeof(double) * (4 * 22 * 23 + 22), st>>>(v);
-  else be_propagate_kernel<46><<<S, 256, sizeof(double) * (4 * 46 * 47 + 46), st>>>(v);
-  LVB_LAUNCH_CHECK(h);
-  const int nthr = be->N <= 256 ? 256 : 512;
-  if (be->N > 512) return lvb_set_err(LVB_E_UNSUPPORTED, "max_features_num > 512");
   LVB_PROF(h, "be_add_obs_kernel");
   be_add_obs_kernel<<<S, nthr, sizeof(unsigned long long) * be->T, st>>>(v);
   LVB_LAUNCH_CHECK(h);
@@ -2876,11 +2885,11 @@ static int be_graph_enqueue(LvbHandle* h) {
   return LVB_OK;
 }
 
-static int be_graph_finish(LvbHandle* h, LvbImu* imu, int* n_imu, int imu_stride, uint8_t* ok_out) {
+// imu/n_imu: the caller's host buffers (mutated like the reference's)
+static int be_finish(LvbHandle* h, LvbImu* imu, int* n_imu, int imu_stride, uint8_t* ok_out) {
   LvbBackEnd* be = h->be;
-  cudaStream_t st = h->stream;
   const int S = be->S;
-  LVB_CUDA(cudaStreamSynchronize(st));
+  LVB_CUDA(cudaStreamSynchronize(h->stream));
   int err = 0;
   for (int s = 0; s < S; ++s) {
     const int* ic = be->pin_icore + (size_t)s * BE_ICORE;
@@ -2899,20 +2908,38 @@ static int be_graph_finish(LvbHandle* h, LvbImu* imu, int* n_imu, int imu_stride
   return LVB_OK;
 }
 
-static int lvb_step_graph(LvbHandle* h, const uint8_t* images, int images_on_device, const double* t_img, LvbImu* imu,
-                          int* n_imu, int imu_stride, uint8_t* published) {
+static int be_check_config(LvbHandle* h) {
   if (const char* why = be_unsupported_reason(h->cfg)) return lvb_set_err(LVB_E_UNSUPPORTED, "%s", why);
   if (h->be->N > 512) return lvb_set_err(LVB_E_UNSUPPORTED, "max_features_num > 512");
+  return LVB_OK;
+}
+
+int be_process(LvbHandle* h, const LvbFeature* d_msg, const int* d_msg_n, const double* d_msg_t, const uint8_t* d_valid,
+               int msg_stride, LvbImu* imu, int* n_imu, int imu_stride, uint8_t* ok_out) {
+  RC(be_check_config(h));
+  RC(be_host_prep(h, imu, n_imu, imu_stride));
+  RC(be_enqueue(h, d_msg, d_msg_n, d_msg_t, d_valid, msg_stride));
+  return be_finish(h, imu, n_imu, imu_stride, ok_out);
+}
+
+// ---- LVB_EXPERIMENT=graph: ONE graph launch per step.  The enqueue halves of processImage / processFeatures are captured
+// once per pyramid parity and replayed; host preparation (pinned staging of IMU, homographies, stamps; the image copy into
+// the fixed staging batch) and the read-back stay outside.  Not used while the profiler or LVB_DEBUG_NAN is on (both
+// synchronise between launches).
+static int lvb_step_graph(LvbHandle* h, const uint8_t* images, int images_on_device, const double* t_img, LvbImu* imu,
+                          int* n_imu, int imu_stride, uint8_t* published) {
+  RC(be_check_config(h));
   cudaStream_t st = h->stream;
-  RC(fe_graph_host_prep(h, images, images_on_device, t_img, imu, n_imu, imu_stride));
-  RC(be_graph_host_prep(h, imu, n_imu, imu_stride));
+  const uint8_t* d_images = nullptr;
+  RC(fe_host_prep(h, images, images_on_device, t_img, imu, n_imu, imu_stride, true, &d_images));
+  RC(be_host_prep(h, imu, n_imu, imu_stride));
   const int par = h->fe.cur & 1;
   if (!h->gexec[par]) {
     cudaGraph_t graph = nullptr;
     const long long l0 = h->launches;
     LVB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = fe_graph_enqueue(h);
-    if (rc == LVB_OK) rc = be_graph_enqueue(h);
+    int rc = fe_enqueue(h, d_images);
+    if (rc == LVB_OK) rc = be_enqueue(h, h->fe.msg, h->fe.msg_n, h->fe.msg_t, h->fe.has_msg, h->fe.N);
     const cudaError_t e = cudaStreamEndCapture(st, &graph);
     if (rc != LVB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) return lvb_set_err(LVB_E_CUDA, "cudaStreamEndCapture -> %s", cudaGetErrorString(e));
@@ -2925,7 +2952,7 @@ static int lvb_step_graph(LvbHandle* h, const uint8_t* images, int images_on_dev
   }
   LVB_CUDA(cudaGraphLaunch(h->gexec[par], st));
   h->fe.cur ^= 1;
-  return be_graph_finish(h, imu, n_imu, imu_stride, published);
+  return be_finish(h, imu, n_imu, imu_stride, published);
 }
 
 extern "C" int lvb_process_features(LvbHandle* h, const uint8_t* valid, const double* t_msg, const LvbFeature* feat,
@@ -2946,7 +2973,7 @@ extern "C" int lvb_process_features(LvbHandle* h, const uint8_t* valid, const do
   LVB_CUDA(cudaMemcpyAsync(be->msg_in_n, be->pin_feat_n, sizeof(int) * S, cudaMemcpyHostToDevice, h->stream));
   LVB_CUDA(cudaMemcpyAsync(be->msg_in_t, be->pin_feat_t, sizeof(double) * S, cudaMemcpyHostToDevice, h->stream));
   LVB_CUDA(cudaMemcpyAsync(be->msg_in_valid, be->pin_valid, S, cudaMemcpyHostToDevice, h->stream));
-  return be_process(h, be->msg_in, be->msg_in_n, be->msg_in_t, be->msg_in_valid, N, imu, n_imu, imu_stride, ok, t_msg, valid);
+  return be_process(h, be->msg_in, be->msg_in_n, be->msg_in_t, be->msg_in_valid, N, imu, n_imu, imu_stride, ok);
 }
 
 extern "C" int lvb_step(LvbHandle* h, const uint8_t* images, int images_on_device, const double* t_img, LvbImu* imu,
@@ -3060,6 +3087,30 @@ extern "C" int lvb_get_state(LvbHandle* h, int seq, double* t, double* q, double
   const int sel[6] = {0, 1, 2, 6, 7, 8};
   if (P_pose36) for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) P_pose36[i * 6 + j] = rows[(size_t)sel[i] * be->LD + sel[j]];
   if (P_vel9) for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) P_vel9[i * 3 + j] = rows[(size_t)(3 + i) * be->LD + 3 + j];
+  return LVB_OK;
+}
+
+extern "C" int lvb_get_points(LvbHandle* h, int seq, int which, unsigned long long* ids, double* xyz, int cap, int* n) {
+  if (!h || !n || seq < 0 || seq >= h->S || (which != 0 && which != 1) || cap < 0) return lvb_set_err(LVB_E_ARG, "lvb_get_points: bad argument");
+  LVB_CUDA(cudaSetDevice(h->device));
+  LvbBackEnd* be = h->be;
+  *n = 0;
+  if (be->PCAP == 0) return LVB_OK;                       // pure MSCKF: there are no EKF-SLAM features
+  const size_t b = (size_t)which * be->S + seq;
+  int cnt[2] = {0, 0};
+  LVB_CUDA(cudaStreamSynchronize(h->stream));
+  LVB_CUDA(cudaMemcpy(&cnt[0], be->pts_n + b, sizeof(int), cudaMemcpyDeviceToHost));
+  LVB_CUDA(cudaMemcpy(&cnt[1], be->pts_drop + b, sizeof(int), cudaMemcpyDeviceToHost));
+  if (cnt[0] > cap) return lvb_set_err(LVB_E_CAPACITY, "lvb_get_points: %d points pending, caller capacity %d (nothing was cleared)", cnt[0], cap);
+  if (cnt[0] > 0 && (!ids || !xyz)) return lvb_set_err(LVB_E_ARG, "lvb_get_points: null output");
+  if (cnt[0] > 0) {
+    LVB_CUDA(cudaMemcpy(ids, be->pts_id + b * be->PCAP, sizeof(unsigned long long) * cnt[0], cudaMemcpyDeviceToHost));
+    LVB_CUDA(cudaMemcpy(xyz, be->pts_xyz + b * be->PCAP * 3, sizeof(double) * 3 * cnt[0], cudaMemcpyDeviceToHost));
+  }
+  LVB_CUDA(cudaMemset(be->pts_n + b, 0, sizeof(int)));   // the reference's getters clear their map (larvio.cpp:2722, 2729)
+  LVB_CUDA(cudaMemset(be->pts_drop + b, 0, sizeof(int)));
+  *n = cnt[0];
+  if (cnt[1] > 0) return lvb_set_err(LVB_E_CAPACITY, "lvb_get_points: %d map points were dropped since the last read (list capacity %d); read more often", cnt[1], be->PCAP);
   return LVB_OK;
 }
 

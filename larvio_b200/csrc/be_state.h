@@ -3,6 +3,7 @@
 #pragma once
 #include "lvb_internal.h"
 
+#define BE_DMAX_PAD 512      // >= any state dimension: 46 + 6*64 + 64
 #define BE_LEG_MAX 46        // legacy error-state size with IMU-intrinsic calibration (larvio.cpp:158-161); 22 without (LvbBackEnd::LEG)
 
 // ---- core[s][BE_CORE] doubles
@@ -18,7 +19,8 @@ enum {
   I_ZUPT = 8, I_OK = 9 /*processFeatures return of this frame*/, I_CONSUMED = 10, I_ROWS = 11 /*stacked rows*/,
   I_R = 12 /*rows after compression*/, I_NUSED = 13, I_RAWROWS = 14, I_ERR = 15, I_RM0 = 16, I_RM1 = 17, I_NRM = 18,
   I_DO_PRUNE = 19, I_ZUPT_EVENTS = 20, I_UPDATES = 21, I_NF = 22 /*EKF-SLAM features in state*/, I_REMAP = 23, I_NEWDIM = 24,
-  I_NNEW = 25 /*new SLAM features accepted this frame*/, I_NCAND = 26, I_RO = 27 /*rows of H_o before the new-feature rows*/, BE_ICORE = 32
+  I_NNEW = 25 /*new SLAM features accepted this frame*/, I_NCAND = 26, I_RO = 27 /*rows of H_o before the new-feature rows*/,
+  I_NC = 28 /*structurally nonzero columns of the stacked Jacobian (kmap)*/, BE_ICORE = 32
 };
 // ---- win[s][slot][BE_WIN] doubles (IMUState_Aug)
 enum { W_TIME = 0, W_DT = 1, W_Q = 2, W_P = 6, W_PFEJ = 9, W_RIC = 12, W_TCI = 21, W_QCAM = 24, W_PCAM = 28, BE_WIN = 32 };
@@ -45,12 +47,17 @@ struct LvbBackEnd {
   // first-estimate position; speculative triangulation results of this frame; state order list
   double* ft_inv; double* ft_oa; int* ft_anchor; double* ft_pfej; double* ft_spec; int* fs_slot; int* cmap; int* cand;
   double* ft_gamma;                           // [S][T] last gating statistic of each slot (diagnostics)
+  // map points for getStableMapPointPositions / getActiveeMapPointPositions (larvio.h:86-87): [which][S][PCAP], which 0 = SLAM
+  // features that left the state (lost_slam_features, larvio.cpp:3342), 1 = features in the state at the end of a step
+  // (active_slam_features, :455-458); both accumulate until lvb_get_points reads and clears them, like the reference's getters
+  unsigned long long* pts_id; double* pts_xyz; int* pts_n; int* pts_drop; int PCAP;
   double* Hnew;                               // [S][NFmax][LD + 4]: (H_1 row, h2, r_1) of the features added this frame
   double* Hraw; double* rraw;                 // [S][RAWMAX][LD], [S][RAWMAX]
   double* Hs; double* rs;                     // stacked, COLUMN-major [S][LD cols][RMAX rows], [S][RMAX]
   double* Tm;                                 // H*P   [S][RMAX? -> Dmax rows][LD]   (rows <= Dmax after compression)
   double* Sm;                                 // [S][LD][LD]
   double* zvec; double* dx;                   // [S][LD]
+  int* kmap;                                  // [S][LD] ascending list of the nonzero columns of the current stacked Jacobian (I_NC entries)
   LvbImu* imu; int* n_imu;                    // per-call IMU staging [S][imu_cap]
   LvbFeature* msg_in; int* msg_in_n; double* msg_in_t; uint8_t* msg_in_valid;   // host-provided messages
   double chi2[100];

@@ -8,21 +8,21 @@
 // Scharr derivatives are computed on the fly from the padded level image (zero outside the image,
 // REFLECT_101 at its edge == the pad content), so no derivative pyramid exists in HBM.
 //
-// Data movement (sm_100a): per pyramid level a warp stages two 32x32-byte tiles with TMA
-// (cp.async.bulk.tensor.3d + a per-warp mbarrier): the source window of the previous image and a
-// search tile of the next image centred on the predicted position.  All <=30 iterations of the level run out of
-// that shared-memory tile (re-staged only if the window walks more than 5 px away), so the dependent
-// iteration chain never waits on global memory.  Each lane keeps its 16 window pixels (patch value,
-// both derivatives) in registers for the whole level.
+// Data movement (sm_100a): per pyramid level a warp stages two tiles with TMA (cp.async.bulk.tensor.3d + a per-warp
+// mbarrier, SASS UTMALDG): the 48x24-byte source window of the previous image and a 48x32-byte search tile of the next
+// image around the predicted position.  TMA wants the innermost coordinate 16-byte aligned, so a tile starts at the
+// 16-aligned column left of what is needed and the window sits at a 0..15 byte offset inside it.  All <=30 iterations
+// of the level run out of the shared-memory tile (re-staged only if the window walks more than 5 px away), so the
+// dependent iteration chain never waits on global memory.  Each lane keeps its 16 window pixels (patch value, both
+// derivatives) in registers for the whole level; bilinear blends are IDP.2A / IDP.4A dot products on packed bytes.
 //
-// Bit-exactness with OpenCV's SSE accumulation order (oracle/lk_exact.py): the sums of the normal
-// equations are sums of integer-valued floats, accumulated by OpenCV in 4 SSE lanes + a scalar tail,
-// i.e. five sequential float chains per sum.  A float chain whose partial sums all stay below 2^24 is exact,
-// hence equal to the integer sum in ANY order; we prove that per chain with a Cauchy-Schwarz bound
-// (sum|d g| <= sqrt(sum d^2 * sum g^2) < 2^24) from integer warp reductions and then take the
-// integer sums (fast path).  When the bound fails the terms are written out and the five chains are replayed
-// in OpenCV's order, one lane per chain (slow path) - the result is bit-identical either way.
+// Bit-exactness with OpenCV's SSE accumulation order (oracle/lk_exact.py): OpenCV accumulates every sum of the normal
+// equations in 4 SSE lanes + a scalar tail, i.e. five sequential float chains per sum, and on CLAHE-contrast images the
+// partial sums exceed 2^24, so the order is part of the result.  All lanes produce the terms into per-chain arrays
+// (zero-padded to a common length: x + 0 is exact), then one lane per chain adds its terms strictly in order - 15
+// chains for (A11, A12, A22) once per level, 10 for (b1, b2) per iteration, all in one uniform 27 x float4 loop.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 #include "lvb_internal.h"
 
@@ -32,66 +32,46 @@ constexpr int WIN = 21;
 constexpr int DT = WIN + 1;                // 22: derivative grid
 constexpr int WARPS = 4;
 constexpr int W_BITS = 14;
-constexpr int TB = 32;                     // staged tiles are TB x TB bytes (TMA box), row pitch TB
+constexpr int TP = 48;                     // tile row pitch = TMA box width in bytes (a multiple of 16)
+constexpr int TA_ROWS = 24, TB_ROWS = 32;  // source tile rows (window + bilinear + Scharr apron), search tile rows
 constexpr int MARGIN = 5;                  // the search window may drift +-MARGIN px inside the staged tile
+constexpr int CH = 108;                    // floats per chain: 105 tail terms / 84 (A) or 42 (b) lane terms, zero-padded
 
-// OpenCV's SSE path accumulates the normal equations in 4 float lanes + a scalar tail (pixels 16..20 of each
-// window row); per sum, accumulator p < 4 receives, row by row, the terms of pixels p, 4+p, 8+p, 12+p (A) resp.
-// the int-pair terms of both 8-pixel chunks (b); accumulator 4 receives pixels 16..20.
-constexpr int NTERM_A = WIN * 16 + WIN * 5 + 3;   // per sum: 336 lane terms + 105 tail terms (+3 pad -> 16-B aligned sums)
-constexpr int NTERM_B = WIN * 8 + WIN * 5 + 3;    // per sum: 168 pair terms + 105 tail terms (+3 pad)
 struct alignas(128) WarpSmem {
-  uint8_t tileB[TB * TB + 128];            // search tile of the next image (+ slack: masked lanes read a few bytes past the end)
-  union {
-    struct { uint8_t tileA[TB * TB]; int2 dgrid[DT * DT + 4]; } st;   // window set-up: source tile, Scharr (dx, dy) on the 22x22 grid
-    float termA[3 * NTERM_A];              // slow path of the A sums
-    float termB[2 * NTERM_B];              // slow path of the b sums
-  } u;
+  uint8_t tileB[TP * TB_ROWS + 128];       // search tile of the next image (+ slack: masked lanes read a few bytes past the end)
+  uint8_t tileA[TP * TA_ROWS];             // source tile of the previous image
+  float term[15 * CH];                     // chain c = sum * 5 + accumulator (accumulator 4 = scalar tail); b sums use chains 0..9
   unsigned long long bar[2];               // [0] source tile, [1] search tile
 };
 
-// Term layout per sum: accumulator p (0..3) owns WIN*K consecutive floats (row-major over (row, k)), followed by the
-// WIN*5 tail terms; K = 4 for the A sums, 2 for the b sums.  Each chain adds its terms strictly in order.
-template <int K>
-__device__ __forceinline__ float run_chain(const float* T, int acc) {
+// One chain: strictly sequential float adds of its CH terms (pads are +0.0f: exact no-ops).
+__device__ __forceinline__ float run_chain(const float* T) {
+  const float4* q = reinterpret_cast<const float4*>(T);
   float a = 0.f;
-  if (acc < 4) {
-    const float2* q = reinterpret_cast<const float2*>(T + acc * (WIN * K));
 #pragma unroll
-    for (int i = 0; i < WIN * K / 2; ++i) {
-      const float2 v = q[i];
-      a = __fadd_rn(a, v.x); a = __fadd_rn(a, v.y);
-    }
-  } else {
-    const float* qt = T + 4 * (WIN * K);          // 336 / 168 floats: 16-byte aligned
-    const float4* q = reinterpret_cast<const float4*>(qt);
-#pragma unroll
-    for (int i = 0; i < (WIN * 5) / 4; ++i) {
-      const float4 v = q[i];
-      a = __fadd_rn(a, v.x); a = __fadd_rn(a, v.y); a = __fadd_rn(a, v.z); a = __fadd_rn(a, v.w);
-    }
-    a = __fadd_rn(a, qt[WIN * 5 - 1]);
+  for (int i = 0; i < CH / 4; ++i) {
+    const float4 v = q[i];
+    a = __fadd_rn(a, v.x); a = __fadd_rn(a, v.y); a = __fadd_rn(a, v.z); a = __fadd_rn(a, v.w);
   }
   return a;
 }
 // total = tail + ((l0 + l2) + (l1 + l3)); chains of this sum live on lanes base..base+4
-__device__ __forceinline__ float combine5(float l0, float l1, float l2, float l3, float tl) {
-  return __fadd_rn(tl, __fadd_rn(__fadd_rn(l0, l2), __fadd_rn(l1, l3)));
-}
 __device__ __forceinline__ float combine_chains(float mine, int base) {
   const float l0 = __shfl_sync(0xffffffffu, mine, base), l1 = __shfl_sync(0xffffffffu, mine, base + 1);
   const float l2 = __shfl_sync(0xffffffffu, mine, base + 2), l3 = __shfl_sync(0xffffffffu, mine, base + 3);
   const float tl = __shfl_sync(0xffffffffu, mine, base + 4);
-  return combine5(l0, l1, l2, l3, tl);
+  return __fadd_rn(tl, __fadd_rn(__fadd_rn(l0, l2), __fadd_rn(l1, l3)));
 }
 
 // ---- sm_100a primitives
 __device__ __forceinline__ int dp2a_lo(int w, unsigned b, int c) { int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(b), "r"(c)); return d; }
 __device__ __forceinline__ int dp2a_hi(int w, unsigned b, int c) { int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) { int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory"); }
-__device__ __forceinline__ void tma_load_tile(unsigned dst, const CUtensorMap* map, int x, int y, int z, unsigned bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(TB * TB) : "memory");
+// x must be a multiple of 16 (bytes): TMA faults on a misaligned innermost coordinate
+__device__ __forceinline__ void tma_load_tile(unsigned dst, const CUtensorMap* map, int x, int y, int z, unsigned bar, int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                :: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
 }
@@ -101,6 +81,17 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ int floor16(int v) { return v & ~15; }        // two's complement: also floors negative values
+
+// 12 bytes [b, b+12) of a tile row as three words, b arbitrary: three aligned 8-byte reads, word select, funnel shifts
+__device__ __forceinline__ void row_bytes12(const uint8_t* rowp, int b, unsigned& a0, unsigned& a1, unsigned& a2) {
+  const uint8_t* q = rowp + (b & ~7);
+  const uint2 r0 = *reinterpret_cast<const uint2*>(q), r1 = *reinterpret_cast<const uint2*>(q + 8), r2 = *reinterpret_cast<const uint2*>(q + 16);
+  const bool hi = (b & 4) != 0;
+  const unsigned w0 = hi ? r0.y : r0.x, w1 = hi ? r1.x : r0.y, w2 = hi ? r1.y : r1.x, w3 = hi ? r2.x : r1.y;
+  const int k = (b & 3) * 8;
+  a0 = __funnelshift_r(w0, w1, k); a1 = __funnelshift_r(w1, w2, k); a2 = __funnelshift_r(w2, w3, k);
+}
 
 // Eight horizontally adjacent pixels of one tile row pair: bytes [b, b+9) of row `rowp` (top) and of the row below,
 // bilinear weights wt = iw00 | iw01 << 16, wb = iw10 | iw11 << 16, per-pixel accumulator start c[j].
@@ -108,7 +99,7 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 __device__ __forceinline__ void bilinear8(const uint8_t* rowp, int b, int wt, int wb, const int* c, int* out) {
   const uint8_t* q = rowp + (b & ~7);
   const uint2 t0 = *reinterpret_cast<const uint2*>(q), t1 = *reinterpret_cast<const uint2*>(q + 8);
-  const uint2 u0 = *reinterpret_cast<const uint2*>(q + TB), u1 = *reinterpret_cast<const uint2*>(q + TB + 8);
+  const uint2 u0 = *reinterpret_cast<const uint2*>(q + TP), u1 = *reinterpret_cast<const uint2*>(q + TP + 8);
   const bool hi = (b & 4) != 0;
   const unsigned tw0 = hi ? t0.y : t0.x, tw1 = hi ? t1.x : t0.y, tw2 = hi ? t1.y : t1.x;
   const unsigned bw0 = hi ? u0.y : u0.x, bw1 = hi ? u1.x : u0.y, bw2 = hi ? u1.y : u1.x;
@@ -127,6 +118,72 @@ __device__ __forceinline__ void bilinear8(const uint8_t* rowp, int b, int wt, in
   out[7] = dp2a_hi(wt, ts1, dp2a_hi(wb, bs1, c[7]));
 }
 
+// One 8-pixel item (window row y, columns x0..x0+7, nv of them valid) of the previous-image window from the staged source
+// tile; tile byte (r, oxa + c) = level pixel (ipy - 1 + r, ipx - 1 + c).  Scharr at grid point (g, c) [level pixel
+// (ipy + g, ipx + c)] needs tile rows g..g+2 and tile columns c..c+2:
+//   dx = 3 (Hd[g] + Hd[g+2]) + 10 Hd[g+1],  Hd[r][c] = tile[r][c+2] - tile[r][c]              (IDP.4A with weights -1 0 1)
+//   dy = Hs[g+2] - Hs[g],                   Hs[r][c] = 3 tile[r][c] + 10 tile[r][c+1] + 3 tile[r][c+2]   (weights 3 10 3)
+// then OpenCV's Q14 bilinear blend with rounding of the four neighbouring grid values, and the Q14 blend >> 9 of the pixels.
+__device__ __forceinline__ void window_item(const uint8_t* tileA, int oxa, int y, int x0, int nv, int iw00, int iw01, int iw10, int iw11,
+                                            bool grid_inside, int ipx, int ipy, int lw, int lh, int* cI, int* gX, int* gY) {
+  int dxg[2][9], dyg[2][9];
+  int hs1[9], hs2[9], hd1[9], hd2[9];       // the two previous tile rows
+  unsigned p1[9], p2[9];                    // byte-shifted words of tile rows y+1 and y+2 (patch value)
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    unsigned a0, a1, a2;
+    row_bytes12(tileA + (y + t) * TP, oxa + x0, a0, a1, a2);
+    unsigned sc[9];
+    sc[0] = a0; sc[1] = __funnelshift_r(a0, a1, 8); sc[2] = __funnelshift_r(a0, a1, 16); sc[3] = __funnelshift_r(a0, a1, 24);
+    sc[4] = a1; sc[5] = __funnelshift_r(a1, a2, 8); sc[6] = __funnelshift_r(a1, a2, 16); sc[7] = __funnelshift_r(a1, a2, 24);
+    sc[8] = a2;
+    int hs[9], hd[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) { hs[c] = dp4a_us(sc[c], 0x00030A03, 0); hd[c] = dp4a_us(sc[c], 0x000100FF, 0); }
+    if (t >= 2) {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) { dxg[t - 2][c] = 3 * (hd2[c] + hd[c]) + 10 * hd1[c]; dyg[t - 2][c] = hs[c] - hs2[c]; }
+    }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+      hs2[c] = hs1[c]; hd2[c] = hd1[c]; hs1[c] = hs[c]; hd1[c] = hd[c];
+      if (t == 1) p1[c] = sc[c];
+      if (t == 2) p2[c] = sc[c];
+    }
+  }
+  if (!grid_inside) {                       // derivative image is zero outside the level (warp-uniform branch)
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        const int gx = ipx + x0 + c, gy = ipy + y + g;
+        if (gx < 0 || gx >= lw || gy < 0 || gy >= lh) { dxg[g][c] = 0; dyg[g][c] = 0; }
+      }
+  }
+  const int wt = (iw00 & 0xffff) | (iw01 << 16), wb = (iw10 & 0xffff) | (iw11 << 16);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ix = (dxg[0][j] * iw00 + dxg[0][j + 1] * iw01 + dxg[1][j] * iw10 + dxg[1][j + 1] * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
+    const int iy = (dyg[0][j] * iw00 + dyg[0][j + 1] * iw01 + dyg[1][j] * iw10 + dyg[1][j + 1] * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
+    const int iv = dp2a_lo(wt, p1[j + 1], dp2a_lo(wb, p2[j + 1], 1 << (W_BITS - 5 - 1)));     // tile bytes (j+1, j+2) of rows y+1, y+2
+    const bool ok = j < nv;
+    cI[j] = ok ? (1 << (W_BITS - 5 - 1)) - ((iv >> (W_BITS - 5)) << (W_BITS - 5)) : 0;
+    gX[j] = ok ? ix : 0;
+    gY[j] = ok ? iy : 0;
+  }
+}
+
+// debug twin of tma_load_tile: same box, same zero fill outside the padded level
+__device__ __forceinline__ void debug_load_tile(uint8_t* dst, int rows, const uint8_t* pyr, const LvbPyramidLayout& L, int level, int s, int x, int y, int lane) {
+  const LvbLevel lv = L.lv[level];
+  const uint8_t* base = pyr + (size_t)s * L.bytes_per_seq + lv.offset;
+  for (int t = lane; t < TP * rows; t += 32) {
+    const int r = t / TP, c = t - r * TP;
+    const int gx = x + c, gy = y + r;
+    dst[t] = (gx >= 0 && gx < lv.pitch && gy >= 0 && gy < lv.rows) ? base[(size_t)gy * lv.pitch + gx] : (uint8_t)0;
+  }
+}
+
 struct LkArgs {
   int stride;                 // per-sequence stride of point arrays
   const float2* ptsA;         // [S][stride] source points (indexed through perm if given)
@@ -142,13 +199,15 @@ struct LkArgs {
 };
 
 struct LkArgs2 {
-  CUtensorMap mapA[LVB_MAX_LEVELS];   // padded level images of the previous / next pyramid: (x, y, sequence), box TB x TB x 1
-  CUtensorMap mapB[LVB_MAX_LEVELS];
+  CUtensorMap mapA[LVB_MAX_LEVELS];   // previous pyramid, box TP x TA_ROWS x 1 per level: (x, y, sequence) over the padded level images
+  CUtensorMap mapB[LVB_MAX_LEVELS];   // next pyramid, box TP x TB_ROWS x 1
   LkArgs a[2];
   int lw[LVB_MAX_LEVELS], lh[LVB_MAX_LEVELS];
   int max_iter; double eps2; double min_eig;
   int max_level;
-  unsigned long long* stats;  // [10] iterations, [11] slow-path iterations, [12] slow-path window set-ups, [13] tile re-stages
+  unsigned long long* stats;  // [10] iterations, [13] search-tile re-stages
+  // debug only (LVB_DEBUG_LK_NOTMA=1): stage the tiles with plain loads instead of TMA, to tell a staging fault from an arithmetic one
+  int no_tma; const uint8_t* pyrA; const uint8_t* pyrB; LvbPyramidLayout L;
 };
 
 __global__ void __launch_bounds__(WARPS * 32, 4) lk_kernel(const __grid_constant__ LkArgs2 aa) {
@@ -164,6 +223,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) lk_kernel(const __grid_constant
     mbar_init(bar0); mbar_init(bar1);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  for (int t = lane; t < 15 * CH / 4; t += 32) reinterpret_cast<float4*>(w.term)[t] = make_float4(0.f, 0.f, 0.f, 0.f);   // chain pads stay zero
   __syncwarp();
   unsigned ph0 = 0, ph1 = 0;
 
@@ -179,7 +239,13 @@ __global__ void __launch_bounds__(WARPS * 32, 4) lk_kernel(const __grid_constant
   const int rowA = row_l, rowB = tail ? min(row_l + 11, WIN - 1) : row_l;
   const int xA = tail ? 16 : 8 * cls, xB = tail ? 16 : 8 * (1 - cls);
   const int nvA = tail ? 5 : 8, nvB = tail ? ((row_l + 11 < WIN) ? 5 : 0) : 8;   // valid pixels per item
-  const unsigned rm = tail ? 0u : 0xffffffffu;
+  // where this lane's terms go.  A sums: pixel (y, x): x < 16 -> chain x & 3, position y * 4 + (x >> 2); else chain 4, position
+  // y * 5 + (x - 16).  b sums: pair term p of chunk ch -> chain p, position y * 2 + ch; tail pixel j -> chain 4, position y * 5 + j.
+  // Per item the k-th value lands at base + k * step (row lanes: the next chain; tail lanes: the next position).
+  const int stepB = tail ? 1 : CH;
+  const int baseB_A = tail ? 4 * CH + rowA * 5 : rowA * 2 + (xA >> 3);
+  const int baseB_B = tail ? 4 * CH + rowB * 5 : rowB * 2 + (xB >> 3);
+  const int pair_mask = tail ? 0 : -1;                                   // row lanes add pixel k + 4 to pixel k (OpenCV's madd pairs)
 
   const int slot = a.perm ? a.perm[(size_t)s * a.stride + i] : i;
   const float2 pA = a.ptsA[(size_t)s * a.stride + slot];
@@ -203,7 +269,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) lk_kernel(const __grid_constant
   bool status = true;
   const float halfWin = (WIN - 1) * 0.5f;
   const float FLT_SCALE = 1.f / (float)(1 << 20);
-  unsigned n_iter = 0, n_slow = 0, n_slowA = 0, n_restage = 0;
+  unsigned n_iter = 0, n_restage = 0;
 
   for (int level = aa.max_level; level >= 0; --level) {
     const int lw = aa.lw[level], lh = aa.lh[level];
@@ -219,134 +285,66 @@ __global__ void __launch_bounds__(WARPS * 32, 4) lk_kernel(const __grid_constant
       continue;
     }
     float2 np = make_float2(__fsub_rn(nxt.x, halfWin), __fsub_rn(nxt.y, halfWin));
-    // ---- stage the source tile (origin ipx-1, ipy-1: window + bilinear +1 + Scharr apron) and the search tile
-    int tx, ty;
+    // ---- stage the source tile (needs columns ipx-1 .. ipx+22, rows ipy-1 .. ipy+22) and the search tile
+    const int txa = floor16(ipx - 1 + LVB_PAD), oxa = ipx - 1 + LVB_PAD - txa;                     // padded-level coordinates
+    int txb, ty;                                                                                   // search tile origin (padded x, level y)
     {
       // float -> int with saturation (np may be far outside for a lost point); the iteration re-checks the range anyway
       const float cx = fminf(fmaxf(floorf(np.x), -4096.f), 8192.f), cy = fminf(fmaxf(floorf(np.y), -4096.f), 8192.f);
-      tx = (int)cx - MARGIN; ty = (int)cy - MARGIN;
+      txb = max(floor16((int)cx - MARGIN + LVB_PAD), 0); ty = max((int)cy - MARGIN, -LVB_PAD);   // tile origins stay inside the padded level
     }
     __syncwarp();
-    if (lane == 0) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // earlier generic writes to the union (term scratch)
-      tma_load_tile(smem_u32(w.u.st.tileA), &aa.mapA[level], ipx - 1 + LVB_PAD, ipy - 1 + LVB_PAD, s, bar0);
-      tma_load_tile(smem_u32(w.tileB), &aa.mapB[level], tx + LVB_PAD, ty + LVB_PAD, s, bar1);
-    }
-    mbar_wait(bar0, ph0); ph0 ^= 1;
-    // ---- Scharr derivatives on the 22x22 grid (zero outside the image)
-    {
-      int dy = 0, dx = lane;                                             // grid point t = lane + 32 k  ->  (dy, dx)
-      if (dx >= DT) { dx -= DT; dy = 1; }
-      for (int t = lane; t < DT * DT; t += 32) {
-        const int gx = ipx + dx, gy = ipy + dy;
-        int2 d = make_int2(0, 0);
-        if (gx >= 0 && gx < lw && gy >= 0 && gy < lh) {
-          const uint8_t* c = &w.u.st.tileA[(dy + 1) * TB + (dx + 1)];
-          const int tl = c[-TB - 1], tc = c[-TB], tr = c[-TB + 1];
-          const int ml = c[-1], mr = c[1];
-          const int bl = c[TB - 1], bc = c[TB], br = c[TB + 1];
-          d.x = 3 * (tr + br - tl - bl) + 10 * (mr - ml);
-          d.y = 3 * (bl + br - tl - tr) + 10 * (bc - tc);
-        }
-        w.u.st.dgrid[t] = d;
-        dx += 32 - DT; dy += 1;                                          // 32 = 22 + 10
-        if (dx >= DT) { dx -= DT; dy += 1; }
+    if (aa.no_tma) {
+      debug_load_tile(w.tileA, TA_ROWS, aa.pyrA, aa.L, level, s, txa, ipy - 1 + LVB_PAD, lane);
+      debug_load_tile(w.tileB, TB_ROWS, aa.pyrB, aa.L, level, s, txb, ty + LVB_PAD, lane);
+      __syncwarp();
+    } else {
+      if (lane == 0) {
+        tma_load_tile(smem_u32(w.tileA), &aa.mapA[level], txa, ipy - 1 + LVB_PAD, s, bar0, TP * TA_ROWS);
+        tma_load_tile(smem_u32(w.tileB), &aa.mapB[level], txb, ty + LVB_PAD, s, bar1, TP * TB_ROWS);
       }
+      mbar_wait(bar0, ph0); ph0 ^= 1;
     }
-    __syncwarp();
-    // ---- this lane's 16 pixels of the previous-image window: patch value folded into the accumulator start
-    //      cI = 256 - (Iw << 9)  (so that I_t = (cI + sum w*J) >> 9 in the iterations), derivatives gX, gY
+    // ---- this lane's 16 pixels of the previous-image window, straight from the staged source tile: Scharr derivatives
+    //      (zero outside the image) at the 2 x 9 grid points each 8-pixel item touches, their bilinear blend gX, gY, and
+    //      the patch value folded into the accumulator start cI = 256 - (Iw << 9)  (I_t = (cI + sum w*J) >> 9 later)
     float fa = __fsub_rn(prevPt.x, (float)ipx), fb = __fsub_rn(prevPt.y, (float)ipy);
     int iw00 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, fa), __fsub_rn(1.f, fb)), (float)(1 << W_BITS)));
     int iw01 = __float2int_rn(__fmul_rn(__fmul_rn(fa, __fsub_rn(1.f, fb)), (float)(1 << W_BITS)));
     int iw10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, fa), fb), (float)(1 << W_BITS)));
     int iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+    const bool grid_inside = ipx >= 0 && ipx + DT <= lw && ipy >= 0 && ipy + DT <= lh;       // warp-uniform: no zero padding needed
     int cI[16], gX[16], gY[16];
+    window_item(w.tileA, oxa, rowA, xA, nvA, iw00, iw01, iw10, iw11, grid_inside, ipx, ipy, lw, lh, &cI[0], &gX[0], &gY[0]);
+    window_item(w.tileA, oxa, rowB, xB, nvB, iw00, iw01, iw10, iw11, grid_inside, ipx, ipy, lw, lh, &cI[8], &gX[8], &gY[8]);
+    // ---- A sums: terms fx*fx, fx*fy, fy*fy into chains 0..4 / 5..9 / 10..14, then 15 lanes replay OpenCV's order
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const int y = it ? rowB : rowA, x0 = it ? xB : xA, nv = it ? nvB : nvA;
-      int c256[8], iv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) c256[j] = 1 << (W_BITS - 5 - 1);
-      bilinear8(&w.u.st.tileA[(y + 1) * TB], x0 + 1, (iw00 & 0xffff) | (iw01 << 16), (iw10 & 0xffff) | (iw11 << 16), c256, iv);
-      const int2* g0 = &w.u.st.dgrid[y * DT + x0];
-      const int2* g1 = g0 + DT;
-      int2 p0 = g0[0], p1 = g1[0];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int2 q0 = g0[j + 1], q1 = g1[j + 1];
-        const int ix = (p0.x * iw00 + q0.x * iw01 + p1.x * iw10 + q1.x * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
-        const int iy = (p0.y * iw00 + q0.y * iw01 + p1.y * iw10 + q1.y * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
-        const bool ok = j < nv;
-        cI[it * 8 + j] = ok ? (1 << (W_BITS - 5 - 1)) - ((iv[j] >> (W_BITS - 5)) << (W_BITS - 5)) : 0;
-        gX[it * 8 + j] = ok ? ix : 0;
-        gY[it * 8 + j] = ok ? iy : 0;
-        p0 = q0; p1 = q1;
+    for (int j = 0; j < 16; ++j) {
+      const int it = j >> 3, jj = j & 7;
+      const int y = it ? rowB : rowA, x = (it ? xB : xA) + jj, nv = it ? nvB : nvA;
+      if (jj < nv) {
+        const float fx = (float)gX[j], fy = (float)gY[j];
+        const int sl = (x < 16) ? ((x & 3) * CH + y * 4 + (x >> 2)) : (4 * CH + y * 5 + (x - 16));
+        w.term[sl] = __fmul_rn(fx, fx);
+        w.term[5 * CH + sl] = __fmul_rn(fx, fy);
+        w.term[10 * CH + sl] = __fmul_rn(fy, fy);
       }
     }
-    // ---- A sums.  Per chain c (4 SSE accumulators + tail): G11 = sum gx^2, G22 = sum gy^2, G12 = sum gx gy, Gab = sum |gx gy|
-    unsigned G11[5], G22[5], Gab[5]; int G12[5];
-    {
-      unsigned g11[4] = {0, 0, 0, 0}, g22[4] = {0, 0, 0, 0}, gab[4] = {0, 0, 0, 0};
-      int g12[4] = {0, 0, 0, 0};
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int xy = gX[j] * gY[j];
-        g11[j & 3] += (unsigned)(gX[j] * gX[j]); g22[j & 3] += (unsigned)(gY[j] * gY[j]);
-        g12[j & 3] += xy; gab[j & 3] += (unsigned)abs(xy);
-      }
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        G11[p] = __reduce_add_sync(0xffffffffu, g11[p] & rm); G22[p] = __reduce_add_sync(0xffffffffu, g22[p] & rm);
-        G12[p] = __reduce_add_sync(0xffffffffu, (int)((unsigned)g12[p] & rm)); Gab[p] = __reduce_add_sync(0xffffffffu, gab[p] & rm);
-      }
-      G11[4] = __reduce_add_sync(0xffffffffu, (g11[0] + g11[1] + g11[2] + g11[3]) & ~rm);
-      G22[4] = __reduce_add_sync(0xffffffffu, (g22[0] + g22[1] + g22[2] + g22[3]) & ~rm);
-      G12[4] = __reduce_add_sync(0xffffffffu, (int)((unsigned)(g12[0] + g12[1] + g12[2] + g12[3]) & ~rm));
-      Gab[4] = __reduce_add_sync(0xffffffffu, (gab[0] + gab[1] + gab[2] + gab[3]) & ~rm);
-    }
-    unsigned gmaxA = 0;
-#pragma unroll
-    for (int c = 0; c < 5; ++c) gmaxA = max(gmaxA, max(max(G11[c], G22[c]), Gab[c]));
-    float A11, A12, A22;
-    if (gmaxA < (1u << 24)) {             // every chain exact: the float chains equal the integer sums
-      A11 = __fmul_rn(combine5((float)G11[0], (float)G11[1], (float)G11[2], (float)G11[3], (float)G11[4]), FLT_SCALE);
-      A12 = __fmul_rn(combine5((float)G12[0], (float)G12[1], (float)G12[2], (float)G12[3], (float)G12[4]), FLT_SCALE);
-      A22 = __fmul_rn(combine5((float)G22[0], (float)G22[1], (float)G22[2], (float)G22[3], (float)G22[4]), FLT_SCALE);
-    } else {                               // replay OpenCV's chains (the staging area is dead from here on)
-      ++n_slowA;
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int it = j >> 3, jj = j & 7;
-        const int y = it ? rowB : rowA, x = (it ? xB : xA) + jj, nv = it ? nvB : nvA;
-        if (jj < nv) {
-          const float fx = (float)gX[j], fy = (float)gY[j];
-          const int sl = (x < 16) ? ((x & 3) * (WIN * 4) + y * 4 + (x >> 2)) : (WIN * 16 + y * 5 + (x - 16));
-          w.u.termA[sl] = __fmul_rn(fx, fx);
-          w.u.termA[NTERM_A + sl] = __fmul_rn(fx, fy);
-          w.u.termA[2 * NTERM_A + sl] = __fmul_rn(fy, fy);
-        }
-      }
-      __syncwarp();
-      float chainv = 0.f;
-      if (lane < 15) chainv = run_chain<4>(w.u.termA + (lane / 5) * NTERM_A, lane % 5);
-      A11 = __fmul_rn(combine_chains(chainv, 0), FLT_SCALE);
-      A12 = __fmul_rn(combine_chains(chainv, 5), FLT_SCALE);
-      A22 = __fmul_rn(combine_chains(chainv, 10), FLT_SCALE);
-      __syncwarp();
-    }
-    // per-chain bound for the b sums: exact while sum d^2 < thr[c] <= 2^48 / max(G11, G22)   (Cauchy-Schwarz)
-    unsigned thr[5];
-#pragma unroll
-    for (int c = 0; c < 5; ++c)
-      thr[c] = __float2uint_rd(__fdiv_rd(281474976710656.f, __uint2float_ru(max(G11[c], G22[c]))));
+    __syncwarp();
+    float chainv = 0.f;
+    if (lane < 15) chainv = run_chain(w.term + lane * CH);
+    const float A11 = __fmul_rn(combine_chains(chainv, 0), FLT_SCALE);
+    const float A12 = __fmul_rn(combine_chains(chainv, 5), FLT_SCALE);
+    const float A22 = __fmul_rn(combine_chains(chainv, 10), FLT_SCALE);
+    __syncwarp();
+    // the b sums reuse chains 0..9; their lane chains hold 42 terms where the A chains held 84: clear the difference once
+    for (int t = lane; t < 8 * 42; t += 32) { const int c = t / 42, q = t - c * 42; w.term[(c + (c >> 2)) * CH + 42 + q] = 0.f; }
 
     float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
     const float dif = __fsub_rn(A11, A22);
     const float rad = __fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.f, A12), A12));
     const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(rad)), (float)(2 * WIN * WIN));
-    mbar_wait(bar1, ph1); ph1 ^= 1;                                      // search tile has landed (needed before any `continue`)
+    if (!aa.no_tma) { mbar_wait(bar1, ph1); ph1 ^= 1; }                  // search tile has landed (needed before any `continue`)
     if ((double)minEig < aa.min_eig || D < 1.1920929e-07f) {
       if (level == 0) status = false;
       continue;
@@ -359,13 +357,16 @@ __global__ void __launch_bounds__(WARPS * 32, 4) lk_kernel(const __grid_constant
         if (level == 0) status = false;
         break;
       }
-      int ox = inx - tx, oy = iny - ty;
-      if (ox < 0 || ox > 2 * MARGIN || oy < 0 || oy > 2 * MARGIN) {    // the window left the staged tile: re-centre it
-        tx = inx - MARGIN; ty = iny - MARGIN; ox = MARGIN; oy = MARGIN;
+      int ox = inx + LVB_PAD - txb, oy = iny - ty;
+      if (ox < 0 || ox > TP - DT || oy < 0 || oy > 2 * MARGIN) {         // the window left the staged tile: re-centre it
+        txb = max(floor16(inx - MARGIN + LVB_PAD), 0); ty = max(iny - MARGIN, -LVB_PAD); ox = inx + LVB_PAD - txb; oy = iny - ty;
         ++n_restage;
         __syncwarp();
-        if (lane == 0) tma_load_tile(smem_u32(w.tileB), &aa.mapB[level], tx + LVB_PAD, ty + LVB_PAD, s, bar1);
-        mbar_wait(bar1, ph1); ph1 ^= 1;
+        if (aa.no_tma) { debug_load_tile(w.tileB, TB_ROWS, aa.pyrB, aa.L, level, s, txb, ty + LVB_PAD, lane); __syncwarp(); }
+        else {
+          if (lane == 0) tma_load_tile(smem_u32(w.tileB), &aa.mapB[level], txb, ty + LVB_PAD, s, bar1, TP * TB_ROWS);
+          mbar_wait(bar1, ph1); ph1 ^= 1;
+        }
       }
       fa = __fsub_rn(np.x, (float)inx);
       fb = __fsub_rn(np.y, (float)iny);
@@ -376,72 +377,33 @@ __global__ void __launch_bounds__(WARPS * 32, 4) lk_kernel(const __grid_constant
       const int wt = (iw00 & 0xffff) | (iw01 << 16), wb = (iw10 & 0xffff) | (iw11 << 16);
       // I_t of this lane's 16 pixels: d = (cI + bilinear) >> 9
       int d[16];
-      bilinear8(&w.tileB[(oy + rowA) * TB], ox + xA, wt, wb, &cI[0], &d[0]);
-      bilinear8(&w.tileB[(oy + rowB) * TB], ox + xB, wt, wb, &cI[8], &d[8]);
-      int s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-      unsigned dq[4] = {0, 0, 0, 0};
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        d[q] >>= (W_BITS - 5);
-        s1[q & 3] += d[q] * gX[q]; s2[q & 3] += d[q] * gY[q];
-        dq[q & 3] += (unsigned)(d[q] * d[q]);
-      }
+      bilinear8(&w.tileB[(oy + rowA) * TP], ox + xA, wt, wb, &cI[0], &d[0]);
+      bilinear8(&w.tileB[(oy + rowB) * TP], ox + xB, wt, wb, &cI[8], &d[8]);
       ++n_iter;
-      // integer warp reductions per chain
-      const unsigned dmax = __reduce_max_sync(0xffffffffu, max(max(dq[0], dq[1]), max(dq[2], dq[3])));
-      int S1[5], S2[5]; unsigned DQ[5];
+      // terms of b1 (chains 0..4) and b2 (chains 5..9): row lanes 4 pair terms per item, tail lanes 5 single terms
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        S1[p] = __reduce_add_sync(0xffffffffu, (int)((unsigned)s1[p] & rm));
-        S2[p] = __reduce_add_sync(0xffffffffu, (int)((unsigned)s2[p] & rm));
-        DQ[p] = __reduce_add_sync(0xffffffffu, dq[p] & rm);
-      }
-      S1[4] = __reduce_add_sync(0xffffffffu, (int)((unsigned)(s1[0] + s1[1] + s1[2] + s1[3]) & ~rm));
-      S2[4] = __reduce_add_sync(0xffffffffu, (int)((unsigned)(s2[0] + s2[1] + s2[2] + s2[3]) & ~rm));
-      DQ[4] = __reduce_add_sync(0xffffffffu, (dq[0] + dq[1] + dq[2] + dq[3]) & ~rm);
-      bool exact = dmax < (1u << 26);                                    // no 32-bit wrap in the DQ reductions
+      for (int it = 0; it < 2; ++it) {
+        const int nv = it ? nvB : nvA;
+        float* t1 = w.term + (it ? baseB_B : baseB_A);
+        float* t2 = t1 + 5 * CH;
+        int p1[8], p2[8];
 #pragma unroll
-      for (int c = 0; c < 5; ++c) exact = exact && (DQ[c] < thr[c]);
-      float b1, b2;
-      if (exact) {
-        b1 = __fmul_rn(combine5((float)S1[0], (float)S1[1], (float)S1[2], (float)S1[3], (float)S1[4]), FLT_SCALE);
-        b2 = __fmul_rn(combine5((float)S2[0], (float)S2[1], (float)S2[2], (float)S2[3], (float)S2[4]), FLT_SCALE);
-      } else {
-        ++n_slow;
-        __syncwarp();
-        if (!tail) {
+        for (int q = 0; q < 8; ++q) { const int dq = d[it * 8 + q] >> (W_BITS - 5); p1[q] = dq * gX[it * 8 + q]; p2[q] = dq * gY[it * 8 + q]; }
+        if (nv > 0) {
 #pragma unroll
-          for (int it = 0; it < 2; ++it) {
-            const int ch = (it ? xB : xA) >> 3;
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-              const int q0 = it * 8 + p, q1 = q0 + 4;
-              const int sl = p * (WIN * 2) + rowA * 2 + ch;
-              w.u.termB[sl] = (float)(d[q0] * gX[q0] + d[q1] * gX[q1]);
-              w.u.termB[NTERM_B + sl] = (float)(d[q0] * gY[q0] + d[q1] * gY[q1]);
-            }
+          for (int k = 0; k < 4; ++k) {
+            t1[k * stepB] = (float)(p1[k] + (p1[k + 4] & pair_mask));
+            t2[k * stepB] = (float)(p2[k] + (p2[k + 4] & pair_mask));
           }
-        } else {
-#pragma unroll
-          for (int it = 0; it < 2; ++it) {
-            const int y = it ? rowB : rowA, nv = it ? nvB : nvA;
-#pragma unroll
-            for (int q = 0; q < 5; ++q) {
-              if (q < nv) {
-                const int sl = WIN * 8 + y * 5 + q;
-                w.u.termB[sl] = (float)(d[it * 8 + q] * gX[it * 8 + q]);
-                w.u.termB[NTERM_B + sl] = (float)(d[it * 8 + q] * gY[it * 8 + q]);
-              }
-            }
-          }
+          if (tail) { t1[4] = (float)p1[4]; t2[4] = (float)p2[4]; }
         }
-        __syncwarp();
-        float cv = 0.f;
-        if (lane < 10) cv = run_chain<2>(w.u.termB + (lane / 5) * NTERM_B, lane % 5);
-        b1 = __fmul_rn(combine_chains(cv, 0), FLT_SCALE);
-        b2 = __fmul_rn(combine_chains(cv, 5), FLT_SCALE);
-        __syncwarp();
       }
+      __syncwarp();
+      float cv = 0.f;
+      if (lane < 10) cv = run_chain(w.term + lane * CH);
+      const float b1 = __fmul_rn(combine_chains(cv, 0), FLT_SCALE);
+      const float b2 = __fmul_rn(combine_chains(cv, 5), FLT_SCALE);
+      __syncwarp();
       float2 delta;
       delta.x = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
       delta.y = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
@@ -473,8 +435,6 @@ __global__ void __launch_bounds__(WARPS * 32, 4) lk_kernel(const __grid_constant
     a.status[(size_t)s * a.stride + i] = status ? 1 : 0;
     if (aa.stats) {
       atomicAdd(&aa.stats[10], (unsigned long long)n_iter);
-      if (n_slow) atomicAdd(&aa.stats[11], (unsigned long long)n_slow);
-      if (n_slowA) atomicAdd(&aa.stats[12], (unsigned long long)n_slowA);
       if (n_restage) atomicAdd(&aa.stats[13], (unsigned long long)n_restage);
     }
   }
@@ -482,7 +442,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) lk_kernel(const __grid_constant
 
 }  // namespace
 
-// ---- TMA descriptors of a padded pyramid block: one 3-D u8 tensor (x, y, sequence) per level, box TB x TB x 1
+// ---- TMA descriptors of a padded pyramid block: one 3-D u8 tensor (x, y, sequence) per level, box TP x rows x 1
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -496,7 +456,7 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-static int make_level_maps(LvbHandle* h, const uint8_t* pyr, int n_seq, CUtensorMap* out) {
+static int make_level_maps(LvbHandle* h, const uint8_t* pyr, int n_seq, int box_rows, CUtensorMap* out) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return lvb_set_err(LVB_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
   const LvbPyramidLayout& L = h->fe.L;
@@ -504,7 +464,7 @@ static int make_level_maps(LvbHandle* h, const uint8_t* pyr, int n_seq, CUtensor
     const LvbLevel& lv = L.lv[l];
     const cuuint64_t dims[3] = {(cuuint64_t)lv.pitch, (cuuint64_t)lv.rows, (cuuint64_t)n_seq};
     const cuuint64_t strides[2] = {(cuuint64_t)lv.pitch, (cuuint64_t)L.bytes_per_seq};
-    const cuuint32_t box[3] = {(cuuint32_t)TB, (cuuint32_t)TB, 1u};
+    const cuuint32_t box[3] = {(cuuint32_t)TP, (cuuint32_t)box_rows, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     const CUresult r = enc(&out[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)(pyr + lv.offset), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -514,20 +474,22 @@ static int make_level_maps(LvbHandle* h, const uint8_t* pyr, int n_seq, CUtensor
   return LVB_OK;
 }
 
-// the handle's own ping-pong pyramids keep their descriptors; temporary pyramids (stage-level entry points) get fresh ones
-static int level_maps(LvbHandle* h, const uint8_t* pyr, int n_seq, CUtensorMap* out) {
+// the handle's own ping-pong pyramids keep their descriptors (two box shapes each: source role, search role); temporary
+// pyramids (stage-level entry points) get fresh ones
+static int level_maps(LvbHandle* h, const uint8_t* pyr, int n_seq, int role /*0 source tile, 1 search tile*/, CUtensorMap* out) {
+  const int box_rows = role == 0 ? TA_ROWS : TB_ROWS;
   for (int k = 0; k < 2; ++k) {
     if (pyr == h->fe.pyr[k] && n_seq == h->fe.S) {
-      if (!h->lk_maps_ok[k]) {
-        int rc = make_level_maps(h, pyr, n_seq, h->lk_maps[k]);
+      if (!h->lk_maps_ok[k][role]) {
+        int rc = make_level_maps(h, pyr, n_seq, box_rows, h->lk_maps[k][role]);
         if (rc != LVB_OK) return rc;
-        h->lk_maps_ok[k] = true;
+        h->lk_maps_ok[k][role] = true;
       }
-      memcpy(out, h->lk_maps[k], sizeof(CUtensorMap) * LVB_MAX_LEVELS);
+      memcpy(out, h->lk_maps[k][role], sizeof(CUtensorMap) * LVB_MAX_LEVELS);
       return LVB_OK;
     }
   }
-  return make_level_maps(h, pyr, n_seq, out);
+  return make_level_maps(h, pyr, n_seq, box_rows, out);
 }
 
 static void fill_lk_args(LkArgs& a, int stride, const float2* ptsA, const int* perm, const int* n_pts, const float2* init,
@@ -540,9 +502,9 @@ static void fill_lk_args(LkArgs& a, int stride, const float2* ptsA, const int* p
 static int fill_lk_common(LvbHandle* h, LkArgs2& aa, const uint8_t* pyrA, const uint8_t* pyrB, int n_seq) {
   if (h->cfg.patch_size != WIN) return lvb_set_err(LVB_E_UNSUPPORTED, "patch_size %d (kernel is built for 21)", h->cfg.patch_size);
   memset(&aa, 0, sizeof(aa));
-  int rc = level_maps(h, pyrA, n_seq, aa.mapA);
+  int rc = level_maps(h, pyrA, n_seq, 0, aa.mapA);
   if (rc != LVB_OK) return rc;
-  rc = level_maps(h, pyrB, n_seq, aa.mapB);
+  rc = level_maps(h, pyrB, n_seq, 1, aa.mapB);
   if (rc != LVB_OK) return rc;
   for (int l = 0; l < h->fe.L.n_levels; ++l) { aa.lw[l] = h->fe.L.lv[l].w; aa.lh[l] = h->fe.L.lv[l].h; }
   int mi = h->cfg.max_iteration; if (mi < 0) mi = 0; if (mi > 100) mi = 100;      // cv clamps maxCount to [0,100]
@@ -550,6 +512,7 @@ static int fill_lk_common(LvbHandle* h, LkArgs2& aa, const uint8_t* pyrA, const 
   aa.max_iter = mi; aa.eps2 = eps * eps; aa.min_eig = 1e-4;
   aa.max_level = h->cfg.pyramid_levels;
   aa.stats = h->fe.stats;
+  aa.no_tma = getenv("LVB_DEBUG_LK_NOTMA") ? 1 : 0; aa.pyrA = pyrA; aa.pyrB = pyrB; aa.L = h->fe.L;
   return LVB_OK;
 }
 

@@ -406,15 +406,20 @@ static int run_compaction(LvbHandle* h, int stage) {
 
 #define RC(x) do { int rc_ = (x); if (rc_ != LVB_OK) return rc_; } while (0)
 
-int fe_process(LvbHandle* h, const uint8_t* images, int on_device, const double* t_img, const LvbImu* imu,
-               const int* n_imu, int imu_stride) {
+// processImage for the whole batch in three pieces, shared by the plain path (fe_process) and the one-graph-per-step path
+// (lvb_step_graph in be_pipeline.cu): host preparation, a capturable enqueue, and the ping-pong toggle.
+//
+// Host part of processImage: bFirstImg gate (:134-142), integrateImuData (:184, :359) and the image batch copy.  Returns in
+// *d_images the device pointer the enqueue reads: the caller's own pointer for device-resident input, fe.img_in otherwise
+// (or always, with stage_to_img_in, so that a captured graph sees one fixed source).
+int fe_host_prep(LvbHandle* h, const uint8_t* images, int on_device, const double* t_img, const LvbImu* imu, const int* n_imu,
+                 int imu_stride, bool stage_to_img_in, const uint8_t** d_images) {
   LvbFrontEnd& fe = h->fe;
-  const int S = fe.S, N = fe.N;
+  const int S = fe.S;
   cudaStream_t st = h->stream;
   const size_t npx = (size_t)fe.W * fe.H;
   // the pinned staging buffers of the previous call must have been consumed
   LVB_CUDA(cudaStreamSynchronize(st));
-  // ---- host part of processImage: bFirstImg gate (:134-142) and integrateImuData (:184, :359)
   for (int s = 0; s < S; ++s) {
     const LvbImu* b = imu + (size_t)s * imu_stride;
     const int nb = n_imu[s];
@@ -429,15 +434,26 @@ int fe_process(LvbHandle* h, const uint8_t* images, int on_device, const double*
     else { for (int i = 0; i < 9; ++i) H[i] = (i % 4 == 0) ? 1.f : 0.f; }
     if (act) { h->h_prev_img_time[s] = t_img[s]; h->h_have_prev[s] = 1; }
   }
-  const uint8_t* d_images = images;
+  *d_images = images;
   if (!on_device) {
     // caller buffers that are already page-locked are copied directly; pageable ones go through pinned staging
     cudaPointerAttributes pa;
     const bool pinned = cudaPointerGetAttributes(&pa, images) == cudaSuccess && pa.type == cudaMemoryTypeHost;
     if (!pinned) { cudaGetLastError(); memcpy(h->pin_images, images, S * npx); }
     LVB_CUDA(cudaMemcpyAsync(fe.img_in, pinned ? images : h->pin_images, S * npx, cudaMemcpyHostToDevice, st));
-    d_images = fe.img_in;
+    *d_images = fe.img_in;
+  } else if (stage_to_img_in) {
+    LVB_CUDA(cudaMemcpyAsync(fe.img_in, images, S * npx, cudaMemcpyDeviceToDevice, st));
+    *d_images = fe.img_in;
   }
+  return LVB_OK;
+}
+
+// Every launch of processImage for the batch (fixed sequence: grids follow capacities, decisions are device-side flags).
+int fe_enqueue(LvbHandle* h, const uint8_t* d_images) {
+  LvbFrontEnd& fe = h->fe;
+  const int S = fe.S, N = fe.N;
+  cudaStream_t st = h->stream;
   LVB_CUDA(cudaMemcpyAsync(fe.Hmat, h->pin_H, sizeof(float) * 9 * S, cudaMemcpyHostToDevice, st));
   LVB_CUDA(cudaMemcpyAsync(fe.active, h->pin_active, sizeof(int) * S, cudaMemcpyHostToDevice, st));
   LVB_CUDA(cudaMemcpyAsync(fe.t_img, h->pin_t, sizeof(double) * S, cudaMemcpyHostToDevice, st));
@@ -484,96 +500,15 @@ int fe_process(LvbHandle* h, const uint8_t* images, int on_device, const double*
   LVB_PROF(h, "publish_kernel");
   publish_kernel<<<S, 256, 0, st>>>(v, lvb_camera(h->cfg));
   LVB_LAUNCH_CHECK(h);
-  fe.cur ^= 1;
   return LVB_OK;
 }
 
-// ---- staged variant (LVB_EXPERIMENT=graph): the front-end half of a step split into host preparation and a
-// capturable enqueue.  The enqueue body below is the launch sequence of fe_process with the staged batch (fe.img_in) as the
-// image source; it must stay in step with fe_process until the split replaces it.
-int fe_graph_host_prep(LvbHandle* h, const uint8_t* images, int on_device, const double* t_img, const LvbImu* imu,
-                       const int* n_imu, int imu_stride) {
-  LvbFrontEnd& fe = h->fe;
-  const int S = fe.S;
-  cudaStream_t st = h->stream;
-  const size_t npx = (size_t)fe.W * fe.H;
-  LVB_CUDA(cudaStreamSynchronize(st));
-  // ---- host part of processImage: bFirstImg gate (:134-142) and integrateImuData (:184, :359)
-  for (int s = 0; s < S; ++s) {
-    const LvbImu* b = imu + (size_t)s * imu_stride;
-    const int nb = n_imu[s];
-    if (!h->h_first_img[s]) {
-      if (nb > 0 && b[0].t - t_img[s] <= 0.0) h->h_first_img[s] = 1;
-    }
-    const int act = h->h_first_img[s];
-    h->pin_active[s] = act;
-    h->pin_t[s] = t_img[s];
-    float* H = h->pin_H + (size_t)s * 9;
-    if (act && h->h_have_prev[s]) predict_homography(h->cfg, b, nb, h->h_prev_img_time[s], t_img[s], H);
-    else { for (int i = 0; i < 9; ++i) H[i] = (i % 4 == 0) ? 1.f : 0.f; }
-    if (act) { h->h_prev_img_time[s] = t_img[s]; h->h_have_prev[s] = 1; }
-  }
-  if (on_device) {
-    LVB_CUDA(cudaMemcpyAsync(fe.img_in, images, S * npx, cudaMemcpyDeviceToDevice, st));
-  } else {
-    cudaPointerAttributes pa;
-    const bool pinned = cudaPointerGetAttributes(&pa, images) == cudaSuccess && pa.type == cudaMemoryTypeHost;
-    if (!pinned) { cudaGetLastError(); memcpy(h->pin_images, images, S * npx); }
-    LVB_CUDA(cudaMemcpyAsync(fe.img_in, pinned ? images : h->pin_images, S * npx, cudaMemcpyHostToDevice, st));
-  }
-  return LVB_OK;
-}
-
-int fe_graph_enqueue(LvbHandle* h) {
-  LvbFrontEnd& fe = h->fe;
-  const int S = fe.S, N = fe.N;
-  cudaStream_t st = h->stream;
-  LVB_CUDA(cudaMemcpyAsync(fe.Hmat, h->pin_H, sizeof(float) * 9 * S, cudaMemcpyHostToDevice, st));
-  LVB_CUDA(cudaMemcpyAsync(fe.active, h->pin_active, sizeof(int) * S, cudaMemcpyHostToDevice, st));
-  LVB_CUDA(cudaMemcpyAsync(fe.t_img, h->pin_t, sizeof(double) * S, cudaMemcpyHostToDevice, st));
-  const int cur = fe.cur, prv = cur ^ 1;
-  RC(fe_build_pyramid(h, fe.img_in, S, fe.pyr[cur], fe.blur[cur]));
-  FeView v = make_view(h);
-  LVB_PROF(h, "frame_begin_kernel");
-  frame_begin_kernel<<<(S + 127) / 128, 128, 0, st>>>(v);
-  LVB_LAUNCH_CHECK(h);
-  LVB_PROF(h, "iota_perm_kernel");
-  iota_perm_kernel<<<dim3((N + 127) / 128, S), 128, 0, st>>>(v);
-  LVB_LAUNCH_CHECK(h);
-  const float2* src[2] = {fe.trk[prv].curr, fe.new_pts};
-  int* perm2[2] = {fe.ch[0].perm, fe.ch[1].perm};
-  int* n2[2] = {fe.ch[0].n, fe.ch[1].n};
-  float2* out2[2] = {fe.ch[0].out, fe.ch[1].out};
-  uint8_t* st2[2] = {fe.ch[0].status, fe.ch[1].status};
-  const float2* cur2[2] = {fe.ch[0].slot_curr, fe.ch[1].slot_curr};
-  // forward LK (+ in-image gate), tracked and new chains in one launch
-  RC(fe_lk_launch2(h, fe.pyr[prv], fe.pyr[cur], S, N, src, perm2, n2, nullptr, 0, fe.Hmat, out2, st2, 1, nullptr));
-  RC(run_compaction(h, 0));
-  // backward LK (+ in-image + 1-px consistency gate)
-  RC(fe_lk_launch2(h, fe.pyr[cur], fe.pyr[prv], S, N, cur2, perm2, n2, src, 1, nullptr, out2, st2, 2, src));
-  RC(run_compaction(h, 1));
-  // descriptor gate: tracked features against the descriptor stored at birth, new ones prev vs curr
-  RC(fe_orb_launch(h, fe.pyr[cur], fe.blur[cur], S, N, fe.ch[0].slot_curr, fe.ch[0].perm, fe.ch[0].n, nullptr, nullptr, 0,
-                   fe.trk[prv].desc, fe.ch[0].status, nullptr));
-  RC(fe_orb_launch(h, fe.pyr[prv], fe.blur[prv], S, N, fe.new_pts, fe.ch[1].perm, fe.ch[1].n, nullptr, fe.ch[1].desc, 1,
-                   nullptr, nullptr, nullptr));
-  RC(fe_orb_launch(h, fe.pyr[cur], fe.blur[cur], S, N, fe.ch[1].slot_curr, fe.ch[1].perm, fe.ch[1].n, nullptr, nullptr, 0,
-                   fe.ch[1].desc, fe.ch[1].status, nullptr));
-  RC(run_compaction(h, 2));
-  // undistort to pixel coordinates + fundamental-matrix RANSAC
-  for (int c = 0; c < 2; ++c) {
-    RC(fe_undistort_launch(h, S, N, src[c], fe.ch[c].perm, fe.ch[c].n, fe.ch[c].uprev, 1));
-    RC(fe_undistort_launch(h, S, N, fe.ch[c].slot_curr, fe.ch[c].perm, fe.ch[c].n, fe.ch[c].ucurr, 1));
-    RC(fe_ransac_launch(h, S, N, fe.ch[c].uprev, fe.ch[c].ucurr, fe.ch[c].n, fe.ch[c].status, nullptr, fe.ch[c].fail));
-  }
-  RC(run_compaction(h, 3));
-  LVB_PROF(h, "finalize_kernel");
-  finalize_kernel<<<S, 256, 0, st>>>(v);
-  LVB_LAUNCH_CHECK(h);
-  RC(fe_detect_launch(h, fe.pyr[cur], S, fe.do_detect, 1, nullptr, fe.trk[cur].curr, fe.mask_n, fe.want, fe.det_pts, fe.det_n));
-  LVB_PROF(h, "publish_kernel");
-  publish_kernel<<<S, 256, 0, st>>>(v, lvb_camera(h->cfg));
-  LVB_LAUNCH_CHECK(h);
+int fe_process(LvbHandle* h, const uint8_t* images, int on_device, const double* t_img, const LvbImu* imu,
+               const int* n_imu, int imu_stride) {
+  const uint8_t* d_images = nullptr;
+  RC(fe_host_prep(h, images, on_device, t_img, imu, n_imu, imu_stride, false, &d_images));
+  RC(fe_enqueue(h, d_images));
+  h->fe.cur ^= 1;
   return LVB_OK;
 }
 

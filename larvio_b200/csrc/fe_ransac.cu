@@ -26,6 +26,7 @@ struct RansacArgs {
   const float2* p1; const float2* p2; const int* n; int stride;
   uint8_t* mask; const int* enable; int* fail;   // fail[s]=1 -> chain already aborted, skip
   double threshold, confidence; int max_iters;
+  unsigned long long* stats;   // [14] += 1 per point set in the 8..13 regime (OpenCV's LMedS winner there is rounding noise)
 };
 
 struct Rng {
@@ -248,6 +249,7 @@ __global__ void __launch_bounds__(256) ransac_kernel(RansacArgs a) {
   __syncthreads();
   if (n == 7) { for (int i = tid; i < n; i += 256) mask[i] = 1; return; }
   const bool lmeds = n < 15;
+  if (tid == 0 && n <= 13 && a.stats) atomicAdd(&a.stats[14], 1ull);
   if (tid == 0) {
     s_ctl[0] = 0; s_ctl[1] = 0; s_ctl[3] = 0; s_ctl[6] = 0; s_ctl[7] = 0;
     int niters = max(a.max_iters, 1);
@@ -378,7 +380,7 @@ int fe_ransac_launch(LvbHandle* h, int n_seq, int stride, const float2* p1, cons
                      uint8_t* mask, const int* enable, int* fail) {
   RansacArgs a;
   a.p1 = p1; a.p2 = p2; a.n = n; a.stride = stride; a.mask = mask; a.enable = enable; a.fail = fail;
-  a.threshold = 1.0; a.confidence = 0.99; a.max_iters = 1000;
+  a.threshold = 1.0; a.confidence = 0.99; a.max_iters = 1000; a.stats = h->fe.stats;
   LVB_PROF(h, "ransac_kernel");
   ransac_kernel<<<n_seq, 256, 0, h->stream>>>(a);
   LVB_LAUNCH_CHECK(h);

@@ -132,8 +132,8 @@ struct LvbHandle {
   // Staged kernel variants, OFF by default: comma-separated names in LVB_EXPERIMENT select them at lvb_create time
   // (DESIGN.md 7); host-only, so the kernel argument layouts of the default path do not change.
   unsigned experiments = 0;
-  CUtensorMap lk_maps[2][LVB_MAX_LEVELS];          // TMA descriptors of the two ping-pong pyramids (fe_lk.cu), built on first use
-  bool lk_maps_ok[2] = {false, false};
+  CUtensorMap lk_maps[2][2][LVB_MAX_LEVELS];       // TMA descriptors of the two ping-pong pyramids x {source, search} box (fe_lk.cu), built on first use
+  bool lk_maps_ok[2][2] = {{false, false}, {false, false}};
   cudaGraphExec_t gexec[2] = {nullptr, nullptr};   // LVB_EXPERIMENT=graph: one captured step per pyramid parity
   long long glaunches[2] = {0, 0};
 };
@@ -185,6 +185,6 @@ int fe_ransac_launch(LvbHandle* h, int n_seq, int stride, const float2* p1, cons
 int fe_process(LvbHandle* h, const uint8_t* images, int on_device, const double* t_img, const LvbImu* imu,
                const int* n_imu, int imu_stride);
 int fe_fetch_messages(LvbHandle* h, LvbFeature* out_feat, int* out_n, uint8_t* has_features);
-int fe_graph_host_prep(LvbHandle* h, const uint8_t* images, int on_device, const double* t_img, const LvbImu* imu,
-                       const int* n_imu, int imu_stride);
-int fe_graph_enqueue(LvbHandle* h);
+int fe_host_prep(LvbHandle* h, const uint8_t* images, int on_device, const double* t_img, const LvbImu* imu, const int* n_imu,
+                 int imu_stride, bool stage_to_img_in, const uint8_t** d_images);
+int fe_enqueue(LvbHandle* h, const uint8_t* d_images);

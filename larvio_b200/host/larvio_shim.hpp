@@ -120,6 +120,10 @@ class LarVio {
   void getVel(double v[3]) { double t; lvb_get_state(s_->h(), 0, &t, nullptr, nullptr, v, nullptr, nullptr, nullptr, nullptr); }
   void getPpose(double P[36]) { double t; lvb_get_state(s_->h(), 0, &t, nullptr, nullptr, nullptr, nullptr, nullptr, P, nullptr); }
   void getPvel(double P[9]) { double t; lvb_get_state(s_->h(), 0, &t, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, P); }
+  // larvio.h:86-87: map<FeatureIDType, Vector3d> -> map<id, Point3>; both clear what they return, like larvio.cpp:2719-2733
+  struct Point3 { double x, y, z; };
+  void getStableMapPointPositions(std::map<unsigned long long, Point3>& mMapPoints) { get_points(0, mMapPoints); }
+  void getActiveeMapPointPositions(std::map<unsigned long long, Point3>& mMapPoints) { get_points(1, mMapPoints); }
   void getSwPoses(std::vector<Pose>& out) {
     double qp[64 * 7]; int n = 0;
     lvb_get_window(s_->h(), 0, qp, 64, &n);
@@ -127,6 +131,11 @@ class LarVio {
     for (int i = 0; i < n; ++i) { std::memcpy(out[i].q_xyzw, qp + i * 7, 4 * sizeof(double)); std::memcpy(out[i].p, qp + i * 7 + 4, 3 * sizeof(double)); }
   }
  private:
+  void get_points(int which, std::map<unsigned long long, Point3>& m) {
+    unsigned long long ids[512]; double xyz[512 * 3]; int n = 0;
+    lvb_get_points(s_->h(), 0, which, ids, xyz, 512, &n);
+    for (int i = 0; i < n; ++i) m[ids[i]] = Point3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+  }
   std::shared_ptr<Session> s_;
   std::string cfg_;
   LvbStaticInit* init_ = nullptr;

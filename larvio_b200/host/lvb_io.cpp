@@ -143,3 +143,26 @@ extern "C" int lvbio_euroc_read_image_list(const char* csv_path, double* t, char
   *n = cnt;
   return 0;
 }
+
+// findFirstAlign (include/utils/DataReader.hpp:123-165): first image / IMU sample pair with equal stamps.  Returns 0 and the
+// two start indices, -1 if the streams never align.
+extern "C" int lvbio_first_align(const double* t_img, int n_img, const LvbImu* imu, int n_imu, int* img0, int* imu0) {
+  if (!t_img || !imu || n_img <= 0 || n_imu <= 0 || !img0 || !imu0) { g_io_err = "lvbio_first_align: bad argument"; return -1; }
+  const double imu_t0 = imu[0].t, img_t0 = t_img[0];
+  if (imu_t0 > img_t0) {
+    for (int i = 1; i < n_img; ++i)
+      if (imu_t0 <= t_img[i]) {
+        for (int j = 0; j < n_imu; ++j)
+          if (imu[j].t == t_img[i]) { *img0 = i; *imu0 = j; return 0; }
+        break;
+      }
+  } else if (imu_t0 < img_t0) {
+    for (int j = 1; j < n_imu; ++j)
+      if (imu[j].t == img_t0) { *img0 = 0; *imu0 = j; return 0; }
+  } else {
+    *img0 = 0; *imu0 = 0;
+    return 0;
+  }
+  g_io_err = "no image/IMU pair with equal stamps";
+  return -1;
+}

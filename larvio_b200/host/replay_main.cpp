@@ -22,6 +22,7 @@ const char* lvbio_last_error(void);
 int lvbio_png_read_gray8(const char* path, uint8_t* out, int cap_bytes, int* w, int* h);
 int lvbio_euroc_read_imu(const char* csv_path, LvbImu* out, int cap, int* n);
 int lvbio_euroc_read_image_list(const char* csv_path, double* t, char* names, int name_len, int cap, int* n);
+int lvbio_first_align(const double* t_img, int n_img, const LvbImu* imu, int n_imu, int* img0, int* imu0);
 }
 
 namespace {
@@ -38,27 +39,6 @@ struct Seq {
   double take_off = 0.0;
   FILE* log = nullptr;
 };
-
-// findFirstAlign (DataReader.hpp:123-165)
-bool first_align(const Seq& q, size_t* img0, size_t* imu0) {
-  const double imu_t0 = q.imu[0].t, img_t0 = q.t_img[0];
-  if (imu_t0 > img_t0) {
-    for (size_t i = 1; i < q.t_img.size(); ++i)
-      if (imu_t0 <= q.t_img[i]) {
-        for (size_t j = 0; j < q.imu.size(); ++j)
-          if (q.imu[j].t == q.t_img[i]) { *img0 = i; *imu0 = j; return true; }
-        return false;
-      }
-    return false;
-  }
-  if (imu_t0 < img_t0) {
-    for (size_t j = 1; j < q.imu.size(); ++j)
-      if (q.imu[j].t == img_t0) { *img0 = 0; *imu0 = j; return true; }
-    return false;
-  }
-  *img0 = 0; *imu0 = 0;
-  return true;
-}
 
 // Quaterniond(R) coefficients (w, x, y, z) of a rotation matrix (row-major)
 void rot_to_quat_wxyz(const double* R, double* q) {
@@ -104,10 +84,10 @@ int main(int argc, char** argv) {
     if (lvbio_euroc_read_imu(mcsv.c_str(), nullptr, 0, &n) != 0 || n == 0) { std::fprintf(stderr, "%s: %s\n", mcsv.c_str(), lvbio_last_error()); return 1; }
     q.imu.resize(n);
     lvbio_euroc_read_imu(mcsv.c_str(), q.imu.data(), n, &n);
-    size_t i0 = 0, m0 = 0;
-    if (!first_align(q, &i0, &m0)) { std::fprintf(stderr, "%s: no image/IMU pair with equal stamps\n", q.dir.c_str()); return 1; }
+    int i0 = 0, m0 = 0;
+    if (lvbio_first_align(q.t_img.data(), (int)q.t_img.size(), q.imu.data(), (int)q.imu.size(), &i0, &m0) != 0) { std::fprintf(stderr, "%s: %s\n", q.dir.c_str(), lvbio_last_error()); return 1; }
     q.t_img.erase(q.t_img.begin(), q.t_img.begin() + i0);
-    q.names.erase(q.names.begin(), q.names.begin() + i0 * NAME_LEN);
+    q.names.erase(q.names.begin(), q.names.begin() + (size_t)i0 * NAME_LEN);
     q.imu.erase(q.imu.begin(), q.imu.begin() + m0);
     if (q.t_img.size() < n_frames) n_frames = q.t_img.size();
     q.init = lvb_static_init_create(&cfg);

@@ -312,6 +312,8 @@ class LarVioOracle:
             self.grid_width = self.x_max - self.x_min; self.grid_height = self.y_max - self.y_min
         self.grid_map = {i: [] for i in range(self.grid_rows * self.grid_cols)}
         self.feature_states = []          # ids of EKF-SLAM features, in state order
+        self.lost_slam_features = {}      # id -> position at removal (larvio.h:208), cleared by the getter
+        self.active_slam_features = {}    # id -> latest position while in the state (larvio.h:212), cleared by the getter
         self.last_ZUPT_time = 0.0
         Qc = np.zeros((12, 12))
         Qc[0:3, 0:3] = np.eye(3) * self.gyro_noise; Qc[3:6, 3:6] = np.eye(3) * self.acc_noise
@@ -361,7 +363,18 @@ class LarVioOracle:
         self._prune()
         if self.if_FEJ_config and not self.if_FEJ and self.imu_state.time - self.take_off_stamp >= 0:
             self.if_FEJ = True
+        for fid in self.feature_states:                    # :455-458  active_slam_features[fid] = map_server[fid]
+            self.active_slam_features[fid] = self.map_server[fid].position.copy()
         return True
+
+    # ---- :2719-2733: both getters hand their map over and clear it
+    def get_stable_map_points(self):
+        out = self.lost_slam_features; self.lost_slam_features = {}
+        return out
+
+    def get_active_map_points(self):
+        out = self.active_slam_features; self.active_slam_features = {}
+        return out
 
     # ---- :464-517
     def _batch_imu(self, time_bound, imu):
@@ -1004,6 +1017,7 @@ class LarVioOracle:
             keep = [i for i in range(self.P.shape[0]) if not (i0 <= i < i0 + self.idp)]
             self.P = self.P[np.ix_(keep, keep)]
             self.feature_states.pop(seq)
+            self.lost_slam_features[fid] = self.map_server[fid].position.copy()      # :3342
             del self.map_server[fid]
 
     # ---- updateGridMap :3351-3370

@@ -468,7 +468,80 @@ def _python_two_call_replay(c, mav_dir):
     return np.array(ref)
 
 
-@pytest.mark.xfail(strict=False, reason="first GPU execution of the C++ replay driver (written after the GPU budget of round 1 was spent)")
+def _write_mav(tmp_path, seq):
+    """A synthetic sequence as an EuRoC ASL directory (PNG + csv, ns stamps)."""
+    import cv2
+    mav = tmp_path / "mav0"
+    (mav / "cam0" / "data").mkdir(parents=True); (mav / "imu0").mkdir(parents=True)
+    with open(mav / "cam0" / "data.csv", "w") as f:
+        f.write("#timestamp [ns],filename\n")
+        for t, im in zip(seq.img_t, seq.images):
+            ns = int(round(t * 1e9)); cv2.imwrite(str(mav / "cam0" / "data" / ("%d.png" % ns)), im); f.write("%d,%d.png\r\n" % (ns, ns))
+    with open(mav / "imu0" / "data.csv", "w") as f:
+        f.write("#timestamp [ns],w_x,w_y,w_z,a_x,a_y,a_z\n")
+        for r in seq.imu:
+            f.write("%d,%.17g,%.17g,%.17g,%.17g,%.17g,%.17g\r\n" % (int(round(r[0] * 1e9)), *r[1:]))
+    return mav
+
+
+def test_shim_facade_linked_and_run_matches_the_oracle(tmp_path, lib_built):
+    """larvio_shim.hpp (the reference's ImageProcessor / LarVio classes over the C ABI) compiled, LINKED and RUN
+    as the reference's own main loop (larvio_b200/bin/larvio_shim_demo <- host/shim_main.cpp, app/larvioMain.cpp:87-117) on an
+    on-disk sequence; euroc.yaml defaults (hybrid, 5x6 SLAM grid), self-start from a standstill.  Every odometry line and
+    every map-point list (getStableMapPointPositions / getActiveeMapPointPositions, larvio.h:86-87) is compared with the
+    CPU oracle driven by the same files."""
+    import subprocess
+    from larvio_b200 import synth, euroc
+    from larvio_b200.config import Config
+    from oracle.frontend import ImageProcessorOracle
+    from oracle.backend import LarVioOracle
+    from oracle.initializer import StaticInitializerOracle
+    cfg_path = os.path.join(ROOT, "configs", "euroc_mono.yaml")
+    c = Config.load(cfg_path)
+    NF = 150
+    seq = synth.make_sequence(c.raw, 3, NF, static_until=1.4)
+    mav = _write_mav(tmp_path, seq)
+    exe = os.path.join(ROOT, "larvio_b200", "bin", "larvio_shim_demo")
+    r = subprocess.run([exe, cfg_path, str(mav)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    odo = [np.array(l.split()[1:], float) for l in r.stdout.splitlines() if l.startswith("ODO ")]
+    pts = [l.split() for l in r.stdout.splitlines() if l.startswith("PTS ")]
+    # the oracle over the same files
+    fe = ImageProcessorOracle(c.raw); be = LarVioOracle(c.raw); init = StaticInitializerOracle(c.raw)
+    imu = []; started = False; ref = []; ref_pts = []
+    for t, img, rows in euroc.Replay(str(mav)):
+        imu.extend(rows.tolist())
+        msg = fe.process_image(img, t, np.array(imu).reshape(-1, 7))
+        if msg is None:
+            continue
+        if not started:
+            o = init.try_inc_init(msg.ids, msg.data[:, :2], msg.t, np.array(imu).reshape(-1, 7))
+            if o is None:
+                continue
+            be.set_initial_state(o["t"], o["q"], o["p"], o["v"], o["bg"], o["ba"])
+            del imu[:o["n_consumed"]]
+            started = True
+        if be.process_features(msg, imu):
+            st = be.imu_state
+            ref.append(np.concatenate([[t], st.q, st.p, st.v]))
+            if len(ref) % 10 == 0:
+                for tag, m in (("S", be.get_stable_map_points()), ("A", be.get_active_map_points())):
+                    if m:
+                        ref_pts.append((tag, m))
+    assert len(odo) == len(ref) >= 60
+    odo = np.array(odo); ref = np.array(ref)
+    assert np.abs(odo[:, 0] - ref[:, 0]).max() < 1e-9
+    qd = np.minimum(np.abs(odo[:, 1:5] - ref[:, 1:5]).max(1), np.abs(odo[:, 1:5] + ref[:, 1:5]).max(1))
+    assert qd.max() < 1e-8 and np.abs(odo[:, 5:] - ref[:, 5:]).max() < 1e-8
+    assert len(pts) == len(ref_pts) >= 2 and any(p[1] == "S" for p in pts) and any(p[1] == "A" for p in pts)
+    for got, (tag, m) in zip(pts, ref_pts):
+        assert got[1] == tag and int(got[2]) == len(m)
+        ids = [int(x) for x in got[3::4]]
+        assert ids == sorted(m.keys())                                     # std::map order
+        xyz = np.array(got[3:], float).reshape(-1, 4)[:, 1:]
+        assert np.abs(xyz - np.array([m[k] for k in ids])).max() < 1e-7
+
+
 def test_cpp_replay_driver_matches_the_python_two_call_path(tmp_path, lib_built):
     """larvio_b200/bin/larvio_replay on a synthetic EuRoC-layout directory (PNG + csv on disk, self-start from a
     standstill) must write the trajectory the Python mirror of the same calls produces."""
@@ -480,16 +553,7 @@ def test_cpp_replay_driver_matches_the_python_two_call_path(tmp_path, lib_built)
     c = Config.load(cfg_path)
     NF = 40
     seq = synth.make_sequence(c.raw, 3, NF, static_until=1.4)
-    mav = tmp_path / "mav0"
-    (mav / "cam0" / "data").mkdir(parents=True); (mav / "imu0").mkdir(parents=True)
-    with open(mav / "cam0" / "data.csv", "w") as f:
-        f.write("#timestamp [ns],filename\n")
-        for t, im in zip(seq.img_t, seq.images):
-            ns = int(round(t * 1e9)); cv2.imwrite(str(mav / "cam0" / "data" / ("%d.png" % ns)), im); f.write("%d,%d.png\r\n" % (ns, ns))
-    with open(mav / "imu0" / "data.csv", "w") as f:
-        f.write("#timestamp [ns],w_x,w_y,w_z,a_x,a_y,a_z\n")
-        for r in seq.imu:
-            f.write("%d,%.17g,%.17g,%.17g,%.17g,%.17g,%.17g\r\n" % (int(round(r[0] * 1e9)), *r[1:]))
+    mav = _write_mav(tmp_path, seq)
     exe = os.path.join(ROOT, "larvio_b200", "bin", "larvio_replay")
     r = subprocess.run([exe, cfg_path, str(tmp_path / "out"), str(mav)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
@@ -658,6 +722,19 @@ def test_full_batch_of_distinct_sequences_matches_oracle_on_a_sample(cfg):
                 steps += 1
     b.close()
     assert steps >= len(sample) * 10 and worst < 1e-8
+
+
+def test_more_than_64_pending_imu_samples_are_consumed_like_the_reference(lib_built):
+    """pub_frequency 2 Hz with a 200 Hz IMU leaves ~100 samples in the caller's buffer per feature message.
+    batchImuProcessing consumes the whole buffer (larvio.cpp:464-512); the per-call staging grows to hold it (it used to
+    be capped at 64 samples, which would have stopped the propagation short of the message time)."""
+    from larvio_b200 import synth
+    from larvio_b200.config import Config
+    c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), max_features_in_one_grid=0, sw_size=12, pub_frequency=2)
+    sq = [synth.make_sequence(c.raw, 20 + s, 64) for s in range(2)]
+    rep = _drive(c, sq, 64, 'step')
+    assert rep['steps'] >= 2 * 5 and rep['ok_mismatch'] == 0 and rep['imu_mismatch'] == 0
+    assert rep['p'] < 1e-8 and rep['v'] < 1e-8 and rep['q'] < 1e-8 and rep['Prel'] < 1e-8
 
 
 def test_unsupported_configs_fail_loudly(lib_built):
