@@ -42,7 +42,7 @@ larvio_b200/csrc/%.o: larvio_b200/csrc/%.cpp include/larvio_b200.h
 
 $(LIB): $(OBJ)
 	mkdir -p larvio_b200/lib
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart -lpthread
 
 clean:
 	rm -f larvio_b200/csrc/*.o larvio_b200/csrc/*.o.log $(LIB) $(IOLIB) $(REPLAY) $(SHIMDEMO)

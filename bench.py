@@ -50,14 +50,20 @@ def probe_fp64_peak(device, n=8192, reps=3):
             t0 = time.perf_counter(); torch.matmul(a, b); dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return 2.0 * n ** 3 / best / 1e12
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch over 64 sequences, from the `ncu --set full` captures summarised
-# in profiles/r1g_ncu_summary.md (scripts/gpu_profile.sh); bytes per SEQUENCE per launch, scaled by the sequences a launch covers
-NCU_TRAFFIC_PER_SEQ = {"lk_kernel": (55.305472e6 + 1.048832e6) / 64, "be_chol_kernel": 1.491712e6 / 64, "be_gemm_kernel": 24.881408e6 / 64,
-                       "orb_kernel": (37.840128e6 + 0.019968e6) / 64, "mineig_kernel": (47.904e6 + 45.15072e6) / 64,
-                       "candidates_kernel": (115.406592e6 + 4.700416e6) / 64, "clahe_apply_kernel": (24.376576e6 + 0.219904e6) / 64,
-                       "blur7_kernel": (24.89728e6 + 0.01664e6) / 64, "ransac_kernel": 0.26752e6 / 64, "be_feature_kernel": (1.123072e6 + 0.026368e6) / 64,
-                       "be_trsm_kernel": 6.039296e6 / 64, "be_propagate_kernel": 2.5344e6 / 64, "select_kernel": 3.261184e6 / 64}
+def load_ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch and per sequence from the newest committed `ncu --set full`
+    summary (profiles/*_ncu_traffic.json, written by scripts/ncu_summary.py on the GPU box)."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_traffic.json"))):
+        best = f
+    if not best:
+        return {}, None
+    try:
+        d = json.load(open(best))
+        return {k: v["dram_bytes_per_launch"] / max(v.get("sequences_per_launch", 64), 1) for k, v in d["kernels"].items()}, os.path.relpath(best, ROOT)
+    except Exception:
+        return {}, None
 
 
 def effective_cores():
@@ -309,8 +315,8 @@ def main():
                   l2_policy="each step reads a fresh %.1f MB image batch and touches >250 MB of per-sequence state (> 126 MB L2)" % (S * B0 / 1e6),
                   inputs=("one pool of %d seeded sequences (seed 1234+i)" % S) + ("" if world == 1 else
                           ", rendered cooperatively by the %d ranks, exchanged over NCCL, replayed on every GPU rotated by rank*%d/%d" % (world, S, world)))
-    if os.environ.get("LVB_EXPERIMENT"):
-        config["experiments"] = os.environ["LVB_EXPERIMENT"]         # staged kernel variants in effect; none by default
+    if os.environ.get("LVB_NO_GRAPH"):
+        config["no_graph"] = True                                    # debugging switch: stream launches instead of one graph per step
     ncores = effective_cores()
 
     # ------------------------------------------------------------------ reference arm
@@ -549,8 +555,9 @@ def main():
             else:
                 ach = mdl[1] / (per_launch_ms * 1e-3) / 1e12
                 roofs[kname] = dict(bound="fp64", achieved=ach, peak=FP64_PEAK_TF, unit="TFLOP/s", frac=ach / FP64_PEAK_TF, flops_per_launch=mdl[1], basis=mdl[2])
-        roof = dict(kernel=dom, bound="hbm", achieved=None, peak=hbm_peak, unit="GB/s", frac=None, traffic=(NCU_TRAFFIC_PER_SEQ[dom] * (S // NSUB) if dom in NCU_TRAFFIC_PER_SEQ else None),
-                    traffic_source="profiles/r1g_ncu_summary.md (ncu --set full, cold cache, per launch)", peak_source=peak_src,
+        ncu_traffic, ncu_src = load_ncu_traffic()
+        roof = dict(kernel=dom, bound="hbm", achieved=None, peak=hbm_peak, unit="GB/s", frac=None, traffic=(ncu_traffic[dom] * (S // NSUB) if dom in ncu_traffic else None),
+                    traffic_source=("%s (ncu --set full, cold cache, per launch, scaled to the sequences of one launch)" % ncu_src) if ncu_src else None, peak_source=peak_src,
                     ms_per_launch=dom_ms / max(dom_n, 1))
         if dom in roofs:
             roof.update({kk: roofs[dom][kk] for kk in ("bound", "achieved", "peak", "unit", "frac")})

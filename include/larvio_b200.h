@@ -161,6 +161,23 @@ int lvb_get_calibration(LvbHandle* h, int seq, double* R_imu_cam9, double* t_cam
 /* Full covariance of one sequence, row-major dim x dim (dim returned). */
 int lvb_get_covariance(LvbHandle* h, int seq, double* P, int cap_dim, int* dim);
 
+/* ---- sharding over the GPUs of a node inside ONE process (lvb_create(cfg, n_seq, gpu_ids, n_gpu)) ----
+ * n_seq independent sequences are split into n_gpu contiguous blocks, block k lives on device gpu_ids[k] (ids may repeat:
+ * several shards per GPU overlap their host work).  Sequences never interact, so there is no exchange step; lvbm_step runs
+ * lvb_step of every shard on its own host thread and lvbm_get_states gathers the trajectories.  Array arguments are the
+ * [n_seq]-sized arrays of lvb_step, images in HOST memory.  (Across processes - one rank per GPU - use one handle per rank
+ * and any transport for the gather; bench.py does that with NCCL.) */
+typedef struct LvbMulti LvbMulti;
+int lvbm_create(const LvbConfig* cfg, int n_seq, const int* gpu_ids, int n_gpu, LvbMulti** out);
+void lvbm_destroy(LvbMulti* m);
+int lvbm_n_shards(const LvbMulti* m);
+int lvbm_set_initial_state(LvbMulti* m, int seq, double t, const double* q_xyzw, const double* p, const double* v,
+                           const double* bg, const double* ba);
+int lvbm_step(LvbMulti* m, const uint8_t* images, const double* t_img, LvbImu* imu, int* n_imu, int imu_stride,
+              uint8_t* published);
+int lvbm_get_states(LvbMulti* m, double* out /* [n_seq][17] */);
+long long lvbm_launch_count(const LvbMulti* m);
+
 /* ---- stage-level entry points (host buffers; used by the parity tests and profilers) ---- */
 /* CLAHE(3.0, 8x8) + 3-level padded LK pyramid + ORB blur for n images: outputs tightly packed
  * (no padding): clahe [n][H][W], l1 [n][H1][W1], l2 [n][H2][W2], blur [n][H][W]. Any may be NULL. */

@@ -79,8 +79,47 @@ EXPORTED_SYMBOLS = [
     "lvb_synchronize", "lvb_set_initial_state", "lvb_get_state", "lvb_get_states", "lvb_get_window",
     "lvb_get_covariance", "lvb_get_calibration", "lvb_static_init_create", "lvb_static_init_destroy", "lvb_static_init_try", "lvbk_pyramid", "lvbk_lk", "lvbk_orb", "lvbk_detect", "lvbk_undistort",
     "lvbk_ransac", "lvb_launch_count", "lvb_profile_enable", "lvb_profile_reset", "lvb_profile_get", "lvb_get_stats", "lvb_debug_icore",
-    "lvb_get_points",
+    "lvb_get_points", "lvbm_create", "lvbm_destroy", "lvbm_n_shards", "lvbm_set_initial_state", "lvbm_step", "lvbm_get_states",
+    "lvbm_launch_count",
 ]
+
+
+class MultiBatch:
+    """lvbm_*: the batch sharded over several GPUs (or several shards of one GPU) inside one process."""
+
+    def __init__(self, cfg, n_seq: int, gpu_ids):
+        self.S = n_seq
+        ids = (C.c_int * len(gpu_ids))(*gpu_ids)
+        h = _vp()
+        _lib.lvbm_create.restype = C.c_int; _lib.lvbm_step.restype = C.c_int; _lib.lvbm_get_states.restype = C.c_int
+        _lib.lvbm_set_initial_state.restype = C.c_int; _lib.lvbm_launch_count.restype = C.c_longlong
+        _lib.lvbm_launch_count.argtypes = [_vp]; _lib.lvbm_destroy.argtypes = [_vp]; _lib.lvbm_destroy.restype = None
+        st = cfg.to_struct() if hasattr(cfg, "to_struct") else cfg
+        _check(_lib.lvbm_create(C.byref(st), n_seq, ids, len(gpu_ids), C.byref(h)))
+        self._h = h
+
+    def set_initial_state(self, seq, t, q_xyzw, p, v, bg, ba):
+        a = [np.ascontiguousarray(x, np.float64) for x in (q_xyzw, p, v, bg, ba)]
+        _check(_lib.lvbm_set_initial_state(self._h, int(seq), C.c_double(float(t)), *[_p(x) for x in a]))
+
+    def step(self, images, t_img, imu, n_imu):
+        images = np.ascontiguousarray(images, np.uint8); t_img = np.ascontiguousarray(t_img, np.float64)
+        pub = np.zeros(self.S, np.uint8)
+        _check(_lib.lvbm_step(self._h, _p(images), _p(t_img), _p(imu), _p(n_imu), imu.shape[1], _p(pub)))
+        return pub
+
+    def get_states(self):
+        out = np.zeros((self.S, 17))
+        _check(_lib.lvbm_get_states(self._h, _p(out)))
+        return out
+
+    @property
+    def launches(self):
+        return int(_lib.lvbm_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            _lib.lvbm_destroy(self._h); self._h = None
 
 
 if hasattr(_lib, "lvb_static_init_create"):

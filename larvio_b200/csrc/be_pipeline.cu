@@ -1216,68 +1216,13 @@ __global__ void __launch_bounds__(256) be_slam_grow_kernel(BeView v) {
   if (tid == 0) { ic[I_DIM] = d + n_new; ic[I_NF] = nf + n_new; ic[I_NNEW] = 0; }
 }
 
-// ====================================================================== thin QR compression (Householder)
-// Only when rows > cols (:1430, :2209).  Column-major Hs, one CTA per sequence.
+// ====================================================================== QR compression (SPQR thin QR at larvio.cpp:1430-1449, 2151-2171)
+// Householder, column by column over the structurally nonzero columns (kmap), on the column-major stack; warp-shuffle dot
+// products, one warp per trailing column.  2 block barriers per column: the warp that updates column j+1 also leaves its
+// squared norm below the diagonal and its diagonal entry in shared memory, so iteration j+1 starts without a reduction pass;
+// every thread derives (alpha, beta) from those two numbers itself; the finished column is zeroed while the reflector is
+// copied out.  (A 5-barrier version with a single-thread section measured 66 us vs 53 us per 16-sequence launch, round 2.)
 __global__ void __launch_bounds__(512) be_qr_kernel(BeView v) {
-  extern __shared__ double qsm[];      // reflector [RMAX]
-  __shared__ double red[16];
-  __shared__ double s_alpha, s_beta;
-  const int s = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  int* ic = icore_of(v, s);
-  if (!ic[I_OK]) return;
-  const int R = ic[I_ROWS], c = ic[I_NC];        // compression over the structurally nonzero columns only (be_colscan_kernel)
-  if (R <= c || R == 0) return;
-  const int RMAX = v.be.RMAX, LD = v.be.LD;
-  double* Hs = v.be.Hs + (size_t)s * LD * RMAX;
-  double* rs = v.be.rs + (size_t)s * RMAX;
-  const int* km = v.be.kmap + (size_t)s * LD;
-  for (int j = 0; j < c; ++j) {
-    double* cj = Hs + (size_t)km[j] * RMAX;
-    double part = 0.0;
-    for (int i = j + tid; i < R; i += 512) { const double x = cj[i]; part += x * x; }
-    part = warp_sum_d(part);
-    if (lane == 0) red[warp] = part;
-    __syncthreads();
-    if (tid == 0) {
-      double n2 = 0.0;
-      for (int w = 0; w < 16; ++w) n2 += red[w];
-      const double nrm = sqrt(n2);
-      const double x0 = cj[j];
-      const double alpha = x0 >= 0 ? -nrm : nrm;
-      const double v0 = x0 - alpha;
-      const double vtv = n2 - x0 * x0 + v0 * v0;
-      s_alpha = alpha;
-      s_beta = vtv > 0.0 ? 2.0 / vtv : 0.0;
-    }
-    __syncthreads();
-    const double alpha = s_alpha, beta = s_beta;
-    for (int i = j + tid; i < R; i += 512) qsm[i] = cj[i] - (i == j ? alpha : 0.0);
-    __syncthreads();
-    if (beta != 0.0) {
-      // each warp owns columns j+1+warp, j+1+warp+16, ... and (column index c) the residual vector
-      for (int k = j + 1 + warp; k <= c; k += 16) {
-        double* ck = (k < c) ? Hs + (size_t)km[k] * RMAX : rs;
-        double dt_ = 0.0;
-        for (int i = j + lane; i < R; i += 32) dt_ += qsm[i] * ck[i];
-        dt_ = warp_sum_d(dt_) * beta;
-        for (int i = j + lane; i < R; i += 32) ck[i] -= dt_ * qsm[i];
-      }
-    }
-    __syncthreads();
-    for (int i = j + tid; i < R; i += 512) cj[i] = (i == j) ? alpha : 0.0;
-    __syncthreads();
-  }
-  if (tid == 0) {
-    ic[I_R] = c;
-    if (v.be.stats) { atomicAdd(&v.be.stats[8], 1ull); atomicAdd(&v.be.stats[9], (unsigned long long)R * c * c); }
-  }
-}
-
-// ---- staged variant (LVB_EXPERIMENT=qr_lean): the same column-by-column Householder with 2 block barriers per column
-// instead of 5.  The warp that updates column j+1 also leaves its squared norm below the diagonal and its diagonal entry in
-// shared memory, so iteration j+1 starts without a reduction pass; every thread derives (alpha, beta) from those two
-// numbers itself (no single-thread section); the finished column is zeroed while the reflector is copied out.
-__global__ void __launch_bounds__(512) be_qr_lean_kernel(BeView v) {
   extern __shared__ double qsm[];      // reflector [RMAX]
   __shared__ double red[16];
   __shared__ double s_n2, s_x0;
@@ -1385,75 +1330,16 @@ struct GemmArgs {
 };
 
 constexpr int GT = 64, GK = 16;
-__global__ void __launch_bounds__(256) be_gemm_kernel(GemmArgs g) {
-  __shared__ double As[GK][GT + 1], Bs[GK][GT + 1];
-  const int s = blockIdx.z;
-  const int* ic = g.icore + (size_t)s * BE_ICORE;
-  if (!ic[I_OK]) return;
-  const int M = ic[g.m_idx], N = ic[g.n_idx], K = ic[g.k_idx];
-  const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
-  if (m0 >= M || n0 >= N || K <= 0) return;
-  const double* A = g.A + (size_t)s * g.sA;
-  const double* B = g.B + (size_t)s * g.sB;
-  double* C = g.C + (size_t)s * g.sC;
-  const int* km = g.kmap ? g.kmap + (size_t)s * g.sK : nullptr;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  double acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (int k0 = 0; k0 < K; k0 += GK) {
-    for (int i = tid; i < GT * GK; i += 256) {
-      int mm, kk;
-      if (g.rsA == 1) { mm = i % GT; kk = i / GT; } else { kk = i % GK; mm = i / GK; }
-      const int gm = m0 + mm, gk = k0 + kk;
-      As[kk][mm] = (gm < M && gk < K) ? A[(size_t)gm * g.rsA + (size_t)(km ? km[gk] : gk) * g.csA] : 0.0;
-    }
-    for (int i = tid; i < GT * GK; i += 256) {
-      int nn, kk;
-      if (g.csB == 1) { nn = i % GT; kk = i / GT; } else { kk = i % GK; nn = i / GK; }
-      const int gn = n0 + nn, gk = k0 + kk;
-      Bs[kk][nn] = (gn < N && gk < K) ? B[(size_t)(km ? km[gk] : gk) * g.rsB + (size_t)gn * g.csB] : 0.0;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < GK; ++kk) {
-      double a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
-      if (gm < M && gn < N) {
-        double* c = C + (size_t)gm * g.rsC + (size_t)gn * g.csC;
-        double val = g.alpha * acc[i][j];
-        if (g.beta != 0.0) val += g.beta * *c;
-        if (gm == gn) val += g.diag_vec ? g.diag_vec[(size_t)s * g.sD + gm] : g.diag;
-        *c = val;
-      }
-    }
-}
-
-// ---- staged variant (LVB_EXPERIMENT=gemm_dmma): the same batched GEMM on the FP64 tensor path.  tcgen05 has no f64
-// kind, so this is warp-level `mma.sync.m8n8k4.f64` (SASS: DMMA): 8 warps tile a 64x64 block as 4 (M) x 2 (N), each warp
-// owns 2 x 4 fragments of 8x8; per 4-deep k step a thread issues 6 shared-memory loads for 8 DMMAs (64 FMAs) where the
-// FMA kernel needs 8 loads for 16.  Operand staging, bounds handling and the epilogue are the FMA kernel's.
+// The dense contractions of the update (T = H P, S = T H^T, P -= Y^T Y) on the FP64 tensor path.  tcgen05 has no f64 kind, so
+// this is warp-level `mma.sync.m8n8k4.f64` (SASS: DMMA): 8 warps tile a 64x64 block as 4 (M) x 2 (N), each warp owns 2 x 4
+// fragments of 8x8; per 4-deep k step a thread issues 6 shared-memory loads for 8 DMMAs (64 FMAs).  (A scalar-FMA version with
+// 4x4 register tiles needed 8 loads per 16 FMAs and measured 10.4 us vs 9.1 us per launch, round 2.)
 constexpr int GTP = GT + 4;      // 68: (k % 4) * 68 + (m % 8) hits 16 distinct 8-byte banks per half warp
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
-__global__ void __launch_bounds__(256) be_gemm_dmma_kernel(GemmArgs g) {
+__global__ void __launch_bounds__(256) be_gemm_kernel(GemmArgs g) {
   __shared__ double As[GK][GTP], Bs[GK][GTP];
   const int s = blockIdx.z;
   const int* ic = g.icore + (size_t)s * BE_ICORE;
@@ -1573,91 +1459,6 @@ __global__ void __launch_bounds__(1024) be_chol_kernel(BeView v) {
 #undef LP
 }
 
-// ---- staged variant (LVB_EXPERIMENT=chol_blocked): right-looking BLOCKED Cholesky, panels of CH_NB columns.
-// Per panel: the CH_NB x CH_NB diagonal block is factored by one thread, every row below solves its CH_NB entries against
-// it (one thread per row, no barrier inside), and the trailing lower triangle receives ONE rank-CH_NB update
-// (CH_NB FMAs per shared-memory read-modify-write instead of 1) - 3 block barriers per CH_NB columns instead of 3 per
-// column.  Same factor as be_chol_kernel up to rounding (different summation order).
-constexpr int CH_NB = 8;
-__global__ void __launch_bounds__(512) be_chol_blocked_kernel(BeView v) {
-  extern __shared__ double csm[];   // packed lower triangle + z [Dmax] + panel [CH_NB][Dmax]
-  __shared__ double s_L11[CH_NB][CH_NB];
-  __shared__ int s_bad;
-  const int s = blockIdx.x, tid = threadIdx.x;
-  int* ic = icore_of(v, s);
-  if (!ic[I_OK]) return;
-  const int r = ic[I_R];
-  if (r <= 0 || r > v.be.Dmax) return;
-  const int LD = v.be.LDS, Dm = v.be.Dmax;
-  double* S = v.be.Sm + (size_t)s * LD * LD;
-  double* Lp = csm;
-  double* z = csm + (size_t)Dm * (Dm + 1) / 2;
-  double* Pn = z + Dm;                                 // Pn[k * Dm + row]
-#define LP(i, j) Lp[(size_t)(i) * ((i) + 1) / 2 + (j)]
-  for (int e = tid; e < r * r; e += 512) { const int i = e / r, j = e - i * r; if (j <= i) LP(i, j) = S[(size_t)i * LD + j]; }
-  if (tid == 0) s_bad = 0;
-  __syncthreads();
-  for (int j0 = 0; j0 < r; j0 += CH_NB) {
-    const int nb = min(CH_NB, r - j0);
-    if (tid == 0) {                                    // diagonal block; a short last panel is padded with the identity
-      for (int a = 0; a < CH_NB; ++a)
-        for (int b2 = 0; b2 < CH_NB; ++b2) s_L11[a][b2] = (a == b2) ? 1.0 : 0.0;
-      for (int a = 0; a < nb; ++a) {
-        for (int b2 = 0; b2 <= a; ++b2) {
-          double x = LP(j0 + a, j0 + b2);
-          for (int k = 0; k < b2; ++k) x -= s_L11[a][k] * s_L11[b2][k];
-          if (a == b2) x = sqrt(x); else x /= s_L11[b2][b2];
-          s_L11[a][b2] = x;
-          LP(j0 + a, j0 + b2) = x;
-        }
-      }
-    }
-    __syncthreads();
-    // rows below the block: x L11^T = a  (forward substitution over the panel columns), kept in Pn for the update
-    for (int i = j0 + nb + tid; i < r; i += 512) {
-      double x[CH_NB];
-#pragma unroll
-      for (int k = 0; k < CH_NB; ++k) {
-        double a = (k < nb) ? LP(i, j0 + k) : 0.0;
-#pragma unroll
-        for (int m = 0; m < k; ++m) a -= x[m] * s_L11[k][m];
-        a /= s_L11[k][k];
-        x[k] = a;
-        if (k < nb) LP(i, j0 + k) = a;
-        Pn[k * Dm + i] = a;
-      }
-    }
-    __syncthreads();
-    // trailing update: rows a over the warps, columns b in [j0+nb, a] over the lanes (padded panel columns hold zeros)
-    for (int a = j0 + nb + (tid >> 5); a < r; a += 16) {
-      double pa[CH_NB];
-#pragma unroll
-      for (int k = 0; k < CH_NB; ++k) pa[k] = Pn[k * Dm + a];
-      double* row = &LP(a, 0);
-      for (int b2 = j0 + nb + (tid & 31); b2 <= a; b2 += 32) {
-        double acc = row[b2];
-#pragma unroll
-        for (int k = 0; k < CH_NB; ++k) acc -= pa[k] * Pn[k * Dm + b2];
-        row[b2] = acc;
-      }
-    }
-    __syncthreads();
-  }
-  for (int e = tid; e < r * r; e += 512) { const int i = e / r, j = e - i * r; if (j <= i) S[(size_t)i * LD + j] = LP(i, j); }
-  if (tid < 32) {                                      // z = L^-1 r, as in be_chol_kernel
-    const double* rs = v.be.rs + (size_t)s * v.be.RMAX;
-    for (int i = 0; i < r; ++i) {
-      double part = 0.0;
-      for (int q = tid; q < i; q += 32) part += LP(i, q) * z[q];
-      part = warp_sum_d(part);
-      if (tid == 0) z[i] = (rs[i] - part) / LP(i, i);
-      __syncwarp();
-    }
-    double* zg = v.be.zvec + (size_t)s * LD;
-    for (int i = tid; i < r; i += 32) zg[i] = z[i];
-  }
-#undef LP
-}
 
 // global-memory variant for windows whose packed S does not fit in shared memory (sw_size > ~33)
 __global__ void __launch_bounds__(512) be_chol_gmem_kernel(BeView v, int min_r) {
@@ -1758,78 +1559,6 @@ __global__ void __launch_bounds__(64) be_trsm_kernel(BeView v) {
   }
 }
 
-// ---- staged variant (LVB_EXPERIMENT=trsm_wide): Y = L^-1 T with 256 threads per 64 columns.  The 32-step dependent
-// solve of a diagonal block still runs on one thread per column, but the trailing updates - 97 % of the flops - are split
-// over four row groups (8 of the 32 tile rows each), so four times as many warps are in flight per column block.
-__global__ void __launch_bounds__(256) be_trsm_wide_kernel(BeView v) {
-  __shared__ double Lt[32][33];
-  __shared__ double Ys[32][64];
-  const int s = blockIdx.y, tid = threadIdx.x, tx = tid & 63, tg = tid >> 6;
-  int* ic = icore_of(v, s);
-  if (!ic[I_OK]) return;
-  const int r = ic[I_R], d = ic[I_DIM];
-  if (r <= 0) return;
-  const int c = blockIdx.x * 64 + tx;
-  if (blockIdx.x * 64 >= d) return;
-  const bool act = c < d;
-  const int LD = v.be.LD, LS = v.be.LDS;
-  const double* L = v.be.Sm + (size_t)s * LS * LS;
-  double* Tm = v.be.Tm + (size_t)s * v.be.RAWMAX * LD;
-  const int nb = (r + 31) / 32;
-  for (int ib = 0; ib < nb; ++ib) {
-    const int i0 = ib * 32;
-    for (int e = tid; e < 32 * 32; e += 256) {
-      const int a = e / 32, b = e % 32;
-      Lt[a][b] = (i0 + a < r && i0 + b < r) ? L[(size_t)(i0 + a) * LS + i0 + b] : ((a == b) ? 1.0 : 0.0);
-    }
-    __syncthreads();
-    if (tg == 0) {
-      double y[32];
-#pragma unroll
-      for (int a = 0; a < 32; ++a) y[a] = (act && i0 + a < r) ? Tm[(size_t)(i0 + a) * LD + c] : 0.0;
-#pragma unroll
-      for (int a = 0; a < 32; ++a) {
-        double x = y[a];
-#pragma unroll
-        for (int q = 0; q < 32; ++q) if (q < a) x -= Lt[a][q] * y[q];
-        y[a] = x / Lt[a][a];
-      }
-#pragma unroll
-      for (int a = 0; a < 32; ++a) {
-        if (act && i0 + a < r) Tm[(size_t)(i0 + a) * LD + c] = y[a];
-        Ys[a][tx] = y[a];
-      }
-    }
-    __syncthreads();
-    if (ib + 1 < nb) {
-      double ys[32];
-#pragma unroll
-      for (int q = 0; q < 32; ++q) ys[q] = Ys[q][tx];
-      for (int jb = ib + 1; jb < nb; ++jb) {
-        const int j0 = jb * 32;
-        __syncthreads();
-        for (int e = tid; e < 32 * 32; e += 256) {
-          const int a = e / 32, b = e % 32;
-          Lt[a][b] = (j0 + a < r && i0 + b < r) ? L[(size_t)(j0 + a) * LS + i0 + b] : 0.0;
-        }
-        __syncthreads();
-        if (act) {
-#pragma unroll
-          for (int a8 = 0; a8 < 8; ++a8) {
-            const int a = tg * 8 + a8;
-            if (j0 + a < r) {
-              double x = 0.0;
-#pragma unroll
-              for (int q = 0; q < 32; ++q) x += Lt[a][q] * ys[q];
-              Tm[(size_t)(j0 + a) * LD + c] -= x;
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-}
 
 // ====================================================================== dx = Y^T z, state correction (:1476-1534, :1692-1750)
 __global__ void __launch_bounds__(256) be_correct_kernel(BeView v) {
@@ -2533,24 +2262,7 @@ int be_alloc(LvbHandle* h) {
   if (be->NFmax > 0) LVB_CUDA(cudaFuncSetAttribute(be_slam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 64 * be->LD)));
   const size_t chol_bytes = sizeof(double) * ((size_t)be->Dmax * (be->Dmax + 1) / 2 + 2 * be->Dmax);
   if (chol_bytes <= 227 * 1024) LVB_CUDA(cudaFuncSetAttribute(be_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_bytes));
-  if (const char* ex = getenv("LVB_EXPERIMENT")) {             // staged kernel variants: exact comma-separated tokens
-    std::string tok;
-    for (const char* q = ex;; ++q) {
-      if (*q == ',' || *q == '\0') {
-        if (tok == "chol_blocked") h->experiments |= LVB_EXP_CHOL_BLOCKED;
-        else if (tok == "qr_lean") h->experiments |= LVB_EXP_QR_LEAN;
-        else if (tok == "gemm_dmma") h->experiments |= LVB_EXP_GEMM_DMMA;
-        else if (tok == "graph") h->experiments |= LVB_EXP_GRAPH;
-        else if (tok == "trsm_wide") h->experiments |= LVB_EXP_TRSM_WIDE;
-        else if (!tok.empty()) return lvb_set_err(LVB_E_CONFIG, "LVB_EXPERIMENT: unknown variant '%s'", tok.c_str());
-        tok.clear();
-        if (*q == '\0') break;
-      } else if (*q != ' ') tok.push_back(*q);
-    }
-  }
-  const size_t cholb_bytes = chol_bytes + sizeof(double) * (size_t)(CH_NB - 1) * be->Dmax;
-  if ((h->experiments & LVB_EXP_CHOL_BLOCKED) && cholb_bytes <= 227 * 1024)
-    LVB_CUDA(cudaFuncSetAttribute(be_chol_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cholb_bytes));
+  h->use_graph = getenv("LVB_NO_GRAPH") ? 0 : 1;          // one CUDA graph launch per step (lvb_step_graph); the env switch is for debugging
   return LVB_OK;
 }
 
@@ -2565,12 +2277,6 @@ void be_free(LvbHandle* h) {
 
 static int launch_gemm(LvbHandle* h, const GemmArgs& g, int max_m, int max_n) {
   LvbBackEnd* be = h->be;
-  if (h->experiments & LVB_EXP_GEMM_DMMA) {
-    LVB_PROF(h, "be_gemm_dmma_kernel");
-    be_gemm_dmma_kernel<<<dim3((max_n + GT - 1) / GT, (max_m + GT - 1) / GT, be->S), 256, 0, h->stream>>>(g);
-    LVB_LAUNCH_CHECK(h);
-    return LVB_OK;
-  }
   LVB_PROF(h, "be_gemm_kernel");
   be_gemm_kernel<<<dim3((max_n + GT - 1) / GT, (max_m + GT - 1) / GT, be->S), 256, 0, h->stream>>>(g);
   LVB_LAUNCH_CHECK(h);
@@ -2589,12 +2295,6 @@ static int be_colscan(LvbHandle* h, BeView& v, int rows_idx) {
 
 static int be_qr(LvbHandle* h, BeView& v) {
   RC(be_colscan(h, v, I_ROWS));
-  if (h->experiments & LVB_EXP_QR_LEAN) {
-    LVB_PROF(h, "be_qr_lean_kernel");
-    be_qr_lean_kernel<<<h->be->S, 512, sizeof(double) * h->be->RMAX, h->stream>>>(v);
-    LVB_LAUNCH_CHECK(h);
-    return LVB_OK;
-  }
   LVB_PROF(h, "be_qr_kernel");
   be_qr_kernel<<<h->be->S, 512, sizeof(double) * h->be->RMAX, h->stream>>>(v);
   LVB_LAUNCH_CHECK(h);
@@ -2627,13 +2327,7 @@ static int be_update(LvbHandle* h, BeView& v, bool zupt_rows = false, bool resca
   g.diag_vec = nullptr;
   const size_t chol_bytes = sizeof(double) * ((size_t)be->Dmax * (be->Dmax + 1) / 2 + 2 * be->Dmax);
   const bool smem_ok = chol_bytes <= 227 * 1024;
-  const size_t cholb_bytes = chol_bytes + sizeof(double) * (size_t)(CH_NB - 1) * be->Dmax;
-  if (smem_ok && (h->experiments & LVB_EXP_CHOL_BLOCKED) && cholb_bytes <= 227 * 1024) {
-    LVB_PROF(h, "be_chol_blocked_kernel");
-    be_chol_blocked_kernel<<<be->S, 512, cholb_bytes, st>>>(v);
-    LVB_LAUNCH_CHECK(h);
-    DBG("be_chol_blocked_kernel");
-  } else if (smem_ok) {
+  if (smem_ok) {
     LVB_PROF(h, "be_chol_kernel");
     be_chol_kernel<<<be->S, 1024, chol_bytes, st>>>(v);
     LVB_LAUNCH_CHECK(h);
@@ -2645,14 +2339,8 @@ static int be_update(LvbHandle* h, BeView& v, bool zupt_rows = false, bool resca
     LVB_LAUNCH_CHECK(h);
     DBG("be_chol_gmem_kernel");
   }
-  BeView vt = v;
-  if (h->experiments & LVB_EXP_TRSM_WIDE) {
-    LVB_PROF(h, "be_trsm_wide_kernel");
-    be_trsm_wide_kernel<<<dim3((be->Dmax + 63) / 64, be->S), 256, 0, st>>>(vt);
-  } else {
   LVB_PROF(h, "be_trsm_kernel");
-  be_trsm_kernel<<<dim3((be->Dmax + 63) / 64, be->S), 64, 0, st>>>(vt);
-  }
+  be_trsm_kernel<<<dim3((be->Dmax + 63) / 64, be->S), 64, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
   DBG("be_trsm_kernel");
   LVB_PROF(h, "be_correct_kernel");
@@ -2922,7 +2610,7 @@ int be_process(LvbHandle* h, const LvbFeature* d_msg, const int* d_msg_n, const 
   return be_finish(h, imu, n_imu, imu_stride, ok_out);
 }
 
-// ---- LVB_EXPERIMENT=graph: ONE graph launch per step.  The enqueue halves of processImage / processFeatures are captured
+// ---- ONE graph launch per step (default; LVB_NO_GRAPH=1 falls back to stream launches).  The enqueue halves of processImage / processFeatures are captured
 // once per pyramid parity and replayed; host preparation (pinned staging of IMU, homographies, stamps; the image copy into
 // the fixed staging batch) and the read-back stay outside.  Not used while the profiler or LVB_DEBUG_NAN is on (both
 // synchronise between launches).
@@ -2980,7 +2668,7 @@ extern "C" int lvb_step(LvbHandle* h, const uint8_t* images, int images_on_devic
                         int* n_imu, int imu_stride, uint8_t* published) {
   if (!h || !images || !t_img || !imu || !n_imu) return lvb_set_err(LVB_E_ARG, "lvb_step: null argument");
   LVB_CUDA(cudaSetDevice(h->device));
-  if ((h->experiments & LVB_EXP_GRAPH) && !h->prof.on && !getenv("LVB_DEBUG_NAN"))
+  if (h->use_graph && !h->prof.on && !getenv("LVB_DEBUG_NAN"))
     return lvb_step_graph(h, images, images_on_device, t_img, imu, n_imu, imu_stride, published);
   RC(fe_process(h, images, images_on_device, t_img, imu, n_imu, imu_stride));
   LvbFrontEnd& fe = h->fe;

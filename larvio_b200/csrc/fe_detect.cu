@@ -28,17 +28,27 @@ __device__ __forceinline__ int float_order_key(float v) {
   return b >= 0 ? b : (b ^ 0x7fffffff);
 }
 
-struct EigArgs {
+struct CornerArgs {
   const uint8_t* pyr; LvbPyramidLayout L;
   const uint8_t* mask;     // [S][H][W] or null
-  float* eig;              // [S][H][W]
+  float* eig;              // [S][H][W] or null: the response map is only written for the stage-level test entry point
   int* eig_max_key;        // [S] ordered-int key of the masked maximum
+  unsigned long long* cand; int* n_cand; int cap;
   const int* enable;       // [S] or null
 };
 
-__global__ void __launch_bounds__(256) mineig_kernel(EigArgs a) {
-  __shared__ uint8_t img[IH][IW + 4];
-  __shared__ float sxx[CH][CW], sxy[CH][CW], syy[CH][CW];
+// cornerMinEigenVal + the masked maximum + the 3x3 non-maximum test in ONE pass over the level (the image is read
+// once; the f32 response map of the two-kernel version - 1.4 MB per sequence written and re-read - no longer exists).
+// A tile computes the response on its 32x16 outputs plus a one-pixel apron (neighbours of the non-maximum test), from the
+// covariance products on a 36x20 grid and the image on 38x22.  The 3x3 box is separable: row sums, then column sums, in
+// double like OpenCV's RowSum<float,double> / ColumnSum<double,float>, 12 DADD per pixel instead of 24.
+// The global threshold 0.01 * max is not known yet, so a tile keeps every local maximum above 0.01 * (its own masked
+// maximum) - a lower bound of the final threshold - and select_kernel applies the exact one.
+__global__ void __launch_bounds__(256) corner_kernel(CornerArgs a) {
+  __shared__ uint8_t img[IH + 2][IW + 6];                 // 22 x 44 (38 used)
+  __shared__ float sxx[CH + 2][CW + 2], sxy[CH + 2][CW + 2], syy[CH + 2][CW + 2];      // products on the 36 x 20 grid
+  __shared__ double hxx[CH + 2][CW], hxy[CH + 2][CW], hyy[CH + 2][CW];                // row sums on 34 x 20
+  __shared__ float se[CH][CW];                            // response on 34 x 18
   __shared__ int blk_max;
   const int s = blockIdx.z;
   if (a.enable && !a.enable[s]) return;
@@ -47,11 +57,12 @@ __global__ void __launch_bounds__(256) mineig_kernel(EigArgs a) {
   const int bx = blockIdx.x * TW, by = blockIdx.y * TH;
   const uint8_t* org = lvb_level_origin(a.pyr, a.L, s, 0);
   const int tid = threadIdx.x;
+  constexpr int PW = CW + 2, PH = CH + 2;                 // product grid 36 x 20: cell (cx, cy) <-> pixel (bx - 2 + cx, by - 2 + cy)
+  constexpr int LW = IW + 2, LH = IH + 2;                 // image tile 38 x 22: (tx, ty) <-> pixel (bx - 3 + tx, by - 3 + ty)
   if (tid == 0) blk_max = INT_MIN;
-  // image tile covers [bx-2, bx+TW+2) x [by-2, by+TH+2) of the padded (REFLECT_101) level
-  for (int i = tid; i < IH * IW; i += 256) {
-    const int ty = i / IW, tx = i - ty * IW;
-    int gx = bx - 2 + tx, gy = by - 2 + ty;
+  for (int i = tid; i < LH * LW; i += 256) {
+    const int ty = i / LW, tx = i - ty * LW;
+    int gx = bx - 3 + tx, gy = by - 3 + ty;
     gx = min(gx, W + LVB_PAD - 1); gy = min(gy, H + LVB_PAD - 1);
     img[ty][tx] = org[(ptrdiff_t)gy * lv.pitch + gx];
   }
@@ -59,12 +70,11 @@ __global__ void __launch_bounds__(256) mineig_kernel(EigArgs a) {
   const double scale = 1.0 / (4.0 * 3.0 * 255.0);
   const float k0 = (float)(2.0 * scale), k1 = (float)scale;
   const int tail_x = W & ~31;
-  // cov grid cell (cx,cy) <-> image pixel (bx-1+cx, by-1+cy), reflected into the image
-  for (int i = tid; i < CH * CW; i += 256) {
-    const int cy = i / CW, cx = i - cy * CW;
-    if (bx - 1 + cx > W || by - 1 + cy > H) { sxx[cy][cx] = 0.f; sxy[cy][cx] = 0.f; syy[cy][cx] = 0.f; continue; }
-    const int gx = reflect101(bx - 1 + cx, W), gy = reflect101(by - 1 + cy, H);
-    const int tx = gx - (bx - 2), ty = gy - (by - 2);   // position inside img[][]
+  for (int i = tid; i < PH * PW; i += 256) {
+    const int cy = i / PW, cx = i - cy * PW;
+    if (bx - 2 + cx > W || by - 2 + cy > H) { sxx[cy][cx] = 0.f; sxy[cy][cx] = 0.f; syy[cy][cx] = 0.f; continue; }
+    const int gx = reflect101(bx - 2 + cx, W), gy = reflect101(by - 2 + cy, H);   // the box filter's REFLECT_101 is on the products
+    const int tx = gx - (bx - 3), ty = gy - (by - 3);     // position inside img[][]
     // Dx: row diff then symmetric column filter with FMA
     const float d0 = (float)((int)img[ty - 1][tx + 1] - (int)img[ty - 1][tx - 1]);
     const float d1 = (float)((int)img[ty][tx + 1] - (int)img[ty][tx - 1]);
@@ -89,71 +99,75 @@ __global__ void __launch_bounds__(256) mineig_kernel(EigArgs a) {
     syy[cy][cx] = __fmul_rn(Dy, Dy);
   }
   __syncthreads();
-  int my_key = INT_MIN;
-  for (int i = tid; i < TH * TW; i += 256) {
-    const int oy = i / TW, ox = i - oy * TW;
-    const int gx = bx + ox, gy = by + oy;
-    if (gx >= W || gy >= H) continue;
-    double xx = 0, xy = 0, yy = 0;
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        xx += (double)sxx[oy + dy][ox + dx];
-        xy += (double)sxy[oy + dy][ox + dx];
-        yy += (double)syy[oy + dy][ox + dx];
-      }
+  // row sums: h[cy][ex] = p[cy][ex] + p[cy][ex + 1] + p[cy][ex + 2]   (ex over the 34 response columns)
+  for (int i = tid; i < PH * CW; i += 256) {
+    const int cy = i / CW, ex = i - cy * CW;
+    hxx[cy][ex] = ((double)sxx[cy][ex] + (double)sxx[cy][ex + 1]) + (double)sxx[cy][ex + 2];
+    hxy[cy][ex] = ((double)sxy[cy][ex] + (double)sxy[cy][ex + 1]) + (double)sxy[cy][ex + 2];
+    hyy[cy][ex] = ((double)syy[cy][ex] + (double)syy[cy][ex + 1]) + (double)syy[cy][ex + 2];
+  }
+  __syncthreads();
+  // column sums + min eigenvalue on the 34 x 18 response grid: cell (ex, ey) <-> pixel (bx - 1 + ex, by - 1 + ey)
+  for (int i = tid; i < CH * CW; i += 256) {
+    const int ey = i / CW, ex = i - ey * CW;
+    const double xx = (hxx[ey][ex] + hxx[ey + 1][ex]) + hxx[ey + 2][ex];
+    const double xy = (hxy[ey][ex] + hxy[ey + 1][ex]) + hxy[ey + 2][ex];
+    const double yy = (hyy[ey][ex] + hyy[ey + 1][ex]) + hyy[ey + 2][ex];
     const float fa = __fmul_rn((float)xx, 0.5f), fb = (float)xy, fc = __fmul_rn((float)yy, 0.5f);
     const float dif = __fsub_rn(fa, fc);
-    const float e = __fsub_rn(__fadd_rn(fa, fc), __fsqrt_rn(__fadd_rn(__fmul_rn(dif, dif), __fmul_rn(fb, fb))));
-    const size_t gi = (size_t)s * W * H + (size_t)gy * W + gx;
-    a.eig[gi] = e;
-    if (!a.mask || a.mask[gi]) my_key = max(my_key, float_order_key(e));
+    se[ey][ex] = __fsub_rn(__fadd_rn(fa, fc), __fsqrt_rn(__fadd_rn(__fmul_rn(dif, dif), __fmul_rn(fb, fb))));
+  }
+  __syncthreads();
+  // masked maximum of this tile
+  float myv[2]; bool mym[2]; int my_key = INT_MIN;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = tid + 256 * r;
+    const int oy = i / TW, ox = i - oy * TW;
+    const int gx = bx + ox, gy = by + oy;
+    myv[r] = 0.f; mym[r] = false;
+    if (gx < W && gy < H) {
+      const size_t gi = (size_t)s * W * H + (size_t)gy * W + gx;
+      const float e = se[oy + 1][ox + 1];
+      myv[r] = e;
+      if (a.eig) a.eig[gi] = e;
+      mym[r] = !a.mask || a.mask[gi];
+      if (mym[r]) my_key = max(my_key, float_order_key(e));
+    }
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) my_key = max(my_key, __shfl_xor_sync(0xffffffffu, my_key, o));
   if ((tid & 31) == 0) atomicMax(&blk_max, my_key);
   __syncthreads();
-  if (tid == 0 && blk_max != INT_MIN) atomicMax(&a.eig_max_key[s], blk_max);
-}
-
-// ---------------------------------------------------------------- threshold + 3x3 NMS -> candidates
-struct CandArgs {
-  const float* eig; const uint8_t* mask; const int* eig_max_key;
-  unsigned long long* cand; int* n_cand; int cap; int W, H;
-  const int* enable;
-};
-
-__global__ void __launch_bounds__(256) candidates_kernel(CandArgs a) {
-  const int s = blockIdx.z;
-  if (a.enable && !a.enable[s]) return;
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  const int W = a.W, H = a.H;
-  bool is = false;
-  float v = 0.f;
-  const int key = a.eig_max_key[s];
-  if (key != INT_MIN && x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
-    const float maxv = __int_as_float(key >= 0 ? key : (key ^ 0x7fffffff));
-    const float thr = (float)((double)maxv * 0.01);
-    const float* e = a.eig + (size_t)s * W * H + (size_t)y * W + x;
-    v = e[0];
-    if (v > thr && (!a.mask || a.mask[(size_t)s * W * H + (size_t)y * W + x])) {
-      is = v >= e[-1] && v >= e[1] && v >= e[-W - 1] && v >= e[-W] && v >= e[-W + 1] &&
-           v >= e[W - 1] && v >= e[W] && v >= e[W + 1];
+  const int key = blk_max;
+  if (key == INT_MIN) return;                             // nothing unmasked in this tile: no maximum, no candidate
+  if (tid == 0) atomicMax(&a.eig_max_key[s], key);
+  const float tile_max = __int_as_float(key >= 0 ? key : (key ^ 0x7fffffff));
+  const float thr_lo = (float)((double)tile_max * 0.01);  // <= the final threshold (float)(0.01 * global max): same monotone rounding
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = tid + 256 * r;
+    const int oy = i / TW, ox = i - oy * TW;
+    const int gx = bx + ox, gy = by + oy;
+    bool is = false;
+    const float v = myv[r];
+    if (mym[r] && gx >= 1 && gx < W - 1 && gy >= 1 && gy < H - 1 && v > thr_lo && v > 0.f) {
+      const int ey = oy + 1, ex = ox + 1;
+      is = v >= se[ey][ex - 1] && v >= se[ey][ex + 1] && v >= se[ey - 1][ex - 1] && v >= se[ey - 1][ex] && v >= se[ey - 1][ex + 1] &&
+           v >= se[ey + 1][ex - 1] && v >= se[ey + 1][ex] && v >= se[ey + 1][ex + 1];
     }
-  }
-  // warp-aggregated append
-  const unsigned m = __ballot_sync(0xffffffffu, is);
-  if (m) {
-    const int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == __ffs(m) - 1) base = atomicAdd(&a.n_cand[s], __popc(m));
-    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (is) {
-      const int pos = base + __popc(m & ((1u << lane) - 1));
-      if (pos < a.cap)
-        a.cand[(size_t)s * a.cap + pos] = ((unsigned long long)(unsigned)__float_as_int(v) << 32) | (unsigned)(y * W + x);
+    // warp-aggregated append
+    const unsigned m = __ballot_sync(0xffffffffu, is);
+    if (m) {
+      const int lane = tid & 31;
+      int base = 0;
+      if (lane == __ffs(m) - 1) base = atomicAdd(&a.n_cand[s], __popc(m));
+      base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+      if (is) {
+        const int pos = base + __popc(m & ((1u << lane) - 1));
+        if (pos < a.cap)
+          a.cand[(size_t)s * a.cap + pos] = ((unsigned long long)(unsigned)__float_as_int(v) << 32) | (unsigned)(gy * W + gx);
+      }
     }
   }
 }
@@ -165,6 +179,7 @@ struct SelArgs {
   const int* want; int W; int min_dist; int stride;
   float2* out; int* out_n; int* overflow;
   const int* enable;
+  const int* eig_max_key;   // [S]: candidates are a superset (tile-local thresholds); the exact test v > (float)(0.01 * max) happens here
 };
 
 __global__ void __launch_bounds__(1024) select_kernel(SelArgs a) {
@@ -184,13 +199,23 @@ __global__ void __launch_bounds__(1024) select_kernel(SelArgs a) {
   __syncthreads();
   if (want <= 0 || n <= 0) { if (tid == 0) a.out_n[s] = 0; return; }
   const int md2 = a.min_dist * a.min_dist;
+  // v > thr for positive floats <=> value bits > thr bits <=> key >= (thr bits + 1) << 32
+  unsigned long long lowk = 0ull;
+  {
+    const int key = a.eig_max_key[s];
+    if (key == INT_MIN) { if (tid == 0) a.out_n[s] = 0; return; }
+    const float maxv = __int_as_float(key >= 0 ? key : (key ^ 0x7fffffff));
+    const float thr = (float)((double)maxv * 0.01);
+    if (!(thr >= 0.f)) { if (tid == 0) a.out_n[s] = 0; return; }       // no positive response anywhere: no corner
+    lowk = ((unsigned long long)(unsigned)__float_as_int(thr) + 1ull) << 32;
+  }
   while (true) {
     const unsigned long long upper = s_upper;
     // --- bisection on the value bits: smallest cut with count{cut<<32 <= k < upper} <= CHUNK
     unsigned long long lo = 0ull, hi = (upper >> 32) + 1ull;   // count(k >= hi<<32, k < upper) == 0
     for (int it = 0; it < 40; ++it) {
       const unsigned long long mid = (it == 0) ? 0ull : lo + ((hi - lo) >> 1);
-      const unsigned long long midk = mid << 32;
+      const unsigned long long midk = max(mid << 32, lowk);
       int cnt = 0;
       for (int i = tid; i < n; i += 1024) { const unsigned long long k = c[i]; cnt += (k >= midk && k < upper); }
 #pragma unroll
@@ -213,7 +238,7 @@ __global__ void __launch_bounds__(1024) select_kernel(SelArgs a) {
       if (total <= CHUNK) hi = mid; else lo = mid;
       if (hi - lo <= 1) break;
     }
-    const unsigned long long cut = hi << 32;
+    const unsigned long long cut = max(hi << 32, lowk);
     // --- gather chunk
     if (tid == 0) s_cnt = 0;
     for (int i = tid; i < CHUNK; i += 1024) keys[i] = 0ull;
@@ -269,7 +294,7 @@ __global__ void __launch_bounds__(1024) select_kernel(SelArgs a) {
       }
       if (tid == 0) {
         s_acc = acc;
-        const bool exhausted = (cut == 0ull);
+        const bool exhausted = (cut <= lowk);
         s_done = (acc >= want) || exhausted || m == 0;
         s_upper = cut;
       }
@@ -321,7 +346,7 @@ __global__ void reset_detect_kernel(int* eig_max_key, int* n_cand, int n) {
 //   use_mask != 0: build the mask from (mask_pts, mask_n) first.  enable: per-sequence gate or null.
 int fe_detect_launch(LvbHandle* h, const uint8_t* pyr, int n_seq, const int* enable, int use_mask,
                      const uint8_t* ext_mask, const float2* mask_pts, const int* mask_n, const int* want,
-                     float2* out, int* out_n) {
+                     float2* out, int* out_n, float* eig_out) {
   LvbFrontEnd& fe = h->fe;
   cudaStream_t st = h->stream;
   const int W = fe.W, H = fe.H;
@@ -339,17 +364,13 @@ int fe_detect_launch(LvbHandle* h, const uint8_t* pyr, int n_seq, const int* ena
     LVB_LAUNCH_CHECK(h);
     mask = fe.mask;
   }
-  EigArgs ea; ea.pyr = pyr; ea.L = fe.L; ea.mask = mask; ea.eig = fe.eig; ea.eig_max_key = fe.eig_max; ea.enable = enable;
-  LVB_PROF(h, "mineig_kernel");
-  mineig_kernel<<<dim3((W + TW - 1) / TW, (H + TH - 1) / TH, n_seq), 256, 0, st>>>(ea);
-  LVB_LAUNCH_CHECK(h);
-  CandArgs ca; ca.eig = fe.eig; ca.mask = mask; ca.eig_max_key = fe.eig_max; ca.cand = fe.cand; ca.n_cand = fe.n_cand;
-  ca.cap = fe.cand_cap; ca.W = W; ca.H = H; ca.enable = enable;
-  LVB_PROF(h, "candidates_kernel");
-  candidates_kernel<<<dim3((W + 31) / 32, (H + 7) / 8, n_seq), 256, 0, st>>>(ca);
+  CornerArgs ca; ca.pyr = pyr; ca.L = fe.L; ca.mask = mask; ca.eig = eig_out; ca.eig_max_key = fe.eig_max; ca.cand = fe.cand; ca.n_cand = fe.n_cand;
+  ca.cap = fe.cand_cap; ca.enable = enable;
+  LVB_PROF(h, "corner_kernel");
+  corner_kernel<<<dim3((W + TW - 1) / TW, (H + TH - 1) / TH, n_seq), 256, 0, st>>>(ca);
   LVB_LAUNCH_CHECK(h);
   SelArgs sa; sa.cand = fe.cand; sa.n_cand = fe.n_cand; sa.cap = fe.cand_cap; sa.want = want; sa.W = W;
-  sa.min_dist = h->cfg.min_distance; sa.stride = fe.N; sa.out = out; sa.out_n = out_n; sa.overflow = fe.overflow; sa.enable = enable;
+  sa.min_dist = h->cfg.min_distance; sa.stride = fe.N; sa.out = out; sa.out_n = out_n; sa.overflow = fe.overflow; sa.enable = enable; sa.eig_max_key = fe.eig_max;
   LVB_PROF(h, "select_kernel");
   select_kernel<<<n_seq, 1024, 0, st>>>(sa);
   LVB_LAUNCH_CHECK(h);

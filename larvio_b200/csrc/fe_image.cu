@@ -74,7 +74,22 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
   lut[((size_t)s * 64 + tile) * 256 + tid] = (uint8_t)r;
 }
 
-// ---------------------------------------------------------------- CLAHE apply -> L0 interior
+// REFLECT_101 pad written by the producer of a level: pixel (x, y) of a w x h level is also the value of its mirror images
+// -x, 2(w-1)-x (and the same in y) wherever those fall inside the LVB_PAD-wide pad (w, h > LVB_PAD + 1 at every level we build).
+__device__ __forceinline__ void store_pad_copies(uint8_t* org, int pitch, int w, int h, int x, int y, uint8_t v) {
+  int xs[2], ys[2], nx = 0, ny = 0;
+  if (x >= 1 && x <= LVB_PAD) xs[nx++] = -x;
+  if (x <= w - 2 && x >= w - 1 - LVB_PAD) xs[nx++] = 2 * (w - 1) - x;
+  if (y >= 1 && y <= LVB_PAD) ys[ny++] = -y;
+  if (y <= h - 2 && y >= h - 1 - LVB_PAD) ys[ny++] = 2 * (h - 1) - y;
+  for (int a = 0; a < nx; ++a) org[(ptrdiff_t)y * pitch + xs[a]] = v;
+  for (int b = 0; b < ny; ++b) {
+    org[(ptrdiff_t)ys[b] * pitch + x] = v;
+    for (int a = 0; a < nx; ++a) org[(ptrdiff_t)ys[b] * pitch + xs[a]] = v;
+  }
+}
+
+// ---------------------------------------------------------------- CLAHE apply -> L0 interior + its REFLECT_101 pad
 // each thread: 4 horizontally adjacent pixels.
 __global__ void __launch_bounds__(256) clahe_apply_kernel(const uint8_t* __restrict__ img, int W, int H,
                                                            const uint8_t* __restrict__ lut,
@@ -125,41 +140,11 @@ __global__ void __launch_bounds__(256) clahe_apply_kernel(const uint8_t* __restr
     }
   }
   *reinterpret_cast<uchar4*>(dst) = make_uchar4(out[0], out[1], out[2], out[3]);
-}
-
-// ---------------------------------------------------------------- REFLECT_101 pad fill
-__device__ __forceinline__ int reflect101(int p, int n) {
-  if (n == 1) return 0;
-  while (p < 0 || p >= n) {
-    if (p < 0) p = -p;
-    else p = 2 * n - 2 - p;
+  if (x0 <= LVB_PAD || x0 + 3 >= W - 1 - LVB_PAD || y <= LVB_PAD || y >= H - 1 - LVB_PAD) {     // border band: also fill the pad
+    uint8_t* org = lvb_level_origin(pyr, L, s, 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) store_pad_copies(org, L.lv[0].pitch, W, H, x0 + k, y, out[k]);
   }
-  return p;
-}
-
-// one thread per PAD pixel: indices 0..2*PAD*PW-1 are the top/bottom bands, the rest the left/right strips
-__global__ void pad_reflect_kernel(uint8_t* __restrict__ pyr, LvbPyramidLayout L, int level) {
-  const int s = blockIdx.y;
-  const LvbLevel lv = L.lv[level];
-  const int PW = lv.w + 2 * LVB_PAD;
-  const int band = LVB_PAD * PW;
-  const int total = 2 * band + lv.h * 2 * LVB_PAD;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  int x, y;
-  if (idx < 2 * band) {
-    const int r = idx / PW;
-    x = idx - r * PW - LVB_PAD;
-    y = (r < LVB_PAD) ? (r - LVB_PAD) : (lv.h + r - LVB_PAD);
-  } else {
-    const int rem = idx - 2 * band;
-    y = rem / (2 * LVB_PAD);
-    const int c = rem - y * 2 * LVB_PAD;
-    x = (c < LVB_PAD) ? (c - LVB_PAD) : (lv.w + c - LVB_PAD);
-  }
-  uint8_t* org = lvb_level_origin(pyr, L, s, level);
-  const int sx = reflect101(x, lv.w), sy = reflect101(y, lv.h);
-  org[(ptrdiff_t)y * lv.pitch + x] = org[(ptrdiff_t)sy * lv.pitch + sx];
 }
 
 // ---------------------------------------------------------------- pyrDown (5x5 binomial, (x+128)>>8)
@@ -195,6 +180,9 @@ __global__ void __launch_bounds__(256) pyrdown_kernel(uint8_t* __restrict__ pyr,
   uint8_t* dst = dorg + (ptrdiff_t)y * ld.pitch + x4;
   if (x4 + 3 < ld.w) *reinterpret_cast<uchar4*>(dst) = make_uchar4(o[0], o[1], o[2], o[3]);
   else for (int k = 0; k < 4 && x4 + k < ld.w; ++k) dst[k] = o[k];
+  if (x4 <= LVB_PAD || x4 + 3 >= ld.w - 1 - LVB_PAD || y <= LVB_PAD || y >= ld.h - 1 - LVB_PAD) {   // the destination level's pad
+    for (int k = 0; k < 4 && x4 + k < ld.w; ++k) store_pad_copies(dorg, ld.pitch, ld.w, ld.h, x4 + k, y, o[k]);
+  }
 }
 
 // ---------------------------------------------------------------- 7x7 sigma=2 fixed-point blur of L0
@@ -284,13 +272,8 @@ int fe_build_pyramid(LvbHandle* h, const uint8_t* d_images, int n, uint8_t* pyr,
     clahe_apply_kernel<<<grd, blk, 0, st>>>(d_images, W, H, fe.lut, pyr, fe.L, h->cfg.flag_equalize);
     LVB_LAUNCH_CHECK(h);
   }
-  for (int l = 0; l < fe.L.n_levels; ++l) {
-    const LvbLevel& lv = fe.L.lv[l];
+  for (int l = 0; l < fe.L.n_levels; ++l) {       // every producer writes the REFLECT_101 pad of the level it produces
     dim3 blk(32, 8);
-    const int pad_total = 2 * LVB_PAD * (lv.w + 2 * LVB_PAD) + lv.h * 2 * LVB_PAD;
-    LVB_PROF(h, "pad_reflect_kernel");
-    pad_reflect_kernel<<<dim3((pad_total + 255) / 256, n), 256, 0, st>>>(pyr, fe.L, l);
-    LVB_LAUNCH_CHECK(h);
     if (l + 1 < fe.L.n_levels) {
       const LvbLevel& ld = fe.L.lv[l + 1];
       dim3 g2(((ld.w + 3) / 4 + 31) / 32, (ld.h + 7) / 8, n);

@@ -41,7 +41,7 @@ int fe_alloc(LvbHandle* h) {
     DA(t.desc, S * N * LVB_DESC_BYTES); DA(t.n, S);
     LvbChain& c = fe.ch[k];
     DA(c.perm, S * N); DA(c.n, S); DA(c.fail, S); DA(c.out, S * N); DA(c.status, S * N);
-    DA(c.slot_curr, S * N); DA(c.uprev, S * N); DA(c.ucurr, S * N); DA(c.desc, S * N * LVB_DESC_BYTES);
+    DA(c.slot_curr, S * N); DA(c.desc, S * N * LVB_DESC_BYTES);
   }
   DA(fe.new_pts, S * N); DA(fe.n_new, S);
   DA(fe.image_state, S); DA(fe.next_id, S);
@@ -49,8 +49,8 @@ int fe_alloc(LvbHandle* h) {
   DA(fe.Hmat, S * 9); DA(fe.active, S); DA(fe.t_img, S);
   DA(fe.do_first, S); DA(fe.do_second, S); DA(fe.do_other, S); DA(fe.do_publish, S); DA(fe.do_detect, S);
   DA(fe.want, S); DA(fe.mask_n, S);
-  DA(fe.eig, S * npx); DA(fe.mask, S * npx); DA(fe.eig_max, S);
-  fe.cand_cap = 32768;
+  DA(fe.mask, S * npx); DA(fe.eig_max, S);
+  fe.cand_cap = 65536;                 // local maxima above 1 % of their tile's maximum (a superset of the final candidates)
   DA(fe.cand, S * (size_t)fe.cand_cap); DA(fe.n_cand, S); DA(fe.overflow, 1); DA(fe.stats, 16);
   DA(fe.det_pts, S * N); DA(fe.det_n, S);
   DA(fe.msg, S * N); DA(fe.msg_n, S); DA(fe.has_msg, S); DA(fe.msg_t, S);
@@ -486,11 +486,10 @@ int fe_enqueue(LvbHandle* h, const uint8_t* d_images) {
   RC(fe_orb_launch(h, fe.pyr[cur], fe.blur[cur], S, N, fe.ch[1].slot_curr, fe.ch[1].perm, fe.ch[1].n, nullptr, nullptr, 0,
                    fe.ch[1].desc, fe.ch[1].status, nullptr));
   RC(run_compaction(h, 2));
-  // undistort to pixel coordinates + fundamental-matrix RANSAC
-  for (int c = 0; c < 2; ++c) {
-    RC(fe_undistort_launch(h, S, N, src[c], fe.ch[c].perm, fe.ch[c].n, fe.ch[c].uprev, 1));
-    RC(fe_undistort_launch(h, S, N, fe.ch[c].slot_curr, fe.ch[c].perm, fe.ch[c].n, fe.ch[c].ucurr, 1));
-    RC(fe_ransac_launch(h, S, N, fe.ch[c].uprev, fe.ch[c].ucurr, fe.ch[c].n, fe.ch[c].status, nullptr, fe.ch[c].fail));
+  // undistort to pixel coordinates + fundamental-matrix RANSAC: both chains in one launch, undistortion fused into its load
+  {
+    int* fail2[2] = {fe.ch[0].fail, fe.ch[1].fail};
+    RC(fe_ransac_launch2(h, S, N, src, cur2, perm2, n2, st2, fail2));
   }
   RC(run_compaction(h, 3));
   LVB_PROF(h, "finalize_kernel");

@@ -15,16 +15,24 @@
 // replays the sequential acceptance rule.  The 2-D null space comes from Gauss-Jordan with full
 // pivoting instead of an SVD: the pencil of F matrices and therefore every candidate model is the same.
 #include <float.h>
+#include <string.h>
 #include "lvb_internal.h"
+#include "fe_device.cuh"
 
 namespace {
 
 constexpr int BATCH = 32;      // hypotheses per round
 constexpr int MAXPTS = 512;
 
+struct RansacSet {             // one chain of point sets ([S] sets, blockIdx.y selects the chain)
+  const float2* p1; const float2* p2; const int* n;
+  const int* perm;             // with `undistort`: p1/p2 are raw pixel coordinates indexed through perm (image_processor.cpp:479-486)
+  uint8_t* mask; int* fail;    // fail[s]=1 -> chain already aborted, skip
+};
 struct RansacArgs {
-  const float2* p1; const float2* p2; const int* n; int stride;
-  uint8_t* mask; const int* enable; int* fail;   // fail[s]=1 -> chain already aborted, skip
+  RansacSet set[2];
+  int stride; const int* enable;
+  int undistort; LvbCamera cam;   // undistortPoints(P = K) fused into the load of the point sets
   double threshold, confidence; int max_iters;
   unsigned long long* stats;   // [14] += 1 per point set in the 8..13 regime (OpenCV's LMedS winner there is rounding noise)
 };
@@ -225,7 +233,8 @@ __device__ int update_num_iters(double p, double ep, int model_points, int max_i
   return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : (int)rint(num / denom);
 }
 
-__global__ void __launch_bounds__(256) ransac_kernel(RansacArgs a) {
+__global__ void __launch_bounds__(256) ransac_kernel(const __grid_constant__ RansacArgs aa) {
+  const RansacSet a = aa.set[blockIdx.y];
   __shared__ float2 sp1[MAXPTS], sp2[MAXPTS];
   __shared__ double sA[63 * 32];
   __shared__ double sF[BATCH][3][9];
@@ -239,27 +248,35 @@ __global__ void __launch_bounds__(256) ransac_kernel(RansacArgs a) {
   __shared__ double s_minmed;
   __shared__ unsigned long long s_rng;
   const int s = blockIdx.x;
-  if (a.enable && !a.enable[s]) return;
+  if (aa.enable && !aa.enable[s]) return;
   if (a.fail && a.fail[s]) return;
   const int n = min(a.n[s], MAXPTS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint8_t* mask = a.mask + (size_t)s * a.stride;
+  uint8_t* mask = a.mask + (size_t)s * aa.stride;
   if (n < 7) { for (int i = tid; i < n; i += 256) mask[i] = 1; return; }   // "no mask" => keep all
-  for (int i = tid; i < n; i += 256) { sp1[i] = a.p1[(size_t)s * a.stride + i]; sp2[i] = a.p2[(size_t)s * a.stride + i]; }
+  for (int i = tid; i < n; i += 256) {
+    if (aa.undistort) {
+      const int slot = a.perm[(size_t)s * aa.stride + i];
+      sp1[i] = lvb_undistort_point(aa.cam, a.p1[(size_t)s * aa.stride + slot], 1);
+      sp2[i] = lvb_undistort_point(aa.cam, a.p2[(size_t)s * aa.stride + slot], 1);
+    } else {
+      sp1[i] = a.p1[(size_t)s * aa.stride + i]; sp2[i] = a.p2[(size_t)s * aa.stride + i];
+    }
+  }
   __syncthreads();
   if (n == 7) { for (int i = tid; i < n; i += 256) mask[i] = 1; return; }
   const bool lmeds = n < 15;
-  if (tid == 0 && n <= 13 && a.stats) atomicAdd(&a.stats[14], 1ull);
+  if (tid == 0 && n <= 13 && aa.stats) atomicAdd(&aa.stats[14], 1ull);
   if (tid == 0) {
     s_ctl[0] = 0; s_ctl[1] = 0; s_ctl[3] = 0; s_ctl[6] = 0; s_ctl[7] = 0;
-    int niters = max(a.max_iters, 1);
-    if (lmeds) { niters = update_num_iters(a.confidence, 0.45, 7, a.max_iters); niters = max(niters, 3); }
+    int niters = max(aa.max_iters, 1);
+    if (lmeds) { niters = update_num_iters(aa.confidence, 0.45, 7, aa.max_iters); niters = max(niters, 3); }
     s_ctl[2] = niters;
     s_minmed = DBL_MAX;
     s_rng = 0xffffffffffffffffull;
   }
   __syncthreads();
-  const float thr2 = (float)(a.threshold * a.threshold);
+  const float thr2 = (float)(aa.threshold * aa.threshold);
   double bestF[9];
   for (int q = 0; q < 9; ++q) bestF[q] = 0;
 
@@ -335,7 +352,7 @@ __global__ void __launch_bounds__(256) ransac_kernel(RansacArgs a) {
             const int good = s_good[hb][m];
             if (good > max(max_good, 6)) {
               max_good = good; s_ctl[4] = hb; s_ctl[5] = m; s_ctl[6] = 1;
-              niters = update_num_iters(a.confidence, (double)(n - good) / n, 7, niters);
+              niters = update_num_iters(aa.confidence, (double)(n - good) / n, 7, niters);
             }
           } else {
             const double med = (double)s_med[hb][m];
@@ -379,10 +396,29 @@ __global__ void __launch_bounds__(256) ransac_kernel(RansacArgs a) {
 int fe_ransac_launch(LvbHandle* h, int n_seq, int stride, const float2* p1, const float2* p2, const int* n,
                      uint8_t* mask, const int* enable, int* fail) {
   RansacArgs a;
-  a.p1 = p1; a.p2 = p2; a.n = n; a.stride = stride; a.mask = mask; a.enable = enable; a.fail = fail;
+  memset(&a, 0, sizeof(a));
+  a.set[0].p1 = p1; a.set[0].p2 = p2; a.set[0].n = n; a.set[0].perm = nullptr; a.set[0].mask = mask; a.set[0].fail = fail;
+  a.stride = stride; a.enable = enable; a.undistort = 0;
   a.threshold = 1.0; a.confidence = 0.99; a.max_iters = 1000; a.stats = h->fe.stats;
   LVB_PROF(h, "ransac_kernel");
-  ransac_kernel<<<n_seq, 256, 0, h->stream>>>(a);
+  ransac_kernel<<<dim3(n_seq, 1), 256, 0, h->stream>>>(a);
+  LVB_LAUNCH_CHECK(h);
+  return LVB_OK;
+}
+
+// Both chains of a frame (tracked + new features) in ONE launch, undistortPoints(P = K) of the raw pixel pairs fused
+// into the load (image_processor.cpp:479-500, 736-757, 949-970): prev[c] / curr[c] are indexed by slot through perm[c].
+int fe_ransac_launch2(LvbHandle* h, int n_seq, int stride, const float2* const prev[2], const float2* const curr[2],
+                      int* const perm[2], int* const n[2], uint8_t* const mask[2], int* const fail[2]) {
+  RansacArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int c = 0; c < 2; ++c) {
+    a.set[c].p1 = prev[c]; a.set[c].p2 = curr[c]; a.set[c].n = n[c]; a.set[c].perm = perm[c]; a.set[c].mask = mask[c]; a.set[c].fail = fail[c];
+  }
+  a.stride = stride; a.enable = nullptr; a.undistort = 1; a.cam = lvb_camera(h->cfg);
+  a.threshold = 1.0; a.confidence = 0.99; a.max_iters = 1000; a.stats = h->fe.stats;
+  LVB_PROF(h, "ransac_kernel");
+  ransac_kernel<<<dim3(n_seq, 2), 256, 0, h->stream>>>(a);
   LVB_LAUNCH_CHECK(h);
   return LVB_OK;
 }

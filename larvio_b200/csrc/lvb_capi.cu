@@ -58,6 +58,8 @@ extern "C" int lvb_create(const LvbConfig* cfg, int n_seq, int device, LvbHandle
     return lvb_set_err(LVB_E_UNSUPPORTED, "image size %dx%d: CLAHE tiles need multiples of 8", cfg->width, cfg->height);
   if (cfg->pyramid_levels + 1 > LVB_MAX_LEVELS || cfg->pyramid_levels < 0)
     return lvb_set_err(LVB_E_UNSUPPORTED, "pyramid_levels %d", cfg->pyramid_levels);
+  if ((cfg->width >> cfg->pyramid_levels) <= LVB_PAD + 1 || (cfg->height >> cfg->pyramid_levels) <= LVB_PAD + 1)
+    return lvb_set_err(LVB_E_UNSUPPORTED, "image %dx%d with %d pyramid levels: the top level must exceed the %d-px pad", cfg->width, cfg->height, cfg->pyramid_levels, LVB_PAD);
   if (cfg->patch_size != 21) return lvb_set_err(LVB_E_UNSUPPORTED, "patch_size %d (LK kernel is specialised for 21)", cfg->patch_size);
   int ndev = 0;
   LVB_CUDA(cudaGetDeviceCount(&ndev));
@@ -261,7 +263,8 @@ extern "C" int lvbk_detect(LvbHandle* h, const uint8_t* images, const uint8_t* m
   int* d_want = tb.get<int>(n);
   float2* d_out = tb.get<float2>((size_t)n * fe.N);
   int* d_cnt = tb.get<int>(n);
-  if (!d_img || !d_pyr || !d_lut || !d_want || !d_out || !d_cnt || (masks && !d_mask)) return lvb_set_err(LVB_E_CUDA, "lvbk_detect: cudaMalloc failed");
+  float* d_eig = eig_map ? tb.get<float>(npx * n) : nullptr;
+  if (!d_img || !d_pyr || !d_lut || !d_want || !d_out || !d_cnt || (masks && !d_mask) || (eig_map && !d_eig)) return lvb_set_err(LVB_E_CUDA, "lvbk_detect: cudaMalloc failed");
   LVB_CUDA(cudaMemcpyAsync(d_img, images, npx * n, cudaMemcpyHostToDevice, h->stream));
   if (masks) LVB_CUDA(cudaMemcpyAsync(d_mask, masks, npx * n, cudaMemcpyHostToDevice, h->stream));
   LVB_CUDA(cudaMemcpyAsync(d_want, want, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -270,11 +273,11 @@ extern "C" int lvbk_detect(LvbHandle* h, const uint8_t* images, const uint8_t* m
   int rc = fe_build_pyramid(h, d_img, n, d_pyr, nullptr);
   h->cfg.flag_equalize = eq; fe.lut = saved;
   if (rc != LVB_OK) return rc;
-  rc = fe_detect_launch(h, d_pyr, n, nullptr, 0, d_mask, nullptr, nullptr, d_want, d_out, d_cnt);
+  rc = fe_detect_launch(h, d_pyr, n, nullptr, 0, d_mask, nullptr, nullptr, d_want, d_out, d_cnt, d_eig);
   if (rc != LVB_OK) return rc;
   LVB_CUDA(cudaMemcpyAsync(out_pts, d_out, (size_t)n * fe.N * sizeof(float2), cudaMemcpyDeviceToHost, h->stream));
   LVB_CUDA(cudaMemcpyAsync(out_n, d_cnt, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  if (eig_map) LVB_CUDA(cudaMemcpyAsync(eig_map, fe.eig, npx * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (eig_map) LVB_CUDA(cudaMemcpyAsync(eig_map, d_eig, npx * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   int ovf = 0;
   LVB_CUDA(cudaMemcpyAsync(&ovf, fe.overflow, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   LVB_CUDA(cudaStreamSynchronize(h->stream));

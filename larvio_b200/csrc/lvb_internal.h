@@ -56,7 +56,6 @@ struct LvbChain {                  // scratch of one LK<->LK<->ORB<->RANSAC chai
   float2* out;      // [S][N] per-stage LK output, indexed by rank i
   uint8_t* status;  // [S][N] per-stage marker, indexed by rank i
   float2* slot_curr;  // [S][N] tracked position in the current image, indexed by slot
-  float2* uprev; float2* ucurr;   // [S][N] undistorted (pixel) coordinates, indexed by rank i
   uint8_t* desc;    // [S][N][32] descriptors computed in the previous image (chain 1), by slot
 };
 
@@ -83,7 +82,6 @@ struct LvbFrontEnd {
   int* do_first; int* do_second; int* do_other; int* do_publish; int* do_detect;
   int* want; int* mask_n;
   // detector scratch
-  float* eig;                     // [S][H][W]
   uint8_t* mask;                  // [S][H][W]
   int* eig_max;                   // [S] ordered-int key of the masked max
   unsigned long long* cand;       // [S][cand_cap] packed (value bits<<32 | pixel index)
@@ -129,15 +127,12 @@ struct LvbHandle {
   float* pin_H; int* pin_active; double* pin_t;
   LvbFeature* pin_msg; int* pin_msg_n; uint8_t* pin_has;
   std::vector<void*> allocs;
-  // Staged kernel variants, OFF by default: comma-separated names in LVB_EXPERIMENT select them at lvb_create time
-  // (DESIGN.md 7); host-only, so the kernel argument layouts of the default path do not change.
-  unsigned experiments = 0;
+  int use_graph = 1;                               // lvb_step replays one captured CUDA graph per pyramid parity (LVB_NO_GRAPH=1 disables)
   CUtensorMap lk_maps[2][2][LVB_MAX_LEVELS];       // TMA descriptors of the two ping-pong pyramids x {source, search} box (fe_lk.cu), built on first use
   bool lk_maps_ok[2][2] = {{false, false}, {false, false}};
-  cudaGraphExec_t gexec[2] = {nullptr, nullptr};   // LVB_EXPERIMENT=graph: one captured step per pyramid parity
+  cudaGraphExec_t gexec[2] = {nullptr, nullptr};   // one captured step per pyramid parity
   long long glaunches[2] = {0, 0};
 };
-enum { LVB_EXP_CHOL_BLOCKED = 1u, LVB_EXP_QR_LEAN = 2u, LVB_EXP_GEMM_DMMA = 4u, LVB_EXP_GRAPH = 8u, LVB_EXP_TRSM_WIDE = 16u };
 
 extern thread_local std::string g_lvb_err;
 int lvb_set_err(int code, const char* fmt, ...);
@@ -179,9 +174,11 @@ int fe_undistort_launch(LvbHandle* h, int n_seq, int stride, const float2* pts, 
                         const int* n_pts, float2* out, int to_pixels);
 int fe_detect_launch(LvbHandle* h, const uint8_t* pyr, int n_seq, const int* enable, int use_mask,
                      const uint8_t* ext_mask, const float2* mask_pts, const int* mask_n, const int* want,
-                     float2* out, int* out_n);
+                     float2* out, int* out_n, float* eig_out = nullptr /*[n_seq][H][W] response map, tests only*/);
 int fe_ransac_launch(LvbHandle* h, int n_seq, int stride, const float2* p1, const float2* p2, const int* n,
                      uint8_t* mask, const int* enable, int* fail);
+int fe_ransac_launch2(LvbHandle* h, int n_seq, int stride, const float2* const prev[2], const float2* const curr[2],
+                      int* const perm[2], int* const n[2], uint8_t* const mask[2], int* const fail[2]);
 int fe_process(LvbHandle* h, const uint8_t* images, int on_device, const double* t_img, const LvbImu* imu,
                const int* n_imu, int imu_stride);
 int fe_fetch_messages(LvbHandle* h, LvbFeature* out_feat, int* out_n, uint8_t* has_features);

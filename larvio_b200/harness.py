@@ -1,5 +1,5 @@
-"""Driver loop of the reference (app/larvioMain.cpp:87-117) for a batch of sequences, shared by tests,
-smoke() and bench.py: IMU windowing (:98), processImage, processFeatures when it returned true."""
+"""Driver-side helpers of the reference loop (app/larvioMain.cpp:87-117) for a batch of sequences, shared by tests,
+smoke() and bench.py: the caller-owned IMU buffers and their windowing (:98).  Nothing here touches the oracle."""
 from __future__ import annotations
 
 import numpy as np
@@ -31,26 +31,3 @@ class ImuFeeder:
     def rows(self, s):
         n = int(self.n[s])
         return np.concatenate([self.buf["t"][s, :n, None], self.buf["gyro"][s, :n], self.buf["acc"][s, :n]], 1)
-
-
-def run_oracle(cfg_raw, seq, n_frames, init_from_truth=True):
-    """CPU oracle over one sequence. Returns per-frame dicts (msg ids/data, state after processFeatures)."""
-    from oracle.frontend import ImageProcessorOracle
-    from oracle.backend import LarVioOracle
-    fe = ImageProcessorOracle(cfg_raw); be = LarVioOracle(cfg_raw)
-    imu = []; k = 0; out = []
-    for j in range(n_frames):
-        k2 = synth.imu_window(seq, k, seq.img_t[j]); imu.extend(seq.imu[k:k2].tolist()); k = k2
-        msg = fe.process_image(seq.images[j], seq.img_t[j], np.array(imu).reshape(-1, 7))
-        rec = dict(frame=j, msg=msg, ok=False)
-        if msg is not None:
-            if init_from_truth and not be.is_gravity_set:
-                be.set_initial_state(seq.img_t[j], seq.gt_q[j], seq.gt_p[j], seq.gt_v[j], np.zeros(3), np.zeros(3))
-            rec["ok"] = be.process_features(msg, imu)
-            if rec["ok"]:
-                s = be.imu_state
-                rec.update(q=s.q.copy(), p=s.p.copy(), v=s.v.copy(), bg=s.bg.copy(), ba=s.ba.copy(), P=be.P.copy(), n_win=len(be.aug),
-                           t=float(seq.img_t[j]), n_slam=len(getattr(be, "feature_states", [])), dim=be.P.shape[0],
-                           pos_err=float(np.linalg.norm(s.p - seq.gt_p[j])))
-        out.append(rec)
-    return out

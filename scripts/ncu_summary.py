@@ -8,6 +8,7 @@ want = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram r
         ("l1tex__t_sector_hit_rate.pct", "L1 hit %"), ("lts__t_sector_hit_rate.pct", "L2 hit %"), ("smsp__inst_executed.sum", "warp instructions"),
         ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64 pipe %"), ("sm__inst_executed_pipe_fp64.sum", "fp64 instr"),
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %")]
+traffic = {}
 out = ["# ncu summaries (%s) — `ncu --set full --clock-control none`, one launch per kernel, scripts/gpu_profile.sh\n" % tag]
 for rep in sorted(glob.glob("gpurun_out/prof_*_%s.ncu-rep" % tag)):
     r = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -28,6 +29,19 @@ for rep in sorted(glob.glob("gpurun_out/prof_*_%s.ncu-rep" % tag)):
         if key in hdr:
             i = hdr.index(key)
             out.append("| %s (`%s`) | %s %s |" % (label, key, vals[i], units[i]))
+    def num(key):
+        if key not in hdr:
+            return None
+        i = hdr.index(key)
+        try:
+            return float(vals[i].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1, "ms": 1e3}.get(units[i], 1)
+        except Exception:
+            return None
+    kn = name.split("(")[0].replace("<unnamed>::", "").strip()
+    rd, wr = num("dram__bytes_read.sum"), num("dram__bytes_write.sum")
+    if rd is not None and wr is not None:
+        traffic[kn] = dict(dram_bytes_per_launch=rd + wr, duration_us=num("gpu__time_duration.sum"), sequences_per_launch=int(os.environ.get("S", "64")),
+                           warp_instructions=num("smsp__inst_executed.sum"))
 lines = [l for l in open("gpurun_out/launches_%s.csv" % tag) if not l.startswith("==")]
 agg = collections.OrderedDict(); tot = 0.0
 for row in csv.DictReader(lines):
@@ -43,6 +57,8 @@ for k, (v, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
 OUT = os.environ.get("OUT", "profiles")
 os.makedirs(OUT, exist_ok=True)
 open(OUT + "/%s_ncu_summary.md" % tag, "w").write("\n".join(out) + "\n")
-import shutil
+import json, shutil
+json.dump(dict(tag=tag, how="ncu --set full --clock-control none, longest of the captured launches of each kernel, %s sequences per launch" % os.environ.get("S", "64"),
+               kernels=traffic), open(OUT + "/%s_ncu_traffic.json" % tag, "w"), indent=1)
 shutil.copy("gpurun_out/launches_%s.csv" % tag, OUT + "/%s_launches.csv" % tag)
 print("\n".join(out[:120]))

@@ -13,8 +13,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 from larvio_b200.config import Config          # noqa: E402
-from larvio_b200 import synth, harness         # noqa: E402
+from larvio_b200 import synth                  # noqa: E402
+from oracle_runner import run_oracle           # noqa: E402
 
 NF = 14
 cfg = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), max_features_in_one_grid=0, sw_size=12)
@@ -23,7 +25,7 @@ for s in range(2):
     seq = synth.make_sequence(cfg.raw, s, NF)
     out["img_sha_%d" % s] = np.frombuffer(hashlib.sha256(seq.images.tobytes()).digest(), np.uint8)
     out["imu_%d" % s] = seq.imu
-    recs = harness.run_oracle(cfg.raw, seq, NF)
+    recs = run_oracle(cfg.raw, seq, NF)
     for r in recs:
         j = r["frame"]
         if r["msg"] is not None:
