@@ -91,6 +91,10 @@ def effective_cores():
 
 
 def load_cfg(args):
+    if getattr(args, "workload", "C") == "E":
+        # BASELINE configs[4] per GPU: 400 tracks, 50-pose window, 4x5 grid of 1-D inverse-depth SLAM features (20 in the state)
+        return Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), max_features_in_one_grid=1, feature_idp_dim=1,
+                           aug_grid_rows=4, aug_grid_cols=5, min_distance=14, sw_size=args.window, max_features_num=args.tracks)
     if getattr(args, "workload", "C") == "D":
         # BASELINE configs[3] per GPU: 1-D inverse-depth hybrid (5x6 grid, one SLAM feature per cell), online extrinsic / td /
         # IMU-intrinsic calibration.  Not the headline workload; selectable for measurements of the hybrid path.
@@ -290,15 +294,16 @@ def main():
     ap.add_argument("--steps", type=int, default=120)
     ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--seqs", type=int, default=64, help="sequences per GPU (BASELINE configs[2]: 64)")
-    ap.add_argument("--tracks", type=int, default=200)
-    ap.add_argument("--window", type=int, default=30)
-    ap.add_argument("--preroll", type=int, default=70,
+    ap.add_argument("--seqs", type=int, default=None, help="sequences per GPU (BASELINE configs[2] and [3]: 64; configs[4]: 128)")
+    ap.add_argument("--tracks", type=int, default=None)
+    ap.add_argument("--window", type=int, default=None)
+    ap.add_argument("--preroll", type=int, default=None,
                     help="untimed frames every arm runs before --warmup so that the sliding window is full (30 poses at 10 Hz publishing = 60 frames)")
     ap.add_argument("--cpu-frames", type=int, default=12, help="timed frames per sequence of the bounded cpu_baseline sample (after the pre-roll)")
     ap.add_argument("--profile-steps", type=int, default=8)
-    ap.add_argument("--workload", choices=["C", "D"], default="C",
-                    help="C = BASELINE configs[2] (MSCKF-only, the headline); D = configs[3] per GPU (1-D IDP hybrid + online calibration)")
+    ap.add_argument("--workload", choices=["C", "D", "E"], default="C",
+                    help="C = BASELINE configs[2] (MSCKF-only, the headline); D = configs[3] per GPU (1-D IDP hybrid + online calibration); "
+                         "E = configs[4] per GPU (128 sequences, 400 tracks, 50-pose window, 20 SLAM features)")
     ap.add_argument("--streams", type=int, default=4,
                     help="sub-batches per GPU, each an independent handle/stream driven by its own host thread")
     args = ap.parse_args()
@@ -306,11 +311,19 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.warmup < 3:
         args.warmup = 3
+    # per-workload defaults; the pre-roll fills the sliding window (2 frames per pose at 10 Hz publishing) and, in the hybrid
+    # workloads, passes the 5 s after which SLAM features are promoted (larvio.cpp:1974)
+    wd = {"C": dict(seqs=64, tracks=200, window=30, preroll=70), "D": dict(seqs=64, tracks=200, window=30, preroll=120),
+          "E": dict(seqs=128, tracks=400, window=50, preroll=130)}[args.workload]
+    for key, val in wd.items():
+        if getattr(args, key) is None:
+            setattr(args, key, val)
     S, K, Wm = args.seqs, args.steps, args.warmup
     PR = max(args.preroll, 0)
     cfg = load_cfg(args)
-    workload = ("configs[2]: %d batched synthetic 752x480@20Hz+200Hz-IMU sequences per GPU, %d tracks, %d-pose window, MSCKF-only" if args.workload == "C" else
-                "configs[3] per GPU: %d batched synthetic sequences, %d tracks, %d-pose window, 1-D IDP hybrid (5x6 grid) + online extrinsic/td/IMU-intrinsic calibration") % (S, args.tracks, args.window)
+    workload = {"C": "configs[2]: %d batched synthetic 752x480@20Hz+200Hz-IMU sequences per GPU, %d tracks, %d-pose window, MSCKF-only",
+                "D": "configs[3] per GPU: %d batched synthetic sequences, %d tracks, %d-pose window, 1-D IDP hybrid (5x6 grid) + online extrinsic/td/IMU-intrinsic calibration",
+                "E": "configs[4] per GPU: %d batched synthetic sequences, %d tracks, %d-pose window, 1-D IDP hybrid with a 4x5 grid (20 SLAM features in the state)"}[args.workload] % (S, args.tracks, args.window)
     config = dict(workload=workload, preroll_frames=PR, sequences_per_gpu=S, sub_batches_per_gpu=args.streams, tracks=args.tracks, window=args.window, image="752x480 u8",
                   l2_policy="each step reads a fresh %.1f MB image batch and touches >250 MB of per-sequence state (> 126 MB L2)" % (S * B0 / 1e6),
                   inputs=("one pool of %d seeded sequences (seed 1234+i)" % S) + ("" if world == 1 else
@@ -479,7 +492,7 @@ def main():
     # steady-state evidence: sliding-window fill and state dimension of every sequence right after the timed region
     ic = np.array([bb.debug_icore(q) for bb in batches for q in range(bb.S)])
     steady = dict(window_poses_mean=float(ic[:, 2].mean()), window_poses_min=int(ic[:, 2].min()), state_dim_mean=float(ic[:, 7].mean()),
-                  window_capacity=int(args.window))
+                  window_capacity=int(args.window), slam_features_in_state_mean=float(ic[:, 22].mean()))
     # ---- per-kernel profile on the next frames (not part of the timed region)
     prof = {}
     prof_stats = []

@@ -57,11 +57,112 @@ __device__ __forceinline__ M3 imu_selector(int kind, V3 x) {
   else { r.m[0] = x.y; r.m[1] = x.z; r.m[5] = x.z; }
   return r;
 }
+// per-sample record left by the sequential nominal-state pass for the parallel construction of Phi_k
+enum { R_DT = 0, R_Q = 1, R_VEL = 5, R_POS = 8, R_VNEW = 11, R_PNEW = 14, R_FOV = 17, R_FOP = 20, R_FNV = 23, R_FNP = 26,
+       R_GYRO = 29, R_ACC = 32, R_GYRO_OLD = 35, R_ACC_OLD = 38, PROP_REC = 42 };
+template <int L> struct PropChunk { static constexpr int N = (L <= 22) ? 8 : 2; };   // samples whose Phi is built concurrently
+
+// calPhi (larvio.cpp:3475-3800) for one IMU sample from its record: fills Phi (L x L, row pitch L + 1).
+template <int L>
+__device__ void prop_build_phi(const double* rec, const double* core, bool fej, double* Phi_) {
+  constexpr int LP = L + 1;
+#define Phi(r, c) Phi_[(r) * LP + (c)]
+  const double dtime = rec[R_DT];
+  const V3 bg = ld3(core + C_BG), ba = ld3(core + C_BA);
+  const M3 Tg = m3_load(core + C_TG), As = m3_load(core + C_AS), Ma = m3_load(core + C_MA);
+  const V3 m_gyro = ld3(rec + R_GYRO), m_acc = ld3(rec + R_ACC);
+  const V3 f = m_acc - ba, acc = m3_vec(Ma, f);
+  const V3 w = m_gyro - m3_vec(As, acc) - bg, gyro = m3_vec(Tg, w);
+  const V3 f_old = ld3(rec + R_ACC_OLD) - ba, acc_old = m3_vec(Ma, f_old);
+  const V3 w_old = ld3(rec + R_GYRO_OLD) - m3_vec(As, acc_old) - bg, gyro_old = m3_vec(Tg, w_old);
+  const double q[4] = {rec[R_Q], rec[R_Q + 1], rec[R_Q + 2], rec[R_Q + 3]};
+  const M3 Rq = quat_to_rot(q);
+  const V3 vel = ld3(rec + R_VEL), pos = ld3(rec + R_POS), vnew = ld3(rec + R_VNEW), pnew = ld3(rec + R_PNEW);
+  const V3 g = v3(0, 0, -9.81);
+  const V3 axis = (gyro_old + gyro) * (dtime * 0.5) + cross(gyro_old, gyro) * (dtime * dtime / 12);
+  const M3 Ah = skew(axis);
+  const M3 C = Rq;       // C_bk2w from imu_state_old.orientation
+  V3 vk, pk, vk1, pk1;
+  if (fej) { vk = ld3(rec + R_FOV); pk = ld3(rec + R_FOP); vk1 = ld3(rec + R_FNV); pk1 = ld3(rec + R_FNP); }
+  else { vk = vel; pk = pos; vk1 = vnew; pk1 = pnew; }
+  for (int r = 0; r < L; ++r) for (int c = 0; c < L; ++c) Phi(r, c) = (r == c) ? 1.0 : 0.0;
+  const M3 I3 = m3_identity();
+  const M3 twoIAh = m3_add(m3_scale(I3, 2.0), Ah);
+  const M3 TA = m3_mul(Tg, As), TAM = m3_mul(TA, Ma);
+  const M3 CtA = m3_scale(m3_mul(C, twoIAh), 0.5 * dtime);       // 0.5*C*(2I+Ah)*dtime
+  const M3 Pqbg = m3_scale(m3_mul(CtA, Tg), -1.0);
+  const M3 Pqba = m3_mul(CtA, TAM);
+  const M3 Pvq = m3_scale(skew(vk1 - vk - g * dtime), -1.0);
+  const M3 Pvbg = m3_add(m3_mul(skew(pk - pk1 + vk1 * dtime - g * (0.5 * dtime * dtime)), C),
+                         m3_mul(m3_mul(skew(pk * 0.5 - pk1 * 0.5 + vk1 * (0.5 * dtime) - g * (dtime * dtime / 6)), C), Ah));
+  const M3 Pvba = m3_sub(m3_scale(m3_mul(CtA, Ma), -1.0), m3_mul(Pvbg, TAM));
+  const M3 Ppq = m3_scale(skew(pk1 - pk - vk * dtime - g * (0.5 * dtime * dtime)), -1.0);
+  const M3 Ppbg = m3_add(m3_scale(m3_mul(skew(g), C), -dtime * dtime * dtime / 6),
+                         m3_scale(m3_mul(m3_mul(skew(pk1 - pk - g * (dtime * dtime / 6)), C), Ah), dtime / 4));
+  const M3 Ppba = m3_sub(m3_mul(m3_scale(m3_mul(C, m3_add(m3_scale(I3, 3.0), Ah)), -dtime * dtime / 6), Ma), m3_mul(Ppbg, TAM));
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      Phi(r, 9 + c) = Pqbg.m[r * 3 + c];
+      Phi(r, 12 + c) = Pqba.m[r * 3 + c];
+      Phi(3 + r, c) = Pvq.m[r * 3 + c];
+      Phi(3 + r, 9 + c) = Pvbg.m[r * 3 + c];
+      Phi(3 + r, 12 + c) = Pvba.m[r * 3 + c];
+      Phi(6 + r, c) = Ppq.m[r * 3 + c];
+      Phi(6 + r, 3 + c) = (r == c) ? dtime : 0.0;
+      Phi(6 + r, 9 + c) = Ppbg.m[r * 3 + c];
+      Phi(6 + r, 12 + c) = Ppba.m[r * 3 + c];
+    }
+  if constexpr (L > 22) {
+    // ---- IMU-intrinsic columns (:3532-3797): 8 groups of 3 columns; selectors Lo/Di/Up place the components of
+    // (w | acc | f) sampled at k, k+1/2, k+1; Simpson weights for q, the reference's RK4 weights for v and p
+    const V3 f_mid = (f + f_old) * 0.5, acc_mid = (acc + acc_old) * 0.5;
+    const V3 w_mid = (w_old + w) * 0.5 + cross(w_old, w) * (dtime / 12);
+    const M3 R_mid = m3_add(I3, m3_scale(Ah, 0.5)), R_kp1 = m3_add(I3, Ah);
+    const M3 S_mid = m3_scale(skew(m3_vec(R_mid, acc_mid)), dtime * 0.5), S_kp1 = skew(m3_vec(R_kp1, acc));
+    for (int gi = 0; gi < 8; ++gi) {
+      const int kind = (gi < 6) ? gi % 3 : gi - 6;                 // 0 Lo, 1 Di, 2 Up
+      const V3 xk = gi < 3 ? w_old : (gi < 6 ? acc_old : f_old);
+      const V3 xh = gi < 3 ? w_mid : (gi < 6 ? acc_mid : f_mid);
+      const V3 xp = gi < 3 ? w : (gi < 6 ? acc : f);
+      const M3 Lf = gi < 3 ? I3 : (gi < 6 ? Tg : TA);
+      const double sgn = gi < 3 ? 1.0 : -1.0;
+      const bool direct = gi >= 6;
+      const M3 sk = imu_selector(kind, xk), sh = imu_selector(kind, xh), sp = imu_selector(kind, xp);
+      const M3 kq1 = m3_mul(Lf, sk), kq2 = m3_mul(R_mid, m3_mul(Lf, sh)), kq4 = m3_mul(R_kp1, m3_mul(Lf, sp));
+      const M3 Rq2 = m3_scale(m3_add(m3_add(kq1, m3_scale(kq2, 4.0)), kq4), dtime / 6);
+      M3 kv1, kv2, kv3, kv4;
+      if (!direct) {
+        kv1 = m3_scale(I3, 0.0); kv2 = m3_mul(S_mid, kq1); kv3 = m3_mul(S_mid, kq2); kv4 = m3_mul(S_kp1, Rq2);
+      } else {
+        const M3 Rh = m3_mul(R_mid, sh);
+        kv1 = sk; kv2 = m3_add(Rh, m3_mul(S_mid, kq1)); kv3 = m3_add(Rh, m3_mul(S_mid, kq2));
+        kv4 = m3_add(m3_mul(R_kp1, sp), m3_mul(S_kp1, Rq2));
+      }
+      const M3 fR = m3_scale(m3_add(m3_add(kv1, m3_scale(m3_add(kv2, kv3), 2.0)), kv4), dtime / 6);
+      const double vs = direct ? 1.0 : -sgn;
+      const M3 kp = m3_scale(m3_add(m3_scale(m3_add(kv1, kv2), dtime), fR), dtime / 6);   // kp1=0, kp2=dt kv1/2, kp3=dt kv2/2, kp4=fR
+      const M3 Bq = m3_scale(m3_mul(C, Rq2), sgn), Bv = m3_scale(m3_mul(C, fR), vs), Bp = m3_scale(m3_mul(C, kp), vs);
+      const int col = 22 + 3 * gi;
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) { Phi(r, col + c) = Bq.m[r * 3 + c]; Phi(3 + r, col + c) = Bv.m[r * 3 + c]; Phi(6 + r, col + c) = Bp.m[r * 3 + c]; }
+    }
+  }
+#undef Phi
+}
+
+// batchImuProcessing / processModel / predictNewState / calPhi for one sequence per CTA.  Three phases per chunk of samples:
+// (1) one thread integrates the nominal state sample by sample (sequential by nature: quaternion + the reference's RK4) and
+// leaves a record per sample; (2) one thread per sample builds its transition matrix Phi_k from the record - the expensive
+// part (calPhi, with the 24 IMU-intrinsic columns when L = 46), now concurrent; (3) all threads run the covariance recursion
+// P_LL <- Phi (P_LL + D dt) Phi^T, PhiTot <- Phi PhiTot sample by sample.  The composed PhiTot is applied ONCE to the
+// cross-covariance at the end.
 template <int L>
 __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
-  extern __shared__ double psm[];                      // Phi, PLL, Tmp, PhiTot: [L][L+1] each; Ddiag [L]
-  __shared__ int s_ok, s_action, s_used;
-  __shared__ double s_dtime, s_dt;
+  extern __shared__ double psm[];                      // PhiC[CHK], PLL, Tmp, PhiTot: [L][L+1] each; Ddiag [L]; rec[CHK][PROP_REC]
+  constexpr int CHK = PropChunk<L>::N;
+  __shared__ int s_ok, s_used, s_stop, s_nact;
+  __shared__ int s_act[CHK];
+  __shared__ double s_dt;
   const int s = blockIdx.x, tid = threadIdx.x;
   double* core = core_of(v, s);
   int* ic = icore_of(v, s);
@@ -69,9 +170,9 @@ __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
   const int n_imu = v.be.n_imu[s];
   constexpr int LP = L + 1;
   const int LD = v.be.LD;
-  double* const Phi_ = psm; double* const PLL_ = psm + L * LP; double* const Tmp_ = psm + 2 * L * LP; double* const PhiTot_ = psm + 3 * L * LP;
-  double* const Ddiag = psm + 4 * L * LP;
-#define Phi(r, c) Phi_[(r) * LP + (c)]
+  double* const PhiC_ = psm; double* const PLL_ = psm + CHK * L * LP; double* const Tmp_ = PLL_ + L * LP; double* const PhiTot_ = Tmp_ + L * LP;
+  double* const Ddiag = PhiTot_ + L * LP;
+  double* const rec_ = Ddiag + L;
 #define PLL(r, c) PLL_[(r) * LP + (c)]
 #define Tmp(r, c) Tmp_[(r) * LP + (c)]
 #define PhiTot(r, c) PhiTot_[(r) * LP + (c)]
@@ -83,7 +184,7 @@ __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
       else ok = 0;
     }
     if (ok && !ic[I_GRAVITY]) ok = 0;                            // :375-391 (initialiser out of scope)
-    s_ok = ok; ic[I_OK] = ok; ic[I_CONSUMED] = 0; s_used = 0; s_dt = 0.0;
+    s_ok = ok; ic[I_OK] = ok; ic[I_CONSUMED] = 0; s_used = 0; s_dt = 0.0; s_stop = 0;
     ic[I_UPDATES] = 0;
   }
   if (tid < L) {
@@ -101,32 +202,37 @@ __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
   }
   __syncthreads();
   const double time_bound = v.msg_t[s] + core[C_TD];
-  for (int k = 0; k < n_imu; ++k) {
+  const bool fej = ic[I_FEJ] != 0;
+  for (int k0 = 0; k0 < n_imu; k0 += CHK) {
+    // ---- phase 1: nominal state of up to CHK samples (processModel :520-578 without Phi, predictNewState :581-649)
     if (tid == 0) {
-      const double t = imu[k].t;
-      if (t <= core[C_TIME]) { s_action = 0; s_used++; }
-      else if (t - time_bound > v.cfg.th_imu) s_action = 2;
-      else {
-        s_action = 1; s_used++;
+      int nact = 0;
+      for (int kk = 0; kk < CHK && k0 + kk < n_imu; ++kk) {
+        const int k = k0 + kk;
+        const double t = imu[k].t;
+        if (t <= core[C_TIME]) { s_used++; continue; }           // already covered by the state
+        if (t - time_bound > v.cfg.th_imu) { s_stop = 1; break; }
+        s_used++;
         s_dt = t - time_bound;
+        double* rec = rec_ + nact * PROP_REC;
         const V3 m_gyro = v3(imu[k].gyro[0], imu[k].gyro[1], imu[k].gyro[2]);
         const V3 m_acc = v3(imu[k].acc[0], imu[k].acc[1], imu[k].acc[2]);
         if (!ic[I_HAVE_OLD]) { st3(core + C_GYRO_OLD, m_gyro); st3(core + C_ACC_OLD, m_acc); ic[I_HAVE_OLD] = 1; }
-        // ---- processModel (:520-578): acc = Ma f, w = m_gyro - As acc - bg, gyro = Tg w
+        // acc = Ma f, w = m_gyro - As acc - bg, gyro = Tg w
         const V3 bg = ld3(core + C_BG), ba = ld3(core + C_BA);
         const M3 Tg = m3_load(core + C_TG), As = m3_load(core + C_AS), Ma = m3_load(core + C_MA);
         const V3 f = m_acc - ba, acc = m3_vec(Ma, f);
         const V3 w = m_gyro - m3_vec(As, acc) - bg, gyro = m3_vec(Tg, w);
-        const V3 f_old = ld3(core + C_ACC_OLD) - ba, acc_old = m3_vec(Ma, f_old);
-        const V3 w_old = ld3(core + C_GYRO_OLD) - m3_vec(As, acc_old) - bg, gyro_old = m3_vec(Tg, w_old);
+        st3(rec + R_GYRO, m_gyro); st3(rec + R_ACC, m_acc);
+        st3(rec + R_GYRO_OLD, ld3(core + C_GYRO_OLD)); st3(rec + R_ACC_OLD, ld3(core + C_ACC_OLD));
         const double dtime = t - core[C_TIME];
-        s_dtime = dtime;
-        // ---- predictNewState (:581-649)
+        rec[R_DT] = dtime;
         const double gn = norm(gyro);
         double q[4] = {core[C_Q], core[C_Q + 1], core[C_Q + 2], core[C_Q + 3]};
         const V3 vel = ld3(core + C_V), pos = ld3(core + C_P);
-        for (int i = 0; i < 4; ++i) core[C_OLD_Q + i] = q[i];
+        for (int i = 0; i < 4; ++i) { core[C_OLD_Q + i] = q[i]; rec[R_Q + i] = q[i]; }
         st3(core + C_OLD_P, pos); st3(core + C_OLD_V, vel);
+        st3(rec + R_VEL, vel); st3(rec + R_POS, pos);
         const V3 qv = v3(q[0], q[1], q[2]);
         const V3 ov = cross(qv, gyro) + gyro * q[3];     // (Omega q).head<3>()
         const double ow = -dot(gyro, qv);                // (Omega q)(3)
@@ -157,112 +263,56 @@ __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
         const V3 vnew = vel + (k1v + 2.0 * k2v + 2.0 * k3v + k4v) * (dtime / 6);
         const V3 pnew = pos + (k1p + 2.0 * k2p + 2.0 * k3p + k4p) * (dtime / 6);
         st3(core + C_V, vnew); st3(core + C_P, pnew);
+        st3(rec + R_VNEW, vnew); st3(rec + R_PNEW, pnew);
         // FEJ bookkeeping (:644-646)
         st3(core + C_FOLD_P, ld3(core + C_FNOW_P)); st3(core + C_FOLD_V, ld3(core + C_FNOW_V));
         st3(core + C_FNOW_P, pnew); st3(core + C_FNOW_V, vnew);
-        // ---- calPhi (:3475-3530)
-        const V3 axis = (gyro_old + gyro) * (dtime * 0.5) + cross(gyro_old, gyro) * (dtime * dtime / 12);
-        const M3 Ah = skew(axis);
-        const M3 C = Rq;       // C_bk2w from imu_state_old.orientation
-        V3 vk, pk, vk1, pk1;
-        if (ic[I_FEJ]) { vk = ld3(core + C_FOLD_V); pk = ld3(core + C_FOLD_P); vk1 = ld3(core + C_FNOW_V); pk1 = ld3(core + C_FNOW_P); }
-        else { vk = vel; pk = pos; vk1 = vnew; pk1 = pnew; }
-        for (int r = 0; r < L; ++r) for (int c = 0; c < L; ++c) Phi(r, c) = (r == c) ? 1.0 : 0.0;
-        const M3 I3 = m3_identity();
-        const M3 twoIAh = m3_add(m3_scale(I3, 2.0), Ah);
-        const M3 TA = m3_mul(Tg, As), TAM = m3_mul(TA, Ma);
-        const M3 CtA = m3_scale(m3_mul(C, twoIAh), 0.5 * dtime);       // 0.5*C*(2I+Ah)*dtime
-        const M3 Pqbg = m3_scale(m3_mul(CtA, Tg), -1.0);
-        const M3 Pqba = m3_mul(CtA, TAM);
-        const M3 Pvq = m3_scale(skew(vk1 - vk - g * dtime), -1.0);
-        const M3 Pvbg = m3_add(m3_mul(skew(pk - pk1 + vk1 * dtime - g * (0.5 * dtime * dtime)), C),
-                               m3_mul(m3_mul(skew(pk * 0.5 - pk1 * 0.5 + vk1 * (0.5 * dtime) - g * (dtime * dtime / 6)), C), Ah));
-        const M3 Pvba = m3_sub(m3_scale(m3_mul(CtA, Ma), -1.0), m3_mul(Pvbg, TAM));
-        const M3 Ppq = m3_scale(skew(pk1 - pk - vk * dtime - g * (0.5 * dtime * dtime)), -1.0);
-        const M3 Ppbg = m3_add(m3_scale(m3_mul(skew(g), C), -dtime * dtime * dtime / 6),
-                               m3_scale(m3_mul(m3_mul(skew(pk1 - pk - g * (dtime * dtime / 6)), C), Ah), dtime / 4));
-        const M3 Ppba = m3_sub(m3_mul(m3_scale(m3_mul(C, m3_add(m3_scale(I3, 3.0), Ah)), -dtime * dtime / 6), Ma), m3_mul(Ppbg, TAM));
-        for (int r = 0; r < 3; ++r)
-          for (int c = 0; c < 3; ++c) {
-            Phi(r, 9 + c) = Pqbg.m[r * 3 + c];
-            Phi(r, 12 + c) = Pqba.m[r * 3 + c];
-            Phi(3 + r, c) = Pvq.m[r * 3 + c];
-            Phi(3 + r, 9 + c) = Pvbg.m[r * 3 + c];
-            Phi(3 + r, 12 + c) = Pvba.m[r * 3 + c];
-            Phi(6 + r, c) = Ppq.m[r * 3 + c];
-            Phi(6 + r, 3 + c) = (r == c) ? dtime : 0.0;
-            Phi(6 + r, 9 + c) = Ppbg.m[r * 3 + c];
-            Phi(6 + r, 12 + c) = Ppba.m[r * 3 + c];
-          }
-        if constexpr (L > 22) {
-          // ---- IMU-intrinsic columns (:3532-3797): 8 groups of 3 columns; selectors Lo/Di/Up place the components of
-          // (w | acc | f) sampled at k, k+1/2, k+1; Simpson weights for q, the reference's RK4 weights for v and p
-          const V3 f_mid = (f + f_old) * 0.5, acc_mid = (acc + acc_old) * 0.5;
-          const V3 w_mid = (w_old + w) * 0.5 + cross(w_old, w) * (dtime / 12);
-          const M3 R_mid = m3_add(I3, m3_scale(Ah, 0.5)), R_kp1 = m3_add(I3, Ah);
-          const M3 S_mid = m3_scale(skew(m3_vec(R_mid, acc_mid)), dtime * 0.5), S_kp1 = skew(m3_vec(R_kp1, acc));
-          for (int gi = 0; gi < 8; ++gi) {
-            const int kind = (gi < 6) ? gi % 3 : gi - 6;                 // 0 Lo, 1 Di, 2 Up
-            const V3 xk = gi < 3 ? w_old : (gi < 6 ? acc_old : f_old);
-            const V3 xh = gi < 3 ? w_mid : (gi < 6 ? acc_mid : f_mid);
-            const V3 xp = gi < 3 ? w : (gi < 6 ? acc : f);
-            const M3 Lf = gi < 3 ? I3 : (gi < 6 ? Tg : TA);
-            const double sgn = gi < 3 ? 1.0 : -1.0;
-            const bool direct = gi >= 6;
-            const M3 sk = imu_selector(kind, xk), sh = imu_selector(kind, xh), sp = imu_selector(kind, xp);
-            const M3 kq1 = m3_mul(Lf, sk), kq2 = m3_mul(R_mid, m3_mul(Lf, sh)), kq4 = m3_mul(R_kp1, m3_mul(Lf, sp));
-            const M3 Rq = m3_scale(m3_add(m3_add(kq1, m3_scale(kq2, 4.0)), kq4), dtime / 6);
-            M3 kv1, kv2, kv3, kv4;
-            if (!direct) {
-              kv1 = m3_scale(I3, 0.0); kv2 = m3_mul(S_mid, kq1); kv3 = m3_mul(S_mid, kq2); kv4 = m3_mul(S_kp1, Rq);
-            } else {
-              const M3 Rh = m3_mul(R_mid, sh);
-              kv1 = sk; kv2 = m3_add(Rh, m3_mul(S_mid, kq1)); kv3 = m3_add(Rh, m3_mul(S_mid, kq2));
-              kv4 = m3_add(m3_mul(R_kp1, sp), m3_mul(S_kp1, Rq));
-            }
-            const M3 fR = m3_scale(m3_add(m3_add(kv1, m3_scale(m3_add(kv2, kv3), 2.0)), kv4), dtime / 6);
-            const double vs = direct ? 1.0 : -sgn;
-            const M3 kp = m3_scale(m3_add(m3_scale(m3_add(kv1, kv2), dtime), fR), dtime / 6);   // kp1=0, kp2=dt kv1/2, kp3=dt kv2/2, kp4=fR
-            const M3 Bq = m3_scale(m3_mul(C, Rq), sgn), Bv = m3_scale(m3_mul(C, fR), vs), Bp = m3_scale(m3_mul(C, kp), vs);
-            const int col = 22 + 3 * gi;
-            for (int r = 0; r < 3; ++r)
-              for (int c = 0; c < 3; ++c) { Phi(r, col + c) = Bq.m[r * 3 + c]; Phi(3 + r, col + c) = Bv.m[r * 3 + c]; Phi(6 + r, col + c) = Bp.m[r * 3 + c]; }
-          }
-        }
+        st3(rec + R_FOP, ld3(core + C_FOLD_P)); st3(rec + R_FOV, ld3(core + C_FOLD_V));
+        st3(rec + R_FNP, pnew); st3(rec + R_FNV, vnew);
         core[C_TIME] = t;
         st3(core + C_GYRO_OLD, m_gyro); st3(core + C_ACC_OLD, m_acc);
+        ++nact;
       }
+      s_nact = nact;
     }
     __syncthreads();
-    const int action = s_action;
-    if (action == 2) break;
-    if (action == 0) { __syncthreads(); continue; }
-    const double dtime = s_dtime;
-    // Tmp = Phi * (PLL + D*dtime)
-    for (int i = tid; i < L * L; i += blockDim.x) {
-      const int r = i / L, c = i - r * L;
-      double acc = 0.0;
-      for (int k2 = 0; k2 < L; ++k2) acc += Phi(r, k2) * (PLL(k2, c) + (k2 == c ? Ddiag[c] * dtime : 0.0));
-      Tmp(r, c) = acc;
+    const int nact = s_nact;
+    // ---- phase 2: Phi_k of every sample of the chunk, one thread each
+    if (tid < nact) prop_build_phi<L>(rec_ + tid * PROP_REC, core, fej, PhiC_ + (size_t)tid * L * LP);
+    __syncthreads();
+    // ---- phase 3: covariance recursion, sample by sample
+    for (int a = 0; a < nact; ++a) {
+      const double* Phi_ = PhiC_ + (size_t)a * L * LP;
+#define Phi(r, c) Phi_[(r) * LP + (c)]
+      const double dtime = rec_[a * PROP_REC + R_DT];
+      // Tmp = Phi * (PLL + D*dtime)
+      for (int i = tid; i < L * L; i += blockDim.x) {
+        const int r = i / L, c = i - r * L;
+        double acc = 0.0;
+        for (int k2 = 0; k2 < L; ++k2) acc += Phi(r, k2) * (PLL(k2, c) + (k2 == c ? Ddiag[c] * dtime : 0.0));
+        Tmp(r, c) = acc;
+      }
+      __syncthreads();
+      for (int i = tid; i < L * L; i += blockDim.x) {
+        const int r = i / L, c = i - r * L;
+        double acc = 0.0;
+        for (int k2 = 0; k2 < L; ++k2) acc += Tmp(r, k2) * Phi(c, k2);
+        PLL(r, c) = acc;
+      }
+      __syncthreads();
+      for (int i = tid; i < L * L; i += blockDim.x) {
+        const int r = i / L, c = i - r * L;
+        double acc = 0.0;
+        for (int k2 = 0; k2 < L; ++k2) acc += Phi(r, k2) * PhiTot(k2, c);
+        Tmp(r, c) = acc;
+        if (r < c) { const double m = 0.5 * (PLL(r, c) + PLL(c, r)); PLL(r, c) = m; PLL(c, r) = m; }
+      }
+      __syncthreads();
+      for (int i = tid; i < L * L; i += blockDim.x) { const int r = i / L, c = i - r * L; PhiTot(r, c) = Tmp(r, c); }
+      __syncthreads();
+#undef Phi
     }
-    __syncthreads();
-    for (int i = tid; i < L * L; i += blockDim.x) {
-      const int r = i / L, c = i - r * L;
-      double acc = 0.0;
-      for (int k2 = 0; k2 < L; ++k2) acc += Tmp(r, k2) * Phi(c, k2);
-      PLL(r, c) = acc;
-    }
-    __syncthreads();
-    for (int i = tid; i < L * L; i += blockDim.x) {
-      const int r = i / L, c = i - r * L;
-      double acc = 0.0;
-      for (int k2 = 0; k2 < L; ++k2) acc += Phi(r, k2) * PhiTot(k2, c);
-      Tmp(r, c) = acc;
-      if (r < c) { const double m = 0.5 * (PLL(r, c) + PLL(c, r)); PLL(r, c) = m; PLL(c, r) = m; }
-    }
-    __syncthreads();
-    for (int i = tid; i < L * L; i += blockDim.x) { const int r = i / L, c = i - r * L; PhiTot(r, c) = Tmp(r, c); }
-    __syncthreads();
+    if (s_stop) break;
   }
   __syncthreads();
   // write back P_LL, apply the composed transition to the cross terms
@@ -278,7 +328,6 @@ __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
       P[(size_t)c * LD + r] = acc;
     }
   }
-#undef Phi
 #undef PLL
 #undef Tmp
 #undef PhiTot
@@ -289,11 +338,20 @@ __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
   }
 }
 
+static size_t be_propagate_smem(int L) {       // PhiC[CHK] + PLL + Tmp + PhiTot ([L][L+1] each) + Ddiag[L] + rec[CHK][PROP_REC]
+  const int chk = (L <= 22) ? 8 : 2;
+  return sizeof(double) * ((size_t)(chk + 3) * L * (L + 1) + L + (size_t)chk * PROP_REC);
+}
+
 // ====================================================================== addFeatureObservations
 // One CTA per sequence, one thread per message feature.
 __global__ void __launch_bounds__(512) be_add_obs_kernel(BeView v) {
   extern __shared__ unsigned long long sm_ids[];      // [T] table ids (0xfff.. = free)
-  __shared__ int s_free_cnt, s_new_cnt, s_tracked, s_nbefore, s_ndis;
+  __shared__ unsigned long long hkey[2048];           // id -> slot hash (open addressing, load <= 0.5: T <= 1024)
+  __shared__ short hval[2048];
+  __shared__ short free_list[1024];                   // k-th free table slot in ascending slot order
+  __shared__ int s_warp_tot[16], s_nfree;
+  __shared__ int s_tracked, s_nbefore, s_ndis;
   __shared__ double s_dis[512];           // double like the reference's norms (larvio.cpp:842-847, 2751-2766)
   const int s = blockIdx.x, tid = threadIdx.x;
   int* ic = icore_of(v, s);
@@ -304,16 +362,37 @@ __global__ void __launch_bounds__(512) be_add_obs_kernel(BeView v) {
   int* ft_flags = v.be.ft_flags + (size_t)s * T;
   unsigned long long* ft_mask = v.be.ft_mask + (size_t)s * T;
   double* ft_obs = v.be.ft_obs + (size_t)s * T * Wcap * 4;
-  if (tid == 0) { s_free_cnt = 0; s_new_cnt = 0; s_tracked = 0; s_nbefore = 0; s_ndis = 0; }
+  if (tid == 0) { s_tracked = 0; s_nbefore = 0; s_ndis = 0; s_nfree = 0; }
+  for (int i = tid; i < 2048; i += blockDim.x) hkey[i] = ~0ull;
   __syncthreads();
   int used_local = 0;
   for (int i = tid; i < T; i += blockDim.x) {
     const bool used = ft_flags[i] & 1;
-    sm_ids[i] = used ? ft_id[i] : ~0ull;
+    const unsigned long long id = used ? ft_id[i] : ~0ull;
+    sm_ids[i] = id;
     used_local += used;
+    if (used) {                                        // insert (ids are unique)
+      unsigned h = (unsigned)((id * 0x9E3779B97F4A7C15ull) >> 53);
+      while (atomicCAS(&hkey[h], ~0ull, id) != ~0ull) h = (h + 1) & 2047;
+      hval[h] = (short)i;
+    }
   }
   atomicAdd(&s_nbefore, used_local);
   __syncthreads();
+  // free slots in ascending order (new features take them in message order, like std::map insertion into a fresh slot)
+  for (int c0 = 0; c0 < T; c0 += blockDim.x) {
+    const int i = c0 + tid;
+    const bool fr = i < T && sm_ids[i] == ~0ull;
+    const unsigned bal = __ballot_sync(0xffffffffu, fr);
+    if ((tid & 31) == 0) s_warp_tot[tid >> 5] = __popc(bal);
+    __syncthreads();
+    int off = s_nfree + __popc(bal & ((1u << (tid & 31)) - 1));
+    for (int w2 = 0; w2 < (tid >> 5); ++w2) off += s_warp_tot[w2];
+    if (fr) free_list[off] = (short)i;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) t += s_warp_tot[w2]; s_nfree += t; }
+    __syncthreads();
+  }
   const int n_msg = min(v.msg_n[s], v.be.N);
   const int n_win = ic[I_NWIN];                       // slot the new state will occupy
   if (n_win >= Wcap) { if (tid == 0) ic[I_ERR] = 2; return; }   // window full: report before anything is written past its slots
@@ -325,7 +404,8 @@ __global__ void __launch_bounds__(512) be_add_obs_kernel(BeView v) {
   LvbFeature f; int slot = -1; bool is_new = false;
   if (tid < n_msg) {
     f = v.msg[(size_t)s * v.msg_stride + tid];
-    for (int i = 0; i < T; ++i) if (sm_ids[i] == f.id) { slot = i; break; }
+    unsigned h = (unsigned)((f.id * 0x9E3779B97F4A7C15ull) >> 53);
+    while (hkey[h] != ~0ull) { if (hkey[h] == f.id) { slot = hval[h]; break; } h = (h + 1) & 2047; }
     is_new = slot < 0;
   }
   __syncthreads();
@@ -337,10 +417,7 @@ __global__ void __launch_bounds__(512) be_add_obs_kernel(BeView v) {
   int rank = __popc(bal & ((1u << (tid & 31)) - 1));
   for (int w = 0; w < (tid >> 5); ++w) rank += warp_new[w];
   if (is_new) {
-    // rank-th free slot
-    int cnt = 0, found = -1;
-    for (int i = 0; i < T; ++i) if (sm_ids[i] == ~0ull) { if (cnt == rank) { found = i; break; } ++cnt; }
-    slot = found;
+    slot = rank < s_nfree ? (int)free_list[rank] : -1;   // rank-th free slot
     if (slot < 0) atomicExch(&ic[I_ERR], 1);           // feature table overflow
   }
   if (tid < n_msg && slot >= 0) {
@@ -2258,7 +2335,8 @@ int be_alloc(LvbHandle* h) {
   // dynamic shared memory opt-ins
   const int fsm_bytes = (int)sizeof(double) * (6 * be->Wcap + 8 + 4 * be->Wcap * be->Wcap + 2 * be->Wcap + (8 + 6 * be->Wcap) / 2 + 4);
   LVB_CUDA(cudaFuncSetAttribute(be_feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm_bytes));
-  LVB_CUDA(cudaFuncSetAttribute(be_propagate_kernel<46>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (4 * 46 * 47 + 46))));
+  LVB_CUDA(cudaFuncSetAttribute(be_propagate_kernel<22>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be_propagate_smem(22)));
+  LVB_CUDA(cudaFuncSetAttribute(be_propagate_kernel<46>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be_propagate_smem(46)));
   if (be->NFmax > 0) LVB_CUDA(cudaFuncSetAttribute(be_slam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 64 * be->LD)));
   const size_t chol_bytes = sizeof(double) * ((size_t)be->Dmax * (be->Dmax + 1) / 2 + 2 * be->Dmax);
   if (chol_bytes <= 227 * 1024) LVB_CUDA(cudaFuncSetAttribute(be_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_bytes));
@@ -2532,8 +2610,8 @@ static int be_enqueue(LvbHandle* h, const LvbFeature* d_msg, const int* d_msg_n,
   BeView v = make_beview(h);
   v.msg = d_msg; v.msg_n = d_msg_n; v.msg_t = d_msg_t; v.msg_valid = d_valid; v.msg_stride = msg_stride;
   LVB_PROF(h, "be_propagate_kernel");
-  if (be->LEG == 22) be_propagate_kernel<22><<<S, 256, sizeof(double) * (4 * 22 * 23 + 22), st>>>(v);
-  else be_propagate_kernel<46><<<S, 256, sizeof(double) * (4 * 46 * 47 + 46), st>>>(v);
+  if (be->LEG == 22) be_propagate_kernel<22><<<S, 256, be_propagate_smem(22), st>>>(v);
+  else be_propagate_kernel<46><<<S, 256, be_propagate_smem(46), st>>>(v);
   LVB_LAUNCH_CHECK(h);
   const int nthr = be->N <= 256 ? 256 : 512;
   LVB_PROF(h, "be_add_obs_kernel");

@@ -50,16 +50,8 @@ struct OrbArgs {
   int max_dist;
 };
 
-__global__ void __launch_bounds__(128) orb_kernel(OrbArgs a) {
-  const int s = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * 4 + warp;
-  if (i >= a.n_pts[s]) return;
-  const int slot = a.perm ? a.perm[(size_t)s * a.stride + i] : i;
-  const float2 pt = a.pts[(size_t)s * a.stride + slot];
-  const LvbLevel lv = a.L.lv[0];
-  const uint8_t* raw = lvb_level_origin(a.pyr, a.L, s, 0);
-  const uint8_t* blr = a.blur + (size_t)s * lv.w * lv.h;
+// angle + this lane's descriptor byte (8 pair tests) of one keypoint; all 32 lanes of the warp cooperate
+__device__ __forceinline__ unsigned orb_describe(const uint8_t* raw, const uint8_t* blr, const LvbLevel& lv, float2 pt, int lane, float* angle_out) {
   const int cx = __float2int_rn(pt.x), cy = __float2int_rn(pt.y);
   // ---- intensity centroid on the raw image
   int m10 = 0, m01 = 0;
@@ -101,6 +93,20 @@ __global__ void __launch_bounds__(128) orb_kernel(OrbArgs a) {
     }
     val |= (unsigned)(t[0] < t[1]) << k;
   }
+  if (angle_out) *angle_out = angle;
+  return val;
+}
+
+__global__ void __launch_bounds__(128) orb_kernel(OrbArgs a) {
+  const int s = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + warp;
+  if (i >= a.n_pts[s]) return;
+  const int slot = a.perm ? a.perm[(size_t)s * a.stride + i] : i;
+  const float2 pt = a.pts[(size_t)s * a.stride + slot];
+  const LvbLevel lv = a.L.lv[0];
+  float angle;
+  const unsigned val = orb_describe(lvb_level_origin(a.pyr, a.L, s, 0), a.blur + (size_t)s * lv.w * lv.h, lv, pt, lane, &angle);
   const size_t oi = (size_t)s * a.stride + i;
   if (a.desc_out) a.desc_out[(a.out_by_slot ? ((size_t)s * a.stride + slot) : oi) * 32 + lane] = (uint8_t)val;
   if (a.angles && lane == 0) a.angles[oi] = angle;
@@ -114,6 +120,41 @@ __global__ void __launch_bounds__(128) orb_kernel(OrbArgs a) {
       if (a.dist_out) a.dist_out[oi] = d;
     }
   }
+}
+
+// The descriptor gate of one frame in ONE launch (image_processor.cpp:436-462, 673-699, 904-930).  blockIdx.z = 0: tracked
+// features, descriptor at the current position against the one stored at birth (:807, kept forever).  blockIdx.z = 1: features
+// detected in the previous frame: descriptor in the previous image (kept as the birth descriptor) and in the current image,
+// compared with each other.
+struct OrbGateArgs {
+  const uint8_t* pyr_cur; const uint8_t* blur_cur; const uint8_t* pyr_prev; const uint8_t* blur_prev; LvbPyramidLayout L;
+  int stride; int max_dist;
+  const float2* cur_pts[2];     // [S][stride] by slot: tracked position in the current image, chain 0 / 1
+  const float2* new_prev_pts;   // [S][stride] by slot: where the new features were detected (previous image)
+  const int* perm[2]; const int* n_pts[2];
+  const uint8_t* birth_desc;    // [S][stride][32] by slot: descriptors of the tracked features
+  uint8_t* new_desc;            // [S][stride][32] by slot: birth descriptors of the new features (output)
+  uint8_t* status[2];           // [S][stride] by rank
+};
+__global__ void __launch_bounds__(128) orb_gate_kernel(const __grid_constant__ OrbGateArgs a) {
+  const int s = blockIdx.y, c = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + warp;
+  if (i >= a.n_pts[c][s]) return;
+  const size_t base = (size_t)s * a.stride;
+  const int slot = a.perm[c][base + i];
+  const LvbLevel lv = a.L.lv[0];
+  const unsigned vcur = orb_describe(lvb_level_origin(a.pyr_cur, a.L, s, 0), a.blur_cur + (size_t)s * lv.w * lv.h, lv, a.cur_pts[c][base + slot], lane, nullptr);
+  unsigned vref;
+  if (c == 0) vref = a.birth_desc[(base + slot) * 32 + lane];
+  else {
+    vref = orb_describe(lvb_level_origin(a.pyr_prev, a.L, s, 0), a.blur_prev + (size_t)s * lv.w * lv.h, lv, a.new_prev_pts[base + slot], lane, nullptr);
+    a.new_desc[(base + slot) * 32 + lane] = (uint8_t)vref;
+  }
+  int d = __popc(vcur ^ vref);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+  if (lane == 0) a.status[c][base + i] = d <= a.max_dist ? 1 : 0;
 }
 
 // ---------------------------------------------------------------- undistortPoints (App. A.7)
@@ -151,6 +192,19 @@ int fe_orb_launch(LvbHandle* h, const uint8_t* pyr, const uint8_t* blur, int n_s
   dim3 grd((stride + 3) / 4, n_seq);
   LVB_PROF(h, "orb_kernel");
   orb_kernel<<<grd, 128, 0, h->stream>>>(a);
+  LVB_LAUNCH_CHECK(h);
+  return LVB_OK;
+}
+
+int fe_orb_gate_launch(LvbHandle* h, const uint8_t* pyr_cur, const uint8_t* blur_cur, const uint8_t* pyr_prev, const uint8_t* blur_prev,
+                       int n_seq, int stride, const float2* const cur_pts[2], const float2* new_prev_pts, int* const perm[2],
+                       int* const n_pts[2], const uint8_t* birth_desc, uint8_t* new_desc, uint8_t* const status[2]) {
+  OrbGateArgs a;
+  a.pyr_cur = pyr_cur; a.blur_cur = blur_cur; a.pyr_prev = pyr_prev; a.blur_prev = blur_prev; a.L = h->fe.L; a.stride = stride; a.max_dist = 58;
+  for (int c = 0; c < 2; ++c) { a.cur_pts[c] = cur_pts[c]; a.perm[c] = perm[c]; a.n_pts[c] = n_pts[c]; a.status[c] = status[c]; }
+  a.new_prev_pts = new_prev_pts; a.birth_desc = birth_desc; a.new_desc = new_desc;
+  LVB_PROF(h, "orb_gate_kernel");
+  orb_gate_kernel<<<dim3((stride + 3) / 4, n_seq, 2), 128, 0, h->stream>>>(a);
   LVB_LAUNCH_CHECK(h);
   return LVB_OK;
 }

@@ -478,13 +478,9 @@ int fe_enqueue(LvbHandle* h, const uint8_t* d_images) {
   // backward LK (+ in-image + 1-px consistency gate)
   RC(fe_lk_launch2(h, fe.pyr[cur], fe.pyr[prv], S, N, cur2, perm2, n2, src, 1, nullptr, out2, st2, 2, src));
   RC(run_compaction(h, 1));
-  // descriptor gate: tracked features against the descriptor stored at birth, new ones prev vs curr
-  RC(fe_orb_launch(h, fe.pyr[cur], fe.blur[cur], S, N, fe.ch[0].slot_curr, fe.ch[0].perm, fe.ch[0].n, nullptr, nullptr, 0,
-                   fe.trk[prv].desc, fe.ch[0].status, nullptr));
-  RC(fe_orb_launch(h, fe.pyr[prv], fe.blur[prv], S, N, fe.new_pts, fe.ch[1].perm, fe.ch[1].n, nullptr, fe.ch[1].desc, 1,
-                   nullptr, nullptr, nullptr));
-  RC(fe_orb_launch(h, fe.pyr[cur], fe.blur[cur], S, N, fe.ch[1].slot_curr, fe.ch[1].perm, fe.ch[1].n, nullptr, nullptr, 0,
-                   fe.ch[1].desc, fe.ch[1].status, nullptr));
+  // descriptor gate: tracked features against the descriptor stored at birth, new ones prev vs curr (one launch)
+  RC(fe_orb_gate_launch(h, fe.pyr[cur], fe.blur[cur], fe.pyr[prv], fe.blur[prv], S, N, cur2, fe.new_pts, perm2, n2, fe.trk[prv].desc,
+                        fe.ch[1].desc, st2));
   RC(run_compaction(h, 2));
   // undistort to pixel coordinates + fundamental-matrix RANSAC: both chains in one launch, undistortion fused into its load
   {

@@ -280,12 +280,16 @@ __global__ void __launch_bounds__(256) ransac_kernel(const __grid_constant__ Ran
   double bestF[9];
   for (int q = 0; q < 9; ++q) bestF[q] = 0;
 
-  while (true) {
-    // ---- thread 0: next BATCH subsets from the RNG stream
+  // The adaptive iteration count collapses to a handful after the first good model (clean tracks: w ~ 0.95 -> ~4 iterations),
+  // so the first round draws and scores 8 hypotheses, later rounds 32 (over-drawing is harmless: a call owns its RNG).
+  for (int round = 0;; ++round) {
+    const int bsz = round == 0 ? 8 : BATCH;
+    // ---- thread 0: next bsz subsets from the RNG stream
     if (tid == 0) {
       Rng rng; rng.state = s_rng;
       const int max_attempts = lmeds ? 1000 : 10000;
-      for (int hb = 0; hb < BATCH; ++hb) {
+      for (int hb = bsz; hb < BATCH; ++hb) s_valid[hb] = 0;
+      for (int hb = 0; hb < bsz; ++hb) {
         bool found = false;
         int idx[7];
         for (int at = 0; at < max_attempts && !found; ++at) {
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(256) ransac_kernel(const __grid_constant__ Ran
         }
         s_valid[hb] = found;
         for (int i = 0; i < 7; ++i) s_idx[hb][i] = idx[i];
-        if (!found) { for (int h2 = hb + 1; h2 < BATCH; ++h2) s_valid[h2] = 0; break; }
+        if (!found) { for (int h2 = hb + 1; h2 < bsz; ++h2) s_valid[h2] = 0; break; }
       }
       s_rng = rng.state;
     }
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(256) ransac_kernel(const __grid_constant__ Ran
     }
     __syncthreads();
     // ---- all warps: score every (hypothesis, model)
-    for (int hm = warp; hm < BATCH * 3; hm += 8) {
+    for (int hm = warp; hm < bsz * 3; hm += 8) {
       const int hb = hm / 3, m = hm - hb * 3;
       if (m >= s_nmodels[hb]) { if (lane == 0) { s_good[hb][m] = -1; s_med[hb][m] = 0.f; } continue; }
       const double* F = &sF[hb][m][0];
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(256) ransac_kernel(const __grid_constant__ Ran
     if (tid == 0) {
       int iter = s_ctl[1], niters = s_ctl[2], max_good = s_ctl[3];
       int hb = 0;
-      for (; hb < BATCH && iter < niters; ++hb) {
+      for (; hb < bsz && iter < niters; ++hb) {
         if (!s_valid[hb]) { if (iter == 0) s_ctl[7] = 1; s_ctl[0] = 1; break; }
         for (int m = 0; m < s_nmodels[hb]; ++m) {
           if (!lmeds) {

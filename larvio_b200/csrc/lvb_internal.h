@@ -170,6 +170,9 @@ int fe_lk_launch2(LvbHandle* h, const uint8_t* pyrA, const uint8_t* pyrB, int n_
 int fe_orb_launch(LvbHandle* h, const uint8_t* pyr, const uint8_t* blur, int n_seq, int stride,
                   const float2* pts, const int* perm, const int* n_pts, float* angles, uint8_t* desc_out,
                   int out_by_slot, const uint8_t* desc_ref, uint8_t* status, int* dist_out);
+int fe_orb_gate_launch(LvbHandle* h, const uint8_t* pyr_cur, const uint8_t* blur_cur, const uint8_t* pyr_prev, const uint8_t* blur_prev,
+                       int n_seq, int stride, const float2* const cur_pts[2], const float2* new_prev_pts, int* const perm[2],
+                       int* const n_pts[2], const uint8_t* birth_desc, uint8_t* new_desc, uint8_t* const status[2]);
 int fe_undistort_launch(LvbHandle* h, int n_seq, int stride, const float2* pts, const int* perm,
                         const int* n_pts, float2* out, int to_pixels);
 int fe_detect_launch(LvbHandle* h, const uint8_t* pyr, int n_seq, const int* enable, int use_mask,
