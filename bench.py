@@ -268,23 +268,23 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- roofline models
 def kernel_models(S_sub, stats, n_frames, n_sub):
-    """ALGORITHMIC bytes (HBM-bound kernels) or FP64 flops per LAUNCH, DESIGN.md §4 / SURVEY.md §8(d):
-    per-unit figure x the units one launch processes.  `stats` are the device-side work counters of the profiled
-    frames summed over sub-batches (lvb_get_stats), so point/row counts are measured, not assumed.  A launch covers
-    one sub-batch of S_sub sequences; there are n_sub sub-batches and n_frames profiled frames."""
+    """ALGORITHMIC bytes (HBM-bound kernels) or FP64 flops per LAUNCH-SET (all launches of that kernel in one frame of one
+    sub-batch), DESIGN.md 4 / SURVEY.md 8(d): per-unit figure x the units processed.  `stats` are the device-side work counters of
+    the profiled frames summed over sub-batches (lvb_get_stats), so point/row counts are measured, not assumed.  The caller
+    divides by the measured number of launches per launch-set."""
     lk_pts, orb_desc, det_runs, msgs, upd, sum_r, sum_rdd, sum_rows, qr_runs, sum_rcc = [float(x) for x in stats[:10]]
+    sum_rncd = float(stats[15])
     nl = max(n_frames * n_sub, 1)          # launch-sets
     m = {}
     m["clahe_lut_kernel"] = ("hbm", B0 * S_sub, "read 752x480 u8 per sequence")
     m["clahe_apply_kernel"] = ("hbm", 2 * B0 * S_sub, "read + write 752x480 u8 per sequence")
-    m["pyrdown_kernel"] = ("hbm", (B0 + B0 // 4 + B0 // 4 + B0 // 16) // 2 * S_sub, "SURVEY F3 over its 2 launches")
+    m["pyrdown_kernel"] = ("hbm", (B0 + B0 // 4 + B0 // 4 + B0 // 16) * S_sub, "SURVEY F3: both levels")
     m["blur7_kernel"] = ("hbm", 2 * B0 * S_sub, "SURVEY F4")
-    m["mineig_kernel"] = ("hbm", B0 * det_runs / nl, "SURVEY F5 pass 1: read 752x480 u8 of the sequences that detect")
-    m["candidates_kernel"] = ("hbm", B0 * det_runs / nl, "SURVEY F5 pass 2: one more pass over 752x480 per detecting sequence")
-    m["lk_kernel"] = ("hbm", 6060.0 * lk_pts / (2 * nl), "6060 B per point-track (SURVEY F6), 2 launches per frame")
-    m["orb_kernel"] = ("hbm", 2986.0 * orb_desc / (3 * nl), "2986 B per descriptor (SURVEY F7), 3 launches per frame")
-    m["be_gemm_kernel"] = ("fp64", (4.0 * sum_rdd / (6 * nl)) if upd else None, "T=HP and P-=Y^TY: 2rd^2 each (S=TH^T not counted), 6 launches per frame")
-    m["be_qr_kernel"] = ("fp64", (2.0 * sum_rcc / (2 * nl)) if qr_runs else None, "2Rc^2 per compression, 2 launches per frame")
+    m["corner_kernel"] = ("hbm", B0 * det_runs / nl, "SURVEY F5: one pass over 752x480 u8 of the sequences that detect")
+    m["lk_kernel"] = ("hbm", 6060.0 * lk_pts / nl, "6060 B per point-track (SURVEY F6)")
+    m["orb_gate_kernel"] = ("hbm", 2986.0 * orb_desc / nl, "2986 B per descriptor (SURVEY F7)")
+    m["be_gemm_kernel"] = ("fp64", ((2.0 * sum_rncd + 2.0 * sum_rdd) / nl) if upd else None, "T = H P over the nonzero columns (2 r nc d) + P -= Y^T Y (2 r d^2); S = T H^T not counted")
+    m["be_qr_kernel"] = ("fp64", (2.0 * sum_rcc / nl) if qr_runs else None, "2 R nc^2 per compression")
     return m
 
 
@@ -548,7 +548,7 @@ def main():
         tot = sum(v[0] for v in prof.values()) or 1.0
         top = sorted(prof.items(), key=lambda kv: -kv[1][0]) or [("none", (0.0, 0))]
         kernel_share = {kname: dict(ms_per_launch=v[0] / max(v[1], 1), launches=v[1], share=v[0] / tot) for kname, v in top}
-        dom, (dom_ms, dom_n) = top[0]
+        dom_by_time = top[0][0]
         pstats = [sum(x) for x in zip(*prof_stats)] if prof_stats else [0] * 16
         if pstats[4]:
             steady.update(mean_update_rows_r=pstats[5] / pstats[4], mean_stacked_rows=pstats[7] / pstats[4], qr_runs_per_update=pstats[8] / pstats[4])
@@ -562,14 +562,18 @@ def main():
             if not mdl or not mdl[1]:
                 continue
             per_launch_ms = v[0] / max(v[1], 1)
+            per_launch = mdl[1] * (args.profile_steps * NSUB) / max(v[1], 1)      # launch-set figure / launches per launch-set
             if mdl[0] == "hbm":
-                ach = mdl[1] / (per_launch_ms * 1e-3) / 1e9
-                roofs[kname] = dict(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, algorithmic_bytes_per_launch=mdl[1], basis=mdl[2])
+                ach = per_launch / (per_launch_ms * 1e-3) / 1e9
+                roofs[kname] = dict(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, algorithmic_bytes_per_launch=per_launch, basis=mdl[2])
             else:
-                ach = mdl[1] / (per_launch_ms * 1e-3) / 1e12
-                roofs[kname] = dict(bound="fp64", achieved=ach, peak=FP64_PEAK_TF, unit="TFLOP/s", frac=ach / FP64_PEAK_TF, flops_per_launch=mdl[1], basis=mdl[2])
+                ach = per_launch / (per_launch_ms * 1e-3) / 1e12
+                roofs[kname] = dict(bound="fp64", achieved=ach, peak=FP64_PEAK_TF, unit="TFLOP/s", frac=ach / FP64_PEAK_TF, flops_per_launch=per_launch, basis=mdl[2])
+        # the roofline object describes the most expensive kernel that has a byte / flop model (per-sequence latency kernels such as
+        # the RANSAC replay have no meaningful one); `dominant_by_time` names the top kernel by device time whatever it is
+        dom, (dom_ms, dom_n) = next(((kname, v) for kname, v in top if kname in roofs), top[0])
         ncu_traffic, ncu_src = load_ncu_traffic()
-        roof = dict(kernel=dom, bound="hbm", achieved=None, peak=hbm_peak, unit="GB/s", frac=None, traffic=(ncu_traffic[dom] * (S // NSUB) if dom in ncu_traffic else None),
+        roof = dict(kernel=dom, dominant_by_time=dom_by_time, bound="hbm", achieved=None, peak=hbm_peak, unit="GB/s", frac=None, traffic=(ncu_traffic[dom] * (S // NSUB) if dom in ncu_traffic else None),
                     traffic_source=("%s (ncu --set full, cold cache, per launch, scaled to the sequences of one launch)" % ncu_src) if ncu_src else None, peak_source=peak_src,
                     ms_per_launch=dom_ms / max(dom_n, 1))
         if dom in roofs:

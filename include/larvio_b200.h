@@ -210,7 +210,8 @@ int lvb_profile_get(LvbHandle* h, const char** names, double* total_ms, long lon
  * [3] published messages, [4] EKF updates, [5] sum r, [6] sum r*d*d, [7] sum stacked rows, [8] QR runs, [9] sum R*c*c,
  * [10] LK iterations, [11] LK iterations on the chain-replay (slow) path, [12] LK window set-ups on the slow path, [13] LK search
  * tile re-stages, [14] findFundamentalMat calls with 8..13 points (OpenCV switches to LMedS below 15 points and its winner is
- * then decided by rounding noise: the one front-end regime where the inlier mask is not reproducible). */
+ * then decided by rounding noise: the one front-end regime where the inlier mask is not reproducible),
+ * [15] sum r*nc*d (nc = nonzero columns of the stacked Jacobian: the flops of T = H P are 2 r nc d). */
 int lvb_get_stats(LvbHandle* h, unsigned long long* out16);
 
 /* debug: the 32 per-sequence integers of the filter (dimension, window size, SLAM feature count, flags ...). */

@@ -60,11 +60,13 @@ __device__ __forceinline__ M3 imu_selector(int kind, V3 x) {
 // per-sample record left by the sequential nominal-state pass for the parallel construction of Phi_k
 enum { R_DT = 0, R_Q = 1, R_VEL = 5, R_POS = 8, R_VNEW = 11, R_PNEW = 14, R_FOV = 17, R_FOP = 20, R_FNV = 23, R_FNP = 26,
        R_GYRO = 29, R_ACC = 32, R_GYRO_OLD = 35, R_ACC_OLD = 38, PROP_REC = 42 };
-template <int L> struct PropChunk { static constexpr int N = (L <= 22) ? 8 : 2; };   // samples whose Phi is built concurrently
+template <int L> struct PropChunk { static constexpr int N = (L <= 22) ? 8 : 4; };   // samples whose Phi is built concurrently
 
 // calPhi (larvio.cpp:3475-3800) for one IMU sample from its record: fills Phi (L x L, row pitch L + 1).
+// role 0 writes the 15-column core blocks, roles 1..8 (L = 46 only) one group of three IMU-intrinsic columns each; the caller has
+// set Phi to the identity.
 template <int L>
-__device__ void prop_build_phi(const double* rec, const double* core, bool fej, double* Phi_) {
+__device__ void prop_build_phi(const double* rec, const double* core, bool fej, double* Phi_, int role) {
   constexpr int LP = L + 1;
 #define Phi(r, c) Phi_[(r) * LP + (c)]
   const double dtime = rec[R_DT];
@@ -85,10 +87,10 @@ __device__ void prop_build_phi(const double* rec, const double* core, bool fej, 
   V3 vk, pk, vk1, pk1;
   if (fej) { vk = ld3(rec + R_FOV); pk = ld3(rec + R_FOP); vk1 = ld3(rec + R_FNV); pk1 = ld3(rec + R_FNP); }
   else { vk = vel; pk = pos; vk1 = vnew; pk1 = pnew; }
-  for (int r = 0; r < L; ++r) for (int c = 0; c < L; ++c) Phi(r, c) = (r == c) ? 1.0 : 0.0;
   const M3 I3 = m3_identity();
-  const M3 twoIAh = m3_add(m3_scale(I3, 2.0), Ah);
   const M3 TA = m3_mul(Tg, As), TAM = m3_mul(TA, Ma);
+  if (role == 0) {
+  const M3 twoIAh = m3_add(m3_scale(I3, 2.0), Ah);
   const M3 CtA = m3_scale(m3_mul(C, twoIAh), 0.5 * dtime);       // 0.5*C*(2I+Ah)*dtime
   const M3 Pqbg = m3_scale(m3_mul(CtA, Tg), -1.0);
   const M3 Pqba = m3_mul(CtA, TAM);
@@ -112,14 +114,17 @@ __device__ void prop_build_phi(const double* rec, const double* core, bool fej, 
       Phi(6 + r, 9 + c) = Ppbg.m[r * 3 + c];
       Phi(6 + r, 12 + c) = Ppba.m[r * 3 + c];
     }
+  }
   if constexpr (L > 22) {
+    if (role == 0) return;
     // ---- IMU-intrinsic columns (:3532-3797): 8 groups of 3 columns; selectors Lo/Di/Up place the components of
     // (w | acc | f) sampled at k, k+1/2, k+1; Simpson weights for q, the reference's RK4 weights for v and p
     const V3 f_mid = (f + f_old) * 0.5, acc_mid = (acc + acc_old) * 0.5;
     const V3 w_mid = (w_old + w) * 0.5 + cross(w_old, w) * (dtime / 12);
     const M3 R_mid = m3_add(I3, m3_scale(Ah, 0.5)), R_kp1 = m3_add(I3, Ah);
     const M3 S_mid = m3_scale(skew(m3_vec(R_mid, acc_mid)), dtime * 0.5), S_kp1 = skew(m3_vec(R_kp1, acc));
-    for (int gi = 0; gi < 8; ++gi) {
+    {
+      const int gi = role - 1;
       const int kind = (gi < 6) ? gi % 3 : gi - 6;                 // 0 Lo, 1 Di, 2 Up
       const V3 xk = gi < 3 ? w_old : (gi < 6 ? acc_old : f_old);
       const V3 xh = gi < 3 ? w_mid : (gi < 6 ? acc_mid : f_mid);
@@ -277,8 +282,19 @@ __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
     }
     __syncthreads();
     const int nact = s_nact;
-    // ---- phase 2: Phi_k of every sample of the chunk, one thread each
-    if (tid < nact) prop_build_phi<L>(rec_ + tid * PROP_REC, core, fej, PhiC_ + (size_t)tid * L * LP);
+    // ---- phase 2: Phi_k of every sample of the chunk: identity by all threads, then one thread per (sample, column group)
+    for (int i = tid; i < nact * L * L; i += blockDim.x) {
+      const int a = i / (L * L), e = i - a * (L * L), r = e / L, c = e - r * L;
+      PhiC_[(size_t)a * L * LP + r * LP + c] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    {
+      constexpr int NROLE = (L > 22) ? 9 : 1;
+      if (tid < nact * NROLE) {
+        const int a = tid / NROLE, role = tid - a * NROLE;
+        prop_build_phi<L>(rec_ + a * PROP_REC, core, fej, PhiC_ + (size_t)a * L * LP, role);
+      }
+    }
     __syncthreads();
     // ---- phase 3: covariance recursion, sample by sample
     for (int a = 0; a < nact; ++a) {
@@ -339,7 +355,7 @@ __global__ void __launch_bounds__(256) be_propagate_kernel(BeView v) {
 }
 
 static size_t be_propagate_smem(int L) {       // PhiC[CHK] + PLL + Tmp + PhiTot ([L][L+1] each) + Ddiag[L] + rec[CHK][PROP_REC]
-  const int chk = (L <= 22) ? 8 : 2;
+  const int chk = (L <= 22) ? 8 : 4;
   return sizeof(double) * ((size_t)(chk + 3) * L * (L + 1) + L + (size_t)chk * PROP_REC);
 }
 
@@ -1171,6 +1187,49 @@ __global__ void __launch_bounds__(512) be_stack_kernel(BeView v, int phase) {
   double* Hs = v.be.Hs + (size_t)s * LD * RMAX;
   double* rs = v.be.rs + (size_t)s * RMAX;
   const int warp = tid >> 5, lane = tid & 31;
+  if (phase == 0) {
+    // MSCKF blocks are structurally sparse (columns 15..21 + the pose blocks of the observing window slots): clear the rows
+    // (coalesced along the column-major stack), scatter only each block's own columns, and derive the list of nonzero
+    // columns (kmap, I_NC) from the union of the slot masks - a superset of the numerically nonzero columns, which is all
+    // the compression and the update need (be_colscan_kernel does the same from the data where rows of other kinds are stacked).
+    __shared__ unsigned long long s_um;
+    if (tid == 0) s_um = 0ull;
+    const int nclr = min(total, cap);
+    for (int c = warp; c < d; c += 16) { double* cj = Hs + (size_t)c * RMAX; for (int r = lane; r < nclr; r += 32) cj[r] = 0.0; }
+    __syncthreads();
+    unsigned long long um_loc = 0ull;
+    for (int i = warp; i < T; i += 16) {
+      const int a = rows_of(i);
+      if (!a) continue;
+      const size_t fi = (size_t)s * T + i;
+      const int dst = v.be.ft_nrows[fi];
+      if (dst + a > cap) continue;
+      const unsigned long long um = v.be.ft_usemask[fi];
+      um_loc |= um;
+      const int nz = 7 + 6 * __popcll(um);
+      const int first = v.be.ft_rowofs[fi] + 3;                 // skip the 3 rows that carry H_f
+      const double* H = v.be.Hraw + ((size_t)s * v.be.RAWMAX + first) * LD;
+      const double* rr = v.be.rraw + (size_t)s * v.be.RAWMAX + first;
+      for (int e = lane; e < a * nz; e += 32) {
+        const int row = e / nz, j = e - row * nz;
+        const int col = (j < 7) ? 15 + j : LEGD + 6 * nth_set_bit(um, (j - 7) / 6) + ((j - 7) % 6);
+        Hs[(size_t)col * RMAX + dst + row] = H[(size_t)row * LD + col];
+      }
+      for (int e = lane; e < a; e += 32) rs[dst + e] = rr[e];
+    }
+    if (lane == 0 && um_loc) atomicOr(&s_um, um_loc);
+    __syncthreads();
+    if (tid == 0) {
+      int* km = v.be.kmap + (size_t)s * LD;
+      int nc = 0;
+      const unsigned long long um = s_um;
+      if (total > 0) {
+        for (int j = 0; j < 7; ++j) km[nc++] = 15 + j;
+        for (int w = 0; w < 64; ++w) if ((um >> w) & 1ull) for (int c = 0; c < 6; ++c) km[nc++] = LEGD + 6 * w + c;
+      }
+      ic[I_NC] = nc;
+    }
+  } else {
   for (int i = warp; i < T; i += 16) {
     const int a = rows_of(i);
     if (!a) continue;
@@ -1190,6 +1249,7 @@ __global__ void __launch_bounds__(512) be_stack_kernel(BeView v, int phase) {
       Hs[(size_t)col * RMAX + dst + row] = H[(size_t)row * LD + col];
     }
     for (int e = lane; e < a; e += 32) rs[dst + e] = rr[e];
+  }
   }
   if (tid == 0) {
     if (phase == 0) { ic[I_ROWS] = total; ic[I_R] = total; }
@@ -1492,12 +1552,13 @@ __global__ void __launch_bounds__(1024) be_chol_kernel(BeView v) {
   int* ic = icore_of(v, s);
   if (!ic[I_OK]) return;
   const int r = ic[I_R];
-  if (r <= 0 || r > v.be.Dmax) return;          // larger systems (hybrid mode) go through be_chol_gmem_kernel
+  const int RC = v.be.chol_cap;
+  if (r <= 0 || r > RC) return;                  // larger systems go through be_chol_gmem_kernel
   const int LD = v.be.LDS;
   double* S = v.be.Sm + (size_t)s * LD * LD;
   double* Lp = csm;
-  double* col = csm + (size_t)v.be.Dmax * (v.be.Dmax + 1) / 2;
-  double* z = col + v.be.Dmax;
+  double* col = csm + (size_t)RC * (RC + 1) / 2;
+  double* z = col + RC;
 #define LP(i, j) Lp[(size_t)(i) * ((i) + 1) / 2 + (j)]
   for (int e = tid; e < r * r; e += 1024) { const int i = e / r, j = e - i * r; if (j <= i) LP(i, j) = S[(size_t)i * LD + j]; }
   __syncthreads();
@@ -1678,6 +1739,7 @@ __global__ void __launch_bounds__(256) be_correct_kernel(BeView v) {
     if (v.be.stats) {
       atomicAdd(&v.be.stats[4], 1ull); atomicAdd(&v.be.stats[5], (unsigned long long)r);
       atomicAdd(&v.be.stats[6], (unsigned long long)r * d * d); atomicAdd(&v.be.stats[7], (unsigned long long)ic[I_ROWS]);
+      atomicAdd(&v.be.stats[15], (unsigned long long)r * ic[I_NC] * d);
     }
   }
   __syncthreads();
@@ -2019,21 +2081,43 @@ __device__ inline void pts_put(const BeView& v, int which, int s, unsigned long 
   pos[k * 3] = xyz[0]; pos[k * 3 + 1] = xyz[1]; pos[k * 3 + 2] = xyz[2];
 }
 
-// end of processFeatures: shrink dims after pruning, FEJ switch (:414-419), active map points (:455-458)
-__global__ void be_frame_end_kernel(BeView v) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= v.be.S) return;
+// end of processFeatures: shrink dims after pruning, FEJ switch (:414-419), active map points (:455-458).  One warp per
+// sequence: lane 0 does the scalar bookkeeping, the id search of the map-point upsert runs across the lanes.
+__global__ void __launch_bounds__(32) be_frame_end_kernel(BeView v) {
+  const int s = blockIdx.x, lane = threadIdx.x;
   int* ic = icore_of(v, s);
   if (!ic[I_OK]) return;
-  if (ic[I_DO_PRUNE]) { ic[I_DIM] -= 6 * ic[I_NRM]; ic[I_NWIN] -= ic[I_NRM]; }
-  const double* core = core_of(v, s);
-  if (v.cfg.if_FEJ_config && !ic[I_FEJ] && core[C_TIME] - core[C_TAKEOFF] >= 0) ic[I_FEJ] = 1;
-  if (v.be.PCAP > 0) {
+  const int nf = ic[I_NF];
+  __syncwarp();
+  if (lane == 0) {
+    if (ic[I_DO_PRUNE]) { ic[I_DIM] -= 6 * ic[I_NRM]; ic[I_NWIN] -= ic[I_NRM]; }
+    const double* core = core_of(v, s);
+    if (v.cfg.if_FEJ_config && !ic[I_FEJ] && core[C_TIME] - core[C_TAKEOFF] >= 0) ic[I_FEJ] = 1;
+  }
+  if (v.be.PCAP > 0 && nf > 0) {
+    const int cap = v.be.PCAP;
+    const size_t b = (size_t)1 * v.be.S + s;                      // list 1: active map points
+    unsigned long long* ids = v.be.pts_id + b * cap;
+    double* pos = v.be.pts_xyz + b * cap * 3;
     const int* fs = v.be.fs_slot + (size_t)s * 64;
-    for (int i = 0; i < ic[I_NF]; ++i) {
+    int n = v.be.pts_n[b];
+    for (int i = 0; i < nf; ++i) {
       const size_t fi = (size_t)s * v.be.T + fs[i];
-      pts_put(v, 1, s, v.be.ft_id[fi], v.be.ft_pos + fi * 3);
+      const unsigned long long id = v.be.ft_id[fi];
+      int k = -1;
+      for (int k0 = 0; k0 < n && k < 0; k0 += 32) {
+        const unsigned hit = __ballot_sync(0xffffffffu, k0 + lane < n && ids[k0 + lane] == id);
+        if (hit) k = k0 + __ffs(hit) - 1;
+      }
+      if (k < 0) {
+        if (n >= cap) { if (lane == 0) v.be.pts_drop[b] += 1; continue; }
+        k = n++;
+        if (lane == 0) ids[k] = id;
+      }
+      if (lane < 3) pos[k * 3 + lane] = v.be.ft_pos[fi * 3 + lane];
+      __syncwarp();
     }
+    if (lane == 0) v.be.pts_n[b] = n;
   }
 }
 
@@ -2338,8 +2422,10 @@ int be_alloc(LvbHandle* h) {
   LVB_CUDA(cudaFuncSetAttribute(be_propagate_kernel<22>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be_propagate_smem(22)));
   LVB_CUDA(cudaFuncSetAttribute(be_propagate_kernel<46>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be_propagate_smem(46)));
   if (be->NFmax > 0) LVB_CUDA(cudaFuncSetAttribute(be_slam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 64 * be->LD)));
-  const size_t chol_bytes = sizeof(double) * ((size_t)be->Dmax * (be->Dmax + 1) / 2 + 2 * be->Dmax);
-  if (chol_bytes <= 227 * 1024) LVB_CUDA(cudaFuncSetAttribute(be_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_bytes));
+  // with the nonzero-column compression r stays near 50..110 rows whatever the window; 192 rows of packed triangle = 148 KB
+  be->chol_cap = be->LDS < 192 ? be->LDS : 192;
+  const size_t chol_bytes = sizeof(double) * ((size_t)be->chol_cap * (be->chol_cap + 1) / 2 + 2 * be->chol_cap);
+  LVB_CUDA(cudaFuncSetAttribute(be_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_bytes));
   h->use_graph = getenv("LVB_NO_GRAPH") ? 0 : 1;          // one CUDA graph launch per step (lvb_step_graph); the env switch is for debugging
   return LVB_OK;
 }
@@ -2371,8 +2457,7 @@ static int be_colscan(LvbHandle* h, BeView& v, int rows_idx) {
   return LVB_OK;
 }
 
-static int be_qr(LvbHandle* h, BeView& v) {
-  RC(be_colscan(h, v, I_ROWS));
+static int be_qr(LvbHandle* h, BeView& v) {       // kmap / I_NC of the MSCKF block come from be_stack_kernel(phase 0)
   LVB_PROF(h, "be_qr_kernel");
   be_qr_kernel<<<h->be->S, 512, sizeof(double) * h->be->RMAX, h->stream>>>(v);
   LVB_LAUNCH_CHECK(h);
@@ -2403,17 +2488,14 @@ static int be_update(LvbHandle* h, BeView& v, bool zupt_rows = false, bool resca
   if (zupt_rows) g.diag_vec = be->dx;
   RC(launch_gemm(h, g, be->LDS, be->LDS));
   g.diag_vec = nullptr;
-  const size_t chol_bytes = sizeof(double) * ((size_t)be->Dmax * (be->Dmax + 1) / 2 + 2 * be->Dmax);
-  const bool smem_ok = chol_bytes <= 227 * 1024;
-  if (smem_ok) {
-    LVB_PROF(h, "be_chol_kernel");
-    be_chol_kernel<<<be->S, 1024, chol_bytes, st>>>(v);
-    LVB_LAUNCH_CHECK(h);
-    DBG("be_chol_kernel");
-  }
-  if (!smem_ok || be->NFmax > 0) {               // systems larger than the packed-smem capacity (hybrid mode, big windows)
+  const size_t chol_bytes = sizeof(double) * ((size_t)be->chol_cap * (be->chol_cap + 1) / 2 + 2 * be->chol_cap);
+  LVB_PROF(h, "be_chol_kernel");
+  be_chol_kernel<<<be->S, 1024, chol_bytes, st>>>(v);
+  LVB_LAUNCH_CHECK(h);
+  DBG("be_chol_kernel");
+  if (be->LDS > be->chol_cap) {                  // innovation systems beyond the shared-memory capacity (rare: > 192 rows)
     LVB_PROF(h, "be_chol_gmem_kernel");
-    be_chol_gmem_kernel<<<be->S, 512, sizeof(double) * be->LDS, st>>>(v, smem_ok ? be->Dmax : 0);
+    be_chol_gmem_kernel<<<be->S, 512, sizeof(double) * be->LDS, st>>>(v, be->chol_cap);
     LVB_LAUNCH_CHECK(h);
     DBG("be_chol_gmem_kernel");
   }
@@ -2645,7 +2727,7 @@ static int be_enqueue(LvbHandle* h, const LvbFeature* d_msg, const int* d_msg_n,
   be_prune_cov_scatter_kernel<<<dim3(be->Dmax, S), 256, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
   LVB_PROF(h, "be_frame_end_kernel");
-  be_frame_end_kernel<<<(S + 63) / 64, 64, 0, st>>>(v);
+  be_frame_end_kernel<<<S, 32, 0, st>>>(v);
   LVB_LAUNCH_CHECK(h);
   LVB_CUDA(cudaMemcpyAsync(be->pin_icore, be->icore, sizeof(int) * (size_t)S * BE_ICORE, cudaMemcpyDeviceToHost, st));
   return LVB_OK;

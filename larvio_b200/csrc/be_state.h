@@ -35,6 +35,7 @@ struct LvbBackEnd {
   int RAWMAX;          // raw (unprojected) Jacobian rows per sequence per pass
   int RMAX;            // stacked (projected, gated) rows per sequence per pass
   int imu_cap;         // IMU samples per sequence per call
+  int chol_cap;        // largest innovation system factorised out of shared memory (packed triangle); larger ones use the global-memory kernel
   int NFmax;           // EKF-SLAM feature capacity (max_features_in_one_grid * grid cells), 0 = pure MSCKF
   int LDS;             // leading dimension of Sm (rows of the stacked H_o can exceed the state dimension in hybrid mode)
   int grid_rows, grid_cols, max_per_cell;
