@@ -30,7 +30,7 @@ struct BeCfg {
   double sg2, sa2, sbg2, sba2, sfeat2;
   double rot_thr, trans_thr, track_thr, feat_trans_thr, zupt_dis, zupt_nv, zupt_np, zupt_nq;
   int max_track_len, sw_size, least_obs, if_FEJ_config, estimate_td, if_ZUPT_valid;
-  int hybrid;                 // EKF-SLAM features enabled (1-D inverse depth)
+  int hybrid;                 // EKF-SLAM features enabled (1-D or 3-D inverse depth: v.be.IDP)
   double x_min, y_min, grid_w, grid_h;
 };
 
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(256) be_augment_kernel(BeView v) {
     // SLAM-feature columns follow the pose block: the new pose is INSERTED before them (larvio.cpp:768-793).
     // P_aug[i][j] = P[m(i)][m(j)] with m = identity / selection rows / shifted feature indices -> generic re-map.
     int* cm = v.be.cmap + (size_t)s * LD;
-    const int pe = d - nf;
+    const int pe = d - v.be.IDP * nf;
     for (int i = tid; i < d + 6; i += blockDim.x) cm[i] = (i < pe) ? i : (i < pe + 6 ? sel[i - pe] : i - 6);
     __syncthreads();
     if (tid == 0) { ic[I_REMAP] = 1; ic[I_NEWDIM] = d + 6; ic[I_NWIN] = n_win + 1; }
@@ -817,10 +817,11 @@ __global__ void __launch_bounds__(512) be_scan_rows_kernel(BeView v, int which /
 
 namespace {
 
-// ---------------------------------------------------------------- measurementJacobian_ekf_1didp (:1117-1244)
-// Observation of an EKF-SLAM feature (1-D inverse depth in its anchor camera) from window slot ws.
-struct Jac1d { double hf[2], ha[2][6], hx[2][6], he[2][6], r[2]; };
-__device__ void meas_jac_1didp(const BeView& v, int s, size_t fi, int ws, bool fej, Jac1d& J) {
+// ---------------------------------------------------------------- measurementJacobian_ekf_1didp (:1117-1244) / _3didp (:984-1114)
+// Observation of an EKF-SLAM feature (inverse depth, or (x/z, y/z, 1/z), in its anchor camera) from window slot ws.
+// hf[a][0..IDP-1] are the feature's own columns.
+struct Jac1d { double hf[2][3], ha[2][6], hx[2][6], he[2][6], r[2]; };
+__device__ void meas_jac_idp(const BeView& v, int s, size_t fi, int ws, bool fej, Jac1d& J) {
   const int Wcap = v.be.Wcap;
   const double* wk = win_of(v, s, ws);
   const int as = v.be.ft_anchor[fi];
@@ -854,10 +855,29 @@ __device__ void meas_jac_1didp(const BeView& v, int s, size_t fi, int ws, bool f
   const M3 Mx = m3_mul(Rka, skew(m3_tvec(R_b2c, p_ca)));
   const M3 Je_l = m3_mul(R_b2c, m3_sub(Sk, Mx));
   const M3 Je_r = m3_mul(R_b2c, m3_sub(Rka, m3_identity()));
+  if (v.be.IDP == 3) {
+    if (ws == as) {                                                   // the anchor's own observation (:1065-1073)
+      for (int a = 0; a < 2; ++a) {
+        for (int c = 0; c < 3; ++c) J.hf[a][c] = (a == c) ? 1.0 : 0.0;
+        for (int c = 0; c < 6; ++c) { J.ha[a][c] = 0.0; J.hx[a][c] = 0.0; J.he[a][c] = 0.0; }
+      }
+      return;
+    }
+    // H_f = J_k * (R_w2ck R_w2ca^T) * J_f,  J_f = d(p_ca)/d(invParam) = [I | -f0/f2, -f1/f2, -1/f2] / f2
+    const M3 Jp = m3_mul(R_w2ck, m3_t(R_w2ca));
+    const double f0 = f_an.x, f1 = f_an.y, f2 = inv;
+    double Jf[3][3] = {{1.0, 0.0, -f0 / f2}, {0.0, 1.0, -f1 / f2}, {0.0, 0.0, -1.0 / f2}};
+    for (int i = 0; i < 3; ++i) for (int c = 0; c < 3; ++c) Jf[i][c] = Jf[i][c] / f2;
+    for (int a = 0; a < 2; ++a) {
+      double kp[3];
+      for (int c = 0; c < 3; ++c) kp[c] = Jk[a][0] * Jp.m[c] + Jk[a][1] * Jp.m[3 + c] + Jk[a][2] * Jp.m[6 + c];
+      for (int c = 0; c < 3; ++c) J.hf[a][c] = kp[0] * Jf[0][c] + kp[1] * Jf[1][c] + kp[2] * Jf[2][c];
+    }
+  }
   const double J_rho = -1.0 / (inv * inv);
   const double jd[3] = {J_d.x, J_d.y, J_d.z};
   for (int a = 0; a < 2; ++a) {
-    J.hf[a] = (Jk[a][0] * jd[0] + Jk[a][1] * jd[1] + Jk[a][2] * jd[2]) * J_rho;
+    if (v.be.IDP == 1) { J.hf[a][0] = (Jk[a][0] * jd[0] + Jk[a][1] * jd[1] + Jk[a][2] * jd[2]) * J_rho; J.hf[a][1] = 0.0; J.hf[a][2] = 0.0; }
     for (int c = 0; c < 3; ++c) {
       double xa = 0, xr = 0, kl = 0, kr = 0, el = 0, er = 0;
       for (int q = 0; q < 3; ++q) {
@@ -941,6 +961,50 @@ __device__ bool gate_block(const BeView& v, const double* P, int LD, const doubl
   return gamma < c_chi2[R];
 }
 
+// ncf Householder reflections that triangularise Hf [nrows][ncf] (a feature's own columns), applied to the listed nonzero
+// columns of the block H and to its residual: afterwards rows ncf.. of (H, rr) are the projection onto the left null space of
+// Hf and rows 0..ncf-1 carry its column space, with the triangular factor (LAPACK sign convention) left in Hf.
+__device__ void reflect_block(double* Hf, int ncf, double* H, double* rr, int nrows, int LD, const int* nzl, int nz, double* vv, int lane) {
+  for (int k = 0; k < ncf; ++k) {
+    double nrm = 0.0;
+    for (int i = k + lane; i < nrows; i += 32) { const double x = Hf[i * ncf + k]; nrm += x * x; }
+    nrm = sqrt(warp_sum_d(nrm));
+    const double x0 = Hf[k * ncf + k];
+    const double alpha = x0 >= 0 ? -nrm : nrm;
+    for (int i = k + lane; i < nrows; i += 32) vv[i] = Hf[i * ncf + k] - (i == k ? alpha : 0.0);
+    __syncwarp();
+    double vtv = 0.0;
+    for (int i = k + lane; i < nrows; i += 32) vtv += vv[i] * vv[i];
+    vtv = warp_sum_d(vtv);
+    if (vtv > 0.0) {
+      const double beta = 2.0 / vtv;
+      for (int c = k; c < ncf; ++c) {
+        double dt_ = 0.0;
+        for (int i = k + lane; i < nrows; i += 32) dt_ += vv[i] * Hf[i * ncf + c];
+        dt_ = warp_sum_d(dt_) * beta;
+        for (int i = k + lane; i < nrows; i += 32) Hf[i * ncf + c] -= dt_ * vv[i];
+      }
+      for (int j = lane; j < nz + 1; j += 32) {
+        if (j < nz) {
+          const int c = nzl[j];
+          double dt_ = 0.0;
+          for (int i = k; i < nrows; ++i) dt_ += vv[i] * H[(size_t)i * LD + c];
+          dt_ *= beta;
+          for (int i = k; i < nrows; ++i) H[(size_t)i * LD + c] -= dt_ * vv[i];
+        } else {
+          double dt_ = 0.0;
+          for (int i = k; i < nrows; ++i) dt_ += vv[i] * rr[i];
+          dt_ *= beta;
+          for (int i = k; i < nrows; ++i) rr[i] -= dt_ * vv[i];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) Hf[k * ncf + k] = alpha;           // the exact diagonal of the triangular factor
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(32) be_feature_kernel(BeView v, double* Traw) {
   extern __shared__ double fsm[];
   const int s = blockIdx.y, slot = blockIdx.x, lane = threadIdx.x;
@@ -972,26 +1036,30 @@ __global__ void __launch_bounds__(32) be_feature_kernel(BeView v, double* Traw) 
     // ---- featureJacobian_ekf (:1341-1417): 2 rows, gate with dof 2 (:2133-2143)
     const int cur = n_win - 1;
     const int as = v.be.ft_anchor[fi];
+    const int idp = v.be.IDP;
     int fidx = -1;
     const int* fs = v.be.fs_slot + (size_t)s * 64;
-    for (int i = 0; i < ic[I_NF]; ++i) if (fs[i] == slot) fidx = LEGD + 6 * n_win + i;
-    if (lane == 0) {
+    for (int i = 0; i < ic[I_NF]; ++i) if (fs[i] == slot) fidx = LEGD + 6 * n_win + idp * i;
+    int nz4 = 0;
+    if (lane == 0 && fidx >= 0) {
       Jac1d J;
-      meas_jac_1didp(v, s, fi, cur, fej, J);
+      meas_jac_idp(v, s, fi, cur, fej, J);
       for (int a = 0; a < 2; ++a) {
         double* row = H + (size_t)a * LD;
         for (int c = 0; c < 6; ++c) { row[LEGD + 6 * as + c] = J.ha[a][c]; row[15 + c] = J.he[a][c]; }
         for (int c = 0; c < 6; ++c) row[LEGD + 6 * cur + c] = J.hx[a][c];
-        row[fidx] = J.hf[a];
+        for (int q = 0; q < idp; ++q) row[fidx + q] = J.hf[a][q];
         if (v.cfg.estimate_td) row[21] = obs[(size_t)cur * 4 + 2 + a];
         rr[a] = J.r[a];
       }
-      for (int j = 0; j < 7; ++j) nzl[j] = 15 + j;
-      for (int c = 0; c < 6; ++c) { nzl[7 + c] = LEGD + 6 * as + c; nzl[13 + c] = LEGD + 6 * cur + c; }
-      nzl[19] = fidx;
+      for (int j = 0; j < 7; ++j) nzl[nz4++] = 15 + j;
+      for (int c = 0; c < 6; ++c) nzl[nz4++] = LEGD + 6 * as + c;
+      if (cur != as) for (int c = 0; c < 6; ++c) nzl[nz4++] = LEGD + 6 * cur + c;
+      for (int q = 0; q < idp; ++q) nzl[nz4++] = fidx + q;
     }
+    nz4 = __shfl_sync(0xffffffffu, nz4, 0);
     __syncwarp();
-    const bool pass = fidx >= 0 && gate_block(v, P, LD, H, Tj, rr, 2, nzl, 20, Ssm, vv, lane);
+    const bool pass = fidx >= 0 && gate_block(v, P, LD, H, Tj, rr, 2, nzl, nz4, Ssm, vv, lane);
     if (lane == 0) v.be.ft_accept[fi] = pass ? 2 : 0;
     return;
   }
@@ -1038,42 +1106,7 @@ __global__ void __launch_bounds__(32) be_feature_kernel(BeView v, double* Traw) 
   for (int j = lane; j < nz; j += 32) nzl[j] = (j < 7) ? 15 + j : LEGD + 6 * nth_set_bit(um, (j - 7) / 6) + ((j - 7) % 6);
   __syncwarp();
   // ---- three Householder reflections on H_f, applied to the nonzero columns of H and to r
-  for (int k = 0; k < 3; ++k) {
-    double nrm = 0.0;
-    for (int i = k + lane; i < nrows; i += 32) { const double x = Hf[i * 3 + k]; nrm += x * x; }
-    nrm = sqrt(warp_sum_d(nrm));
-    const double x0 = Hf[k * 3 + k];
-    const double alpha = x0 >= 0 ? -nrm : nrm;
-    for (int i = k + lane; i < nrows; i += 32) vv[i] = Hf[i * 3 + k] - (i == k ? alpha : 0.0);
-    __syncwarp();
-    double vtv = 0.0;
-    for (int i = k + lane; i < nrows; i += 32) vtv += vv[i] * vv[i];
-    vtv = warp_sum_d(vtv);
-    if (vtv > 0.0) {
-      const double beta = 2.0 / vtv;
-      for (int c = k; c < 3; ++c) {
-        double dt_ = 0.0;
-        for (int i = k + lane; i < nrows; i += 32) dt_ += vv[i] * Hf[i * 3 + c];
-        dt_ = warp_sum_d(dt_) * beta;
-        for (int i = k + lane; i < nrows; i += 32) Hf[i * 3 + c] -= dt_ * vv[i];
-      }
-      for (int j = lane; j < nz + 1; j += 32) {
-        if (j < nz) {
-          const int c = nzl[j];
-          double dt_ = 0.0;
-          for (int i = k; i < nrows; ++i) dt_ += vv[i] * H[(size_t)i * LD + c];
-          dt_ *= beta;
-          for (int i = k; i < nrows; ++i) H[(size_t)i * LD + c] -= dt_ * vv[i];
-        } else {
-          double dt_ = 0.0;
-          for (int i = k; i < nrows; ++i) dt_ += vv[i] * rr[i];
-          dt_ *= beta;
-          for (int i = k; i < nrows; ++i) rr[i] -= dt_ * vv[i];
-        }
-      }
-    }
-    __syncwarp();
-  }
+  reflect_block(Hf, 3, H, rr, nrows, LD, nzl, nz, vv, lane);
   // ---- gating test (:1865-1880) on rows 3..nrows-1
   const int R = nrows - 3;
   const bool pass = gate_block(v, P, LD, H + (size_t)3 * LD, Tj + (size_t)3 * LD, rr + 3, R, nzl, nz, Ssm, vv, lane, v.be.ft_gamma + fi);
@@ -1084,68 +1117,50 @@ __global__ void __launch_bounds__(32) be_feature_kernel(BeView v, double* Traw) 
     if (lane == 0) { v.be.ft_accept[fi] = 0; v.be.ft_action[fi] = 0; }
     return;
   }
-  // featureJacobian_ekf_new (:1247-1338): every observation except the anchor's, rows [2m, 2m + 2(m-1))
+  // featureJacobian_ekf_new (:1247-1338): every observation (1-D inverse depth: except the anchor's, :1260-1262), rows from 2m
+  const int idp = v.be.IDP;
   const int as = v.be.ft_anchor[fi];
-  const unsigned long long um2 = um & ~(1ull << as);
+  const unsigned long long um2 = (idp == 1) ? (um & ~(1ull << as)) : um;
   const int m2 = __popcll(um2), nr2 = 2 * m2;
   double* H2 = H + (size_t)nrows * LD;
   double* r2 = rr + nrows;
-  double* hf = Hf;                               // own inverse-depth column [2(m-1)]
+  double* hf = Hf;                               // own columns [2 m2][idp]
   for (int k = lane; k < m2; k += 32) {
     const int ws = nth_set_bit(um2, k);
     Jac1d J;
-    meas_jac_1didp(v, s, fi, ws, fej, J);
+    meas_jac_idp(v, s, fi, ws, fej, J);
     for (int a = 0; a < 2; ++a) {
       double* row = H2 + (size_t)(2 * k + a) * LD;
       for (int c = 0; c < 6; ++c) { row[LEGD + 6 * as + c] = J.ha[a][c]; row[15 + c] = J.he[a][c]; }
       for (int c = 0; c < 6; ++c) row[LEGD + 6 * ws + c] = J.hx[a][c];
       if (v.cfg.estimate_td) row[21] = obs[(size_t)ws * 4 + 2 + a];
-      hf[2 * k + a] = J.hf[a];
+      for (int q = 0; q < idp; ++q) hf[(2 * k + a) * idp + q] = J.hf[a][q];
       r2[2 * k + a] = J.r[a];
     }
   }
   __syncwarp();
-  // one Householder reflection on the own column: row 0 <- column space (H_1, h2, r_1), rows 1.. <- left null space
-  {
-    double nrm = 0.0;
-    for (int i = lane; i < nr2; i += 32) nrm += hf[i] * hf[i];
-    nrm = sqrt(warp_sum_d(nrm));
-    const double x0 = hf[0];
-    const double alpha = x0 >= 0 ? -nrm : nrm;
-    for (int i = lane; i < nr2; i += 32) vv[i] = hf[i] - (i == 0 ? alpha : 0.0);
-    __syncwarp();
-    double vtv = 0.0;
-    for (int i = lane; i < nr2; i += 32) vtv += vv[i] * vv[i];
-    vtv = warp_sum_d(vtv);
-    if (vtv > 0.0) {
-      const double beta = 2.0 / vtv;
-      for (int j = lane; j < nz + 1; j += 32) {
-        if (j < nz) {
-          const int c = nzl[j];
-          double dt_ = 0.0;
-          for (int i = 0; i < nr2; ++i) dt_ += vv[i] * H2[(size_t)i * LD + c];
-          dt_ *= beta;
-          for (int i = 0; i < nr2; ++i) H2[(size_t)i * LD + c] -= dt_ * vv[i];
-        } else {
-          double dt_ = 0.0;
-          for (int i = 0; i < nr2; ++i) dt_ += vv[i] * r2[i];
-          dt_ *= beta;
-          for (int i = 0; i < nr2; ++i) r2[i] -= dt_ * vv[i];
-        }
+  if (nr2 <= idp) {                              // nothing left to define the state with: treated like a failed gate
+    if (lane == 0) { v.be.ft_accept[fi] = 0; v.be.ft_action[fi] = 0; }
+    return;
+  }
+  // Householder reflections on the own columns: rows 0..idp-1 <- column space (H_1, H_2 triangular, r_1), the rest <- left
+  // null space (:2094-2125: any orthonormal basis of either space gives the same update up to row signs, which cancel)
+  reflect_block(hf, idp, H2, r2, nr2, LD, nzl, nz, vv, lane);
+  // (H_1 | H_2 | r_1) rows of this feature -> Hnew[s][idp * rank + j], rank = position among this frame's candidates
+  const int* cand = v.be.cand + (size_t)s * 128;
+  int rank = -1;
+  for (int k = 0; k < ic[I_NCAND]; ++k) if (cand[k] == slot) rank = k;
+  if (rank >= 0) {
+    for (int j = 0; j < idp; ++j) {
+      double* hn = v.be.Hnew + ((size_t)s * 64 * idp + (size_t)rank * idp + j) * (LD + 4);
+      for (int c = lane; c < LD; c += 32) hn[c] = H2[(size_t)j * LD + c];
+      if (lane == 0) {
+        for (int q = 0; q < 3; ++q) hn[LD + q] = (q < idp && q >= j) ? hf[j * idp + q] : 0.0;
+        hn[LD + 3] = r2[j];
       }
     }
-    __syncwarp();
-    // (H_1, h2, r_1) of this feature -> Hnew[s][rank], rank = position among this frame's candidates
-    const int* cand = v.be.cand + (size_t)s * 128;
-    int rank = -1;
-    for (int k = 0; k < ic[I_NCAND]; ++k) if (cand[k] == slot) rank = k;
-    if (rank >= 0) {
-      double* hn = v.be.Hnew + ((size_t)s * 64 + rank) * (LD + 4);
-      for (int c = lane; c < LD; c += 32) hn[c] = H2[c];
-      if (lane == 0) { hn[LD] = alpha; hn[LD + 1] = r2[0]; }
-    }
-    if (lane == 0) v.be.ft_accept[fi] = (rank >= 0) ? nr2 - 1 : 0;
   }
+  if (lane == 0) v.be.ft_accept[fi] = (rank >= 0) ? nr2 - idp : 0;
 }
 
 // ====================================================================== stacking (column-major Hs)
@@ -1238,10 +1253,10 @@ __global__ void __launch_bounds__(512) be_stack_kernel(BeView v, int phase) {
     if (dst + a > cap) continue;
     const int act = v.be.ft_action[fi];
     // first raw row of the block that goes into H_o: MSCKF skips the 3 rows that carry H_f; a new SLAM feature keeps
-    // the rows after its 2m gating rows and after the one row that defines the new state
+    // the rows after its 2m gating rows and after the IDP rows that define the new state
     int first = v.be.ft_rowofs[fi];
     if (act == 2) first += 3;
-    else if (act == 3) first += 2 * __popcll(v.be.ft_usemask[fi]) + 1;
+    else if (act == 3) first += 2 * __popcll(v.be.ft_usemask[fi]) + v.be.IDP;
     const double* H = v.be.Hraw + ((size_t)s * v.be.RAWMAX + first) * LD;
     const double* rr = v.be.rraw + (size_t)s * v.be.RAWMAX + first;
     for (int e = lane; e < a * d; e += 32) {
@@ -1274,9 +1289,10 @@ __global__ void be_slam_accept_kernel(BeView v) {
     const size_t fi = (size_t)s * T + slot;
     if (v.be.ft_action[fi] != 3) continue;                 // rejected by the gate (action reset to 0)
     if (k2 != k) {
-      const double* src = v.be.Hnew + ((size_t)s * 64 + k) * (LD + 4);
-      double* dst = v.be.Hnew + ((size_t)s * 64 + k2) * (LD + 4);
-      for (int c = 0; c < LD + 2; ++c) dst[c] = src[c];
+      const int idp = v.be.IDP;
+      const double* src = v.be.Hnew + ((size_t)s * 64 + k) * idp * (LD + 4);
+      double* dst = v.be.Hnew + ((size_t)s * 64 + k2) * idp * (LD + 4);
+      for (int c = 0; c < idp * (LD + 4); ++c) dst[c] = src[c];
     }
     fs[nf + k2] = slot;
     v.be.ft_flags[fi] |= 4;                                // in_state
@@ -1286,71 +1302,87 @@ __global__ void be_slam_accept_kernel(BeView v) {
 }
 
 // second half of measurementUpdate_hybrid (:1661-1676, :1821-1854): the states of the new SLAM features and the grown
-// covariance.  H_2 is diagonal for 1-D inverse depth (App. C-13), so HH = H_1 / h2 row by row.
+// covariance.  The reference solves with H_2.ldlt(), which reads the lower triangle of the upper-triangular factor, i.e. its
+// diagonal (App. C-13): HH = H_1 / diag(H_2) row by row; only P22's noise term uses the full factor (H_2^T H_2)^-1 (:1823-1825).
+// Scratch: HH [nn][LD] in Tm (free after P -= Y^T Y), nHHP [nn][LD] in Sm.
 __global__ void __launch_bounds__(256) be_slam_grow_kernel(BeView v) {
-  extern __shared__ double gsm[];          // HH [n_new][d]
   const int s = blockIdx.x, tid = threadIdx.x;
   int* ic = icore_of(v, s);
   if (!ic[I_OK]) return;
   const int n_new = ic[I_NNEW];
   if (n_new == 0) return;
+  const int idp = v.be.IDP, nn = idp * n_new;
   const int d = ic[I_DIM], LD = v.be.LD, T = v.be.T;
   double* P = P_of(v, s);
   const double* dx = v.be.dx + (size_t)s * v.be.LDS;
   const bool have_dx = ic[I_R] > 0;
   const int* fs = v.be.fs_slot + (size_t)s * 64;
   const int nf = ic[I_NF];
-  double* HH = gsm;
-  for (int e = tid; e < n_new * d; e += blockDim.x) {
+  const double* Hn = v.be.Hnew + (size_t)s * 64 * idp * (LD + 4);
+  double* HH = v.be.Tm + (size_t)s * v.be.RAWMAX * LD;
+  for (int e = tid; e < nn * d; e += blockDim.x) {
     const int k = e / d, c = e - k * d;
-    const double* hn = v.be.Hnew + ((size_t)s * 64 + k) * (LD + 4);
-    HH[e] = hn[c] / hn[LD];
+    const double* hn = Hn + (size_t)k * (LD + 4);
+    HH[(size_t)k * LD + c] = hn[c] / hn[LD + k % idp];
   }
   __syncthreads();
-  // new rows/cols of P: nHHP = -HH P (P already updated), P22 = -nHHP HH^T + sigma^2 / h2^2
-  double* Sd = v.be.Sm + (size_t)s * v.be.LDS * v.be.LDS;          // scratch for nHHP [n_new][d]
-  for (int e = tid; e < n_new * d; e += blockDim.x) {
+  // new rows/cols of P: nHHP = -HH P (P already updated), P22 = -nHHP HH^T + sigma^2 (H_2^T H_2)^-1
+  double* Sd = v.be.Sm + (size_t)s * v.be.LDS * v.be.LDS;          // scratch for nHHP [nn][LD]
+  for (int e = tid; e < nn * d; e += blockDim.x) {
     const int k = e / d, c = e - k * d;
     double acc = 0.0;
-    for (int q = 0; q < d; ++q) acc += HH[k * d + q] * P[(size_t)q * LD + c];
+    for (int q = 0; q < d; ++q) acc += HH[(size_t)k * LD + q] * P[(size_t)q * LD + c];
     Sd[(size_t)k * LD + c] = -acc;
   }
   __syncthreads();
-  for (int e = tid; e < n_new * d; e += blockDim.x) {
+  for (int e = tid; e < nn * d; e += blockDim.x) {
     const int k = e / d, c = e - k * d;
     const double val = Sd[(size_t)k * LD + c];
     P[(size_t)(d + k) * LD + c] = val;
     P[(size_t)c * LD + d + k] = val;
   }
-  for (int e = tid; e < n_new * n_new; e += blockDim.x) {
-    const int a = e / n_new, b = e - a * n_new;
+  for (int e = tid; e < nn * nn; e += blockDim.x) {
+    const int a = e / nn, b = e - a * nn;
     double acc = 0.0;
-    for (int q = 0; q < d; ++q) acc += Sd[(size_t)a * LD + q] * HH[b * d + q];
+    for (int q = 0; q < d; ++q) acc += Sd[(size_t)a * LD + q] * HH[(size_t)b * LD + q];
     acc = -acc;
-    if (a == b) { const double h2 = v.be.Hnew[((size_t)s * 64 + a) * (LD + 4) + LD]; acc += v.cfg.sfeat2 / (h2 * h2); }
+    if (idp == 1) {
+      if (a == b) { const double h2 = Hn[(size_t)a * (LD + 4) + LD]; acc += v.cfg.sfeat2 / (h2 * h2); }
+    } else if (a / 3 == b / 3) {
+      // (R^T R)^-1 = R^-1 R^-T of this feature's upper-triangular 3x3 factor
+      const double* h0 = Hn + (size_t)(a / 3 * 3) * (LD + 4) + LD;
+      const double r00 = h0[0], r01 = h0[1], r02 = h0[2], r11 = h0[(LD + 4) + 1], r12 = h0[(LD + 4) + 2], r22 = h0[2 * (LD + 4) + 2];
+      double Ri[3][3] = {{1.0 / r00, -r01 / (r00 * r11), (r01 * r12 - r02 * r11) / (r00 * r11 * r22)}, {0.0, 1.0 / r11, -r12 / (r11 * r22)}, {0.0, 0.0, 1.0 / r22}};
+      const int ia = a % 3, ib = b % 3;
+      acc += v.cfg.sfeat2 * (Ri[ia][0] * Ri[ib][0] + Ri[ia][1] * Ri[ib][1] + Ri[ia][2] * Ri[ib][2]);
+    }
     P[(size_t)(d + a) * LD + d + b] = acc;
   }
   __syncthreads();
-  for (int e = tid; e < n_new * n_new; e += blockDim.x) {             // symmetrise the new block (:1852-1853)
-    const int a = e / n_new, b = e - a * n_new;
+  for (int e = tid; e < nn * nn; e += blockDim.x) {             // symmetrise the new block (:1852-1853)
+    const int a = e / nn, b = e - a * nn;
     if (a < b) { const double mval = 0.5 * (P[(size_t)(d + a) * LD + d + b] + P[(size_t)(d + b) * LD + d + a]); P[(size_t)(d + a) * LD + d + b] = mval; P[(size_t)(d + b) * LD + d + a] = mval; }
   }
-  // dx_new = -HH dx_leg + r_1 / h2, inverse depth and world position of the new features
+  // dx_new = -HH dx_leg + r_1 / diag(H_2); inverse-depth parameters and world position of the new features
   if (tid < n_new) {
     const int k = tid;
-    const double* hn = v.be.Hnew + ((size_t)s * 64 + k) * (LD + 4);
-    double acc = 0.0;
-    if (have_dx) for (int q = 0; q < d; ++q) acc += HH[k * d + q] * dx[q];
-    const double dxn = -acc + hn[LD + 1] / hn[LD];
+    double dxn[3] = {0.0, 0.0, 0.0};
+    for (int j = 0; j < idp; ++j) {
+      const double* hn = Hn + (size_t)(k * idp + j) * (LD + 4);
+      double acc = 0.0;
+      if (have_dx) for (int q = 0; q < d; ++q) acc += HH[(size_t)(k * idp + j) * LD + q] * dx[q];
+      dxn[j] = -acc + hn[LD + 3] / hn[LD + j];
+    }
     const size_t fi = (size_t)s * T + fs[nf + k];
-    const double inv = v.be.ft_inv[fi] + dxn;
+    if (idp == 3) { v.be.ft_oa[fi * 2] += dxn[0]; v.be.ft_oa[fi * 2 + 1] += dxn[1]; }
+    const double inv = v.be.ft_inv[fi] + dxn[idp - 1];
     v.be.ft_inv[fi] = inv;
     const double* wa = win_of(v, s, v.be.ft_anchor[fi]);
     const V3 p_c = v3(v.be.ft_oa[fi * 2] / inv, v.be.ft_oa[fi * 2 + 1] / inv, 1.0 / inv);
     st3(v.be.ft_pos + fi * 3, m3_vec(quat_to_rot(wa + W_QCAM), p_c) + ld3(wa + W_PCAM));
   }
   __syncthreads();
-  if (tid == 0) { ic[I_DIM] = d + n_new; ic[I_NF] = nf + n_new; ic[I_NNEW] = 0; }
+  if (tid == 0) { ic[I_DIM] = d + nn; ic[I_NF] = nf + n_new; ic[I_NNEW] = 0; }
 }
 
 // ====================================================================== QR compression (SPQR thin QR at larvio.cpp:1430-1449, 2151-2171)
@@ -1760,11 +1792,12 @@ __global__ void __launch_bounds__(256) be_correct_kernel(BeView v) {
   }
   __syncthreads();
   // inverse depth of the SLAM features already in the state and their world positions (:1536-1575, :1752-1801)
-  const int nf = ic[I_NF];
+  const int nf = ic[I_NF], idp = v.be.IDP;
   const int base = LEGD + 6 * n_win;
   for (int i = tid; i < nf; i += blockDim.x) {
     const size_t fi = (size_t)s * v.be.T + v.be.fs_slot[(size_t)s * 64 + i];
-    const double inv = v.be.ft_inv[fi] + dx[base + i];
+    if (idp == 3) { v.be.ft_oa[fi * 2] += dx[base + 3 * i]; v.be.ft_oa[fi * 2 + 1] += dx[base + 3 * i + 1]; }
+    const double inv = v.be.ft_inv[fi] + dx[base + idp * i + idp - 1];
     v.be.ft_inv[fi] = inv;
     const double* wa = win_of(v, s, v.be.ft_anchor[fi]);
     const V3 p_c = v3(v.be.ft_oa[fi * 2] / inv, v.be.ft_oa[fi * 2 + 1] / inv, 1.0 / inv);
@@ -1781,7 +1814,7 @@ __global__ void __launch_bounds__(256) be_zupt_build_kernel(BeView v) {
   if (!ic[I_ZUPT]) { if (tid == 0) { ic[I_ROWS] = 0; ic[I_R] = 0; } return; }
   const int RMAX = v.be.RMAX, LD = v.be.LD;
   const int nf0 = ic[I_NF];
-  const int d = ic[I_DIM] - nf0, N = ic[I_NWIN];        // read before thread 0 rewrites I_DIM below
+  const int d = ic[I_DIM] - v.be.IDP * nf0, N = ic[I_NWIN];        // read before thread 0 rewrites I_DIM below
   if (nf0 > 0) {                                        // :2770-2782: every SLAM feature leaves the state
     for (int i = tid; i < nf0; i += blockDim.x) {
       const size_t fi = (size_t)s * v.be.T + v.be.fs_slot[(size_t)s * 64 + i];
@@ -1883,12 +1916,14 @@ __device__ int new_anchor_slot(const BeView& v, int s, size_t fi, int n_win, int
 }
 
 // anchor changes of pruneImuStateBuffer (:2345-2461) for features whose anchor pose is about to leave the window:
-// in-state SLAM features get updateFeatureCov_1didp (:3125-3293), one after the other in feature-id order (each rewrites
-// one row/column of P that the next one reads); potential SLAM features outside the state are only re-anchored.
+// in-state SLAM features get updateFeatureCov_1didp (:3125-3293) / _3didp (:2965-3122), one after the other in feature-id
+// order (each rewrites its rows/columns of P that the next one reads); potential SLAM features outside the state are only
+// re-anchored.  With 3-D inverse depth the new anchor is always the newest state (:2361-2378, :2420-2437).
 __global__ void __launch_bounds__(256) be_anchor_kernel(BeView v) {
-  __shared__ double Jv[20]; __shared__ int Jc[20];
-  __shared__ int s_list[64]; __shared__ int s_n, s_new;
-  extern __shared__ double pfl[];          // [LD]
+  __shared__ double Jv[3][20]; __shared__ int Jc[20];
+  __shared__ int s_list[64]; __shared__ int s_n, s_nj;
+  extern __shared__ double pfl[];          // [IDP][LD]
+  const int idp = v.be.IDP;
   const int s = blockIdx.x, tid = threadIdx.x;
   int* ic = icore_of(v, s);
   if (!ic[I_OK] || !ic[I_DO_PRUNE]) return;
@@ -1907,11 +1942,12 @@ __global__ void __launch_bounds__(256) be_anchor_kernel(BeView v) {
       const int as = v.be.ft_anchor[fi];
       if (as != r0 && as != r1) continue;
       if (!((v.be.ft_mask[fi] >> as) & 1)) continue;
-      const int ns = new_anchor_slot(v, s, fi, n_win, r0, r1);
+      const int ns = (idp == 3) ? n_win - 1 : new_anchor_slot(v, s, fi, n_win, r0, r1);
       const double* w = win_of(v, s, ns);
       const V3 pn = m3_tvec(quat_to_rot(w + W_QCAM), ld3(v.be.ft_pos + fi * 3) - ld3(w + W_PCAM));
       v.be.ft_inv[fi] = 1.0 / pn.z;
-      v.be.ft_oa[fi * 2] = v.be.ft_obs[(fi * Wcap + ns) * 4]; v.be.ft_oa[fi * 2 + 1] = v.be.ft_obs[(fi * Wcap + ns) * 4 + 1];
+      if (idp == 3) { v.be.ft_oa[fi * 2] = pn.x / pn.z; v.be.ft_oa[fi * 2 + 1] = pn.y / pn.z; }      // invParam (:2429-2432)
+      else { v.be.ft_oa[fi * 2] = v.be.ft_obs[(fi * Wcap + ns) * 4]; v.be.ft_oa[fi * 2 + 1] = v.be.ft_obs[(fi * Wcap + ns) * 4 + 1]; }
       v.be.ft_anchor[fi] = ns;
     }
     // in-state features to re-anchor, sorted by feature id
@@ -1933,11 +1969,54 @@ __global__ void __launch_bounds__(256) be_anchor_kernel(BeView v) {
   for (int it = 0; it < n; ++it) {
     const int fcnt = s_list[it];
     const size_t fi = (size_t)s * T + fs[fcnt];
-    const int fidx = LEGD + 6 * n_win + fcnt;
-    if (tid == 0) {
+    const int fidx = LEGD + 6 * n_win + idp * fcnt;
+    if (tid == 0 && idp == 3) {
+      const int os = v.be.ft_anchor[fi];
+      const int ns = n_win - 1;
+      const double* wo = win_of(v, s, os);
+      const double* wn = win_of(v, s, ns);
+      const V3 p_w = ld3(v.be.ft_pos + fi * 3), p_fej = ld3(v.be.ft_pfej + fi * 3);
+      const V3 pnew = m3_tvec(quat_to_rot(wn + W_QCAM), p_w - ld3(wn + W_PCAM));
+      const double iv[3] = {pnew.x / pnew.z, pnew.y / pnew.z, 1.0 / pnew.z};      // invParam in the new anchor (:2366-2370)
+      v.be.ft_oa[fi * 2] = iv[0]; v.be.ft_oa[fi * 2 + 1] = iv[1]; v.be.ft_inv[fi] = iv[2];
+      // ---- updateFeatureCov_3didp, literally: the reference looks the "new" pose and its column block up with
+      // old_state_id (:3000, :3066), so every "new" quantity below is the OLD anchor's and H_x_new lands in the old block
+      const M3 R_b2c = m3_load(core + C_RIC); const V3 t_c_b = ld3(core + C_TCI);
+      const M3 R_b2w_old = quat_to_rot(wo + W_Q), R_c2w_old = quat_to_rot(wo + W_QCAM);
+      V3 p_old;
+      if (fej) p_old = m3_vec(R_b2c, m3_tvec(R_b2w_old, p_fej - ld3(wo + W_PFEJ)) - t_c_b);
+      else p_old = m3_tvec(R_c2w_old, p_w - ld3(wo + W_PCAM));
+      const M3 R_w2b_new = m3_t(R_b2w_old), R_w2c_new = m3_t(R_c2w_old);
+      const V3 pbn = fej ? (p_fej - ld3(wo + W_PFEJ)) : (p_w - ld3(wo + W_P));
+      double Jfp[3][3] = {{1.0, 0.0, -iv[0]}, {0.0, 1.0, -iv[1]}, {0.0, 0.0, -iv[2]}};
+      for (int i = 0; i < 3; ++i) for (int c = 0; c < 3; ++c) Jfp[i][c] = iv[2] * Jfp[i][c];
+      const M3 Jp = m3_mul(R_w2c_new, R_c2w_old);
+      const M3 Jxn_l = m3_mul(R_w2c_new, skew(pbn));                    // J_x_new = [R skew(p_bf_new) | -R]
+      const M3 Sk = skew(m3_vec(R_w2b_new, pbn) - t_c_b);
+      const M3 Rno = m3_mul(R_w2b_new, R_b2w_old);
+      const M3 Mx = m3_mul(Rno, skew(m3_tvec(R_b2c, p_old)));
+      const M3 Jet = m3_mul(R_b2c, m3_sub(Sk, Mx));
+      const M3 Jep = m3_mul(R_b2c, m3_sub(Rno, m3_identity()));
+      double Jpf[3][3] = {{1.0, 0.0, -p_old.x}, {0.0, 1.0, -p_old.y}, {0.0, 0.0, -p_old.z}};
+      for (int i = 0; i < 3; ++i) for (int c = 0; c < 3; ++c) Jpf[i][c] = p_old.z * Jpf[i][c];
+      for (int c = 0; c < 3; ++c) { Jc[c] = fidx + c; Jc[3 + c] = LEGD + 6 * os + c; Jc[6 + c] = LEGD + 6 * os + 3 + c; Jc[9 + c] = 15 + c; Jc[12 + c] = 18 + c; }
+      for (int a = 0; a < 3; ++a) {
+        double fp[3];                                                   // row a of J_fp_new * J_p
+        for (int c = 0; c < 3; ++c) fp[c] = Jfp[a][0] * Jp.m[c] + Jfp[a][1] * Jp.m[3 + c] + Jfp[a][2] * Jp.m[6 + c];
+        for (int c = 0; c < 3; ++c) {
+          Jv[a][c] = fp[0] * Jpf[0][c] + fp[1] * Jpf[1][c] + fp[2] * Jpf[2][c];
+          Jv[a][3 + c] = Jfp[a][0] * Jxn_l.m[c] + Jfp[a][1] * Jxn_l.m[3 + c] + Jfp[a][2] * Jxn_l.m[6 + c];
+          Jv[a][6 + c] = -(Jfp[a][0] * R_w2c_new.m[c] + Jfp[a][1] * R_w2c_new.m[3 + c] + Jfp[a][2] * R_w2c_new.m[6 + c]);
+          Jv[a][9 + c] = Jfp[a][0] * Jet.m[c] + Jfp[a][1] * Jet.m[3 + c] + Jfp[a][2] * Jet.m[6 + c];
+          Jv[a][12 + c] = Jfp[a][0] * Jep.m[c] + Jfp[a][1] * Jep.m[3 + c] + Jfp[a][2] * Jep.m[6 + c];
+        }
+      }
+      s_nj = 15;
+      v.be.ft_anchor[fi] = ns;
+    }
+    if (tid == 0 && idp == 1) {
       const int os = v.be.ft_anchor[fi];
       const int ns = new_anchor_slot(v, s, fi, n_win, r0, r1);
-      s_new = ns;
       const double* wo = win_of(v, s, os);
       const double* wn = win_of(v, s, ns);
       const V3 p_w = ld3(v.be.ft_pos + fi * 3), p_fej = ld3(v.be.ft_pfej + fi * 3);
@@ -1970,27 +2049,40 @@ __global__ void __launch_bounds__(256) be_anchor_kernel(BeView v) {
       const M3 Jet = m3_mul(R_b2c, m3_sub(Sk, Mx));
       const M3 Jep = m3_mul(R_b2c, m3_sub(Rno, m3_identity()));
       int k = 0;
-      Jc[k] = fidx; Jv[k++] = Jr * J_d * (-1.0 / (inv_old * inv_old));
-      for (int c = 0; c < 3; ++c) { Jc[k] = LEGD + 6 * os + c; Jv[k++] = Jr * Jto.m[6 + c]; }
-      for (int c = 0; c < 3; ++c) { Jc[k] = LEGD + 6 * os + 3 + c; Jv[k++] = Jr * R_w2c_new.m[6 + c]; }
-      for (int c = 0; c < 3; ++c) { Jc[k] = LEGD + 6 * ns + c; Jv[k++] = Jr * Jtn.m[6 + c]; }
-      for (int c = 0; c < 3; ++c) { Jc[k] = LEGD + 6 * ns + 3 + c; Jv[k++] = Jr * -R_w2c_new.m[6 + c]; }
-      for (int c = 0; c < 3; ++c) { Jc[k] = 15 + c; Jv[k++] = Jr * Jet.m[6 + c]; }
-      for (int c = 0; c < 3; ++c) { Jc[k] = 18 + c; Jv[k++] = Jr * Jep.m[6 + c]; }
+      Jc[k] = fidx; Jv[0][k++] = Jr * J_d * (-1.0 / (inv_old * inv_old));
+      for (int c = 0; c < 3; ++c) { Jc[k] = LEGD + 6 * os + c; Jv[0][k++] = Jr * Jto.m[6 + c]; }
+      for (int c = 0; c < 3; ++c) { Jc[k] = LEGD + 6 * os + 3 + c; Jv[0][k++] = Jr * R_w2c_new.m[6 + c]; }
+      for (int c = 0; c < 3; ++c) { Jc[k] = LEGD + 6 * ns + c; Jv[0][k++] = Jr * Jtn.m[6 + c]; }
+      for (int c = 0; c < 3; ++c) { Jc[k] = LEGD + 6 * ns + 3 + c; Jv[0][k++] = Jr * -R_w2c_new.m[6 + c]; }
+      for (int c = 0; c < 3; ++c) { Jc[k] = 15 + c; Jv[0][k++] = Jr * Jet.m[6 + c]; }
+      for (int c = 0; c < 3; ++c) { Jc[k] = 18 + c; Jv[0][k++] = Jr * Jep.m[6 + c]; }
+      s_nj = k;
       v.be.ft_anchor[fi] = ns;
     }
     __syncthreads();
-    for (int c = tid; c < d; c += blockDim.x) {
+    const int nj = s_nj;
+    // P_fl = J P (IDP rows), P_ff = P_fl J^T; the feature's rows and columns of P are replaced (:3100-3121, :3272-3292)
+    for (int e = tid; e < idp * d; e += blockDim.x) {
+      const int a = e / d, c = e - a * d;
       double acc = 0.0;
-      for (int k = 0; k < 19; ++k) acc += Jv[k] * P[(size_t)Jc[k] * LD + c];
-      pfl[c] = acc;
+      for (int k = 0; k < nj; ++k) acc += Jv[a][k] * P[(size_t)Jc[k] * LD + c];
+      pfl[a * LD + c] = acc;
     }
     __syncthreads();
     double pff = 0.0;
-    if (tid == 0) for (int k = 0; k < 19; ++k) pff += pfl[Jc[k]] * Jv[k];
+    if (tid < idp * idp) { const int a = tid / idp, b = tid - a * idp; for (int k = 0; k < nj; ++k) pff += pfl[a * LD + Jc[k]] * Jv[b][k]; }
     __syncthreads();
-    for (int c = tid; c < d; c += blockDim.x) if (c != fidx) { P[(size_t)fidx * LD + c] = pfl[c]; P[(size_t)c * LD + fidx] = pfl[c]; }
-    if (tid == 0) P[(size_t)fidx * LD + fidx] = pff;
+    for (int e = tid; e < idp * d; e += blockDim.x) {
+      const int a = e / d, c = e - a * d;
+      if (c < fidx || c >= fidx + idp) { P[(size_t)(fidx + a) * LD + c] = pfl[a * LD + c]; P[(size_t)c * LD + fidx + a] = pfl[a * LD + c]; }
+    }
+    if (tid < idp * idp) P[(size_t)(fidx + tid / idp) * LD + fidx + tid % idp] = pff;
+    __syncthreads();
+    if (idp == 3 && tid < 3) {                    // (P + P^T) / 2 (:3122): only the 3x3 block can be unsymmetric
+      const int a = tid == 2 ? 1 : 0, b = tid == 0 ? 1 : 2;
+      const double mval = 0.5 * (P[(size_t)(fidx + a) * LD + fidx + b] + P[(size_t)(fidx + b) * LD + fidx + a]);
+      P[(size_t)(fidx + a) * LD + fidx + b] = mval; P[(size_t)(fidx + b) * LD + fidx + a] = mval;
+    }
     __syncthreads();
   }
 }
@@ -2179,7 +2271,8 @@ __global__ void __launch_bounds__(64) be_slam_pre_kernel(BeView v) {
   if (nf == 0) return;
   int* fs = v.be.fs_slot + (size_t)s * 64;
   const int cur = ic[I_NWIN] - 1, d = ic[I_DIM];
-  const int base = d - nf;
+  const int idp = v.be.IDP;
+  const int base = d - idp * nf;
   int* cm = v.be.cmap + (size_t)s * LD;
   int keep = 0;
   for (int i = 0; i < base; ++i) cm[i] = i;
@@ -2187,7 +2280,7 @@ __global__ void __launch_bounds__(64) be_slam_pre_kernel(BeView v) {
     const int slot = fs[i];
     const size_t fi = (size_t)s * T + slot;
     if ((v.be.ft_mask[fi] >> cur) & 1) {
-      cm[base + keep] = base + i;
+      for (int q = 0; q < idp; ++q) cm[base + idp * keep + q] = base + idp * i + q;
       fs[keep++] = slot;
       const double* o = v.be.ft_obs + (fi * Wcap + cur) * 4;
       const int code = grid_code(v, o[0], o[1]);
@@ -2197,7 +2290,7 @@ __global__ void __launch_bounds__(64) be_slam_pre_kernel(BeView v) {
       v.be.ft_flags[fi] = 0; v.be.ft_mask[fi] = 0;              // rmLostFeaturesCov erases the feature
     }
   }
-  if (keep != nf) { ic[I_REMAP] = 1; ic[I_NEWDIM] = base + keep; ic[I_NF] = keep; }
+  if (keep != nf) { ic[I_REMAP] = 1; ic[I_NEWDIM] = base + idp * keep; ic[I_NF] = keep; }
 }
 
 // ---------------------------------------------------------------- sequential part of the promotion rule (:1968-2002)
@@ -2263,7 +2356,7 @@ __global__ void __launch_bounds__(256) be_slam_decide_kernel(BeView v) {
         if (spec_ok) commit_spec(true);
       }
       if (flags & 2) {
-        action = 3; usemask = mask; nrows = 2 * m + 2 * (m - 1);
+        action = 3; usemask = mask; nrows = 2 * m + (v.be.IDP == 3 ? 2 * m : 2 * (m - 1));      // gate rows + featureJacobian_ekf_new rows (the anchor's own observation only counts with 3-D inverse depth, :1260-1262)
         grid[code]++; newlist[n_new++] = slot;
       }
     } else {
@@ -2296,7 +2389,6 @@ static int bdalloc(LvbHandle* h, T** p, size_t count) {
 
 static const char* be_unsupported_reason(const LvbConfig& c) {
   if (c.max_features_in_one_grid > 0 && c.aug_grid_rows * c.aug_grid_cols != 0) {
-    if (c.feature_idp_dim != 1) return "feature_idp_dim: 3 (3-D inverse-depth SLAM features) is not built yet; use 1";
     if (c.use_schmidt) return "use_schmidt: 1 (Schmidt nuisance states) is not built yet";
     if (c.max_features_in_one_grid * c.aug_grid_rows * c.aug_grid_cols > 64) return "more than 64 EKF-SLAM features";
   }
@@ -2372,9 +2464,10 @@ int be_alloc(LvbHandle* h) {
   be->T = 2 * be->N;
   be->grid_rows = c.aug_grid_rows; be->grid_cols = c.aug_grid_cols; be->max_per_cell = c.max_features_in_one_grid > 0 ? c.max_features_in_one_grid : 0;
   be->NFmax = be->max_per_cell * be->grid_rows * be->grid_cols;
-  if (be->NFmax > 64 || c.feature_idp_dim != 1 || c.use_schmidt) be->NFmax = 0;   // such configs are refused at the first back-end call
+  if (be->NFmax > 64 || c.use_schmidt) be->NFmax = 0;   // such configs are refused at the first back-end call
+  be->IDP = (c.feature_idp_dim == 1) ? 1 : 3;           // anything but 1 means 3 (larvio.cpp:270-274)
   be->LEG = h->cfg.calib_imu_instrinsic ? 46 : 22;
-  be->Dmax = be->LEG + 6 * be->Wcap + be->NFmax;
+  be->Dmax = be->LEG + 6 * be->Wcap + be->IDP * be->NFmax;
   be->LD = ((be->Dmax + 7) / 8) * 8;
   be->LDS = be->NFmax ? ((be->Dmax + 2 * be->NFmax + 16 * be->NFmax + 7) / 8) * 8 : be->LD;
   // row capacities of one measurement pass: every track that reaches max_track_len in the same frame contributes
@@ -2402,7 +2495,7 @@ int be_alloc(LvbHandle* h) {
   BDA(be->Tm, S * (size_t)be->RAWMAX * LD);      // doubles as the per-feature H*P scratch of the gate
   BDA(be->Sm, S * (size_t)be->LDS * be->LDS); BDA(be->zvec, S * (size_t)be->LDS); BDA(be->dx, S * (size_t)be->LDS);
   BDA(be->ft_inv, S * T); BDA(be->ft_oa, S * T * 2); BDA(be->ft_anchor, S * T); BDA(be->ft_pfej, S * T * 3); BDA(be->ft_spec, S * T * 8);
-  BDA(be->ft_gamma, S * T); BDA(be->fs_slot, S * 64); BDA(be->cmap, S * LD); BDA(be->cand, S * 128); BDA(be->Hnew, S * 64 * (LD + 4));
+  BDA(be->ft_gamma, S * T); BDA(be->fs_slot, S * 64); BDA(be->cmap, S * LD); BDA(be->cand, S * 128); BDA(be->Hnew, S * 64 * be->IDP * (LD + 4));
   BDA(be->imu, S * be->imu_cap); BDA(be->n_imu, S);
   BDA(be->msg_in, S * be->N); BDA(be->msg_in_n, S); BDA(be->msg_in_t, S); BDA(be->msg_in_valid, S);
   BPIN(be->pin_imu, LvbImu, S * be->imu_cap); BPIN(be->pin_n_imu, int, S); BPIN(be->pin_icore, int, S * BE_ICORE);
@@ -2421,7 +2514,6 @@ int be_alloc(LvbHandle* h) {
   LVB_CUDA(cudaFuncSetAttribute(be_feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm_bytes));
   LVB_CUDA(cudaFuncSetAttribute(be_propagate_kernel<22>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be_propagate_smem(22)));
   LVB_CUDA(cudaFuncSetAttribute(be_propagate_kernel<46>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be_propagate_smem(46)));
-  if (be->NFmax > 0) LVB_CUDA(cudaFuncSetAttribute(be_slam_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 64 * be->LD)));
   // with the nonzero-column compression r stays near 50..110 rows whatever the window; 192 rows of packed triangle = 148 KB
   be->chol_cap = be->LDS < 192 ? be->LDS : 192;
   const size_t chol_bytes = sizeof(double) * ((size_t)be->chol_cap * (be->chol_cap + 1) / 2 + 2 * be->chol_cap);
@@ -2596,7 +2688,7 @@ static int be_measurement_pass(LvbHandle* h, BeView& v, int mode) {
   }
   if (hybrid && mode == 1) {
     LVB_PROF(h, "be_anchor_kernel");
-    be_anchor_kernel<<<be->S, 256, sizeof(double) * be->LD, st>>>(v);
+    be_anchor_kernel<<<be->S, 256, sizeof(double) * be->IDP * be->LD, st>>>(v);
     LVB_LAUNCH_CHECK(h);
     DBG("be_anchor_kernel");
   }
@@ -2639,7 +2731,7 @@ static int be_measurement_pass(LvbHandle* h, BeView& v, int mode) {
   RC(be_update(h, v, false, hybrid && mode == 0));
   if (hybrid && mode == 0) {
     LVB_PROF(h, "be_slam_grow_kernel");
-    be_slam_grow_kernel<<<be->S, 256, sizeof(double) * 64 * be->LD, st>>>(v);
+    be_slam_grow_kernel<<<be->S, 256, 0, st>>>(v);
     LVB_LAUNCH_CHECK(h);
     DBG("be_slam_grow_kernel");
   }

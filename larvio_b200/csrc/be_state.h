@@ -37,6 +37,7 @@ struct LvbBackEnd {
   int imu_cap;         // IMU samples per sequence per call
   int chol_cap;        // largest innovation system factorised out of shared memory (packed triangle); larger ones use the global-memory kernel
   int NFmax;           // EKF-SLAM feature capacity (max_features_in_one_grid * grid cells), 0 = pure MSCKF
+  int IDP;             // state columns per EKF-SLAM feature: 1 (inverse depth) or 3 (x/z, y/z, 1/z in the anchor camera), larvio.cpp:270-274
   int LDS;             // leading dimension of Sm (rows of the stacked H_o can exceed the state dimension in hybrid mode)
   int grid_rows, grid_cols, max_per_cell;
   double* core; int* icore;
@@ -44,15 +45,16 @@ struct LvbBackEnd {
   double* P[2]; int pcur;                     // ping-pong covariance [S][LD][LD], row-major
   unsigned long long* ft_id; int* ft_flags; double* ft_pos; unsigned long long* ft_mask; double* ft_obs;  // [S][T]...
   int* ft_action; int* ft_rowofs; int* ft_nrows; int* ft_accept; unsigned long long* ft_usemask;
-  // EKF-SLAM (1-D inverse depth) bookkeeping per table slot: invDepth, corrected anchor observation (x,y), anchor window slot,
-  // first-estimate position; speculative triangulation results of this frame; state order list
+  // EKF-SLAM bookkeeping per table slot: invDepth, corrected anchor observation (x,y) - with 3-D inverse depth the triple
+  // (ft_oa[0], ft_oa[1], ft_inv) IS invParam = (x/z, y/z, 1/z) (feature.hpp:231) -, anchor window slot, first-estimate position;
+  // speculative triangulation results of this frame; state order list
   double* ft_inv; double* ft_oa; int* ft_anchor; double* ft_pfej; double* ft_spec; int* fs_slot; int* cmap; int* cand;
   double* ft_gamma;                           // [S][T] last gating statistic of each slot (diagnostics)
   // map points for getStableMapPointPositions / getActiveeMapPointPositions (larvio.h:86-87): [which][S][PCAP], which 0 = SLAM
   // features that left the state (lost_slam_features, larvio.cpp:3342), 1 = features in the state at the end of a step
   // (active_slam_features, :455-458); both accumulate until lvb_get_points reads and clears them, like the reference's getters
   unsigned long long* pts_id; double* pts_xyz; int* pts_n; int* pts_drop; int PCAP;
-  double* Hnew;                               // [S][NFmax][LD + 4]: (H_1 row, h2, r_1) of the features added this frame
+  double* Hnew;                               // [S][64 * IDP][LD + 4]: per new state column (H_1 row | H_2 row [3] | r_1), features added this frame
   double* Hraw; double* rraw;                 // [S][RAWMAX][LD], [S][RAWMAX]
   double* Hs; double* rs;                     // stacked, COLUMN-major [S][LD cols][RMAX rows], [S][RMAX]
   double* Tm;                                 // H*P   [S][RMAX? -> Dmax rows][LD]   (rows <= Dmax after compression)

@@ -241,6 +241,7 @@ def _drive(cfg, seqs, nf, mode, S=2):
             assert P.shape == bes[s].P.shape
             rep['max_dim'] = max(rep.get('max_dim', 0), int(P.shape[0]))
             rep['max_slam'] = max(rep.get('max_slam', 0), len(getattr(bes[s], 'feature_states', [])))
+            rep['anchor_changes'] = rep.get('anchor_changes', 0) + int(bes[s].stats.get('anchor_changes', 0) or 0)
             assert np.abs(P - P.T).max() == 0.0                               # symmetric by construction
             rep['Prel'] = max(rep['Prel'], float(np.linalg.norm(P - bes[s].P) / np.linalg.norm(bes[s].P)))
             cal = b.get_calibration(s)
@@ -311,6 +312,21 @@ def test_hybrid_slam_features_match_oracle(lib_built):
     hs = [synth.make_sequence(hc.raw, s, 130) for s in range(2)]
     rep = _drive(hc, hs, 130, 'step')
     assert rep['steps'] >= 60 and rep['ok_mismatch'] == 0 and rep['imu_mismatch'] == 0
+    assert rep['p'] < 1e-8 and rep['v'] < 1e-8 and rep['q'] < 1e-8 and rep['Prel'] < 1e-8
+
+
+def test_hybrid_3d_inverse_depth_slam_features_match_oracle(lib_built):
+    """feature_idp_dim: 3 - SLAM features carry (x/z, y/z, 1/z) in their anchor camera (3 state columns each): the anchor's
+    own observation takes part in featureJacobian_ekf_new (larvio.cpp:1260-1262), three reflections split a new feature's
+    block, H_2 is a 3x3 triangle (:1661-1676, :1821-1854), and when the anchor pose leaves the window the newest state
+    becomes the anchor with updateFeatureCov_3didp (:2965-3122, including its old_state_id slip)."""
+    from larvio_b200 import synth
+    from larvio_b200.config import Config
+    hc = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), sw_size=16, feature_idp_dim=3)
+    hs = [synth.make_sequence(hc.raw, s, 130) for s in range(2)]
+    rep = _drive(hc, hs, 130, 'step')
+    assert rep['steps'] >= 60 and rep['ok_mismatch'] == 0 and rep['imu_mismatch'] == 0
+    assert rep['max_slam'] >= 8 and rep['max_dim'] >= 22 + 6 * 15 + 3 * 8 and rep['anchor_changes'] >= 10
     assert rep['p'] < 1e-8 and rep['v'] < 1e-8 and rep['q'] < 1e-8 and rep['Prel'] < 1e-8
 
 
@@ -760,7 +776,7 @@ def test_sharded_batch_through_the_c_abi_matches_one_handle(cfg, seqs):
 def test_unsupported_configs_fail_loudly(lib_built):
     from larvio_b200 import api
     from larvio_b200.config import Config
-    c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), feature_idp_dim=3)      # 3-D inverse depth: not built
+    c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), use_schmidt=1)          # Schmidt nuisance states: not built
     b = api.Batch(c, n_seq=1)
     imu = np.zeros((1, 8), api.IMU_DTYPE); n = np.zeros(1, np.int32)
     with pytest.raises(api.LarvioB200Error) as e:
