@@ -15,7 +15,18 @@ IOLIB := larvio_b200/lib/liblarvio_io.so
 REPLAY := larvio_b200/bin/larvio_replay
 SHIMDEMO := larvio_b200/bin/larvio_shim_demo
 
-all: $(LIB) $(IOLIB) $(REPLAY) $(SHIMDEMO)
+ORACLE_C := oracle/_build/liboracle_backend.so oracle/_build/liboracle_orb.so
+
+all: $(LIB) $(IOLIB) $(REPLAY) $(SHIMDEMO) $(ORACLE_C)
+
+# the compiled CPU oracle of processFeatures (test infrastructure / bench CPU legs only; never linked into the product)
+oracle/_build/liboracle_backend.so: oracle/backend_c.cpp
+	mkdir -p oracle/_build
+	g++ -O3 -march=x86-64-v3 -std=c++17 -shared -fPIC -o $@ $<
+
+oracle/_build/liboracle_orb.so: oracle/orb_c.cpp
+	mkdir -p oracle/_build
+	g++ -O3 -march=x86-64-v3 -ffp-contract=off -std=c++17 -shared -fPIC -o $@ $<
 
 # host-side on-disk formats (PNG/CSV readers, links zlib) and the C++ batched replay driver (app/larvioMain.cpp's role)
 $(IOLIB): larvio_b200/host/lvb_io.cpp include/larvio_b200.h
@@ -45,4 +56,4 @@ $(LIB): $(OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart -lpthread
 
 clean:
-	rm -f larvio_b200/csrc/*.o larvio_b200/csrc/*.o.log $(LIB) $(IOLIB) $(REPLAY) $(SHIMDEMO)
+	rm -f larvio_b200/csrc/*.o larvio_b200/csrc/*.o.log $(LIB) $(IOLIB) $(REPLAY) $(SHIMDEMO) $(ORACLE_C)

@@ -163,9 +163,12 @@ def _cpu_worker(conn, cfg_raw, seqs):
         pass
     from oracle.frontend import ImageProcessorOracle
     from oracle.backend import LarVioOracle
+    from oracle import backend_c, orb
+    orb.use_compiled(True)                # compiled ORB (oracle/orb_c.cpp), bit-identical to the numpy one
+    BE = backend_c.LarVioOracleC if backend_c.supported(cfg_raw) else LarVioOracle      # compiled filter where it covers the config
     st = []
     for sq in seqs:
-        st.append(dict(fe=ImageProcessorOracle(cfg_raw), be=LarVioOracle(cfg_raw), imu=[], k=0, seq=sq, t_fe=0.0, t_be=0.0, n_be=0))
+        st.append(dict(fe=ImageProcessorOracle(cfg_raw), be=BE(cfg_raw), imu=[], k=0, seq=sq, t_fe=0.0, t_be=0.0, n_be=0))
         st[-1]["be"].set_initial_state(sq.img_t[0], sq.gt_q[0], sq.gt_p[0], sq.gt_v[0], np.zeros(3), np.zeros(3))
     conn.send("ready")
     while True:
@@ -195,8 +198,18 @@ def _cpu_worker(conn, cfg_raw, seqs):
             s["t_fe"] = s["t_be"] = 0.0; s["n_be"] = 0
 
 
+def cpu_arm_description(cfg_raw):
+    """What the CPU arm runs (cpu_baseline.sample): the oracle with its compiled pieces switched on."""
+    from oracle import backend_c
+    if backend_c.supported(cfg_raw):
+        return "cv2 4.13 C++ for the OpenCV calls + compiled ORB (oracle/orb_c.cpp) + compiled filter (oracle/backend_c.cpp, g++ -O3, pinned to the numpy oracle to 1e-9), Python glue"
+    return "cv2 4.13 C++ for the OpenCV calls + compiled ORB (oracle/orb_c.cpp) + numpy f64 filter (oracle/backend.py: the compiled filter covers pure MSCKF only), Python glue"
+
+
 class CpuArm:
     def __init__(self, cfg_raw, seqs, cores):
+        from oracle import backend_c, orb
+        backend_c.load(); orb.use_compiled(True); orb.use_compiled(False)      # build the compiled oracle pieces once, before forking
         ctx = mp.get_context("fork")
         self.cores = min(cores, len(seqs))
         self.conns = []; self.procs = []
@@ -348,7 +361,7 @@ def main():
                     ms_per_step=1e3 * dt / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8+f32 front end, f64 filter",
                     data="synthetic", config=config, impl="reference",
                     cpu_baseline=dict(value=val, unit="frames/s", cores=arm.cores, kind="port", os_cpu_count=os.cpu_count(), worker_cpu_utilisation=util,
-                                      sample="%d sequences x %d frames after a %d-frame pre-roll, cv2 4.13 front end + numpy f64 back end (oracle/), one worker process per core" % (S, K, PR + Wm),
+                                      sample="%d sequences x %d frames after a %d-frame pre-roll; %s; one worker process per core" % (S, K, PR + Wm, cpu_arm_description(cfg.raw)),
                                       fe_ms_per_frame=1e3 * tfe / (S * K), be_ms_per_update=1e3 * tbe / max(nbe, 1)),
                     e2e=dict(value=val, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
@@ -376,7 +389,7 @@ def main():
         util = arm.last_util
         arm.close()
         cpu_baseline = dict(value=ncpu * nf / dt, unit="frames/s", cores=arm.cores, kind="port", os_cpu_count=os.cpu_count(), worker_cpu_utilisation=util,
-                            sample="%d sequences (one per core) x %d frames after a %d-frame pre-roll of the same workload; cv2 4.13 front end + numpy f64 back end (oracle/)" % (ncpu, nf, PR),
+                            sample="%d sequences (one per core) x %d frames after a %d-frame pre-roll of the same workload; %s" % (ncpu, nf, PR, cpu_arm_description(cfg.raw)),
                             fe_ms_per_frame=1e3 * tfe / (ncpu * nf), be_ms_per_update=1e3 * tbe / max(nbe, 1))
 
     import torch

@@ -1,0 +1,133 @@
+"""ctypes wrapper of oracle/backend_c.cpp - the compiled CPU oracle of LarVio::processFeatures (TEST INFRASTRUCTURE, see
+oracle/__init__.py).  Same driving interface as oracle.backend.LarVioOracle for what bench.py's CPU legs and the tests use
+(``set_initial_state``, ``process_features(msg, imu_list)``, ``imu_state``, ``P``, ``aug``-count, ``td``); restricted to the
+configuration BASELINE.json's metric is quoted on: pure MSCKF, no IMU-intrinsic calibration.  ``supported(cfg_raw)`` says
+whether a config is inside that scope; outside it callers keep the numpy oracle."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "oracle", "backend_c.cpp")
+LIB = os.path.join(ROOT, "oracle", "_build", "liboracle_backend.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """g++ -O3 -march=x86-64-v3: AVX2 + FMA, portable between the build container and the GPU box's host CPU (the .so
+    travels with the snapshot; the reference's own CMakeLists builds with -O3 -march=native)."""
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(SRC):
+        os.makedirs(os.path.dirname(LIB), exist_ok=True)
+        subprocess.run(["g++", "-O3", "-march=x86-64-v3", "-std=c++17", "-shared", "-fPIC", "-o", LIB, SRC], check=True)
+    return LIB
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            build()
+        L = ctypes.CDLL(LIB)
+        L.lvo_create.restype = ctypes.c_void_p
+        L.lvo_create.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.lvo_destroy.argtypes = [ctypes.c_void_p]
+        L.lvo_set_initial_state.argtypes = [ctypes.c_void_p, ctypes.c_double] + [ctypes.c_void_p] * 5
+        L.lvo_process_features.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.lvo_get_state.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.lvo_dim.argtypes = [ctypes.c_void_p]
+        L.lvo_get_cov.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.lvo_counter.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.lvo_counter.restype = ctypes.c_longlong
+        _lib = L
+    return _lib
+
+
+def supported(r: dict) -> bool:
+    hybrid = max(int(r["max_features_in_one_grid"]), 0) * int(r["aug_grid_rows"]) * int(r["aug_grid_cols"]) != 0
+    return not hybrid and not int(r["calib_imu_instrinsic"])
+
+
+def _cfg_vector(r: dict) -> np.ndarray:
+    from scipy.stats import chi2
+    v = [r["imu_rate"], r["rotation_threshold"], r["translation_threshold"], r["tracking_rate_threshold"],
+         r["feature_translation_threshold"], r["td"],
+         r["noise_gyro"], r["noise_acc"], r["noise_gyro_bias"], r["noise_acc_bias"], r["noise_feature"],
+         r["initial_covariance_orientation"], r["initial_covariance_velocity"], r["initial_covariance_position"],
+         r["initial_covariance_gyro_bias"], r["initial_covariance_acc_bias"], r["initial_covariance_extrin_rot"],
+         r["initial_covariance_extrin_trans"],
+         r["zupt_max_feature_dis"], r["zupt_noise_v"], r["zupt_noise_p"], r["zupt_noise_q"],
+         r["max_track_len"], r["sw_size"], r["least_observation_number"], r["if_FEJ"], r["estimate_td"], r["estimate_extrin"],
+         r["if_ZUPT_valid"]]
+    v = [float(x) for x in v]
+    v += [float(x) for x in np.array(r["T_cam_imu"]["data"], np.float64).reshape(16)]
+    v += [0.0] + [float(chi2.ppf(0.05, i)) for i in range(1, 100)]          # boost chi_squared quantile(0.05) (larvio.cpp:353-357)
+    return np.array(v, np.float64)
+
+
+class LarVioOracleC:
+    def __init__(self, cfg_raw: dict):
+        if not supported(cfg_raw):
+            raise NotImplementedError("the compiled oracle covers pure MSCKF without IMU-intrinsic calibration")
+        self.L = load()
+        vec = _cfg_vector(cfg_raw)
+        assert len(vec) == self.L.lvo_cfg_doubles()
+        self.h = self.L.lvo_create(vec.ctypes.data, len(vec))
+        if not self.h:
+            raise RuntimeError("lvo_create failed")
+        self.is_gravity_set = False
+        self.stats = {}
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.lvo_destroy(self.h); self.h = None
+
+    def set_initial_state(self, t, q_xyzw, p, v, bg, ba):
+        a = [np.ascontiguousarray(x, np.float64) for x in (q_xyzw, p, v, bg, ba)]
+        self.L.lvo_set_initial_state(self.h, float(t), *[x.ctypes.data for x in a])
+        self.is_gravity_set = True
+
+    def process_features(self, msg, imu: list) -> bool:
+        """imu: list of rows [t, w(3), a(3)], consumed samples are erased like larvio.cpp:510-512."""
+        ids = np.ascontiguousarray(msg.ids, np.int64)
+        data = np.ascontiguousarray(msg.data, np.float64).reshape(-1, 8)
+        im = np.ascontiguousarray(np.array(imu, np.float64).reshape(-1, 7))
+        used = ctypes.c_int(0)
+        ok = self.L.lvo_process_features(self.h, float(msg.t), ids.ctypes.data, data.ctypes.data, len(ids), im.ctypes.data, len(im),
+                                         ctypes.byref(used))
+        del imu[:used.value]
+        return bool(ok)
+
+    def _state(self):
+        out = np.zeros(31)
+        self.L.lvo_get_state(self.h, out.ctypes.data)
+        return out
+
+    @property
+    def imu_state(self):
+        o = self._state()
+        return types.SimpleNamespace(time=o[0], q=o[1:5].copy(), p=o[5:8].copy(), v=o[8:11].copy(), bg=o[11:14].copy(), ba=o[14:17].copy(),
+                                     R_imu_cam0=o[17:26].reshape(3, 3).copy(), t_cam0_imu=o[26:29].copy())
+
+    @property
+    def td(self):
+        return float(self._state()[29])
+
+    @property
+    def n_window(self):
+        return int(self._state()[30])
+
+    @property
+    def P(self):
+        d = self.L.lvo_dim(self.h)
+        out = np.zeros((d, d))
+        self.L.lvo_get_cov(self.h, out.ctypes.data)
+        return out
+
+    def counter(self, which):          # 0 updates, 1 ZUPT events, 2 features in the map
+        return int(self.L.lvo_counter(self.h, which))

@@ -161,16 +161,17 @@ class ImageProcessorOracle:
             return np.zeros((0, 2), f32)
         K = np.array([[self.intr[0], 0, self.intr[2]], [0, self.intr[1], self.intr[3]], [0, 0, 1]], np.float64).astype(f32)
         H = _mm33_f32(_mm33_f32(K, self.R_p2c), _inv33_f32(K))
+        # H * (x, y, 1) in float32, products and sums rounded one by one like the Matx/Point3f arithmetic (vectorised over points:
+        # numpy float32 array ops round after every operation, exactly like the scalar loop they replace)
+        x = np.ascontiguousarray(pts[:, 0], f32); y = np.ascontiguousarray(pts[:, 1], f32)
+        q = []
+        for r in range(3):
+            sacc = H[r, 0] * x
+            sacc = sacc + H[r, 1] * y
+            sacc = sacc + f32(H[r, 2] * f32(1.0))
+            q.append(sacc.astype(f32))
         out = np.zeros((len(pts), 2), f32)
-        for i, p in enumerate(pts):
-            v = [f32(p[0]), f32(p[1]), f32(1.0)]
-            q = []
-            for r in range(3):
-                s = f32(0)
-                for k in range(3):
-                    s = f32(s + f32(H[r, k] * v[k]))
-                q.append(s)
-            out[i, 0] = f32(q[0] / q[2]); out[i, 1] = f32(q[1] / q[2])
+        out[:, 0] = q[0] / q[2]; out[:, 1] = q[1] / q[2]
         return out
 
     def _lk(self, img_a, img_b, pts_a, init_b):
@@ -184,26 +185,19 @@ class ImageProcessorOracle:
     def _in_image(self, pts, st):
         h, w = self.curr_img.shape
         st = st.copy()
-        for i in range(len(pts)):
-            if st[i] == 0:
-                continue
-            if pts[i, 1] < 0 or pts[i, 1] > h - 1 or pts[i, 0] < 0 or pts[i, 0] > w - 1:
-                st[i] = 0
+        if len(pts):
+            out = (pts[:, 1] < 0) | (pts[:, 1] > h - 1) | (pts[:, 0] < 0) | (pts[:, 0] > w - 1)
+            st[out & (st != 0)] = 0
         return st
 
     def _reverse_check(self, curr_in, prev_in):
         back, st = self._lk(self.curr_img, self.prev_img, curr_in, prev_in.copy())
         h, w = self.prev_img.shape
-        for i in range(len(back)):
-            if st[i] == 0:
-                continue
-            if back[i, 1] < 0 or back[i, 1] > h - 1 or back[i, 0] < 0 or back[i, 0] > w - 1:
-                st[i] = 0
-                continue
-            d = (back[i] - prev_in[i]).astype(f32)                  # Point2f difference
-            dis = f32(np.sqrt(np.float64(d[0]) * np.float64(d[0]) + np.float64(d[1]) * np.float64(d[1])))
-            if dis > 1:
-                st[i] = 0
+        if len(back):
+            out = (back[:, 1] < 0) | (back[:, 1] > h - 1) | (back[:, 0] < 0) | (back[:, 0] > w - 1)
+            d = (back - prev_in).astype(f32)                                  # Point2f difference
+            dis = np.sqrt(d[:, 0].astype(np.float64) * d[:, 0].astype(np.float64) + d[:, 1].astype(np.float64) * d[:, 1].astype(np.float64)).astype(f32)
+            st[(st != 0) & (out | (dis > 1))] = 0
         return st
 
     def _undistort(self, pts, to_pixels: bool):

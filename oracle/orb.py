@@ -39,6 +39,33 @@ _DISC_V = np.concatenate([np.full(2 * UMAX[abs(v)] + 1, v) for v in range(-HALF_
 _DISC_U = np.concatenate([np.arange(-UMAX[abs(v)], UMAX[abs(v)] + 1) for v in range(-HALF_PATCH, HALF_PATCH + 1)]).astype(np.int64)
 
 
+# The compiled twin (oracle/orb_c.cpp): bench.py's CPU legs switch it on with ``use_compiled(True)`` so that they time compiled
+# code; the numpy path below stays the default and is what the parity tests use (the two are pinned bit for bit in tests/test_cpu.py).
+_C = None
+_USE_C = False
+_UMAX32 = None
+_PATTERN32 = None
+
+
+def use_compiled(on: bool = True):
+    """Route ``OrbOracle.compute`` / ``hamming_rows`` through oracle/_build/liboracle_orb.so (built on demand with g++)."""
+    global _C, _USE_C, _UMAX32, _PATTERN32
+    if on and _C is None:
+        import ctypes
+        import subprocess
+        here = os.path.dirname(os.path.abspath(__file__))
+        lib = os.path.join(here, "_build", "liboracle_orb.so"); src = os.path.join(here, "orb_c.cpp")
+        if not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(src):
+            os.makedirs(os.path.dirname(lib), exist_ok=True)
+            subprocess.run(["g++", "-O3", "-march=x86-64-v3", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-o", lib, src], check=True)
+        _C = ctypes.CDLL(lib)
+        _C.orbc_compute.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _C.orbc_hamming_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        _UMAX32 = np.array(UMAX, np.int32); _PATTERN32 = np.ascontiguousarray(_PATTERN, np.int32)
+    _USE_C = bool(on)
+
+
 class OrbOracle:
     """One instance per image, like ``new ORBdescriptor(curr_pyramid_[0], 2, levels)``."""
 
@@ -104,6 +131,12 @@ class OrbOracle:
         n = len(pts)
         if n == 0:
             return np.zeros((0, 32), np.uint8)
+        if _USE_C:
+            pts = np.ascontiguousarray(pts); out = np.zeros((n, 32), np.uint8)
+            assert self.raw.flags.c_contiguous and self.blur.flags.c_contiguous
+            _C.orbc_compute(self.raw.ctypes.data, self.blur.ctypes.data, self.raw.shape[1], BORDER, pts.ctypes.data, n,
+                            _PATTERN32.ctypes.data, _UMAX32.ctypes.data, out.ctypes.data, None)
+            return out
         ang = (self.angles(pts) * FACTOR_PI).astype(np.float32)
         a = np.cos(ang.astype(np.float64)).astype(np.float32)[:, None, None]
         b = np.sin(ang.astype(np.float64)).astype(np.float32)[:, None, None]
@@ -124,4 +157,8 @@ def hamming(a: np.ndarray, b: np.ndarray) -> int:
 
 
 def hamming_rows(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    if _USE_C and len(a):
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8); out = np.zeros(len(a), np.int32)
+        _C.orbc_hamming_rows(a.ctypes.data, b.ctypes.data, len(a), out.ctypes.data)
+        return out
     return np.unpackbits(np.bitwise_xor(a, b), axis=1).sum(1).astype(np.int32)

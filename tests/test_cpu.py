@@ -658,3 +658,82 @@ def test_shard_and_gather_two_ranks_gloo():
     assert out[0][2] == [float(i) for i in range(10)] and out[1][2] is None
     assert out[0][3] == b"abc" and out[1][3] == b"abc"
     assert out[0][4] and out[1][4]
+
+
+def _compare_compiled_backend(cfg_raw, seq, nf):
+    """Drive oracle/backend.py (numpy) and oracle/backend_c.cpp (compiled) with the same front-end messages."""
+    import copy
+    from oracle.frontend import ImageProcessorOracle
+    from oracle.backend import LarVioOracle
+    from oracle.backend_c import LarVioOracleC
+    from larvio_b200 import synth
+    fe = ImageProcessorOracle(cfg_raw); a = LarVioOracle(cfg_raw); b = LarVioOracleC(cfg_raw)
+    imu_a, imu_b, k = [], [], 0
+    w = dict(p=0.0, v=0.0, q=0.0, bias=0.0, P=0.0, ext=0.0, steps=0, max_dim=0)
+    for j in range(nf):
+        k2 = synth.imu_window(seq, k, seq.img_t[j]); rows = seq.imu[k:k2].tolist(); k = k2
+        imu_a.extend(rows); imu_b.extend(copy.deepcopy(rows))
+        msg = fe.process_image(seq.images[j], seq.img_t[j], np.array(imu_a).reshape(-1, 7))
+        if msg is None:
+            continue
+        if not a.is_gravity_set:
+            for o in (a, b):
+                o.set_initial_state(seq.img_t[j], seq.gt_q[j], seq.gt_p[j], seq.gt_v[j], np.zeros(3), np.zeros(3))
+        oka = a.process_features(msg, imu_a); okb = b.process_features(msg, imu_b)
+        assert oka == okb and len(imu_a) == len(imu_b)                      # same consumed IMU samples (larvio.cpp:510-512)
+        if not oka:
+            continue
+        sa, sb, Pa, Pb = a.imu_state, b.imu_state, a.P, b.P
+        assert Pa.shape == Pb.shape and len(a.aug) == b.n_window and len(a.map_server) == b.counter(2)
+        w['steps'] += 1; w['max_dim'] = max(w['max_dim'], Pa.shape[0])
+        w['p'] = max(w['p'], float(np.abs(sa.p - sb.p).max())); w['v'] = max(w['v'], float(np.abs(sa.v - sb.v).max()))
+        w['q'] = max(w['q'], float(min(np.abs(sa.q - sb.q).max(), np.abs(sa.q + sb.q).max())))
+        w['bias'] = max(w['bias'], float(max(np.abs(sa.bg - sb.bg).max(), np.abs(sa.ba - sb.ba).max())))
+        w['ext'] = max(w['ext'], float(max(np.abs(sa.R_imu_cam0 - sb.R_imu_cam0).max(), np.abs(sa.t_cam0_imu - sb.t_cam0_imu).max(), abs(a.td - b.td))))
+        w['P'] = max(w['P'], float(np.linalg.norm(Pa - Pb) / np.linalg.norm(Pa)))
+    w['zupt'] = (a.zupt_events, b.counter(1))
+    return w
+
+
+def test_compiled_backend_matches_the_numpy_oracle(cfg):
+    """oracle/backend_c.cpp (what bench.py's CPU legs time) against oracle/backend.py (the parity oracle): 64 frames with a
+    12-pose window (augmentation, triangulation, gating, QR compression, update, pruning) - pose, biases, extrinsics, td and
+    covariance to 1e-9, identical bookkeeping (consumed IMU samples, window length, map size)."""
+    from larvio_b200 import synth
+    from larvio_b200.config import Config
+    c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), max_features_in_one_grid=0, sw_size=12)
+    w = _compare_compiled_backend(c.raw, synth.make_sequence(c.raw, 0, 64), 64)
+    assert w['steps'] >= 30 and w['max_dim'] >= 22 + 6 * 11
+    assert max(w['p'], w['v'], w['q'], w['bias'], w['ext']) < 1e-9 and w['P'] < 1e-9, w
+
+
+def test_compiled_backend_zupt_matches_the_numpy_oracle(cfg):
+    """checkZUPT / measurementUpdate_ZUPT_vpq (larvio.cpp:2751-2962) in the compiled oracle: one second of standstill, then motion."""
+    from larvio_b200 import synth
+    w = _compare_compiled_backend(cfg.raw if not int(cfg.raw["max_features_in_one_grid"]) else dict(cfg.raw, max_features_in_one_grid=0),
+                                  synth.make_sequence(cfg.raw, 5, 34, static_until=1.0), 34)
+    assert w['steps'] >= 14 and w['zupt'][0] == w['zupt'][1] and w['zupt'][0] >= 3, w
+    assert max(w['p'], w['v'], w['q'], w['bias'], w['ext']) < 1e-9 and w['P'] < 1e-9, w
+
+
+def test_compiled_orb_equals_the_numpy_restatement(cfg):
+    """oracle/orb_c.cpp (what bench.py's CPU legs run) against oracle/orb.py: angles, 256-bit descriptors and Hamming distances
+    bit for bit, incl. points on the image border and on .5 rounding ties."""
+    import cv2
+    from oracle import orb
+    from larvio_b200 import synth
+    img = cv2.createCLAHE(3.0, (8, 8)).apply(synth.make_sequence(cfg.raw, 3, 1).images[0])
+    rng = np.random.default_rng(0)
+    pts = np.stack([rng.uniform(0, 751, 1500), rng.uniform(0, 479, 1500)], 1).astype(np.float32)
+    pts[:50] = np.round(pts[:50]) + 0.5
+    pts[50:58] = [[0, 0], [751, 479], [0, 479], [751, 0], [0.5, 0.5], [750.5, 478.5], [1.5, 2.5], [2.5, 1.5]]
+    o = orb.OrbOracle(img)
+    try:
+        orb.use_compiled(False)
+        d0 = o.compute(pts); h0 = orb.hamming_rows(d0[:700], d0[700:1400])
+        orb.use_compiled(True)
+        d1 = o.compute(pts); h1 = orb.hamming_rows(d0[:700], d0[700:1400])
+    finally:
+        orb.use_compiled(False)
+    assert np.array_equal(d0, d1) and np.array_equal(h0, h1)
+    assert np.array_equal(d0[:40], o.compute_loop(pts[:40]))               # and both equal the literal per-point restatement
