@@ -2514,8 +2514,9 @@ int be_alloc(LvbHandle* h) {
   LVB_CUDA(cudaFuncSetAttribute(be_feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm_bytes));
   LVB_CUDA(cudaFuncSetAttribute(be_propagate_kernel<22>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be_propagate_smem(22)));
   LVB_CUDA(cudaFuncSetAttribute(be_propagate_kernel<46>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be_propagate_smem(46)));
-  // with the nonzero-column compression r stays near 50..110 rows whatever the window; 192 rows of packed triangle = 148 KB
-  be->chol_cap = be->LDS < 192 ? be->LDS : 192;
+  // with the nonzero-column compression r stays near 50..110 rows whatever the window; the pure-MSCKF BASELINE window (LDS 208)
+  // fits entirely, so be_chol_gmem_kernel is not even launched there
+  be->chol_cap = be->LDS < 224 ? be->LDS : 224;          // 224 rows of packed triangle + 2 vectors = 205 KB of the 227 KB a CTA can have
   const size_t chol_bytes = sizeof(double) * ((size_t)be->chol_cap * (be->chol_cap + 1) / 2 + 2 * be->chol_cap);
   LVB_CUDA(cudaFuncSetAttribute(be_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_bytes));
   h->use_graph = getenv("LVB_NO_GRAPH") ? 0 : 1;          // one CUDA graph launch per step (lvb_step_graph); the env switch is for debugging
@@ -2585,7 +2586,7 @@ static int be_update(LvbHandle* h, BeView& v, bool zupt_rows = false, bool resca
   be_chol_kernel<<<be->S, 1024, chol_bytes, st>>>(v);
   LVB_LAUNCH_CHECK(h);
   DBG("be_chol_kernel");
-  if (be->LDS > be->chol_cap) {                  // innovation systems beyond the shared-memory capacity (rare: > 192 rows)
+  if (be->LDS > be->chol_cap) {                  // innovation systems beyond the shared-memory capacity (rare: > 224 rows)
     LVB_PROF(h, "be_chol_gmem_kernel");
     be_chol_gmem_kernel<<<be->S, 512, sizeof(double) * be->LDS, st>>>(v, be->chol_cap);
     LVB_LAUNCH_CHECK(h);

@@ -330,6 +330,18 @@ def test_hybrid_3d_inverse_depth_slam_features_match_oracle(lib_built):
     assert rep['p'] < 1e-8 and rep['v'] < 1e-8 and rep['q'] < 1e-8 and rep['Prel'] < 1e-8
 
 
+def test_hybrid_3d_inverse_depth_with_online_calibration(lib_built):
+    """configs[3]'s switches with the other parameterisation: 3-D inverse depth + estimate_extrin/td + IMU-intrinsic calibration
+    (LEG_DIM 46: the feature blocks start behind 46 + 6N columns)."""
+    from larvio_b200 import synth
+    from larvio_b200.config import Config
+    cc = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), sw_size=16, calib_imu_instrinsic=1, feature_idp_dim=3)
+    cs = [synth.make_sequence(cc.raw, s, 124) for s in range(2)]
+    rep = _drive(cc, cs, 124, 'step')
+    assert rep['steps'] >= 58 and rep['ok_mismatch'] == 0 and rep['imu_mismatch'] == 0 and rep['max_slam'] >= 5
+    assert rep['p'] < 1e-8 and rep['v'] < 1e-8 and rep['q'] < 1e-8 and rep['Prel'] < 1e-8 and rep['calib'] < 1e-9
+
+
 def test_imu_intrinsic_calibration_matches_oracle(lib_built):
     """calib_imu_instrinsic: 1 -> LEG_DIM 46 (larvio.cpp:158-161): the 24 Tg/As/Ma states are propagated (calPhi
     :3532-3797) and corrected (:1497-1507) exactly like the oracle's, in pure-MSCKF mode."""
