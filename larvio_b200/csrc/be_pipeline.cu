@@ -1386,24 +1386,83 @@ __global__ void __launch_bounds__(256) be_slam_grow_kernel(BeView v) {
 }
 
 // ====================================================================== QR compression (SPQR thin QR at larvio.cpp:1430-1449, 2151-2171)
-// Householder, column by column over the structurally nonzero columns (kmap), on the column-major stack; warp-shuffle dot
-// products, one warp per trailing column.  2 block barriers per column: the warp that updates column j+1 also leaves its
-// squared norm below the diagonal and its diagonal entry in shared memory, so iteration j+1 starts without a reduction pass;
-// every thread derives (alpha, beta) from those two numbers itself; the finished column is zeroed while the reflector is
-// copied out.  (A 5-barrier version with a single-thread section measured 66 us vs 53 us per 16-sequence launch, round 2.)
+// Householder, column by column over the structurally nonzero columns (kmap), one warp per trailing column with warp-shuffle dot
+// products.  The panel [nc + 1 columns (H | r)][R rows] is staged into shared memory (column-major, <= QR_SMEM_DOUBLES) and
+// factorised there with ONE block barrier per column: the reflector is read in place (its first entry is the only one that
+// differs from the column, and every thread derives (alpha, v0, beta) itself from the column's squared norm and diagonal, which
+// the warp that updated that column left in shared memory during the previous iteration), and the finished column is never
+// rewritten - the triangular factor is assembled on the way back to global memory.  Panels that do not fit (R * (nc + 1) beyond
+// the capacity: hundreds of tracks consumed in one frame) take the same algorithm on the global column-major stack with two
+// barriers per column.  (Round 2: 5-barrier global version 66 us, 2-barrier global version 53 us per 16-sequence launch.)
+constexpr int QR_SMEM_DOUBLES = 26000;               // 203 KB of the 227 KB a CTA can have
+
 __global__ void __launch_bounds__(512) be_qr_kernel(BeView v) {
-  extern __shared__ double qsm[];      // reflector [RMAX]
+  extern __shared__ double qsm[];      // panel [(c + 1)][R] (shared-memory path) or reflector [RMAX] (global path)
   __shared__ double red[16];
   __shared__ double s_n2, s_x0;
+  __shared__ double s_nb[2], s_xb[2];      // shared-memory path: (norm^2, diagonal) of the next column, double-buffered by column parity
+  __shared__ double s_diag[BE_DMAX_PAD];
   const int s = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int* ic = icore_of(v, s);
   if (!ic[I_OK]) return;
-  const int R = ic[I_ROWS], c = ic[I_NC];        // compression over the structurally nonzero columns only (be_colscan_kernel)
+  const int R = ic[I_ROWS], c = ic[I_NC];        // compression over the structurally nonzero columns only (be_stack_kernel / be_colscan_kernel)
   if (R <= c || R == 0) return;
   const int RMAX = v.be.RMAX, LD = v.be.LD;
   double* Hs = v.be.Hs + (size_t)s * LD * RMAX;
   double* rs = v.be.rs + (size_t)s * RMAX;
   const int* km = v.be.kmap + (size_t)s * LD;
+  const bool in_smem = (size_t)R * (c + 1) <= (size_t)QR_SMEM_DOUBLES && (size_t)RMAX <= (size_t)QR_SMEM_DOUBLES;
+  if (in_smem) {
+    for (int k = warp; k <= c; k += 16) {
+      const double* src = (k < c) ? Hs + (size_t)km[k] * RMAX : rs;
+      double* dst = qsm + (size_t)k * R;
+      for (int i = lane; i < R; i += 32) dst[i] = src[i];
+    }
+    __syncthreads();
+    {                                                    // column 0: the only block-wide reduction
+      double part = 0.0;
+      for (int i = tid; i < R; i += 512) { const double x = qsm[i]; part += x * x; }
+      part = warp_sum_d(part);
+      if (lane == 0) red[warp] = part;
+      __syncthreads();
+      if (tid == 0) { double n2 = 0.0; for (int w = 0; w < 16; ++w) n2 += red[w]; s_nb[0] = n2; s_xb[0] = qsm[0]; }
+      __syncthreads();
+    }
+    for (int j = 0; j < c; ++j) {
+      const double* cj = qsm + (size_t)j * R;
+      const double n2 = s_nb[j & 1], x0 = s_xb[j & 1];   // squared norm of rows >= j of column j, and its diagonal entry
+      const double nrm = sqrt(n2);
+      const double alpha = x0 >= 0 ? -nrm : nrm;
+      const double v0 = x0 - alpha;
+      const double vtv = n2 - x0 * x0 + v0 * v0;
+      const double beta = vtv > 0.0 ? 2.0 / vtv : 0.0;
+      if (tid == 0) s_diag[j] = alpha;
+      for (int k = j + 1 + warp; k <= c; k += 16) {
+        double* ck = qsm + (size_t)k * R;
+        if (beta != 0.0) {
+          double dt_ = 0.0;
+          for (int i = j + lane; i < R; i += 32) dt_ += ((i == j) ? v0 : cj[i]) * ck[i];
+          dt_ = warp_sum_d(dt_) * beta;
+          for (int i = j + lane; i < R; i += 32) ck[i] -= dt_ * ((i == j) ? v0 : cj[i]);
+        }
+        if (k == j + 1 && k < c) {                       // hand the next column's norm and diagonal to the next iteration
+          __syncwarp();
+          double part = 0.0;
+          for (int i = j + 1 + lane; i < R; i += 32) { const double x = ck[i]; part += x * x; }
+          part = warp_sum_d(part);
+          if (lane == 0) { s_nb[(j + 1) & 1] = part; s_xb[(j + 1) & 1] = ck[j + 1]; }      // the other buffer: slower warps may still read this column's
+        }
+      }
+      __syncthreads();
+    }
+    // the triangular factor (rows < c) and Q^T r back to the global stack; rows >= c are dead after I_R = c
+    for (int k = warp; k <= c; k += 16) {
+      const double* src = qsm + (size_t)k * R;
+      double* dst = (k < c) ? Hs + (size_t)km[k] * RMAX : rs;
+      if (k < c) { for (int i = lane; i < c; i += 32) dst[i] = (i < k) ? src[i] : (i == k ? s_diag[k] : 0.0); }
+      else { for (int i = lane; i < c; i += 32) dst[i] = src[i]; }
+    }
+  } else {
   {                                                    // column 0: the only block-wide reduction
     double part = 0.0;
     for (int i = tid; i < R; i += 512) { const double x = Hs[(size_t)km[0] * RMAX + i]; part += x * x; }
@@ -1444,6 +1503,7 @@ __global__ void __launch_bounds__(512) be_qr_kernel(BeView v) {
       }
     }
     __syncthreads();
+  }
   }
   if (tid == 0) {
     ic[I_R] = c;
@@ -2512,6 +2572,7 @@ int be_alloc(LvbHandle* h) {
   // dynamic shared memory opt-ins
   const int fsm_bytes = (int)sizeof(double) * (6 * be->Wcap + 8 + 4 * be->Wcap * be->Wcap + 2 * be->Wcap + (8 + 6 * be->Wcap) / 2 + 4);
   LVB_CUDA(cudaFuncSetAttribute(be_feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm_bytes));
+  LVB_CUDA(cudaFuncSetAttribute(be_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * QR_SMEM_DOUBLES)));
   LVB_CUDA(cudaFuncSetAttribute(be_propagate_kernel<22>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be_propagate_smem(22)));
   LVB_CUDA(cudaFuncSetAttribute(be_propagate_kernel<46>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be_propagate_smem(46)));
   // with the nonzero-column compression r stays near 50..110 rows whatever the window; the pure-MSCKF BASELINE window (LDS 208)
@@ -2552,7 +2613,7 @@ static int be_colscan(LvbHandle* h, BeView& v, int rows_idx) {
 
 static int be_qr(LvbHandle* h, BeView& v) {       // kmap / I_NC of the MSCKF block come from be_stack_kernel(phase 0)
   LVB_PROF(h, "be_qr_kernel");
-  be_qr_kernel<<<h->be->S, 512, sizeof(double) * h->be->RMAX, h->stream>>>(v);
+  be_qr_kernel<<<h->be->S, 512, sizeof(double) * QR_SMEM_DOUBLES, h->stream>>>(v);
   LVB_LAUNCH_CHECK(h);
   return LVB_OK;
 }
