@@ -1411,11 +1411,14 @@ __global__ void __launch_bounds__(512) be_qr_kernel(BeView v) {
   double* Hs = v.be.Hs + (size_t)s * LD * RMAX;
   double* rs = v.be.rs + (size_t)s * RMAX;
   const int* km = v.be.kmap + (size_t)s * LD;
-  const bool in_smem = (size_t)R * (c + 1) <= (size_t)QR_SMEM_DOUBLES && (size_t)RMAX <= (size_t)QR_SMEM_DOUBLES;
+  // column stride in shared memory: R rounded up to 8 (mod 16) doubles, so that the 4 lane groups of a warp (below) hit the 32
+  // banks in two wavefronts, the minimum for 32 x 8 bytes
+  const int Rp = ((R + 7) / 16) * 16 + 8;
+  const bool in_smem = (size_t)Rp * (c + 1) <= (size_t)QR_SMEM_DOUBLES && (size_t)RMAX <= (size_t)QR_SMEM_DOUBLES;
   if (in_smem) {
     for (int k = warp; k <= c; k += 16) {
       const double* src = (k < c) ? Hs + (size_t)km[k] * RMAX : rs;
-      double* dst = qsm + (size_t)k * R;
+      double* dst = qsm + (size_t)k * Rp;
       for (int i = lane; i < R; i += 32) dst[i] = src[i];
     }
     __syncthreads();
@@ -1428,8 +1431,12 @@ __global__ void __launch_bounds__(512) be_qr_kernel(BeView v) {
       if (tid == 0) { double n2 = 0.0; for (int w = 0; w < 16; ++w) n2 += red[w]; s_nb[0] = n2; s_xb[0] = qsm[0]; }
       __syncthreads();
     }
+    // G lanes per trailing column: with the usual ~50 nonzero columns every trailing column (and r) has its own group of 8 lanes,
+    // so one pass of the block covers them all; fewer columns get wider groups
+    const int G = (c + 1 <= 16) ? 32 : (c + 1 <= 32) ? 16 : 8;
+    const int gpw = 32 / G, grp = lane / G, gl = lane - grp * G;
     for (int j = 0; j < c; ++j) {
-      const double* cj = qsm + (size_t)j * R;
+      const double* cj = qsm + (size_t)j * Rp;
       const double n2 = s_nb[j & 1], x0 = s_xb[j & 1];   // squared norm of rows >= j of column j, and its diagonal entry
       const double nrm = sqrt(n2);
       const double alpha = x0 >= 0 ? -nrm : nrm;
@@ -1437,27 +1444,28 @@ __global__ void __launch_bounds__(512) be_qr_kernel(BeView v) {
       const double vtv = n2 - x0 * x0 + v0 * v0;
       const double beta = vtv > 0.0 ? 2.0 / vtv : 0.0;
       if (tid == 0) s_diag[j] = alpha;
-      for (int k = j + 1 + warp; k <= c; k += 16) {
-        double* ck = qsm + (size_t)k * R;
-        if (beta != 0.0) {
-          double dt_ = 0.0;
-          for (int i = j + lane; i < R; i += 32) dt_ += ((i == j) ? v0 : cj[i]) * ck[i];
-          dt_ = warp_sum_d(dt_) * beta;
-          for (int i = j + lane; i < R; i += 32) ck[i] -= dt_ * ((i == j) ? v0 : cj[i]);
-        }
-        if (k == j + 1 && k < c) {                       // hand the next column's norm and diagonal to the next iteration
+      for (int kb = j + 1 + warp * gpw; kb <= c; kb += 16 * gpw) {      // warp-uniform trip count: the shuffles below use the full mask
+        const int k = kb + grp;
+        const bool act = k <= c;
+        double* ck = qsm + (size_t)(act ? k : j) * Rp;
+        double dt_ = 0.0;
+        if (act) for (int i = j + gl; i < R; i += G) dt_ += ((i == j) ? v0 : cj[i]) * ck[i];
+        for (int o = G >> 1; o; o >>= 1) dt_ += __shfl_xor_sync(0xffffffffu, dt_, o);
+        dt_ *= beta;
+        if (act && beta != 0.0) for (int i = j + gl; i < R; i += G) ck[i] -= dt_ * ((i == j) ? v0 : cj[i]);
+        if (kb == j + 1) {                               // (warp 0) hand the next column's norm and diagonal to the next iteration
           __syncwarp();
           double part = 0.0;
-          for (int i = j + 1 + lane; i < R; i += 32) { const double x = ck[i]; part += x * x; }
-          part = warp_sum_d(part);
-          if (lane == 0) { s_nb[(j + 1) & 1] = part; s_xb[(j + 1) & 1] = ck[j + 1]; }      // the other buffer: slower warps may still read this column's
+          if (grp == 0 && k < c) for (int i = j + 1 + gl; i < R; i += G) { const double x = ck[i]; part += x * x; }
+          for (int o = G >> 1; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+          if (lane == 0 && k < c) { s_nb[(j + 1) & 1] = part; s_xb[(j + 1) & 1] = ck[j + 1]; }      // the other buffer: slower warps may still read this column's
         }
       }
       __syncthreads();
     }
     // the triangular factor (rows < c) and Q^T r back to the global stack; rows >= c are dead after I_R = c
     for (int k = warp; k <= c; k += 16) {
-      const double* src = qsm + (size_t)k * R;
+      const double* src = qsm + (size_t)k * Rp;
       double* dst = (k < c) ? Hs + (size_t)km[k] * RMAX : rs;
       if (k < c) { for (int i = lane; i < c; i += 32) dst[i] = (i < k) ? src[i] : (i == k ? s_diag[k] : 0.0); }
       else { for (int i = lane; i < c; i += 32) dst[i] = src[i]; }

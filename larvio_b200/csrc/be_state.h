@@ -3,7 +3,7 @@
 #pragma once
 #include "lvb_internal.h"
 
-#define BE_DMAX_PAD 512      // >= any state dimension: 46 + 6*64 + 64
+#define BE_DMAX_PAD 640      // >= any state dimension: 46 + 6*64 + 3*64
 #define BE_LEG_MAX 46        // legacy error-state size with IMU-intrinsic calibration (larvio.cpp:158-161); 22 without (LvbBackEnd::LEG)
 
 // ---- core[s][BE_CORE] doubles
