@@ -1386,21 +1386,23 @@ __global__ void __launch_bounds__(256) be_slam_grow_kernel(BeView v) {
 }
 
 // ====================================================================== QR compression (SPQR thin QR at larvio.cpp:1430-1449, 2151-2171)
-// Householder, column by column over the structurally nonzero columns (kmap), one warp per trailing column with warp-shuffle dot
-// products.  The panel [nc + 1 columns (H | r)][R rows] is staged into shared memory (column-major, <= QR_SMEM_DOUBLES) and
-// factorised there with ONE block barrier per column: the reflector is read in place (its first entry is the only one that
-// differs from the column, and every thread derives (alpha, v0, beta) itself from the column's squared norm and diagonal, which
-// the warp that updated that column left in shared memory during the previous iteration), and the finished column is never
-// rewritten - the triangular factor is assembled on the way back to global memory.  Panels that do not fit (R * (nc + 1) beyond
-// the capacity: hundreds of tracks consumed in one frame) take the same algorithm on the global column-major stack with two
-// barriers per column.  (Round 2: 5-barrier global version 66 us, 2-barrier global version 53 us per 16-sequence launch.)
+// Householder, column by column over the structurally nonzero columns (kmap), on a shared-memory panel [nc + 1 columns (H | r)]
+// [rows], column-major.  Rows arrive in blocks: the panel holds as many rows as fit (<= QR_SMEM_DOUBLES), is reduced to its
+// nc x nc triangle, and the next block of rows is stacked under that triangle and reduced again (a thin QR is invariant to this
+// row blocking) - so the bursts of 300..650 rows that a frame with many tracks ending together produces never leave shared memory.
+// Per column ONE block barrier: the warp that updates column j+1 also derives its reflector (norm below the diagonal -> alpha, v0
+// written in place of the diagonal entry, beta into a parity-buffered slot), so the next iteration reads the column as the
+// reflector directly; groups of 8/16/32 lanes own a trailing column each and walk it two rows at a time (LDS.128).  Systems whose
+// column count leaves no room for a useful row block (hybrid configurations with hundreds of nonzero columns) take the same
+// algorithm on the global column-major stack with two barriers per column.
+// (Round 2, per 16-sequence launch: 5-barrier global version 66 us, 2-barrier global version 53 us.)
 constexpr int QR_SMEM_DOUBLES = 26000;               // 203 KB of the 227 KB a CTA can have
 
 __global__ void __launch_bounds__(512) be_qr_kernel(BeView v) {
-  extern __shared__ double qsm[];      // panel [(c + 1)][R] (shared-memory path) or reflector [RMAX] (global path)
+  extern __shared__ double qsm[];      // panel [(c + 1)][Rp] (shared-memory path) or reflector [RMAX] (global path)
   __shared__ double red[16];
   __shared__ double s_n2, s_x0;
-  __shared__ double s_nb[2], s_xb[2];      // shared-memory path: (norm^2, diagonal) of the next column, double-buffered by column parity
+  __shared__ double s_beta[2];             // shared-memory path: beta of the next column's reflector, double-buffered by column parity
   __shared__ double s_diag[BE_DMAX_PAD];
   const int s = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int* ic = icore_of(v, s);
@@ -1411,64 +1413,97 @@ __global__ void __launch_bounds__(512) be_qr_kernel(BeView v) {
   double* Hs = v.be.Hs + (size_t)s * LD * RMAX;
   double* rs = v.be.rs + (size_t)s * RMAX;
   const int* km = v.be.kmap + (size_t)s * LD;
-  // column stride in shared memory: R rounded up to 8 (mod 16) doubles, so that the 4 lane groups of a warp (below) hit the 32
-  // banks in two wavefronts, the minimum for 32 x 8 bytes
-  const int Rp = ((R + 7) / 16) * 16 + 8;
-  const bool in_smem = (size_t)Rp * (c + 1) <= (size_t)QR_SMEM_DOUBLES && (size_t)RMAX <= (size_t)QR_SMEM_DOUBLES;
+  // rows the panel can hold: stride Rp = 8 (mod 16) doubles (even: 16-byte aligned pairs; lane groups of neighbouring columns
+  // land in different bank halves)
+  int cap_rows = QR_SMEM_DOUBLES / (c + 1);
+  cap_rows = ((cap_rows - 8) / 16) * 16 + 8;
+  const bool in_smem = cap_rows >= c + 32 && (size_t)RMAX <= (size_t)QR_SMEM_DOUBLES;
   if (in_smem) {
-    for (int k = warp; k <= c; k += 16) {
-      const double* src = (k < c) ? Hs + (size_t)km[k] * RMAX : rs;
-      double* dst = qsm + (size_t)k * Rp;
-      for (int i = lane; i < R; i += 32) dst[i] = src[i];
-    }
-    __syncthreads();
-    {                                                    // column 0: the only block-wide reduction
-      double part = 0.0;
-      for (int i = tid; i < R; i += 512) { const double x = qsm[i]; part += x * x; }
-      part = warp_sum_d(part);
-      if (lane == 0) red[warp] = part;
-      __syncthreads();
-      if (tid == 0) { double n2 = 0.0; for (int w = 0; w < 16; ++w) n2 += red[w]; s_nb[0] = n2; s_xb[0] = qsm[0]; }
-      __syncthreads();
-    }
-    // G lanes per trailing column: with the usual ~50 nonzero columns every trailing column (and r) has its own group of 8 lanes,
-    // so one pass of the block covers them all; fewer columns get wider groups
-    const int G = (c + 1 <= 16) ? 32 : (c + 1 <= 32) ? 16 : 8;
-    const int gpw = 32 / G, grp = lane / G, gl = lane - grp * G;
-    for (int j = 0; j < c; ++j) {
-      const double* cj = qsm + (size_t)j * Rp;
-      const double n2 = s_nb[j & 1], x0 = s_xb[j & 1];   // squared norm of rows >= j of column j, and its diagonal entry
-      const double nrm = sqrt(n2);
-      const double alpha = x0 >= 0 ? -nrm : nrm;
-      const double v0 = x0 - alpha;
-      const double vtv = n2 - x0 * x0 + v0 * v0;
-      const double beta = vtv > 0.0 ? 2.0 / vtv : 0.0;
-      if (tid == 0) s_diag[j] = alpha;
-      for (int kb = j + 1 + warp * gpw; kb <= c; kb += 16 * gpw) {      // warp-uniform trip count: the shuffles below use the full mask
-        const int k = kb + grp;
-        const bool act = k <= c;
-        double* ck = qsm + (size_t)(act ? k : j) * Rp;
-        double dt_ = 0.0;
-        if (act) for (int i = j + gl; i < R; i += G) dt_ += ((i == j) ? v0 : cj[i]) * ck[i];
-        for (int o = G >> 1; o; o >>= 1) dt_ += __shfl_xor_sync(0xffffffffu, dt_, o);
-        dt_ *= beta;
-        if (act && beta != 0.0) for (int i = j + gl; i < R; i += G) ck[i] -= dt_ * ((i == j) ? v0 : cj[i]);
-        if (kb == j + 1) {                               // (warp 0) hand the next column's norm and diagonal to the next iteration
-          __syncwarp();
-          double part = 0.0;
-          if (grp == 0 && k < c) for (int i = j + 1 + gl; i < R; i += G) { const double x = ck[i]; part += x * x; }
-          for (int o = G >> 1; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-          if (lane == 0 && k < c) { s_nb[(j + 1) & 1] = part; s_xb[(j + 1) & 1] = ck[j + 1]; }      // the other buffer: slower warps may still read this column's
-        }
+    const int Rp = min(cap_rows, ((R + 7) / 16) * 16 + 8);
+    int done = 0, top = 0;
+    while (done < R) {
+      const int take = min(R - done, Rp - top);
+      const int m = top + take;
+      // ---- rows [done, done + take) of (H | r) under the triangle of the rows reduced so far; zero padding up to Rp
+      for (int k = warp; k <= c; k += 16) {
+        const double* src = ((k < c) ? Hs + (size_t)km[k] * RMAX : rs) + done;
+        double* dst = qsm + (size_t)k * Rp;
+        for (int i = lane; i < Rp - top; i += 32) dst[top + i] = (i < take) ? src[i] : 0.0;
       }
       __syncthreads();
+      {                                                  // reflector of column 0: the only block-wide reduction of the pass
+        double part = 0.0;
+        for (int i = tid; i < m; i += 512) { const double x = qsm[i]; part += x * x; }
+        part = warp_sum_d(part);
+        if (lane == 0) red[warp] = part;
+        __syncthreads();
+        if (tid == 0) {
+          double n2 = 0.0; for (int w = 0; w < 16; ++w) n2 += red[w];
+          const double x0 = qsm[0], nrm = sqrt(n2), alpha = x0 >= 0 ? -nrm : nrm, v0 = x0 - alpha, vtv = n2 - x0 * x0 + v0 * v0;
+          qsm[0] = v0; s_diag[0] = alpha; s_beta[0] = vtv > 0.0 ? 2.0 / vtv : 0.0;
+        }
+        __syncthreads();
+      }
+      const int G = (m > 192) ? 32 : (m > 64) ? 16 : 8;  // lanes per trailing column; each lane walks pairs of rows
+      const int gpw = 32 / G, grp = lane / G, gl = lane - grp * G;
+      const int m_even = (m + 1) & ~1;                   // rows m..Rp-1 are zero
+      for (int j = 0; j < c; ++j) {
+        const double* cj = qsm + (size_t)j * Rp;         // rows >= j: the reflector (v0 already in place of the diagonal entry)
+        const double beta = s_beta[j & 1];
+        const int e0 = j & ~1;                           // pairs start at an even row; row j-1 of an odd j is masked out
+        for (int kb = j + 1 + warp * gpw; kb <= c; kb += 16 * gpw) {      // warp-uniform trip count: full-mask shuffles below
+          const int k = kb + grp;
+          const bool act = k <= c;
+          double* ck = qsm + (size_t)(act ? k : j + 1) * Rp;
+          double dt_ = 0.0;
+          if (act && beta != 0.0)
+            for (int i = e0 + 2 * gl; i < m_even; i += 2 * G) {
+              double2 r2 = *reinterpret_cast<const double2*>(cj + i);
+              const double2 a2 = *reinterpret_cast<const double2*>(ck + i);
+              if (i < j) r2.x = 0.0;
+              dt_ += r2.x * a2.x + r2.y * a2.y;
+            }
+          for (int o = G >> 1; o; o >>= 1) dt_ += __shfl_xor_sync(0xffffffffu, dt_, o);
+          dt_ *= beta;
+          if (act && beta != 0.0)
+            for (int i = e0 + 2 * gl; i < m_even; i += 2 * G) {
+              double2 r2 = *reinterpret_cast<const double2*>(cj + i);
+              double2 a2 = *reinterpret_cast<double2*>(ck + i);
+              if (i < j) r2.x = 0.0;
+              a2.x -= dt_ * r2.x; a2.y -= dt_ * r2.y;
+              *reinterpret_cast<double2*>(ck + i) = a2;
+            }
+          if (kb == j + 1) {                             // (warp 0) the reflector of column j+1 for the next iteration
+            __syncwarp();
+            double part = 0.0;
+            const int j1 = j + 1, f0 = j1 & ~1;
+            if (grp == 0 && k < c)
+              for (int i = f0 + 2 * gl; i < m_even; i += 2 * G) {
+                const double2 a2 = *reinterpret_cast<const double2*>(ck + i);
+                part += ((i < j1) ? 0.0 : a2.x * a2.x) + a2.y * a2.y;
+              }
+            for (int o = G >> 1; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (lane == 0 && k < c) {
+              const double x0 = ck[j1], nrm = sqrt(part), alpha = x0 >= 0 ? -nrm : nrm, v0 = x0 - alpha, vtv = part - x0 * x0 + v0 * v0;
+              ck[j1] = v0; s_diag[j1] = alpha; s_beta[j1 & 1] = vtv > 0.0 ? 2.0 / vtv : 0.0;      // the other parity slot: slower warps may still read this column's
+            }
+          }
+        }
+        __syncthreads();
+      }
+      // ---- the panel's rows < c become the triangle: diagonal from s_diag, zeros below (the reflectors are dropped)
+      for (int k = warp; k < c; k += 16) {
+        double* ck = qsm + (size_t)k * Rp;
+        for (int i = k + lane; i < c; i += 32) ck[i] = (i == k) ? s_diag[k] : 0.0;
+      }
+      __syncthreads();
+      done += take; top = c;
     }
     // the triangular factor (rows < c) and Q^T r back to the global stack; rows >= c are dead after I_R = c
     for (int k = warp; k <= c; k += 16) {
       const double* src = qsm + (size_t)k * Rp;
       double* dst = (k < c) ? Hs + (size_t)km[k] * RMAX : rs;
-      if (k < c) { for (int i = lane; i < c; i += 32) dst[i] = (i < k) ? src[i] : (i == k ? s_diag[k] : 0.0); }
-      else { for (int i = lane; i < c; i += 32) dst[i] = src[i]; }
+      for (int i = lane; i < c; i += 32) dst[i] = src[i];
     }
   } else {
   {                                                    // column 0: the only block-wide reduction
