@@ -66,6 +66,9 @@ typedef struct LvbConfig {
   int max_track_len, sw_size, least_observation_number;
   int if_FEJ, estimate_extrin, estimate_td, calib_imu_instrinsic, if_ZUPT_valid;
   int max_features_in_one_grid, aug_grid_rows, aug_grid_cols, feature_idp_dim, use_schmidt, _pad1;
+  /* hybrid filter: max_features_in_one_grid * aug_grid_rows * aug_grid_cols EKF-SLAM features (<= 64, 0 = pure MSCKF);
+     feature_idp_dim 1 = inverse depth on the anchor bearing, anything else = 3-D (x/z, y/z, 1/z) like larvio.cpp:270-274;
+     use_schmidt != 0 is refused with LVB_E_UNSUPPORTED */
 } LvbConfig;
 
 /* include/sensors/ImuData.hpp:16-38 as a POD. */

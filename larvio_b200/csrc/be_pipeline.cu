@@ -1,4 +1,5 @@
-// Batched LarVio::processFeatures (larvio.cpp:363-461), pure-MSCKF configuration, FP64.
+// Batched LarVio::processFeatures (larvio.cpp:363-461), FP64: pure MSCKF and hybrid MSCKF + EKF-SLAM features (1-D or 3-D
+// inverse depth), ZUPT, online extrinsics / td / IMU-intrinsic calibration; Schmidt nuisance states are refused.
 //   be_propagate_kernel   batchImuProcessing / processModel / predictNewState / calPhi (:464-649, :3475-3530)
 //   be_add_obs_kernel     addFeatureObservations (:804-856) + the checkZUPT detector (:2751-2766)
 //   be_augment_kernel     stateAugmentation (:720-801)
@@ -10,6 +11,10 @@
 //   be_update_*           measurementUpdate_hybrid / _msckf (:1420-1602, :1605-1862) as
 //                         T=HP, S=TH^T+s^2 I, S=LL^T, Y=L^-1 T, dx=Y^T L^-1 r, P-=Y^T Y
 //   be_prune_*            findRedundantImuStates / pruneImuStateBuffer (:2259-2307, :2310-2641)
+//   be_slam_*, be_anchor_kernel, be_remap_*   the hybrid filter: promotion rule (:1968-2002), featureJacobian_ekf[_new] with
+//                         measurementJacobian_ekf_1didp / _3didp (:984-1417), new-feature states and grown covariance
+//                         (:1661-1676, :1821-1854), anchor hand-over with updateFeatureCov_1didp / _3didp (:2345-2461,
+//                         :2965-3293), rmLostFeaturesCov (:3296-3348), map-point lists (:455-458, :3342)
 // One CTA per sequence for the sequential parts, (tiles x sequences) grids for the dense algebra.
 #include <math.h>
 #include <string.h>
