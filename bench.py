@@ -54,16 +54,17 @@ def load_ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch and per sequence from the newest committed `ncu --set full`
     summary (profiles/*_ncu_traffic.json, written by scripts/ncu_summary.py on the GPU box)."""
     import glob
-    best = None
-    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_traffic.json"))):
-        best = f
-    if not best:
-        return {}, None
-    try:
-        d = json.load(open(best))
-        return {k: v["dram_bytes_per_launch"] / max(v.get("sequences_per_launch", 64), 1) for k, v in d["kernels"].items()}, os.path.relpath(best, ROOT)
-    except Exception:
-        return {}, None
+    out = {}; newest = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_traffic.json"))):      # later tags override earlier captures
+        try:
+            d = json.load(open(f))
+            for k, v in d["kernels"].items():
+                name = k.replace("void ", "").split("<")[0].strip()
+                out[name] = v["dram_bytes_per_launch"] / max(v.get("sequences_per_launch", 64), 1)
+            newest = f
+        except Exception:
+            continue
+    return out, (os.path.relpath(newest, ROOT) if newest else None)
 
 
 def effective_cores():
@@ -266,6 +267,9 @@ class ClockSampler:
             except Exception:
                 pass
             time.sleep(self.period)
+
+    def reset(self):
+        self.sm = []; self.bits = 0
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
@@ -490,9 +494,11 @@ def main():
     # ---- device-resident pass: `value`
     dev_frames = pinned.to("cuda", non_blocking=False)
     st = fresh_state()
+    sampler = ClockSampler(local_rank) if rank == 0 else None      # NVML polling thread (5 ms period), started before the pre-roll so that
     run_pass("dev", 0, PR + Wm, st)          # untimed: pre-roll to a full sliding window, then the warm-up steps
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None      # NVML samples over the timed region (5 ms period)
+    if sampler:
+        sampler.reset()                      # ... it is already running when the timed region starts: only samples from here on count
     l0 = launches_total()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(); t0 = time.perf_counter()
