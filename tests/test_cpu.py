@@ -737,3 +737,46 @@ def test_compiled_orb_equals_the_numpy_restatement(cfg):
         orb.use_compiled(False)
     assert np.array_equal(d0, d1) and np.array_equal(h0, h1)
     assert np.array_equal(d0[:40], o.compute_loop(pts[:40]))               # and both equal the literal per-point restatement
+
+
+def _load_bench():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_bench_helpers_core_count_and_ncu_traffic():
+    """bench.py host-side helpers: the usable-core count honours affinity and the cgroup quota (never more than either), the
+    ncu traffic table merges the committed capture tags (newest overrides, template arguments stripped from kernel names)."""
+    b = _load_bench()
+    n = b.effective_cores()
+    assert 1 <= n <= len(os.sched_getaffinity(0))
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            assert n <= max(1, int(float(q) / float(per) + 0.999))
+    except OSError:
+        pass
+    traffic, src = b.load_ncu_traffic()
+    assert src and src.startswith("profiles/") and src.endswith("_ncu_traffic.json")
+    assert traffic["lk_kernel"] > 0 and "be_propagate_kernel" in traffic and all("<" not in k and not k.startswith("void ") for k in traffic)
+    assert "compiled filter" in b.cpu_arm_description(dict(max_features_in_one_grid=0, aug_grid_rows=5, aug_grid_cols=6, calib_imu_instrinsic=0))
+    assert "numpy f64 filter" in b.cpu_arm_description(dict(max_features_in_one_grid=1, aug_grid_rows=5, aug_grid_cols=6, calib_imu_instrinsic=0))
+
+
+def test_reference_arm_prints_the_contract_line(tmp_path):
+    """`bench.py --impl reference` runs without a GPU (it is the CPU arm) and prints one JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, LVB_BENCH_CACHE=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--preroll", "2",
+                        "--seqs", "2"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == dict(value=line["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    assert line["metric"] == "batched VIO frames/sec" and "workload" in line["config"]
