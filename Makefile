@@ -57,3 +57,14 @@ $(LIB): $(OBJ)
 
 clean:
 	rm -f larvio_b200/csrc/*.o larvio_b200/csrc/*.o.log $(LIB) $(IOLIB) $(REPLAY) $(SHIMDEMO) $(ORACLE_C)
+
+# The reference's own filter (src/larvio.cpp + the static initialiser, compiled UNMODIFIED from where they lie) against the
+# stand-in headers of oracle/ref_shim/ (Eigen / boost / OpenCV-core subsets written for this purpose; none of them is in the
+# image).  Test infrastructure: tests/golden/make_ref_golden.py runs it to produce the golden vectors that pin the oracle
+# and the CUDA back end.  Only buildable where /root/reference exists; outputs only into oracle/_ref/ (git-ignored).
+REF_SRC := /root/reference
+REF_FLAGS := -O2 -std=c++17 -w -Ioracle/ref_shim -I$(REF_SRC)/include
+ref: oracle/_ref/larvio_ref
+oracle/_ref/larvio_ref: oracle/ref_driver.cpp oracle/ref_shim/Eigen/Dense oracle/ref_shim/opencv2/core/utility.hpp oracle/ref_shim/boost/math/distributions/chi_squared.hpp oracle/ref_shim/Initializer/DynamicInitializer.h
+	mkdir -p oracle/_ref
+	g++ $(REF_FLAGS) -o $@ oracle/ref_driver.cpp $(REF_SRC)/src/larvio.cpp $(REF_SRC)/src/StaticInitializer.cpp $(REF_SRC)/src/FlexibleInitializer.cpp

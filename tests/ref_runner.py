@@ -1,0 +1,175 @@
+"""TEST INFRASTRUCTURE: record the stream app/larvioMain.cpp:87-117 feeds LarVio::processFeatures (feature messages of the
+front-end oracle + the IMU samples between them) and replay it through oracle/_ref/larvio_ref - the reference's own
+src/larvio.cpp + StaticInitializer.cpp compiled unmodified against oracle/ref_shim/ (Makefile target `ref`; only possible
+where /root/reference exists, i.e. in the build container).  tests/golden/make_ref_golden.py turns the replies into the
+committed fixtures tests/golden/ref_*.npz, which travel to the GPU box.  Never imported by the package."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+from larvio_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "larvio_ref")
+
+_SCALARS = """sw_size max_track_len least_observation_number if_FEJ estimate_extrin estimate_td calib_imu_instrinsic feature_idp_dim
+use_schmidt max_features_in_one_grid aug_grid_rows aug_grid_cols rotation_threshold translation_threshold tracking_rate_threshold
+feature_translation_threshold position_std_threshold reset_fej_threshold noise_gyro noise_acc noise_gyro_bias noise_acc_bias
+noise_feature initial_covariance_orientation initial_covariance_velocity initial_covariance_position initial_covariance_gyro_bias
+initial_covariance_acc_bias initial_covariance_extrin_rot initial_covariance_extrin_trans if_ZUPT_valid zupt_max_feature_dis
+zupt_noise_v zupt_noise_p zupt_noise_q static_duration imu_rate pub_frequency resolution_width resolution_height td""".split()
+
+
+def write_reference_yaml(cfg_raw: dict, path: str, output_dir: str):
+    """cfg_raw -> a settings file in the reference's own format (config/euroc.yaml), every key larvio.cpp:58-277 reads."""
+    lines = ["%YAML:1.0", "", 'output_dir: "%s"' % output_dir]
+    for k in _SCALARS:
+        lines.append("%s: %s" % (k, repr(cfg_raw[k]) if isinstance(cfg_raw[k], float) else cfg_raw[k]))
+    it = cfg_raw["intrinsics"]
+    lines.append("intrinsics:")
+    for k in ("fx", "fy", "cx", "cy"):
+        lines.append("   %s: %r" % (k, float(it[k])))
+    T = np.asarray(cfg_raw["T_cam_imu"]["data"], np.float64).reshape(4, 4)
+    lines += ["T_cam_imu: !!opencv-matrix", "   rows: 4", "   cols: 4", "   dt: d", "   data:"]
+    rows = [", ".join(repr(float(v)) for v in T[i]) for i in range(4)]
+    lines.append("    [" + ",\n     ".join(rows) + "]")
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
+def record_calls(cfg_raw, seq, n_frames):
+    """Front-end oracle over the images of one sequence -> the list of processFeatures calls [(t_msg, new imu rows, ids, data)]
+    plus the frame index of each call."""
+    from oracle.frontend import ImageProcessorOracle
+    fe = ImageProcessorOracle(cfg_raw)
+    imu = []
+    pending = []
+    k = 0
+    calls = []
+    for j in range(n_frames):
+        k2 = synth.imu_window(seq, k, seq.img_t[j])
+        new = seq.imu[k:k2]
+        imu.extend(new.tolist()); pending.extend(new.tolist()); k = k2
+        msg = fe.process_image(seq.images[j], seq.img_t[j], np.array(imu).reshape(-1, 7))
+        if msg is not None:
+            calls.append(dict(frame=j, t=float(msg.t), imu=np.array(pending, np.float64).reshape(-1, 7),
+                              ids=np.asarray(msg.ids, np.uint64).copy(), data=np.asarray(msg.data, np.float64).copy()))
+            pending = []
+        # the front end only trims ITS view of the buffer; the filter consumes the caller's copy (larvio.cpp:510-512)
+    return calls
+
+
+def run_oracle_on_calls(cfg_raw, calls, init=None, static_init=False):
+    """oracle/backend.py over recorded calls.  init = (t, q, p, v, bg, ba) forces the initial state before the first call;
+    static_init=True uses oracle/initializer.py the way tests/oracle_runner.py does for self-starting runs."""
+    from oracle.backend import LarVioOracle
+    from oracle.frontend import FeatureMsg
+    be = LarVioOracle(cfg_raw)
+    si = None
+    if static_init:
+        from oracle.initializer import StaticInitializerOracle
+        si = StaticInitializerOracle(cfg_raw)
+    imu = []
+    out = []
+    for c in calls:
+        imu.extend(c["imu"].tolist())
+        msg = FeatureMsg(c["t"]); msg.ids = c["ids"]; msg.data = c["data"]
+        if init is not None and not be.is_gravity_set:
+            be.set_initial_state(*init)
+        if si is not None and not be.is_gravity_set:
+            # larvio.cpp:365-389: the bFirstFeatures gate precedes the initialiser
+            if not be.bFirstFeatures:
+                if len(imu) > 0 and imu[0][0] - msg.t - be.td <= 0.0:
+                    be.bFirstFeatures = True
+                else:
+                    out.append(dict(ok=False)); continue
+            r = si.try_inc_init(msg.ids, msg.data[:, 0:2], msg.t, imu)
+            if r is None:
+                out.append(dict(ok=False)); continue
+            be.set_initial_state(r["t"], r["q"], r["p"], r["v"], r["bg"], r["ba"])
+            be.m_gyro_old = r["gyro_old"]; be.m_acc_old = r["acc_old"]
+            del imu[:r["n_consumed"]]
+        ok = be.process_features(msg, imu)
+        rec = dict(ok=bool(ok))
+        if ok:
+            s = be.imu_state
+            rec.update(t=s.time, q=s.q.copy(), p=s.p.copy(), v=s.v.copy(), bg=s.bg.copy(), ba=s.ba.copy(),
+                       R_imu_cam0=s.R_imu_cam0.copy(), t_cam0_imu=s.t_cam0_imu.copy(), td=float(be.td), P=be.P.copy(),
+                       n_win=len(be.aug), slam_ids=[int(i) for i in be.feature_states], n_imu_left=len(imu),
+                       win_ids=sorted(int(i) for i in be.aug))
+        out.append(rec)
+    return out
+
+
+def run_reference_on_calls(cfg_raw, calls, init=None, static_init=False):
+    """The compiled reference over recorded calls; same record layout as run_oracle_on_calls (+ window, map points)."""
+    if not os.path.exists(REF_BIN):
+        raise FileNotFoundError(REF_BIN + " (build it with `make ref`; needs /root/reference)")
+    with tempfile.TemporaryDirectory() as td:
+        ypath = os.path.join(td, "cfg.yaml"); ipath = os.path.join(td, "in.bin"); opath = os.path.join(td, "out.bin")
+        write_reference_yaml(cfg_raw, ypath, td + "/")
+        buf = [0.0 if not static_init else 1.0]
+        if init is not None:
+            t, q, p, v, bg, ba = init
+            buf += [float(t)] + list(map(float, q)) + list(map(float, p)) + list(map(float, v)) + list(map(float, bg)) + list(map(float, ba))
+        else:
+            buf += [0.0] * 17
+        buf.append(float(len(calls)))
+        for c in calls:
+            buf += [c["t"], float(len(c["imu"]))] + c["imu"].reshape(-1).tolist() + [float(len(c["ids"]))]
+            for i, d in zip(c["ids"], c["data"]):
+                buf += [float(i)] + d.tolist()
+        np.asarray(buf, np.float64).tofile(ipath)
+        r = subprocess.run([REF_BIN, ypath, ipath, opath], capture_output=True, text=True, timeout=1800)
+        if r.returncode != 0:
+            raise RuntimeError("larvio_ref failed (%d): %s" % (r.returncode, r.stderr[-2000:]))
+        o = np.fromfile(opath, np.float64)
+    k = 0
+    out = []
+
+    def take(n):
+        nonlocal k
+        v = o[k:k + n].copy(); k += n
+        return v
+    for _ in calls:
+        ok = bool(take(1)[0])
+        rec = dict(ok=ok)
+        if ok:
+            rec["t"] = float(take(1)[0]); rec["q"] = take(4); rec["p"] = take(3); rec["v"] = take(3); rec["bg"] = take(3); rec["ba"] = take(3)
+            rec["R_imu_cam0"] = take(9).reshape(3, 3); rec["t_cam0_imu"] = take(3); rec["td"] = float(take(1)[0])
+            rec["Tg"] = take(9).reshape(3, 3); rec["As"] = take(9).reshape(3, 3); rec["Ma"] = take(9).reshape(3, 3)
+            n_win, n_slam, n_nui, dim = (int(x) for x in take(4))
+            rec["P"] = take(dim * dim).reshape(dim, dim)
+            w = take(n_win * 8).reshape(n_win, 8)
+            rec["n_win"] = n_win; rec["win_ids"] = [int(x) for x in w[:, 0]]; rec["win_q"] = w[:, 1:5]; rec["win_p"] = w[:, 5:8]
+            rec["slam_ids"] = [int(x) for x in take(n_slam)]; rec["slam_pos"] = take(3 * n_slam).reshape(n_slam, 3)
+            rec["nui_ids"] = [int(x) for x in take(n_nui)]
+            ns = int(take(1)[0]); st = take(4 * ns).reshape(ns, 4); rec["stable"] = {int(r_[0]): r_[1:4] for r_ in st}
+            na = int(take(1)[0]); ac = take(4 * na).reshape(na, 4); rec["active"] = {int(r_[0]): r_[1:4] for r_ in ac}
+            rec["n_imu_left"] = int(take(1)[0])
+        out.append(rec)
+    assert k == len(o), "trailing output of larvio_ref not consumed"
+    return out
+
+
+def compare_runs(a, b):
+    """Largest deviations between two runs (lists of per-call records)."""
+    worst = dict(q=0.0, p=0.0, v=0.0, bg=0.0, ba=0.0, ext=0.0, td=0.0, P=0.0, n=0)
+    for x, y in zip(a, b):
+        assert x["ok"] == y["ok"], "processFeatures returned differently"
+        if not x["ok"]:
+            continue
+        assert x["P"].shape == y["P"].shape, "state dimension differs: %s vs %s" % (x["P"].shape, y["P"].shape)
+        assert x["n_win"] == y["n_win"] and list(x["slam_ids"]) == list(y["slam_ids"]), "window / SLAM feature bookkeeping differs"
+        assert x["n_imu_left"] == y["n_imu_left"], "IMU buffer consumed differently"
+        dq = min(np.abs(x["q"] - y["q"]).max(), np.abs(x["q"] + y["q"]).max())
+        worst["q"] = max(worst["q"], float(dq))
+        for k in ("p", "v", "bg", "ba"):
+            worst[k] = max(worst[k], float(np.abs(x[k] - y[k]).max()))
+        worst["ext"] = max(worst["ext"], float(np.abs(x["R_imu_cam0"] - y["R_imu_cam0"]).max()), float(np.abs(x["t_cam0_imu"] - y["t_cam0_imu"]).max()))
+        worst["td"] = max(worst["td"], abs(x["td"] - y["td"]))
+        worst["P"] = max(worst["P"], float(np.linalg.norm(x["P"] - y["P"]) / np.linalg.norm(y["P"])))
+        worst["n"] += 1
+    return worst
