@@ -2363,6 +2363,15 @@ __device__ __forceinline__ int grid_code(const BeView& v, double x, double y) {
   return row * v.be.grid_cols + col;
 }
 
+// grid_map[code] of the reference (a std::map<int, vector>): the rows*cols cells are emptied by updateGridMap every step
+// (larvio.cpp:3355-3357) and live in cand[s][64..127]; any other code is created on first touch (:3366, :1972, :1988) and
+// never emptied - those counts persist in grid_oor.  nullptr: a code outside the tracked range [-64, 192).
+__device__ __forceinline__ int* grid_cell(const BeView& v, int s, int* grid, int code) {
+  if (code >= 0 && code < v.be.grid_rows * v.be.grid_cols) return grid + code;
+  if (code >= -BE_GRID_OOR_NEG && code < BE_GRID_OOR - BE_GRID_OOR_NEG) return v.be.grid_oor + (size_t)s * BE_GRID_OOR + code + BE_GRID_OOR_NEG;
+  return nullptr;
+}
+
 // ---------------------------------------------------------------- in-state SLAM features at the start of removeLostFeatures
 // (:1896-1924): lost ones leave the state (covariance re-map, feature erased); grid occupancy of the rest (updateGridMap).
 // grid counts live in cand[s][64..127].
@@ -2391,8 +2400,8 @@ __global__ void __launch_bounds__(64) be_slam_pre_kernel(BeView v) {
       for (int q = 0; q < idp; ++q) cm[base + idp * keep + q] = base + idp * i + q;
       fs[keep++] = slot;
       const double* o = v.be.ft_obs + (fi * Wcap + cur) * 4;
-      const int code = grid_code(v, o[0], o[1]);
-      if (code >= 0 && code < 64) grid[code]++;
+      int* cell = grid_cell(v, s, grid, grid_code(v, o[0], o[1]));
+      if (cell) (*cell)++;
     } else {
       pts_put(v, 0, s, v.be.ft_id[fi], v.be.ft_pos + fi * 3);   // lost_slam_features[id] = map_server[id] (:3342)
       v.be.ft_flags[fi] = 0; v.be.ft_mask[fi] = 0;              // rmLostFeaturesCov erases the feature
@@ -2444,7 +2453,9 @@ __global__ void __launch_bounds__(256) be_slam_decide_kernel(BeView v) {
     const int code = grid_code(v, o[0], o[1]);
     const double* sp = v.be.ft_spec + fi * 8;
     const bool spec_ok = sp[0] != 0.0;
-    const bool slam = v.cfg.hybrid && code >= 0 && code < 64 && grid[code] < v.be.max_per_cell &&
+    int* cell = v.cfg.hybrid ? grid_cell(v, s, grid, code) : nullptr;
+    if (v.cfg.hybrid && !cell) atomicExch(&ic[I_ERR], 5);
+    const bool slam = cell && *cell < v.be.max_per_cell &&
                       core[C_TIME] - core[C_LAST_ZUPT] > 5 && (nf + n_new) < v.be.NFmax;
     auto commit_spec = [&](bool ekf) {
       double* pos = v.be.ft_pos + fi * 3;
@@ -2465,7 +2476,7 @@ __global__ void __launch_bounds__(256) be_slam_decide_kernel(BeView v) {
       }
       if (flags & 2) {
         action = 3; usemask = mask; nrows = 2 * m + (v.be.IDP == 3 ? 2 * m : 2 * (m - 1));      // gate rows + featureJacobian_ekf_new rows (the anchor's own observation only counts with 3-D inverse depth, :1260-1262)
-        grid[code]++; newlist[n_new++] = slot;
+        (*cell)++; newlist[n_new++] = slot;
       }
     } else {
       if (!(flags & 2) && spec_ok) commit_spec(false);
@@ -2603,7 +2614,7 @@ int be_alloc(LvbHandle* h) {
   BDA(be->Tm, S * (size_t)be->RAWMAX * LD);      // doubles as the per-feature H*P scratch of the gate
   BDA(be->Sm, S * (size_t)be->LDS * be->LDS); BDA(be->zvec, S * (size_t)be->LDS); BDA(be->dx, S * (size_t)be->LDS);
   BDA(be->ft_inv, S * T); BDA(be->ft_oa, S * T * 2); BDA(be->ft_anchor, S * T); BDA(be->ft_pfej, S * T * 3); BDA(be->ft_spec, S * T * 8);
-  BDA(be->ft_gamma, S * T); BDA(be->fs_slot, S * 64); BDA(be->cmap, S * LD); BDA(be->cand, S * 128); BDA(be->Hnew, S * 64 * be->IDP * (LD + 4));
+  BDA(be->ft_gamma, S * T); BDA(be->fs_slot, S * 64); BDA(be->cmap, S * LD); BDA(be->cand, S * 128); BDA(be->grid_oor, S * BE_GRID_OOR); BDA(be->Hnew, S * 64 * be->IDP * (LD + 4));
   BDA(be->imu, S * be->imu_cap); BDA(be->n_imu, S);
   BDA(be->msg_in, S * be->N); BDA(be->msg_in_n, S); BDA(be->msg_in_t, S); BDA(be->msg_in_valid, S);
   BPIN(be->pin_imu, LvbImu, S * be->imu_cap); BPIN(be->pin_n_imu, int, S); BPIN(be->pin_icore, int, S * BE_ICORE);
@@ -2954,7 +2965,7 @@ static int be_finish(LvbHandle* h, LvbImu* imu, int* n_imu, int imu_stride, uint
       if (ic[I_ERR]) err = ic[I_ERR];
     }
   }
-  if (err) return lvb_set_err(LVB_E_CAPACITY, "back-end capacity exceeded (code %d: 1 feature table, 2 window, 3 raw rows, 4 stacked rows)", err);
+  if (err) return lvb_set_err(LVB_E_CAPACITY, "back-end capacity exceeded (code %d: 1 feature table, 2 window, 3 raw rows, 4 stacked rows, 5 grid cell code outside [-64, 192))", err);
   return LVB_OK;
 }
 

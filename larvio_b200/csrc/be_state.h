@@ -20,7 +20,8 @@ enum {
   I_R = 12 /*rows after compression*/, I_NUSED = 13, I_RAWROWS = 14, I_ERR = 15, I_RM0 = 16, I_RM1 = 17, I_NRM = 18,
   I_DO_PRUNE = 19, I_ZUPT_EVENTS = 20, I_UPDATES = 21, I_NF = 22 /*EKF-SLAM features in state*/, I_REMAP = 23, I_NEWDIM = 24,
   I_NNEW = 25 /*new SLAM features accepted this frame*/, I_NCAND = 26, I_RO = 27 /*rows of H_o before the new-feature rows*/,
-  I_NC = 28 /*structurally nonzero columns of the stacked Jacobian (kmap)*/, BE_ICORE = 32
+  I_NC = 28 /*structurally nonzero columns of the stacked Jacobian (kmap)*/, BE_ICORE = 32,
+  BE_GRID_OOR = 256, BE_GRID_OOR_NEG = 64
 };
 // ---- win[s][slot][BE_WIN] doubles (IMUState_Aug)
 enum { W_TIME = 0, W_DT = 1, W_Q = 2, W_P = 6, W_PFEJ = 9, W_RIC = 12, W_TCI = 21, W_QCAM = 24, W_PCAM = 28, BE_WIN = 32 };
@@ -49,6 +50,10 @@ struct LvbBackEnd {
   // (ft_oa[0], ft_oa[1], ft_inv) IS invParam = (x/z, y/z, 1/z) (feature.hpp:231) -, anchor window slot, first-estimate position;
   // speculative triangulation results of this frame; state order list
   double* ft_inv; double* ft_oa; int* ft_anchor; double* ft_pfej; double* ft_spec; int* fs_slot; int* cmap; int* cand;
+  // occupancy of the reference's grid_map cells whose code lies OUTSIDE [0, rows*cols): [S][BE_GRID_OOR], index = code + BE_GRID_OOR_NEG.
+  // updateGridMap (larvio.cpp:3355-3357) empties the rows*cols cells only; a cell created by an observation beyond the image
+  // border (row == grid_rows, col < 0, ...) is never emptied, so these counts persist for the life of the handle
+  int* grid_oor;
   double* ft_gamma;                           // [S][T] last gating statistic of each slot (diagnostics)
   // map points for getStableMapPointPositions / getActiveeMapPointPositions (larvio.h:86-87): [which][S][PCAP], which 0 = SLAM
   // features that left the state (lost_slam_features, larvio.cpp:3342), 1 = features in the state at the end of a step

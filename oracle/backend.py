@@ -1028,7 +1028,11 @@ class LarVioOracle:
     def _update_grid_map(self):
         if self.grid_rows * self.grid_cols == 0:
             return
-        self.grid_map = {i: [] for i in range(self.grid_rows * self.grid_cols)}
+        # :3355-3357 clears the rows*cols cells only: a cell whose code falls OUTSIDE that range (observations beyond the image
+        # border, e.g. row == grid_rows) is created by operator[] below or at :1972/:1988 and never emptied again, so it stays
+        # "occupied" for the rest of the run (pinned against the compiled reference, tests/golden/ref_*.npz)
+        for i in range(self.grid_rows * self.grid_cols):
+            self.grid_map[i] = []
         for fid in self.feature_states:
             code = self._grid_code(self.map_server[fid].obs[self.imu_state.id])
             self.grid_map.setdefault(code, []).append(fid)

@@ -95,6 +95,17 @@ int main(int argc, char** argv) {
       forced = true;
     }
     bool ok = vio.processFeatures(&msg, imu_buf);
+    if (const char* tr = std::getenv("LVB_REF_TRACE_FEATURE")) {   // debugging aid: one feature's bookkeeping after every call
+      long long fid = std::atoll(tr);
+      auto it = vio.map_server.find(fid);
+      if (it == vio.map_server.end()) std::fprintf(stderr, "call %d: feature %lld not in map_server\n", c, fid);
+      else {
+        const Feature& f = it->second;
+        std::fprintf(stderr, "call %d: feature %lld obs %zu init %d in_state %d ekf %d anchor %lld invDepth %.17g pos %.17g %.17g %.17g\n", c, fid,
+                     f.observations.size(), (int)f.is_initialized, (int)f.in_state, (int)f.ekf_feature, (long long)f.id_anchor, f.invDepth,
+                     f.position(0), f.position(1), f.position(2));
+      }
+    }
     out.push_back(ok ? 1.0 : 0.0);
     if (!ok) continue;
     const IMUState& s = vio.state_server.imu_state;
