@@ -28,6 +28,13 @@ CASES = {
     "self_start": (dict(max_features_in_one_grid=0, sw_size=16), 3, 56, dict(static_until=1.4), True),
     "config_e": (E, 0, 132, {}, False),
     "no_fej_no_calib": (dict(max_features_in_one_grid=0, sw_size=12, if_FEJ=0, estimate_extrin=0, estimate_td=0), 1, 50, {}, False),
+    # translation_threshold 0.02: the two newest poses are never "redundant", so findRedundantImuStates removes the OLDEST ones
+    # (larvio.cpp:2292-2297): marginalised poses carry real measurements, old anchors are handed over / become nuisance states
+    "msckf_oldest": (dict(max_features_in_one_grid=0, sw_size=12, translation_threshold=0.02), 2, 70, {}, False),
+    "hybrid_1d_oldest": (dict(sw_size=12, translation_threshold=0.02), 0, 130, {}, False),
+    "hybrid_3d_oldest": (dict(sw_size=12, translation_threshold=0.02, feature_idp_dim=3), 0, 130, {}, False),
+    "schmidt_1d_oldest": (dict(sw_size=12, translation_threshold=0.02, use_schmidt=1), 0, 130, {}, False),
+    "schmidt_3d_oldest": (dict(sw_size=12, translation_threshold=0.02, use_schmidt=1, feature_idp_dim=3), 0, 130, {}, False),
     "schmidt_1d": (dict(sw_size=16, use_schmidt=1), 0, 130, {}, False),
     "schmidt_3d": (dict(sw_size=16, use_schmidt=1, feature_idp_dim=3), 0, 130, {}, False),
 }

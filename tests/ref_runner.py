@@ -173,3 +173,102 @@ def compare_runs(a, b):
         worst["P"] = max(worst["P"], float(np.linalg.norm(x["P"] - y["P"]) / np.linalg.norm(y["P"])))
         worst["n"] += 1
     return worst
+
+
+# ---- committed fixtures (tests/golden/ref_<case>.npz): the recorded calls + what the compiled reference answered ----------
+def fingerprint_vector(d):
+    """Fixed probe vector: the fixtures keep P z and diag(P) of every call instead of the d x d matrix."""
+    i = np.arange(d, dtype=np.float64)
+    return np.cos(1.7 * i + 0.3) + 0.25 * np.sin(0.37 * i * i)
+
+
+def pack_fixture(overrides, init, static_init, calls, ref):
+    import json
+    out = dict(cfg_json=np.array(json.dumps(overrides)), static_init=np.array(int(static_init)),
+               init=np.zeros(0) if init is None else np.concatenate([[init[0]], init[1], init[2], init[3], init[4], init[5]]).astype(np.float64))
+    out["call_t"] = np.array([c["t"] for c in calls]); out["call_frame"] = np.array([c["frame"] for c in calls], np.int32)
+    out["imu_ofs"] = np.cumsum([0] + [len(c["imu"]) for c in calls]).astype(np.int64)
+    out["imu"] = np.concatenate([c["imu"].reshape(-1, 7) for c in calls])
+    out["feat_ofs"] = np.cumsum([0] + [len(c["ids"]) for c in calls]).astype(np.int64)
+    out["ids"] = np.concatenate([c["ids"] for c in calls]).astype(np.uint64)
+    out["data"] = np.concatenate([c["data"].reshape(-1, 8) for c in calls])
+    n = len(calls)
+    ok = np.array([r["ok"] for r in ref], np.uint8)
+    state = np.zeros((n, 16)); ext = np.zeros((n, 12)); td = np.zeros(n); calib = np.zeros((n, 27))
+    meta = np.zeros((n, 5), np.int64)       # dim, n_win, n_slam, n_nui, n_imu_left
+    Pz = []; Pd = []; slam = []; Pfro = np.zeros(n)
+    last = None
+    for i, r in enumerate(ref):
+        if not r["ok"]:
+            continue
+        state[i] = np.concatenate([r["q"], r["p"], r["v"], r["bg"], r["ba"]])
+        ext[i] = np.concatenate([r["R_imu_cam0"].reshape(-1), r["t_cam0_imu"]]); td[i] = r["td"]
+        calib[i] = np.concatenate([r["Tg"].reshape(-1), r["As"].reshape(-1), r["Ma"].reshape(-1)])
+        d = r["P"].shape[0]
+        meta[i] = (d, r["n_win"], len(r["slam_ids"]), len(r["nui_ids"]), r["n_imu_left"])
+        Pz.append(r["P"] @ fingerprint_vector(d)); Pd.append(np.diag(r["P"]).copy()); slam.append(np.array(r["slam_ids"], np.int64))
+        Pfro[i] = np.linalg.norm(r["P"])
+        last = i
+    out.update(ok=ok, state=state, ext=ext, td=td, calib=calib, meta=meta, Pfro=Pfro,
+               Pz=np.concatenate(Pz) if Pz else np.zeros(0), Pdiag=np.concatenate(Pd) if Pd else np.zeros(0),
+               slam_ids=np.concatenate(slam) if slam else np.zeros(0, np.int64))
+    if last is not None:
+        out["P_last"] = ref[last]["P"]; out["P_last_call"] = np.array(last)
+    return out
+
+
+def load_fixture(path):
+    """-> (overrides, init tuple or None, static_init, calls, per-call reference records)."""
+    import json
+    z = np.load(path)
+    overrides = json.loads(str(z["cfg_json"]))
+    iv = z["init"]
+    init = None if len(iv) == 0 else (float(iv[0]), iv[1:5], iv[5:8], iv[8:11], iv[11:14], iv[14:17])
+    calls = []
+    for i in range(len(z["call_t"])):
+        a, b = z["imu_ofs"][i], z["imu_ofs"][i + 1]; f0, f1 = z["feat_ofs"][i], z["feat_ofs"][i + 1]
+        calls.append(dict(frame=int(z["call_frame"][i]), t=float(z["call_t"][i]), imu=z["imu"][a:b], ids=z["ids"][f0:f1], data=z["data"][f0:f1]))
+    ref = []
+    kd = 0; ks = 0
+    for i in range(len(calls)):
+        r = dict(ok=bool(z["ok"][i]))
+        if r["ok"]:
+            st = z["state"][i]; d, n_win, n_slam, n_nui, n_left = (int(x) for x in z["meta"][i])
+            r.update(q=st[0:4], p=st[4:7], v=st[7:10], bg=st[10:13], ba=st[13:16], R_imu_cam0=z["ext"][i][:9].reshape(3, 3),
+                     t_cam0_imu=z["ext"][i][9:12], td=float(z["td"][i]), Tg=z["calib"][i][0:9].reshape(3, 3), As=z["calib"][i][9:18].reshape(3, 3),
+                     Ma=z["calib"][i][18:27].reshape(3, 3), dim=d, n_win=n_win, n_nui=n_nui, n_imu_left=n_left,
+                     Pz=z["Pz"][kd:kd + d], Pdiag=z["Pdiag"][kd:kd + d], Pfro=float(z["Pfro"][i]), slam_ids=[int(x) for x in z["slam_ids"][ks:ks + n_slam]])
+            kd += d; ks += n_slam
+            if "P_last_call" in z.files and int(z["P_last_call"]) == i:
+                r["P"] = z["P_last"]
+        ref.append(r)
+    return overrides, init, bool(int(z["static_init"])), calls, ref
+
+
+def compare_with_fixture(run, ref):
+    """run: records with q p v bg ba R_imu_cam0 t_cam0_imu td P n_win slam_ids n_imu_left (oracle, compiled oracle or GPU);
+    ref: load_fixture records.  Bookkeeping must be identical; returns the largest numeric deviations."""
+    worst = dict(q=0.0, p=0.0, v=0.0, bg=0.0, ba=0.0, ext=0.0, td=0.0, Pz=0.0, Pdiag=0.0, P=0.0, n=0)
+    for i, (x, y) in enumerate(zip(run, ref)):
+        assert bool(x["ok"]) == y["ok"], "call %d: processFeatures returned %s, the reference %s" % (i, x["ok"], y["ok"])
+        if not y["ok"]:
+            continue
+        assert x["P"].shape[0] == y["dim"], "call %d: state dimension %d, the reference has %d" % (i, x["P"].shape[0], y["dim"])
+        assert x["n_win"] == y["n_win"], "call %d: window size differs" % i
+        if "slam_ids" in x:
+            assert list(x["slam_ids"]) == list(y["slam_ids"]), "call %d: SLAM features in the state differ" % i
+        if "n_imu_left" in x:
+            assert x["n_imu_left"] == y["n_imu_left"], "call %d: IMU buffer consumed differently" % i
+        worst["q"] = max(worst["q"], float(min(np.abs(x["q"] - y["q"]).max(), np.abs(x["q"] + y["q"]).max())))
+        for k in ("p", "v", "bg", "ba"):
+            worst[k] = max(worst[k], float(np.abs(x[k] - y[k]).max()))
+        if "R_imu_cam0" in x:
+            worst["ext"] = max(worst["ext"], float(np.abs(x["R_imu_cam0"] - y["R_imu_cam0"]).max()), float(np.abs(x["t_cam0_imu"] - y["t_cam0_imu"]).max()))
+            worst["td"] = max(worst["td"], abs(x["td"] - y["td"]))
+        d = y["dim"]
+        worst["Pz"] = max(worst["Pz"], float(np.linalg.norm(x["P"] @ fingerprint_vector(d) - y["Pz"]) / np.linalg.norm(y["Pz"])))
+        worst["Pdiag"] = max(worst["Pdiag"], float(np.linalg.norm(np.diag(x["P"]) - y["Pdiag"]) / np.linalg.norm(y["Pdiag"])))
+        if "P" in y:
+            worst["P"] = max(worst["P"], float(np.linalg.norm(x["P"] - y["P"]) / np.linalg.norm(y["P"])))
+        worst["n"] += 1
+    return worst
