@@ -3061,6 +3061,10 @@ __global__ void be_set_state_kernel(BeView v, int s, double t, const double* val
   core[C_TAKEOFF] = t;
   core[C_LAST_ZUPT] = t;
   ic[I_GRAVITY] = 1;
+  // the initialiser only ever runs behind the bFirstFeatures gate (larvio.cpp:366-376), and the call that initialises goes on
+  // to batchImuProcessing with the samples the initialiser left (StaticInitializer.cpp:149-150): a state handed in means the
+  // gate has been passed, it must not be re-evaluated on the shortened buffer
+  ic[I_FIRST] = 1;
 }
 
 extern "C" int lvb_set_initial_state(LvbHandle* h, int seq, double t, const double* q_xyzw, const double* p,

@@ -86,6 +86,7 @@ class LarVio {
     LvbConfig c;
     if (lvb_parse_config(cfg_.c_str(), &c) != LVB_OK) return false;
     init_ = lvb_static_init_create(&c);
+    td0_ = c.td;
     return init_ != nullptr;
   }
   // what FlexibleInitializer::tryIncInit leaves behind (larvio.cpp:376-386), for callers that start the filter themselves
@@ -104,6 +105,10 @@ class LarVio {
     for (size_t i = 0; i < msg->features.size(); ++i) std::memcpy(&f[i], &msg->features[i], sizeof(LvbFeature));
     int n_imu = (int)imu.size(), n_feat = (int)msg->features.size(); uint8_t valid = 1, ok = 0; double t = msg->timeStampToSec;
     if (!gravity_set_) {                                            // larvio.cpp:375-391 (static initialiser only)
+      if (!first_features_) {                                       // :365-372: no initialiser before an IMU sample precedes a message
+        if (n_imu > 0 && b[0].t - t - td0_ <= 0.0) first_features_ = true;
+        else return false;
+      }
       double st[17], g0[3], a0[3]; int used = 0;
       if (lvb_static_init_try(init_, f.data(), n_feat, t, b.data(), n_imu, st, g0, a0, &used) != 1) return false;
       if (lvb_set_initial_state(s_->h(), 0, st[0], st + 1, st + 5, st + 8, st + 11, st + 14) != LVB_OK) return false;
@@ -140,6 +145,8 @@ class LarVio {
   std::string cfg_;
   LvbStaticInit* init_ = nullptr;
   bool gravity_set_ = false;
+  bool first_features_ = false;
+  double td0_ = 0.0;
 };
 
 }  // namespace larvio

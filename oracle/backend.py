@@ -300,8 +300,9 @@ class LarVioOracle:
         if self.feature_idp_dim not in (1, 3):
             self.feature_idp_dim = 3                                   # larvio.cpp:270-274
         self.idp = self.feature_idp_dim
-        if self.hybrid and self.use_schmidt:
-            raise NotImplementedError("hybrid mode is restated without Schmidt nuisance states only")
+        # use_schmidt (larvio.cpp:277): poses that leave the window while they anchor SLAM features stay behind the feature block
+        # as nuisance states (:2351-2358, :2569-2613): ids in covariance order, their frozen pose, the features they anchor
+        self.nui_ids = []; self.nui_states = {}; self.nui_features = {}
         it = r["intrinsics"]
         fx, fy, cx, cy = float(it["fx"]), float(it["fy"]), float(it["cx"]), float(it["cy"])
         U, V = int(r["resolution_width"]), int(r["resolution_height"])
@@ -340,6 +341,7 @@ class LarVioOracle:
         s.time = float(t); s.q = np.array(q_xyzw, float); s.p = np.array(p, float); s.v = np.array(v, float)
         s.bg = np.array(bg, float); s.ba = np.array(ba, float)
         self.is_gravity_set = True
+        self.bFirstFeatures = True        # tryIncInit is only reached behind the gate of :366-372, and the initialising call goes on (:391)
         self.take_off_stamp = s.time
         self.last_ZUPT_time = s.time
         self.FEJ_now = s.copy()
@@ -549,8 +551,8 @@ class LarVioOracle:
         sel = [0, 1, 2, 6, 7, 8]
         P12 = P[sel, :]
         P11 = P12[:, sel]
-        nf = self.idp * len(self.feature_states)
-        pe = d - nf                        # end of the pose block; SLAM features follow (larvio.cpp:768-793)
+        nf = self.idp * len(self.feature_states) + 6 * len(self.nui_ids)
+        pe = d - nf                        # end of the pose block; SLAM features and nuisance states follow (larvio.cpp:768-793)
         order = list(range(pe)) + list(range(d, d + 6)) + list(range(pe, d))
         Pn = np.zeros((d + 6, d + 6))
         Pn[:d, :d] = P
@@ -695,6 +697,8 @@ class LarVioOracle:
                 (ekf_ids if sid_now in ft.obs else ekf_lost).append(fid)
         self.stats["n_ekf_lost"] = len(ekf_lost)
         self._rm_lost_features_cov(ekf_lost)
+        if self.use_schmidt:
+            self._rm_useless_nuisance()                             # :1920-1921
         self._update_grid_map()
         for fid in sorted(self.map_server.keys()):
             ft = self.map_server[fid]
@@ -835,9 +839,19 @@ class LarVioOracle:
             R_b2w = quat_to_rot(a.q)
             a.q_cam = rot_to_quat(R_b2w @ s.R_imu_cam0.T)
             a.p_cam = a.p + R_b2w @ s.t_cam0_imu
-        self._update_feature_states(dx, self.LEG + 6 * len(self.aug))
+        base = self.LEG + 6 * len(self.aug)
+        num_old = len(self.feature_states) - n_new // self.idp
+        self._update_feature_states(dx, base, d, num_old)
+        nn = 6 * len(self.nui_ids) if self.use_schmidt else 0
         if H_o.shape[0]:
-            P = (np.eye(d) - K @ H_o) @ P
+            I_KH = np.eye(d) - K @ H_o
+            if nn:                                               # :1805-1814
+                n0 = base + self.idp * num_old
+                P_nui = P[n0:n0 + nn, n0:n0 + nn].copy()
+                P = I_KH @ P
+                P[n0:n0 + nn, n0:n0 + nn] = P_nui
+            else:
+                P = I_KH @ P
             P = (P + P.T) / 2.0
         if n_new:
             nHHP = -HH @ P
@@ -845,6 +859,9 @@ class LarVioOracle:
             P22 = -nHHP @ HH.T + self.feature_noise * np.linalg.solve(H22, np.eye(n_new))
             Pn = np.zeros((d + n_new, d + n_new))
             Pn[:d, :d] = P; Pn[d:, :d] = nHHP; Pn[:d, d:] = nHHP.T; Pn[d:, d:] = P22
+            if nn:                                               # :1832-1845: the new columns go in FRONT of the nuisance block
+                order = list(range(d - nn)) + list(range(d, d + n_new)) + list(range(d - nn, d))
+                Pn = Pn[np.ix_(order, order)]
             P = (Pn + Pn.T) / 2.0
         self.P = P
 
@@ -876,32 +893,46 @@ class LarVioOracle:
             a.p_cam = a.p + R_b2w @ s.t_cam0_imu
         self._update_feature_states(dx, self.LEG + 6 * len(self.aug))
         I_KH = np.eye(K.shape[0]) - K @ H
-        P = I_KH @ P
+        if self.use_schmidt and self.nui_ids:          # :1579-1589 / :2940-2950: the nuisance block keeps its prior
+            n0 = self.LEG + 6 * len(self.aug) + self.idp * len(self.feature_states); n1 = n0 + 6 * len(self.nui_ids)
+            P_nui = P[n0:n1, n0:n1].copy()
+            P = I_KH @ P
+            P[n0:n1, n0:n1] = P_nui
+        else:
+            P = I_KH @ P
         self.P = (P + P.T) / 2.0
 
     # inverse-depth correction of the in-state features + recomputed world positions (:1536-1575, :1752-1801)
-    def _update_feature_states(self, dx, base):
+    # new_at / num_old: in measurementUpdate_hybrid the corrections of the features added by this update sit behind the old
+    # covariance (:1777-1793), i.e. behind the nuisance block when there is one
+    def _update_feature_states(self, dx, base, new_at=None, num_old=None):
         for i, fid in enumerate(self.feature_states):
             ft = self.map_server[fid]
-            a = self.aug[ft.id_anchor]
+            a = self._anchor_state(ft)
+            at = base + self.idp * i if (num_old is None or i < num_old) else new_at + self.idp * (i - num_old)
             if self.idp == 3:
-                ft.invParam = ft.invParam + dx[base + 3 * i:base + 3 * i + 3]
+                ft.invParam = ft.invParam + dx[at:at + 3]
                 p_c = np.array([ft.invParam[0] / ft.invParam[2], ft.invParam[1] / ft.invParam[2], 1 / ft.invParam[2]])
             else:
-                ft.invDepth += dx[base + i]
+                ft.invDepth += dx[at]
                 p_c = np.array([ft.obs_anchor[0] / ft.invDepth, ft.obs_anchor[1] / ft.invDepth, 1 / ft.invDepth])
             ft.position = quat_to_rot(a.q_cam) @ p_c + a.p_cam
 
-    # ---- measurementJacobian_ekf_3didp :984-1114 (no Schmidt: the anchor is always a window state)
+    # the anchor pose of an in-state feature: a window state, or with use_schmidt a nuisance state (:1000-1010, :1543-1549)
+    def _anchor_state(self, ft):
+        return self.aug[ft.id_anchor] if ft.id_anchor in self.aug else self.nui_states[ft.id_anchor]
+
+    # ---- measurementJacobian_ekf_3didp :984-1114
     def _meas_jacobian_3didp(self, sid, ft):
-        k = self.aug[sid]; a = self.aug[ft.id_anchor]
+        k = self.aug[sid]; a = self._anchor_state(ft)
+        nui = ft.id_anchor not in self.aug                       # :999-1010: a nuisance anchor is used as frozen (no FEJ, its own camera pose)
         R_b2c = k.R_imu_cam0; t_c_b = k.t_cam0_imu
         R_bk2w = quat_to_rot(k.q); R_w2bk = R_bk2w.T
         R_w2ck = R_b2c @ R_w2bk; t_ck_w = k.p + R_bk2w @ t_c_b
         R_ba2w = quat_to_rot(a.q); R_w2ba = R_ba2w.T
-        R_w2ca = R_b2c @ R_w2ba
+        R_w2ca = quat_to_rot(a.q_cam).T if nui else R_b2c @ R_w2ba           # :1032-1038
         f_ca = ft.invParam
-        if self.if_FEJ:
+        if self.if_FEJ and not nui:
             p_ca = R_b2c @ (R_w2ba @ (ft.position_FEJ - a.p_FEJ) - t_c_b)
         else:
             p_ca = np.array([f_ca[0] / f_ca[2], f_ca[1] / f_ca[2], 1 / f_ca[2]])
@@ -916,7 +947,7 @@ class LarVioOracle:
         J_k[0, 0] = 1 / p_ck[2]; J_k[1, 1] = 1 / p_ck[2]
         J_k[0, 2] = -p_ck[0] / (p_ck[2] * p_ck[2]); J_k[1, 2] = -p_ck[1] / (p_ck[2] * p_ck[2])
         J_p = R_w2ck @ R_w2ca.T
-        p_baf_w = (ft.position_FEJ - a.p_FEJ) if self.if_FEJ else (p_w - a.p)
+        p_baf_w = (ft.position_FEJ - a.p_FEJ) if (self.if_FEJ and not nui) else (p_w - a.p)
         p_bkf_w = (ft.position_FEJ - k.p_FEJ) if self.if_FEJ else (p_w - k.p)
         J_xa = np.zeros((3, 6)); J_xa[:, :3] = -R_w2ck @ skew(p_baf_w); J_xa[:, 3:] = R_w2ck
         J_xk = np.zeros((3, 6)); J_xk[:, :3] = R_w2ck @ skew(p_bkf_w); J_xk[:, 3:] = -R_w2ck
@@ -938,14 +969,15 @@ class LarVioOracle:
 
     # ---- measurementJacobian_ekf_1didp :1117-1244
     def _meas_jacobian_1didp(self, sid, ft):
-        k = self.aug[sid]; a = self.aug[ft.id_anchor]
+        k = self.aug[sid]; a = self._anchor_state(ft)
+        nui = ft.id_anchor not in self.aug                       # :1132-1143
         R_b2c = k.R_imu_cam0; t_c_b = k.t_cam0_imu
         f_an = ft.obs_anchor
         R_bk2w = quat_to_rot(k.q); R_w2bk = R_bk2w.T
         R_w2ck = R_b2c @ R_w2bk; t_ck_w = k.p + R_bk2w @ t_c_b
         R_ba2w = quat_to_rot(a.q); R_w2ba = R_ba2w.T
-        R_w2ca = R_b2c @ R_w2ba
-        if self.if_FEJ:
+        R_w2ca = quat_to_rot(a.q_cam).T if nui else R_b2c @ R_w2ba           # :1168-1174
+        if self.if_FEJ and not nui:
             p_ca = R_b2c @ (R_w2ba @ (ft.position_FEJ - a.p_FEJ) - t_c_b)
         else:
             p_ca = np.array([f_an[0] / ft.invDepth, f_an[1] / ft.invDepth, 1 / ft.invDepth])
@@ -957,7 +989,7 @@ class LarVioOracle:
         J_k[0, 0] = 1 / p_ck[2]; J_k[1, 1] = 1 / p_ck[2]
         J_k[0, 2] = -p_ck[0] / (p_ck[2] * p_ck[2]); J_k[1, 2] = -p_ck[1] / (p_ck[2] * p_ck[2])
         J_d = R_w2ck @ R_w2ca.T @ f_an
-        p_baf_w = (ft.position_FEJ - a.p_FEJ) if self.if_FEJ else (p_w - a.p)
+        p_baf_w = (ft.position_FEJ - a.p_FEJ) if (self.if_FEJ and not nui) else (p_w - a.p)
         p_bkf_w = (ft.position_FEJ - k.p_FEJ) if self.if_FEJ else (p_w - k.p)
         J_xa = np.zeros((3, 6)); J_xa[:, :3] = -R_w2ck @ skew(p_baf_w); J_xa[:, 3:] = R_w2ck
         J_xk = np.zeros((3, 6)); J_xk[:, :3] = R_w2ck @ skew(p_bkf_w); J_xk[:, 3:] = -R_w2ck
@@ -973,11 +1005,14 @@ class LarVioOracle:
         idp = self.idp
         # the anchor's own observation is not used with 1-D inverse depth (:1260-1262)
         valid = [sid for sid in state_ids if sid in ft.obs and not (idp == 1 and sid == ft.id_anchor)]
-        ncol = self.LEG + 6 * len(self.aug) + idp * len(self.feature_states)
+        ncol = self.LEG + 6 * len(self.aug) + idp * len(self.feature_states) + 6 * len(self.nui_ids)
         H = np.zeros((2 * len(valid), ncol)); r = np.zeros(2 * len(valid))
         order = sorted(self.aug.keys())
         a_idx = self.LEG + 6 * order.index(ft.id_anchor)
-        f_idx = self.LEG + 6 * len(self.aug) + idp * self.feature_states.index(ft.id)
+        # the features this call adds are not in the covariance yet; their columns follow it, i.e. the nuisance block (:1291-1300)
+        d = self.P.shape[0]
+        num_old = len(self.feature_states) - (ncol - d) // idp
+        f_idx = d + idp * (self.feature_states.index(ft.id) - num_old)
         k = 0
         for sid in valid:
             H_f, H_a, H_x, H_e, r_i = self._meas_jacobian_idp(sid, ft)
@@ -1000,7 +1035,11 @@ class LarVioOracle:
         H_f, H_a, H_x, H_e, r = self._meas_jacobian_idp(sid, ft)
         f_idx = self.LEG + 6 * len(self.aug) + self.idp * self.feature_states.index(ft.id)
         H[:, f_idx:f_idx + self.idp] = H_f
-        a_idx = self.LEG + 6 * order.index(ft.id_anchor)
+        if self.use_schmidt and ft.id_anchor in self.nui_ids:     # :1351-1366: the anchor's columns are in the nuisance block
+            num_new = (self.LEG + 6 * len(self.aug) + self.idp * len(self.feature_states) + 6 * len(self.nui_ids) - self.P.shape[0]) // self.idp
+            a_idx = (self.LEG + 6 * len(self.aug) + self.idp * (len(self.feature_states) - num_new) + 6 * self.nui_ids.index(ft.id_anchor))
+        else:
+            a_idx = self.LEG + 6 * order.index(ft.id_anchor)
         H[:, a_idx:a_idx + 6] = H_a
         c = self.LEG + 6 * order.index(sid)
         H[:, c:c + 6] = H_x
@@ -1017,8 +1056,21 @@ class LarVioOracle:
             keep = [i for i in range(self.P.shape[0]) if not (i0 <= i < i0 + self.idp)]
             self.P = self.P[np.ix_(keep, keep)]
             self.feature_states.pop(seq)
+            if self.use_schmidt:                                                     # :3329-3339
+                an = self.map_server[fid].id_anchor
+                if an in self.nui_ids:
+                    self.nui_features[an].remove(fid)
             self.lost_slam_features[fid] = self.map_server[fid].position.copy()      # :3342
             del self.map_server[fid]
+
+    # ---- rmUselessNuisanceState :3850-3895: nuisance states that anchor no feature any more leave the covariance
+    def _rm_useless_nuisance(self):
+        for nid in [i for i in self.nui_ids if len(self.nui_features.get(i, [])) == 0]:
+            seq = self.nui_ids.index(nid)
+            n0 = self.LEG + 6 * len(self.aug) + self.idp * len(self.feature_states) + 6 * seq
+            keep = [i for i in range(self.P.shape[0]) if not (n0 <= i < n0 + 6)]
+            self.P = self.P[np.ix_(keep, keep)]
+            self.nui_ids.pop(seq); del self.nui_states[nid]; self.nui_features.pop(nid, None)
 
     # ---- updateGridMap :3351-3370
     def _grid_code(self, xy):
@@ -1172,6 +1224,7 @@ class LarVioOracle:
             rm_ids = [self.imu_state.id - 1]
         rows = 0
         used = []
+        new_nui = []
         sid_now = self.imu_state.id
         for fid in sorted(self.map_server.keys()):
             ft = self.map_server[fid]
@@ -1180,6 +1233,11 @@ class LarVioOracle:
                 continue
             if ft.in_state:
                 if ft.id_anchor in involved:                       # :2345-2405
+                    if self.use_schmidt and self.imu_state.id - ft.id_anchor > 2:      # :2351-2358: a mature anchor becomes a nuisance state
+                        self.nui_features.setdefault(ft.id_anchor, []).append(fid)
+                        if ft.id_anchor not in new_nui:
+                            new_nui.append(ft.id_anchor)
+                        continue
                     if self.idp == 3:                              # the newest state becomes the anchor (:2361-2378)
                         new_id = self.imu_state.id
                         a = self.aug[new_id]
@@ -1248,7 +1306,12 @@ class LarVioOracle:
             seq = order.index(sid)
             a0 = self.LEG + 6 * seq
             keep = [i for i in range(self.P.shape[0]) if not (a0 <= i < a0 + 6)]
-            self.P = self.P[np.ix_(keep, keep)]
+            if self.use_schmidt and sid in new_nui:                # :2569-2613: the pose block moves behind everything else
+                perm = keep + list(range(a0, a0 + 6))
+                self.P = self.P[np.ix_(perm, perm)]
+                self.nui_ids.append(sid); self.nui_states[sid] = self.aug[sid]
+            else:
+                self.P = self.P[np.ix_(keep, keep)]
             del self.aug[sid]
 
     # ---- getNewAnchorId :3412-3472

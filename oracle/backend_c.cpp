@@ -823,7 +823,7 @@ void lvo_set_initial_state(void* h, double t, const double* q, const double* p, 
   f->s.time = t;
   memcpy(f->s.q, q, sizeof(double) * 4); memcpy(f->s.p, p, sizeof(double) * 3); memcpy(f->s.v, v, sizeof(double) * 3);
   memcpy(f->s.bg, bg, sizeof(double) * 3); memcpy(f->s.ba, ba, sizeof(double) * 3);
-  f->gravity_set = true; f->take_off = t; f->last_zupt = t; f->fej_now = f->s;
+  f->gravity_set = true; f->first = true /* the initialiser runs behind the gate of larvio.cpp:366-372 */; f->take_off = t; f->last_zupt = t; f->fej_now = f->s;
 }
 
 int lvo_process_features(void* h, double t_msg, const long long* ids, const double* data, int n, const double* imu, int m, int* consumed) {

@@ -94,7 +94,29 @@ int main(int argc, char** argv) {
         if (d.timeStampToSec > s.time) { vio.m_gyro_old = d.angular_velocity; vio.m_acc_old = d.linear_acceleration; break; }
       forced = true;
     }
-    bool ok = vio.processFeatures(&msg, imu_buf);
+    bool ok;
+    const char* stg = std::getenv("LVB_REF_STAGES");   // debugging aid: run ONE call stage by stage (the body of larvio.cpp:391-417) and dump P after each
+    if (stg && std::atoi(stg) == c && vio.is_gravity_set && vio.bFirstFeatures) {
+      auto dump = [&](const char* what) {
+        const Eigen::MatrixXd& P = vio.state_server.state_cov;
+        std::string path = std::string(std::getenv("LVB_REF_STAGES_DIR") ? std::getenv("LVB_REF_STAGES_DIR") : "/tmp") + "/stage_" + what + ".bin";
+        FILE* f = std::fopen(path.c_str(), "wb"); double d = (double)P.rows(); std::fwrite(&d, 8, 1, f);
+        for (int i = 0; i < P.rows(); ++i) for (int j = 0; j < P.cols(); ++j) { double v = P(i, j); std::fwrite(&v, 8, 1, f); }
+        std::fclose(f);
+      };
+      dump("0_start");
+      vio.batchImuProcessing(msg.timeStampToSec + vio.state_server.td, imu_buf); dump("1_propagated");
+      vio.addFeatureObservations(&msg);
+      vio.stateAugmentation(); dump("2_augmented");
+      if (vio.if_ZUPT_valid) vio.if_ZUPT = vio.checkZUPT();
+      vio.removeLostFeatures(); dump("3_updated");
+      vio.pruneImuStateBuffer(); dump("4_pruned");
+      if (vio.if_FEJ_config && !vio.if_FEJ && vio.state_server.imu_state.time - vio.take_off_stamp >= 0) vio.if_FEJ = true;
+      for (auto fid : vio.state_server.feature_states) vio.active_slam_features[fid] = vio.map_server[fid];
+      ok = true;
+    } else {
+      ok = vio.processFeatures(&msg, imu_buf);
+    }
     if (const char* tr = std::getenv("LVB_REF_TRACE_FEATURE")) {   // debugging aid: one feature's bookkeeping after every call
       long long fid = std::atoll(tr);
       auto it = vio.map_server.find(fid);

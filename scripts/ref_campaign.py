@@ -33,8 +33,8 @@ CASES = {
     "msckf_oldest": (dict(max_features_in_one_grid=0, sw_size=12, translation_threshold=0.02), 2, 70, {}, False),
     "hybrid_1d_oldest": (dict(sw_size=12, translation_threshold=0.02), 0, 130, {}, False),
     "hybrid_3d_oldest": (dict(sw_size=12, translation_threshold=0.02, feature_idp_dim=3), 0, 130, {}, False),
-    "schmidt_1d_oldest": (dict(sw_size=12, translation_threshold=0.02, use_schmidt=1), 0, 130, {}, False),
-    "schmidt_3d_oldest": (dict(sw_size=12, translation_threshold=0.02, use_schmidt=1, feature_idp_dim=3), 0, 130, {}, False),
+    "schmidt_1d_oldest": (dict(sw_size=12, translation_threshold=0.02, use_schmidt=1), 0, 150, {}, False),
+    "schmidt_3d_oldest": (dict(sw_size=12, translation_threshold=0.02, use_schmidt=1, feature_idp_dim=3), 0, 150, {}, False),
     "schmidt_1d": (dict(sw_size=16, use_schmidt=1), 0, 130, {}, False),
     "schmidt_3d": (dict(sw_size=16, use_schmidt=1, feature_idp_dim=3), 0, 130, {}, False),
 }
@@ -59,8 +59,8 @@ def run_case(name):
         return
     w = rr.compare_runs(a, b)
     oks = [r for r in b if r["ok"]]
-    print("%-16s calls %3d ok %3d  max dim %3d  max slam %2d | q %.1e p %.1e v %.1e bg %.1e ba %.1e ext %.1e td %.1e P %.1e | synth+fe %.0fs ref %.1fs oracle %.0fs" % (
-        name, len(b), len(oks), max(r["P"].shape[0] for r in oks), max(len(r["slam_ids"]) for r in oks), w["q"], w["p"], w["v"], w["bg"], w["ba"],
+    print("%-16s calls %3d ok %3d  max dim %3d  max slam %2d  max nui %d | q %.1e p %.1e v %.1e bg %.1e ba %.1e ext %.1e td %.1e P %.1e | synth+fe %.0fs ref %.1fs oracle %.0fs" % (
+        name, len(b), len(oks), max(r["P"].shape[0] for r in oks), max(len(r["slam_ids"]) for r in oks), max(len(r["nui_ids"]) for r in oks), w["q"], w["p"], w["v"], w["bg"], w["ba"],
         w["ext"], w["td"], w["P"], t1 - t0, t2 - t1, time.time() - t2), flush=True)
 
 

@@ -98,7 +98,7 @@ def run_oracle_on_calls(cfg_raw, calls, init=None, static_init=False):
             rec.update(t=s.time, q=s.q.copy(), p=s.p.copy(), v=s.v.copy(), bg=s.bg.copy(), ba=s.ba.copy(),
                        R_imu_cam0=s.R_imu_cam0.copy(), t_cam0_imu=s.t_cam0_imu.copy(), td=float(be.td), P=be.P.copy(),
                        n_win=len(be.aug), slam_ids=[int(i) for i in be.feature_states], n_imu_left=len(imu),
-                       win_ids=sorted(int(i) for i in be.aug))
+                       win_ids=sorted(int(i) for i in be.aug), nui_ids=[int(i) for i in getattr(be, "nui_ids", [])])
         out.append(rec)
     return out
 
@@ -164,6 +164,7 @@ def compare_runs(a, b):
         assert x["P"].shape == y["P"].shape, "state dimension differs: %s vs %s" % (x["P"].shape, y["P"].shape)
         assert x["n_win"] == y["n_win"] and list(x["slam_ids"]) == list(y["slam_ids"]), "window / SLAM feature bookkeeping differs"
         assert x["n_imu_left"] == y["n_imu_left"], "IMU buffer consumed differently"
+        assert list(x.get("nui_ids", [])) == list(y.get("nui_ids", [])), "nuisance states differ"
         dq = min(np.abs(x["q"] - y["q"]).max(), np.abs(x["q"] + y["q"]).max())
         worst["q"] = max(worst["q"], float(dq))
         for k in ("p", "v", "bg", "ba"):
@@ -259,6 +260,8 @@ def compare_with_fixture(run, ref):
             assert list(x["slam_ids"]) == list(y["slam_ids"]), "call %d: SLAM features in the state differ" % i
         if "n_imu_left" in x:
             assert x["n_imu_left"] == y["n_imu_left"], "call %d: IMU buffer consumed differently" % i
+        if "nui_ids" in x:
+            assert len(x["nui_ids"]) == y["n_nui"], "call %d: %d nuisance states, the reference has %d" % (i, len(x["nui_ids"]), y["n_nui"])
         worst["q"] = max(worst["q"], float(min(np.abs(x["q"] - y["q"]).max(), np.abs(x["q"] + y["q"]).max())))
         for k in ("p", "v", "bg", "ba"):
             worst[k] = max(worst[k], float(np.abs(x[k] - y[k]).max()))

@@ -579,6 +579,22 @@ def test_gpu_test_harness_runs_against_the_mock(cfg, monkeypatch):
     assert rep['steps'] >= 8 and rep['p'] == 0.0 and rep['imu_mismatch'] == 0
 
 
+def test_reference_fixture_harness_runs_against_the_mock(monkeypatch, lib_built):
+    """tests/test_gpu.py::_drive_fixture (the harness of the `-m gpu` tests that compare the CUDA filter with the reference-made
+    fixtures) executed on CPU with the oracle behind the Batch interface: forced start, self start through the real host-side
+    static initialiser, SLAM features and IMU-intrinsic calibration - the deviations must be the oracle's own (<= 1e-9)."""
+    import importlib
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from larvio_b200 import api
+    from mock_batch import MockBatch
+    tg = importlib.import_module("test_gpu")
+    monkeypatch.setattr(api, "Batch", MockBatch)
+    for name in ("msckf_oldest", "self_start", "hybrid_3d", "config_d"):
+        w = tg._drive_fixture(name)
+        assert w["n"] >= 18 and max(w["q"], w["p"], w["v"], w["bg"], w["ba"], w["ext"], w["td"], w["Pz"], w["Pdiag"], w["P"], w["calib"]) < 1e-9, (name, w)
+
+
 def test_self_start_and_replay_harness_run_against_the_mock(tmp_path, monkeypatch, lib_built):
     """Same idea for the two harnesses that start the filter with the static initialiser (real host C++, no GPU needed):
     the self-start GPU test and the Python half of the replay-driver test."""
@@ -595,7 +611,7 @@ def test_self_start_and_replay_harness_run_against_the_mock(tmp_path, monkeypatc
     seq = synth.make_sequence(c.raw, 3, 34, static_until=1.4)
     mav = _write_asl(tmp_path, seq, 34)
     rows = tg._python_two_call_replay(c, str(mav))
-    assert rows.shape[1] == 17 and rows.shape[0] >= 5 and rows[0, 0] > 0.0 and np.all(np.diff(rows[:, 0]) > 0)
+    assert rows.shape[1] == 17 and rows.shape[0] >= 5 and rows[0, 0] >= 0.0 and np.all(np.diff(rows[:, 0]) > 0)   # the initialising call itself publishes (larvio.cpp:376-391), at take-off time
 
 
 def test_update_invariant_to_orthogonal_row_transform(cfg):
@@ -783,7 +799,8 @@ def test_reference_arm_prints_the_contract_line(tmp_path):
 
 
 # ---- golden vectors produced by the REFERENCE's own filter (tests/golden/ref_*.npz, tests/golden/make_ref_golden.py) -----------------
-REF_CASES_ORACLE = ["msckf_sw30", "msckf_oldest", "hybrid_1d_oldest", "hybrid_3d", "config_d", "zupt", "self_start"]
+REF_CASES_ORACLE = ["msckf_sw30", "msckf_oldest", "hybrid_1d_oldest", "hybrid_3d", "config_d", "zupt", "self_start", "schmidt_1d_oldest",
+                    "schmidt_3d_oldest"]
 
 
 def _fixture(name):
