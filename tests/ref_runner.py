@@ -98,7 +98,9 @@ def run_oracle_on_calls(cfg_raw, calls, init=None, static_init=False):
             rec.update(t=s.time, q=s.q.copy(), p=s.p.copy(), v=s.v.copy(), bg=s.bg.copy(), ba=s.ba.copy(),
                        R_imu_cam0=s.R_imu_cam0.copy(), t_cam0_imu=s.t_cam0_imu.copy(), td=float(be.td), P=be.P.copy(),
                        n_win=len(be.aug), slam_ids=[int(i) for i in be.feature_states], n_imu_left=len(imu),
-                       win_ids=sorted(int(i) for i in be.aug), nui_ids=[int(i) for i in getattr(be, "nui_ids", [])])
+                       win_ids=sorted(int(i) for i in be.aug), nui_ids=[int(i) for i in getattr(be, "nui_ids", [])],
+                       stable={int(k_): np.array(v_) for k_, v_ in be.get_stable_map_points().items()},       # both getters clear what
+                       active={int(k_): np.array(v_) for k_, v_ in be.get_active_map_points().items()})       # they return (larvio.cpp:2719-2733)
         out.append(rec)
     return out
 
@@ -198,6 +200,7 @@ def pack_fixture(overrides, init, static_init, calls, ref):
     state = np.zeros((n, 16)); ext = np.zeros((n, 12)); td = np.zeros(n); calib = np.zeros((n, 27))
     meta = np.zeros((n, 5), np.int64)       # dim, n_win, n_slam, n_nui, n_imu_left
     Pz = []; Pd = []; slam = []; Pfro = np.zeros(n)
+    pts = []; pts_n = np.zeros((n, 2), np.int64)     # map points the two getters returned after the call: rows [id x y z], stable then active
     last = None
     for i, r in enumerate(ref):
         if not r["ok"]:
@@ -209,10 +212,14 @@ def pack_fixture(overrides, init, static_init, calls, ref):
         meta[i] = (d, r["n_win"], len(r["slam_ids"]), len(r["nui_ids"]), r["n_imu_left"])
         Pz.append(r["P"] @ fingerprint_vector(d)); Pd.append(np.diag(r["P"]).copy()); slam.append(np.array(r["slam_ids"], np.int64))
         Pfro[i] = np.linalg.norm(r["P"])
+        for w_, key in enumerate(("stable", "active")):
+            pts_n[i, w_] = len(r[key])
+            pts += [np.concatenate([[float(k_)], r[key][k_]]) for k_ in sorted(r[key])]
         last = i
     out.update(ok=ok, state=state, ext=ext, td=td, calib=calib, meta=meta, Pfro=Pfro,
                Pz=np.concatenate(Pz) if Pz else np.zeros(0), Pdiag=np.concatenate(Pd) if Pd else np.zeros(0),
-               slam_ids=np.concatenate(slam) if slam else np.zeros(0, np.int64))
+               slam_ids=np.concatenate(slam) if slam else np.zeros(0, np.int64),
+               pts=np.array(pts).reshape(-1, 4), pts_n=pts_n)
     if last is not None:
         out["P_last"] = ref[last]["P"]; out["P_last_call"] = np.array(last)
     return out
@@ -230,7 +237,7 @@ def load_fixture(path):
         a, b = z["imu_ofs"][i], z["imu_ofs"][i + 1]; f0, f1 = z["feat_ofs"][i], z["feat_ofs"][i + 1]
         calls.append(dict(frame=int(z["call_frame"][i]), t=float(z["call_t"][i]), imu=z["imu"][a:b], ids=z["ids"][f0:f1], data=z["data"][f0:f1]))
     ref = []
-    kd = 0; ks = 0
+    kd = 0; ks = 0; kp = 0
     for i in range(len(calls)):
         r = dict(ok=bool(z["ok"][i]))
         if r["ok"]:
@@ -240,6 +247,9 @@ def load_fixture(path):
                      Ma=z["calib"][i][18:27].reshape(3, 3), dim=d, n_win=n_win, n_nui=n_nui, n_imu_left=n_left,
                      Pz=z["Pz"][kd:kd + d], Pdiag=z["Pdiag"][kd:kd + d], Pfro=float(z["Pfro"][i]), slam_ids=[int(x) for x in z["slam_ids"][ks:ks + n_slam]])
             kd += d; ks += n_slam
+            for w_, key in enumerate(("stable", "active")):
+                m_ = int(z["pts_n"][i, w_]); rows = z["pts"][kp:kp + m_]; kp += m_
+                r[key] = {int(q_[0]): q_[1:4] for q_ in rows}
             if "P_last_call" in z.files and int(z["P_last_call"]) == i:
                 r["P"] = z["P_last"]
         ref.append(r)
@@ -249,7 +259,7 @@ def load_fixture(path):
 def compare_with_fixture(run, ref):
     """run: records with q p v bg ba R_imu_cam0 t_cam0_imu td P n_win slam_ids n_imu_left (oracle, compiled oracle or GPU);
     ref: load_fixture records.  Bookkeeping must be identical; returns the largest numeric deviations."""
-    worst = dict(q=0.0, p=0.0, v=0.0, bg=0.0, ba=0.0, ext=0.0, td=0.0, Pz=0.0, Pdiag=0.0, P=0.0, n=0)
+    worst = dict(q=0.0, p=0.0, v=0.0, bg=0.0, ba=0.0, ext=0.0, td=0.0, Pz=0.0, Pdiag=0.0, P=0.0, n=0, pts=0.0, n_pts=0)
     for i, (x, y) in enumerate(zip(run, ref)):
         assert bool(x["ok"]) == y["ok"], "call %d: processFeatures returned %s, the reference %s" % (i, x["ok"], y["ok"])
         if not y["ok"]:
@@ -273,5 +283,10 @@ def compare_with_fixture(run, ref):
         worst["Pdiag"] = max(worst["Pdiag"], float(np.linalg.norm(np.diag(x["P"]) - y["Pdiag"]) / np.linalg.norm(y["Pdiag"])))
         if "P" in y:
             worst["P"] = max(worst["P"], float(np.linalg.norm(x["P"] - y["P"]) / np.linalg.norm(y["P"])))
+        for key in ("stable", "active"):                 # getStableMapPointPositions / getActiveeMapPointPositions (larvio.h:86-87)
+            if key in x:
+                assert sorted(x[key]) == sorted(y[key]), "call %d: %s map points differ: %s vs %s" % (i, key, sorted(x[key]), sorted(y[key]))
+                for k_ in y[key]:
+                    worst["pts"] = max(worst["pts"], float(np.abs(np.asarray(x[key][k_]) - y[key][k_]).max())); worst["n_pts"] += 1
         worst["n"] += 1
     return worst

@@ -814,7 +814,7 @@ def _drive_fixture(name):
     c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), **ov)
     b = api.Batch(c, n_seq=1)
     host_init = api.StaticInitializer(c) if static_init else None
-    cap = ((int(c.raw["max_features_num"]) + 31) // 32) * 32
+    cap = b.cap
     buf = np.zeros((1, 1024), api.IMU_DTYPE); n_buf = np.zeros(1, np.int32)
     started = False; first = False
     run = []
@@ -849,7 +849,8 @@ def _drive_fixture(name):
             st = b.get_state(0); cal = b.get_calibration(0); P = b.get_covariance(0)
             rec.update(q=st["q"], p=st["p"], v=st["v"], bg=st["bg"], ba=st["ba"], R_imu_cam0=cal["R_imu_cam0"], t_cam0_imu=cal["t_cam0_imu"],
                        td=float(cal["td"]), P=P, n_win=int(round((P.shape[0] - _fixture_leg(c) - _fixture_idp(c) * _n_slam(ref, len(run))) / 6)),
-                       n_imu_left=int(n_buf[0]), Tg=cal["Tg"], As=cal["As"], Ma=cal["Ma"])
+                       n_imu_left=int(n_buf[0]), Tg=cal["Tg"], As=cal["As"], Ma=cal["Ma"],
+                       stable=b.get_points(0, 0), active=b.get_points(0, 1))          # larvio.h:86-87, read (and cleared) after every call like the fixture
         run.append(rec)
     b.close()
     if host_init is not None:
@@ -882,3 +883,4 @@ def test_backend_matches_the_compiled_reference(name, lib_built):
     assert w["n"] >= 18, w
     assert max(w["q"], w["p"], w["v"], w["bg"], w["ba"], w["ext"], w["td"]) < 1e-8, w
     assert max(w["Pz"], w["Pdiag"], w["P"]) < 1e-8 and w["calib"] < 1e-9, w
+    assert w["pts"] < 1e-7 and (w["n_pts"] > 0) == (name in ("hybrid_1d_oldest", "hybrid_3d", "config_d")), w     # map-point getters
