@@ -52,6 +52,14 @@ __device__ __forceinline__ double* core_of(const BeView& v, int s) { return v.be
 __device__ __forceinline__ int* icore_of(const BeView& v, int s) { return v.be.icore + (size_t)s * BE_ICORE; }
 __device__ __forceinline__ double* win_of(const BeView& v, int s, int slot) { return v.be.win + ((size_t)s * v.be.Wcap + slot) * BE_WIN; }
 __device__ __forceinline__ double* P_of(const BeView& v, int s) { return v.P + (size_t)s * v.be.LD * v.be.LD; }
+// anchor pose of a SLAM feature: a window slot, or (use_schmidt) a frozen nuisance state (larvio.cpp:1000-1010, 1543-1549)
+__device__ __forceinline__ const double* anchor_rec(const BeView& v, int s, int as) {
+  return as >= BE_NUI_BASE ? v.be.nui_win + ((size_t)s * v.be.NUI + (as - BE_NUI_BASE)) * BE_WIN : v.be.win + ((size_t)s * v.be.Wcap + as) * BE_WIN;
+}
+// first covariance column of that pose: the nuisance block follows the nf feature blocks that are in the covariance (:1351-1366)
+__device__ __forceinline__ int anchor_col(const BeView& v, int as, int n_win, int nf) {
+  return as >= BE_NUI_BASE ? v.be.LEG + 6 * n_win + v.be.IDP * nf + 6 * (as - BE_NUI_BASE) : v.be.LEG + 6 * as;
+}
 
 // ====================================================================== propagate
 // selector matrices of calPhi's IMU-intrinsic blocks (larvio.cpp:3534-3629): lower / diagonal / upper placement of a vector
@@ -514,12 +522,12 @@ __global__ void __launch_bounds__(256) be_augment_kernel(BeView v) {
     st3(w + W_PCAM, ld3(core + C_P) + m3_vec(R_b2w, ld3(core + C_TCI)));
   }
   const int sel[6] = {0, 1, 2, 6, 7, 8};
-  const int nf = ic[I_NF];
-  if (nf > 0) {
-    // SLAM-feature columns follow the pose block: the new pose is INSERTED before them (larvio.cpp:768-793).
+  const int nf = ic[I_NF], nnui = ic[I_NNUI];
+  if (nf > 0 || nnui > 0) {
+    // SLAM-feature (and nuisance) columns follow the pose block: the new pose is INSERTED before them (larvio.cpp:768-793).
     // P_aug[i][j] = P[m(i)][m(j)] with m = identity / selection rows / shifted feature indices -> generic re-map.
     int* cm = v.be.cmap + (size_t)s * LD;
-    const int pe = d - v.be.IDP * nf;
+    const int pe = d - v.be.IDP * nf - 6 * nnui;
     for (int i = tid; i < d + 6; i += blockDim.x) cm[i] = (i < pe) ? i : (i < pe + 6 ? sel[i - pe] : i - 6);
     __syncthreads();
     if (tid == 0) { ic[I_REMAP] = 1; ic[I_NEWDIM] = d + 6; ic[I_NWIN] = n_win + 1; }
@@ -830,7 +838,9 @@ __device__ void meas_jac_idp(const BeView& v, int s, size_t fi, int ws, bool fej
   const int Wcap = v.be.Wcap;
   const double* wk = win_of(v, s, ws);
   const int as = v.be.ft_anchor[fi];
-  const double* wa = win_of(v, s, as);
+  const double* wa = anchor_rec(v, s, as);
+  const bool nui = as >= BE_NUI_BASE;              // a nuisance anchor is used as frozen: its own camera pose, no first estimates (:1032-1046)
+  const bool fej_a = fej && !nui;
   const M3 R_b2c = m3_load(wk + W_RIC);
   const V3 t_c_b = ld3(wk + W_TCI);
   const V3 f_an = v3(v.be.ft_oa[fi * 2], v.be.ft_oa[fi * 2 + 1], 1.0);
@@ -841,17 +851,17 @@ __device__ void meas_jac_idp(const BeView& v, int s, size_t fi, int ws, bool fej
   const V3 t_ck_w = t_bk_w + m3_vec(R_bk2w, t_c_b);
   const M3 R_ba2w = quat_to_rot(wa + W_Q), R_w2ba = m3_t(R_ba2w);
   const V3 t_ba_w = ld3(wa + W_P);
-  const M3 R_w2ca = m3_mul(R_b2c, R_w2ba);
+  const M3 R_w2ca = nui ? m3_t(quat_to_rot(wa + W_QCAM)) : m3_mul(R_b2c, R_w2ba);
   const V3 p_w = ld3(v.be.ft_pos + fi * 3), p_fej = ld3(v.be.ft_pfej + fi * 3);
   V3 p_ca;
-  if (fej) p_ca = m3_vec(R_b2c, m3_vec(R_w2ba, p_fej - ld3(wa + W_PFEJ)) - t_c_b);
+  if (fej_a) p_ca = m3_vec(R_b2c, m3_vec(R_w2ba, p_fej - ld3(wa + W_PFEJ)) - t_c_b);
   else p_ca = v3(f_an.x / inv, f_an.y / inv, 1.0 / inv);
   const double* z = v.be.ft_obs + (fi * Wcap + ws) * 4;
   const V3 p_ck = m3_vec(R_w2ck, p_w - t_ck_w);
   J.r[0] = z[0] - p_ck.x / p_ck.z; J.r[1] = z[1] - p_ck.y / p_ck.z;
   const double Jk[2][3] = {{1 / p_ck.z, 0, -p_ck.x / (p_ck.z * p_ck.z)}, {0, 1 / p_ck.z, -p_ck.y / (p_ck.z * p_ck.z)}};
   const V3 J_d = m3_vec(R_w2ck, m3_tvec(R_w2ca, f_an));              // R_w2ck * R_w2ca^T * f_an
-  const V3 p_baf_w = fej ? (p_fej - ld3(wa + W_PFEJ)) : (p_w - t_ba_w);
+  const V3 p_baf_w = fej_a ? (p_fej - ld3(wa + W_PFEJ)) : (p_w - t_ba_w);
   const V3 p_bkf_w = fej ? (p_fej - ld3(wk + W_PFEJ)) : (p_w - t_bk_w);
   const M3 Jxa_l = m3_scale(m3_mul(R_w2ck, skew(p_baf_w)), -1.0);    // J_xa = [-R skew(p_baf) | R]
   const M3 Jxk_l = m3_mul(R_w2ck, skew(p_bkf_w));                   // J_xk = [R skew(p_bkf) | -R]
@@ -1049,16 +1059,17 @@ __global__ void __launch_bounds__(32) be_feature_kernel(BeView v, double* Traw) 
     if (lane == 0 && fidx >= 0) {
       Jac1d J;
       meas_jac_idp(v, s, fi, cur, fej, J);
+      const int acol = anchor_col(v, as, n_win, ic[I_NF]);
       for (int a = 0; a < 2; ++a) {
         double* row = H + (size_t)a * LD;
-        for (int c = 0; c < 6; ++c) { row[LEGD + 6 * as + c] = J.ha[a][c]; row[15 + c] = J.he[a][c]; }
+        for (int c = 0; c < 6; ++c) { row[acol + c] = J.ha[a][c]; row[15 + c] = J.he[a][c]; }
         for (int c = 0; c < 6; ++c) row[LEGD + 6 * cur + c] = J.hx[a][c];
         for (int q = 0; q < idp; ++q) row[fidx + q] = J.hf[a][q];
         if (v.cfg.estimate_td) row[21] = obs[(size_t)cur * 4 + 2 + a];
         rr[a] = J.r[a];
       }
       for (int j = 0; j < 7; ++j) nzl[nz4++] = 15 + j;
-      for (int c = 0; c < 6; ++c) nzl[nz4++] = LEGD + 6 * as + c;
+      for (int c = 0; c < 6; ++c) nzl[nz4++] = acol + c;
       if (cur != as) for (int c = 0; c < 6; ++c) nzl[nz4++] = LEGD + 6 * cur + c;
       for (int q = 0; q < idp; ++q) nzl[nz4++] = fidx + q;
     }
@@ -1387,7 +1398,36 @@ __global__ void __launch_bounds__(256) be_slam_grow_kernel(BeView v) {
     st3(v.be.ft_pos + fi * 3, m3_vec(quat_to_rot(wa + W_QCAM), p_c) + ld3(wa + W_PCAM));
   }
   __syncthreads();
+  const int nnui = ic[I_NNUI];
+  if (nnui > 0) {
+    // the new columns were appended behind the nuisance block (where featureJacobian_ekf_new puts them, :1291-1300); the
+    // reference then moves the nuisance block to the end (:1832-1845): [.. old features | new features | nuisance]
+    int* cm = v.be.cmap + (size_t)s * LD;
+    const int n0 = d - 6 * nnui;
+    for (int i = tid; i < d + nn; i += blockDim.x) cm[i] = (i < n0) ? i : (i < n0 + nn ? d + (i - n0) : i - nn);
+    __syncthreads();
+    if (tid == 0) { ic[I_REMAP] = 1; ic[I_NEWDIM] = d + nn; }
+  }
   if (tid == 0) { ic[I_DIM] = d + nn; ic[I_NF] = nf + n_new; ic[I_NNEW] = 0; }
+}
+
+// Schmidt update (:1579-1589, :1805-1814, :2940-2950): the nuisance block of P keeps its prior through every update - saved
+// before the update kernels, written back after P -= Y^T Y (before new feature columns are attached)
+__global__ void __launch_bounds__(256) be_nui_block_kernel(BeView v, int restore) {
+  const int s = blockIdx.x;
+  int* ic = icore_of(v, s);
+  if (!ic[I_OK]) return;
+  const int nn = 6 * ic[I_NNUI];
+  if (nn == 0) return;
+  const int LD = v.be.LD, W = 6 * v.be.NUI;
+  const int n0 = LEGD + 6 * ic[I_NWIN] + v.be.IDP * ic[I_NF];
+  double* P = P_of(v, s);
+  double* B = v.be.nui_P + (size_t)s * W * W;
+  for (int e = threadIdx.x; e < nn * nn; e += blockDim.x) {
+    const int a = e / nn, b = e - a * nn;
+    if (restore) P[(size_t)(n0 + a) * LD + n0 + b] = B[a * W + b];
+    else B[a * W + b] = P[(size_t)(n0 + a) * LD + n0 + b];
+  }
 }
 
 // ====================================================================== QR compression (SPQR thin QR at larvio.cpp:1430-1449, 2151-2171)
@@ -1907,7 +1947,7 @@ __global__ void __launch_bounds__(256) be_correct_kernel(BeView v) {
     if (idp == 3) { v.be.ft_oa[fi * 2] += dx[base + 3 * i]; v.be.ft_oa[fi * 2 + 1] += dx[base + 3 * i + 1]; }
     const double inv = v.be.ft_inv[fi] + dx[base + idp * i + idp - 1];
     v.be.ft_inv[fi] = inv;
-    const double* wa = win_of(v, s, v.be.ft_anchor[fi]);
+    const double* wa = anchor_rec(v, s, v.be.ft_anchor[fi]);
     const V3 p_c = v3(v.be.ft_oa[fi * 2] / inv, v.be.ft_oa[fi * 2 + 1] / inv, 1.0 / inv);
     st3(v.be.ft_pos + fi * 3, m3_vec(quat_to_rot(wa + W_QCAM), p_c) + ld3(wa + W_PCAM));
   }
@@ -1922,6 +1962,9 @@ __global__ void __launch_bounds__(256) be_zupt_build_kernel(BeView v) {
   if (!ic[I_ZUPT]) { if (tid == 0) { ic[I_ROWS] = 0; ic[I_R] = 0; } return; }
   const int RMAX = v.be.RMAX, LD = v.be.LD;
   const int nf0 = ic[I_NF];
+  // with nuisance states behind the feature block the reference's conservativeResize (:2770-2773) cuts the TAIL of the nuisance
+  // block off and leaves nui_ids behind: its own state is inconsistent from there on - reported, not imitated
+  if (tid == 0 && ic[I_NNUI] > 0) atomicExch(&ic[I_ERR], 6);
   const int d = ic[I_DIM] - v.be.IDP * nf0, N = ic[I_NWIN];        // read before thread 0 rewrites I_DIM below
   if (nf0 > 0) {                                        // :2770-2782: every SLAM feature leaves the state
     for (int i = tid; i < nf0; i += blockDim.x) {
@@ -1975,7 +2018,7 @@ __global__ void be_prune_select_kernel(BeView v) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= v.be.S) return;
   int* ic = icore_of(v, s);
-  ic[I_DO_PRUNE] = 0; ic[I_NRM] = 0;
+  ic[I_DO_PRUNE] = 0; ic[I_NRM] = 0; ic[I_NEWNUI] = 0;
   if (!ic[I_OK]) return;
   const int n = ic[I_NWIN];
   if (ic[I_ZUPT]) {                                       // :2321-2325: the previous state goes, whatever the window size
@@ -2061,10 +2104,24 @@ __global__ void __launch_bounds__(256) be_anchor_kernel(BeView v) {
     // in-state features to re-anchor, sorted by feature id
     const int* fs = v.be.fs_slot + (size_t)s * 64;
     int n = 0;
+    // use_schmidt (:2351-2358): a MATURE anchor pose (more than 2 states old - never one of the two newest poses the pruning
+    // rule may pick) is not handed over: it stays behind the feature block as a nuisance state, with every feature it anchors
+    int newnui = 0;
+    if (v.be.NUI > 0) {
+      for (int k = 0; k < 2; ++k) {
+        const int r = k ? r1 : r0;
+        if (r < 0 || (long long)ic[I_ID] - v.be.win_id[(size_t)s * Wcap + r] <= 2) continue;
+        for (int i = 0; i < ic[I_NF]; ++i) if (v.be.ft_anchor[(size_t)s * T + fs[i]] == r) { newnui |= 1 << k; break; }
+      }
+      const int cnt = (newnui & 1) + ((newnui >> 1) & 1);
+      if (ic[I_NNUI] + cnt > v.be.NUI) { atomicExch(&ic[I_ERR], 6); newnui = 0; }     // capacity: reported, handled as without Schmidt
+      ic[I_NEWNUI] = newnui;
+    }
     for (int i = 0; i < ic[I_NF]; ++i) {
       const size_t fi = (size_t)s * T + fs[i];
       const int as = v.be.ft_anchor[fi];
       if (as != r0 && as != r1) continue;
+      if ((as == r0 && (newnui & 1)) || (as == r1 && (newnui & 2))) continue;
       int k = n++;
       while (k > 0 && v.be.ft_id[(size_t)s * T + fs[s_list[k - 1]]] > v.be.ft_id[fi]) { s_list[k] = s_list[k - 1]; --k; }
       s_list[k] = i;
@@ -2204,6 +2261,24 @@ __global__ void __launch_bounds__(256) be_prune_tables_kernel(BeView v) {
   const int T = v.be.T, Wcap = v.be.Wcap;
   const int n = ic[I_NWIN];
   const int r0 = ic[I_RM0], r1 = (ic[I_NRM] > 1) ? ic[I_RM1] : -1;
+  // new nuisance states (:2611-2613): the pose record as the update left it, the number of features it anchors; in the order
+  // of the removed ids (r0 < r1), behind the existing ones
+  const int newnui = ic[I_NEWNUI];
+  const int idx0 = ic[I_NNUI], idx1 = idx0 + (newnui & 1);
+  if (newnui) {
+    if (tid < BE_WIN) {
+      if (newnui & 1) v.be.nui_win[((size_t)s * v.be.NUI + idx0) * BE_WIN + tid] = win_of(v, s, r0)[tid];
+      if (newnui & 2) v.be.nui_win[((size_t)s * v.be.NUI + idx1) * BE_WIN + tid] = win_of(v, s, r1)[tid];
+    }
+    if (tid == 0) {
+      int c0 = 0, c1 = 0;
+      const int* fs = v.be.fs_slot + (size_t)s * 64;
+      for (int i = 0; i < ic[I_NF]; ++i) { const int as = v.be.ft_anchor[(size_t)s * T + fs[i]]; c0 += (as == r0); c1 += (as == r1); }
+      if (newnui & 1) v.be.nui_cnt[(size_t)s * v.be.NUI + idx0] = c0;
+      if (newnui & 2) v.be.nui_cnt[(size_t)s * v.be.NUI + idx1] = c1;
+    }
+  }
+  __syncthreads();
   for (int i = tid; i < T; i += blockDim.x) {
     const size_t fi = (size_t)s * T + i;
     if (!(v.be.ft_flags[fi] & 1)) continue;
@@ -2220,8 +2295,10 @@ __global__ void __launch_bounds__(256) be_prune_tables_kernel(BeView v) {
       ++dst;
     }
     v.be.ft_mask[fi] = nm;
-    const int as = v.be.ft_anchor[fi];                 // anchors are window slots: follow the re-pack
-    if (as >= 0) v.be.ft_anchor[fi] = as - (as > r0 ? 1 : 0) - ((r1 >= 0 && as > r1) ? 1 : 0);
+    const int as = v.be.ft_anchor[fi];                 // anchors are window slots: follow the re-pack (nuisance anchors stay)
+    if ((v.be.ft_flags[fi] & 4) && as == r0 && (newnui & 1)) v.be.ft_anchor[fi] = BE_NUI_BASE + idx0;
+    else if ((v.be.ft_flags[fi] & 4) && r1 >= 0 && as == r1 && (newnui & 2)) v.be.ft_anchor[fi] = BE_NUI_BASE + idx1;
+    else if (as >= 0 && as < BE_NUI_BASE) v.be.ft_anchor[fi] = as - (as > r0 ? 1 : 0) - ((r1 >= 0 && as > r1) ? 1 : 0);
   }
   __syncthreads();
   if (tid < BE_WIN + 1) {
@@ -2243,11 +2320,15 @@ __global__ void __launch_bounds__(256) be_prune_cov_gather_kernel(BeView v) {
   int* ic = icore_of(v, s);
   if (!ic[I_OK] || !ic[I_DO_PRUNE]) return;
   const int d = ic[I_DIM], LD = v.be.LD;
-  const int nrm = ic[I_NRM];
-  const int nd = d - 6 * nrm;
+  const int nrm = ic[I_NRM], newnui = ic[I_NEWNUI];
+  const int ndk = d - 6 * nrm;                                     // columns that stay where they are (relative order)
+  const int nd = ndk + 6 * ((newnui & 1) + ((newnui >> 1) & 1));   // + the pose blocks that become nuisance states, moved to the end (:2569-2610)
   if (row >= nd) return;
   const int a0 = LEGD + 6 * ic[I_RM0], a1 = (nrm > 1) ? LEGD + 6 * ic[I_RM1] : (1 << 30);
-  auto src = [&](int i) { int x = i; if (x >= a0) x += 6; if (x >= a1) x += 6; return x; };
+  auto src = [&](int i) {
+    if (i >= ndk) { const int j = i - ndk; const bool first = (j < 6) && (newnui & 1); return (first ? a0 : a1) + j % 6; }
+    int x = i; if (x >= a0) x += 6; if (x >= a1) x += 6; return x;
+  };
   const double* P = P_of(v, s);
   double* Sd = v.be.Sm + (size_t)s * v.be.LDS * v.be.LDS;
   const int sr = src(row);
@@ -2258,7 +2339,8 @@ __global__ void __launch_bounds__(256) be_prune_cov_scatter_kernel(BeView v) {
   int* ic = icore_of(v, s);
   if (!ic[I_OK] || !ic[I_DO_PRUNE]) return;
   const int d = ic[I_DIM], LD = v.be.LD;
-  const int nd = d - 6 * ic[I_NRM];
+  const int newnui = ic[I_NEWNUI];
+  const int nd = d - 6 * ic[I_NRM] + 6 * ((newnui & 1) + ((newnui >> 1) & 1));
   if (row >= nd) return;
   double* P = P_of(v, s);
   const double* Sd = v.be.Sm + (size_t)s * v.be.LDS * v.be.LDS;
@@ -2290,7 +2372,10 @@ __global__ void __launch_bounds__(32) be_frame_end_kernel(BeView v) {
   const int nf = ic[I_NF];
   __syncwarp();
   if (lane == 0) {
-    if (ic[I_DO_PRUNE]) { ic[I_DIM] -= 6 * ic[I_NRM]; ic[I_NWIN] -= ic[I_NRM]; }
+    if (ic[I_DO_PRUNE]) {
+      const int nk = (ic[I_NEWNUI] & 1) + ((ic[I_NEWNUI] >> 1) & 1);       // removed poses that stay in the covariance as nuisance states
+      ic[I_DIM] -= 6 * (ic[I_NRM] - nk); ic[I_NWIN] -= ic[I_NRM]; ic[I_NNUI] += nk; ic[I_NEWNUI] = 0;
+    }
     const double* core = core_of(v, s);
     if (v.cfg.if_FEJ_config && !ic[I_FEJ] && core[C_TIME] - core[C_TAKEOFF] >= 0) ic[I_FEJ] = 1;
   }
@@ -2384,13 +2469,14 @@ __global__ void __launch_bounds__(64) be_slam_pre_kernel(BeView v) {
   if (tid < 64) grid[tid] = 0;
   __syncthreads();
   if (tid != 0) return;
-  const int nf = ic[I_NF];
-  if (nf == 0) return;
+  const int nf = ic[I_NF], nnui = ic[I_NNUI];
+  if (nf == 0 && nnui == 0) return;
   int* fs = v.be.fs_slot + (size_t)s * 64;
   const int cur = ic[I_NWIN] - 1, d = ic[I_DIM];
   const int idp = v.be.IDP;
-  const int base = d - idp * nf;
+  const int base = d - idp * nf - 6 * nnui;
   int* cm = v.be.cmap + (size_t)s * LD;
+  int* ncnt = v.be.nui_cnt + (size_t)s * (v.be.NUI > 0 ? v.be.NUI : 1);
   int keep = 0;
   for (int i = 0; i < base; ++i) cm[i] = i;
   for (int i = 0; i < nf; ++i) {
@@ -2399,15 +2485,45 @@ __global__ void __launch_bounds__(64) be_slam_pre_kernel(BeView v) {
     if ((v.be.ft_mask[fi] >> cur) & 1) {
       for (int q = 0; q < idp; ++q) cm[base + idp * keep + q] = base + idp * i + q;
       fs[keep++] = slot;
-      const double* o = v.be.ft_obs + (fi * Wcap + cur) * 4;
-      int* cell = grid_cell(v, s, grid, grid_code(v, o[0], o[1]));
-      if (cell) (*cell)++;
     } else {
+      const int as = v.be.ft_anchor[fi];
+      if (as >= BE_NUI_BASE) ncnt[as - BE_NUI_BASE] -= 1;       // nui_features[id_anchor].erase(feature) (:3329-3339)
       pts_put(v, 0, s, v.be.ft_id[fi], v.be.ft_pos + fi * 3);   // lost_slam_features[id] = map_server[id] (:3342)
       v.be.ft_flags[fi] = 0; v.be.ft_mask[fi] = 0;              // rmLostFeaturesCov erases the feature
     }
   }
-  if (keep != nf) { ic[I_REMAP] = 1; ic[I_NEWDIM] = base + idp * keep; ic[I_NF] = keep; }
+  // rmUselessNuisanceState (:3850-3895): nuisance states that anchor no feature any more leave the covariance; the others
+  // close ranks (their order is the order of nui_ids), and the anchors of the remaining features follow
+  int nkeep = 0;
+  if (nnui > 0) {
+    int newidx[BE_NUI_MAX];
+    const int c0 = base + idp * keep, o0 = base + idp * nf;
+    for (int k = 0; k < nnui; ++k) {
+      if (ncnt[k] > 0) {
+        for (int q = 0; q < 6; ++q) cm[c0 + 6 * nkeep + q] = o0 + 6 * k + q;
+        if (nkeep != k) {
+          double* dst = v.be.nui_win + ((size_t)s * v.be.NUI + nkeep) * BE_WIN;
+          const double* src = v.be.nui_win + ((size_t)s * v.be.NUI + k) * BE_WIN;
+          for (int q = 0; q < BE_WIN; ++q) dst[q] = src[q];
+          ncnt[nkeep] = ncnt[k];
+        }
+        newidx[k] = nkeep++;
+      } else newidx[k] = -1;
+    }
+    if (nkeep != nnui)
+      for (int i = 0; i < keep; ++i) {
+        const size_t fi = (size_t)s * T + fs[i];
+        const int as = v.be.ft_anchor[fi];
+        if (as >= BE_NUI_BASE) v.be.ft_anchor[fi] = BE_NUI_BASE + newidx[as - BE_NUI_BASE];
+      }
+  }
+  for (int i = 0; i < keep; ++i) {                               // updateGridMap (:3351-3370) over the features that stay
+    const size_t fi = (size_t)s * T + fs[i];
+    const double* o = v.be.ft_obs + (fi * Wcap + cur) * 4;
+    int* cell = grid_cell(v, s, grid, grid_code(v, o[0], o[1]));
+    if (cell) (*cell)++;
+  }
+  if (keep != nf || nkeep != nnui) { ic[I_REMAP] = 1; ic[I_NEWDIM] = base + idp * keep + 6 * nkeep; ic[I_NF] = keep; ic[I_NNUI] = nkeep; }
 }
 
 // ---------------------------------------------------------------- sequential part of the promotion rule (:1968-2002)
@@ -2508,7 +2624,6 @@ static int bdalloc(LvbHandle* h, T** p, size_t count) {
 
 static const char* be_unsupported_reason(const LvbConfig& c) {
   if (c.max_features_in_one_grid > 0 && c.aug_grid_rows * c.aug_grid_cols != 0) {
-    if (c.use_schmidt) return "use_schmidt: 1 (Schmidt nuisance states) is not built yet";
     if (c.max_features_in_one_grid * c.aug_grid_rows * c.aug_grid_cols > 64) return "more than 64 EKF-SLAM features";
   }
   if (c.sw_size + 1 > 64) return "sw_size > 63";
@@ -2583,10 +2698,11 @@ int be_alloc(LvbHandle* h) {
   be->T = 2 * be->N;
   be->grid_rows = c.aug_grid_rows; be->grid_cols = c.aug_grid_cols; be->max_per_cell = c.max_features_in_one_grid > 0 ? c.max_features_in_one_grid : 0;
   be->NFmax = be->max_per_cell * be->grid_rows * be->grid_cols;
-  if (be->NFmax > 64 || c.use_schmidt) be->NFmax = 0;   // such configs are refused at the first back-end call
+  if (be->NFmax > 64) be->NFmax = 0;                     // such configs are refused at the first back-end call
+  be->NUI = (c.use_schmidt && be->NFmax > 0) ? BE_NUI_MAX : 0;
   be->IDP = (c.feature_idp_dim == 1) ? 1 : 3;           // anything but 1 means 3 (larvio.cpp:270-274)
   be->LEG = h->cfg.calib_imu_instrinsic ? 46 : 22;
-  be->Dmax = be->LEG + 6 * be->Wcap + be->IDP * be->NFmax;
+  be->Dmax = be->LEG + 6 * be->Wcap + be->IDP * be->NFmax + 6 * be->NUI;
   be->LD = ((be->Dmax + 7) / 8) * 8;
   be->LDS = be->NFmax ? ((be->Dmax + 2 * be->NFmax + 16 * be->NFmax + 7) / 8) * 8 : be->LD;
   // row capacities of one measurement pass: every track that reaches max_track_len in the same frame contributes
@@ -2614,7 +2730,8 @@ int be_alloc(LvbHandle* h) {
   BDA(be->Tm, S * (size_t)be->RAWMAX * LD);      // doubles as the per-feature H*P scratch of the gate
   BDA(be->Sm, S * (size_t)be->LDS * be->LDS); BDA(be->zvec, S * (size_t)be->LDS); BDA(be->dx, S * (size_t)be->LDS);
   BDA(be->ft_inv, S * T); BDA(be->ft_oa, S * T * 2); BDA(be->ft_anchor, S * T); BDA(be->ft_pfej, S * T * 3); BDA(be->ft_spec, S * T * 8);
-  BDA(be->ft_gamma, S * T); BDA(be->fs_slot, S * 64); BDA(be->cmap, S * LD); BDA(be->cand, S * 128); BDA(be->grid_oor, S * BE_GRID_OOR); BDA(be->Hnew, S * 64 * be->IDP * (LD + 4));
+  BDA(be->ft_gamma, S * T); BDA(be->fs_slot, S * 64); BDA(be->cmap, S * LD); BDA(be->cand, S * 128); BDA(be->grid_oor, S * BE_GRID_OOR);
+  { const size_t nu = be->NUI > 0 ? be->NUI : 1; BDA(be->nui_win, S * nu * BE_WIN); BDA(be->nui_cnt, S * nu); BDA(be->nui_P, S * 36 * nu * nu); } BDA(be->Hnew, S * 64 * be->IDP * (LD + 4));
   BDA(be->imu, S * be->imu_cap); BDA(be->n_imu, S);
   BDA(be->msg_in, S * be->N); BDA(be->msg_in_n, S); BDA(be->msg_in_t, S); BDA(be->msg_in_valid, S);
   BPIN(be->pin_imu, LvbImu, S * be->imu_cap); BPIN(be->pin_n_imu, int, S); BPIN(be->pin_icore, int, S * BE_ICORE);
@@ -2682,6 +2799,11 @@ static int be_update(LvbHandle* h, BeView& v, bool zupt_rows = false, bool resca
   LvbBackEnd* be = h->be;
   if (zupt_rows || rescan) RC(be_colscan(h, v, I_R));
   cudaStream_t st = h->stream;
+  if (be->NUI > 0) {                               // use_schmidt: the nuisance block keeps its prior (saved here, restored below)
+    LVB_PROF(h, "be_nui_block_kernel");
+    be_nui_block_kernel<<<be->S, 256, 0, st>>>(v, 0);
+    LVB_LAUNCH_CHECK(h);
+  }
   const size_t LD = be->LD;
   GemmArgs g;
   g.icore = be->icore; g.diag_vec = nullptr; g.sD = be->LDS;
@@ -2728,6 +2850,11 @@ static int be_update(LvbHandle* h, BeView& v, bool zupt_rows = false, bool resca
   g.m_idx = I_DIM; g.n_idx = I_DIM; g.k_idx = I_R; g.alpha = -1.0; g.beta = 1.0; g.diag = 0.0;
   RC(launch_gemm(h, g, be->Dmax, be->Dmax));
   DBG("gemm P-=YtY");
+  if (be->NUI > 0) {
+    LVB_PROF(h, "be_nui_block_kernel");
+    be_nui_block_kernel<<<be->S, 256, 0, st>>>(v, 1);
+    LVB_LAUNCH_CHECK(h);
+  }
   return LVB_OK;
 }
 
@@ -2855,6 +2982,7 @@ static int be_measurement_pass(LvbHandle* h, BeView& v, int mode) {
     be_slam_grow_kernel<<<be->S, 256, 0, st>>>(v);
     LVB_LAUNCH_CHECK(h);
     DBG("be_slam_grow_kernel");
+    if (be->NUI > 0) RC(be_remap(h, v));             // the nuisance block moves behind the new feature columns (:1832-1845)
   }
   return LVB_OK;
 }
@@ -2965,7 +3093,7 @@ static int be_finish(LvbHandle* h, LvbImu* imu, int* n_imu, int imu_stride, uint
       if (ic[I_ERR]) err = ic[I_ERR];
     }
   }
-  if (err) return lvb_set_err(LVB_E_CAPACITY, "back-end capacity exceeded (code %d: 1 feature table, 2 window, 3 raw rows, 4 stacked rows, 5 grid cell code outside [-64, 192))", err);
+  if (err) return lvb_set_err(LVB_E_CAPACITY, "back-end capacity exceeded (code %d: 1 feature table, 2 window, 3 raw rows, 4 stacked rows, 5 grid cell code outside [-64, 192), 6 nuisance states: more than 16, or a ZUPT while some exist)", err);
   return LVB_OK;
 }
 

@@ -20,7 +20,10 @@ enum {
   I_R = 12 /*rows after compression*/, I_NUSED = 13, I_RAWROWS = 14, I_ERR = 15, I_RM0 = 16, I_RM1 = 17, I_NRM = 18,
   I_DO_PRUNE = 19, I_ZUPT_EVENTS = 20, I_UPDATES = 21, I_NF = 22 /*EKF-SLAM features in state*/, I_REMAP = 23, I_NEWDIM = 24,
   I_NNEW = 25 /*new SLAM features accepted this frame*/, I_NCAND = 26, I_RO = 27 /*rows of H_o before the new-feature rows*/,
-  I_NC = 28 /*structurally nonzero columns of the stacked Jacobian (kmap)*/, BE_ICORE = 32,
+  I_NC = 28 /*structurally nonzero columns of the stacked Jacobian (kmap)*/,
+  I_NNUI = 29 /*Schmidt nuisance states in the covariance (use_schmidt, larvio.cpp:2351-2358)*/,
+  I_NEWNUI = 30 /*bit k: window slot I_RM0+k becomes a nuisance state in this prune (:2569-2613)*/, BE_ICORE = 32,
+  BE_NUI_MAX = 16 /*capacity of the nuisance block*/, BE_NUI_BASE = 64 /*ft_anchor >= BE_NUI_BASE: nuisance state ft_anchor - BE_NUI_BASE*/,
   BE_GRID_OOR = 256, BE_GRID_OOR_NEG = 64
 };
 // ---- win[s][slot][BE_WIN] doubles (IMUState_Aug)
@@ -54,6 +57,11 @@ struct LvbBackEnd {
   // updateGridMap (larvio.cpp:3355-3357) empties the rows*cols cells only; a cell created by an observation beyond the image
   // border (row == grid_rows, col < 0, ...) is never emptied, so these counts persist for the life of the handle
   int* grid_oor;
+  // Schmidt nuisance states (use_schmidt: 1): poses that left the window while they anchored SLAM features stay BEHIND the feature
+  // block of the covariance, frozen (larvio.cpp:2351-2358, 2569-2613).  NUI = capacity (0 without use_schmidt); nui_win[S][NUI][BE_WIN]
+  // = the IMUState_Aug copies (nui_imu_states), nui_cnt[S][NUI] = features each one still anchors (nui_features[id].size()),
+  // nui_P[S][(6 NUI)^2] = the block an update must leave untouched (:1579-1589)
+  int NUI; double* nui_win; int* nui_cnt; double* nui_P;
   double* ft_gamma;                           // [S][T] last gating statistic of each slot (diagnostics)
   // map points for getStableMapPointPositions / getActiveeMapPointPositions (larvio.h:86-87): [which][S][PCAP], which 0 = SLAM
   // features that left the state (lost_slam_features, larvio.cpp:3342), 1 = features in the state at the end of a step

@@ -78,6 +78,10 @@ class MockBatch:
         b = self.be[s]; o = b.imu_state
         return dict(R_imu_cam0=o.R_imu_cam0.copy(), t_cam0_imu=o.t_cam0_imu.copy(), td=b.td, Tg=b.Tg.copy(), As=b.As.copy(), Ma=b.Ma.copy())
 
+    def get_window(self, s, cap=64):
+        a = self.be[s].aug
+        return np.array([np.concatenate([a[k].q, a[k].p]) for k in sorted(a)]).reshape(-1, 7)
+
     def get_points(self, s, which, cap=512):
         m = self.be[s].get_active_map_points() if which else self.be[s].get_stable_map_points()
         return {int(k): np.array(v) for k, v in m.items()}

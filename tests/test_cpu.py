@@ -590,7 +590,7 @@ def test_reference_fixture_harness_runs_against_the_mock(monkeypatch, lib_built)
     from mock_batch import MockBatch
     tg = importlib.import_module("test_gpu")
     monkeypatch.setattr(api, "Batch", MockBatch)
-    for name in ("msckf_oldest", "self_start", "hybrid_3d", "config_d"):
+    for name in ("msckf_oldest", "self_start", "hybrid_3d", "config_d", "schmidt_1d_oldest"):
         w = tg._drive_fixture(name)
         assert w["n"] >= 18 and max(w["q"], w["p"], w["v"], w["bg"], w["ba"], w["ext"], w["td"], w["Pz"], w["Pdiag"], w["P"], w["calib"]) < 1e-9, (name, w)
 

@@ -788,17 +788,18 @@ def test_sharded_batch_through_the_c_abi_matches_one_handle(cfg, seqs):
 def test_unsupported_configs_fail_loudly(lib_built):
     from larvio_b200 import api
     from larvio_b200.config import Config
-    c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), use_schmidt=1)          # Schmidt nuisance states: not built
+    c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), max_features_in_one_grid=3)     # 3 x 30 cells: beyond the 64-feature SLAM block
     b = api.Batch(c, n_seq=1)
     imu = np.zeros((1, 8), api.IMU_DTYPE); n = np.zeros(1, np.int32)
     with pytest.raises(api.LarvioB200Error) as e:
         b.step(np.zeros((1, 480, 752), np.uint8), np.array([0.1]), imu, n)
-    assert "not built yet" in str(e.value)
+    assert "more than 64 EKF-SLAM features" in str(e.value)
     b.close()
 
 
 # ---- the CUDA back end against golden vectors the REFERENCE ITSELF produced (tests/golden/ref_*.npz) ---------------------------------
-REF_CASES_GPU = ["msckf_sw30", "msckf_oldest", "hybrid_1d_oldest", "hybrid_3d", "config_d", "zupt", "self_start"]
+REF_CASES_GPU = ["msckf_sw30", "msckf_oldest", "hybrid_1d_oldest", "hybrid_3d", "config_d", "zupt", "self_start", "schmidt_1d_oldest",
+                 "schmidt_3d_oldest"]
 
 
 def _drive_fixture(name):
@@ -848,7 +849,7 @@ def _drive_fixture(name):
         if rec["ok"]:
             st = b.get_state(0); cal = b.get_calibration(0); P = b.get_covariance(0)
             rec.update(q=st["q"], p=st["p"], v=st["v"], bg=st["bg"], ba=st["ba"], R_imu_cam0=cal["R_imu_cam0"], t_cam0_imu=cal["t_cam0_imu"],
-                       td=float(cal["td"]), P=P, n_win=int(round((P.shape[0] - _fixture_leg(c) - _fixture_idp(c) * _n_slam(ref, len(run))) / 6)),
+                       td=float(cal["td"]), P=P, n_win=len(b.get_window(0)),
                        n_imu_left=int(n_buf[0]), Tg=cal["Tg"], As=cal["As"], Ma=cal["Ma"],
                        stable=b.get_points(0, 0), active=b.get_points(0, 1))          # larvio.h:86-87, read (and cleared) after every call like the fixture
         run.append(rec)
@@ -861,18 +862,6 @@ def _drive_fixture(name):
     return w
 
 
-def _fixture_leg(c):
-    return 46 if int(c.raw["calib_imu_instrinsic"]) else 22
-
-
-def _fixture_idp(c):
-    return 3 if int(c.raw["feature_idp_dim"]) == 3 else 1
-
-
-def _n_slam(ref, i):
-    return len(ref[i]["slam_ids"]) if ref[i]["ok"] else 0
-
-
 @pytest.mark.parametrize("name", REF_CASES_GPU)
 def test_backend_matches_the_compiled_reference(name, lib_built):
     """The CUDA filter against the REFERENCE's own answers (not the numpy oracle): fixtures made by /root/reference/src/larvio.cpp
@@ -883,4 +872,4 @@ def test_backend_matches_the_compiled_reference(name, lib_built):
     assert w["n"] >= 18, w
     assert max(w["q"], w["p"], w["v"], w["bg"], w["ba"], w["ext"], w["td"]) < 1e-8, w
     assert max(w["Pz"], w["Pdiag"], w["P"]) < 1e-8 and w["calib"] < 1e-9, w
-    assert w["pts"] < 1e-7 and (w["n_pts"] > 0) == (name in ("hybrid_1d_oldest", "hybrid_3d", "config_d")), w     # map-point getters
+    assert w["pts"] < 1e-7 and (w["n_pts"] > 0) == (name in ("hybrid_1d_oldest", "hybrid_3d", "config_d", "schmidt_1d_oldest", "schmidt_3d_oldest")), w   # map-point getters
