@@ -68,7 +68,8 @@ typedef struct LvbConfig {
   int max_features_in_one_grid, aug_grid_rows, aug_grid_cols, feature_idp_dim, use_schmidt, _pad1;
   /* hybrid filter: max_features_in_one_grid * aug_grid_rows * aug_grid_cols EKF-SLAM features (<= 64, 0 = pure MSCKF);
      feature_idp_dim 1 = inverse depth on the anchor bearing, anything else = 3-D (x/z, y/z, 1/z) like larvio.cpp:270-274;
-     use_schmidt != 0 is refused with LVB_E_UNSUPPORTED */
+     use_schmidt != 0 (larvio.cpp:277): anchor poses older than two states that leave the window stay behind the feature block
+     as nuisance states (up to 16 per sequence; more is reported as LVB_E_CAPACITY) */
 } LvbConfig;
 
 /* include/sensors/ImuData.hpp:16-38 as a POD. */
