@@ -4,13 +4,16 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
 ``--impl reference`` legs may import this package.  The product (``larvio_b200``)
 never does: it fails loudly when its CUDA library is missing.
 
-Parity status: **parity unpinned** by the reference's own tests — the reference ships no
-tests, fixtures or golden vectors and cannot be compiled here (no
-Eigen / OpenCV C++ / SuiteSparse / Boost).  The front-end oracle therefore calls the
-very OpenCV functions the reference calls (cv2 4.13, pinned in this image) and restates
-the glue of image_processor.cpp around them; the back-end oracle is a numpy float64
-restatement of larvio.cpp / feature.hpp.  Golden vectors under tests/golden/ are
-generated from this oracle by tests/golden/make_golden.py.
+Parity status: **pinned**.  The reference ships no tests, fixtures or golden vectors, so the pins are:
+* front end — the very OpenCV functions the reference calls, executed by cv2 4.13 (pinned in this image), with the glue of
+  image_processor.cpp restated around them (frontend.py, orb.py, lk_exact.py, ransac.py: each checked against cv2 itself);
+* back end — golden vectors produced by the reference's OWN filter: `make ref` compiles /root/reference/src/larvio.cpp,
+  StaticInitializer.cpp and FlexibleInitializer.cpp unmodified against the stand-in headers of oracle/ref_shim/ (Eigen / boost /
+  OpenCV-core subsets written for this purpose; the real libraries are not in the image) into oracle/_ref/larvio_ref, driven by
+  oracle/ref_driver.cpp.  tests/golden/make_ref_golden.py records its answers in tests/golden/ref_*.npz; backend.py,
+  backend_c.cpp and the CUDA filter are tested against them (tests/test_cpu.py, tests/test_gpu.py).  The pin is of the reference's
+  logic; its linear algebra runs on the stand-in (rounding differs from real Eigen, nothing else).
+tests/golden/oracle_seq.npz (tests/golden/make_golden.py) additionally pins the synthetic generator and the front-end oracle.
 
 backend_c.cpp / orb_c.cpp are compiled twins of backend.py (pure MSCKF scope) and orb.py,
 pinned to them by tests/test_cpu.py and used by bench.py's CPU legs so that the CPU arm

@@ -1,7 +1,8 @@
 """CPU oracle of ``LarVio`` (TEST INFRASTRUCTURE — see oracle/__init__.py).
 
-numpy float64 restatement of /root/reference/src/larvio.cpp for the pure-MSCKF configuration
-(``max_features_in_one_grid: 0``) with FEJ, online extrinsics and td:
+numpy float64 restatement of /root/reference/src/larvio.cpp - pure MSCKF and hybrid (1-D / 3-D inverse-depth EKF-SLAM features,
+Schmidt nuisance states), FEJ, online extrinsics / td / IMU intrinsics, ZUPT - pinned call by call against the reference's own
+larvio.cpp compiled unmodified (oracle/_ref, tests/golden/ref_*.npz, tests/test_cpu.py::test_backend_oracle_matches_the_compiled_reference):
 processFeatures :363-461, batchImuProcessing :464-517, processModel :520-578, predictNewState
 :581-649, calPhi :3475-3530, stateAugmentation :720-801, addFeatureObservations :804-856,
 measurementJacobian_msckf :859-921, featureJacobian_msckf :924-981, measurementUpdate_msckf

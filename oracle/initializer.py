@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE (see oracle/__init__.py): CPU restatement of the reference's inclinometer initialiser,
 src/StaticInitializer.cpp:13-161, as FlexibleInitializer::tryIncInit (src/FlexibleInitializer.cpp:10-26) drives it.
-Parity unpinned by the reference (it ships no tests); the restatement is checked against the synthetic truth."""
+Pinned by tests/golden/ref_self_start.npz: the reference's own StaticInitializer.cpp (compiled unmodified, oracle/_ref) starts the
+filter at the same call with the same state; also checked against the synthetic truth."""
 import numpy as np
 
 
