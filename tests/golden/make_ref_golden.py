@@ -30,6 +30,8 @@ CASES = {
     "config_d": (dict(sw_size=16, calib_imu_instrinsic=1), 0, 120, {}, False),                              # BASELINE configs[3]
     "zupt": (dict(max_features_in_one_grid=0, sw_size=12), 5, 40, dict(static_until=1.0), False),
     "self_start": (dict(max_features_in_one_grid=0, sw_size=16), 3, 56, dict(static_until=1.4), True),
+    "no_fej_no_calib": (dict(max_features_in_one_grid=0, sw_size=12, if_FEJ=0, estimate_extrin=0, estimate_td=0), 1, 50, {}, False),
+    "calib_3d": (dict(sw_size=16, calib_imu_instrinsic=1, feature_idp_dim=3), 0, 116, {}, False),
     "schmidt_1d_oldest": (dict(sw_size=12, translation_threshold=0.02, use_schmidt=1), 0, 150, {}, False),
     "schmidt_3d_oldest": (dict(sw_size=12, translation_threshold=0.02, use_schmidt=1, feature_idp_dim=3), 0, 150, {}, False),
 }

@@ -799,7 +799,7 @@ def test_reference_arm_prints_the_contract_line(tmp_path):
 
 
 # ---- golden vectors produced by the REFERENCE's own filter (tests/golden/ref_*.npz, tests/golden/make_ref_golden.py) -----------------
-REF_CASES_ORACLE = ["msckf_sw30", "msckf_oldest", "hybrid_1d_oldest", "hybrid_3d", "config_d", "zupt", "self_start", "schmidt_1d_oldest",
+REF_CASES_ORACLE = ["msckf_sw30", "msckf_oldest", "hybrid_1d_oldest", "hybrid_3d", "config_d", "zupt", "self_start", "no_fej_no_calib", "calib_3d", "schmidt_1d_oldest",
                     "schmidt_3d_oldest"]
 
 

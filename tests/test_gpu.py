@@ -798,7 +798,7 @@ def test_unsupported_configs_fail_loudly(lib_built):
 
 
 # ---- the CUDA back end against golden vectors the REFERENCE ITSELF produced (tests/golden/ref_*.npz) ---------------------------------
-REF_CASES_GPU = ["msckf_sw30", "msckf_oldest", "hybrid_1d_oldest", "hybrid_3d", "config_d", "zupt", "self_start", "schmidt_1d_oldest",
+REF_CASES_GPU = ["msckf_sw30", "msckf_oldest", "hybrid_1d_oldest", "hybrid_3d", "config_d", "zupt", "self_start", "no_fej_no_calib", "calib_3d", "schmidt_1d_oldest",
                  "schmidt_3d_oldest"]
 
 
@@ -872,4 +872,4 @@ def test_backend_matches_the_compiled_reference(name, lib_built):
     assert w["n"] >= 18, w
     assert max(w["q"], w["p"], w["v"], w["bg"], w["ba"], w["ext"], w["td"]) < 1e-8, w
     assert max(w["Pz"], w["Pdiag"], w["P"]) < 1e-8 and w["calib"] < 1e-9, w
-    assert w["pts"] < 1e-7 and (w["n_pts"] > 0) == (name in ("hybrid_1d_oldest", "hybrid_3d", "config_d", "schmidt_1d_oldest", "schmidt_3d_oldest")), w   # map-point getters
+    assert w["pts"] < 1e-7 and (w["n_pts"] > 0) == (name in ("hybrid_1d_oldest", "hybrid_3d", "config_d", "calib_3d", "schmidt_1d_oldest", "schmidt_3d_oldest")), w   # map-point getters
