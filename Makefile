@@ -65,6 +65,13 @@ clean:
 REF_SRC := /root/reference
 REF_FLAGS := -O2 -std=c++17 -w -Ioracle/ref_shim -I$(REF_SRC)/include
 ref: oracle/_ref/larvio_ref
-oracle/_ref/larvio_ref: oracle/ref_driver.cpp oracle/ref_shim/Eigen/Dense oracle/ref_shim/opencv2/core/utility.hpp oracle/ref_shim/boost/math/distributions/chi_squared.hpp oracle/ref_shim/Initializer/DynamicInitializer.h
+oracle/_ref/larvio_ref: oracle/ref_driver.cpp oracle/ref_shim/Eigen/Dense oracle/ref_shim/opencv2/lvb_cv.hpp oracle/ref_shim/boost/math/distributions/chi_squared.hpp oracle/ref_shim/Initializer/DynamicInitializer.h
 	mkdir -p oracle/_ref
 	g++ $(REF_FLAGS) -o $@ oracle/ref_driver.cpp $(REF_SRC)/src/larvio.cpp $(REF_SRC)/src/StaticInitializer.cpp $(REF_SRC)/src/FlexibleInitializer.cpp
+
+# The reference's own FRONT END (src/image_processor.cpp + src/ORBDescriptor.cpp, compiled UNMODIFIED) against the same stand-in
+# headers; their OpenCV functions are executed by cv2 through oracle/cv_server.py (no OpenCV C++ headers in the image).
+ref_fe: oracle/_ref/larvio_ref_fe
+oracle/_ref/larvio_ref_fe: oracle/ref_fe_driver.cpp oracle/ref_shim/opencv2/lvb_cv.hpp oracle/ref_shim/Eigen/Dense
+	mkdir -p oracle/_ref
+	g++ $(REF_FLAGS) -ffp-contract=off -o $@ oracle/ref_fe_driver.cpp $(REF_SRC)/src/image_processor.cpp $(REF_SRC)/src/ORBDescriptor.cpp

@@ -19,7 +19,9 @@ use_schmidt max_features_in_one_grid aug_grid_rows aug_grid_cols rotation_thresh
 feature_translation_threshold position_std_threshold reset_fej_threshold noise_gyro noise_acc noise_gyro_bias noise_acc_bias
 noise_feature initial_covariance_orientation initial_covariance_velocity initial_covariance_position initial_covariance_gyro_bias
 initial_covariance_acc_bias initial_covariance_extrin_rot initial_covariance_extrin_trans if_ZUPT_valid zupt_max_feature_dis
-zupt_noise_v zupt_noise_p zupt_noise_q static_duration imu_rate pub_frequency resolution_width resolution_height td""".split()
+zupt_noise_v zupt_noise_p zupt_noise_q static_duration imu_rate pub_frequency resolution_width resolution_height td
+fast_threshold patch_size pyramid_levels max_iteration track_precision ransac_threshold max_features_num min_distance flag_equalize
+img_rate""".split()
 
 
 def write_reference_yaml(cfg_raw: dict, path: str, output_dir: str):
@@ -27,16 +29,56 @@ def write_reference_yaml(cfg_raw: dict, path: str, output_dir: str):
     lines = ["%YAML:1.0", "", 'output_dir: "%s"' % output_dir]
     for k in _SCALARS:
         lines.append("%s: %s" % (k, repr(cfg_raw[k]) if isinstance(cfg_raw[k], float) else cfg_raw[k]))
+    lines.append('distortion_model: "%s"' % cfg_raw["distortion_model"])
     it = cfg_raw["intrinsics"]
     lines.append("intrinsics:")
     for k in ("fx", "fy", "cx", "cy"):
         lines.append("   %s: %r" % (k, float(it[k])))
+    lines.append("distortion_coeffs:")
+    for k in ("k1", "k2", "p1", "p2"):
+        lines.append("   %s: %r" % (k, float(cfg_raw["distortion_coeffs"][k])))
     T = np.asarray(cfg_raw["T_cam_imu"]["data"], np.float64).reshape(4, 4)
     lines += ["T_cam_imu: !!opencv-matrix", "   rows: 4", "   cols: 4", "   dt: d", "   data:"]
     rows = [", ".join(repr(float(v)) for v in T[i]) for i in range(4)]
     lines.append("    [" + ",\n     ".join(rows) + "]")
     with open(path, "w") as f:
         f.write("\n".join(lines) + "\n")
+
+
+REF_FE_BIN = os.path.join(ROOT, "oracle", "_ref", "larvio_ref_fe")
+
+
+def run_reference_frontend(cfg_raw, seq, n_frames):
+    """The reference's own ImageProcessor (oracle/_ref/larvio_ref_fe, `make ref_fe`; its OpenCV calls run in cv2 through
+    oracle/cv_server.py) over the images and IMU rows of one sequence -> per frame None or dict(t, ids, data[n][8])."""
+    if not os.path.exists(REF_FE_BIN):
+        raise FileNotFoundError(REF_FE_BIN + " (build it with `make ref_fe`; needs /root/reference)")
+    import sys
+    with tempfile.TemporaryDirectory() as td:
+        ypath = os.path.join(td, "cfg.yaml"); ipath = os.path.join(td, "in.bin"); opath = os.path.join(td, "out.bin")
+        write_reference_yaml(cfg_raw, ypath, td + "/")
+        imgs = np.ascontiguousarray(seq.images[:n_frames], np.uint8)
+        with open(ipath, "wb") as f:
+            np.array([n_frames, imgs.shape[1], imgs.shape[2], len(seq.imu)], np.float64).tofile(f)
+            np.asarray(seq.img_t[:n_frames], np.float64).tofile(f)
+            np.ascontiguousarray(seq.imu, np.float64).tofile(f)
+            imgs.tofile(f)
+        env = dict(os.environ, LVB_CV_SERVER=os.path.join(ROOT, "oracle", "cv_server.py"), LVB_CV_SERVER_PYTHON=sys.executable)
+        r = subprocess.run([REF_FE_BIN, ypath, ipath, opath], capture_output=True, text=True, timeout=3600, env=env)
+        if r.returncode != 0:
+            raise RuntimeError("larvio_ref_fe failed (%d): %s" % (r.returncode, (r.stderr or r.stdout)[-3000:]))
+        o = np.fromfile(opath, np.float64)
+    k = 0
+    out = []
+    for _ in range(n_frames):
+        has = bool(o[k]); k += 1
+        if not has:
+            out.append(None); continue
+        t = float(o[k]); n = int(o[k + 1]); k += 2
+        rows = o[k:k + 9 * n].reshape(n, 9); k += 9 * n
+        out.append(dict(t=t, ids=rows[:, 0].astype(np.uint64), data=rows[:, 1:].copy()))
+    assert k == len(o)
+    return out
 
 
 def record_calls(cfg_raw, seq, n_frames):
