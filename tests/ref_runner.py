@@ -332,3 +332,66 @@ def compare_with_fixture(run, ref):
                     worst["pts"] = max(worst["pts"], float(np.abs(np.asarray(x[key][k_]) - y[key][k_]).max())); worst["n_pts"] += 1
         worst["n"] += 1
     return worst
+
+
+# ---- front-end fixtures (tests/golden/ref_fe_<case>.npz): what the reference's own ImageProcessor published -----------------
+FE_CASES = {
+    # name: (config overrides, sequence id, frames, synth kwargs, image edit)
+    "fe_plain": (dict(max_features_in_one_grid=0), 0, 60, {}, None),
+    "fe_blackout": (dict(max_features_in_one_grid=0), 0, 44, {}, "blackout"),            # every track lost for four frames, then repopulated
+    "fe_failed_second": (dict(max_features_in_one_grid=0), 1, 30, {}, "grey_second"),     # initializeFirstFeatures fails -> back to FIRST_IMAGE
+    "fe_400_tracks": (dict(max_features_in_one_grid=0, max_features_num=400, min_distance=14), 2, 24, {}, None),   # configs[4]'s front end
+    "fe_static_start": (dict(max_features_in_one_grid=0), 3, 40, dict(static_until=1.0), None),
+}
+
+
+def fe_case_sequence(name):
+    """(Config, Sequence, n_frames) of a front-end fixture, rebuilt deterministically from the synthetic generator."""
+    import copy
+    from larvio_b200.config import Config
+    ov, sid, nf, kw, edit = FE_CASES[name]
+    cfg = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"), **ov)
+    seq = copy.copy(synth.make_sequence(cfg.raw, sid, nf, **kw))
+    seq.images = seq.images.copy()
+    if edit == "blackout":
+        seq.images[20:24] = 117
+    elif edit == "grey_second":
+        seq.images[1] = 117
+    return cfg, seq, nf
+
+
+def pack_fe_fixture(name, seq, msgs):
+    import hashlib
+    has = np.array([m is not None for m in msgs], np.uint8)
+    ofs = np.cumsum([0] + [0 if m is None else len(m["ids"]) for m in msgs]).astype(np.int64)
+    ids = np.concatenate([m["ids"] for m in msgs if m is not None] or [np.zeros(0, np.uint64)]).astype(np.uint64)
+    data = np.concatenate([m["data"].reshape(-1, 8) for m in msgs if m is not None] or [np.zeros((0, 8))])
+    return dict(name=np.array(name), has=has, ofs=ofs, ids=ids, data=data, t=np.array([np.nan if m is None else m["t"] for m in msgs]),
+                img_sha=np.frombuffer(hashlib.sha256(seq.images.tobytes()).digest(), np.uint8))
+
+
+def load_fe_fixture(path):
+    z = np.load(path)
+    msgs = []
+    for j in range(len(z["has"])):
+        if not z["has"][j]:
+            msgs.append(None); continue
+        a, b = z["ofs"][j], z["ofs"][j + 1]
+        msgs.append(dict(t=float(z["t"][j]), ids=z["ids"][a:b], data=z["data"][a:b]))
+    return msgs, z["img_sha"]
+
+
+def compare_fe(msgs, ref):
+    """msgs: per frame None or dict(ids, data) of the implementation under test; ref: fixture.  Returns (published frames,
+    frames whose ids or order differ, largest |difference| of the eight message columns over frames with equal ids)."""
+    n_pub = 0; bad_ids = 0; worst = 0.0
+    for j, (m, r) in enumerate(zip(msgs, ref)):
+        assert (m is None) == (r is None), "frame %d: published %s, the reference %s" % (j, m is not None, r is not None)
+        if r is None:
+            continue
+        n_pub += 1
+        if len(m["ids"]) != len(r["ids"]) or not np.array_equal(np.asarray(m["ids"], np.uint64), r["ids"]):
+            bad_ids += 1; continue
+        if len(r["ids"]):
+            worst = max(worst, float(np.abs(np.asarray(m["data"], np.float64) - r["data"]).max()))
+    return n_pub, bad_ids, worst

@@ -593,6 +593,8 @@ def test_reference_fixture_harness_runs_against_the_mock(monkeypatch, lib_built)
     for name in ("msckf_oldest", "self_start", "hybrid_3d", "config_d", "schmidt_1d_oldest"):
         w = tg._drive_fixture(name)
         assert w["n"] >= 18 and max(w["q"], w["p"], w["v"], w["bg"], w["ba"], w["ext"], w["td"], w["Pz"], w["Pdiag"], w["P"], w["calib"]) < 1e-9, (name, w)
+    n_pub, bad_ids, worst = tg._drive_fe_fixture("fe_failed_second")           # the front-end fixture harness, same idea
+    assert n_pub >= 10 and bad_ids == 0 and worst == 0.0
 
 
 def test_self_start_and_replay_harness_run_against_the_mock(tmp_path, monkeypatch, lib_built):
@@ -882,3 +884,37 @@ def test_stand_in_chi_square_table_matches_scipy():
         out = subprocess.run([os.path.join(td, "t")], capture_output=True, text=True, check=True).stdout.split()
     got = np.array([float(x) for x in out]); want = chi2.ppf(0.05, np.arange(1, 100))
     assert np.abs(got / want - 1.0).max() < 1e-13
+
+
+# ---- the feature messages the REFERENCE's own front end publishes (tests/golden/ref_fe_*.npz, tests/golden/make_ref_fe_golden.py) ----
+REF_FE_CASES = ["fe_plain", "fe_blackout", "fe_failed_second", "fe_400_tracks", "fe_static_start"]
+
+
+@pytest.mark.parametrize("name", REF_FE_CASES)
+def test_frontend_oracle_matches_the_compiled_reference(name):
+    """oracle/frontend.py against the reference's own src/image_processor.cpp + src/ORBDescriptor.cpp, compiled unmodified against
+    the stand-in cv:: headers of oracle/ref_shim/ (their OpenCV functions executed by cv2 4.13 through oracle/cv_server.py): the same
+    frames publish, with the same feature ids in the same order and bit-identical u / v / velocity columns.  Cases: 60 plain
+    frames, a four-frame blackout that loses every track, a failed second image (state machine back to FIRST_IMAGE), 400 tracks
+    (configs[4]'s front end), a static start."""
+    import hashlib
+    import ref_runner as rr
+    cfg, seq, nf = rr.fe_case_sequence(name)
+    ref, sha = rr.load_fe_fixture(os.path.join(ROOT, "tests", "golden", "ref_%s.npz" % name))
+    assert np.array_equal(np.frombuffer(hashlib.sha256(seq.images.tobytes()).digest(), np.uint8), sha), "the synthetic generator changed"
+    calls = {c["frame"]: c for c in rr.record_calls(cfg.raw, seq, nf)}
+    n_pub, bad_ids, worst = rr.compare_fe([calls.get(j) for j in range(nf)], ref)
+    assert n_pub >= 10 and bad_ids == 0 and worst == 0.0, (n_pub, bad_ids, worst)
+
+
+def test_reference_frontend_fixture_is_what_the_reference_publishes_now():
+    """Build container only: rebuild oracle/_ref/larvio_ref_fe and replay one fixture bit for bit."""
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("no /root/reference here: the fixtures were generated in the build container")
+    import subprocess
+    import ref_runner as rr
+    subprocess.run(["make", "-s", "ref_fe"], cwd=ROOT, check=True, capture_output=True)
+    cfg, seq, nf = rr.fe_case_sequence("fe_failed_second")
+    ref, _ = rr.load_fe_fixture(os.path.join(ROOT, "tests", "golden", "ref_fe_failed_second.npz"))
+    n_pub, bad_ids, worst = rr.compare_fe(rr.run_reference_frontend(cfg.raw, seq, nf), ref)
+    assert n_pub >= 10 and bad_ids == 0 and worst == 0.0
