@@ -75,3 +75,9 @@ ref_fe: oracle/_ref/larvio_ref_fe
 oracle/_ref/larvio_ref_fe: oracle/ref_fe_driver.cpp oracle/ref_shim/opencv2/lvb_cv.hpp oracle/ref_shim/Eigen/Dense
 	mkdir -p oracle/_ref
 	g++ $(REF_FLAGS) -ffp-contract=off -o $@ oracle/ref_fe_driver.cpp $(REF_SRC)/src/image_processor.cpp $(REF_SRC)/src/ORBDescriptor.cpp
+
+# ... and the whole per-frame pipeline: front end + filter + static initialiser behind the loop of app/larvioMain.cpp:87-117
+ref_main: oracle/_ref/larvio_ref_main
+oracle/_ref/larvio_ref_main: oracle/ref_main_driver.cpp oracle/ref_shim/opencv2/lvb_cv.hpp oracle/ref_shim/Eigen/Dense
+	mkdir -p oracle/_ref
+	g++ $(REF_FLAGS) -ffp-contract=off -o $@ oracle/ref_main_driver.cpp $(REF_SRC)/src/image_processor.cpp $(REF_SRC)/src/ORBDescriptor.cpp $(REF_SRC)/src/larvio.cpp $(REF_SRC)/src/StaticInitializer.cpp $(REF_SRC)/src/FlexibleInitializer.cpp

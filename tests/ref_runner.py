@@ -395,3 +395,120 @@ def compare_fe(msgs, ref):
         if len(r["ids"]):
             worst = max(worst, float(np.abs(np.asarray(m["data"], np.float64) - r["data"]).max()))
     return n_pub, bad_ids, worst
+
+
+# ---- the whole reference pipeline (oracle/_ref/larvio_ref_main): front end + static initialiser + filter, larvioMain's loop ------
+REF_MAIN_BIN = os.path.join(ROOT, "oracle", "_ref", "larvio_ref_main")
+
+
+def write_mav(dirpath, seq):
+    """A synthetic sequence as an EuRoC ASL directory (PNG + csv, ns stamps) - what the replay tools read."""
+    import cv2
+    mav = os.path.join(str(dirpath), "mav0")
+    os.makedirs(os.path.join(mav, "cam0", "data")); os.makedirs(os.path.join(mav, "imu0"))
+    with open(os.path.join(mav, "cam0", "data.csv"), "w") as f:
+        f.write("#timestamp [ns],filename\n")
+        for t, im in zip(seq.img_t, seq.images):
+            ns = int(round(t * 1e9)); cv2.imwrite(os.path.join(mav, "cam0", "data", "%d.png" % ns), im); f.write("%d,%d.png\r\n" % (ns, ns))
+    with open(os.path.join(mav, "imu0", "data.csv"), "w") as f:
+        f.write("#timestamp [ns],w_x,w_y,w_z,a_x,a_y,a_z\n")
+        for r in seq.imu:
+            f.write("%d,%.17g,%.17g,%.17g,%.17g,%.17g,%.17g\r\n" % (int(round(r[0] * 1e9)), *r[1:]))
+    return mav
+
+
+def parse_odometry_lines(text):
+    """ODO / PTS lines of larvio_ref_main (rotation matrix) or larvio_shim_demo (quaternion x y z w) -> (odo rows, map-point lists)."""
+    odo = [np.array(l.split()[1:], float) for l in text.splitlines() if l.startswith("ODO ")]
+    pts = []
+    for l in text.splitlines():
+        if not l.startswith("PTS "):
+            continue
+        w = l.split()
+        vals = np.array(w[3:], float).reshape(-1, 4)
+        pts.append((w[1], {int(r[0]): r[1:4] for r in vals}))
+    return odo, pts
+
+
+def run_reference_pipeline(cfg_raw, mav_dir):
+    """The reference's main loop on the files of an EuRoC ASL directory (read like the replay tools read them)."""
+    import sys
+    from larvio_b200 import euroc
+    if not os.path.exists(REF_MAIN_BIN):
+        raise FileNotFoundError(REF_MAIN_BIN + " (build it with `make ref_main`; needs /root/reference)")
+    ts = []; imgs = []; rows = []
+    for t, img, r in euroc.Replay(str(mav_dir)):
+        ts.append(t); imgs.append(img); rows.append(r)
+    imgs = np.ascontiguousarray(np.stack(imgs), np.uint8); imu = np.concatenate(rows).reshape(-1, 7)
+    with tempfile.TemporaryDirectory() as td:
+        ypath = os.path.join(td, "cfg.yaml"); ipath = os.path.join(td, "in.bin")
+        write_reference_yaml(cfg_raw, ypath, td + "/")
+        with open(ipath, "wb") as f:
+            np.array([len(ts), imgs.shape[1], imgs.shape[2], len(imu)], np.float64).tofile(f)
+            np.asarray(ts, np.float64).tofile(f); np.ascontiguousarray(imu, np.float64).tofile(f); imgs.tofile(f)
+        env = dict(os.environ, LVB_CV_SERVER=os.path.join(ROOT, "oracle", "cv_server.py"), LVB_CV_SERVER_PYTHON=sys.executable)
+        r = subprocess.run([REF_MAIN_BIN, ypath, ipath], capture_output=True, text=True, timeout=3600, env=env)
+        if r.returncode != 0:
+            raise RuntimeError("larvio_ref_main failed (%d): %s" % (r.returncode, (r.stderr or r.stdout)[-3000:]))
+    return "\n".join(l for l in r.stdout.splitlines() if l.startswith(("ODO ", "PTS ")))
+
+
+def quat_xyzw_to_rot(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def compare_odometry(demo_text, ref_text):
+    """larvio_shim_demo's lines (t q p v) against larvio_ref_main's (t R p v): same publications, same map-point lists."""
+    odo, pts = parse_odometry_lines(demo_text); rodo, rpts = parse_odometry_lines(ref_text)
+    assert len(odo) == len(rodo), "%d odometry messages, the reference published %d" % (len(odo), len(rodo))
+    w = dict(n=len(odo), t=0.0, R=0.0, p=0.0, v=0.0, pts=0.0, n_lists=len(rpts))
+    for a, b in zip(odo, rodo):
+        w["t"] = max(w["t"], abs(a[0] - b[0]))
+        w["R"] = max(w["R"], float(np.abs(quat_xyzw_to_rot(a[1:5]) - b[1:10].reshape(3, 3)).max()))
+        w["p"] = max(w["p"], float(np.abs(a[5:8] - b[10:13]).max())); w["v"] = max(w["v"], float(np.abs(a[8:11] - b[13:16]).max()))
+    assert len(pts) == len(rpts), "%d map-point lists, the reference returned %d" % (len(pts), len(rpts))
+    for (ta, ma), (tb, mb) in zip(pts, rpts):
+        assert ta == tb and sorted(ma) == sorted(mb), "map-point list %s differs: %s vs %s" % (tb, sorted(ma), sorted(mb))
+        for k_ in mb:
+            w["pts"] = max(w["pts"], float(np.abs(ma[k_] - mb[k_]).max()))
+    return w
+
+
+def run_oracle_pipeline(cfg_raw, mav_dir):
+    """oracle/frontend.py + oracle/initializer.py + oracle/backend.py behind the same loop, printing larvio_shim_demo's lines."""
+    from larvio_b200 import euroc
+    from oracle.frontend import ImageProcessorOracle
+    from oracle.backend import LarVioOracle
+    from oracle.initializer import StaticInitializerOracle
+    fe = ImageProcessorOracle(cfg_raw); be = LarVioOracle(cfg_raw); init = StaticInitializerOracle(cfg_raw)
+    imu = []; lines = []; pubs = 0; first = False
+    for t, img, rows in euroc.Replay(str(mav_dir)):
+        imu.extend(rows.tolist())
+        msg = fe.process_image(img, t, np.array(imu).reshape(-1, 7))
+        if msg is None:
+            continue
+        if not be.is_gravity_set:
+            if not first:                                       # larvio.cpp:365-372
+                if len(imu) > 0 and imu[0][0] - msg.t - be.td <= 0.0:
+                    first = True
+                else:
+                    continue
+            o = init.try_inc_init(msg.ids, msg.data[:, :2], msg.t, np.array(imu).reshape(-1, 7))
+            if o is None:
+                continue
+            be.set_initial_state(o["t"], o["q"], o["p"], o["v"], o["bg"], o["ba"])
+            be.m_gyro_old = o["gyro_old"]; be.m_acc_old = o["acc_old"]
+            del imu[:o["n_consumed"]]
+        if not be.process_features(msg, imu):
+            continue
+        s = be.imu_state
+        lines.append("ODO %.9f " % t + " ".join("%.17g" % x for x in list(s.q) + list(s.p) + list(s.v)))
+        pubs += 1
+        if pubs % 10 == 0:
+            for tag, m in (("S", be.get_stable_map_points()), ("A", be.get_active_map_points())):
+                if m:
+                    lines.append("PTS %s %d " % (tag, len(m)) + " ".join("%d %.17g %.17g %.17g" % (k_, *m[k_]) for k_ in sorted(m)))
+    return "\n".join(lines)

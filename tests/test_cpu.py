@@ -918,3 +918,22 @@ def test_reference_frontend_fixture_is_what_the_reference_publishes_now():
     ref, _ = rr.load_fe_fixture(os.path.join(ROOT, "tests", "golden", "ref_fe_failed_second.npz"))
     n_pub, bad_ids, worst = rr.compare_fe(rr.run_reference_frontend(cfg.raw, seq, nf), ref)
     assert n_pub >= 10 and bad_ids == 0 and worst == 0.0
+
+
+def test_oracle_pipeline_matches_the_whole_reference_pipeline(tmp_path):
+    """Front end + static initialiser + hybrid filter behind app/larvioMain.cpp's loop: the oracle pipeline against what the
+    reference's own five source files (compiled unmodified, `make ref_main`) published on the same on-disk sequence
+    (tests/golden/ref_main_hybrid_selfstart.txt): the same 60+ publications, rotation / position / velocity <= 1e-9, identical
+    map-point lists (getStableMapPointPositions / getActiveeMapPointPositions) with positions <= 1e-9."""
+    import ref_runner as rr
+    from larvio_b200 import synth
+    from larvio_b200.config import Config
+    sys_path_tests = os.path.join(ROOT, "tests", "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_ref_main_golden", os.path.join(sys_path_tests, "make_ref_main_golden.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"))
+    seq = synth.make_sequence(c.raw, g.SPEC["seq"], g.SPEC["frames"], static_until=g.SPEC["static_until"])
+    mav = rr.write_mav(tmp_path, seq)
+    w = rr.compare_odometry(rr.run_oracle_pipeline(c.raw, mav), open(os.path.join(sys_path_tests, "ref_main_hybrid_selfstart.txt")).read())
+    assert w["n"] >= 60 and w["n_lists"] >= 2 and w["t"] < 1e-9 and max(w["R"], w["p"], w["v"], w["pts"]) < 1e-9, w

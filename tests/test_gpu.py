@@ -906,3 +906,25 @@ def test_frontend_matches_the_compiled_reference(name, lib_built):
     and their order bit-exact, all eight message columns bit-identical."""
     n_pub, bad_ids, worst = _drive_fe_fixture(name)
     assert n_pub >= 10 and bad_ids == 0 and worst == 0.0, (n_pub, bad_ids, worst)
+
+
+def test_shim_facade_matches_the_whole_reference_pipeline(tmp_path, lib_built):
+    """The drop-in claim end to end: larvio_b200/bin/larvio_shim_demo (app/larvioMain.cpp's loop on the shim's ImageProcessor /
+    LarVio over the CUDA library) against the reference's own five source files compiled unmodified behind the same loop
+    (oracle/_ref/larvio_ref_main; tests/golden/ref_main_hybrid_selfstart.txt) on the same on-disk sequence: euroc.yaml defaults
+    (hybrid, 5x6 SLAM grid), self start from a standstill.  Same publications, rotation / position / velocity within 1e-8,
+    identical map-point lists within 1e-7."""
+    import subprocess
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ref_runner as rr
+    from larvio_b200 import synth
+    from larvio_b200.config import Config
+    cfg_path = os.path.join(ROOT, "configs", "euroc_mono.yaml")
+    c = Config.load(cfg_path)
+    seq = synth.make_sequence(c.raw, 3, 150, static_until=1.4)          # tests/golden/make_ref_main_golden.py: SPEC
+    mav = rr.write_mav(tmp_path, seq)
+    exe = os.path.join(ROOT, "larvio_b200", "bin", "larvio_shim_demo")
+    r = subprocess.run([exe, cfg_path, str(mav)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    w = rr.compare_odometry(r.stdout, open(os.path.join(ROOT, "tests", "golden", "ref_main_hybrid_selfstart.txt")).read())
+    assert w["n"] >= 60 and w["n_lists"] >= 2 and w["t"] < 1e-9 and max(w["R"], w["p"], w["v"]) < 1e-8 and w["pts"] < 1e-7, w
