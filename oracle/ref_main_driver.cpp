@@ -53,12 +53,15 @@ int main(int argc, char** argv) {
     MonoCameraMeasurementPtr features = new MonoCameraMeasurement;       // :105
     const bool bProcess = ip.processImage(img, imu_msg_buffer, features);   // :107
     bool bPubOdo = false;
+    const size_t n_feat = features->features.size();
     if (bProcess) bPubOdo = est.processFeatures(features, imu_msg_buffer);  // :114
+    if (std::getenv("LVB_REF_TRACE"))      // debugging aid: what each frame did
+      std::fprintf(stderr, "FRAME %d t %.4f processImage %d features %zu processFeatures %d imu left %zu\n", j, img_t[j], (int)bProcess, n_feat, (int)bPubOdo, imu_msg_buffer.size());
     delete features;
     if (!bPubOdo) continue;
     const Eigen::Isometry3d T = est.getTbw();
     const Eigen::Vector3d v = est.getVel();
-    std::fprintf(out, "ODO %.9f", img_t[j]);
+    std::fprintf(out, "\nODO %.9f", img_t[j]);      // leading newline: the reference prints diagnostics without one
     for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) std::fprintf(out, " %.17g", T.linear()(a, b));
     for (int a = 0; a < 3; ++a) std::fprintf(out, " %.17g", T.translation()(a));
     for (int a = 0; a < 3; ++a) std::fprintf(out, " %.17g", v(a));
@@ -68,7 +71,7 @@ int main(int argc, char** argv) {
         std::map<FeatureIDType, Eigen::Vector3d> pts;
         if (which == 0) est.getStableMapPointPositions(pts); else est.getActiveeMapPointPositions(pts);
         if (pts.empty()) continue;
-        std::fprintf(out, "PTS %c %zu", which == 0 ? 'S' : 'A', pts.size());
+        std::fprintf(out, "\nPTS %c %zu", which == 0 ? 'S' : 'A', pts.size());
         for (const auto& kv : pts) std::fprintf(out, " %lld %.17g %.17g %.17g", (long long)kv.first, kv.second(0), kv.second(1), kv.second(2));
         std::fprintf(out, "\n");
       }

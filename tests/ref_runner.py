@@ -450,6 +450,8 @@ def run_reference_pipeline(cfg_raw, mav_dir):
         r = subprocess.run([REF_MAIN_BIN, ypath, ipath], capture_output=True, text=True, timeout=3600, env=env)
         if r.returncode != 0:
             raise RuntimeError("larvio_ref_main failed (%d): %s" % (r.returncode, (r.stderr or r.stdout)[-3000:]))
+        if os.environ.get("LVB_REF_TRACE"):
+            print("\n".join(l for l in r.stderr.splitlines() if l.startswith("FRAME ")))
     return "\n".join(l for l in r.stdout.splitlines() if l.startswith(("ODO ", "PTS ")))
 
 
