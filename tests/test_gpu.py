@@ -800,6 +800,9 @@ def test_unsupported_configs_fail_loudly(lib_built):
 # ---- the CUDA back end against golden vectors the REFERENCE ITSELF produced (tests/golden/ref_*.npz) ---------------------------------
 REF_CASES_GPU = ["msckf_sw30", "msckf_oldest", "hybrid_1d_oldest", "hybrid_3d", "config_d", "zupt", "self_start", "no_fej_no_calib", "calib_3d", "schmidt_1d_oldest",
                  "schmidt_3d_oldest"]
+# written after the round's GPU minutes were spent (every case above ran green on a B200, profiles/r2q_*, r2r_*): the oracle matches this
+# fixture on CPU, the device has not replayed it yet - a failure here is a finding, not a regression
+REF_CASES_GPU_UNRUN = ["hybrid_zupt"]
 
 
 def _drive_fixture(name):
@@ -862,7 +865,8 @@ def _drive_fixture(name):
     return w
 
 
-@pytest.mark.parametrize("name", REF_CASES_GPU)
+@pytest.mark.parametrize("name", REF_CASES_GPU + [pytest.param(n, marks=pytest.mark.xfail(strict=False, reason="first GPU run is the driver's"))
+                                                  for n in REF_CASES_GPU_UNRUN])
 def test_backend_matches_the_compiled_reference(name, lib_built):
     """The CUDA filter against the REFERENCE's own answers (not the numpy oracle): fixtures made by /root/reference/src/larvio.cpp
     compiled unmodified (oracle/_ref, tests/golden/make_ref_golden.py).  Per call: same return value, state dimension and IMU
@@ -872,7 +876,7 @@ def test_backend_matches_the_compiled_reference(name, lib_built):
     assert w["n"] >= 18, w
     assert max(w["q"], w["p"], w["v"], w["bg"], w["ba"], w["ext"], w["td"]) < 1e-8, w
     assert max(w["Pz"], w["Pdiag"], w["P"]) < 1e-8 and w["calib"] < 1e-9, w
-    assert w["pts"] < 1e-7 and (w["n_pts"] > 0) == (name in ("hybrid_1d_oldest", "hybrid_3d", "config_d", "calib_3d", "schmidt_1d_oldest", "schmidt_3d_oldest")), w   # map-point getters
+    assert w["pts"] < 1e-7 and (w["n_pts"] > 0) == (name in ("hybrid_1d_oldest", "hybrid_3d", "config_d", "calib_3d", "hybrid_zupt", "schmidt_1d_oldest", "schmidt_3d_oldest")), w   # map-point getters
 
 
 # ---- the CUDA front end against the feature messages the REFERENCE's own front end published (tests/golden/ref_fe_*.npz) ------------
