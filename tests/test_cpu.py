@@ -937,3 +937,27 @@ def test_oracle_pipeline_matches_the_whole_reference_pipeline(tmp_path):
     mav = rr.write_mav(tmp_path, seq)
     w = rr.compare_odometry(rr.run_oracle_pipeline(c.raw, mav), open(os.path.join(sys_path_tests, "ref_main_hybrid_selfstart.txt")).read())
     assert w["n"] >= 60 and w["n_lists"] >= 2 and w["t"] < 1e-9 and max(w["R"], w["p"], w["v"], w["pts"]) < 1e-9, w
+
+
+def test_c_parser_reads_the_reference_own_settings_files(lib_built):
+    """The drop-in reads the reference's OWN files (config/euroc.yaml, config/mynteye.yaml), not only this repo's regrouped copy:
+    lvb_parse_config on them gives the values the stand-in cv::FileStorage of the compiled reference sees (python parser as the
+    cross-check), and euroc.yaml equals configs/euroc_mono.yaml field by field (output_dir aside).  Build container only."""
+    ref_cfg = "/root/reference/config"
+    if not os.path.isdir(ref_cfg):
+        pytest.skip("no /root/reference here")
+    from larvio_b200 import api
+    from larvio_b200.config import Config
+    ours = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml")).to_struct()
+    for fn in ("euroc.yaml", "mynteye.yaml"):
+        path = os.path.join(ref_cfg, fn)
+        c = api.parse_config(path)
+        p = Config.load(path).to_struct()
+        for name, _ in p._fields_:
+            a, b = getattr(c, name), getattr(p, name)
+            assert (list(a) == list(b)) if hasattr(a, "__len__") else (a == b), (fn, name)
+            if fn == "euroc.yaml" and name not in ("output_dir",):
+                o = getattr(ours, name)
+                assert (list(a) == list(o)) if hasattr(a, "__len__") else (a == o), (fn, name, "differs from configs/euroc_mono.yaml")
+    m = api.parse_config(os.path.join(ref_cfg, "mynteye.yaml"))
+    assert m.width == 1280 and m.height == 720 and m.max_features_num == 300 and abs(m.pub_frequency - 20) < 1e-12
