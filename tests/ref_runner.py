@@ -430,8 +430,9 @@ def parse_odometry_lines(text):
     return odo, pts
 
 
-def run_reference_pipeline(cfg_raw, mav_dir):
-    """The reference's main loop on the files of an EuRoC ASL directory (read like the replay tools read them)."""
+def run_reference_pipeline(cfg_raw, mav_dir, with_logs=False):
+    """The reference's main loop on the files of an EuRoC ASL directory (read like the replay tools read them).  with_logs: also
+    return the two files LarVio itself writes into output_dir (larvio.cpp:388, 420-453): msckf_2_state.txt, msckf_2_takeoff.txt."""
     import sys
     from larvio_b200 import euroc
     if not os.path.exists(REF_MAIN_BIN):
@@ -452,7 +453,9 @@ def run_reference_pipeline(cfg_raw, mav_dir):
             raise RuntimeError("larvio_ref_main failed (%d): %s" % (r.returncode, (r.stderr or r.stdout)[-3000:]))
         if os.environ.get("LVB_REF_TRACE"):
             print("\n".join(l for l in r.stderr.splitlines() if l.startswith("FRAME ")))
-    return "\n".join(l for l in r.stdout.splitlines() if l.startswith(("ODO ", "PTS ")))
+        logs = (open(os.path.join(td, "msckf_2_state.txt")).read(), open(os.path.join(td, "msckf_2_takeoff.txt")).read()) if with_logs else None
+    txt = "\n".join(l for l in r.stdout.splitlines() if l.startswith(("ODO ", "PTS ")))
+    return (txt, logs[0], logs[1]) if with_logs else txt
 
 
 def quat_xyzw_to_rot(q):
@@ -479,14 +482,17 @@ def compare_odometry(demo_text, ref_text):
     return w
 
 
-def run_oracle_pipeline(cfg_raw, mav_dir):
-    """oracle/frontend.py + oracle/initializer.py + oracle/backend.py behind the same loop, printing larvio_shim_demo's lines."""
+def run_oracle_pipeline(cfg_raw, mav_dir, with_logs=False):
+    """oracle/frontend.py + oracle/initializer.py + oracle/backend.py behind the same loop, printing larvio_shim_demo's lines.
+    with_logs: also the text of msckf_2_state.txt / msckf_2_takeoff.txt as the PRODUCT's writer (larvio_b200.euroc.state_line, the
+    formatter of TrajectoryLog and of the replay tool's C++ twin) renders the same states."""
     from larvio_b200 import euroc
     from oracle.frontend import ImageProcessorOracle
     from oracle.backend import LarVioOracle
     from oracle.initializer import StaticInitializerOracle
     fe = ImageProcessorOracle(cfg_raw); be = LarVioOracle(cfg_raw); init = StaticInitializerOracle(cfg_raw)
     imu = []; lines = []; pubs = 0; first = False
+    log_lines = []; take_off = None
     for t, img, rows in euroc.Replay(str(mav_dir)):
         imu.extend(rows.tolist())
         msg = fe.process_image(img, t, np.array(imu).reshape(-1, 7))
@@ -504,13 +510,17 @@ def run_oracle_pipeline(cfg_raw, mav_dir):
             be.set_initial_state(o["t"], o["q"], o["p"], o["v"], o["bg"], o["ba"])
             be.m_gyro_old = o["gyro_old"]; be.m_acc_old = o["acc_old"]
             del imu[:o["n_consumed"]]
+            take_off = o["t"]
         if not be.process_features(msg, imu):
             continue
         s = be.imu_state
+        log_lines.append(euroc.state_line(s.time - take_off, s.q, s.v, s.p, s.bg, s.ba, s.R_imu_cam0, s.t_cam0_imu))
         lines.append("ODO %.9f " % t + " ".join("%.17g" % x for x in list(s.q) + list(s.p) + list(s.v)))
         pubs += 1
         if pubs % 10 == 0:
             for tag, m in (("S", be.get_stable_map_points()), ("A", be.get_active_map_points())):
                 if m:
                     lines.append("PTS %s %d " % (tag, len(m)) + " ".join("%d %.17g %.17g %.17g" % (k_, *m[k_]) for k_ in sorted(m)))
+    if with_logs:
+        return "\n".join(lines), "\n".join(log_lines) + "\n", "%.9f\n" % take_off
     return "\n".join(lines)

@@ -935,8 +935,23 @@ def test_oracle_pipeline_matches_the_whole_reference_pipeline(tmp_path):
     c = Config.load(os.path.join(ROOT, "configs", "euroc_mono.yaml"))
     seq = synth.make_sequence(c.raw, g.SPEC["seq"], g.SPEC["frames"], static_until=g.SPEC["static_until"])
     mav = rr.write_mav(tmp_path, seq)
-    w = rr.compare_odometry(rr.run_oracle_pipeline(c.raw, mav), open(os.path.join(sys_path_tests, "ref_main_hybrid_selfstart.txt")).read())
+    otxt, state_log, takeoff_log = rr.run_oracle_pipeline(c.raw, mav, with_logs=True)
+    w = rr.compare_odometry(otxt, open(os.path.join(sys_path_tests, "ref_main_hybrid_selfstart.txt")).read())
     assert w["n"] >= 60 and w["n_lists"] >= 2 and w["t"] < 1e-9 and max(w["R"], w["p"], w["v"], w["pts"]) < 1e-9, w
+    # SURVEY 8(f-4), output side: the file LarVio ITSELF wrote during that run (msckf_2_state.txt, larvio.cpp:420-453: default stream
+    # precision) against the product's writer (euroc.state_line = TrajectoryLog = the replay tool's format) fed with the same states:
+    # same lines, same 24 columns, token for token identical except where a 6-digit rounding boundary falls inside 1e-10
+    ref_lines = open(os.path.join(sys_path_tests, "ref_main_msckf_2_state.txt")).read().split("\n")
+    our_lines = state_log.split("\n")
+    assert len(ref_lines) == len(our_lines) and takeoff_log == open(os.path.join(sys_path_tests, "ref_main_msckf_2_takeoff.txt")).read()
+    same = 0; total = 0
+    for a, b in zip(our_lines, ref_lines):
+        ta, tb = a.split(), b.split()
+        assert len(ta) == len(tb) and (len(tb) == 24 or not b)
+        for x, y in zip(ta, tb):
+            total += 1; same += (x == y)
+            assert abs(float(x) - float(y)) <= 2e-6 * max(abs(float(y)), 1e-4), (x, y)
+    assert total >= 60 * 24 and same >= 0.97 * total, (same, total)
 
 
 def test_c_parser_reads_the_reference_own_settings_files(lib_built):

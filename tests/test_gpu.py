@@ -932,3 +932,28 @@ def test_shim_facade_matches_the_whole_reference_pipeline(tmp_path, lib_built):
     assert r.returncode == 0, r.stderr[-2000:]
     w = rr.compare_odometry(r.stdout, open(os.path.join(ROOT, "tests", "golden", "ref_main_hybrid_selfstart.txt")).read())
     assert w["n"] >= 60 and w["n_lists"] >= 2 and w["t"] < 1e-9 and max(w["R"], w["p"], w["v"]) < 1e-8 and w["pts"] < 1e-7, w
+
+
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU minutes were spent: first GPU run is the driver's")
+def test_replay_tool_writes_the_file_the_reference_writes(tmp_path, lib_built):
+    """SURVEY 8(f-4), both directions of the on-disk formats: larvio_b200/bin/larvio_replay reads the EuRoC ASL directory (PNG + csv)
+    and writes msckf_2_state.txt / msckf_2_takeoff.txt; the reference's own LarVio wrote the same two files while its whole
+    pipeline (oracle/_ref/larvio_ref_main) ran on the same directory (tests/golden/ref_main_msckf_2_state.txt, _takeoff.txt).
+    Same number of lines, same 24 columns, values equal to the 6 significant digits of the format."""
+    import subprocess
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ref_runner as rr
+    from larvio_b200 import synth
+    from larvio_b200.config import Config
+    cfg_path = os.path.join(ROOT, "configs", "euroc_mono.yaml")
+    c = Config.load(cfg_path)
+    seq = synth.make_sequence(c.raw, 3, 150, static_until=1.4)          # tests/golden/make_ref_main_golden.py: SPEC
+    mav = rr.write_mav(tmp_path, seq)
+    exe = os.path.join(ROOT, "larvio_b200", "bin", "larvio_replay")
+    r = subprocess.run([exe, cfg_path, str(tmp_path / "out"), str(mav)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = np.loadtxt(str(tmp_path / "out" / "seq0" / "msckf_2_state.txt"), ndmin=2)
+    ref = np.loadtxt(os.path.join(ROOT, "tests", "golden", "ref_main_msckf_2_state.txt"), ndmin=2)
+    assert got.shape == ref.shape and ref.shape[1] == 24 and ref.shape[0] >= 60
+    assert np.allclose(got, ref, rtol=2e-5, atol=2e-6)
+    assert open(str(tmp_path / "out" / "seq0" / "msckf_2_takeoff.txt")).read().split() == open(os.path.join(ROOT, "tests", "golden", "ref_main_msckf_2_takeoff.txt")).read().split()
