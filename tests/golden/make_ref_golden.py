@@ -22,7 +22,7 @@ import ref_runner as rr                        # noqa: E402
 
 Y = os.path.join(ROOT, "configs", "euroc_mono.yaml")
 # name: (config overrides, sequence id, frames, synth kwargs [+ "freeze": (a, b): images a..b-1 repeat image a, which the filter sees as a
-#        standstill], static initialiser instead of an injected state)
+#        standstill; "jump": (a, b): images a..b-1 show the last image], static initialiser instead of an injected state)
 CASES = {
     "msckf_sw30": (dict(max_features_in_one_grid=0, sw_size=30), 10, 90, {}, False),                       # BASELINE configs[1]/[2]
     "msckf_oldest": (dict(max_features_in_one_grid=0, sw_size=12, translation_threshold=0.02), 2, 60, {}, False),
@@ -36,6 +36,8 @@ CASES = {
     # a standstill in the middle of a hybrid run: checkZUPT drops every SLAM feature from the state (larvio.cpp:2770-2782) and blocks
     # promotions for 5 s; self start
     "hybrid_zupt": (dict(sw_size=16), 26, 176, dict(static_until=1.4, freeze=(150, 166)), True),
+    # the scene jumps during the standstill: the static initialiser restarts its count (StaticInitializer.cpp:46-71) and starts later
+    "self_start_jump": (dict(max_features_in_one_grid=0, sw_size=12), 61, 70, dict(static_until=2.2, jump=(8, 10)), True),
     "schmidt_1d_oldest": (dict(sw_size=12, translation_threshold=0.02, use_schmidt=1), 0, 150, {}, False),
     "schmidt_3d_oldest": (dict(sw_size=12, translation_threshold=0.02, use_schmidt=1, feature_idp_dim=3), 0, 150, {}, False),
 }
@@ -44,10 +46,12 @@ if __name__ == "__main__":
     for name in (sys.argv[1:] or list(CASES)):
         ov, sid, nf, kw, static_init = CASES[name]
         cfg = Config.load(Y, **ov)
-        kw = dict(kw); freeze = kw.pop("freeze", None)
+        kw = dict(kw); freeze = kw.pop("freeze", None); jump = kw.pop("jump", None)
         seq = synth.make_sequence(cfg.raw, sid, nf, **kw)
         if freeze:
             seq.images = seq.images.copy(); seq.images[freeze[0]:freeze[1]] = seq.images[freeze[0]]
+        if jump:                                                   # images jump[0]..jump[1]-1 show the END of the sequence
+            seq.images = seq.images.copy(); seq.images[jump[0]:jump[1]] = seq.images[-1]
         calls = rr.record_calls(cfg.raw, seq, nf)
         j0 = calls[0]["frame"]
         init = None if static_init else (float(seq.img_t[j0]), seq.gt_q[j0], seq.gt_p[j0], seq.gt_v[j0], np.zeros(3), np.zeros(3))

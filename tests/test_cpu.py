@@ -590,7 +590,7 @@ def test_reference_fixture_harness_runs_against_the_mock(monkeypatch, lib_built)
     from mock_batch import MockBatch
     tg = importlib.import_module("test_gpu")
     monkeypatch.setattr(api, "Batch", MockBatch)
-    for name in ("msckf_oldest", "self_start", "hybrid_3d", "config_d", "schmidt_1d_oldest", "hybrid_zupt"):
+    for name in ("msckf_oldest", "self_start", "self_start_jump", "hybrid_3d", "config_d", "schmidt_1d_oldest", "hybrid_zupt"):
         w = tg._drive_fixture(name)
         assert w["n"] >= 18 and max(w["q"], w["p"], w["v"], w["bg"], w["ba"], w["ext"], w["td"], w["Pz"], w["Pdiag"], w["P"], w["calib"]) < 1e-9, (name, w)
     n_pub, bad_ids, worst = tg._drive_fe_fixture("fe_failed_second")           # the front-end fixture harness, same idea
@@ -801,7 +801,7 @@ def test_reference_arm_prints_the_contract_line(tmp_path):
 
 
 # ---- golden vectors produced by the REFERENCE's own filter (tests/golden/ref_*.npz, tests/golden/make_ref_golden.py) -----------------
-REF_CASES_ORACLE = ["msckf_sw30", "msckf_oldest", "hybrid_1d_oldest", "hybrid_3d", "config_d", "zupt", "self_start", "no_fej_no_calib", "calib_3d", "hybrid_zupt", "schmidt_1d_oldest",
+REF_CASES_ORACLE = ["msckf_sw30", "msckf_oldest", "hybrid_1d_oldest", "hybrid_3d", "config_d", "zupt", "self_start", "self_start_jump", "no_fej_no_calib", "calib_3d", "hybrid_zupt", "schmidt_1d_oldest",
                     "schmidt_3d_oldest"]
 
 
