@@ -203,7 +203,7 @@ def cpu_arm_description(cfg_raw):
     """What the CPU arm runs (cpu_baseline.sample): the oracle with its compiled pieces switched on."""
     from oracle import backend_c
     if backend_c.supported(cfg_raw):
-        return "cv2 4.13 C++ for the OpenCV calls + compiled ORB (oracle/orb_c.cpp) + compiled filter (oracle/backend_c.cpp, g++ -O3, pinned to the numpy oracle to 1e-9), Python glue"
+        return "cv2 4.13 C++ for the OpenCV calls + compiled ORB (oracle/orb_c.cpp) + compiled filter (oracle/backend_c.cpp, g++ -O3, pinned to golden vectors of the reference's own larvio.cpp and to the numpy oracle to 1e-9), Python glue"
     return "cv2 4.13 C++ for the OpenCV calls + compiled ORB (oracle/orb_c.cpp) + numpy f64 filter (oracle/backend.py: the compiled filter covers pure MSCKF only), Python glue"
 
 

@@ -42,6 +42,7 @@ def load():
         L.lvo_get_state.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.lvo_dim.argtypes = [ctypes.c_void_p]
         L.lvo_get_cov.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.lvo_get_slam.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.lvo_counter.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.lvo_counter.restype = ctypes.c_longlong
         _lib = L
@@ -49,8 +50,11 @@ def load():
 
 
 def supported(r: dict) -> bool:
+    """pure MSCKF, or the hybrid filter with 1-D inverse-depth SLAM features; no IMU-intrinsic calibration, no Schmidt nuisance states"""
     hybrid = max(int(r["max_features_in_one_grid"]), 0) * int(r["aug_grid_rows"]) * int(r["aug_grid_cols"]) != 0
-    return not hybrid and not int(r["calib_imu_instrinsic"])
+    if int(r["calib_imu_instrinsic"]):
+        return False
+    return not hybrid or (int(r.get("feature_idp_dim", 3)) == 1 and not int(r.get("use_schmidt", 0)))
 
 
 def _cfg_vector(r: dict) -> np.ndarray:
@@ -67,13 +71,22 @@ def _cfg_vector(r: dict) -> np.ndarray:
     v = [float(x) for x in v]
     v += [float(x) for x in np.array(r["T_cam_imu"]["data"], np.float64).reshape(16)]
     v += [0.0] + [float(chi2.ppf(0.05, i)) for i in range(1, 100)]          # boost chi_squared quantile(0.05) (larvio.cpp:353-357)
+    # hybrid filter: features per cell, grid, boundary of the normalised image plane (larvio.cpp:226-268)
+    it = r["intrinsics"]
+    fx, fy, cx, cy = float(it["fx"]), float(it["fy"]), float(it["cx"]), float(it["cy"])
+    U, V = int(r["resolution_width"]), int(r["resolution_height"])
+    x_min, y_min, x_max, y_max = -cx / fx, -cy / fy, (U - cx) / fx, (V - cy) / fy
+    rows, cols = int(r["aug_grid_rows"]), int(r["aug_grid_cols"])
+    gw = (x_max - x_min) / cols if rows * cols != 0 else (x_max - x_min)
+    gh = (y_max - y_min) / rows if rows * cols != 0 else (y_max - y_min)
+    v += [float(max(int(r["max_features_in_one_grid"]), 0)), float(rows), float(cols), x_min, y_min, gw, gh]
     return np.array(v, np.float64)
 
 
 class LarVioOracleC:
     def __init__(self, cfg_raw: dict):
         if not supported(cfg_raw):
-            raise NotImplementedError("the compiled oracle covers pure MSCKF without IMU-intrinsic calibration")
+            raise NotImplementedError("the compiled oracle covers pure MSCKF and 1-D inverse-depth hybrid filters without IMU-intrinsic calibration")
         self.L = load()
         vec = _cfg_vector(cfg_raw)
         assert len(vec) == self.L.lvo_cfg_doubles()
@@ -128,6 +141,12 @@ class LarVioOracleC:
         out = np.zeros((d, d))
         self.L.lvo_get_cov(self.h, out.ctypes.data)
         return out
+
+    @property
+    def feature_states(self):
+        ids = np.zeros(64, np.int64)
+        n = self.L.lvo_get_slam(self.h, ids.ctypes.data, 64)
+        return [int(x) for x in ids[:n]]
 
     def counter(self, which):          # 0 updates, 1 ZUPT events, 2 features in the map
         return int(self.L.lvo_counter(self.h, which))

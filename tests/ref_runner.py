@@ -103,12 +103,16 @@ def record_calls(cfg_raw, seq, n_frames):
     return calls
 
 
-def run_oracle_on_calls(cfg_raw, calls, init=None, static_init=False):
-    """oracle/backend.py over recorded calls.  init = (t, q, p, v, bg, ba) forces the initial state before the first call;
-    static_init=True uses oracle/initializer.py the way tests/oracle_runner.py does for self-starting runs."""
-    from oracle.backend import LarVioOracle
+def run_oracle_on_calls(cfg_raw, calls, init=None, static_init=False, compiled=False):
+    """oracle/backend.py (compiled=True: oracle/backend_c.cpp) over recorded calls.  init = (t, q, p, v, bg, ba) forces the initial
+    state before the first call; static_init=True uses oracle/initializer.py the way tests/oracle_runner.py does for self-starting runs."""
     from oracle.frontend import FeatureMsg
-    be = LarVioOracle(cfg_raw)
+    if compiled:
+        from oracle.backend_c import LarVioOracleC
+        be = LarVioOracleC(cfg_raw); be.bFirstFeatures = False
+    else:
+        from oracle.backend import LarVioOracle
+        be = LarVioOracle(cfg_raw)
     si = None
     if static_init:
         from oracle.initializer import StaticInitializerOracle
@@ -139,10 +143,13 @@ def run_oracle_on_calls(cfg_raw, calls, init=None, static_init=False):
             s = be.imu_state
             rec.update(t=s.time, q=s.q.copy(), p=s.p.copy(), v=s.v.copy(), bg=s.bg.copy(), ba=s.ba.copy(),
                        R_imu_cam0=s.R_imu_cam0.copy(), t_cam0_imu=s.t_cam0_imu.copy(), td=float(be.td), P=be.P.copy(),
-                       n_win=len(be.aug), slam_ids=[int(i) for i in be.feature_states], n_imu_left=len(imu),
-                       win_ids=sorted(int(i) for i in be.aug), nui_ids=[int(i) for i in getattr(be, "nui_ids", [])],
-                       stable={int(k_): np.array(v_) for k_, v_ in be.get_stable_map_points().items()},       # both getters clear what
-                       active={int(k_): np.array(v_) for k_, v_ in be.get_active_map_points().items()})       # they return (larvio.cpp:2719-2733)
+                       slam_ids=[int(i) for i in be.feature_states], n_imu_left=len(imu))
+            if compiled:
+                rec.update(n_win=be.n_window)
+            else:
+                rec.update(n_win=len(be.aug), win_ids=sorted(int(i) for i in be.aug), nui_ids=[int(i) for i in getattr(be, "nui_ids", [])],
+                           stable={int(k_): np.array(v_) for k_, v_ in be.get_stable_map_points().items()},   # both getters clear what
+                           active={int(k_): np.array(v_) for k_, v_ in be.get_active_map_points().items()})   # they return (larvio.cpp:2719-2733)
         out.append(rec)
     return out
 

@@ -781,7 +781,9 @@ def test_bench_helpers_core_count_and_ncu_traffic():
     assert src and src.startswith("profiles/") and src.endswith("_ncu_traffic.json")
     assert traffic["lk_kernel"] > 0 and "be_propagate_kernel" in traffic and all("<" not in k and not k.startswith("void ") for k in traffic)
     assert "compiled filter" in b.cpu_arm_description(dict(max_features_in_one_grid=0, aug_grid_rows=5, aug_grid_cols=6, calib_imu_instrinsic=0))
-    assert "numpy f64 filter" in b.cpu_arm_description(dict(max_features_in_one_grid=1, aug_grid_rows=5, aug_grid_cols=6, calib_imu_instrinsic=0))
+    assert "compiled filter" in b.cpu_arm_description(dict(max_features_in_one_grid=1, aug_grid_rows=5, aug_grid_cols=6, calib_imu_instrinsic=0, feature_idp_dim=1, use_schmidt=0))
+    assert "numpy f64 filter" in b.cpu_arm_description(dict(max_features_in_one_grid=1, aug_grid_rows=5, aug_grid_cols=6, calib_imu_instrinsic=0, feature_idp_dim=3))
+    assert "numpy f64 filter" in b.cpu_arm_description(dict(max_features_in_one_grid=1, aug_grid_rows=5, aug_grid_cols=6, calib_imu_instrinsic=1, feature_idp_dim=1))
 
 
 def test_reference_arm_prints_the_contract_line(tmp_path):
@@ -831,27 +833,14 @@ def test_backend_oracle_matches_the_compiled_reference(name):
     assert max(w["Pz"], w["Pdiag"], w["P"]) < 1e-9, w
 
 
-@pytest.mark.parametrize("name", ["msckf_sw30", "msckf_oldest", "zupt"])
+@pytest.mark.parametrize("name", ["msckf_sw30", "msckf_oldest", "zupt", "self_start", "self_start_jump", "no_fej_no_calib", "hybrid_1d_oldest", "hybrid_zupt"])
 def test_compiled_oracle_matches_the_compiled_reference(name):
-    """oracle/backend_c.cpp (the CPU arm of bench.py) against the same reference-made fixtures, in its scope (pure MSCKF)."""
+    """oracle/backend_c.cpp (the CPU arm of bench.py) against the same reference-made fixtures, in its scope: pure MSCKF and the
+    hybrid filter with 1-D inverse-depth SLAM features (promotion, anchor hand-over, the standstill that drops them), forced and
+    self start.  Identical bookkeeping incl. the SLAM feature ids in the state; state and covariance within 1e-9."""
     import ref_runner as rr
-    from oracle.backend_c import LarVioOracleC
-    from oracle.frontend import FeatureMsg
     c, init, static_init, calls, ref = _fixture(name)
-    be = LarVioOracleC(c.raw); imu = []; run = []
-    for cl in calls:
-        imu.extend(cl["imu"].tolist())
-        msg = FeatureMsg(cl["t"]); msg.ids = cl["ids"]; msg.data = cl["data"]
-        if not be.is_gravity_set:
-            be.set_initial_state(*init)
-        ok = be.process_features(msg, imu)
-        rec = dict(ok=bool(ok))
-        if ok:
-            s = be.imu_state
-            rec.update(q=s.q.copy(), p=s.p.copy(), v=s.v.copy(), bg=s.bg.copy(), ba=s.ba.copy(), R_imu_cam0=s.R_imu_cam0.copy(),
-                       t_cam0_imu=s.t_cam0_imu.copy(), td=float(be.td), P=be.P.copy(), n_win=be.n_window, n_imu_left=len(imu))
-        run.append(rec)
-    w = rr.compare_with_fixture(run, ref)
+    w = rr.compare_with_fixture(rr.run_oracle_on_calls(c.raw, calls, init, static_init, compiled=True), ref)
     assert w["n"] >= 18 and max(w["q"], w["p"], w["v"], w["bg"], w["ba"], w["ext"], w["td"], w["Pz"], w["Pdiag"], w["P"]) < 1e-9, w
 
 
