@@ -1,13 +1,13 @@
 // CPU oracle of LarVio::processFeatures, compiled (TEST INFRASTRUCTURE - see oracle/__init__.py: only tests/, smoke() and
 // bench.py's CPU legs may load this; the product never does).
 //
-// C++17, dense loops, no Eigen: the same restatement of /root/reference/src/larvio.cpp as oracle/backend.py, restricted to LEG_DIM 22
-// (no IMU-intrinsic calibration): pure MSCKF (max_features_in_one_grid: 0, the configuration BASELINE.json's metric is quoted on) and
+// C++17, dense loops, no Eigen: the same restatement of /root/reference/src/larvio.cpp as oracle/backend.py, LEG_DIM 22 or 46
+// (IMU-intrinsic calibration): pure MSCKF (max_features_in_one_grid: 0, the configuration BASELINE.json's metric is quoted on) and
 // the hybrid filter with 1-D inverse-depth EKF-SLAM features (promotion rule with the grid map, featureJacobian_ekf / _ekf_new,
 // measurementUpdate_hybrid, anchor hand-over with updateFeatureCov_1didp, the standstill that drops them), with FEJ, online
 // extrinsics / td and ZUPT.  It exists so that the CPU arm of bench.py times compiled code, as the reference is compiled code
 // (VERDICT r1 item 6).  Pinned to golden vectors produced by the reference's OWN larvio.cpp (tests/golden/ref_*.npz,
-// tests/test_cpu.py::test_compiled_oracle_matches_the_compiled_reference: 8 cases, <= 1e-9) and to oracle/backend.py
+// tests/test_cpu.py::test_compiled_oracle_matches_the_compiled_reference: 9 cases, <= 1e-9) and to oracle/backend.py
 // (test_compiled_backend_matches_the_numpy_oracle).
 //
 // processFeatures :363-461, batchImuProcessing :464-517, processModel :520-578, predictNewState :581-649, calPhi :3475-3530,
@@ -119,7 +119,6 @@ struct Feature {
 };
 
 const V3 GRAV = {0.0, 0.0, -9.81};
-constexpr int LEG = 22;
 
 struct Cfg {               // order = the vector oracle/backend_c.py passes
   double imu_rate, rotation_threshold, translation_threshold, tracking_rate_threshold, feature_translation_threshold, td;
@@ -130,10 +129,14 @@ struct Cfg {               // order = the vector oracle/backend_c.py passes
   double T_cam_imu[16];
   double chi2[100];
   double max_features, grid_rows, grid_cols, x_min, y_min, grid_w, grid_h;     // larvio.cpp:226-268 (0 features per cell = pure MSCKF)
+  double calib_imu;                                                            // calib_imu_instrinsic: LEG_DIM 46 (:158-161)
 };
 
 struct Filter {
   Cfg c;
+  int LEG;                                   // legacy error-state size: 22, or 46 with the 24 IMU-intrinsic states T1 T2 T3 A1 A2 A3 M1 M2
+  M3 Tg = eye3(), As = {{0, 0, 0, 0, 0, 0, 0, 0, 0}}, Ma = eye3();   // larvio.cpp:129-131
+  double intr[24] = {0, 0, 0, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1};
   double th, sg2, sa2, sbg2, sba2, sfeat2, td;
   ImuS s, imu_old, fej_now, fej_old;
   Mat P;
@@ -153,7 +156,9 @@ struct Filter {
     th = 1.0 / (2.0 * c.imu_rate);
     sg2 = c.noise_gyro * c.noise_gyro; sa2 = c.noise_acc * c.noise_acc; sbg2 = c.noise_gyro_bias * c.noise_gyro_bias;
     sba2 = c.noise_acc_bias * c.noise_acc_bias; sfeat2 = c.noise_feature * c.noise_feature; td = c.td;
+    LEG = c.calib_imu != 0 ? 46 : 22;
     P = Mat(LEG, LEG);
+    for (int i = 22; i < LEG; ++i) P(i, i) = 1e-4;                               // :183-186
     for (int i = 0; i < 3; ++i) {
       P(i, i) = c.cov_ori; P(3 + i, 3 + i) = c.cov_vel; P(6 + i, 6 + i) = c.cov_pos; P(9 + i, 9 + i) = c.cov_bg; P(12 + i, 12 + i) = c.cov_ba;
       if (c.estimate_extrin != 0) { P(15 + i, 15 + i) = c.cov_er; P(18 + i, 18 + i) = c.cov_et; }
@@ -204,61 +209,101 @@ struct Filter {
     fej_now = s;
   }
 
-  // ---------------------------------------------------------------- :520-578 with calPhi :3475-3530 (Ma = Tg = I, As = 0)
+  // ---------------------------------------------------------------- :520-578 with calPhi :3475-3530 and its IMU-intrinsic columns :3532-3797
   void process_model(double time, V3 m_gyro, V3 m_acc) {
-    const V3 f = m_acc - ld(s.ba), acc = f;
-    const V3 w = m_gyro - ld(s.bg), gyro = w;
-    const V3 w_old = ld(g_old) - ld(s.bg), gyro_old = w_old;
+    const V3 f = m_acc - ld(s.ba), acc = mv(Ma, f);
+    const V3 w = m_gyro - mv(As, acc) - ld(s.bg), gyro = mv(Tg, w);
+    const V3 f_old = ld(a_old) - ld(s.ba), acc_old = mv(Ma, f_old);
+    const V3 w_old = ld(g_old) - mv(As, acc_old) - ld(s.bg), gyro_old = mv(Tg, w_old);
     const double dtime = time - s.time;
     predict_new_state(dtime, gyro, acc);
     const V3 axis = (gyro_old + gyro) * (dtime / 2) + cross(gyro_old, gyro) * (dtime * dtime / 12);
     const M3 Ah = skew(axis);
     const M3 C = quat_to_rot(imu_old.q);
     const M3 I3 = eye3();
+    const M3 TA = mul(Tg, As);
     V3 vk, pk, vk1, pk1;
     if (if_FEJ) { vk = ld(fej_old.v); pk = ld(fej_old.p); vk1 = ld(fej_now.v); pk1 = ld(fej_now.p); }
     else { vk = ld(imu_old.v); pk = ld(imu_old.p); vk1 = ld(s.v); pk1 = ld(s.p); }
     const V3 g = GRAV;
-    double Phi[LEG][LEG];
-    for (int i = 0; i < LEG; ++i) for (int j = 0; j < LEG; ++j) Phi[i][j] = (i == j) ? 1.0 : 0.0;
-    auto put = [&](int r0, int c0, const M3& B) { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Phi[r0 + i][c0 + j] = B.m[i * 3 + j]; };
+    const int L = LEG;
+    Mat Phi(L, L);
+    for (int i = 0; i < L; ++i) Phi(i, i) = 1.0;
+    auto put = [&](int r0, int c0, const M3& B) { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Phi(r0 + i, c0 + j) = B.m[i * 3 + j]; };
     const M3 CA2 = mul(C, add(scl(I3, 2.0), Ah));
-    put(0, 9, scl(CA2, -0.5 * dtime));
-    put(0, 12, scl(I3, 0.0));                                                     // ... @ (Tg As) @ Ma = 0
+    put(0, 9, mul(scl(CA2, -0.5 * dtime), Tg));
+    put(0, 12, mul(mul(scl(CA2, 0.5 * dtime), TA), Ma));
     put(3, 0, scl(skew(vk1 - vk - g * dtime), -1.0));
     const M3 P39 = add(mul(skew(pk * 1.0 - pk1 + vk1 * dtime - g * (0.5 * dtime * dtime)), C),
                        mul(mul(skew(pk * 0.5 - pk1 * 0.5 + vk1 * (0.5 * dtime) - g * (dtime * dtime / 6)), C), Ah));
     put(3, 9, P39);
-    put(3, 12, scl(CA2, -0.5 * dtime));
+    put(3, 12, sub(mul(scl(CA2, -0.5 * dtime), Ma), mul(mul(P39, TA), Ma)));
     put(6, 0, scl(skew(pk1 - pk - vk * dtime - g * (0.5 * dtime * dtime)), -1.0));
     put(6, 3, scl(I3, dtime));
     const M3 P69 = add(scl(mul(skew(g), C), -dtime * dtime * dtime / 6), scl(mul(mul(skew(pk1 - pk - g * (dtime * dtime / 6)), C), Ah), dtime / 4));
     put(6, 9, P69);
-    put(6, 12, scl(mul(C, add(scl(I3, 3.0), Ah)), -dtime * dtime / 6));
+    put(6, 12, sub(mul(scl(mul(C, add(scl(I3, 3.0), Ah)), -dtime * dtime / 6), Ma), mul(mul(P69, TA), Ma)));
+    if (L > 22) {
+      // selectors of a 3-vector x: Lo (1,0)=x0 (2,1)=x0 (2,2)=x1 ; Di = diag(x) ; Up (0,0)=x1 (0,1)=x2 (1,2)=x2   (:3532-3797)
+      auto Lo = [](V3 x) { M3 m = {{0, 0, 0, 0, 0, 0, 0, 0, 0}}; m.m[3] = x.x; m.m[7] = x.x; m.m[8] = x.y; return m; };
+      auto Di = [](V3 x) { M3 m = {{0, 0, 0, 0, 0, 0, 0, 0, 0}}; m.m[0] = x.x; m.m[4] = x.y; m.m[8] = x.z; return m; };
+      auto Up = [](V3 x) { M3 m = {{0, 0, 0, 0, 0, 0, 0, 0, 0}}; m.m[0] = x.y; m.m[1] = x.z; m.m[5] = x.z; return m; };
+      const V3 f_mid = (f + f_old) * 0.5, acc_mid = (acc + acc_old) * 0.5;
+      const V3 w_mid = (w_old + w) * 0.5 + cross(w_old, w) * (dtime / 12);
+      const M3 R_mid = add(I3, scl(Ah, 0.5)), R_kp1 = add(I3, Ah);
+      const M3 S_mid = skew(mv(R_mid, acc_mid)), S_kp1 = skew(mv(R_kp1, acc));
+      const M3 Z3 = {{0, 0, 0, 0, 0, 0, 0, 0, 0}};
+      for (int grp = 0; grp < 8; ++grp) {
+        const int col = 22 + 3 * grp;
+        const int which = grp % 3;                                   // 0 Lo, 1 Di, 2 Up (the last group pair is Lo, Di)
+        const int fam = grp / 3;                                     // 0: T (w), 1: A (acc), 2: M (f)
+        V3 xk, xh, xp; M3 Lf; double sgn; bool direct;
+        if (fam == 0) { xk = w_old; xh = w_mid; xp = w; Lf = I3; sgn = 1; direct = false; }
+        else if (fam == 1) { xk = acc_old; xh = acc_mid; xp = acc; Lf = Tg; sgn = -1; direct = false; }
+        else { xk = f_old; xh = f_mid; xp = f; Lf = TA; sgn = -1; direct = true; }
+        auto sel = [&](V3 x) { return which == 0 ? Lo(x) : which == 1 ? Di(x) : Up(x); };
+        const M3 kq1 = mul(Lf, sel(xk)), kq2 = mul(R_mid, mul(Lf, sel(xh))), kq4 = mul(R_kp1, mul(Lf, sel(xp)));
+        const M3 Rq = scl(add(add(kq1, scl(kq2, 4.0)), kq4), dtime / 6);
+        put(0, col, scl(mul(C, Rq), sgn));
+        M3 kv1, kv2, kv3, kv4;
+        if (!direct) {
+          kv1 = Z3; kv2 = scl(mul(scl(S_mid, dtime), kq1), 0.5); kv3 = scl(mul(scl(S_mid, dtime), kq2), 0.5); kv4 = mul(S_kp1, Rq);
+        } else {
+          kv1 = sel(xk);
+          kv2 = add(mul(R_mid, sel(xh)), scl(mul(scl(S_mid, dtime), kq1), 0.5));
+          kv3 = add(mul(R_mid, sel(xh)), scl(mul(scl(S_mid, dtime), kq2), 0.5));
+          kv4 = add(mul(R_kp1, sel(xp)), mul(S_kp1, Rq));
+        }
+        const M3 fR = scl(add(add(kv1, scl(kv2, 2.0)), add(scl(kv3, 2.0), kv4)), dtime / 6);
+        const double vs = direct ? 1.0 : -sgn;                       // Phi_v: -C f for T, +C f for A, +C v for M
+        put(3, col, scl(mul(C, fR), vs));
+        const M3 kp2 = scl(kv1, dtime / 2), kp3 = scl(kv2, dtime / 2);
+        put(6, col, scl(mul(C, scl(add(add(scl(kp2, 2.0), scl(kp3, 2.0)), fR), dtime / 6)), vs));
+      }
+    }
     // Q = Phi G Qc G^T Phi^T dt, G Qc G^T = blkdiag(sg2 C C^T, sa2 C C^T, 0, sbg2 I, sba2 I, 0)
     const M3 CCt = mul(C, tr(C));
-    double M[LEG][LEG];
-    for (int i = 0; i < LEG; ++i) for (int j = 0; j < LEG; ++j) M[i][j] = 0.0;
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { M[i][j] = sg2 * CCt.m[i * 3 + j]; M[3 + i][3 + j] = sa2 * CCt.m[i * 3 + j]; }
-    for (int i = 0; i < 3; ++i) { M[9 + i][9 + i] = sbg2; M[12 + i][12 + i] = sba2; }
-    double PM[LEG][LEG], Q[LEG][LEG];
-    for (int i = 0; i < LEG; ++i) for (int j = 0; j < LEG; ++j) { double a_ = 0; for (int k = 0; k < 15; ++k) a_ += Phi[i][k] * M[k][j]; PM[i][j] = a_; }
-    for (int i = 0; i < LEG; ++i) for (int j = 0; j < LEG; ++j) { double a_ = 0; for (int k = 0; k < 15; ++k) a_ += PM[i][k] * Phi[j][k]; Q[i][j] = a_ * dtime; }
+    Mat M(15, 15);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { M(i, j) = sg2 * CCt.m[i * 3 + j]; M(3 + i, 3 + j) = sa2 * CCt.m[i * 3 + j]; }
+    for (int i = 0; i < 3; ++i) { M(9 + i, 9 + i) = sbg2; M(12 + i, 12 + i) = sba2; }
+    Mat PM(L, 15), Q(L, L);
+    for (int i = 0; i < L; ++i) for (int j = 0; j < 15; ++j) { double a_ = 0; for (int k = 0; k < 15; ++k) a_ += Phi(i, k) * M(k, j); PM(i, j) = a_; }
+    for (int i = 0; i < L; ++i) for (int j = 0; j < L; ++j) { double a_ = 0; for (int k = 0; k < 15; ++k) a_ += PM(i, k) * Phi(j, k); Q(i, j) = a_ * dtime; }
     // P[:L,:L] = Phi P Phi^T + Q ; P[:L,L:] = Phi P[:L,L:] ; P[L:,:L] = transpose ; P = (P + P^T)/2
     const int d = P.r;
-    std::vector<double> top((size_t)LEG * d);
-    for (int i = 0; i < LEG; ++i) {
+    std::vector<double> top((size_t)L * d);
+    for (int i = 0; i < L; ++i) {
       double* o = top.data() + (size_t)i * d;
       for (int j = 0; j < d; ++j) o[j] = 0.0;
-      for (int k = 0; k < LEG; ++k) { const double ph = Phi[i][k]; if (ph == 0.0) continue; const double* pr = P.row(k); for (int j = 0; j < d; ++j) o[j] += ph * pr[j]; }
+      for (int k = 0; k < L; ++k) { const double ph = Phi(i, k); if (ph == 0.0) continue; const double* pr = P.row(k); for (int j = 0; j < d; ++j) o[j] += ph * pr[j]; }
     }
-    double LL[LEG][LEG];
-    for (int i = 0; i < LEG; ++i) for (int j = 0; j < LEG; ++j) { double a_ = 0; for (int k = 0; k < LEG; ++k) a_ += top[(size_t)i * d + k] * Phi[j][k]; LL[i][j] = a_ + Q[i][j]; }
-    for (int i = 0; i < LEG; ++i) {
-      for (int j = 0; j < LEG; ++j) P(i, j) = LL[i][j];
-      for (int j = LEG; j < d; ++j) { P(i, j) = top[(size_t)i * d + j]; P(j, i) = top[(size_t)i * d + j]; }
+    Mat LL(L, L);
+    for (int i = 0; i < L; ++i) for (int j = 0; j < L; ++j) { double a_ = 0; for (int k = 0; k < L; ++k) a_ += top[(size_t)i * d + k] * Phi(j, k); LL(i, j) = a_ + Q(i, j); }
+    for (int i = 0; i < L; ++i) {
+      for (int j = 0; j < L; ++j) P(i, j) = LL(i, j);
+      for (int j = L; j < d; ++j) { P(i, j) = top[(size_t)i * d + j]; P(j, i) = top[(size_t)i * d + j]; }
     }
-    for (int i = 0; i < LEG; ++i) for (int j = i + 1; j < LEG; ++j) { const double m_ = 0.5 * (P(i, j) + P(j, i)); P(i, j) = m_; P(j, i) = m_; }
+    for (int i = 0; i < L; ++i) for (int j = i + 1; j < L; ++j) { const double m_ = 0.5 * (P(i, j) + P(j, i)); P(i, j) = m_; P(j, i) = m_; }
     s.time = time; fej_now.time = time;
   }
 
@@ -359,6 +404,14 @@ struct Filter {
     s.R_ic = mul(s.R_ic, tr(quat_to_rot(dq)));
     for (int i = 0; i < 3; ++i) s.t_ci[i] += dx[18 + i];
     td += dx[21];
+    if (LEG > 22) {                                   // T1 T2 T3 A1 A2 A3 M1 M2 += dx(22:46), then updateImuMx (:1497-1507, 3803-3847)
+      for (int k = 0; k < 24; ++k) intr[k] += dx[22 + k];
+      const double* T1 = intr; const double* T2 = intr + 3; const double* T3 = intr + 6; const double* A1 = intr + 9; const double* A2 = intr + 12;
+      const double* A3 = intr + 15; const double* M1 = intr + 18; const double* M2 = intr + 21;
+      Tg = {{T2[0], T3[0], T3[1], T1[0], T2[1], T3[2], T1[1], T1[2], T2[2]}};
+      As = {{A2[0], A3[0], A3[1], A1[0], A2[1], A3[2], A1[1], A1[2], A2[2]}};
+      Ma.m[0] = M2[0]; Ma.m[3] = M1[0]; Ma.m[4] = M2[1]; Ma.m[6] = M1[1]; Ma.m[7] = M1[2]; Ma.m[8] = M2[2];   // the upper triangle is never written (:3839-3844)
+    }
     int i = 0;
     for (auto& kv : aug) {
       Aug& a = kv.second;
