@@ -50,10 +50,10 @@ def load():
 
 
 def supported(r: dict) -> bool:
-    """pure MSCKF, or the hybrid filter with 1-D inverse-depth SLAM features, with or without IMU-intrinsic calibration; no 3-D
-    features, no Schmidt nuisance states"""
+    """pure MSCKF, or the hybrid filter with 1-D inverse-depth SLAM features, with or without IMU-intrinsic calibration and Schmidt
+    nuisance states; no 3-D features"""
     hybrid = max(int(r["max_features_in_one_grid"]), 0) * int(r["aug_grid_rows"]) * int(r["aug_grid_cols"]) != 0
-    return not hybrid or (int(r.get("feature_idp_dim", 3)) == 1 and not int(r.get("use_schmidt", 0)))
+    return not hybrid or int(r.get("feature_idp_dim", 3)) == 1
 
 
 def _cfg_vector(r: dict) -> np.ndarray:
@@ -79,14 +79,14 @@ def _cfg_vector(r: dict) -> np.ndarray:
     gw = (x_max - x_min) / cols if rows * cols != 0 else (x_max - x_min)
     gh = (y_max - y_min) / rows if rows * cols != 0 else (y_max - y_min)
     v += [float(max(int(r["max_features_in_one_grid"]), 0)), float(rows), float(cols), x_min, y_min, gw, gh]
-    v += [float(int(r["calib_imu_instrinsic"]))]
+    v += [float(int(r["calib_imu_instrinsic"])), float(int(r.get("use_schmidt", 0)))]
     return np.array(v, np.float64)
 
 
 class LarVioOracleC:
     def __init__(self, cfg_raw: dict):
         if not supported(cfg_raw):
-            raise NotImplementedError("the compiled oracle covers pure MSCKF and 1-D inverse-depth hybrid filters (no 3-D features, no Schmidt)")
+            raise NotImplementedError("the compiled oracle covers pure MSCKF and 1-D inverse-depth hybrid filters (no 3-D features)")
         self.L = load()
         vec = _cfg_vector(cfg_raw)
         assert len(vec) == self.L.lvo_cfg_doubles()
