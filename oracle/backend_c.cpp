@@ -1,14 +1,14 @@
 // CPU oracle of LarVio::processFeatures, compiled (TEST INFRASTRUCTURE - see oracle/__init__.py: only tests/, smoke() and
 // bench.py's CPU legs may load this; the product never does).
 //
-// C++17, dense loops, no Eigen: the same restatement of /root/reference/src/larvio.cpp as oracle/backend.py, LEG_DIM 22 or 46
-// (IMU-intrinsic calibration): pure MSCKF (max_features_in_one_grid: 0, the configuration BASELINE.json's metric is quoted on) and
-// the hybrid filter with 1-D inverse-depth EKF-SLAM features (promotion rule with the grid map, featureJacobian_ekf / _ekf_new,
-// measurementUpdate_hybrid, anchor hand-over with updateFeatureCov_1didp, the standstill that drops them, Schmidt nuisance states), with FEJ, online
-// extrinsics / td and ZUPT.  It exists so that the CPU arm of bench.py times compiled code, as the reference is compiled code
-// (VERDICT r1 item 6).  Pinned to golden vectors produced by the reference's OWN larvio.cpp (tests/golden/ref_*.npz,
-// tests/test_cpu.py::test_compiled_oracle_matches_the_compiled_reference: 10 cases, <= 1e-9) and to oracle/backend.py
-// (test_compiled_backend_matches_the_numpy_oracle).
+// C++17, dense loops, no Eigen: the same restatement of /root/reference/src/larvio.cpp as oracle/backend.py, for every configuration of the
+// filter: LEG_DIM 22 or 46 (IMU-intrinsic calibration), pure MSCKF (max_features_in_one_grid: 0, the configuration BASELINE.json's metric is
+// quoted on) and the hybrid filter with 1-D or 3-D inverse-depth EKF-SLAM features (promotion rule with the grid map, featureJacobian_ekf /
+// _ekf_new, measurementUpdate_hybrid, anchor hand-over with updateFeatureCov_1didp / _3didp, the standstill that drops them, Schmidt
+// nuisance states), with FEJ, online extrinsics / td and ZUPT.  It exists so that the CPU arm of bench.py times compiled code, as the
+// reference is compiled code.  Pinned to golden vectors produced by the reference's OWN larvio.cpp
+// (tests/golden/ref_*.npz, tests/test_cpu.py::test_compiled_oracle_matches_the_compiled_reference: all 13 fixtures, <= 1e-9) and to
+// oracle/backend.py (test_compiled_backend_matches_the_numpy_oracle).
 //
 // processFeatures :363-461, batchImuProcessing :464-517, processModel :520-578, predictNewState :581-649, calPhi :3475-3530,
 // stateAugmentation :720-801, addFeatureObservations :804-856, measurementJacobian_msckf :859-921, featureJacobian_msckf
@@ -116,6 +116,7 @@ struct Feature {
   // corrected bearing in the anchor camera
   bool in_state = false, ekf = false;
   double inv_depth = 0.0, obs_anchor[3] = {0, 0, 1};
+  double inv_param[3] = {0, 0, 0};           // 3-D inverse depth: (x/z, y/z, 1/z) in the anchor camera (feature.hpp:231)
 };
 
 const V3 GRAV = {0.0, 0.0, -9.81};
@@ -131,10 +132,12 @@ struct Cfg {               // order = the vector oracle/backend_c.py passes
   double max_features, grid_rows, grid_cols, x_min, y_min, grid_w, grid_h;     // larvio.cpp:226-268 (0 features per cell = pure MSCKF)
   double calib_imu;                                                            // calib_imu_instrinsic: LEG_DIM 46 (:158-161)
   double use_schmidt;                                                          // :277
+  double feature_idp_dim;                                                      // 1, anything else means 3 (:270-274)
 };
 
 struct Filter {
   Cfg c;
+  int idp = 1;                               // state columns per SLAM feature
   int LEG;                                   // legacy error-state size: 22, or 46 with the 24 IMU-intrinsic states T1 T2 T3 A1 A2 A3 M1 M2
   M3 Tg = eye3(), As = {{0, 0, 0, 0, 0, 0, 0, 0, 0}}, Ma = eye3();   // larvio.cpp:129-131
   double intr[24] = {0, 0, 0, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1};
@@ -163,6 +166,7 @@ struct Filter {
     sg2 = c.noise_gyro * c.noise_gyro; sa2 = c.noise_acc * c.noise_acc; sbg2 = c.noise_gyro_bias * c.noise_gyro_bias;
     sba2 = c.noise_acc_bias * c.noise_acc_bias; sfeat2 = c.noise_feature * c.noise_feature; td = c.td;
     LEG = c.calib_imu != 0 ? 46 : 22;
+    idp = (c.feature_idp_dim == 1) ? 1 : 3;
     P = Mat(LEG, LEG);
     for (int i = 22; i < LEG; ++i) P(i, i) = 1e-4;                               // :183-186
     for (int i = 0; i < 3; ++i) {
@@ -351,7 +355,7 @@ struct Filter {
       for (int j = 0; j < d; ++j) { const double v_ = P(sel[i], j); Pn(d + i, j) = v_; Pn(j, d + i) = v_; }
       for (int j = 0; j < 6; ++j) Pn(d + i, d + j) = P(sel[i], sel[j]);
     }
-    const int nf = (int)fstates.size() + 6 * (int)nui_ids.size();
+    const int nf = idp * (int)fstates.size() + 6 * (int)nui_ids.size();
     if (nf > 0) {                                       // the new pose goes in FRONT of the SLAM-feature (and nuisance) block (:768-793)
       std::vector<int> order; const int pe = d - nf;
       for (int i = 0; i < pe; ++i) order.push_back(i);
@@ -433,10 +437,16 @@ struct Filter {
     const int base = LEG + 6 * (int)aug.size();       // inverse depth of the in-state features, world position from the anchor (:1536-1575)
     for (int k = 0; k < (int)fstates.size(); ++k) {
       Feature& ft = map.at(fstates[k]);
-      const int at = (num_old < 0 || k < num_old) ? base + k : new_at + (k - num_old);
-      ft.inv_depth += dx[at];
+      const int at = (num_old < 0 || k < num_old) ? base + idp * k : new_at + idp * (k - num_old);
       const Aug& an = anchor_state(ft);
-      const V3 p_c = {ft.obs_anchor[0] / ft.inv_depth, ft.obs_anchor[1] / ft.inv_depth, 1.0 / ft.inv_depth};
+      V3 p_c;
+      if (idp == 3) {
+        for (int q = 0; q < 3; ++q) ft.inv_param[q] += dx[at + q];
+        p_c = {ft.inv_param[0] / ft.inv_param[2], ft.inv_param[1] / ft.inv_param[2], 1.0 / ft.inv_param[2]};
+      } else {
+        ft.inv_depth += dx[at];
+        p_c = {ft.obs_anchor[0] / ft.inv_depth, ft.obs_anchor[1] / ft.inv_depth, 1.0 / ft.inv_depth};
+      }
       st(ft.pos, mv(quat_to_rot(an.q_cam), p_c) + ld(an.p_cam));
     }
   }
@@ -539,7 +549,7 @@ struct Filter {
     if (!solve_update(H, r, Rdiag, dx, Y)) return;
     inject(dx);
     if (schmidt() && !nui_ids.empty()) {
-      const int n0 = LEG + 6 * (int)aug.size() + (int)fstates.size();
+      const int n0 = LEG + 6 * (int)aug.size() + idp * (int)fstates.size();
       const Mat B = nuisance_block(n0);
       apply_cov(Y);
       restore_nuisance_block(n0, B);
@@ -679,6 +689,7 @@ struct Filter {
       ft.anchor = cam_ids.back();
       ft.inv_depth = 1.0 / fin.z;                                    // feature.hpp:541-546
       ft.obs_anchor[0] = fin.x * ft.inv_depth; ft.obs_anchor[1] = fin.y * ft.inv_depth; ft.obs_anchor[2] = 1.0;
+      ft.inv_param[0] = fin.x / fin.z; ft.inv_param[1] = fin.y / fin.z; ft.inv_param[2] = 1.0 / fin.z;      // feature.hpp:711-713
     }
     return valid;
   }
@@ -755,13 +766,14 @@ struct Filter {
 
   // ================================================================ hybrid filter: 1-D inverse-depth EKF-SLAM features
   // ---------------------------------------------------------------- measurementJacobian_ekf_1didp :1117-1244
-  struct Jac1 { double hf[2], ha[2][6], hx[2][6], he[2][6], r[2]; };
-  void meas_jacobian_1didp(long long sid, const Feature& ft, Jac1& J) const {
+  struct Jac1 { double hf[2][3], ha[2][6], hx[2][6], he[2][6], r[2]; };
+  void meas_jacobian_idp(long long sid, const Feature& ft, Jac1& J) const {
     const Aug& k = aug.at(sid); const Aug& a = anchor_state(ft);
     const bool nui = anchor_is_nui(ft);                  // a nuisance anchor is used as frozen: own camera pose, no first estimates (:1168-1183)
     const bool fej_a = if_FEJ && !nui;
     const M3 R_b2c = k.R_ic; const V3 t_c_b = ld(k.t_ci);
-    const V3 f_an = {ft.obs_anchor[0], ft.obs_anchor[1], ft.obs_anchor[2]};
+    const V3 f_an = idp == 3 ? V3{ft.inv_param[0], ft.inv_param[1], 1.0} : V3{ft.obs_anchor[0], ft.obs_anchor[1], ft.obs_anchor[2]};
+    const double inv_d = idp == 3 ? ft.inv_param[2] : ft.inv_depth;
     const M3 R_bk2w = quat_to_rot(k.q), R_w2bk = tr(R_bk2w);
     const M3 R_w2ck = mul(R_b2c, R_w2bk); const V3 t_ck_w = ld(k.p) + mv(R_bk2w, t_c_b);
     const M3 R_ba2w = quat_to_rot(a.q), R_w2ba = tr(R_ba2w);
@@ -769,10 +781,12 @@ struct Filter {
     const V3 p_w = ld(ft.pos), p_fej = ld(ft.pos_fej);
     V3 p_ca;
     if (fej_a) p_ca = mv(R_b2c, mv(R_w2ba, p_fej - ld(a.p_fej)) - t_c_b);
-    else p_ca = {f_an.x / ft.inv_depth, f_an.y / ft.inv_depth, 1.0 / ft.inv_depth};
+    else p_ca = {f_an.x / inv_d, f_an.y / inv_d, 1.0 / inv_d};
     const Obs& o = ft.obs.at(sid);
     const V3 p_ck = mv(R_w2ck, p_w - t_ck_w);
     J.r[0] = o.z[0] - p_ck.x / p_ck.z; J.r[1] = o.z[1] - p_ck.y / p_ck.z;
+    for (int a_ = 0; a_ < 2; ++a_) { for (int q = 0; q < 3; ++q) J.hf[a_][q] = 0.0; for (int q = 0; q < 6; ++q) { J.ha[a_][q] = 0.0; J.hx[a_][q] = 0.0; J.he[a_][q] = 0.0; } }
+    if (idp == 3 && sid == ft.anchor) { J.hf[0][0] = 1.0; J.hf[1][1] = 1.0; return; }        // the anchor's own observation (:1065-1073)
     const double Jk[2][3] = {{1 / p_ck.z, 0, -p_ck.x / (p_ck.z * p_ck.z)}, {0, 1 / p_ck.z, -p_ck.y / (p_ck.z * p_ck.z)}};
     const V3 J_d = mv(R_w2ck, mtv(R_w2ca, f_an));
     const V3 p_baf_w = fej_a ? (p_fej - ld(a.p_fej)) : (p_w - ld(a.p));
@@ -784,10 +798,21 @@ struct Filter {
     const M3 Mx = mul(Rka, skew(mtv(R_b2c, p_ca)));
     const M3 Je_l = mul(R_b2c, sub(Sk, Mx));
     const M3 Je_r = mul(R_b2c, sub(Rka, eye3()));
-    const double J_rho = -1.0 / (ft.inv_depth * ft.inv_depth);
+    const double J_rho = -1.0 / (inv_d * inv_d);
     const double jd[3] = {J_d.x, J_d.y, J_d.z};
+    if (idp == 3) {            // H_f = J_k (R_w2ck R_w2ca^T) J_f, J_f = d(p_ca)/d(invParam) = [I | -f0/f2, -f1/f2, -1/f2] / f2   (:1075-1114)
+      const M3 Jp = mul(R_w2ck, tr(R_w2ca));
+      const double f0 = ft.inv_param[0], f1 = ft.inv_param[1], f2 = ft.inv_param[2];
+      double Jf[3][3] = {{1.0, 0.0, -f0 / f2}, {0.0, 1.0, -f1 / f2}, {0.0, 0.0, -1.0 / f2}};
+      for (int i = 0; i < 3; ++i) for (int q = 0; q < 3; ++q) Jf[i][q] = Jf[i][q] / f2;
+      for (int a_ = 0; a_ < 2; ++a_) {
+        double kp[3];
+        for (int q = 0; q < 3; ++q) kp[q] = Jk[a_][0] * Jp.m[q] + Jk[a_][1] * Jp.m[3 + q] + Jk[a_][2] * Jp.m[6 + q];
+        for (int q = 0; q < 3; ++q) J.hf[a_][q] = kp[0] * Jf[0][q] + kp[1] * Jf[1][q] + kp[2] * Jf[2][q];
+      }
+    }
     for (int a_ = 0; a_ < 2; ++a_) {
-      J.hf[a_] = (Jk[a_][0] * jd[0] + Jk[a_][1] * jd[1] + Jk[a_][2] * jd[2]) * J_rho;
+      if (idp == 1) J.hf[a_][0] = (Jk[a_][0] * jd[0] + Jk[a_][1] * jd[1] + Jk[a_][2] * jd[2]) * J_rho;
       for (int cc = 0; cc < 3; ++cc) {
         double xa = 0, xr = 0, kl = 0, kr = 0, el = 0, er = 0;
         for (int q = 0; q < 3; ++q) {
@@ -805,19 +830,19 @@ struct Filter {
   // ---------------------------------------------------------------- featureJacobian_ekf_new :1247-1338 (columns: state + one per feature in fstates)
   void feature_jacobian_ekf_new(const Feature& ft, Mat& H, std::vector<double>& r) const {
     std::vector<long long> valid;
-    for (auto& o : ft.obs) if (o.first != ft.anchor) valid.push_back(o.first);      // the anchor's own observation is not used (:1260-1262)
-    const int ncol = LEG + 6 * (int)aug.size() + (int)fstates.size() + 6 * (int)nui_ids.size();
+    for (auto& o : ft.obs) if (idp == 3 || o.first != ft.anchor) valid.push_back(o.first);      // 1-D: the anchor's own observation is not used (:1260-1262)
+    const int ncol = LEG + 6 * (int)aug.size() + idp * (int)fstates.size() + 6 * (int)nui_ids.size();
     H = Mat(2 * (int)valid.size(), ncol); r.assign(2 * valid.size(), 0.0);
     // the features this call adds are not in the covariance yet: their columns follow it, i.e. the nuisance block (:1291-1300)
-    const int num_old = (int)fstates.size() - (ncol - P.r);
-    const int a_idx = LEG + 6 * window_index(ft.anchor), f_idx = P.r + (feature_index(ft.id) - num_old);
+    const int num_old = (int)fstates.size() - (ncol - P.r) / idp;
+    const int a_idx = LEG + 6 * window_index(ft.anchor), f_idx = P.r + idp * (feature_index(ft.id) - num_old);
     int k = 0;
     for (long long sid : valid) {
-      Jac1 J; meas_jacobian_1didp(sid, ft, J);
+      Jac1 J; meas_jacobian_idp(sid, ft, J);
       const int cidx = LEG + 6 * window_index(sid);
       for (int a_ = 0; a_ < 2; ++a_) {
         double* row = H.row(k + a_);
-        row[f_idx] = J.hf[a_];
+        for (int q = 0; q < idp; ++q) row[f_idx + q] = J.hf[a_][q];
         for (int q = 0; q < 6; ++q) row[a_idx + q] = J.ha[a_][q];
         for (int q = 0; q < 6; ++q) row[cidx + q] = J.hx[a_][q];
         for (int q = 0; q < 6; ++q) row[15 + q] = J.he[a_][q];
@@ -831,16 +856,16 @@ struct Filter {
   void feature_jacobian_ekf(const Feature& ft, Mat& H, std::vector<double>& r) const {
     const long long sid = s.id;
     H = Mat(2, P.r); r.assign(2, 0.0);
-    Jac1 J; meas_jacobian_1didp(sid, ft, J);
-    const int f_idx = LEG + 6 * (int)aug.size() + feature_index(ft.id), cidx = LEG + 6 * window_index(sid);
+    Jac1 J; meas_jacobian_idp(sid, ft, J);
+    const int f_idx = LEG + 6 * (int)aug.size() + idp * feature_index(ft.id), cidx = LEG + 6 * window_index(sid);
     int a_idx = LEG + 6 * window_index(ft.anchor);
     if (anchor_is_nui(ft)) {                             // :1351-1366: the anchor's columns are in the nuisance block
-      const int num_new = LEG + 6 * (int)aug.size() + (int)fstates.size() + 6 * (int)nui_ids.size() - P.r;
-      a_idx = LEG + 6 * (int)aug.size() + ((int)fstates.size() - num_new) + 6 * (int)(std::find(nui_ids.begin(), nui_ids.end(), ft.anchor) - nui_ids.begin());
+      const int num_new = (LEG + 6 * (int)aug.size() + idp * (int)fstates.size() + 6 * (int)nui_ids.size() - P.r) / idp;
+      a_idx = LEG + 6 * (int)aug.size() + idp * ((int)fstates.size() - num_new) + 6 * (int)(std::find(nui_ids.begin(), nui_ids.end(), ft.anchor) - nui_ids.begin());
     }
     for (int a_ = 0; a_ < 2; ++a_) {
       double* row = H.row(a_);
-      row[f_idx] = J.hf[a_];
+      for (int q = 0; q < idp; ++q) row[f_idx + q] = J.hf[a_][q];
       for (int q = 0; q < 6; ++q) row[a_idx + q] = J.ha[a_][q];
       for (int q = 0; q < 6; ++q) row[cidx + q] = J.hx[a_][q];
       for (int q = 0; q < 6; ++q) row[15 + q] = J.he[a_][q];
@@ -851,8 +876,8 @@ struct Filter {
   // ---------------------------------------------------------------- rmLostFeaturesCov :3296-3348
   void rm_lost_features_cov(const std::vector<long long>& lost) {
     for (long long fid : lost) {
-      const int seq = feature_index(fid), i0 = LEG + 6 * (int)aug.size() + seq;
-      std::vector<int> keep; for (int i = 0; i < P.r; ++i) if (i != i0) keep.push_back(i);
+      const int seq = feature_index(fid), i0 = LEG + 6 * (int)aug.size() + idp * seq;
+      std::vector<int> keep; for (int i = 0; i < P.r; ++i) if (i < i0 || i >= i0 + idp) keep.push_back(i);
       P = permuted(P, keep);
       fstates.erase(fstates.begin() + seq);
       if (schmidt()) {                                                // :3329-3339
@@ -869,7 +894,7 @@ struct Filter {
     std::vector<long long> rm; for (long long id : nui_ids) if (nui_features[id].empty()) rm.push_back(id);
     for (long long id : rm) {
       const int seq = (int)(std::find(nui_ids.begin(), nui_ids.end(), id) - nui_ids.begin());
-      const int n0 = LEG + 6 * (int)aug.size() + (int)fstates.size() + 6 * seq;
+      const int n0 = LEG + 6 * (int)aug.size() + idp * (int)fstates.size() + 6 * seq;
       std::vector<int> keep; for (int i = 0; i < P.r; ++i) if (i < n0 || i >= n0 + 6) keep.push_back(i);
       P = permuted(P, keep);
       nui_ids.erase(nui_ids.begin() + seq); nui_states.erase(id); nui_features.erase(id);
@@ -949,6 +974,54 @@ struct Filter {
     for (int j = 0; j < d; ++j) { P(fi, j) = Pfl[j]; P(j, fi) = Pfl[j]; }
     P(fi, fi) = Pff;
   }
+  // ---------------------------------------------------------------- updateFeatureCov_3didp :2965-3122, literally: the reference looks the "new" pose and
+  // its column block up with old_state_id (:3000, :3066), so H_x_new overwrites H_x_old in the old block
+  void update_feature_cov_3didp(const Feature& ft, long long old_id) {
+    const int N = (int)aug.size();
+    const V3 p_w = ld(ft.pos), p_fej = ld(ft.pos_fej);
+    const M3 R_b2c = s.R_ic; const V3 t_c_b = ld(s.t_ci);
+    const Aug& o = aug.at(old_id); const Aug& n = o;                       // sic
+    const M3 R_b2w_old = quat_to_rot(o.q), R_c2w_old = quat_to_rot(o.q_cam);
+    V3 p_old;
+    if (if_FEJ) p_old = mv(R_b2c, mtv(R_b2w_old, p_fej - ld(o.p_fej)) - t_c_b);
+    else p_old = mtv(R_c2w_old, p_w - ld(o.p_cam));
+    const M3 R_b2w_new = quat_to_rot(n.q), R_w2b_new = tr(R_b2w_new);
+    const M3 R_w2c_new = tr(quat_to_rot(n.q_cam));
+    const double* iv = ft.inv_param;
+    V3 pbo, pbn;
+    if (if_FEJ) { pbo = p_fej - ld(o.p_fej); pbn = p_fej - ld(n.p_fej); }
+    else { pbo = p_w - ld(o.p); pbn = p_w - ld(n.p); }
+    double Jfp[3][3] = {{1.0, 0.0, -iv[0]}, {0.0, 1.0, -iv[1]}, {0.0, 0.0, -iv[2]}};
+    for (int i = 0; i < 3; ++i) for (int q = 0; q < 3; ++q) Jfp[i][q] = iv[2] * Jfp[i][q];
+    const M3 Jp = mul(R_w2c_new, R_c2w_old);
+    const M3 Jxo_l = scl(mul(R_w2c_new, skew(pbo)), -1.0);               // J_x_old = [-R skew(p_bf_old) | R]
+    const M3 Jxn_l = mul(R_w2c_new, skew(pbn));                         // J_x_new = [R skew(p_bf_new) | -R]
+    const M3 Sk = skew(mv(R_w2b_new, pbn) - t_c_b);
+    const M3 Rno = mul(R_w2b_new, R_b2w_old);
+    const M3 Mx = mul(Rno, skew(mtv(R_b2c, p_old)));
+    const M3 Jet = mul(R_b2c, sub(Sk, Mx));
+    const M3 Jep = mul(R_b2c, sub(Rno, eye3()));
+    double Jpf[3][3] = {{1.0, 0.0, -p_old.x}, {0.0, 1.0, -p_old.y}, {0.0, 0.0, -p_old.z}};
+    for (int i = 0; i < 3; ++i) for (int q = 0; q < 3; ++q) Jpf[i][q] = p_old.z * Jpf[i][q];
+    const int d = P.r;
+    Mat J(3, d);
+    const int oc = window_index(old_id), fi = LEG + 6 * N + 3 * feature_index(ft.id);
+    auto m3rows = [](const double A[3][3], const M3& B, int a_, int q) { return A[a_][0] * B.m[q] + A[a_][1] * B.m[3 + q] + A[a_][2] * B.m[6 + q]; };
+    for (int a_ = 0; a_ < 3; ++a_) {
+      double fp[3]; for (int q = 0; q < 3; ++q) fp[q] = m3rows(Jfp, Jp, a_, q);
+      for (int q = 0; q < 3; ++q) J(a_, fi + q) = fp[0] * Jpf[0][q] + fp[1] * Jpf[1][q] + fp[2] * Jpf[2][q];
+      (void)Jxo_l;                                                      // H_x_old is written first and then overwritten by H_x_new (same block)
+      for (int q = 0; q < 3; ++q) { J(a_, LEG + 6 * oc + q) = m3rows(Jfp, Jxn_l, a_, q); J(a_, LEG + 6 * oc + 3 + q) = -m3rows(Jfp, R_w2c_new, a_, q); }
+      for (int q = 0; q < 3; ++q) { J(a_, 15 + q) = m3rows(Jfp, Jet, a_, q); J(a_, 18 + q) = m3rows(Jfp, Jep, a_, q); }
+    }
+    Mat Pfl(3, d);
+    for (int a_ = 0; a_ < 3; ++a_) for (int i = 0; i < d; ++i) { const double jv = J(a_, i); if (jv == 0.0) continue; const double* pr = P.row(i); double* o_ = Pfl.row(a_); for (int j = 0; j < d; ++j) o_[j] += jv * pr[j]; }
+    double Pff[3][3];
+    for (int a_ = 0; a_ < 3; ++a_) for (int b = 0; b < 3; ++b) { double acc = 0; for (int j = 0; j < d; ++j) acc += Pfl(a_, j) * J(b, j); Pff[a_][b] = acc; }
+    for (int a_ = 0; a_ < 3; ++a_) for (int j = 0; j < d; ++j) if (j < fi || j >= fi + 3) { P(fi + a_, j) = Pfl(a_, j); P(j, fi + a_) = Pfl(a_, j); }
+    for (int a_ = 0; a_ < 3; ++a_) for (int b = 0; b < 3; ++b) P(fi + a_, fi + b) = Pff[a_][b];
+    for (int a_ = 0; a_ < 3; ++a_) for (int b = a_ + 1; b < 3; ++b) { const double m_ = 0.5 * (P(fi + a_, fi + b) + P(fi + b, fi + a_)); P(fi + a_, fi + b) = m_; P(fi + b, fi + a_) = m_; }
+  }
   // ---------------------------------------------------------------- measurementUpdate_hybrid :1605-1862
   // H_new: rows [0, nn) = the rows that define the nn new states (H_1 | H_2 upper triangular | r_1), rows [nn, ..) = their null-space rows
   void update_hybrid(const Mat& H_new, const std::vector<double>& r_new, int nn, const Mat& H_ekf, const std::vector<double>& r_ekf,
@@ -974,11 +1047,11 @@ struct Filter {
       for (int j = 0; j < d; ++j) { HH(i, j) = H_new(i, j) / h2; acc += HH(i, j) * dx_leg[j]; }
       dx.push_back(-acc + r_new[i] / h2);
     }
-    inject(dx, d, (int)fstates.size() - nn);
+    inject(dx, d, (int)fstates.size() - nn / idp);
     const int nui_cols = schmidt() ? 6 * (int)nui_ids.size() : 0;
     if (have) {
       if (nui_cols) {
-        const int n0 = LEG + 6 * (int)aug.size() + ((int)fstates.size() - nn);
+        const int n0 = LEG + 6 * (int)aug.size() + idp * ((int)fstates.size() - nn / idp);
         const Mat B = nuisance_block(n0);
         apply_cov(Y);
         restore_nuisance_block(n0, B);
@@ -1020,7 +1093,7 @@ struct Filter {
     if (dd[dd.size() - 9] < c.zupt_max_feature_dis) {
       ++zupt_events;
       if (!fstates.empty()) {                                        // :2770-2782: every SLAM feature leaves the state
-        const int nd = P.r - (int)fstates.size();
+        const int nd = P.r - idp * (int)fstates.size();
         std::vector<int> keep; for (int i = 0; i < nd; ++i) keep.push_back(i);
         P = permuted(P, keep);
         for (long long fid : fstates) { Feature& ft = map.at(fid); ft.init = false; ft.ekf = false; ft.in_state = false; }
@@ -1101,7 +1174,7 @@ struct Filter {
       }
       fstates.resize(fstates.size() - n_all);
       for (long long fid : kept) fstates.push_back(fid);
-      const int nn = (int)kept.size();
+      const int nn = idp * (int)kept.size();
       Mat H_new; std::vector<double> r_new;
       if (nn) {
         // the columns of the features that failed the gate disappear; then Householder reflections on the nn own columns:
@@ -1109,11 +1182,11 @@ struct Filter {
         int rows = 0; for (auto& h : Hn) rows += h.r;
         H_new = Mat(rows, d + nn); r_new.assign(rows, 0.0);
         int r0 = 0;
-        for (int f = 0; f < nn; ++f) {
-          const int src_col = d + (int)(std::find(ekf_new.begin(), ekf_new.end(), kept[f]) - ekf_new.begin());
+        for (int f = 0; f < (int)kept.size(); ++f) {
+          const int src_col = d + idp * (int)(std::find(ekf_new.begin(), ekf_new.end(), kept[f]) - ekf_new.begin());
           for (int i = 0; i < Hn[f].r; ++i) {
             memcpy(H_new.row(r0 + i), Hn[f].row(i), sizeof(double) * d);
-            H_new(r0 + i, d + f) = Hn[f](i, src_col);
+            for (int q = 0; q < idp; ++q) H_new(r0 + i, d + idp * f + q) = Hn[f](i, src_col + q);
             r_new[r0 + i] = rn[f][i];
           }
           r0 += Hn[f].r;
@@ -1207,22 +1280,30 @@ struct Filter {
           continue;
         }
         if (anchor_goes) {
-          const long long new_id = new_anchor_id(ft, inv);
+          const long long new_id = idp == 3 ? s.id : new_anchor_id(ft, inv);          // 3-D: always the newest state (:2361-2378)
           const Aug& a = aug.at(new_id);
           const V3 pn = mtv(quat_to_rot(a.q_cam), ld(ft.pos) - ld(a.p_cam));
-          ft.inv_depth = 1.0 / pn.z;
-          ft.obs_anchor[0] = pn.x / pn.z; ft.obs_anchor[1] = pn.y / pn.z;
-          update_feature_cov_1didp(ft, ft.anchor, new_id);
+          if (idp == 3) {
+            ft.inv_param[0] = pn.x / pn.z; ft.inv_param[1] = pn.y / pn.z; ft.inv_param[2] = 1.0 / pn.z;
+            update_feature_cov_3didp(ft, ft.anchor);
+          } else {
+            ft.inv_depth = 1.0 / pn.z;
+            ft.obs_anchor[0] = pn.x / pn.z; ft.obs_anchor[1] = pn.y / pn.z;
+            update_feature_cov_1didp(ft, ft.anchor, new_id);
+          }
           ft.anchor = new_id;
         }
         continue;
       }
       if (hybrid() && ft.init && anchor_goes) {                               // :2407-2460: potential features are only re-anchored
-        const long long new_id = new_anchor_id(ft, inv);
+        const long long new_id = idp == 3 ? s.id : new_anchor_id(ft, inv);
         const Aug& a = aug.at(new_id);
         const V3 pn = mtv(quat_to_rot(a.q_cam), ld(ft.pos) - ld(a.p_cam));
-        ft.inv_depth = 1.0 / pn.z;
-        ft.obs_anchor[0] = ft.obs.at(new_id).z[0]; ft.obs_anchor[1] = ft.obs.at(new_id).z[1];
+        if (idp == 3) { ft.inv_param[0] = pn.x / pn.z; ft.inv_param[1] = pn.y / pn.z; ft.inv_param[2] = 1.0 / pn.z; }
+        else {
+          ft.inv_depth = 1.0 / pn.z;
+          ft.obs_anchor[0] = ft.obs.at(new_id).z[0]; ft.obs_anchor[1] = ft.obs.at(new_id).z[1];
+        }
         ft.anchor = new_id;
       }
       if (!if_ZUPT && !ft.ekf && inv.size() > 1) {

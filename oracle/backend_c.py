@@ -1,8 +1,7 @@
 """ctypes wrapper of oracle/backend_c.cpp - the compiled CPU oracle of LarVio::processFeatures (TEST INFRASTRUCTURE, see
 oracle/__init__.py).  Same driving interface as oracle.backend.LarVioOracle for what bench.py's CPU legs and the tests use
-(``set_initial_state``, ``process_features(msg, imu_list)``, ``imu_state``, ``P``, ``aug``-count, ``td``); restricted to the
-configuration BASELINE.json's metric is quoted on: pure MSCKF, no IMU-intrinsic calibration.  ``supported(cfg_raw)`` says
-whether a config is inside that scope; outside it callers keep the numpy oracle."""
+(``set_initial_state``, ``process_features(msg, imu_list)``, ``imu_state``, ``P``, ``aug``-count, ``td``, ``feature_states``), for every
+configuration of the filter; pinned to the golden vectors of the reference's own larvio.cpp (tests/golden/ref_*.npz)."""
 from __future__ import annotations
 
 import ctypes
@@ -50,10 +49,9 @@ def load():
 
 
 def supported(r: dict) -> bool:
-    """pure MSCKF, or the hybrid filter with 1-D inverse-depth SLAM features, with or without IMU-intrinsic calibration and Schmidt
-    nuisance states; no 3-D features"""
-    hybrid = max(int(r["max_features_in_one_grid"]), 0) * int(r["aug_grid_rows"]) * int(r["aug_grid_cols"]) != 0
-    return not hybrid or int(r.get("feature_idp_dim", 3)) == 1
+    """Every configuration of the reference's filter is covered (pure MSCKF; hybrid with 1-D or 3-D inverse-depth SLAM features; IMU-intrinsic
+    calibration; Schmidt nuisance states); kept as the switch bench.py asks."""
+    return True
 
 
 def _cfg_vector(r: dict) -> np.ndarray:
@@ -79,7 +77,7 @@ def _cfg_vector(r: dict) -> np.ndarray:
     gw = (x_max - x_min) / cols if rows * cols != 0 else (x_max - x_min)
     gh = (y_max - y_min) / rows if rows * cols != 0 else (y_max - y_min)
     v += [float(max(int(r["max_features_in_one_grid"]), 0)), float(rows), float(cols), x_min, y_min, gw, gh]
-    v += [float(int(r["calib_imu_instrinsic"])), float(int(r.get("use_schmidt", 0)))]
+    v += [float(int(r["calib_imu_instrinsic"])), float(int(r.get("use_schmidt", 0))), float(int(r.get("feature_idp_dim", 3)))]
     return np.array(v, np.float64)
 
 

@@ -780,11 +780,9 @@ def test_bench_helpers_core_count_and_ncu_traffic():
     traffic, src = b.load_ncu_traffic()
     assert src and src.startswith("profiles/") and src.endswith("_ncu_traffic.json")
     assert traffic["lk_kernel"] > 0 and "be_propagate_kernel" in traffic and all("<" not in k and not k.startswith("void ") for k in traffic)
-    assert "compiled filter" in b.cpu_arm_description(dict(max_features_in_one_grid=0, aug_grid_rows=5, aug_grid_cols=6, calib_imu_instrinsic=0))
-    assert "compiled filter" in b.cpu_arm_description(dict(max_features_in_one_grid=1, aug_grid_rows=5, aug_grid_cols=6, calib_imu_instrinsic=0, feature_idp_dim=1, use_schmidt=0))
-    assert "numpy f64 filter" in b.cpu_arm_description(dict(max_features_in_one_grid=1, aug_grid_rows=5, aug_grid_cols=6, calib_imu_instrinsic=0, feature_idp_dim=3))
-    assert "compiled filter" in b.cpu_arm_description(dict(max_features_in_one_grid=1, aug_grid_rows=5, aug_grid_cols=6, calib_imu_instrinsic=1, feature_idp_dim=1))
-    assert "compiled filter" in b.cpu_arm_description(dict(max_features_in_one_grid=1, aug_grid_rows=5, aug_grid_cols=6, calib_imu_instrinsic=0, feature_idp_dim=1, use_schmidt=1))
+    for kw in (dict(max_features_in_one_grid=0), dict(max_features_in_one_grid=1, feature_idp_dim=1), dict(max_features_in_one_grid=1, feature_idp_dim=3),
+               dict(max_features_in_one_grid=1, feature_idp_dim=1, calib_imu_instrinsic=1), dict(max_features_in_one_grid=1, feature_idp_dim=3, use_schmidt=1)):
+        assert "compiled filter" in b.cpu_arm_description(dict(dict(aug_grid_rows=5, aug_grid_cols=6, calib_imu_instrinsic=0), **kw))     # every configuration
 
 
 def test_reference_arm_prints_the_contract_line(tmp_path):
@@ -834,12 +832,12 @@ def test_backend_oracle_matches_the_compiled_reference(name):
     assert max(w["Pz"], w["Pdiag"], w["P"]) < 1e-9, w
 
 
-@pytest.mark.parametrize("name", ["msckf_sw30", "msckf_oldest", "zupt", "self_start", "self_start_jump", "no_fej_no_calib", "hybrid_1d_oldest", "hybrid_zupt",
-                                  "config_d", "schmidt_1d_oldest"])
+@pytest.mark.parametrize("name", REF_CASES_ORACLE)
 def test_compiled_oracle_matches_the_compiled_reference(name):
-    """oracle/backend_c.cpp (the CPU arm of bench.py) against the same reference-made fixtures, in its scope: pure MSCKF and the
-    hybrid filter with 1-D inverse-depth SLAM features (promotion, anchor hand-over, the standstill that drops them), IMU-intrinsic
-    calibration (configs[3]), Schmidt nuisance states, forced and self start.  Identical bookkeeping incl. the SLAM feature ids in the state; state and covariance within 1e-9."""
+    """oracle/backend_c.cpp (the CPU arm of bench.py) against the same reference-made fixtures - every one of them: pure MSCKF, the
+    hybrid filter with 1-D and 3-D inverse-depth SLAM features (promotion, anchor hand-over, the standstill that drops them),
+    IMU-intrinsic calibration (configs[3]), Schmidt nuisance states, forced and self start.  Identical bookkeeping incl. the SLAM
+    feature ids in the state; state and covariance within 1e-9."""
     import ref_runner as rr
     c, init, static_init, calls, ref = _fixture(name)
     w = rr.compare_with_fixture(rr.run_oracle_on_calls(c.raw, calls, init, static_init, compiled=True), ref)
