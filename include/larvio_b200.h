@@ -124,8 +124,10 @@ int lvb_step(LvbHandle* h, const uint8_t* images, int images_on_device, const do
              int* n_imu, int imu_stride, uint8_t* published);
 int lvb_synchronize(LvbHandle* h);
 
-/* State left by the (out-of-scope) initialiser: body->world Hamilton quaternion [x y z w],
- * position, velocity, biases at time t; marks gravity as set (larvio.cpp:378-386). */
+/* State left by the initialiser: body->world Hamilton quaternion [x y z w], position, velocity, biases at time t; marks
+ * gravity as set (larvio.cpp:378-386) and the bFirstFeatures gate as passed (the reference only reaches its initialiser behind that
+ * gate, :365-376), so the lvb_process_features call that follows in the same frame runs the filter on the IMU samples the
+ * initialiser left, as larvio.cpp:391 does. */
 int lvb_set_initial_state(LvbHandle* h, int seq, double t, const double* q_xyzw, const double* p,
                           const double* v, const double* bg, const double* ba);
 
